@@ -1,0 +1,288 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of oracle/_build/libtss_oracle.so (the CPU restatement of the reference's
+feasibility-and-bound path, see oracle/oracle.hpp).  Importable only from tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs; the product package
+never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libtss_oracle.so")
+
+PLATFORMS_1X1 = [(1, 1)]
+PLATFORMS_DEFAULT = [(1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (3, 3), (5, 5)]  # src/platform.rs:23-32
+FAMILIES = ["dag_impl", "dag_sibling", "t3_platform", "layer", "unit_t0", "overlap_anchor", "overlap_cross",
+            "oob", "limit_link", "card", "pb"]
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp"))]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        L = _lib
+        L.tsso_encode.restype = C.c_void_p
+        L.tsso_encoding_cnf.restype = C.c_void_p
+        L.tsso_with_limits.restype = C.c_void_p
+        L.tsso_cnf_num_lits.restype = C.c_long
+        L.tsso_total_weight.restype = C.c_long
+        L.tsso_assignment_total_weight.restype = C.c_long
+        L.tsso_validate_sites_batch.restype = C.c_double
+    return _lib
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a, t=C.c_int):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _grid(grid):
+    g = np.ascontiguousarray(grid, dtype=np.uint8)
+    assert g.ndim == 2
+    return g
+
+
+# --------------------------------------------------------------------------- math / platform
+def dims_partial_cmp(a, b):
+    r = lib().tsso_dims_partial_cmp(a[0], a[1], b[0], b[1])
+    return None if r == 2 else r
+
+
+def iter_within(w, h):
+    out = np.zeros((w * h + 1, 2), np.int32)
+    n = lib().tsso_iter_within(w, h, _p(out), len(out))
+    return [tuple(map(int, p)) for p in out[:n]]
+
+
+def iter_manhattan(c, dist):
+    out = np.zeros((4 * (dist + 1) ** 2, 2), np.int32)
+    n = lib().tsso_iter_manhattan(c[0], c[1], dist, _p(out), len(out))
+    return [tuple(map(int, p)) for p in out[:n]]
+
+
+def neighbors(p):
+    out = np.zeros((4, 2), np.int32)
+    lib().tsso_neighbors(p[0], p[1], _p(out))
+    return [tuple(map(int, q)) for q in out]
+
+
+def platform_overlaps(a, b):
+    """a, b: (x, y, def_w, def_h, rotated)"""
+    return bool(lib().tsso_platform_overlaps(_p(_i32(a)), _p(_i32(b))))
+
+
+# --------------------------------------------------------------------------- world
+class WorldParseError(ValueError):
+    pass
+
+
+def parse_world(text: str):
+    """-> (grid uint8[h, w], ragged)"""
+    out = np.zeros(1 << 22, np.uint8)
+    w, h, rg = C.c_int(), C.c_int(), C.c_int()
+    err = C.create_string_buffer(512)
+    r = lib().tsso_parse_world(text.encode(), _p(out, C.c_uint8), len(out), C.byref(w), C.byref(h), C.byref(rg), err, 512)
+    if r != 0:
+        raise WorldParseError(err.value.decode() or "grid too large")
+    return out[: w.value * h.value].reshape(h.value, w.value).copy(), bool(rg.value)
+
+
+def world_to_toml(grid) -> str:
+    g = _grid(grid)
+    buf = C.create_string_buffer(g.size * 2 + 64 * g.shape[0] + 64)
+    n = lib().tsso_world_to_toml(_p(g, C.c_uint8), g.shape[1], g.shape[0], buf, len(buf))
+    assert n >= 0
+    return buf.value.decode()
+
+
+def dag_edges(defs):
+    d = _i32(defs)
+    out = np.zeros((256, 4), np.int32)
+    n = lib().tsso_dag_platform_edges(_p(d), len(d), _p(out), len(out))
+    plat = [((int(a), int(b)), (int(c), int(e))) for a, b, c, e in out[:n]]
+    n = lib().tsso_dag_point_edges(_p(d), len(d), _p(out), len(out))
+    pts = [((int(a), int(b)), (int(c), int(e))) for a, b, c, e in out[:n]]
+    return plat, pts
+
+
+# --------------------------------------------------------------------------- CNF
+class Cnf:
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+        L = lib()
+        self.n_vars = L.tsso_cnf_num_vars(self._h)
+        self.n_clauses = L.tsso_cnf_num_clauses(self._h)
+        self.n_lits = L.tsso_cnf_num_lits(self._h)
+        self.lits = np.zeros(max(self.n_lits, 1), np.int32)
+        self.offsets = np.zeros(self.n_clauses + 1, np.uint32)
+        self.family = np.zeros(max(self.n_clauses, 1), np.uint8)
+        L.tsso_cnf_get(self._h, _p(self.lits), _p(self.offsets, C.c_uint32), _p(self.family, C.c_uint8))
+        self.lits = self.lits[: self.n_lits]
+        self.family = self.family[: self.n_clauses]
+
+    def __del__(self):
+        if lib is not None and self._h:
+            lib().tsso_cnf_free(self._h)
+            self._h = None
+
+    def clauses(self):
+        o = self.offsets
+        return [tuple(int(x) for x in self.lits[o[i]: o[i + 1]]) for i in range(self.n_clauses)]
+
+    def family_counts(self):
+        return {FAMILIES[f]: int((self.family == f).sum()) for f in np.unique(self.family)}
+
+    def solve(self, conflict_budget=-1):
+        """-> (result 10/20/0, assignment uint8[n_vars+1] or None, stats dict)"""
+        a = np.full(self.n_vars + 1, 2, np.uint8)
+        st = (C.c_ulonglong * 5)()
+        sec = C.c_double()
+        r = lib().tsso_cnf_solve(self._h, _p(a, C.c_uint8), C.c_long(conflict_budget), None, st, C.byref(sec))
+        stats = dict(conflicts=st[0], decisions=st[1], propagations=st[2], restarts=st[3], learnts=st[4], seconds=sec.value)
+        return r, (a if r == 10 else None), stats
+
+    def count_falsified(self, assignment):
+        a = np.ascontiguousarray(assignment, dtype=np.uint8)
+        assert len(a) == self.n_vars + 1
+        first = C.c_int()
+        n = lib().tsso_cnf_count_falsified(self._h, _p(a, C.c_uint8), C.byref(first))
+        return n, first.value
+
+    def dimacs(self) -> str:
+        lines = [f"p cnf {self.n_vars} {self.n_clauses}"]
+        lines += [" ".join(map(str, c)) + " 0" for c in self.clauses()]
+        return "\n".join(lines) + "\n"
+
+
+class Encoding:
+    """src/encoder.rs:428-667"""
+
+    def __init__(self, defs, grid):
+        self.grid = _grid(grid)
+        self.defs = [tuple(d) for d in defs]
+        d = _i32(self.defs)
+        self._h = C.c_void_p(lib().tsso_encode(_p(self.grid, C.c_uint8), self.grid.shape[1], self.grid.shape[0], _p(d), len(d)))
+        K = lib().tsso_encoding_num_dims(self._h)
+        dims = np.zeros((K, 2), np.int32)
+        lib().tsso_encoding_dims(self._h, _p(dims))
+        self.dims = [tuple(map(int, x)) for x in dims]
+        tiles = self.grid.size
+        self.plat_var = np.zeros((tiles, K), np.int32)
+        self.terr_var = np.zeros((tiles, 4), np.int32)
+        lib().tsso_encoding_var_maps(self._h, _p(self.plat_var), _p(self.terr_var))
+
+    def __del__(self):
+        if lib is not None and self._h:
+            lib().tsso_encoding_free(self._h)
+            self._h = None
+
+    def cnf(self) -> Cnf:
+        return Cnf(lib().tsso_encoding_cnf(self._h))
+
+    def with_limits(self, card_limits=None, weights=None, weight_limit=None) -> Cnf:
+        """card_limits / weights: {(w, h): value} keyed by canonical def dims (platform_limits.rs:6-13)"""
+        card = _i32([[k[0], k[1], v] for k, v in (card_limits or {}).items()]).reshape(-1, 3)
+        wts = _i32([[k[0], k[1], v] for k, v in (weights or {}).items()]).reshape(-1, 3)
+        h = lib().tsso_with_limits(self._h, _p(card), len(card), _p(wts), len(wts),
+                                   int(weight_limit is not None), C.c_long(weight_limit or 0))
+        return Cnf(h)
+
+    def layout_from_assignment(self, assignment):
+        a = np.ascontiguousarray(assignment, dtype=np.uint8)
+        out = np.zeros((self.grid.size + 1, 5), np.int32)
+        n = lib().tsso_layout_from_assignment(self._h, _p(a, C.c_uint8), len(a), _p(out), len(out))
+        return [tuple(map(int, p)) for p in out[:n]]
+
+    def assignment_total_weight(self, assignment, weights):
+        a = np.ascontiguousarray(assignment, dtype=np.uint8)
+        wts = _i32([[k[0], k[1], v] for k, v in weights.items()]).reshape(-1, 3)
+        return int(lib().tsso_assignment_total_weight(self._h, _p(a, C.c_uint8), len(a), _p(wts), len(wts)))
+
+
+# --------------------------------------------------------------------------- layout
+@dataclass
+class Validation:
+    unsupported: np.ndarray  # uint8[h, w]
+    overlapping: list
+    out_of_bounds: list
+
+    @property
+    def is_valid(self):
+        return not self.unsupported.any() and not self.overlapping and not self.out_of_bounds
+
+
+def validate(grid, platforms) -> Validation:
+    """src/encoder/platform_layout.rs:85-149.  platforms: [(x, y, def_w, def_h, rotated)]"""
+    g = _grid(grid)
+    p = _i32(platforms).reshape(-1, 5)
+    uns = np.zeros(g.shape, np.uint8)
+    flags = np.zeros(max(len(p), 1), np.uint8)
+    lib().tsso_validate(_p(g, C.c_uint8), g.shape[1], g.shape[0], _p(p), len(p), _p(uns, C.c_uint8), _p(flags, C.c_uint8))
+    plats = [tuple(map(int, x)) for x in p]
+    return Validation(uns, [plats[i] for i in range(len(p)) if flags[i] & 1], [plats[i] for i in range(len(p)) if flags[i] & 2])
+
+
+def trivial_optimization(grid, platforms):
+    g = _grid(grid)
+    p = _i32(platforms).reshape(-1, 5)
+    out = np.zeros((len(p) + 1, 5), np.int32)
+    n = lib().tsso_trivial_optimization(_p(g, C.c_uint8), g.shape[1], g.shape[0], _p(p), len(p), _p(out), len(out))
+    return [tuple(map(int, x)) for x in out[:n]]
+
+
+def total_weight(platforms, weights):
+    p = _i32(platforms).reshape(-1, 5)
+    wts = _i32([[k[0], k[1], v] for k, v in weights.items()]).reshape(-1, 3)
+    return int(lib().tsso_total_weight(_p(p), len(p), _p(wts), len(wts)))
+
+
+def validate_sites_batch(grid, sites, threads=1):
+    """sites: uint8[n, h, w] 1x1 support masks -> (uncovered int32[n], count int32[n], seconds)"""
+    g = _grid(grid)
+    s = np.ascontiguousarray(sites, dtype=np.uint8).reshape(-1, g.shape[0], g.shape[1])
+    unc = np.zeros(len(s), np.int32)
+    cnt = np.zeros(len(s), np.int32)
+    sec = lib().tsso_validate_sites_batch(_p(g, C.c_uint8), g.shape[1], g.shape[0], _p(s, C.c_uint8), C.c_long(len(s)),
+                                          threads, _p(unc), _p(cnt))
+    return unc, cnt, sec
+
+
+# --------------------------------------------------------------------------- solver_loop
+def solver_loop(grid, defs, initial_limit=None, conflict_budget=-1):
+    """crates/repl/src/main.rs:280-366 -> dict(steps=[...], best=[platforms], proved_optimal)"""
+    g = _grid(grid)
+    d = _i32(defs)
+    steps = np.zeros((4096, 5), np.int64)
+    secs = np.zeros(4096, np.float64)
+    plats = np.zeros((g.size + 1, 5), np.int32)
+    n_plats, proved = C.c_int(), C.c_int()
+    n = lib().tsso_solver_loop(_p(g, C.c_uint8), g.shape[1], g.shape[0], _p(d), len(d),
+                               C.c_long(-1 if initial_limit is None else initial_limit), C.c_long(conflict_budget), None,
+                               _p(steps, C.c_long), len(steps), _p(secs, C.c_double), _p(plats), len(plats),
+                               C.byref(n_plats), C.byref(proved))
+    return dict(
+        steps=[dict(bound=int(s[0]), result=int(s[1]), count=int(s[2]), valid=bool(s[3]), conflicts=int(s[4]), seconds=float(secs[i]))
+               for i, s in enumerate(steps[:n])],
+        best=[tuple(map(int, p)) for p in plats[: n_plats.value]],
+        proved_optimal=bool(proved.value),
+    )

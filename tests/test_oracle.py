@@ -1,0 +1,289 @@
+"""Pins the oracle (oracle/, the CPU restatement of the reference path) against every golden vector the
+reference holds for this path and against independently derived known answers."""
+import numpy as np
+import pytest
+
+import oracle.oracle as O
+from conftest import golden, rows_to_grid
+
+ONE = (1, 1)
+
+
+def sites(points):
+    return [(x, y, 1, 1, 0) for x, y in points]
+
+
+# ---- src/math tests ---------------------------------------------------------------------------
+def test_iter_dims():  # src/math/dimensions.rs:163-171
+    pts = O.iter_within(7, 9)
+    assert len(pts) == 7 * 9
+    assert all(0 <= x < 7 and 0 <= y < 9 for x, y in pts)
+    assert pts == [(x, y) for y in range(9) for x in range(7)]  # row-major, x fastest
+
+
+def test_iter_manhattan():  # src/math/point.rs:139-151
+    pts = O.iter_manhattan((1, 2), 3)
+    assert len(pts) == 1 + 3 + 5 + 7 + 5 + 3 + 1
+    assert all(a[1] < b[1] or (a[1] == b[1] and a[0] < b[0]) for a, b in zip(pts, pts[1:]))
+    assert all(abs(x - 1) + abs(y - 2) <= 3 for x, y in pts)
+
+
+def test_neighbors_order():  # src/math/point.rs:46-53
+    assert O.neighbors((4, 7)) == [(5, 7), (4, 8), (3, 7), (4, 6)]
+
+
+def test_dims_partial_order():  # src/math/dimensions.rs:74-114
+    assert O.dims_partial_cmp((1, 1), (1, 2)) == -1
+    assert O.dims_partial_cmp((3, 3), (1, 3)) == 1
+    assert O.dims_partial_cmp((1, 6), (5, 5)) is None
+    assert O.dims_partial_cmp((2, 1), (1, 2)) is None
+    assert O.dims_partial_cmp((3, 3), (3, 3)) == 0
+    assert O.dims_partial_cmp((0, 5), (4, 0)) == 0  # both empty
+    assert O.dims_partial_cmp((0, 5), (1, 1)) == -1
+    assert O.dims_partial_cmp((1, 1), (7, 0)) == 1
+
+
+# ---- src/platform.rs:139-233 --------------------------------------------------------------------
+def test_platform_overlap_tables():
+    g = golden("platform_overlap")
+    assert len(g["overlap_yes"]) == 22 and len(g["overlap_no"]) == 18
+    for a, b in g["overlap_yes"]:
+        assert O.platform_overlaps(a, b) and O.platform_overlaps(b, a), (a, b)
+    for a, b in g["overlap_no"]:
+        assert not O.platform_overlaps(a, b) and not O.platform_overlaps(b, a), (a, b)
+
+
+def test_platform_rotation_dims():  # src/platform.rs:111-113
+    assert O.platform_overlaps((0, 0, 1, 4, 1), (3, 0, 1, 1, 0))      # rotated 1x4 = 4 wide
+    assert not O.platform_overlaps((0, 0, 1, 4, 0), (3, 0, 1, 1, 0))  # unrotated = 1 wide
+
+
+# ---- src/world.rs:49-79 ------------------------------------------------------------------------
+def test_world_fixtures_roundtrip(fixtures):
+    assert fixtures["ex1"].shape == (6, 5) and fixtures["ex1"].sum() == 19
+    assert fixtures["ex2"].shape == (16, 21) and fixtures["ex2"].sum() == 236
+    assert fixtures["ex3"].shape == (7, 11) and fixtures["ex3"].sum() == 73
+    for g in fixtures.values():
+        g2, ragged = O.parse_world(O.world_to_toml(g))
+        assert not ragged and np.array_equal(g, g2)
+
+
+def test_world_errors_and_ragged():
+    g, ragged = O.parse_world('[world]\ngrid = ["XX", "X", ""]\n')
+    assert ragged and g.tolist() == [[1, 1], [1, 0], [0, 0]]  # left-aligned, padded false (world.rs:82-86)
+    with pytest.raises(O.WorldParseError, match="expected `X` or ` `"):
+        O.parse_world('[world]\ngrid = ["X.X"]\n')            # world.rs:58
+    with pytest.raises(O.WorldParseError, match="invalid length 0"):
+        O.parse_world("[world]\ngrid = []\n")                 # world.rs:63-65
+    with pytest.raises(O.WorldParseError):
+        O.parse_world("[world]\n")
+
+
+# ---- src/encoder.rs:45-51 doc-comment DAG ------------------------------------------------------------
+def test_dag_matches_doc_diagram():
+    want = {tuple(e) for e in golden("dag_default8")["edges_smaller_to_larger"]}
+    plat, pts = O.dag_edges(O.PLATFORMS_DEFAULT)
+    got = {(f"{a[0]}x{a[1]}", f"{b[0]}x{b[1]}") for a, b in plat}
+    assert got == want and len(plat) == 15
+    assert len(pts) == 27  # 25 points of 5x5 + (0,5) + (5,0); (5,5) etc. are isolated and dropped (encoder.rs:331)
+    minimal = dict(pts)
+    assert minimal[(0, 0)] == (1, 1) and minimal[(1, 1)] == (3, 3) and minimal[(0, 5)] == (1, 6) and minimal[(3, 1)] == (5, 5)
+    plat1, pts1 = O.dag_edges(O.PLATFORMS_1X1)
+    assert plat1 == [] and pts1 == [((0, 0), (1, 1))]
+
+
+# ---- encoder clause families (SURVEY.md §6 counts, derived independently by the survey's restatement) -------------
+@pytest.mark.parametrize("name,defs,want", [
+    ("ex1", O.PLATFORMS_1X1, (106, 95, 309)), ("ex1", O.PLATFORMS_DEFAULT, (466, 1625, 3072)),
+    ("ex3", O.PLATFORMS_1X1, (369, 365, 1425)), ("ex3", O.PLATFORMS_DEFAULT, (1293, 4707, 10526)),
+    ("ex2", O.PLATFORMS_1X1, (1280, 1180, 4698)), ("ex2", O.PLATFORMS_DEFAULT, (5312, 22486, 51492)),
+])
+def test_encoder_sizes(fixtures, name, defs, want):
+    c = O.Encoding(defs, fixtures[name]).cnf()
+    assert (c.n_vars, c.n_clauses, c.n_lits) == want
+
+
+def test_encoder_family_breakdown_ex2(fixtures):
+    c = O.Encoding(O.PLATFORMS_DEFAULT, fixtures["ex2"]).cnf()
+    assert c.family_counts() == dict(dag_impl=5040, dag_sibling=1680, t3_platform=236, layer=708, unit_t0=236,
+                                     overlap_anchor=6801, overlap_cross=5850, oob=1935)
+
+
+def test_encoder_1x1_shape():
+    """with {1x1} exactly 5 clauses per ceiling tile, none for empty tiles."""
+    g = rows_to_grid(["XX ", " X ", "   "])
+    e = O.Encoding(O.PLATFORMS_1X1, g)
+    c = e.cnf()
+    assert c.n_vars == 9 + 4 * 3 and c.n_clauses == 5 * 3
+    cl = set(c.clauses())
+    p = lambda x, y: int(e.plat_var[y * 3 + x, 0])
+    t = lambda x, y, l: int(e.terr_var[y * 3 + x, l])
+    assert (-t(0, 0, 3), p(0, 0)) in cl                                    # T3 -> P(1x1) here   (encoder.rs:500-516)
+    assert (-t(1, 0, 0), t(1, 1, 1), t(0, 0, 1), t(1, 0, 1)) in cl          # neighbours +x,+y,-x,-y then self (encoder.rs:522-537)
+    assert (t(1, 1, 0),) in cl                                              # unit T0             (encoder.rs:543)
+    assert np.array_equal(e.terr_var[2], [0, 0, 0, 0])                      # no terrain vars for empty tiles
+
+
+# ---- README golden layouts through validate (platform_layout.rs:85-149) -----------------------------
+def test_readme_layouts_validate(readme):
+    grid, layouts = readme
+    assert grid.shape == (16, 21) and grid.sum() == 240
+    for lay in layouts:
+        v = O.validate(grid, sites(lay["supports"]))
+        assert v.is_valid, lay["marked"]
+        # removing any support of the tightest layout must break coverage somewhere or stay valid — just check count
+    # dropping one support from the 15-layout leaves tiles unsupported (it is not trivially redundant)
+    assert not all(O.validate(grid, sites(layouts[3]["supports"][:i] + layouts[3]["supports"][i + 1:])).is_valid for i in range(15))
+
+
+def test_readme_layouts_satisfy_cnf(readme):
+    """A validated layout extends to a model of the encoder's CNF under the at-most-n bound."""
+    grid, layouts = readme
+    enc = O.Encoding(O.PLATFORMS_1X1, grid)
+    for lay in layouts:
+        cnf = enc.with_limits({ONE: lay["marked"]})
+        units = [(int(enc.plat_var[y * grid.shape[1] + x, 0]),) for x, y in lay["supports"]]
+        # fix the layout's platform vars through extra unit clauses in DIMACS -> z3-free check with own CDCL
+        r, a, _ = _solve_with_units(cnf, units, enc, lay["supports"], grid)
+        assert r == 10
+        assert sorted(p[:2] for p in enc.layout_from_assignment(a)) == sorted(map(tuple, lay["supports"]))
+
+
+def _solve_with_units(cnf, units, enc, supports, grid):
+    import ctypes as C
+    # assignment by construction: P = layout, T_l(p) = "within 3-l geodesic steps of a supported tile"
+    h, w = grid.shape
+    a = np.zeros(cnf.n_vars + 1, np.uint8)
+    a[0] = 2
+    sup = np.zeros_like(grid)
+    for x, y in supports:
+        a[enc.plat_var[y * w + x, 0]] = 1
+        sup[y, x] = grid[y, x]
+    layers = [sup.copy()]
+    for _ in range(3):
+        s = layers[-1]
+        n = s.copy()
+        n[1:] |= s[:-1]; n[:-1] |= s[1:]; n[:, 1:] |= s[:, :-1]; n[:, :-1] |= s[:, 1:]
+        layers.append(n & grid)
+    for l in range(4):  # T3 = directly supported ... T0 = after 3 spreading rounds
+        m = layers[3 - l].reshape(-1)
+        tv = enc.terr_var[:, l]
+        a[tv[(tv > 0) & (m > 0)]] = 1
+    base = enc.cnf()
+    nf, first = base.count_falsified(a[: base.n_vars + 1])
+    assert nf == 0, (nf, first)
+    return cnf.solve()[0], a, None
+
+
+# ---- solver loop known answers (UNSAT proven one below) -----------------------------
+@pytest.mark.parametrize("name,defs,optimum", [
+    ("ex1", O.PLATFORMS_1X1, 3), ("ex1", O.PLATFORMS_DEFAULT, 1),
+    ("ex3", O.PLATFORMS_1X1, 4), ("ex3", O.PLATFORMS_DEFAULT, 1),
+    ("ex2", O.PLATFORMS_DEFAULT, 4),
+])
+def test_solver_loop_optimum(fixtures, name, defs, optimum):
+    r = O.solver_loop(fixtures[name], defs)
+    assert r["proved_optimal"] and len(r["best"]) == optimum
+    assert all(s["valid"] for s in r["steps"] if s["result"] == 10)
+    assert r["steps"][0]["bound"] == -1                      # first solve is unbounded (main.rs:57-70,249)
+    for a, b in zip(r["steps"], r["steps"][1:]):
+        assert b["bound"] == a["count"] - 1                  # main.rs:346
+    assert O.validate(fixtures[name], r["best"]).is_valid
+
+
+def test_solver_loop_rect8():
+    r = O.solver_loop(np.ones((8, 8), np.uint8), O.PLATFORMS_1X1)
+    assert r["proved_optimal"] and len(r["best"]) == 4
+
+
+@pytest.mark.slow
+def test_solver_loop_ex2_1x1(fixtures):
+    r = O.solver_loop(fixtures["ex2"], O.PLATFORMS_1X1)
+    assert r["proved_optimal"] and len(r["best"]) == 14
+
+
+def test_z3_agrees_with_cdcl(fixtures):
+    """Independent exact solver (z3 QF_FD) on the same DIMACS: SAT at the optimum, UNSAT one below."""
+    z3 = pytest.importorskip("z3")
+    for name, defs, opt in [("ex1", O.PLATFORMS_1X1, 3), ("ex3", O.PLATFORMS_1X1, 4), ("ex1", O.PLATFORMS_DEFAULT, 1), ("ex3", O.PLATFORMS_DEFAULT, 1)]:
+        enc = O.Encoding(defs, fixtures[name])
+        for bound, want in [(opt, z3.sat), (opt - 1, z3.unsat)]:
+            cnf = enc.with_limits({ONE: bound})
+            s = z3.SolverFor("QF_FD")
+            vs = [None] + [z3.Bool(f"v{i}") for i in range(1, cnf.n_vars + 1)]
+            for cl in cnf.clauses():
+                s.add(z3.Or([vs[l] if l > 0 else z3.Not(vs[-l]) for l in cl]) if cl else z3.BoolVal(False))
+            assert s.check() == want, (name, bound)
+            assert cnf.solve()[0] == (10 if want == z3.sat else 20)
+
+
+def test_totalizer_semantics():
+    """with_limits' cardinality lowering (rustsat into_cnf stand-in, parity unpinned): exactly the assignments
+    with <= k true inputs extend to models."""
+    import itertools
+    g = np.zeros((1, 5), np.uint8)  # no ceiling -> base CNF has no clauses, P vars free
+    enc = O.Encoding(O.PLATFORMS_1X1, g)
+    for k in range(0, 6):
+        cnf = enc.with_limits({ONE: k})
+        for bits in itertools.product([0, 1], repeat=5):
+            extra = O.Encoding(O.PLATFORMS_1X1, g).with_limits({ONE: k})
+            # force inputs via assumptions-as-units: rebuild DIMACS with units and solve using z3-free CDCL
+            r = _solve_units(extra, [(v if b else -v) for v, b in zip(enc.plat_var[:, 0].tolist(), bits)])
+            assert (r == 10) == (sum(bits) <= k), (k, bits)
+
+
+def _solve_units(cnf, units):
+    import ctypes as C
+    L = O.lib()
+    # append unit clauses by solving a fresh CNF assembled in Python through the DIMACS-level entry point
+    clauses = cnf.clauses() + [(u,) for u in units]
+    return _solve_clause_list(cnf.n_vars, clauses)
+
+
+def _solve_clause_list(n_vars, clauses):
+    z3 = pytest.importorskip("z3")
+    s = z3.SolverFor("QF_FD")
+    vs = [None] + [z3.Bool(f"v{i}") for i in range(1, n_vars + 1)]
+    for cl in clauses:
+        s.add(z3.Or([vs[l] if l > 0 else z3.Not(vs[-l]) for l in cl]) if cl else z3.BoolVal(False))
+    return 10 if s.check() == z3.sat else 20
+
+
+def test_weight_limit_pb(fixtures):
+    """GUI objective (app.rs:53-62,235-245): weights 1x1=5, 1xN=1, 3x3=2, 5x5=4; total_weight mirrors the PB sum."""
+    weights = {(1, 1): 5, (1, 2): 1, (1, 3): 1, (1, 4): 1, (1, 5): 1, (1, 6): 1, (3, 3): 2, (5, 5): 4}
+    assert O.total_weight([(0, 0, 5, 5, 0)], weights) == 5 + 1 + 1 + 1 + 1 + 2 + 4   # all defs <= 5x5 except 1x6
+    assert O.total_weight([(0, 0, 1, 6, 1)], weights) == 5 + 5                        # 1x1..1x6 chain
+    assert O.total_weight([(0, 0, 3, 3, 0), (4, 4, 1, 1, 0)], weights) == (5 + 1 + 1 + 2) + 5
+    enc = O.Encoding(O.PLATFORMS_DEFAULT, fixtures["ex1"])
+    r, a, _ = enc.with_limits(weights=weights, weight_limit=15).solve()
+    assert r == 10
+    lay = enc.layout_from_assignment(a)
+    assert O.validate(fixtures["ex1"], lay).is_valid
+    assert enc.assignment_total_weight(a, weights) <= 15
+    assert O.total_weight(lay, weights) <= enc.assignment_total_weight(a, weights)
+    assert enc.with_limits(weights=weights, weight_limit=4).solve()[0] == 20            # any platform costs >= 5
+
+
+def test_trivial_optimization(fixtures):  # platform_layout.rs:151-172
+    g = fixtures["ex1"]
+    lay = [(0, 0, 5, 5, 0), (3, 5, 1, 1, 0), (2, 3, 1, 1, 0)]  # (3,5) and (2,3) sit under no ceiling
+    assert O.trivial_optimization(g, lay) == [(0, 0, 5, 5, 0)]
+
+
+def test_validate_reports(fixtures):
+    g = fixtures["ex1"]
+    v = O.validate(g, [(0, 0, 3, 3, 0), (2, 2, 3, 3, 0), (4, 4, 1, 2, 1)])
+    assert (0, 0, 3, 3, 0) in v.overlapping and (2, 2, 3, 3, 0) in v.overlapping   # share tile (2,2)
+    assert v.out_of_bounds == [(4, 4, 1, 2, 1)]                                    # rotated 1x2 = 2 wide at x=4 of width 5
+    v = O.validate(g, [])
+    assert v.unsupported.sum() == 19 and np.array_equal(v.unsupported, g)
+
+
+def test_validate_geodesic_not_manhattan():
+    """Support spreads only THROUGH ceiling tiles (platform_layout.rs:134-138): a gap blocks it."""
+    g = rows_to_grid(["XXX XXX"])
+    v = O.validate(g, sites([(0, 0)]))
+    assert v.unsupported.tolist() == [[0, 0, 0, 0, 1, 1, 1]]
+    g = rows_to_grid(["XXXXXXX"])
+    assert O.validate(g, sites([(3, 0)])).is_valid and not O.validate(g, sites([(2, 0)])).is_valid
