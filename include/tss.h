@@ -1,0 +1,222 @@
+/* tss.h — C ABI of libtss, the B200 (sm_100a) upper-bound engine for Timberborn ceiling-support placement.
+ *
+ * Drop-in boundary for ONE path of MetaflameDragon/timberborn_support_solver: the feasibility-and-bound loop
+ * (encode -> bound -> CNF -> solve -> decode -> validate -> tighten).  Every entry point cites the reference
+ * interface (file:line, relative to the reference tree) it stands behind; INTEGRATION.md shows the Rust
+ * `extern "C"` block + safe wrapper a maintainer would add.
+ *
+ * Conventions
+ *   - grids are row-major u8, index x + y*width, non-zero = ceiling           (src/math/grid.rs:66-68, src/world.rs:19)
+ *   - a platform is (x, y) of its min-x/min-y corner + CANONICAL def dims (w <= h as in PLATFORMS_DEFAULT)
+ *     + `rotated` (effective dims flipped)                                      (src/platform.rs:64-70,111-113)
+ *   - literals are DIMACS-signed int32 over 1-based variables (rustsat Var idx + 1)
+ *   - assignments are u8 per variable, index = variable (slot 0 unused): 0 False, 1 True, 2 DontCare (rustsat TernaryVal)
+ *   - bit-packed grids ("rows"): each grid row is ceil(width/32) little-endian u32 words, bit (x & 31) of word
+ *     (x >> 5) = tile (x, y); unused high bits are zero
+ *   - all buffers are caller-allocated HOST memory unless the name ends in `_dev`; the engine never keeps a
+ *     caller pointer after the call returns; outputs that do not fit return TSS_E_CAPACITY
+ *   - no exceptions / aborts cross this boundary; every call returns a status (>= 0 ok, < 0 error) and
+ *     tss_last_error() describes the last failure on that engine
+ *   - the GPU path has NO CPU fallback: without a usable CUDA device tss_engine_create fails with TSS_E_CUDA
+ */
+#ifndef TSS_H
+#define TSS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSS_VERSION 100
+
+/* status codes; solve results follow IPASIR / rustsat SolverResult (crates/repl/src/main.rs:326-339) */
+#define TSS_OK 0
+#define TSS_UNKNOWN 0       /* budget exhausted or interrupted: no layout within the bound was found (NOT a proof) */
+#define TSS_SAT 10          /* a validated layout within the bound was found */
+#define TSS_UNSAT 20        /* never produced by the GPU engine: only the exact solver proves UNSAT */
+#define TSS_E_INVALID (-1)  /* bad argument (null pointer, zero-sized grid, platform set without 1x1, ...) */
+#define TSS_E_CAPACITY (-2) /* an output buffer is too small; the required size is reported where documented */
+#define TSS_E_CUDA (-3)     /* CUDA runtime failure or no device */
+#define TSS_E_UNSUPPORTED (-4) /* valid input outside what this build accelerates (e.g. grid larger than 256x256 for SLS) */
+#define TSS_E_PARSE (-5)    /* project file rejected (src/world.rs:49-79) */
+
+typedef struct tss_engine tss_engine;     /* one per GPU / CUDA stream; single caller except tss_interrupt */
+typedef struct tss_encoding tss_encoding; /* host-side Encoding (src/encoder.rs:428-432) */
+typedef struct tss_cnf tss_cnf;           /* a CNF resident on the device in CSR form */
+typedef struct tss_search tss_search;     /* a device-resident SLS portfolio on one terrain */
+
+/* src/platform.rs:64-70 Platform {point, def, rotated} */
+typedef struct tss_platform {
+    int32_t x, y;         /* anchor = min corner */
+    int32_t def_w, def_h; /* canonical def dims */
+    int32_t rotated;
+} tss_platform;
+
+/* src/platform.rs:11-15 PlatformDef */
+typedef struct tss_dims {
+    int32_t w, h;
+} tss_dims;
+
+/* rustsat SolveStats (crates/repl/src/main.rs:363) + engine counters */
+typedef struct tss_stats {
+    uint64_t layouts_evaluated;   /* full evaluations by the coverage kernel (a) */
+    uint64_t candidates_scored;   /* candidate layouts scored incrementally by the SLS kernel (b) */
+    uint64_t sls_steps;           /* swap / drop steps executed over all chains */
+    uint64_t clauses_checked;     /* clause x assignment evaluations by the CNF kernel (c) */
+    uint64_t kernel_launches;     /* kernels launched by this engine */
+    uint64_t n_solves;            /* tss_solve_upper_bound / tss_search_run calls */
+    double   device_ms;           /* device time of the kernels of the last call (CUDA events on the engine stream) */
+    int32_t  best_count;          /* best platform count of the last solve (-1 if none) */
+    int32_t  interrupted;         /* last solve ended by tss_interrupt */
+} tss_stats;
+
+/* ------------------------------------------------------------------------------------------------ engine */
+int tss_version(void);
+/* device < 0: current device.  Fails with TSS_E_CUDA when no CUDA device is usable (no CPU fallback). */
+int tss_engine_create(int device, tss_engine** out);
+void tss_engine_destroy(tss_engine* e);
+/* Run the engine's kernels on a caller-owned cudaStream_t (e.g. the host framework's current stream) instead of
+ * the engine's own stream.  NULL restores the engine stream. */
+int tss_engine_set_stream(tss_engine* e, void* cuda_stream);
+const char* tss_last_error(const tss_engine* e);
+/* rustsat InterruptSolver::interrupt (crates/repl/src/main.rs:310-317, crates/gui/src/solver_backend.rs:47-49):
+ * callable from any thread while a solve runs on `e`; the running call returns TSS_UNKNOWN with stats.interrupted. */
+void tss_interrupt(tss_engine* e);
+void tss_clear_interrupt(tss_engine* e);
+int tss_get_stats(const tss_engine* e, tss_stats* out);
+/* name[<=cap], SM count, max SM clock in kHz */
+int tss_device_info(const tss_engine* e, char* name, int cap, int* sm_count, int* clock_khz);
+
+/* --------------------------------------------------------------------------------- world (src/world.rs:49-79) */
+/* Parses `[world] grid = ["XX ", ...]`.  Ragged rows are left-aligned and padded false as world.rs:82-86 documents
+ * (the reference's copy_from_slice at :73 would panic instead; *ragged reports that case).  err gets a message. */
+int tss_world_parse_toml(const char* text, uint8_t* grid, size_t cap, int32_t* w, int32_t* h, int32_t* ragged,
+                         char* err, size_t err_cap);
+/* world.rs:21-40 serialiser; returns bytes written (excl. NUL) or TSS_E_CAPACITY */
+int tss_world_to_toml(const uint8_t* grid, int32_t w, int32_t h, char* out, size_t cap);
+/* SURVEY.md §8(d) synthetic terrain: ceiling iff (splitmix64(seed*0x9E3779B97F4A7C15 + (t<<20) + y*w + x) >> 40) < density_q24 */
+int tss_world_synthetic(int32_t w, int32_t h, uint64_t seed, uint64_t t, uint32_t density_q24, uint8_t* grid);
+
+/* --------------------------------------------------------------- encoder (src/encoder.rs:435-667), host side */
+/* Encoding::encode(&[PlatformDef], &WorldGrid) (encoder.rs:435).  Rejects a platform set without 1x1 with
+ * TSS_E_INVALID (the reference unwraps, encoder.rs:564-566). */
+int tss_encoding_create(const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs, tss_encoding** out);
+void tss_encoding_destroy(tss_encoding* enc);
+/* sizes of the base instance: vars, clauses, literals, number of dims keys K (encoder.rs:121-130) */
+int tss_encoding_sizes(const tss_encoding* enc, int32_t* n_vars, int32_t* n_clauses, int64_t* n_lits, int32_t* n_dims);
+/* dims keys in variable order (deterministic replacement for the reference's HashMap order, encoder.rs:191-194) */
+int tss_encoding_dims(const tss_encoding* enc, tss_dims* out_dims /* [K] */);
+/* Encoding::vars() (encoder.rs:615): plat_var[tile*K + k], terr_var[tile*4 + layer]; 0 = absent */
+int tss_encoding_var_maps(const tss_encoding* enc, int32_t* plat_var, int32_t* terr_var);
+/* the base CNF in CSR form: lits[n_lits], offsets[n_clauses+1] */
+int tss_encoding_cnf(const tss_encoding* enc, int32_t* lits, uint32_t* offsets);
+/* Encoding::with_limits(&PlatformLimits) + SatInstance::into_cnf() (encoder.rs:619-667, crates/repl/src/main.rs:292-293).
+ * card / weights are records (def_w, def_h, value); weight_limit is ignored unless has_weight_limit.
+ * Two-call protocol: with lits == NULL only the sizes are returned. */
+int tss_encoding_with_limits(const tss_encoding* enc, const int32_t* card, int32_t n_card, const int32_t* weights,
+                             int32_t n_weights, int32_t has_weight_limit, int64_t weight_limit, int32_t* n_vars,
+                             int32_t* n_clauses, int64_t* n_lits, int32_t* lits, uint32_t* offsets);
+/* PlatformLayout::from_assignment (src/encoder/platform_layout.rs:26-52): largest platform per anchor.
+ * returns the number of platforms (may exceed cap -> TSS_E_CAPACITY). */
+int tss_layout_from_assignment(const tss_encoding* enc, const uint8_t* assignment, int32_t n_assignment,
+                               tss_platform* out, int32_t cap, int32_t* n_out);
+/* The inverse used to hand a GPU witness to the exact solver / CNF check: platform vars from the layout (every dims
+ * key <= the platform's dims at its anchor, per the DAG implications encoder.rs:449-458), terrain-layer vars from
+ * the support layers (T_l(p) = p within 3-l steps of a directly supported tile).  Runs the coverage kernel (a). */
+int tss_layout_to_assignment(tss_engine* e, const tss_encoding* enc, const tss_platform* plats, int32_t n_plats,
+                             uint8_t* assignment /* [n_vars_base + 1] */);
+/* run_trivial_optimization (platform_layout.rs:151-172): drop platforms under no ceiling tile; returns new count */
+int tss_layout_trivial_optimization(const uint8_t* grid, int32_t w, int32_t h, tss_platform* plats, int32_t n);
+/* total_weight (platform_layout.rs:174-183); weights are records (def_w, def_h, weight) */
+int64_t tss_layout_total_weight(const tss_platform* plats, int32_t n, const int32_t* weights, int32_t n_weights);
+/* Platform::overlaps (src/platform.rs:86-97) */
+int tss_platform_overlaps(const tss_platform* a, const tss_platform* b);
+
+/* ------------------------------------------------------- kernel (a): coverage evaluator == PlatformLayout::validate */
+/* validate() of ONE layout (platform_layout.rs:85-149), on the GPU.  out_unsupported: u8[w*h] mask of unsupported
+ * terrain; out_flags[n]: bit0 overlapping, bit1 out of bounds.  Returns the number of unsupported tiles. */
+int tss_validate(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_platform* plats, int32_t n,
+                 uint8_t* out_unsupported, uint8_t* out_flags);
+/* Batched validate of 1x1-only layouts given as u8 site masks [n][w*h] (non-zero = support) on one terrain. */
+int tss_eval_sites(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const uint8_t* sites, int64_t n,
+                   int32_t* out_uncovered, int32_t* out_count);
+/* Same with bit-packed inputs: grid_rows[h*wpr], layouts[n][h*wpr] (wpr = ceil(w/32)).  Host buffers. */
+int tss_eval_packed(tss_engine* e, const uint32_t* grid_rows, int32_t w, int32_t h, const uint32_t* layouts, int64_t n,
+                    int32_t* out_uncovered, int32_t* out_count);
+/* Device-resident variant (inputs/outputs already in HBM; async on the engine stream).  `layouts_dev` uses the
+ * compact row format: for grids up to 32x32 the row stride is 1, 2 or 4 bytes for w <= 8, 16, 32 and a layout is
+ * padded to a multiple of 4 bytes; larger grids use 4*wpr bytes per row.  out_dev: int32[n][2] =
+ * (uncovered, count).  per_layout_terrain != 0: grid_dev holds n terrains (one per layout, same format). */
+int tss_eval_compact_dev(tss_engine* e, const void* grid_dev, int32_t w, int32_t h, const void* layouts_dev, int64_t n,
+                         int32_t per_layout_terrain, int32_t* out_dev);
+size_t tss_compact_row_bytes(int32_t w, int32_t h);
+size_t tss_compact_layout_bytes(int32_t w, int32_t h);
+/* Batched validate of general platform layouts: layout i = plats[offsets[i] .. offsets[i+1]).  out[n][4] =
+ * (unsupported tiles, platforms, overlapping platforms, out-of-bounds platforms). */
+int tss_eval_platforms(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_platform* plats,
+                       const uint32_t* offsets, int64_t n, int32_t* out);
+
+/* -------------------------------------------- kernel (c): clause evaluation + unit propagation over the encoder's CNF */
+/* Solve::add_cnf analogue (crates/repl/src/solver_runner.rs:12): uploads lits/offsets (CSR) once. */
+int tss_cnf_upload(tss_engine* e, const int32_t* lits, const uint32_t* offsets, int32_t n_clauses, int32_t n_vars, tss_cnf** out);
+void tss_cnf_destroy(tss_cnf* c);
+/* Evaluates every clause under n assignments [n][n_vars+1] (0 F / 1 T / 2 DontCare; a DontCare literal satisfies
+ * nothing).  out_n_falsified[n], out_first_falsified[n] (clause index or -1). */
+int tss_cnf_check(tss_engine* e, const tss_cnf* c, const uint8_t* assignments, int64_t n, int32_t* out_n_falsified,
+                  int32_t* out_first_falsified);
+/* Unit propagation to fixpoint from n partial assignments (in/out).  out_conflict[n] = index of a clause falsified
+ * at the fixpoint, or -1.  out_rounds (optional) = propagation rounds executed. */
+int tss_cnf_propagate(tss_engine* e, const tss_cnf* c, uint8_t* assignments, int64_t n, int32_t* out_conflict, int32_t* out_rounds);
+
+/* --------------------------------------------------- kernel (b): batched stochastic local search (upper bounds) */
+typedef struct tss_search_params {
+    uint64_t seed;         /* counter-based RNG key; results are reproducible for (seed, n_chains, chain_offset) */
+    int32_t n_chains;      /* independent layouts searched in parallel (one per warp); 0 = fill the device */
+    int32_t chain_offset;  /* global index of this engine's first chain (rank * n_chains in a multi-GPU portfolio) */
+    int32_t noise_pct;     /* probability (percent) of a random instead of greedy add move; < 0 = default */
+    int32_t reserved;
+} tss_search_params;
+
+/* Creates a portfolio on one terrain.  defs must contain 1x1 (encoder.rs:564-566). */
+int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,
+                      const tss_search_params* params, tss_search** out);
+void tss_search_destroy(tss_search* s);
+/* Runs `steps` SLS steps per chain (one epoch, one kernel launch + a best-reduce), asynchronously on the engine
+ * stream.  Chains stop early once a layout with <= target_count platforms is found (target < 0: never). */
+int tss_search_run(tss_search* s, int64_t steps, int32_t target_count);
+/* Best validated platform count found so far (synchronises the stream); -1 if no complete layout yet. */
+int tss_search_best_count(tss_search* s, int32_t* count);
+/* Shares an externally known bound (e.g. the all-reduce-min over GPUs): chains only look for layouts with fewer
+ * than `count` platforms from now on. */
+int tss_search_set_bound(tss_search* s, int32_t count);
+/* Best layout (re-validated by kernel (a) before it is returned). */
+int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_t* n_out);
+int tss_search_n_chains(const tss_search* s);
+/* Introspection for the parity tests (the CPU model in oracle/sls_model.cpp replays the same trajectories): per-chain
+ * state after the last epoch.  S / best_S: support rows u32[n_chains][32]; any pointer may be NULL. */
+int tss_search_read_chains(tss_search* s, uint32_t* S, uint32_t* best_S, int32_t* k, int32_t* best, uint32_t* step, uint64_t* scored);
+
+/* The solve-with-bound entry point (the SAT side of crates/repl/src/main.rs:292-329 / crates/gui/src/solver_backend.rs:69-97):
+ * find a layout with at most `card_limit` platforms (card_limit < 0: unbounded, any complete layout) within
+ * `budget_ms` (<= 0: until target reached or interrupted; bounded by max_steps per chain if > 0).
+ * Returns TSS_SAT with the layout, TSS_UNKNOWN if none was found (never TSS_UNSAT). */
+int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,
+                          int32_t card_limit, uint64_t seed, int32_t budget_ms, int64_t max_steps, tss_platform* out,
+                          int32_t cap, int32_t* n_out);
+/* Terrain batch: n independent terrains [n][w*h], 1x1 supports; out_counts[n] = best count per
+ * terrain; out_layouts (optional) = packed support rows [n][h*wpr]. */
+int tss_solve_batch(tss_engine* e, const uint8_t* grids, int32_t w, int32_t h, int64_t n, uint64_t seed, int64_t steps,
+                    int32_t* out_counts, uint32_t* out_layouts);
+
+/* ------------------------------------------------------------------------------------------ measured peaks */
+/* Runs the integer-issue (LOP3 / POPC / SHFL) and shared-memory micro-benchmarks SURVEY.md §8(d) asks for.
+ * out[0] LOP3 Gop/s (thread-ops), out[1] POPC Gop/s, out[2] SHFL Gop/s, out[3] shared-memory GB/s, out[4] SM clock MHz
+ * observed (cycles / elapsed). */
+int tss_measure_peaks(tss_engine* e, double* out, int32_t n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSS_H */

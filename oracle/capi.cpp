@@ -186,6 +186,15 @@ int tsso_cnf_solve(void* c, uint8_t* assignment /* n_vars+1 */, long conflict_bu
     if (seconds) *seconds = st.seconds;
     return r;
 }
+// solve a caller-provided CSR CNF (lets tests hand the PRODUCT's CNF to the oracle's CDCL as the Glucose stand-in)
+int tsso_solve_csr(const int* lits, const unsigned* offsets, int n_clauses, int n_vars, uint8_t* assignment, long conflict_budget) {
+    std::vector<Clause> cls((size_t)n_clauses);
+    for (int i = 0; i < n_clauses; i++) cls[i].assign(lits + offsets[i], lits + offsets[i + 1]);
+    Assignment a;
+    int r = solve_cnf(n_vars, cls, a, nullptr, conflict_budget, nullptr);
+    if (r == 10 && assignment) std::memcpy(assignment, a.data(), a.size());
+    return r;
+}
 // plain CPU clause check of a full assignment (1/0/2): returns number of falsified clauses
 int tsso_cnf_count_falsified(void* c, const uint8_t* assignment, int* first) {
     auto& inst = ((CnfHandle*)c)->inst;

@@ -286,3 +286,23 @@ def solver_loop(grid, defs, initial_limit=None, conflict_budget=-1):
         best=[tuple(map(int, p)) for p in plats[: n_plats.value]],
         proved_optimal=bool(proved.value),
     )
+
+
+# --------------------------------------------------------------------------- SLS model (oracle/sls_model.cpp)
+def sls_model(grid, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, share_bound=True):
+    """Replays kernel (b)'s published step rule on the CPU.  epochs: [(steps, bound, target)].
+    -> dict(S uint8[n,32,32], bestS, k, best, step, scored, steps)"""
+    g = _grid(grid)
+    ep = np.ascontiguousarray(epochs, dtype=np.int64).reshape(-1, 3)
+    S = np.zeros((n_chains, 32, 32), np.uint8)
+    bestS = np.zeros((n_chains, 32, 32), np.uint8)
+    k = np.zeros(n_chains, np.int32)
+    best = np.zeros(n_chains, np.int32)
+    step = np.zeros(n_chains, np.uint32)
+    scored = np.zeros(n_chains, np.uint64)
+    steps = np.zeros(n_chains, np.uint64)
+    rc = lib().tsso_sls_model(_p(g, C.c_uint8), g.shape[1], g.shape[0], n_chains, C.c_uint32(chain_offset), C.c_uint64(seed), noise_pct,
+                              _p(ep, C.c_longlong), len(ep), int(share_bound), _p(S, C.c_uint8), _p(bestS, C.c_uint8), _p(k), _p(best),
+                              _p(step, C.c_uint32), _p(scored, C.c_uint64), _p(steps, C.c_uint64))
+    assert rc == 0
+    return dict(S=S, bestS=bestS, k=k, best=best, step=step, scored=scored, steps=steps)

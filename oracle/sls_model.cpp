@@ -1,0 +1,207 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle.hpp).
+//
+// Scalar CPU model of the batched stochastic local search (kernel (b), timberborn_support_solver_b200/csrc/sls.cu).
+// The SLS has no counterpart in the reference ("the three CUDA kernels ... have no counterpart"); its
+// SEMANTICS are anchored on the reference's range rule: a site's reach is what PlatformLayout::validate's three
+// ceiling-masked 4-neighbour dilations produce from that site alone (src/encoder/platform_layout.rs:127-141), and a
+// layout is complete iff validate() reports no unsupported terrain.  This model is written tile-by-tile with byte
+// counters (no bit tricks) and replays the kernel's published step rule and counter-based RNG so the GPU
+// trajectories can be compared bit for bit (tests/test_sls.py).  It deliberately re-declares the constants of
+// sls_spec.hpp: the oracle never includes product headers; a test checks they agree.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+constexpr uint32_t K1 = 0x9E3779B9u, K2 = 0x85EBCA6Bu;
+constexpr int SALT_ROW = 1, SALT_COL = 2, SALT_NOISE = 3, SALT_PICK = 4, SALT_REMOVE = 1000, SALT_ADD = 200;
+constexpr int NO_BOUND = 1 << 20;
+
+uint32_t fmix32(uint32_t h) { h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h; }
+uint32_t chain_base(uint64_t seed, uint32_t chain) { return fmix32((uint32_t)seed ^ fmix32((uint32_t)(seed >> 32) + chain * K1 + 0x5bd1e995u)); }
+uint32_t rnd(uint32_t base, uint32_t step, uint32_t salt) { return fmix32(base ^ (step * K1) ^ (salt * K2)); }
+
+struct Model {
+    int w, h;
+    std::vector<uint8_t> ceil;               // [32*32], index y*32+x
+    std::vector<std::vector<int>> reach;     // per site: tiles within geodesic distance <= 3 through ceiling
+
+    void build(const uint8_t* grid, int w_, int h_) {
+        w = w_; h = h_;
+        ceil.assign(1024, 0);
+        for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) ceil[y * 32 + x] = grid[y * w + x] != 0;
+        reach.assign(1024, {});
+        for (int s = 0; s < 1024; s++) {
+            if (!ceil[s]) continue;
+            std::vector<uint8_t> sup(1024, 0);
+            sup[s] = 1;
+            for (int round = 0; round < 3; round++) {  // platform_layout.rs:127-141
+                std::vector<uint8_t> nxt = sup;
+                for (int t = 0; t < 1024; t++) {
+                    if (!sup[t]) continue;
+                    int x = t & 31, y = t >> 5;
+                    const int nx[4] = {x + 1, x, x - 1, x}, ny[4] = {y, y + 1, y, y - 1};
+                    for (int d = 0; d < 4; d++)
+                        if (nx[d] >= 0 && nx[d] < 32 && ny[d] >= 0 && ny[d] < 32 && ceil[ny[d] * 32 + nx[d]]) nxt[ny[d] * 32 + nx[d]] = 1;
+                }
+                sup = nxt;
+            }
+            for (int t = 0; t < 1024; t++) if (sup[t]) reach[s].push_back(t);
+        }
+    }
+};
+
+struct Chain {
+    std::vector<uint8_t> S, bestS;  // [1024]
+    std::vector<uint8_t> cnt;       // cover count per tile
+    std::vector<int> sites;
+    int k = 0, best = NO_BOUND, tabu_add = -1, tabu_rem = -1, done = 0;
+    uint32_t step = 0;
+    uint64_t scored = 0, steps_done = 0;
+};
+
+int pick_rotated(uint32_t bits, uint32_t r) {
+    uint32_t o = r & 31u;
+    uint32_t rot = o ? ((bits >> o) | (bits << (32 - o))) : bits;
+    return (int)((__builtin_ctz(rot) + o) & 31u);
+}
+
+struct Runner {
+    const Model& M;
+    Chain& c;
+    uint32_t base;
+    Runner(const Model& m, Chain& ch, uint32_t b) : M(m), c(ch), base(b) {}
+
+    bool uncovered(int t) const { return M.ceil[t] && c.cnt[t] == 0; }
+    int loss(int u) const { int n = 0; for (int t : M.reach[u]) n += c.cnt[t] == 1; return n; }
+    int gain(int v) const { int n = 0; for (int t : M.reach[v]) n += c.cnt[t] == 0; return n; }
+
+    int remove_min_loss(int exclude) {
+        uint32_t best_key = 0xffffffffu;
+        int best_i = 0;
+        for (int i = 0; i < c.k; i++) {  // chunks of 32 lanes, lowest lane wins ties; strict < across chunks
+            int v = c.sites[i];
+            if (v == exclude && c.k > 1) continue;
+            uint32_t key = ((uint32_t)loss(v) << 16) | (rnd(base, c.step, SALT_REMOVE + i) & 0xffffu);
+            if (key < best_key) { best_key = key; best_i = i; }
+        }
+        int u = c.sites[best_i];
+        c.sites[best_i] = c.sites[c.k - 1];
+        c.sites.pop_back();
+        c.k--;
+        for (int t : M.reach[u]) c.cnt[t]--;
+        c.S[u] = 0;
+        return u;
+    }
+
+    void run(long long steps, int epoch_bound, int target, int noise_pct) {
+        if (c.done) return;
+        // epoch start: site list in row-major order
+        c.sites.clear();
+        for (int t = 0; t < 1024; t++) if (c.S[t]) c.sites.push_back(t);
+        c.cnt.assign(1024, 0);
+        for (int s : c.sites) for (int t : M.reach[s]) c.cnt[t]++;
+        long long it = 0;
+        for (; it < steps; it++, c.step++) {
+            const int limit = std::min(epoch_bound, c.best);
+            if (c.k >= limit) {
+                if (c.k == 0) { c.done = 1; break; }
+                c.scored += (uint64_t)c.k;
+                c.tabu_add = remove_min_loss(-1);
+                continue;
+            }
+            bool any = false;
+            for (int t = 0; t < 1024 && !any; t++) any = uncovered(t);
+            if (!any) {
+                c.best = c.k;
+                c.bestS = c.S;
+                if (c.k <= target || c.k == 0) { c.done = 1; it++; c.step++; break; }
+                continue;
+            }
+            if (c.k == limit - 1 && c.k > 0) {
+                c.scored += (uint64_t)c.k;
+                c.tabu_add = remove_min_loss(c.tabu_rem);
+            }
+            uint32_t rowmask = 0;
+            for (int y = 0; y < 32; y++) for (int x = 0; x < 32; x++) if (uncovered(y * 32 + x)) rowmask |= 1u << y;
+            int y = pick_rotated(rowmask, rnd(base, c.step, SALT_ROW));
+            uint32_t urow = 0;
+            for (int x = 0; x < 32; x++) if (uncovered(y * 32 + x)) urow |= 1u << x;
+            int x = pick_rotated(urow, rnd(base, c.step, SALT_COL));
+            int t = y * 32 + x;
+            // candidates in window order (dy, then dx) == diamond lane order
+            std::vector<std::pair<int, int>> cand;  // (site, window bit)
+            for (int dy = -3; dy <= 3; dy++)
+                for (int dx = -3; dx <= 3; dx++) {
+                    if (std::abs(dx) + std::abs(dy) > 3) continue;
+                    int cx = x + dx, cy = y + dy;
+                    if (cx < 0 || cy < 0 || cx >= 32 || cy >= 32) continue;
+                    int v = cy * 32 + cx;
+                    if (std::find(M.reach[t].begin(), M.reach[t].end(), v) != M.reach[t].end()) cand.push_back({v, 7 * (dy + 3) + dx + 3});
+                }
+            int nc = (int)cand.size(), v;
+            if ((int)(rnd(base, c.step, SALT_NOISE) % 100u) < noise_pct) {
+                v = cand[rnd(base, c.step, SALT_PICK) % (uint32_t)nc].first;
+            } else {
+                uint32_t mx = 0;
+                v = cand[0].first;
+                bool first = true;
+                for (auto& [cv, bit] : cand) {
+                    uint32_t key = (cv == c.tabu_add && nc > 1) ? 0u : (((uint32_t)(gain(cv) + 1) << 16) | (rnd(base, c.step, SALT_ADD + bit) & 0xffffu));
+                    if (first || key > mx) { mx = key; v = cv; first = false; }
+                }
+                c.scored += (uint64_t)nc;
+            }
+            for (int tt : M.reach[v]) c.cnt[tt]++;
+            c.S[v] = 1;
+            c.sites.push_back(v);
+            c.k++;
+            c.tabu_rem = v;
+        }
+        c.steps_done += (uint64_t)it;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+// Runs `n_chains` model chains (global ids chain_offset..) for the given epochs on one terrain.
+// epochs: records (steps, epoch_bound, target); between epochs the caller-visible state is what the kernel persists.
+// If share_bound != 0 the bound of epoch e+1 is min(given bound, best over all chains after epoch e) — the
+// portfolio's all-reduce-min.
+// Outputs per chain: S and bestS as u8[1024] (index y*32+x), k, best, step, scored (u64), steps_done (u64).
+int tsso_sls_model(const uint8_t* grid, int w, int h, int n_chains, uint32_t chain_offset, uint64_t seed, int noise_pct,
+                   const long long* epochs, int n_epochs, int share_bound, uint8_t* out_S, uint8_t* out_bestS, int* out_k,
+                   int* out_best, uint32_t* out_step, uint64_t* out_scored, uint64_t* out_steps) {
+    if (w > 32 || h > 32) return -1;
+    Model M;
+    M.build(grid, w, h);
+    std::vector<Chain> chains(n_chains);
+    for (auto& c : chains) { c.S.assign(1024, 0); c.bestS.assign(1024, 0); c.cnt.assign(1024, 0); }
+    int shared = NO_BOUND;
+    for (int e = 0; e < n_epochs; e++) {
+        long long steps = epochs[3 * e];
+        int bound = (int)epochs[3 * e + 1], target = (int)epochs[3 * e + 2];
+        if (share_bound) bound = std::min(bound, shared);
+        for (int i = 0; i < n_chains; i++) Runner(M, chains[i], chain_base(seed, chain_offset + (uint32_t)i)).run(steps, bound, target, noise_pct);
+        for (auto& c : chains) shared = std::min(shared, c.best);
+    }
+    for (int i = 0; i < n_chains; i++) {
+        std::memcpy(out_S + (size_t)i * 1024, chains[i].S.data(), 1024);
+        std::memcpy(out_bestS + (size_t)i * 1024, chains[i].bestS.data(), 1024);
+        out_k[i] = chains[i].k; out_best[i] = chains[i].best; out_step[i] = chains[i].step;
+        out_scored[i] = chains[i].scored; out_steps[i] = chains[i].steps_done;
+    }
+    return 0;
+}
+
+// constants of the spec, for the agreement test against sls_spec.hpp
+void tsso_sls_constants(uint32_t* out) {
+    out[0] = K1; out[1] = K2; out[2] = SALT_ROW; out[3] = SALT_COL; out[4] = SALT_NOISE; out[5] = SALT_PICK;
+    out[6] = SALT_REMOVE; out[7] = SALT_ADD; out[8] = NO_BOUND;
+}
+
+}  // extern "C"

@@ -1,0 +1,361 @@
+"""Parity tests proper: the CUDA path (through the C ABI of libtss) against the oracle on the same seeded inputs,
+against the committed golden fixtures, and through size-independent properties at BASELINE.json's full sizes.
+Bit-exact everywhere: the path is integer / boolean only (no floating point)."""
+import numpy as np
+import pytest
+
+import oracle.oracle as O
+import timberborn_support_solver_b200 as T
+from conftest import rows_to_grid, synth_terrain
+
+pytestmark = pytest.mark.gpu
+ONE = T.PlatformDef(1, 1)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = T.Engine(0)
+    yield e
+    e.close()
+
+
+def tup(p):
+    return (p.x, p.y, p.definition.width, p.definition.height, int(p.rotated))
+
+
+def random_sites(rng, n, h, w, p):
+    return (rng.random((n, h, w)) < p).astype(np.uint8)
+
+
+def pack_rows(mask):
+    """uint8[..., h, w] -> uint32[..., h, ceil(w/32)] (tss.h bit-packed rows)"""
+    h, w = mask.shape[-2:]
+    wpr = (w + 31) // 32
+    pad = np.zeros(mask.shape[:-1] + (wpr * 32,), np.uint8)
+    pad[..., :w] = mask
+    bits = pad.reshape(mask.shape[:-1] + (wpr, 32)).astype(np.uint64)
+    return (bits << np.arange(32, dtype=np.uint64)).sum(-1).astype(np.uint32)
+
+
+# =============================================================================== kernel (a): coverage evaluator
+@pytest.mark.parametrize("w,h", [(1, 1), (5, 6), (8, 8), (7, 3), (16, 16), (11, 7), (13, 29), (21, 16), (32, 32), (32, 5), (17, 32)])
+def test_eval_sites_small_grids_match_validate(eng, w, h):
+    rng = np.random.default_rng(w * 100 + h)
+    for density in (1.0, 0.7, 0.3):
+        grid = (rng.random((h, w)) < density).astype(np.uint8)
+        sites = random_sites(rng, 257, h, w, 0.08)
+        sites[0] = 0                 # empty layout: everything unsupported
+        sites[1] = 1                 # a support everywhere
+        unc, cnt = eng.eval_sites(T.WorldGrid(grid) if grid.any() or True else None, sites)
+        o_unc, o_cnt, _ = O.validate_sites_batch(grid, sites)
+        assert np.array_equal(unc, o_unc) and np.array_equal(cnt, o_cnt), (w, h, density)
+        assert unc[0] == grid.sum() and unc[1] == 0
+
+
+def test_eval_packed_equals_eval_sites(eng, fixtures):
+    rng = np.random.default_rng(3)
+    for name in ("ex1", "ex2", "ex3"):
+        g = fixtures[name]
+        h, w = g.shape
+        sites = random_sites(rng, 100, h, w, 0.1)
+        unc, cnt = eng.eval_sites(T.WorldGrid(g), sites)
+        unc2, cnt2 = eng.eval_packed(pack_rows(g), w, h, pack_rows(sites))
+        assert np.array_equal(unc, unc2) and np.array_equal(cnt, cnt2)
+
+
+@pytest.mark.parametrize("w,h", [(40, 40), (33, 7), (64, 64), (100, 37), (256, 256)])
+def test_eval_sites_tiled_grids_match_validate(eng, w, h):
+    rng = np.random.default_rng(w + h)
+    grid = synth_terrain(w, h, seed=1)
+    n = 6 if w * h > 10000 else 40
+    sites = random_sites(rng, n, h, w, 0.05)
+    unc, cnt = eng.eval_sites(T.WorldGrid(grid), sites)
+    o_unc, o_cnt, _ = O.validate_sites_batch(grid, sites)
+    assert np.array_equal(unc, o_unc) and np.array_equal(cnt, o_cnt)
+
+
+def test_readme_golden_layouts_validate_on_gpu(eng, readme):
+    grid, layouts = readme
+    sites = np.zeros((len(layouts), 16, 21), np.uint8)
+    for i, lay in enumerate(layouts):
+        for x, y in lay["supports"]:
+            sites[i, y, x] = 1
+    unc, cnt = eng.eval_sites(T.WorldGrid(grid), sites)
+    assert unc.tolist() == [0, 0, 0, 0] and cnt.tolist() == [18, 17, 16, 15]      # README.md:47-116
+    for lay in layouts:
+        v = T.PlatformLayout(T.Platform(x, y, ONE) for x, y in lay["supports"]).validate(T.World(T.WorldGrid(grid)), eng)
+        assert v.is_valid()
+
+
+def test_geodesic_not_manhattan(eng):
+    g = T.WorldGrid(rows_to_grid(["XXX XXX"]))
+    v = eng.validate(g, [T.Platform(0, 0, ONE)])
+    assert v.unsupported_terrain == {(4, 0), (5, 0), (6, 0)}
+    g = T.WorldGrid(rows_to_grid(["XXXXXXX"]))
+    assert eng.validate(g, [T.Platform(3, 0, ONE)]).is_valid() and not eng.validate(g, [T.Platform(2, 0, ONE)]).is_valid()
+
+
+def random_platforms(rng, w, h, n):
+    defs = [(1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (3, 3), (5, 5)]
+    out = []
+    for _ in range(n):
+        d = defs[rng.integers(len(defs))]
+        out.append((int(rng.integers(-2, w + 1)), int(rng.integers(-2, h + 1)), d[0], d[1], int(rng.integers(2))))
+    return list({(p[0], p[1]): p for p in out}.values())  # one platform per anchor, like the reference's HashMap
+
+
+@pytest.mark.parametrize("w,h", [(5, 6), (21, 16), (32, 32), (50, 20), (256, 256)])
+def test_validate_platform_layouts_match_oracle(eng, w, h):
+    rng = np.random.default_rng(w * 7 + h)
+    grid = synth_terrain(w, h, seed=2, density_q24=int(0.8 * (1 << 24)))
+    layouts = [random_platforms(rng, w, h, int(rng.integers(0, max(2, w * h // 30)))) for _ in range(8 if w * h < 5000 else 2)]
+    out = eng.eval_platforms(T.WorldGrid(grid), [[T.Platform(p[0], p[1], T.PlatformDef(p[2], p[3]), bool(p[4])) for p in l] for l in layouts])
+    for i, l in enumerate(layouts):
+        ref = O.validate(grid, l)
+        assert out[i].tolist() == [int(ref.unsupported.sum()), len(l), len(ref.overlapping), len(ref.out_of_bounds)], (w, h, i)
+        v = eng.validate(T.WorldGrid(grid), [T.Platform(p[0], p[1], T.PlatformDef(p[2], p[3]), bool(p[4])) for p in l])
+        assert {(x, y) for y, x in zip(*np.nonzero(ref.unsupported))} == v.unsupported_terrain
+        assert {tup(p) for p in v.overlapping_platforms} == set(ref.overlapping)
+        assert {tup(p) for p in v.out_of_bounds_platforms} == set(ref.out_of_bounds)
+
+
+def test_eval_full_size_properties(eng):
+    """C4 / C5 sizes: properties instead of the (slow) oracle — monotone in the support set, exact on the extremes,
+    and one random 256x256 layout cross-checked against the oracle."""
+    rng = np.random.default_rng(0)
+    grid = synth_terrain(256, 256, seed=1)
+    assert grid.sum() == 45811                                            # SURVEY.md §6 example draw
+    a = random_sites(rng, 3, 256, 256, 0.03)
+    b = a | random_sites(rng, 3, 256, 256, 0.03)
+    ua, _ = eng.eval_sites(T.WorldGrid(grid), a)
+    ub, cb = eng.eval_sites(T.WorldGrid(grid), b)
+    assert (ub <= ua).all() and (cb == b.reshape(3, -1).sum(1)).all()
+    u, _ = eng.eval_sites(T.WorldGrid(grid), np.stack([np.zeros_like(grid), grid]))
+    assert u.tolist() == [45811, 0]
+    o_unc, _, _ = O.validate_sites_batch(grid, a[:1])
+    assert o_unc[0] == ua[0]
+    # 4096 terrains of the C5 generator, supports on a 5-lattice: evaluated per terrain == oracle on a sample
+    terr = np.stack([synth_terrain(32, 32, seed=1, t=t) for t in range(64)])
+    lat = np.zeros((32, 32), np.uint8)
+    lat[2::5, 2::5] = 1
+    for t in (0, 17, 63):
+        u, c = eng.eval_sites(T.WorldGrid(terr[t]), lat[None])
+        o_u, o_c, _ = O.validate_sites_batch(terr[t], lat[None])
+        assert u[0] == o_u[0] and c[0] == o_c[0] == 36
+
+
+# =============================================================================== kernel (c): CNF check / propagate
+def py_unit_propagate(clauses, a):
+    a = a.copy()
+    changed = True
+    while changed:
+        changed = False
+        for cl in clauses:
+            vals = [(a[abs(l)] == (1 if l > 0 else 0)) if a[abs(l)] != 2 else None for l in cl]
+            if any(v is True for v in vals):
+                continue
+            un = [l for l, v in zip(cl, vals) if v is None]
+            if len(un) == 1:
+                a[abs(un[0])] = 1 if un[0] > 0 else 0
+                changed = True
+    conflict = -1
+    for i, cl in enumerate(clauses):
+        if all(a[abs(l)] != 2 and a[abs(l)] != (1 if l > 0 else 0) for l in cl):
+            conflict = i
+            break
+    return a, conflict
+
+
+@pytest.mark.parametrize("name,defs", [("ex1", "1x1"), ("ex3", "1x1"), ("ex1", "default"), ("ex3", "default")])
+def test_cnf_check_matches_oracle(eng, fixtures, name, defs):
+    d = T.PLATFORMS_DEFAULT[:1] if defs == "1x1" else T.PLATFORMS_DEFAULT
+    g = fixtures[name]
+    enc = T.Encoding.encode(d, T.WorldGrid(g))
+    cnf = enc.with_limits(T.PlatformLimits.new_unweighted({ONE: 5}))
+    ocnf = O.Encoding([x.dims() for x in d], g).with_limits({(1, 1): 5})
+    dev = eng.upload_cnf(cnf)
+    rng = np.random.default_rng(11)
+    a = rng.integers(0, 3, (70, cnf.n_vars + 1)).astype(np.uint8)   # False / True / DontCare
+    a[0] = 1
+    a[1] = 0
+    r, model, _ = ocnf.solve()
+    assert r == 10
+    a[2] = model
+    nf, first = dev.check(a)
+    for i in range(len(a)):
+        want = ocnf.count_falsified(a[i])
+        assert (int(nf[i]), int(first[i])) == want, i
+    assert nf[2] == 0 and first[2] == -1
+
+
+def test_cnf_propagate_matches_reference_semantics(eng, fixtures):
+    g = fixtures["ex1"]
+    enc = T.Encoding.encode(T.PLATFORMS_DEFAULT[:1], T.WorldGrid(g))
+    cnf = enc.with_limits(T.PlatformLimits.new_unweighted({ONE: 3}))
+    clauses = cnf.clauses()
+    dev = eng.upload_cnf(cnf)
+    rng = np.random.default_rng(2)
+    h, w = g.shape
+    batch = []
+    for i in range(40):
+        a = np.full(cnf.n_vars + 1, 2, np.uint8)
+        pv = enc.vars().plat_var[:, 0]
+        a[pv] = 0
+        k = int(rng.integers(0, 5))
+        a[rng.choice(pv, k, replace=False)] = 1          # platform vars fixed, everything else open
+        batch.append(a)
+    out, conflict, rounds = dev.propagate(np.stack(batch))
+    assert rounds >= 2
+    for i, a in enumerate(batch):
+        want, wc = py_unit_propagate(clauses, a)
+        assert (conflict[i] >= 0) == (wc >= 0), i
+        if wc < 0:
+            assert np.array_equal(out[i][1:], want[1:]), i
+        # validate(layout) <=> no UP conflict with platform vars fixed (and <= 3 platforms here)
+        plats = [(int(t % w), int(t // w), 1, 1, 0) for t in range(w * h) if a[enc.vars().plat_var[t, 0]] == 1]
+        ok = O.validate(g, plats).is_valid and len(plats) <= 3
+        assert ok == (conflict[i] < 0), i
+
+
+# =============================================================================== kernel (b): batched SLS
+KNOWN_OPTIMA = [("ex1", 3), ("ex3", 4), ("ex2", 14)]   # proven by the oracle's CDCL loop (tests/test_oracle.py) / SURVEY.md §6
+
+
+@pytest.mark.parametrize("name,optimum", KNOWN_OPTIMA)
+def test_sls_reaches_proven_optimum(eng, fixtures, name, optimum):
+    g = T.WorldGrid(fixtures[name])
+    res, layout = eng.solve_upper_bound(g, T.PLATFORMS_DEFAULT[:1], card_limit=optimum, seed=7, max_steps=200000)
+    assert res == T.SAT and layout.platform_count() == optimum
+    plats = [tup(p) for p in layout.platforms().values()]
+    assert O.validate(g.data, plats).is_valid                                    # the reference's coverage check
+    enc = T.Encoding.encode(T.PLATFORMS_DEFAULT[:1], g)
+    a = eng.layout_to_assignment(enc, layout)
+    ocnf = O.Encoding(O.PLATFORMS_1X1, g.data).cnf()
+    assert ocnf.count_falsified(a) == (0, -1)                                    # the reference encoder's CNF
+    assert eng.upload_cnf(enc.cnf()).check(a[None])[0][0] == 0                   # same, on the GPU (kernel c)
+    # one below the proven optimum nothing is ever reported (the GPU proves nothing, it just must not lie)
+    res, layout = eng.solve_upper_bound(g, T.PLATFORMS_DEFAULT[:1], card_limit=optimum - 1, seed=7, max_steps=3000)
+    assert res == T.INTERRUPTED and layout is None
+
+
+def test_sls_rect16_and_readme_terrain(eng, readme):
+    res, layout = eng.solve_upper_bound(T.WorldGrid(np.ones((16, 16))), card_limit=15, seed=1, max_steps=200000)
+    assert res == T.SAT and layout.platform_count() == 15                        # optimum 15, UNSAT <= 14
+    grid, _ = readme
+    res, layout = eng.solve_upper_bound(T.WorldGrid(grid), card_limit=14, seed=1, max_steps=200000)
+    assert res == T.SAT and layout.platform_count() == 14                        # one better than the README transcript reached
+
+
+@pytest.mark.parametrize("shape,seed", [((16, 16), 1), ((21, 16), 5), ((32, 32), 9), ((6, 5), 3)])
+def test_sls_trajectories_bit_exact_vs_model(eng, fixtures, shape, seed):
+    """The kernel and the scalar CPU model (oracle/sls_model.cpp) execute the same published step rule with the same
+    counter-based RNG: every chain's supports, best layout, counters and step count agree bit for bit across epochs."""
+    w, h = shape
+    grid = {(16, 16): np.ones((16, 16), np.uint8), (21, 16): fixtures["ex2"], (6, 5): fixtures["ex1"].T.copy()}.get(shape)
+    if grid is None:
+        grid = synth_terrain(32, 32, seed=1, t=4)
+    n_chains, offset = 24, 100
+    epochs = [(50, 1 << 20, 0), (300, 1 << 20, 0), (1000, 1 << 20, 0)]
+    s = eng.search(T.WorldGrid(grid), seed=seed, n_chains=n_chains, chain_offset=offset)
+    for steps, _, target in epochs:
+        s.run(steps, target)
+    got = s.read_chains()
+    want = O.sls_model(grid, n_chains, epochs, seed=seed, chain_offset=offset, share_bound=True)
+    unpack = lambda rows: ((rows[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8)
+    assert np.array_equal(got["k"], want["k"])
+    assert np.array_equal(got["best"], want["best"])
+    assert np.array_equal(got["step"], want["step"])
+    assert np.array_equal(got["scored"], want["scored"])
+    assert np.array_equal(unpack(got["S"]), want["S"])
+    assert np.array_equal(unpack(got["bestS"]), want["bestS"])
+    assert s.best_count() == int(want["best"].min())
+    s.close()
+
+
+def test_sls_bound_sharing_and_determinism(eng):
+    g = T.WorldGrid(np.ones((16, 16)))
+    runs = []
+    for _ in range(2):
+        s = eng.search(g, seed=3, n_chains=64)
+        s.set_bound(17)                       # externally known bound (the all-reduce-min of a portfolio)
+        s.run(400, 0)
+        runs.append((s.best_count(), s.read_chains()))
+        s.close()
+    assert runs[0][0] == runs[1][0] and runs[0][0] is not None and runs[0][0] <= 16
+    assert np.array_equal(runs[0][1]["S"], runs[1][1]["S"]) and np.array_equal(runs[0][1]["best"], runs[1][1]["best"])
+    assert (runs[0][1]["best"][runs[0][1]["best"] < (1 << 20)] <= 16).all()       # nobody reports a layout >= the bound
+
+
+def test_solve_batch_terrains(eng):
+    """C5 shape (scaled down): per-terrain counts are complete layouts, never below the trivial lower bound, and
+    agree with the oracle's proven optimum where that is cheap to prove."""
+    n = 96
+    grids = np.stack([synth_terrain(32, 32, seed=1, t=t) for t in range(n)])
+    counts, layouts = eng.solve_batch(grids, seed=1, steps=3000, want_layouts=True)
+    assert (counts > 0).all()
+    sites = ((layouts[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8)
+    for t in range(0, n, 7):
+        unc, cnt, _ = O.validate_sites_batch(grids[t], sites[t][None])
+        assert unc[0] == 0 and cnt[0] == counts[t]
+        assert counts[t] >= -(-int(grids[t].sum()) // 25)
+    small = np.stack([synth_terrain(8, 8, seed=3, t=t) for t in range(12)])
+    c2 = eng.solve_batch(small, seed=1, steps=2000)
+    for t in range(12):
+        r = O.solver_loop(small[t], O.PLATFORMS_1X1)
+        assert r["proved_optimal"] and c2[t] == len(r["best"]), t
+
+
+def test_solver_loop_gpu_then_exact_proof(eng, fixtures):
+    """crates/repl/src/main.rs:280-366 with the GPU as the SAT side and the oracle's CDCL as the Glucose stand-in:
+    the loop ends with UNSAT one below the GPU's count, i.e. the GPU reached the proven optimum."""
+    def exact(cnf):
+        import ctypes as C
+        a = np.full(cnf.n_vars + 1, 2, np.uint8)
+        clauses = [list(map(int, c)) for c in cnf.clauses()]
+        h = O.lib()
+        # route the product's CNF through the oracle's solver entry (DIMACS arrays in, model out)
+        from oracle.oracle import _p
+        lits = np.ascontiguousarray(cnf.lits, np.int32)
+        offs = np.ascontiguousarray(cnf.offsets, np.uint32)
+        h.tsso_solve_csr.restype = C.c_int
+        r = h.tsso_solve_csr(_p(lits), _p(offs, C.c_uint32), cnf.n_clauses, cnf.n_vars, _p(a, C.c_uint8), C.c_long(-1))
+        return {10: T.SAT, 20: T.UNSAT}.get(r, T.INTERRUPTED), a
+
+    for name, optimum in KNOWN_OPTIMA[:2]:
+        g = T.WorldGrid(fixtures[name])
+        proj = T.Project(T.World(g))
+        enc = T.Encoding.encode(T.PLATFORMS_DEFAULT[:1], g)
+        out = T.solver_loop(proj, enc, T.PlatformLimits(), eng, exact_solver=exact, seed=1, budget_ms=0)
+        assert out["proved_optimal"] and out["best"].platform_count() == optimum
+        assert all(s["valid"] for s in out["steps"] if s["result"] == T.SAT)
+        assert out["steps"][-1]["result"] == T.UNSAT and out["steps"][-1]["source"] == "exact"
+        assert [s["source"] for s in out["steps"][:-1]] == ["gpu"] * (len(out["steps"]) - 1)
+
+
+def test_interrupt_returns_unknown(eng):
+    g = T.WorldGrid(np.ones((16, 16)))
+    eng.interrupt()
+    res, layout = eng.solve_upper_bound(g, card_limit=14, seed=1, budget_ms=2000)
+    eng.clear_interrupt()
+    assert res == T.INTERRUPTED and eng.stats()["interrupted"] == 1
+
+
+def test_errors_and_edge_cases(eng):
+    with pytest.raises(T.TssError) as e:
+        eng.search(T.WorldGrid(np.ones((4, 4))), defs=[T.PlatformDef(3, 3)])
+    assert e.value.code == -1                                                    # no 1x1 in the platform set
+    res, layout = eng.solve_upper_bound(T.WorldGrid(np.zeros((5, 5))), seed=1, max_steps=100)
+    assert res == T.SAT and layout.platform_count() == 0                         # no ceiling: the empty layout
+    res, layout = eng.solve_upper_bound(T.WorldGrid(rows_to_grid(["X X X X"])), seed=1, max_steps=1000)
+    assert res == T.SAT and layout.platform_count() == 4                         # isolated tiles need one support each
+    unc, cnt = eng.eval_sites(T.WorldGrid(np.ones((3, 3))), np.zeros((0, 3, 3), np.uint8))
+    assert len(unc) == 0
+
+
+def test_measured_peaks_sane(eng):
+    p = eng.measure_peaks()
+    sm = eng.device_info()["sm_count"]
+    assert 500 < p["sm_mhz"] < 2500
+    # LOP3: at most 64 lanes/clk/SM (alu pipe, 16 lanes per SMSP) .. allow the 128-lane case too
+    assert 0.2 * 64 * sm * p["sm_mhz"] / 1e3 < p["lop3_gops"] < 1.1 * 128 * sm * p["sm_mhz"] / 1e3
+    assert p["popc_gops"] > 0 and p["shfl_gops"] > 0 and p["smem_gbs"] > 1000

@@ -1,0 +1,172 @@
+"""CPU-side tests of the product's host logic (no GPU): the C-ABI library loads and exports every symbol
+include/tss.h declares, and its host-side mirror of the reference interface agrees with the oracle."""
+import ctypes as C
+import os
+import re
+from collections import Counter
+
+import numpy as np
+import pytest
+
+import oracle.oracle as O
+import timberborn_support_solver_b200 as T
+from conftest import ROOT, golden, rows_to_grid, synth_terrain
+
+ONE = T.PlatformDef(1, 1)
+
+
+def o_defs(defs):
+    return [d.dims() for d in defs]
+
+
+def canon(clauses):
+    return Counter(tuple(sorted(c)) for c in clauses)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "tss.h")).read()
+    declared = set(re.findall(r"\b(tss_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(T.SIGNATURES), declared ^ set(T.SIGNATURES)
+    lib = C.CDLL(T.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.tss_version() == 100
+
+
+def test_engine_needs_a_gpu_no_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(T.TssError) as e:
+        T.Engine()
+    assert e.value.code == -3  # TSS_E_CUDA
+
+
+def test_sls_spec_constants_agree_with_model():
+    spec = open(os.path.join(ROOT, "timberborn_support_solver_b200", "csrc", "sls_spec.hpp")).read()
+    out = (C.c_uint32 * 9)()
+    O.lib().tsso_sls_constants(out)
+    want = {"K1": out[0], "K2": out[1], "SALT_ROW": out[2], "SALT_COL": out[3], "SALT_NOISE": out[4], "SALT_PICK": out[5],
+            "SALT_REMOVE": out[6], "SALT_ADD": out[7]}
+    for name, val in want.items():
+        m = re.search(rf"\b{name} = (0x[0-9A-Fa-f]+|\d+)", spec)
+        assert m and int(m.group(1), 0) == val, name
+    assert "NO_BOUND = 1 << 20" in spec and out[8] == 1 << 20
+
+
+# ---- world -----------------------------------------------------------------------------------------
+def test_world_parse_matches_oracle(fixtures):
+    for name in ("ex1", "ex2", "ex3"):
+        text = O.world_to_toml(fixtures[name])
+        g = T.WorldGrid.from_toml(text)
+        assert np.array_equal(g.data, fixtures[name]) and not g.ragged
+        assert g.to_toml() == text
+    g = T.WorldGrid.from_toml('[world]\ngrid = ["XX", "X", ""]\n')
+    assert g.ragged and g.data.tolist() == [[1, 1], [1, 0], [0, 0]]
+
+
+@pytest.mark.parametrize("text,msg", [
+    ('[world]\ngrid = ["X.X"]\n', "expected `X` or ` `"),   # world.rs:58
+    ("[world]\ngrid = []\n", "invalid length 0"),             # world.rs:63-65
+    ("[world]\n", "missing field"),
+    ('[world]\ngrid = ["XX"\n', "unterminated"),
+])
+def test_world_errors(text, msg):
+    with pytest.raises(T.TssError, match=re.escape(msg)) as e:
+        T.WorldGrid.from_toml(text)
+    assert e.value.code == -5
+    with pytest.raises(O.WorldParseError):
+        O.parse_world(text)
+
+
+def test_synthetic_terrain_generator():
+    """the host generator and the numpy one in conftest produce identical grids."""
+    for (w, h, seed, t) in [(32, 32, 1, 0), (32, 32, 1, 99999), (256, 256, 1, 0), (16, 16, 7, 3)]:
+        assert np.array_equal(T.WorldGrid.synthetic(w, h, seed, t).data, synth_terrain(w, h, seed, t))
+    d = T.WorldGrid.synthetic(256, 256, 1, 0).data.mean()
+    assert 0.69 < d < 0.71
+
+
+# ---- platform ----------------------------------------------------------------------------------------
+def test_platform_overlap_tables():
+    g = golden("platform_overlap")
+    mk = lambda r: T.Platform(r[0], r[1], T.PlatformDef(r[2], r[3]), bool(r[4]))
+    for a, b in g["overlap_yes"]:
+        assert mk(a).overlaps(mk(b)) and mk(b).overlaps(mk(a))
+    for a, b in g["overlap_no"]:
+        assert not mk(a).overlaps(mk(b)) and not mk(b).overlaps(mk(a))
+    assert T.Platform(0, 0, T.PlatformDef(1, 4), True).dims() == (4, 1)
+
+
+# ---- encoder -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["ex1", "ex2", "ex3"])
+@pytest.mark.parametrize("defs", [T.PLATFORMS_DEFAULT[:1], T.PLATFORMS_DEFAULT], ids=["1x1", "default8"])
+def test_encoder_matches_oracle(fixtures, name, defs):
+    g = fixtures[name]
+    enc = T.Encoding.encode(defs, T.WorldGrid(g))
+    ref = O.Encoding(o_defs(defs), g)
+    ocnf = ref.cnf()
+    assert (enc.n_vars, enc.n_clauses, enc.n_lits) == (ocnf.n_vars, ocnf.n_clauses, ocnf.n_lits)
+    assert enc.vars().dims == ref.dims
+    assert np.array_equal(enc.vars().plat_var, ref.plat_var) and np.array_equal(enc.vars().terr_var, ref.terr_var)
+    assert canon(enc.cnf().clauses()) == canon(ocnf.clauses())
+
+
+def test_encoder_random_terrains_and_platform_sets():
+    rng = np.random.default_rng(5)
+    sets = [[(1, 1)], [(1, 1), (2, 2)], [(1, 1), (1, 3), (2, 2)], [(1, 1), (2, 3), (3, 3)], [(1, 1), (1, 2), (1, 3), (3, 3), (5, 5)]]
+    for i in range(10):
+        w, h = int(rng.integers(1, 12)), int(rng.integers(1, 12))
+        g = (rng.random((h, w)) < 0.7).astype(np.uint8)
+        defs = sets[i % len(sets)]
+        enc = T.Encoding.encode([T.PlatformDef(*d) for d in defs], T.WorldGrid(g))
+        ref = O.Encoding(defs, g).cnf()
+        assert canon(enc.cnf().clauses()) == canon(ref.clauses()), (w, h, defs)
+
+
+def test_encoder_rejects_missing_1x1():
+    with pytest.raises(T.TssError):
+        T.Encoding.encode([T.PlatformDef(3, 3)], T.WorldGrid(np.ones((4, 4))))
+
+
+def test_with_limits_matches_oracle(fixtures):
+    g = fixtures["ex3"]
+    enc = T.Encoding.encode(T.PLATFORMS_DEFAULT, T.WorldGrid(g))
+    ref = O.Encoding(O.PLATFORMS_DEFAULT, g)
+    weights = {(1, 1): 5, (1, 2): 1, (1, 3): 1, (1, 4): 1, (1, 5): 1, (1, 6): 1, (3, 3): 2, (5, 5): 4}   # crates/gui/src/app.rs:53-62
+    for card, wl in [({(1, 1): 4}, None), ({(1, 1): 0}, None), ({(1, 1): 10, (1, 4): 2, (5, 5): 1}, None), ({}, 20), ({(1, 1): 3}, 12)]:
+        lim = T.PlatformLimits({T.PlatformDef(*k): v for k, v in card.items()}, {T.PlatformDef(*k): v for k, v in weights.items()} if wl else {}, wl)
+        mine = enc.with_limits(lim)
+        theirs = ref.with_limits(card, weights if wl else None, wl)
+        assert mine.n_vars == theirs.n_vars and canon(mine.clauses()) == canon(theirs.clauses()), (card, wl)
+
+
+# ---- layout decode -------------------------------------------------------------------------------------
+def test_layout_from_assignment_matches_oracle(fixtures):
+    g = fixtures["ex2"]
+    enc = T.Encoding.encode(T.PLATFORMS_DEFAULT, T.WorldGrid(g))
+    ref = O.Encoding(O.PLATFORMS_DEFAULT, g)
+    r, a, _ = ref.with_limits({(1, 1): 6}).solve()
+    assert r == 10
+    mine = T.PlatformLayout.from_assignment(a[: enc.n_vars + 1], enc)
+    theirs = ref.layout_from_assignment(a)
+    got = sorted((p.x, p.y, p.definition.width, p.definition.height, int(p.rotated)) for p in mine.platforms().values())
+    assert got == sorted(theirs) and mine.platform_count() <= 6
+    rng = np.random.default_rng(1)  # arbitrary (even unsound) assignments decode identically: largest def per anchor wins
+    for _ in range(5):
+        a = (rng.random(enc.n_vars + 1) < 0.02).astype(np.uint8)
+        a[rng.integers(1, enc.n_vars, 20)] = 2
+        got = sorted((p.x, p.y, p.definition.width, p.definition.height, int(p.rotated)) for p in T.PlatformLayout.from_assignment(a, enc).platforms().values())
+        assert got == sorted(ref.layout_from_assignment(a))
+
+
+def test_trivial_optimization_and_total_weight(fixtures):
+    w = T.World(T.WorldGrid(fixtures["ex1"]))
+    lay = T.PlatformLayout([T.Platform(0, 0, T.PlatformDef(5, 5)), T.Platform(3, 5, ONE), T.Platform(2, 3, ONE)])
+    lay.run_trivial_optimization(w)
+    assert list(lay.platforms().values()) == [T.Platform(0, 0, T.PlatformDef(5, 5))]
+    weights = {T.PlatformDef(*k): v for k, v in {(1, 1): 5, (1, 2): 1, (1, 3): 1, (1, 4): 1, (1, 5): 1, (1, 6): 1, (3, 3): 2, (5, 5): 4}.items()}
+    for plats in ([(0, 0, 5, 5, 0)], [(0, 0, 1, 6, 1)], [(0, 0, 3, 3, 0), (4, 4, 1, 1, 0)], [(1, 1, 1, 4, 0), (0, 0, 1, 2, 1)]):
+        lay = T.PlatformLayout(T.Platform(x, y, T.PlatformDef(dw, dh), bool(r)) for x, y, dw, dh, r in plats)
+        assert lay.total_weight(weights) == O.total_weight(plats, {k.dims(): v for k, v in weights.items()})
+    assert T.PlatformLayout([T.Platform(0, 0, ONE), T.Platform(1, 0, ONE)]).platform_stats() == {ONE: 2}

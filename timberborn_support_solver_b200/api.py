@@ -1,0 +1,620 @@
+"""Host-side mirror of the reference's interface for the feasibility-and-bound path, over the C ABI of libtss.
+
+Names, argument meaning and error behaviour follow the reference lib crate and its two drivers:
+  World / WorldGrid / Project           src/world.rs:13-19,96-103, src/lib.rs:15-17
+  PlatformDef / Platform                src/platform.rs:11-32,64-118
+  Encoding.encode / with_limits / vars  src/encoder.rs:435,615,619
+  PlatformLimits                        src/encoder/platform_limits.rs:6-26
+  PlatformLayout.*                      src/encoder/platform_layout.rs:26-183  (validate runs on the GPU: kernel (a))
+  GpuBoundSolver                        the `Solve + Interrupt + SolveStats` shape the drivers are generic over
+                                        (crates/repl/src/solver_runner.rs:8-20, crates/gui/src/solver_backend.rs:69-97)
+  solver_loop                           crates/repl/src/main.rs:280-366
+Everything that computes goes through libtss (ctypes); nothing here imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Callable, Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import Dims as _Dims
+from ._lib import Platform as _Platform
+
+SAT, UNSAT, INTERRUPTED = "Sat", "Unsat", "Interrupted"  # rustsat SolverResult
+
+
+class TssError(RuntimeError):
+    def __init__(self, code: int, message: str = ""):
+        self.code = code
+        super().__init__(f"{_lib.ERROR_NAMES.get(code, code)}: {message}" if message else str(_lib.ERROR_NAMES.get(code, code)))
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+# ------------------------------------------------------------------------------------------------- domain types
+@dataclass(frozen=True, order=True)
+class PlatformDef:
+    """src/platform.rs:11-15; dims are canonical (width <= height as in PLATFORMS_DEFAULT)."""
+    width: int
+    height: int
+
+    def dims(self):
+        return (self.width, self.height)
+
+    def dimensions_str(self) -> str:
+        return f"{self.width}x{self.height}"
+
+    def rectangular(self) -> bool:  # platform.rs:51-53
+        return self.width != self.height
+
+
+PLATFORMS_DEFAULT = tuple(PlatformDef(w, h) for w, h in [(1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (3, 3), (5, 5)])
+
+
+@dataclass(frozen=True, order=True)
+class Platform:
+    """src/platform.rs:64-70: anchor point (min corner), def, rotated."""
+    x: int
+    y: int
+    definition: PlatformDef
+    rotated: bool = False
+
+    def point(self):
+        return (self.x, self.y)
+
+    def dims(self):  # platform.rs:111-113
+        return (self.definition.height, self.definition.width) if self.rotated else self.definition.dims()
+
+    def _c(self) -> _Platform:
+        return _Platform(self.x, self.y, self.definition.width, self.definition.height, int(self.rotated))
+
+    def overlaps(self, other: "Platform") -> bool:  # platform.rs:86-97
+        a, b = self._c(), other._c()
+        return bool(_lib.load().tss_platform_overlaps(C.byref(a), C.byref(b)))
+
+    @staticmethod
+    def _from_c(p: _Platform) -> "Platform":
+        return Platform(p.x, p.y, PlatformDef(p.def_w, p.def_h), bool(p.rotated))
+
+
+def _plat_array(platforms: Sequence[Platform]):
+    arr = (_Platform * max(len(platforms), 1))()
+    for i, p in enumerate(platforms):
+        arr[i] = p._c()
+    return arr
+
+
+def _defs_array(defs: Sequence[PlatformDef]):
+    arr = (_Dims * max(len(defs), 1))()
+    for i, d in enumerate(defs):
+        arr[i] = _Dims(d.width, d.height)
+    return arr
+
+
+class WorldGrid:
+    """src/world.rs:19 — Grid<bool>, row-major, index x + y*width (src/math/grid.rs:66-68)."""
+
+    def __init__(self, data):
+        self.data = _u8(np.asarray(data) != 0)
+        if self.data.ndim != 2 or self.data.size == 0:
+            raise ValueError("WorldGrid needs a non-empty 2-D array")
+
+    @property
+    def width(self):
+        return self.data.shape[1]
+
+    @property
+    def height(self):
+        return self.data.shape[0]
+
+    def dims(self):
+        return (self.width, self.height)
+
+    def get(self, x, y):
+        return bool(self.data[y, x]) if 0 <= x < self.width and 0 <= y < self.height else None
+
+    @staticmethod
+    def from_toml(text: str) -> "WorldGrid":
+        """world.rs:49-79: rows of `X` / space; any other character or an empty array is an error."""
+        lib = _lib.load()
+        buf = np.zeros(max(len(text), 16), np.uint8)
+        w, h, rg = C.c_int32(), C.c_int32(), C.c_int32()
+        err = C.create_string_buffer(256)
+        rc = lib.tss_world_parse_toml(text.encode(), _ptr(buf, C.c_uint8), buf.size, C.byref(w), C.byref(h), C.byref(rg), err, 256)
+        if rc != 0:
+            raise TssError(rc, err.value.decode())
+        g = WorldGrid(buf[: w.value * h.value].reshape(h.value, w.value))
+        g.ragged = bool(rg.value)
+        return g
+
+    def to_toml(self) -> str:
+        buf = C.create_string_buffer(self.data.size + 16 * self.height + 64)
+        n = _lib.load().tss_world_to_toml(_ptr(self.data, C.c_uint8), self.width, self.height, buf, len(buf))
+        if n < 0:
+            raise TssError(n)
+        return buf.value.decode()
+
+    @staticmethod
+    def synthetic(w: int, h: int, seed: int = 1, t: int = 0, density: float = 0.7) -> "WorldGrid":
+        """SURVEY.md §8(d) generator shared by host, CUDA and tests."""
+        g = np.zeros((h, w), np.uint8)
+        _lib.load().tss_world_synthetic(w, h, seed, t, int(density * (1 << 24)), _ptr(g, C.c_uint8))
+        return WorldGrid(g)
+
+
+@dataclass
+class World:  # src/world.rs:13-16,96-103
+    _grid: WorldGrid
+
+    def grid(self) -> WorldGrid:
+        return self._grid
+
+
+@dataclass
+class Project:  # src/lib.rs:15-17, crates/repl/src/main.rs:272-278
+    world: World
+
+    @staticmethod
+    def load(path: str) -> "Project":
+        with open(path, "r", encoding="utf-8") as f:
+            return Project(World(WorldGrid.from_toml(f.read())))
+
+
+@dataclass
+class PlatformLimits:  # src/encoder/platform_limits.rs:6-13
+    card_limits: dict = field(default_factory=dict)   # PlatformDef -> usize
+    weights: dict = field(default_factory=dict)       # PlatformDef -> isize
+    weight_limit: Optional[int] = None
+
+    @staticmethod
+    def new_unweighted(limits: dict) -> "PlatformLimits":
+        return PlatformLimits(dict(limits), {}, None)
+
+
+@dataclass
+class Cnf:
+    """rustsat Cnf after SatInstance::into_cnf(): CSR clauses, DIMACS-signed literals."""
+    n_vars: int
+    lits: np.ndarray      # int32
+    offsets: np.ndarray   # uint32 [n_clauses + 1]
+
+    @property
+    def n_clauses(self):
+        return len(self.offsets) - 1
+
+    def clauses(self):
+        o = self.offsets
+        return [tuple(int(x) for x in self.lits[o[i]: o[i + 1]]) for i in range(self.n_clauses)]
+
+
+class EncodingVars:
+    """src/encoder.rs:175-279 — explicit var maps instead of hash-order numbering."""
+
+    def __init__(self, dims, plat_var, terr_var, width, height):
+        self.dims, self.plat_var, self.terr_var, self.width, self.height = dims, plat_var, terr_var, width, height
+
+    def for_dims_at(self, x, y, dims):
+        return int(self.plat_var[y * self.width + x, self.dims.index(tuple(dims))])
+
+    def terrain_at(self, x, y):
+        t = self.terr_var[y * self.width + x]
+        return None if t[0] == 0 else [int(v) for v in t]
+
+
+class Encoding:
+    """src/encoder.rs:428-667."""
+
+    def __init__(self, handle, grid: WorldGrid, defs):
+        self._h, self._grid, self.defs = handle, grid, tuple(defs)
+        lib = _lib.load()
+        nv, nc, nl, nd = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int32()
+        lib.tss_encoding_sizes(self._h, C.byref(nv), C.byref(nc), C.byref(nl), C.byref(nd))
+        self.n_vars, self.n_clauses, self.n_lits, K = nv.value, nc.value, nl.value, nd.value
+        dims = (_Dims * K)()
+        lib.tss_encoding_dims(self._h, dims)
+        plat = np.zeros((grid.data.size, K), np.int32)
+        terr = np.zeros((grid.data.size, 4), np.int32)
+        lib.tss_encoding_var_maps(self._h, _ptr(plat, C.c_int32), _ptr(terr, C.c_int32))
+        self._vars = EncodingVars([(d.w, d.h) for d in dims], plat, terr, grid.width, grid.height)
+
+    @staticmethod
+    def encode(platform_defs: Iterable[PlatformDef], terrain: WorldGrid) -> "Encoding":
+        defs = list(platform_defs)
+        h = C.c_void_p()
+        rc = _lib.load().tss_encoding_create(_ptr(terrain.data, C.c_uint8), terrain.width, terrain.height, _defs_array(defs), len(defs), C.byref(h))
+        if rc != 0:
+            raise TssError(rc, "Encoding::encode rejected its input (the platform set must contain 1x1; src/encoder.rs:564-566)")
+        return Encoding(h, terrain, defs)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lib.load().tss_encoding_destroy(self._h)
+            self._h = None
+
+    def vars(self) -> EncodingVars:
+        return self._vars
+
+    def cnf(self) -> Cnf:
+        lits = np.zeros(max(self.n_lits, 1), np.int32)
+        offsets = np.zeros(self.n_clauses + 1, np.uint32)
+        _lib.load().tss_encoding_cnf(self._h, _ptr(lits, C.c_int32), _ptr(offsets, C.c_uint32))
+        return Cnf(self.n_vars, lits[: self.n_lits], offsets)
+
+    def with_limits(self, limits: PlatformLimits) -> Cnf:
+        """encoder.rs:619-667 followed by into_cnf() (crates/repl/src/main.rs:292-293)."""
+        card = np.array([[d.width, d.height, v] for d, v in limits.card_limits.items()], np.int32).reshape(-1, 3)
+        wts = np.array([[d.width, d.height, v] for d, v in limits.weights.items()], np.int32).reshape(-1, 3)
+        lib = _lib.load()
+        args = (self._h, _ptr(card, C.c_int32), len(card), _ptr(wts, C.c_int32), len(wts), int(limits.weight_limit is not None),
+                int(limits.weight_limit or 0))
+        nv, nc, nl = C.c_int32(), C.c_int32(), C.c_int64()
+        rc = lib.tss_encoding_with_limits(*args, C.byref(nv), C.byref(nc), C.byref(nl), None, None)
+        if rc != 0:
+            raise TssError(rc)
+        lits = np.zeros(max(nl.value, 1), np.int32)
+        offsets = np.zeros(nc.value + 1, np.uint32)
+        lib.tss_encoding_with_limits(*args, None, None, None, _ptr(lits, C.c_int32), _ptr(offsets, C.c_uint32))
+        return Cnf(nv.value, lits[: nl.value], offsets)
+
+
+@dataclass
+class ValidationResult:  # src/encoder/platform_layout.rs:187-191
+    unsupported_terrain: set
+    overlapping_platforms: set
+    out_of_bounds_platforms: set
+
+    def is_valid(self) -> bool:
+        return not (self.unsupported_terrain or self.overlapping_platforms or self.out_of_bounds_platforms)
+
+
+class PlatformLayout:
+    """src/encoder/platform_layout.rs:20-183."""
+
+    def __init__(self, platforms: Iterable[Platform] = ()):
+        self._platforms = {p.point(): p for p in platforms}
+
+    @staticmethod
+    def from_assignment(assignment, encoding: Encoding) -> "PlatformLayout":
+        a = _u8(assignment)
+        out = (_Platform * (encoding._grid.data.size + 1))()
+        n = C.c_int32()
+        rc = _lib.load().tss_layout_from_assignment(encoding._h, _ptr(a, C.c_uint8), len(a), out, len(out), C.byref(n))
+        if rc != 0:
+            raise TssError(rc)
+        return PlatformLayout(Platform._from_c(out[i]) for i in range(n.value))
+
+    def platforms(self):
+        return self._platforms
+
+    def platform_count(self) -> int:
+        return len(self._platforms)
+
+    def platform_stats(self) -> dict:
+        out: dict = {}
+        for p in self._platforms.values():
+            out[p.definition] = out.get(p.definition, 0) + 1
+        return out
+
+    def get_platform(self, point):
+        return self._platforms.get(tuple(point))
+
+    def validate(self, world: World, engine: "Engine") -> ValidationResult:
+        """platform_layout.rs:85-149 — computed by the coverage kernel (a)."""
+        return engine.validate(world.grid(), list(self._platforms.values()))
+
+    def run_trivial_optimization(self, world: World) -> None:
+        g = world.grid()
+        plats = list(self._platforms.values())
+        arr = _plat_array(plats)
+        n = _lib.load().tss_layout_trivial_optimization(_ptr(g.data, C.c_uint8), g.width, g.height, arr, len(plats))
+        if n < 0:
+            raise TssError(n)
+        self._platforms = {(arr[i].x, arr[i].y): Platform._from_c(arr[i]) for i in range(n)}
+
+    def total_weight(self, weights: dict) -> int:
+        plats = list(self._platforms.values())
+        wts = np.array([[d.width, d.height, v] for d, v in weights.items()], np.int32).reshape(-1, 3)
+        return int(_lib.load().tss_layout_total_weight(_plat_array(plats), len(plats), _ptr(wts, C.c_int32), len(wts)))
+
+
+# ------------------------------------------------------------------------------------------------- engine
+class DeviceCnf:
+    def __init__(self, engine: "Engine", cnf: Cnf):
+        self.engine, self.cnf = engine, cnf
+        self._h = C.c_void_p()
+        lits = np.ascontiguousarray(cnf.lits, np.int32)
+        offs = np.ascontiguousarray(cnf.offsets, np.uint32)
+        engine._check(engine.lib.tss_cnf_upload(engine._h, _ptr(lits, C.c_int32), _ptr(offs, C.c_uint32), cnf.n_clauses, cnf.n_vars, C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self.engine._h:
+            self.engine.lib.tss_cnf_destroy(self._h)
+            self._h = None
+
+    def check(self, assignments):
+        """-> (n_falsified int32[n], first_falsified int32[n])"""
+        a = _u8(assignments).reshape(-1, self.cnf.n_vars + 1)
+        nf = np.zeros(len(a), np.int32)
+        first = np.zeros(len(a), np.int32)
+        e = self.engine
+        e._check(e.lib.tss_cnf_check(e._h, self._h, _ptr(a, C.c_uint8), len(a), _ptr(nf, C.c_int32), _ptr(first, C.c_int32)))
+        return nf, first
+
+    def propagate(self, assignments):
+        """Unit propagation to fixpoint -> (assignments uint8[n, n_vars+1], conflict int32[n], rounds)"""
+        a = _u8(assignments).reshape(-1, self.cnf.n_vars + 1).copy()
+        conflict = np.zeros(len(a), np.int32)
+        rounds = C.c_int32()
+        e = self.engine
+        e._check(e.lib.tss_cnf_propagate(e._h, self._h, _ptr(a, C.c_uint8), len(a), _ptr(conflict, C.c_int32), C.byref(rounds)))
+        return a, conflict, rounds.value
+
+
+class Search:
+    """A device-resident SLS portfolio on one terrain (kernel (b))."""
+
+    def __init__(self, engine: "Engine", grid: WorldGrid, defs=PLATFORMS_DEFAULT[:1], seed=0, n_chains=0, chain_offset=0, noise_pct=-1):
+        self.engine, self.grid = engine, grid
+        self._h = C.c_void_p()
+        params = _lib.SearchParams(seed, n_chains, chain_offset, noise_pct, 0)
+        defs = list(defs)
+        engine._check(engine.lib.tss_search_create(engine._h, _ptr(grid.data, C.c_uint8), grid.width, grid.height, _defs_array(defs), len(defs),
+                                                   C.byref(params), C.byref(self._h)))
+        self.n_chains = engine.lib.tss_search_n_chains(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) and self.engine._h:
+            self.engine.lib.tss_search_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def run(self, steps: int, target_count: int = 0):
+        """One epoch: `steps` SLS steps per chain, asynchronous on the engine stream."""
+        self.engine._check(self.engine.lib.tss_search_run(self._h, steps, target_count))
+
+    def best_count(self) -> Optional[int]:
+        c = C.c_int32()
+        self.engine._check(self.engine.lib.tss_search_best_count(self._h, C.byref(c)))
+        return None if c.value < 0 else c.value
+
+    def set_bound(self, count: int):
+        self.engine._check(self.engine.lib.tss_search_set_bound(self._h, count))
+
+    def read_chains(self) -> dict:
+        """Per-chain state after the last epoch (parity tests replay it on the CPU model)."""
+        n = self.n_chains
+        S, bestS = np.zeros((n, 32), np.uint32), np.zeros((n, 32), np.uint32)
+        k, best = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        step, scored = np.zeros(n, np.uint32), np.zeros(n, np.uint64)
+        self.engine._check(self.engine.lib.tss_search_read_chains(self._h, _ptr(S, C.c_uint32), _ptr(bestS, C.c_uint32), _ptr(k, C.c_int32),
+                                                                   _ptr(best, C.c_int32), _ptr(step, C.c_uint32), _ptr(scored, C.c_uint64)))
+        return dict(S=S, bestS=bestS, k=k, best=best, step=step, scored=scored)
+
+    def best_layout(self) -> PlatformLayout:
+        out = (_Platform * (self.grid.data.size + 1))()
+        n = C.c_int32()
+        self.engine._check(self.engine.lib.tss_search_best_layout(self._h, out, len(out), C.byref(n)))
+        return PlatformLayout(Platform._from_c(out[i]) for i in range(n.value))
+
+
+class Engine:
+    """One tss_engine: a GPU, a stream, scratch memory, an interrupt flag."""
+
+    def __init__(self, device: int = -1):
+        self.lib = _lib.load()
+        self._h = C.c_void_p()
+        rc = self.lib.tss_engine_create(device, C.byref(self._h))
+        if rc != 0:
+            self._h = None
+            raise TssError(rc, "no usable CUDA device (the GPU path has no CPU fallback)")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.tss_engine_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise TssError(rc, self.lib.tss_last_error(self._h).decode())
+        return rc
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.tss_engine_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def interrupt(self):
+        self.lib.tss_interrupt(self._h)
+
+    def clear_interrupt(self):
+        self.lib.tss_clear_interrupt(self._h)
+
+    def stats(self) -> dict:
+        s = _lib.Stats()
+        self.lib.tss_get_stats(self._h, C.byref(s))
+        return {k: getattr(s, k) for k, _ in _lib.Stats._fields_}
+
+    def device_info(self) -> dict:
+        name = C.create_string_buffer(128)
+        sm, khz = C.c_int(), C.c_int()
+        self.lib.tss_device_info(self._h, name, 128, C.byref(sm), C.byref(khz))
+        return dict(name=name.value.decode(), sm_count=sm.value, clock_khz=khz.value)
+
+    # ---- kernel (a)
+    def validate(self, grid: WorldGrid, platforms: Sequence[Platform]) -> ValidationResult:
+        uns = np.zeros((grid.height, grid.width), np.uint8)
+        flags = np.zeros(max(len(platforms), 1), np.uint8)
+        self._check(self.lib.tss_validate(self._h, _ptr(grid.data, C.c_uint8), grid.width, grid.height, _plat_array(platforms), len(platforms),
+                                          _ptr(uns, C.c_uint8), _ptr(flags, C.c_uint8)))
+        ys, xs = np.nonzero(uns)
+        return ValidationResult({(int(x), int(y)) for x, y in zip(xs, ys)},
+                                {p for p, f in zip(platforms, flags) if f & 1}, {p for p, f in zip(platforms, flags) if f & 2})
+
+    def eval_sites(self, grid: WorldGrid, sites):
+        """sites: uint8[n, h, w] -> (uncovered int32[n], count int32[n])"""
+        s = _u8(sites).reshape(-1, grid.height, grid.width)
+        unc, cnt = np.zeros(len(s), np.int32), np.zeros(len(s), np.int32)
+        self._check(self.lib.tss_eval_sites(self._h, _ptr(grid.data, C.c_uint8), grid.width, grid.height, _ptr(s, C.c_uint8), len(s),
+                                            _ptr(unc, C.c_int32), _ptr(cnt, C.c_int32)))
+        return unc, cnt
+
+    def eval_packed(self, grid_rows, w: int, h: int, layouts):
+        g = np.ascontiguousarray(grid_rows, np.uint32)
+        l = np.ascontiguousarray(layouts, np.uint32).reshape(-1, g.size)
+        unc, cnt = np.zeros(len(l), np.int32), np.zeros(len(l), np.int32)
+        self._check(self.lib.tss_eval_packed(self._h, _ptr(g, C.c_uint32), w, h, _ptr(l, C.c_uint32), len(l), _ptr(unc, C.c_int32), _ptr(cnt, C.c_int32)))
+        return unc, cnt
+
+    def eval_compact_dev(self, grid_dev_ptr: int, w: int, h: int, layouts_dev_ptr: int, n: int, out_dev_ptr: int, per_layout_terrain=False):
+        self._check(self.lib.tss_eval_compact_dev(self._h, C.c_void_p(grid_dev_ptr), w, h, C.c_void_p(layouts_dev_ptr), n, int(per_layout_terrain),
+                                                  C.c_void_p(out_dev_ptr)))
+
+    def eval_platforms(self, grid: WorldGrid, layouts: Sequence[Sequence[Platform]]):
+        """-> int32[n, 4] = (unsupported tiles, platforms, overlapping platforms, out-of-bounds platforms)"""
+        flat = [p for l in layouts for p in l]
+        offsets = np.zeros(len(layouts) + 1, np.uint32)
+        offsets[1:] = np.cumsum([len(l) for l in layouts])
+        out = np.zeros((len(layouts), 4), np.int32)
+        self._check(self.lib.tss_eval_platforms(self._h, _ptr(grid.data, C.c_uint8), grid.width, grid.height, _plat_array(flat),
+                                                _ptr(offsets, C.c_uint32), len(layouts), _ptr(out, C.c_int32)))
+        return out
+
+    def layout_to_assignment(self, encoding: Encoding, layout: PlatformLayout) -> np.ndarray:
+        plats = list(layout.platforms().values())
+        a = np.zeros(encoding.n_vars + 1, np.uint8)
+        self._check(self.lib.tss_layout_to_assignment(self._h, encoding._h, _plat_array(plats), len(plats), _ptr(a, C.c_uint8)))
+        return a
+
+    # ---- kernel (c)
+    def upload_cnf(self, cnf: Cnf) -> DeviceCnf:
+        return DeviceCnf(self, cnf)
+
+    # ---- kernel (b)
+    def search(self, grid: WorldGrid, defs=PLATFORMS_DEFAULT[:1], **kw) -> Search:
+        return Search(self, grid, defs, **kw)
+
+    def solve_upper_bound(self, grid: WorldGrid, defs=PLATFORMS_DEFAULT[:1], card_limit: Optional[int] = None, seed=0, budget_ms=0, max_steps=0):
+        """-> (SAT | INTERRUPTED, PlatformLayout | None).  Never UNSAT: the GPU proves nothing."""
+        defs = list(defs)
+        out = (_Platform * (grid.data.size + 1))()
+        n = C.c_int32()
+        rc = self._check(self.lib.tss_solve_upper_bound(self._h, _ptr(grid.data, C.c_uint8), grid.width, grid.height, _defs_array(defs), len(defs),
+                                                        -1 if card_limit is None else card_limit, seed, budget_ms, max_steps, out, len(out), C.byref(n)))
+        if rc == _lib.TSS_SAT:
+            return SAT, PlatformLayout(Platform._from_c(out[i]) for i in range(n.value))
+        return INTERRUPTED, None
+
+    def solve_batch(self, grids, seed=0, steps=2048, want_layouts=False):
+        """grids: uint8[n, h, w] -> counts int32[n] (and packed support rows uint32[n, h] if asked)"""
+        g = _u8(grids)
+        n, h, w = g.shape
+        counts = np.zeros(n, np.int32)
+        layouts = np.zeros((n, h), np.uint32) if want_layouts else None
+        self._check(self.lib.tss_solve_batch(self._h, _ptr(g, C.c_uint8), w, h, n, seed, steps, _ptr(counts, C.c_int32),
+                                             _ptr(layouts, C.c_uint32) if want_layouts else None))
+        return (counts, layouts) if want_layouts else counts
+
+    def measure_peaks(self) -> dict:
+        out = (C.c_double * 8)()
+        self._check(self.lib.tss_measure_peaks(self._h, out, 8))
+        return dict(lop3_gops=out[0], popc_gops=out[1], shfl_gops=out[2], smem_gbs=out[3], sm_mhz=out[4])
+
+
+# ------------------------------------------------------------------------------------------------- solver shape
+class GpuBoundSolver:
+    """The `Solve + Interrupt + SolveStats (+ Default)` shape of rustsat solvers as the drivers use it
+    (crates/repl/src/solver_runner.rs:8-20, crates/gui/src/solver_backend.rs:69-97), answered by the GPU engine:
+    solve() returns SAT with a CNF-verified witness when a layout within the instance's bound exists in the budget,
+    INTERRUPTED (unknown) otherwise — never UNSAT, only the exact solver proves that."""
+
+    def __init__(self, engine: Engine, encoding: Encoding, limits: PlatformLimits, seed=0, budget_ms=50, max_steps=0):
+        self.engine, self.encoding, self.limits = engine, encoding, limits
+        self.seed, self.budget_ms, self.max_steps = seed, budget_ms, max_steps
+        self._cnf: Optional[Cnf] = None
+        self._dev: Optional[DeviceCnf] = None
+        self._solution = None
+        self._layout = None
+
+    def add_cnf(self, cnf: Cnf):  # Solve::add_cnf
+        self._cnf = cnf
+        self._dev = self.engine.upload_cnf(cnf)
+
+    def interrupter(self) -> Callable[[], None]:  # Interrupt::interrupter
+        return self.engine.interrupt
+
+    def solve(self) -> str:  # Solve::solve
+        one = PlatformDef(1, 1)
+        bound = self.limits.card_limits.get(one)
+        res, layout = self.engine.solve_upper_bound(self.encoding._grid, self.encoding.defs, bound, self.seed, self.budget_ms, self.max_steps)
+        if res != SAT:
+            return INTERRUPTED
+        a = self.engine.layout_to_assignment(self.encoding, layout)
+        if self._cnf is not None:  # witness check against the very clauses the exact solver would get (kernel (c))
+            full = np.full(self._cnf.n_vars + 1, 2, np.uint8)
+            full[: len(a)] = a
+            # auxiliary (cardinality / PB) variables are implied: unit propagation assigns them or finds a conflict
+            prop, conflict, _ = self._dev.propagate(full[None, :])
+            if conflict[0] >= 0:
+                return INTERRUPTED
+            prop[prop == 2] = 0
+            nf, _ = self._dev.check(prop)
+            if nf[0] != 0:
+                return INTERRUPTED
+            a = prop[0]
+        self._solution, self._layout = a, layout
+        return SAT
+
+    def full_solution(self):  # Solve::full_solution
+        if self._solution is None:
+            raise RuntimeError("no solution: solve() did not return Sat")
+        return self._solution
+
+    def stats(self) -> dict:  # SolveStats::stats
+        return self.engine.stats()
+
+
+def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, engine: Engine, exact_solver=None, seed=0, budget_ms=50,
+                on_solution=None):
+    """crates/repl/src/main.rs:280-366 with the GPU engine as the SAT side and an optional exact solver
+    (`exact_solver(cnf) -> (SAT|UNSAT|INTERRUPTED, assignment)`, Glucose in the reference) for the proof.
+
+    Returns dict(best=PlatformLayout|None, proved_optimal=bool, steps=[...])."""
+    one = PlatformDef(1, 1)
+    limits = PlatformLimits(dict(limits.card_limits), dict(limits.weights), limits.weight_limit)
+    steps, best, proved = [], None, False
+    while True:
+        cnf = encoding.with_limits(limits)                      # main.rs:292-293
+        solver = GpuBoundSolver(engine, encoding, limits, seed=seed, budget_ms=budget_ms)
+        solver.add_cnf(cnf)                                     # solver_runner.rs:12
+        result = solver.solve()
+        source = "gpu"
+        assignment = solver.full_solution() if result == SAT else None
+        if result != SAT and exact_solver is not None:          # the GPU found nothing in budget: ask the prover
+            result, assignment = exact_solver(cnf)
+            source = "exact"
+        bound = limits.card_limits.get(one)
+        if result != SAT:                                       # main.rs:331-338
+            steps.append(dict(bound=bound, result=result, source=source))
+            proved = result == UNSAT and best is not None
+            break
+        layout = PlatformLayout.from_assignment(assignment, encoding)   # main.rs:328-329
+        count = layout.platform_count()
+        valid = layout.validate(project.world, engine).is_valid()       # main.rs:353 (warn only)
+        steps.append(dict(bound=bound, result=SAT, count=count, valid=valid, source=source))
+        if on_solution:
+            on_solution(layout)
+        best = layout
+        if count == 0:                                          # main.rs:341-344
+            break
+        limits.card_limits[one] = count - 1                     # main.rs:346
+    return dict(best=best, proved_optimal=proved, steps=steps)

@@ -1,0 +1,288 @@
+// Kernel (c): batched clause evaluation and unit propagation over the encoder's CNF (src/encoder.rs:435-667), used
+// to verify GPU witnesses against the exact clauses the SAT solver receives (Solve::add_cnf,
+// crates/repl/src/solver_runner.rs:12).
+//
+// Layout in HBM
+//   clauses      CSR: lits int32[n_lits] (DIMACS-signed, 1-based), offsets u32[n_clauses+1]
+//   assignments  BIT-SLICED over the batch: two planes pos/neg, u32[n_vars+1][nbw], bit b of word bw = assignment
+//                32*bw+b.  pos = assigned True, neg = assigned False, neither = DontCare/unassigned.  One clause
+//                evaluation is one LOP per literal for 32 assignments; consecutive threads take consecutive batch
+//                words of the same clause, so plane reads are coalesced 128 B lines when the batch is >= 1024.
+//   propagation  assigning a literal is ONE atomicOr on ONE plane, so concurrent readers only ever see a subset of
+//                the final (monotone) state: rounds can update in place and the fixpoint is order-independent.
+#include "engine.hpp"
+
+struct tss_cnf {
+    tss_engine* engine = nullptr;
+    int32_t* lits = nullptr;
+    uint32_t* offsets = nullptr;
+    int n_clauses = 0, n_vars = 0;
+    int64_t n_lits = 0;
+};
+
+namespace tss {
+
+// u8 assignments [n][stride] -> planes.  One thread per (var, batch word).
+__global__ void cnf_pack_kernel(const uint8_t* __restrict__ a, long long n, int n_vars, int nbw, uint32_t* __restrict__ pos,
+                                uint32_t* __restrict__ neg) {
+    long long total = (long long)(n_vars + 1) * nbw;
+    const long long stride = n_vars + 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int bw = (int)(i / (n_vars + 1)), v = (int)(i % (n_vars + 1));  // consecutive threads -> consecutive vars (coalesced bytes)
+        uint32_t p = 0, q = 0;
+        for (int b = 0; b < 32; b++) {
+            long long idx = (long long)bw * 32 + b;
+            if (idx >= n) break;
+            uint8_t x = a[idx * stride + v];
+            p |= (uint32_t)(x == 1) << b;
+            q |= (uint32_t)(x == 0) << b;
+        }
+        if (v == 0) { p = 0; q = 0; }
+        pos[(long long)v * nbw + bw] = p;
+        neg[(long long)v * nbw + bw] = q;
+    }
+}
+
+__global__ void cnf_unpack_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ neg, long long n, int n_vars,
+                                  int nbw, uint8_t* __restrict__ a) {
+    long long total = (long long)(n_vars + 1) * nbw;
+    const long long stride = n_vars + 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int bw = (int)(i / (n_vars + 1)), v = (int)(i % (n_vars + 1));
+        uint32_t p = pos[(long long)v * nbw + bw], q = neg[(long long)v * nbw + bw];
+        for (int b = 0; b < 32; b++) {
+            long long idx = (long long)bw * 32 + b;
+            if (idx >= n) break;
+            a[idx * stride + v] = v == 0 ? 2 : (((p >> b) & 1u) ? 1 : (((q >> b) & 1u) ? 0 : 2));  // True wins a forced clash
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t batch_mask(long long n, int bw) {
+    long long rem = n - (long long)bw * 32;
+    return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+}
+
+// Clause evaluation.  falsified bit = no literal of the clause is True.
+__global__ void cnf_check_kernel(const int32_t* __restrict__ lits, const uint32_t* __restrict__ offsets, int n_clauses, int nbw,
+                                 long long n, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ neg,
+                                 int* __restrict__ n_falsified, int* __restrict__ first_falsified) {
+    long long total = (long long)n_clauses * nbw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i / nbw), bw = (int)(i % nbw);
+        uint32_t sat = 0;
+        for (uint32_t k = offsets[c]; k < offsets[c + 1]; k++) {
+            int l = lits[k];
+            sat |= l > 0 ? pos[(long long)l * nbw + bw] : neg[(long long)(-l) * nbw + bw];
+        }
+        uint32_t bad = ~sat & batch_mask(n, bw);
+        while (bad) {
+            int b = __ffs(bad) - 1;
+            bad &= bad - 1;
+            atomicAdd(&n_falsified[bw * 32 + b], 1);
+            atomicMin(&first_falsified[bw * 32 + b], c);
+        }
+    }
+}
+
+// One unit-propagation round over all clauses (in place, monotone).
+__global__ void cnf_propagate_kernel(const int32_t* __restrict__ lits, const uint32_t* __restrict__ offsets, int n_clauses, int nbw,
+                                     long long n, uint32_t* __restrict__ pos, uint32_t* __restrict__ neg, int* __restrict__ changed) {
+    long long total = (long long)n_clauses * nbw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i / nbw), bw = (int)(i % nbw);
+        const uint32_t k0 = offsets[c], k1 = offsets[c + 1];
+        uint32_t sat = 0, un1 = 0, un2 = 0;
+        for (uint32_t k = k0; k < k1; k++) {
+            int l = lits[k], v = l > 0 ? l : -l;
+            uint32_t p = pos[(long long)v * nbw + bw], q = neg[(long long)v * nbw + bw];
+            sat |= l > 0 ? p : q;
+            uint32_t u = ~(p | q);
+            un2 |= un1 & u;
+            un1 |= u;
+        }
+        uint32_t unit = ~sat & un1 & ~un2 & batch_mask(n, bw);
+        if (!unit) continue;
+        for (uint32_t k = k0; k < k1; k++) {
+            int l = lits[k], v = l > 0 ? l : -l;
+            uint32_t u = ~(pos[(long long)v * nbw + bw] | neg[(long long)v * nbw + bw]) & unit;
+            if (u) {
+                atomicOr(l > 0 ? &pos[(long long)v * nbw + bw] : &neg[(long long)v * nbw + bw], u);
+                unit &= ~u;
+                *changed = 1;
+            }
+        }
+    }
+}
+
+__global__ void cnf_relax_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ neg, uint32_t* __restrict__ pos2,
+                                 uint32_t* __restrict__ neg2, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t p = pos[i], q = neg[i], u = ~(p | q);
+        pos2[i] = p | u;
+        neg2[i] = (q & ~p) | u;  // True wins a forced clash
+    }
+}
+
+static unsigned grid_for(tss_engine* e, long long total) {
+    long long blocks = (total + 255) / 256, cap = (long long)e->prop.multiProcessorCount * 16;
+    return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace tss
+
+using namespace tss;
+
+extern "C" {
+
+int tss_cnf_upload(tss_engine* e, const int32_t* lits, const uint32_t* offsets, int32_t n_clauses, int32_t n_vars, tss_cnf** out) {
+    if (!e) return TSS_E_INVALID;
+    if (!out || !offsets || n_clauses < 0 || n_vars < 0) return e->fail(TSS_E_INVALID, "tss_cnf_upload: bad arguments");
+    int64_t n_lits = offsets[n_clauses];
+    if (n_lits > 0 && !lits) return e->fail(TSS_E_INVALID, "tss_cnf_upload: lits is null");
+    for (int64_t k = 0; k < n_lits; k++) {
+        int v = lits[k] > 0 ? lits[k] : -lits[k];
+        if (v == 0 || v > n_vars) return e->fail(TSS_E_INVALID, "tss_cnf_upload: literal %d out of range (n_vars = %d)", lits[k], n_vars);
+    }
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    tss_cnf* c = new tss_cnf();
+    c->engine = e; c->n_clauses = n_clauses; c->n_vars = n_vars; c->n_lits = n_lits;
+    cudaError_t err = cudaMalloc(&c->lits, sizeof(int32_t) * (size_t)(n_lits > 0 ? n_lits : 1));
+    if (err == cudaSuccess) err = cudaMalloc(&c->offsets, sizeof(uint32_t) * (size_t)(n_clauses + 1));
+    if (err == cudaSuccess && n_lits) err = cudaMemcpyAsync(c->lits, lits, sizeof(int32_t) * (size_t)n_lits, cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(c->offsets, offsets, sizeof(uint32_t) * (size_t)(n_clauses + 1), cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) { tss_cnf_destroy(c); return e->fail(TSS_E_CUDA, "tss_cnf_upload: %s", cudaGetErrorString(err)); }
+    *out = c;
+    return TSS_OK;
+}
+
+void tss_cnf_destroy(tss_cnf* c) {
+    if (!c) return;
+    cudaFree(c->lits);
+    cudaFree(c->offsets);
+    delete c;
+}
+
+// scratch slots: 0 = u8 assignments, 1 = pos plane, 2 = neg plane, 3 = int outputs
+static int cnf_stage(tss_engine* e, const tss_cnf* c, const uint8_t* assignments, int64_t n, uint32_t** pos, uint32_t** neg, int* nbw_out) {
+    const int nbw = (int)((n + 31) / 32);
+    const size_t abytes = (size_t)n * (c->n_vars + 1), pbytes = sizeof(uint32_t) * (size_t)(c->n_vars + 1) * nbw;
+    uint8_t* a = (uint8_t*)e->dev(0, abytes);
+    *pos = (uint32_t*)e->dev(1, pbytes);
+    *neg = (uint32_t*)e->dev(2, pbytes);
+    if (!a || !*pos || !*neg) return TSS_E_CUDA;
+    TSS_CUDA(e, cudaMemcpyAsync(a, assignments, abytes, cudaMemcpyHostToDevice, e->stream));
+    cnf_pack_kernel<<<grid_for(e, (long long)(c->n_vars + 1) * nbw), 256, 0, e->stream>>>(a, n, c->n_vars, nbw, *pos, *neg);
+    TSS_CHECK_LAUNCH(e);
+    e->stats.kernel_launches++;
+    *nbw_out = nbw;
+    return TSS_OK;
+}
+
+int tss_cnf_check(tss_engine* e, const tss_cnf* c, const uint8_t* assignments, int64_t n, int32_t* out_n_falsified,
+                  int32_t* out_first_falsified) {
+    if (!e) return TSS_E_INVALID;
+    if (!c || !assignments || n < 0 || !out_n_falsified) return e->fail(TSS_E_INVALID, "tss_cnf_check: bad arguments");
+    if (n == 0) return TSS_OK;
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    uint32_t *pos, *neg;
+    int nbw;
+    int rc = cnf_stage(e, c, assignments, n, &pos, &neg, &nbw);
+    if (rc) return rc;
+    int* outs = (int*)e->dev(3, sizeof(int) * (size_t)nbw * 64);
+    if (!outs) return TSS_E_CUDA;
+    int *cnt = outs, *first = outs + (size_t)nbw * 32;
+    TSS_CUDA(e, cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)nbw * 32, e->stream));
+    TSS_CUDA(e, cudaMemsetAsync(first, 0x7f, sizeof(int) * (size_t)nbw * 32, e->stream));
+    TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    if (c->n_clauses > 0) {
+        cnf_check_kernel<<<grid_for(e, (long long)c->n_clauses * nbw), 256, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos, neg, cnt, first);
+        TSS_CHECK_LAUNCH(e);
+        e->stats.kernel_launches++;
+    }
+    TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    e->stats.clauses_checked += (uint64_t)c->n_clauses * (uint64_t)n;
+    TSS_CUDA(e, cudaMemcpyAsync(out_n_falsified, cnt, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    std::vector<int> tmp;
+    if (out_first_falsified) TSS_CUDA(e, cudaMemcpyAsync(out_first_falsified, first, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->stats.device_ms = ms;
+    if (out_first_falsified)
+        for (int64_t i = 0; i < n; i++)
+            if (out_n_falsified[i] == 0) out_first_falsified[i] = -1;
+    return TSS_OK;
+}
+
+int tss_cnf_propagate(tss_engine* e, const tss_cnf* c, uint8_t* assignments, int64_t n, int32_t* out_conflict, int32_t* out_rounds) {
+    if (!e) return TSS_E_INVALID;
+    if (!c || !assignments || n < 0) return e->fail(TSS_E_INVALID, "tss_cnf_propagate: bad arguments");
+    if (out_rounds) *out_rounds = 0;
+    if (n == 0) return TSS_OK;
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    uint32_t *pos, *neg;
+    int nbw;
+    int rc = cnf_stage(e, c, assignments, n, &pos, &neg, &nbw);
+    if (rc) return rc;
+    int* outs = (int*)e->dev(3, sizeof(int) * ((size_t)nbw * 64 + 1));
+    int* flag_host = (int*)e->pin(0, sizeof(int));
+    if (!outs || !flag_host) return TSS_E_CUDA;
+    int *cnt = outs, *first = outs + (size_t)nbw * 32, *changed = outs + (size_t)nbw * 64;
+    const unsigned grid = grid_for(e, (long long)c->n_clauses * nbw);
+    int rounds = 0;
+    TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    for (; c->n_clauses > 0 && rounds <= c->n_vars; rounds++) {  // every productive round assigns >= 1 variable
+        if (e->interrupted()) break;
+        TSS_CUDA(e, cudaMemsetAsync(changed, 0, sizeof(int), e->stream));
+        cnf_propagate_kernel<<<grid, 256, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos, neg, changed);
+        TSS_CHECK_LAUNCH(e);
+        e->stats.kernel_launches++;
+        e->stats.clauses_checked += (uint64_t)c->n_clauses * (uint64_t)n;
+        TSS_CUDA(e, cudaMemcpyAsync(flag_host, changed, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        TSS_CUDA(e, cudaStreamSynchronize(e->stream));
+        if (!*flag_host) { rounds++; break; }
+    }
+    if (out_rounds) *out_rounds = rounds;
+    // conflicts at the fixpoint = clauses whose literals are all False (True wins a forced clash, so the clause that
+    // forced the opposite value shows up as falsified)
+    TSS_CUDA(e, cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)nbw * 32, e->stream));
+    TSS_CUDA(e, cudaMemsetAsync(first, 0x7f, sizeof(int) * (size_t)nbw * 32, e->stream));
+    if (c->n_clauses > 0) {
+        // a clause is in conflict only if it has no unassigned literal: evaluate with "unassigned counts as True"
+        // by checking against pos|~assigned is wrong for negatives, so run the check on dedicated planes:
+        // reuse cnf_check_kernel with pos' = pos | unassigned, neg' = neg | unassigned (scratch slots 4, 5)
+        size_t pbytes = sizeof(uint32_t) * (size_t)(c->n_vars + 1) * nbw;
+        uint32_t* pos2 = (uint32_t*)e->dev(4, pbytes);
+        uint32_t* neg2 = (uint32_t*)e->dev(5, pbytes);
+        if (!pos2 || !neg2) return TSS_E_CUDA;
+        cnf_relax_kernel<<<grid_for(e, (long long)(c->n_vars + 1) * nbw), 256, 0, e->stream>>>(pos, neg, pos2, neg2, (long long)(c->n_vars + 1) * nbw);
+        TSS_CHECK_LAUNCH(e);
+        cnf_check_kernel<<<grid, 256, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos2, neg2, cnt, first);
+        TSS_CHECK_LAUNCH(e);
+        e->stats.kernel_launches += 2;
+    }
+    TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    uint8_t* a = (uint8_t*)e->scratch[0].ptr;
+    cnf_unpack_kernel<<<grid_for(e, (long long)(c->n_vars + 1) * nbw), 256, 0, e->stream>>>(pos, neg, n, c->n_vars, nbw, a);
+    TSS_CHECK_LAUNCH(e);
+    e->stats.kernel_launches++;
+    TSS_CUDA(e, cudaMemcpyAsync(assignments, a, (size_t)n * (c->n_vars + 1), cudaMemcpyDeviceToHost, e->stream));
+    std::vector<int> cnt_host((size_t)n);
+    if (out_conflict) {
+        TSS_CUDA(e, cudaMemcpyAsync(out_conflict, first, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+        TSS_CUDA(e, cudaMemcpyAsync(cnt_host.data(), cnt, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    }
+    TSS_CUDA(e, cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->stats.device_ms = ms;
+    if (out_conflict)
+        for (int64_t i = 0; i < n; i++)
+            if (cnt_host[(size_t)i] == 0) out_conflict[i] = -1;
+    return TSS_OK;
+}
+
+}  // extern "C"
+

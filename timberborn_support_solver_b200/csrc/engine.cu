@@ -1,0 +1,615 @@
+// Engine, device buffers and the C ABI entry points that touch the GPU (include/tss.h).  Host-only entry points
+// (world / encoder / layout decode) live in capi_host.cpp.
+#include "engine.hpp"
+
+#include <chrono>
+#include <cstring>
+#include <new>
+
+#include "sls_spec.hpp"
+
+namespace tss {
+int sls_build_reach(tss_engine* e, const uint32_t* rows_dev, int n_terrains, uint2* tabs_dev);
+int sls_init_states(tss_engine* e, sls::ChainState* states, int n);
+int sls_run(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls::ChainState* states, int n_chains,
+            int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
+            int noise_pct, unsigned long long* totals_dev);
+int sls_best_reduce(tss_engine* e, const sls::ChainState* states, int chains_per_group, int n_chains, int n_groups, int2* out_dev,
+                    int* bounds_dev);
+int run_peaks(tss_engine* e, double* out, int n_out);
+
+// u8 grids [n][w*h] -> rows32 [n][32] (one u32 per row, rows >= h are zero); w, h <= 32
+__global__ void pack_rows32_kernel(const uint8_t* __restrict__ bytes, int w, int h, long long n, uint32_t* __restrict__ out) {
+    long long total = n * 32;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i >> 5;
+        int y = (int)(i & 31);
+        uint32_t v = 0;
+        if (y < h) {
+            const uint8_t* src = bytes + t * (long long)w * h + (long long)y * w;
+            for (int x = 0; x < w; x++) v |= (uint32_t)(src[x] != 0) << x;
+        }
+        out[i] = v;
+    }
+}
+}  // namespace tss
+
+void* tss_engine::dev(int slot, size_t bytes) {
+    TssBuffer& b = scratch[slot];
+    if (bytes <= b.cap && b.ptr) return b.ptr;
+    if (b.ptr) { cudaStreamSynchronize(stream); cudaFree(b.ptr); b.ptr = nullptr; b.cap = 0; }
+    size_t want = bytes < 4096 ? 4096 : bytes + bytes / 4;
+    cudaError_t err = cudaMalloc(&b.ptr, want);
+    if (err != cudaSuccess) { b.ptr = nullptr; fail(TSS_E_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(err)); return nullptr; }
+    b.cap = want;
+    return b.ptr;
+}
+void* tss_engine::pin(int slot, size_t bytes) {
+    TssBuffer& b = staging[slot];
+    if (bytes <= b.cap && b.ptr) return b.ptr;
+    if (b.ptr) { cudaStreamSynchronize(stream); cudaFreeHost(b.ptr); b.ptr = nullptr; b.cap = 0; }
+    size_t want = bytes < 4096 ? 4096 : bytes + bytes / 4;
+    cudaError_t err = cudaHostAlloc(&b.ptr, want, cudaHostAllocDefault);
+    if (err != cudaSuccess) { b.ptr = nullptr; fail(TSS_E_CUDA, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(err)); return nullptr; }
+    b.cap = want;
+    b.pinned = true;
+    return b.ptr;
+}
+
+struct tss_search {
+    tss_engine* e = nullptr;
+    int w = 0, h = 0;
+    std::vector<uint8_t> grid;
+    int n_chains = 0, n_groups = 1, chains_per_terrain = 0;
+    uint32_t chain_offset = 0;
+    uint64_t seed = 0;
+    int noise = tss::sls::DEFAULT_NOISE_PCT;
+    uint32_t* rows_dev = nullptr;
+    uint2* tabs_dev = nullptr;
+    tss::sls::ChainState* states = nullptr;
+    unsigned long long* totals_dev = nullptr;  // [2]
+    int2* best_dev = nullptr;                  // [n_groups]
+    int* bounds_dev = nullptr;                 // [n_groups]
+    int2* best_host = nullptr;                 // pinned [n_groups]
+    unsigned long long* totals_host = nullptr; // pinned [2]
+    unsigned long long totals_seen[2] = {0, 0};
+    bool dirty = false;
+};
+
+using namespace tss;
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" {
+
+int tss_version(void) { return TSS_VERSION; }
+
+int tss_engine_create(int device, tss_engine** out) {
+    if (!out) return TSS_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return TSS_E_CUDA;  // no CPU fallback
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) return TSS_E_CUDA; }
+    if (device >= count) return TSS_E_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return TSS_E_CUDA;
+    tss_engine* e = new (std::nothrow) tss_engine();
+    if (!e) return TSS_E_INVALID;
+    e->device = device;
+    e->stats.best_count = -1;
+    bool ok = cudaGetDeviceProperties(&e->prop, device) == cudaSuccess && cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess;
+    void* flag = nullptr;
+    ok = ok && cudaHostAlloc(&flag, sizeof(int), cudaHostAllocMapped) == cudaSuccess;
+    if (ok) {
+        e->interrupt_host = (volatile int*)flag;
+        *e->interrupt_host = 0;
+        ok = cudaHostGetDevicePointer((void**)&e->interrupt_dev, flag, 0) == cudaSuccess;
+    }
+    if (!ok) { cudaGetLastError(); tss_engine_destroy(e); return TSS_E_CUDA; }
+    e->stream = e->own_stream;
+    *out = e;
+    return TSS_OK;
+}
+
+void tss_engine_destroy(tss_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+    for (auto& b : e->scratch) if (b.ptr) cudaFree(b.ptr);
+    for (auto& b : e->staging) if (b.ptr) cudaFreeHost(b.ptr);
+    if (e->interrupt_host) cudaFreeHost((void*)e->interrupt_host);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+int tss_engine_set_stream(tss_engine* e, void* cuda_stream) {
+    if (!e) return TSS_E_INVALID;
+    cudaStreamSynchronize(e->stream);
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return TSS_OK;
+}
+
+const char* tss_last_error(const tss_engine* e) { return e ? e->error.c_str() : "null engine"; }
+
+void tss_interrupt(tss_engine* e) {
+    if (!e) return;
+    e->interrupt_flag.store(1);
+    if (e->interrupt_host) *e->interrupt_host = 1;
+}
+void tss_clear_interrupt(tss_engine* e) {
+    if (!e) return;
+    e->interrupt_flag.store(0);
+    if (e->interrupt_host) *e->interrupt_host = 0;
+}
+int tss_get_stats(const tss_engine* e, tss_stats* out) {
+    if (!e || !out) return TSS_E_INVALID;
+    *out = e->stats;
+    return TSS_OK;
+}
+int tss_device_info(const tss_engine* e, char* name, int cap, int* sm_count, int* clock_khz) {
+    if (!e) return TSS_E_INVALID;
+    if (name && cap > 0) { std::strncpy(name, e->prop.name, (size_t)cap - 1); name[cap - 1] = 0; }
+    if (sm_count) *sm_count = e->prop.multiProcessorCount;
+    if (clock_khz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device); *clock_khz = khz; }
+    return TSS_OK;
+}
+
+size_t tss_compact_row_bytes(int32_t w, int32_t h) { return tss_row_bytes(w, h); }
+size_t tss_compact_layout_bytes(int32_t w, int32_t h) { return tss_layout_bytes(w, h); }
+
+// ------------------------------------------------------------------------------------------------ kernel (a)
+int tss_eval_compact_dev(tss_engine* e, const void* grid_dev, int32_t w, int32_t h, const void* layouts_dev, int64_t n,
+                         int32_t per_layout_terrain, int32_t* out_dev) {
+    if (!e) return TSS_E_INVALID;
+    if (!grid_dev || !layouts_dev || !out_dev || w <= 0 || h <= 0 || n < 0) return e->fail(TSS_E_INVALID, "tss_eval_compact_dev: bad arguments");
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    return launch_eval_compact(e, grid_dev, w, h, layouts_dev, n, per_layout_terrain != 0, out_dev);
+}
+
+// shared tail: evaluate n compact layouts already on the device (scratch slot 1) against one terrain, copy results out
+static int eval_compact_and_fetch(tss_engine* e, const uint8_t* grid_compact_host, int w, int h, const void* layouts_dev, int64_t n,
+                                  int32_t* out_uncovered, int32_t* out_count) {
+    size_t lb = tss_layout_bytes(w, h);
+    void* g = e->dev(2, lb);
+    int32_t* out = (int32_t*)e->dev(3, sizeof(int32_t) * 2 * (size_t)n);
+    int32_t* host = (int32_t*)e->pin(1, sizeof(int32_t) * 2 * (size_t)n);
+    if (!g || !out || !host) return TSS_E_CUDA;
+    TSS_CUDA(e, cudaMemcpyAsync(g, grid_compact_host, lb, cudaMemcpyHostToDevice, e->stream));
+    TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    int rc = launch_eval_compact(e, g, w, h, layouts_dev, n, false, out);
+    if (rc) return rc;
+    TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    TSS_CUDA(e, cudaMemcpyAsync(host, out, sizeof(int32_t) * 2 * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->stats.device_ms = ms;
+    for (int64_t i = 0; i < n; i++) {
+        if (out_uncovered) out_uncovered[i] = host[2 * i];
+        if (out_count) out_count[i] = host[2 * i + 1];
+    }
+    return TSS_OK;
+}
+
+int tss_eval_sites(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const uint8_t* sites, int64_t n,
+                   int32_t* out_uncovered, int32_t* out_count) {
+    if (!e) return TSS_E_INVALID;
+    if (!grid || (!sites && n > 0) || w <= 0 || h <= 0 || n < 0) return e->fail(TSS_E_INVALID, "tss_eval_sites: bad arguments");
+    if (n == 0) return TSS_OK;
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    size_t lb = tss_layout_bytes(w, h), tiles = (size_t)w * h;
+    uint8_t* bytes = (uint8_t*)e->dev(0, tiles * (size_t)n);
+    void* compact = e->dev(1, lb * (size_t)n);
+    if (!bytes || !compact) return TSS_E_CUDA;
+    TSS_CUDA(e, cudaMemcpyAsync(bytes, sites, tiles * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    int rc = launch_pack_bytes(e, bytes, w, h, n, compact);
+    if (rc) return rc;
+    std::vector<uint8_t> gc(lb);
+    pack_compact_host(grid, w, h, gc.data());
+    return eval_compact_and_fetch(e, gc.data(), w, h, compact, n, out_uncovered, out_count);
+}
+
+int tss_eval_packed(tss_engine* e, const uint32_t* grid_rows, int32_t w, int32_t h, const uint32_t* layouts, int64_t n,
+                    int32_t* out_uncovered, int32_t* out_count) {
+    if (!e) return TSS_E_INVALID;
+    if (!grid_rows || (!layouts && n > 0) || w <= 0 || h <= 0 || n < 0) return e->fail(TSS_E_INVALID, "tss_eval_packed: bad arguments");
+    if (n == 0) return TSS_OK;
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    const size_t lb = tss_layout_bytes(w, h), nw = (size_t)h * ((w + 31) / 32);
+    void* compact = e->dev(1, lb * (size_t)n);
+    if (!compact) return TSS_E_CUDA;
+    std::vector<uint8_t> gc(lb);
+    rows_to_compact_host(grid_rows, w, h, gc.data());
+    if (lb == nw * 4) {  // rows are already in the compact format (w > 16 or a large grid)
+        TSS_CUDA(e, cudaMemcpyAsync(compact, layouts, lb * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        uint8_t* stage = (uint8_t*)e->pin(0, lb * (size_t)n);
+        if (!stage) return TSS_E_CUDA;
+        for (int64_t i = 0; i < n; i++) rows_to_compact_host(layouts + (size_t)i * nw, w, h, stage + (size_t)i * lb);
+        TSS_CUDA(e, cudaMemcpyAsync(compact, stage, lb * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    }
+    return eval_compact_and_fetch(e, gc.data(), w, h, compact, n, out_uncovered, out_count);
+}
+
+// uploads grid rows + platforms and runs the platform evaluator; outputs stay on the device in scratch slots
+//   slot 0 grid rows, 1 plats(int4), 2 offsets, 3 out(int4 per layout), 4 unsupported rows, 5 flags, 6 layers
+static int eval_platforms_dev(tss_engine* e, const uint8_t* grid, int w, int h, const tss_platform* plats, const uint32_t* offsets,
+                              int64_t n, bool want_rows, bool want_flags, bool want_layers) {
+    const int wpr = (w + 31) / 32;
+    const size_t nw = (size_t)h * wpr, np = offsets[n];
+    BitGrid bg = BitGrid::from_bytes(grid, w, h);
+    uint32_t* g = (uint32_t*)e->dev(0, nw * 4);
+    int4* p = (int4*)e->dev(1, sizeof(int4) * (np ? np : 1));
+    uint32_t* off = (uint32_t*)e->dev(2, sizeof(uint32_t) * (size_t)(n + 1));
+    int32_t* out = (int32_t*)e->dev(3, sizeof(int32_t) * 4 * (size_t)n);
+    uint32_t* rows = want_rows ? (uint32_t*)e->dev(4, nw * 4 * (size_t)n) : nullptr;
+    uint8_t* flags = want_flags ? (uint8_t*)e->dev(5, np ? np : 1) : nullptr;
+    uint32_t* layers = want_layers ? (uint32_t*)e->dev(6, nw * 16 * (size_t)n) : nullptr;
+    if (!g || !p || !off || !out || (want_rows && !rows) || (want_flags && !flags) || (want_layers && !layers)) return TSS_E_CUDA;
+    std::vector<int4> eff(np);
+    for (size_t i = 0; i < np; i++) {
+        Dims d = platform_dims(plats[i]);
+        eff[i] = make_int4(plats[i].x, plats[i].y, d.w, d.h);
+    }
+    TSS_CUDA(e, cudaMemcpyAsync(g, bg.rows.data(), nw * 4, cudaMemcpyHostToDevice, e->stream));
+    if (np) TSS_CUDA(e, cudaMemcpyAsync(p, eff.data(), sizeof(int4) * np, cudaMemcpyHostToDevice, e->stream));
+    TSS_CUDA(e, cudaMemcpyAsync(off, offsets, sizeof(uint32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, e->stream));
+    TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    int rc = launch_eval_platforms(e, g, w, h, p, off, n, out, rows, flags, layers);
+    if (rc) return rc;
+    TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    TSS_CUDA(e, cudaStreamSynchronize(e->stream));  // eff / bg are host temporaries
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->stats.device_ms = ms;
+    return TSS_OK;
+}
+
+int tss_eval_platforms(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_platform* plats,
+                       const uint32_t* offsets, int64_t n, int32_t* out) {
+    if (!e) return TSS_E_INVALID;
+    if (!grid || !offsets || !out || w <= 0 || h <= 0 || n < 0 || (!plats && offsets[n] > 0)) return e->fail(TSS_E_INVALID, "tss_eval_platforms: bad arguments");
+    if (n == 0) return TSS_OK;
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    int rc = eval_platforms_dev(e, grid, w, h, plats, offsets, n, false, false, false);
+    if (rc) return rc;
+    TSS_CUDA(e, cudaMemcpy(out, e->scratch[3].ptr, sizeof(int32_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    return TSS_OK;
+}
+
+int tss_validate(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_platform* plats, int32_t n,
+                 uint8_t* out_unsupported, uint8_t* out_flags) {
+    if (!e) return TSS_E_INVALID;
+    if (!grid || w <= 0 || h <= 0 || n < 0 || (!plats && n > 0)) return e->fail(TSS_E_INVALID, "tss_validate: bad arguments");
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    uint32_t offsets[2] = {0, (uint32_t)n};
+    int rc = eval_platforms_dev(e, grid, w, h, plats, offsets, 1, true, true, false);
+    if (rc) return rc;
+    const int wpr = (w + 31) / 32;
+    std::vector<uint32_t> rows((size_t)h * wpr);
+    int32_t res[4];
+    TSS_CUDA(e, cudaMemcpy(res, e->scratch[3].ptr, sizeof res, cudaMemcpyDeviceToHost));
+    TSS_CUDA(e, cudaMemcpy(rows.data(), e->scratch[4].ptr, rows.size() * 4, cudaMemcpyDeviceToHost));
+    if (out_flags && n > 0) TSS_CUDA(e, cudaMemcpy(out_flags, e->scratch[5].ptr, (size_t)n, cudaMemcpyDeviceToHost));
+    if (out_unsupported)
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) out_unsupported[(size_t)y * w + x] = (rows[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
+    return res[0];
+}
+
+// declared in tss.h next to the encoder; needs the evaluator's support layers
+int tss_layout_to_assignment_impl(tss_engine* e, const Encoding& enc, const uint8_t* grid, const tss_platform* plats, int32_t n_plats,
+                                  uint8_t* assignment) {
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    const int w = enc.w, h = enc.h, wpr = (w + 31) / 32, K = enc.K();
+    uint32_t offsets[2] = {0, (uint32_t)n_plats};
+    int rc = eval_platforms_dev(e, grid, w, h, plats, offsets, 1, false, false, true);
+    if (rc) return rc;
+    std::vector<uint32_t> layers((size_t)4 * h * wpr);
+    TSS_CUDA(e, cudaMemcpy(layers.data(), e->scratch[6].ptr, layers.size() * 4, cudaMemcpyDeviceToHost));
+    for (int v = 0; v <= enc.base.n_vars; v++) assignment[v] = v == 0 ? 2 : 0;
+    for (int i = 0; i < n_plats; i++) {  // every dims key contained in the platform's effective dims (DAG implications)
+        if (plats[i].x < 0 || plats[i].y < 0 || plats[i].x >= w || plats[i].y >= h) continue;
+        Dims d = platform_dims(plats[i]);
+        int tile = plats[i].y * w + plats[i].x;
+        for (int k = 0; k < K; k++)
+            if (dims_le(enc.keys[k], d)) assignment[enc.plat_var[(size_t)tile * K + k]] = 1;
+    }
+    for (int t = 0; t < w * h; t++)
+        for (int l = 0; l < 4; l++) {
+            int var = enc.terr_var[(size_t)t * 4 + l];
+            if (!var) continue;
+            int x = t % w, y = t / w;
+            const uint32_t* plane = layers.data() + (size_t)(3 - l) * h * wpr;  // T3 = directly supported ... T0 = after 3 rounds
+            assignment[var] = (plane[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
+        }
+    return TSS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel (b)
+static void search_free(tss_search* s) {
+    if (!s) return;
+    cudaFree(s->rows_dev); cudaFree(s->tabs_dev); cudaFree(s->states); cudaFree(s->totals_dev); cudaFree(s->best_dev); cudaFree(s->bounds_dev);
+    if (s->best_host) cudaFreeHost(s->best_host);
+    if (s->totals_host) cudaFreeHost(s->totals_host);
+    delete s;
+}
+
+// rows32_host: [n_terrains][32]
+static int search_alloc(tss_engine* e, tss_search* s, const uint32_t* rows32_host, int n_terrains) {
+    TSS_CUDA(e, cudaMalloc(&s->rows_dev, sizeof(uint32_t) * 32 * (size_t)n_terrains));
+    TSS_CUDA(e, cudaMalloc(&s->tabs_dev, sizeof(uint2) * 1024 * (size_t)n_terrains));
+    TSS_CUDA(e, cudaMalloc(&s->states, sizeof(sls::ChainState) * (size_t)s->n_chains));
+    TSS_CUDA(e, cudaMalloc(&s->totals_dev, sizeof(unsigned long long) * 2));
+    TSS_CUDA(e, cudaMalloc(&s->best_dev, sizeof(int2) * (size_t)s->n_groups));
+    TSS_CUDA(e, cudaMalloc(&s->bounds_dev, sizeof(int) * (size_t)s->n_groups));
+    TSS_CUDA(e, cudaHostAlloc((void**)&s->best_host, sizeof(int2) * (size_t)s->n_groups, cudaHostAllocDefault));
+    TSS_CUDA(e, cudaHostAlloc((void**)&s->totals_host, sizeof(unsigned long long) * 2, cudaHostAllocDefault));
+    if (rows32_host) TSS_CUDA(e, cudaMemcpyAsync(s->rows_dev, rows32_host, sizeof(uint32_t) * 32 * (size_t)n_terrains, cudaMemcpyHostToDevice, e->stream));
+    return TSS_OK;
+}
+
+static int search_init_device(tss_engine* e, tss_search* s, int n_terrains) {
+    TSS_CUDA(e, cudaMemsetAsync(s->totals_dev, 0, sizeof(unsigned long long) * 2, e->stream));
+    std::vector<int> nb((size_t)s->n_groups, sls::NO_BOUND);
+    TSS_CUDA(e, cudaMemcpyAsync(s->bounds_dev, nb.data(), sizeof(int) * nb.size(), cudaMemcpyHostToDevice, e->stream));
+    for (int g = 0; g < s->n_groups; g++) s->best_host[g] = make_int2(sls::NO_BOUND, -1);
+    s->totals_host[0] = s->totals_host[1] = 0;
+    int rc = sls_build_reach(e, s->rows_dev, n_terrains, s->tabs_dev);
+    if (rc) return rc;
+    rc = sls_init_states(e, s->states, s->n_chains);
+    if (rc) return rc;
+    TSS_CUDA(e, cudaStreamSynchronize(e->stream));  // nb is a host temporary
+    return TSS_OK;
+}
+
+int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,
+                      const tss_search_params* params, tss_search** out) {
+    if (!e) return TSS_E_INVALID;
+    if (!grid || !out || w <= 0 || h <= 0 || (!defs && n_defs > 0)) return e->fail(TSS_E_INVALID, "tss_search_create: bad arguments");
+    bool has_1x1 = n_defs == 0;
+    for (int i = 0; i < n_defs; i++) {
+        if (defs[i].w <= 0 || defs[i].h <= 0) return e->fail(TSS_E_INVALID, "tss_search_create: empty platform dimensions");
+        has_1x1 = has_1x1 || (defs[i].w == 1 && defs[i].h == 1);
+    }
+    if (!has_1x1) return e->fail(TSS_E_INVALID, "the platform set must contain 1x1 (src/encoder.rs:564-566)");
+    if (w > 32 || h > 32) return e->fail(TSS_E_UNSUPPORTED, "tss_search: grids larger than 32x32 are not accelerated yet (got %dx%d)", w, h);
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    tss_search* s = new tss_search();
+    s->e = e; s->w = w; s->h = h;
+    s->grid.assign(grid, grid + (size_t)w * h);
+    s->seed = params ? params->seed : 0;
+    s->chain_offset = params ? (uint32_t)params->chain_offset : 0;
+    s->noise = (params && params->noise_pct >= 0) ? params->noise_pct : sls::DEFAULT_NOISE_PCT;
+    s->n_chains = (params && params->n_chains > 0) ? params->n_chains : e->prop.multiProcessorCount * 32;
+    s->n_groups = 1;
+    s->chains_per_terrain = 0;
+    uint32_t rows[32] = {0};
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            if (grid[(size_t)y * w + x]) rows[y] |= 1u << x;
+    int rc = search_alloc(e, s, rows, 1);
+    if (rc == TSS_OK) rc = search_init_device(e, s, 1);
+    if (rc != TSS_OK) { search_free(s); return rc; }
+    *out = s;
+    return TSS_OK;
+}
+
+void tss_search_destroy(tss_search* s) {
+    if (!s) return;
+    cudaSetDevice(s->e->device);
+    cudaStreamSynchronize(s->e->stream);
+    search_free(s);
+}
+
+int tss_search_n_chains(const tss_search* s) { return s ? s->n_chains : TSS_E_INVALID; }
+
+int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
+    if (!s) return TSS_E_INVALID;
+    tss_engine* e = s->e;
+    if (steps <= 0) return e->fail(TSS_E_INVALID, "tss_search_run: steps must be positive");
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    int chains_per_group = s->n_groups == 1 ? s->n_chains : s->chains_per_terrain;
+    int rc = sls_run(e, s->rows_dev, s->tabs_dev, s->states, s->n_chains, s->chains_per_terrain, s->chain_offset, s->seed, steps,
+                     s->bounds_dev, target_count < 0 ? -1 : target_count, s->noise, s->totals_dev);
+    if (rc == TSS_OK) rc = sls_best_reduce(e, s->states, chains_per_group, s->n_chains, s->n_groups, s->best_dev, s->bounds_dev);
+    if (rc) return rc;
+    TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    TSS_CUDA(e, cudaMemcpyAsync(s->best_host, s->best_dev, sizeof(int2) * (size_t)s->n_groups, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaMemcpyAsync(s->totals_host, s->totals_dev, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, e->stream));
+    s->dirty = true;
+    e->stats.n_solves++;
+    return TSS_OK;
+}
+
+static int search_sync(tss_search* s) {
+    tss_engine* e = s->e;
+    if (!s->dirty) return TSS_OK;
+    TSS_CUDA(e, cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->stats.device_ms = ms;
+    e->stats.candidates_scored += s->totals_host[0] - s->totals_seen[0];
+    e->stats.sls_steps += s->totals_host[1] - s->totals_seen[1];
+    s->totals_seen[0] = s->totals_host[0];
+    s->totals_seen[1] = s->totals_host[1];
+    s->dirty = false;
+    return TSS_OK;
+}
+
+int tss_search_best_count(tss_search* s, int32_t* count) {
+    if (!s || !count) return TSS_E_INVALID;
+    int rc = search_sync(s);
+    if (rc) return rc;
+    int best = sls::NO_BOUND;
+    for (int g = 0; g < s->n_groups; g++) best = s->best_host[g].x < best ? s->best_host[g].x : best;
+    *count = best >= sls::NO_BOUND ? -1 : best;
+    s->e->stats.best_count = *count;
+    return TSS_OK;
+}
+
+int tss_search_set_bound(tss_search* s, int32_t count) {
+    if (!s) return TSS_E_INVALID;
+    tss_engine* e = s->e;
+    if (count < 0) return e->fail(TSS_E_INVALID, "tss_search_set_bound: negative bound");
+    int rc = search_sync(s);
+    if (rc) return rc;
+    std::vector<int> nb((size_t)s->n_groups);
+    TSS_CUDA(e, cudaMemcpy(nb.data(), s->bounds_dev, sizeof(int) * nb.size(), cudaMemcpyDeviceToHost));
+    for (int& b : nb) b = b < count ? b : count;
+    TSS_CUDA(e, cudaMemcpy(s->bounds_dev, nb.data(), sizeof(int) * nb.size(), cudaMemcpyHostToDevice));
+    return TSS_OK;
+}
+
+int tss_search_read_chains(tss_search* s, uint32_t* S, uint32_t* best_S, int32_t* k, int32_t* best, uint32_t* step, uint64_t* scored) {
+    if (!s) return TSS_E_INVALID;
+    tss_engine* e = s->e;
+    int rc = search_sync(s);
+    if (rc) return rc;
+    std::vector<sls::ChainState> st((size_t)s->n_chains);
+    TSS_CUDA(e, cudaMemcpy(st.data(), s->states, sizeof(sls::ChainState) * st.size(), cudaMemcpyDeviceToHost));
+    for (size_t c = 0; c < st.size(); c++) {
+        if (S) std::memcpy(S + c * 32, st[c].S, 128);
+        if (best_S) std::memcpy(best_S + c * 32, st[c].bestS, 128);
+        if (k) k[c] = st[c].k;
+        if (best) best[c] = st[c].best;
+        if (step) step[c] = st[c].step;
+        if (scored) scored[c] = ((uint64_t)st[c].scored_hi << 32) | st[c].scored_lo;
+    }
+    return TSS_OK;
+}
+
+int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_t* n_out) {
+    if (!s || !n_out) return TSS_E_INVALID;
+    tss_engine* e = s->e;
+    int rc = search_sync(s);
+    if (rc) return rc;
+    int2 best = s->best_host[0];
+    if (best.x >= sls::NO_BOUND || best.y < 0) { *n_out = 0; return e->fail(TSS_E_INVALID, "tss_search_best_layout: no complete layout found yet"); }
+    sls::ChainState st;
+    TSS_CUDA(e, cudaMemcpy(&st, s->states + best.y, sizeof st, cudaMemcpyDeviceToHost));
+    std::vector<tss_platform> plats;
+    for (int y = 0; y < s->h; y++)
+        for (int x = 0; x < s->w; x++)
+            if ((st.bestS[y] >> x) & 1u) plats.push_back(tss_platform{x, y, 1, 1, 0});
+    *n_out = (int)plats.size();
+    // every witness is re-validated by kernel (a) before it leaves the engine
+    int unsupported = tss_validate(e, s->grid.data(), s->w, s->h, plats.data(), (int)plats.size(), nullptr, nullptr);
+    if (unsupported < 0) return unsupported;
+    if (unsupported != 0 || (int)plats.size() != best.x)
+        return e->fail(TSS_E_CUDA, "internal error: SLS witness failed validation (%d unsupported tiles, %zu platforms, expected %d)", unsupported, plats.size(), best.x);
+    if ((int)plats.size() > cap || !out) return e->fail(TSS_E_CAPACITY, "tss_search_best_layout: need room for %zu platforms", plats.size());
+    std::memcpy(out, plats.data(), sizeof(tss_platform) * plats.size());
+    return TSS_OK;
+}
+
+int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,
+                          int32_t card_limit, uint64_t seed, int32_t budget_ms, int64_t max_steps, tss_platform* out,
+                          int32_t cap, int32_t* n_out) {
+    if (!e) return TSS_E_INVALID;
+    if (n_out) *n_out = 0;
+    tss_search_params p{seed, 0, 0, -1, 0};
+    tss_search* s = nullptr;
+    e->stats.interrupted = 0;
+    e->stats.best_count = -1;
+    int rc = tss_search_create(e, grid, w, h, defs, n_defs, &p, &s);
+    if (rc) return rc;
+    if (card_limit >= 0) rc = tss_search_set_bound(s, card_limit + 1);
+    const double t0 = now_ms();
+    const bool first_model_only = budget_ms <= 0 && max_steps <= 0;
+    int64_t done_steps = 0, epoch = 64;
+    int best = -1;
+    while (rc == TSS_OK) {
+        if (e->interrupted()) { e->stats.interrupted = 1; break; }
+        int64_t steps = epoch;
+        if (max_steps > 0 && done_steps + steps > max_steps) steps = max_steps - done_steps;
+        if (steps <= 0) break;
+        rc = tss_search_run(s, steps, 0);
+        if (rc) break;
+        rc = tss_search_best_count(s, &best);
+        if (rc) break;
+        done_steps += steps;
+        if (best == 0) break;
+        if (first_model_only && best >= 0) break;
+        if (budget_ms > 0 && now_ms() - t0 >= budget_ms) break;
+        if (epoch < 4096) epoch *= 2;
+    }
+    int result = TSS_UNKNOWN;
+    if (rc == TSS_OK && best >= 0) {
+        int n = 0;
+        rc = tss_search_best_layout(s, out, cap, &n);
+        if (n_out) *n_out = n;
+        if (rc == TSS_OK) result = TSS_SAT;
+    }
+    tss_search_destroy(s);
+    return rc != TSS_OK ? rc : result;
+}
+
+int tss_solve_batch(tss_engine* e, const uint8_t* grids, int32_t w, int32_t h, int64_t n, uint64_t seed, int64_t steps,
+                    int32_t* out_counts, uint32_t* out_layouts) {
+    if (!e) return TSS_E_INVALID;
+    if (!grids || !out_counts || w <= 0 || h <= 0 || n < 0 || steps <= 0) return e->fail(TSS_E_INVALID, "tss_solve_batch: bad arguments");
+    if (w > 32 || h > 32) return e->fail(TSS_E_UNSUPPORTED, "tss_solve_batch: terrains larger than 32x32 are not accelerated yet");
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    const int CPT = 4;                       // chains per terrain = one CTA
+    const int64_t CHUNK = 32768;             // terrains per pass (reach tables: 8 KB each)
+    const size_t tiles = (size_t)w * h;
+    e->stats.interrupted = 0;
+    double dev_ms = 0;
+    for (int64_t base = 0; base < n; base += CHUNK) {
+        if (e->interrupted()) { e->stats.interrupted = 1; return TSS_UNKNOWN; }
+        const int nt = (int)((n - base) < CHUNK ? (n - base) : CHUNK);
+        tss_search* s = new tss_search();
+        s->e = e; s->w = w; s->h = h; s->seed = seed; s->chain_offset = (uint32_t)(base * CPT);
+        s->n_chains = nt * CPT; s->n_groups = nt; s->chains_per_terrain = CPT;
+        int rc = search_alloc(e, s, nullptr, nt);
+        uint8_t* bytes = rc == TSS_OK ? (uint8_t*)e->dev(0, tiles * (size_t)nt) : nullptr;
+        if (rc == TSS_OK && !bytes) rc = TSS_E_CUDA;
+        if (rc == TSS_OK) {
+            cudaError_t err = cudaMemcpyAsync(bytes, grids + (size_t)base * tiles, tiles * (size_t)nt, cudaMemcpyHostToDevice, e->stream);
+            if (err != cudaSuccess) rc = e->fail(TSS_E_CUDA, "tss_solve_batch: %s", cudaGetErrorString(err));
+        }
+        if (rc == TSS_OK) {
+            pack_rows32_kernel<<<e->prop.multiProcessorCount * 8, 256, 0, e->stream>>>(bytes, w, h, nt, s->rows_dev);
+            e->stats.kernel_launches++;
+            rc = search_init_device(e, s, nt);
+        }
+        // epochs of 1024 steps so the four chains of a terrain share their bound and an interrupt is honoured
+        for (int64_t done = 0; rc == TSS_OK && done < steps; done += 1024) {
+            if (e->interrupted()) break;
+            rc = tss_search_run(s, (steps - done) < 1024 ? (steps - done) : 1024, 0);
+        }
+        if (rc == TSS_OK) rc = search_sync(s);
+        if (rc == TSS_OK) {
+            dev_ms += e->stats.device_ms;
+            for (int t = 0; t < nt; t++) out_counts[base + t] = s->best_host[t].x >= sls::NO_BOUND ? -1 : s->best_host[t].x;
+            if (out_layouts) {
+                std::vector<sls::ChainState> st((size_t)s->n_chains);
+                cudaError_t err = cudaMemcpy(st.data(), s->states, sizeof(sls::ChainState) * st.size(), cudaMemcpyDeviceToHost);
+                if (err != cudaSuccess) rc = e->fail(TSS_E_CUDA, "tss_solve_batch: %s", cudaGetErrorString(err));
+                for (int t = 0; t < nt && rc == TSS_OK; t++) {
+                    int c = s->best_host[t].y;
+                    for (int y = 0; y < h; y++) out_layouts[(size_t)(base + t) * h + y] = c >= 0 ? st[(size_t)c].bestS[y] : 0u;
+                }
+            }
+        }
+        search_free(s);
+        if (rc != TSS_OK) return rc;
+    }
+    e->stats.device_ms = dev_ms;
+    return e->interrupted() ? TSS_UNKNOWN : TSS_SAT;
+}
+
+int tss_measure_peaks(tss_engine* e, double* out, int32_t n_out) {
+    if (!e) return TSS_E_INVALID;
+    if (!out || n_out < 5) return e->fail(TSS_E_INVALID, "tss_measure_peaks: need room for 5 values");
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    return run_peaks(e, out, n_out);
+}
+
+}  // extern "C"

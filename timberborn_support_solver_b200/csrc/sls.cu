@@ -1,0 +1,323 @@
+// Kernel (b): batched stochastic local search over support sites (see sls_spec.hpp for the algorithm).
+// One layout per warp, lane r = grid row r, cover counts as five bit-planes in registers, reach windows of all
+// sites in an 8 KB shared-memory table per CTA, counter-based RNG.  No HBM traffic inside the step loop: the chain
+// state (320 B) is read at the start of an epoch and written back at its end.
+//
+// Candidate scoring is lane-parallel: lane i scores ONE candidate layout (the current layout with site v_i added or
+// u_i removed) exactly, as popcount(U & R(v_i)) resp. popcount(O & R(u_i)): seven indexed warp shuffles fetch the
+// window rows, seven shift/AND/POPC triples score them.  A swap step scores k removals and up to 25 additions.
+#include "engine.hpp"
+#include "sls_spec.hpp"
+
+namespace tss {
+namespace sls {
+
+constexpr int WARPS = 4;  // chains per CTA
+constexpr unsigned FULL = 0xffffffffu;
+
+struct Lane {
+    uint32_t C, S, c0, c1, c2, c3, c4, U, O;
+};
+
+__device__ __forceinline__ void derive(Lane& L) {
+    uint32_t hi = L.c1 | L.c2 | L.c3 | L.c4;
+    L.U = L.C & ~(L.c0 | hi);
+    L.O = L.c0 & ~hi;
+}
+
+// Row `lane` of the reach mask of site (x, y) in grid coordinates.
+__device__ __forceinline__ uint32_t row_mask(uint2 win, int x, int y, int lane) {
+    int dy = lane - y + 3;
+    int d = min(max(dy, 0), 6);
+    uint32_t m = d < 4 ? (win.x >> (7 * d)) : (win.y >> (7 * (d - 4)));
+    m = dy == d ? (m & 0x7fu) : 0u;
+    return x >= 3 ? m << (x - 3) : m >> (3 - x);
+}
+
+__device__ __forceinline__ void planes_add(Lane& L, uint32_t m) {
+    uint32_t t;
+    t = L.c0 & m; L.c0 ^= m; m = t;
+    t = L.c1 & m; L.c1 ^= m; m = t;
+    t = L.c2 & m; L.c2 ^= m; m = t;
+    t = L.c3 & m; L.c3 ^= m; m = t;
+    L.c4 ^= m;
+}
+__device__ __forceinline__ void planes_sub(Lane& L, uint32_t m) {
+    uint32_t t;
+    t = ~L.c0 & m; L.c0 ^= m; m = t;
+    t = ~L.c1 & m; L.c1 ^= m; m = t;
+    t = ~L.c2 & m; L.c2 ^= m; m = t;
+    t = ~L.c3 & m; L.c3 ^= m; m = t;
+    L.c4 ^= m;
+}
+
+// popcount(B & R(site at (x, y))) where B is a row-distributed bitboard (lane r holds row r) and `win` the site's
+// reach window.  Every lane scores its own site; all 32 lanes must call.
+__device__ __forceinline__ int score(uint32_t B, int x, int y, uint2 win) {
+    int s = 0;
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        uint32_t row = __shfl_sync(FULL, B, (y - 3 + j) & 31);
+        uint32_t m = (j < 4 ? (win.x >> (7 * j)) : (win.y >> (7 * (j - 4)))) & 0x7fu;
+        uint32_t wv = x >= 3 ? row >> (x - 3) : row << (3 - x);
+        s += __popc(wv & m);
+    }
+    return s;
+}
+
+__device__ __forceinline__ int pick_rotated(uint32_t bits, uint32_t r) {  // some set bit of `bits`, start offset r&31
+    uint32_t o = r & 31u;
+    uint32_t rot = __funnelshift_r(bits, bits, o);
+    return (int)((__ffs(rot) - 1 + o) & 31u);
+}
+
+// Reach windows: one thread per tile, three masked dilations inside the tile's own 7x7 window (geodesic paths of
+// length <= 3 never leave it).  rows: [n_terrains][32] ; out: [n_terrains][1024].
+__global__ void build_reach_kernel(const uint32_t* __restrict__ rows, int n_terrains, uint2* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_terrains * 1024) return;
+    int t = (int)(i >> 10), v = (int)(i & 1023), x = v & 31, y = v >> 5;
+    const uint32_t* C = rows + (size_t)t * 32;
+    uint32_t c[7], X[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        int yy = y - 3 + j;
+        uint32_t row = (yy >= 0 && yy < 32) ? C[yy] : 0u;
+        c[j] = (x >= 3 ? row >> (x - 3) : row << (3 - x)) & 0x7fu;
+        X[j] = 0;
+    }
+    X[3] = c[3] & 8u;  // the site itself, if it is a ceiling tile
+    for (int round = 0; round < kTerrainSupportDistance - 1; round++) {
+        uint32_t N[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            uint32_t v2 = X[j] | (X[j] << 1) | (X[j] >> 1);
+            if (j > 0) v2 |= X[j - 1];
+            if (j < 6) v2 |= X[j + 1];
+            N[j] = v2 & c[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 7; j++) X[j] = N[j];
+    }
+    out[i] = make_uint2(X[0] | (X[1] << 7) | (X[2] << 14) | (X[3] << 21), X[4] | (X[5] << 7) | (X[6] << 14));
+}
+
+struct WarpCtx {
+    const uint2* tab;
+    uint16_t* sites;
+    int lane;
+    uint32_t base;
+};
+
+// Removes the support with the smallest loss (random ties), skipping `exclude` when another choice exists.
+// Returns the removed site.  Scores k candidate layouts.
+__device__ __forceinline__ int remove_min_loss(Lane& L, const WarpCtx& w, int& k, uint32_t step, int exclude) {
+    uint32_t best_key = 0xffffffffu;
+    int best_i = 0;
+    for (int b = 0; b < k; b += 32) {
+        int i = b + w.lane;
+        bool valid = i < k;
+        int v = valid ? w.sites[i] : 0;
+        uint2 win = w.tab[v];
+        int loss = score(L.O, v & 31, v >> 5, win);
+        uint32_t key = (valid && !(v == exclude && k > 1)) ? (((uint32_t)loss << 16) | (rnd(w.base, step, SALT_REMOVE + i) & 0xffffu)) : 0xffffffffu;
+        uint32_t mn = __reduce_min_sync(FULL, key);
+        if (mn < best_key) {
+            best_key = mn;
+            best_i = b + __ffs(__ballot_sync(FULL, key == mn)) - 1;
+        }
+    }
+    int u = w.sites[best_i];
+    __syncwarp();
+    if (w.lane == 0) w.sites[best_i] = w.sites[k - 1];
+    __syncwarp();
+    k--;
+    planes_sub(L, row_mask(w.tab[u], u & 31, u >> 5, w.lane));
+    derive(L);
+    if (w.lane == (u >> 5)) L.S &= ~(1u << (u & 31));
+    return u;
+}
+
+__global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restrict__ terrain_rows, const uint2* __restrict__ rtabs,
+                                                        ChainState* __restrict__ states, int n_chains, int chains_per_terrain,
+                                                        uint32_t chain_offset, uint64_t seed, long long steps,
+                                                        const int* __restrict__ bounds, int target, int noise_pct,
+                                                        const volatile int* interrupt,
+                                                        unsigned long long* __restrict__ totals) {
+    __shared__ uint2 tab[1024];
+    __shared__ uint16_t sites_all[WARPS][MAX_SITES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chain = blockIdx.x * WARPS + warp;
+    const int terrain = chains_per_terrain > 0 ? (blockIdx.x * WARPS) / chains_per_terrain : 0;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) tab[i] = rtabs[(size_t)terrain * 1024 + i];
+    __syncthreads();
+    if (chain >= n_chains) return;
+    ChainState& st = states[chain];
+    if (st.done) return;
+
+    // bound of this epoch: smallest complete count known for this terrain when the epoch started (group = terrain)
+    const int epoch_bound = bounds[chains_per_terrain > 0 ? terrain : 0];
+    WarpCtx w{tab, sites_all[warp], lane, chain_base(seed, chain_offset + (uint32_t)chain)};
+    Lane L;
+    L.C = terrain_rows[(size_t)terrain * 32 + lane];
+    L.S = st.S[lane];
+    uint32_t bestS = st.bestS[lane];
+    int k = st.k, best = st.best, tabu_add = st.tabu_add, tabu_rem = st.tabu_rem, done = 0;
+    uint32_t step = st.step;
+    unsigned long long scored = 0;
+
+    // rebuild the site list (row-major) and the cover-count planes from S
+    {
+        int c = __popc(L.S), off = c;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, off, o); if (lane >= o) off += t; }
+        off -= c;
+        for (uint32_t bits = L.S; bits; bits &= bits - 1) w.sites[off++] = (uint16_t)(lane * 32 + __ffs(bits) - 1);
+        __syncwarp();
+        L.c0 = L.c1 = L.c2 = L.c3 = L.c4 = 0;
+        for (int i = 0; i < k; i++) { int v = w.sites[i]; planes_add(L, row_mask(tab[v], v & 31, v >> 5, lane)); }
+        derive(L);
+    }
+
+    // diamond of the 25 window positions within Manhattan distance 3 (a superset of every reach set)
+    int ldx, ldy, lbit;
+    {
+        int i = lane, r = (i >= 1) + (i >= 4) + (i >= 9) + (i >= 16) + (i >= 21) + (i >= 24);
+        int start = r <= 4 ? r * r : (r == 5 ? 21 : 24);
+        ldy = r - 3;
+        ldx = (i - start) - (3 - abs(ldy));
+        lbit = 7 * (ldy + 3) + ldx + 3;
+    }
+
+    long long it = 0;
+    for (; it < steps; it++, step++) {
+        if ((it & 1023) == 1023 && *interrupt) break;
+        const int limit = min(epoch_bound, best);
+        if (k >= limit) {  // 1. too many supports for an improvement: drop one
+            if (k == 0) { done = 1; break; }
+            scored += (unsigned)k;
+            tabu_add = remove_min_loss(L, w, k, step, -1);
+            continue;
+        }
+        const uint32_t rowmask = __ballot_sync(FULL, L.U != 0);
+        if (rowmask == 0) {  // 2. complete layout with k < limit supports
+            best = k;
+            bestS = L.S;
+            if (k <= target || k == 0) { done = 1; it++; step++; break; }
+            continue;
+        }
+        if (k == limit - 1 && k > 0) {  // 3. at capacity: swap = remove + add
+            scored += (unsigned)k;
+            tabu_add = remove_min_loss(L, w, k, step, tabu_rem);
+        }
+        const uint32_t rowmask2 = __ballot_sync(FULL, L.U != 0);
+        const int y = pick_rotated(rowmask2, rnd(w.base, step, SALT_ROW));
+        const uint32_t Urow = __shfl_sync(FULL, L.U, y);
+        const int x = pick_rotated(Urow, rnd(w.base, step, SALT_COL));
+        const uint2 wt = tab[y * 32 + x];
+        const bool valid = lane < 25 && ((lbit < 28 ? (wt.x >> lbit) : (wt.y >> (lbit - 28))) & 1u);
+        const int cx = x + ldx, cy = y + ldy, cv = valid ? cy * 32 + cx : 0;
+        const uint32_t vmask = __ballot_sync(FULL, valid);
+        const int nc = __popc(vmask);
+        int chosen;
+        if ((int)(rnd(w.base, step, SALT_NOISE) % 100u) < noise_pct) {
+            chosen = __fns(vmask, 0, (int)(rnd(w.base, step, SALT_PICK) % (uint32_t)nc) + 1);
+        } else {
+            const uint2 wc = tab[cv];
+            int g = score(L.U, cv & 31, cv >> 5, wc);
+            uint32_t key = (valid && !(cv == tabu_add && nc > 1)) ? (((uint32_t)(g + 1) << 16) | (rnd(w.base, step, SALT_ADD + lbit) & 0xffffu)) : 0u;
+            uint32_t mx = __reduce_max_sync(FULL, key);
+            chosen = __ffs(__ballot_sync(FULL, key == mx)) - 1;
+            scored += (unsigned)nc;
+        }
+        const int v = __shfl_sync(FULL, cv, chosen);
+        planes_add(L, row_mask(tab[v], v & 31, v >> 5, lane));
+        derive(L);
+        if (lane == (v >> 5)) L.S |= 1u << (v & 31);
+        if (lane == 0) w.sites[k] = (uint16_t)v;
+        __syncwarp();
+        k++;
+        tabu_rem = v;
+    }
+
+    st.S[lane] = L.S;
+    st.bestS[lane] = bestS;
+    if (lane == 0) {
+        st.k = k; st.best = best; st.step = step; st.tabu_add = tabu_add; st.tabu_rem = tabu_rem; st.done = done;
+        unsigned long long tot = ((unsigned long long)st.scored_hi << 32 | st.scored_lo) + scored;
+        st.scored_lo = (uint32_t)tot; st.scored_hi = (uint32_t)(tot >> 32);
+        st.steps_done += (uint32_t)it;
+        atomicAdd(&totals[0], scored);
+        atomicAdd(&totals[1], (unsigned long long)it);
+    }
+}
+
+// Smallest `best` over chains [c0, c0+count) per group (ties: lowest chain).  One CTA per group.
+// out[group] = (best count or NO_BOUND, chain index)
+__global__ void best_reduce_kernel(const ChainState* __restrict__ states, int chains_per_group, int n_chains, int2* __restrict__ out,
+                                   int* __restrict__ bounds) {
+    __shared__ unsigned long long sm[256];
+    const int c0 = blockIdx.x * chains_per_group, c1 = min(c0 + chains_per_group, n_chains);
+    unsigned long long key = ~0ull;
+    for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+        unsigned long long kk = ((unsigned long long)(uint32_t)states[c].best << 32) | (uint32_t)c;
+        key = kk < key ? kk : key;
+    }
+    sm[threadIdx.x] = key;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o && sm[threadIdx.x + o] < sm[threadIdx.x]) sm[threadIdx.x] = sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int2 r = sm[0] == ~0ull ? make_int2(NO_BOUND, -1) : make_int2((int)(sm[0] >> 32), (int)(sm[0] & 0xffffffffu));
+        out[blockIdx.x] = r;
+        if (r.x < bounds[blockIdx.x]) bounds[blockIdx.x] = r.x;  // next epoch looks for fewer than the best known
+    }
+}
+
+__global__ void init_states_kernel(ChainState* states, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ChainState s;
+    for (int r = 0; r < 32; r++) { s.S[r] = 0; s.bestS[r] = 0; }
+    s.k = 0; s.best = NO_BOUND; s.step = 0; s.tabu_add = -1; s.tabu_rem = -1; s.done = 0;
+    s.scored_lo = s.scored_hi = 0; s.steps_done = 0;
+    for (int r = 0; r < 7; r++) s.pad[r] = 0;
+    states[i] = s;
+}
+
+}  // namespace sls
+
+// ---------------------------------------------------------------------------------------------- launch helpers
+int sls_build_reach(tss_engine* e, const uint32_t* rows_dev, int n_terrains, uint2* tabs_dev) {
+    long long total = (long long)n_terrains * 1024;
+    sls::build_reach_kernel<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(rows_dev, n_terrains, tabs_dev);
+    TSS_CHECK_LAUNCH(e);
+    e->stats.kernel_launches++;
+    return TSS_OK;
+}
+int sls_init_states(tss_engine* e, sls::ChainState* states, int n) {
+    sls::init_states_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(states, n);
+    TSS_CHECK_LAUNCH(e);
+    e->stats.kernel_launches++;
+    return TSS_OK;
+}
+int sls_run(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls::ChainState* states, int n_chains,
+            int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
+            int noise_pct, unsigned long long* totals_dev) {
+    int blocks = (n_chains + sls::WARPS - 1) / sls::WARPS;
+    sls::sls_kernel<<<blocks, sls::WARPS * 32, 0, e->stream>>>(rows_dev, tabs_dev, states, n_chains, chains_per_terrain, chain_offset, seed,
+                                                             steps, bounds_dev, target, noise_pct, e->interrupt_dev, totals_dev);
+    TSS_CHECK_LAUNCH(e);
+    e->stats.kernel_launches++;
+    return TSS_OK;
+}
+int sls_best_reduce(tss_engine* e, const sls::ChainState* states, int chains_per_group, int n_chains, int n_groups, int2* out_dev,
+                    int* bounds_dev) {
+    sls::best_reduce_kernel<<<n_groups, n_groups > 1 ? 32 : 256, 0, e->stream>>>(states, chains_per_group, n_chains, out_dev, bounds_dev);
+    TSS_CHECK_LAUNCH(e);
+    e->stats.kernel_launches++;
+    return TSS_OK;
+}
+
+}  // namespace tss

@@ -1,0 +1,66 @@
+// Specification constants of the batched stochastic local search (kernel (b)); shared by sls.cu and by the CPU
+// model in oracle/sls_model.cpp that the parity tests replay it against (the model re-declares the same values and
+// a test compares them — the oracle never includes product headers).
+//
+// Problem: with 1x1 supports the encoder's CNF is "choose S, every ceiling tile within geodesic
+// distance <= 3 (through ceiling tiles) of a ceiling tile in S, |S| <= n" (src/encoder.rs:500-544, 619-667).
+// A site's reach R(s) is the result of validate()'s three masked dilations from {s} (platform_layout.rs:127-141); it
+// lives in the 7x7 window around s and is stored as 49 bits (row dy in bits [7*dy, 7*dy+7)).
+//
+// One chain = one layout = one warp.  Lane r owns grid row r: ceiling C, supports S, and the cover count of every tile
+// as five bit-planes c0..c4 (a tile is covered by at most 25 sites).  uncovered U = C & ~(c0|..|c4), covered-once
+// O = c0 & ~(c1|..|c4).
+//
+// A step with bound L (smallest complete count known at the start of the epoch, or the chain's own best):
+//   1. k >= L                -> drop the support with the smallest loss (tiles only it covers), random ties
+//   2. U empty               -> record (k, S) as the chain's best; done if k <= target
+//   3. otherwise, if k == L-1 -> remove the min-loss support other than the one just added (tabu)
+//      then pick a random uncovered tile t and add the site v in R(t) with the largest gain |U & R(v)| (random
+//      ties; with probability noise% a random site of R(t) instead), never the site just removed unless it is the
+//      only candidate.
+// Random numbers are counter based: rnd(salt) = fmix32(base ^ step*K1 ^ salt*K2), base keyed by (seed, global chain).
+#pragma once
+#include <cstdint>
+
+namespace tss {
+namespace sls {
+
+constexpr uint32_t K1 = 0x9E3779B9u, K2 = 0x85EBCA6Bu;
+constexpr int SALT_ROW = 1, SALT_COL = 2, SALT_NOISE = 3, SALT_PICK = 4, SALT_REMOVE = 1000, SALT_ADD = 200;
+constexpr int DEFAULT_NOISE_PCT = 20;
+constexpr int MAX_SITES = 1024;   // supports per chain (<= tiles of a 32x32 grid)
+constexpr int NO_BOUND = 1 << 20;
+
+#if defined(__CUDACC__)
+#define TSS_HD __host__ __device__ __forceinline__
+#else
+#define TSS_HD inline
+#endif
+
+TSS_HD uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+TSS_HD uint32_t chain_base(uint64_t seed, uint32_t chain) {
+    return fmix32((uint32_t)seed ^ fmix32((uint32_t)(seed >> 32) + chain * K1 + 0x5bd1e995u));
+}
+TSS_HD uint32_t rnd(uint32_t base, uint32_t step, uint32_t salt) { return fmix32(base ^ (step * K1) ^ (salt * K2)); }
+
+// Persistent per-chain state in HBM (one 320-byte record per chain).
+struct ChainState {
+    uint32_t S[32];      // current supports, row r in S[r]
+    uint32_t bestS[32];  // best complete layout found by this chain
+    int32_t k;           // current number of supports
+    int32_t best;        // supports in bestS, NO_BOUND if none yet
+    uint32_t step;       // RNG step counter (persists across epochs)
+    int32_t tabu_add;    // site removed last (not re-added immediately), -1 none
+    int32_t tabu_rem;    // site added last (not removed immediately), -1 none
+    int32_t done;        // reached the target or nothing left to do
+    uint32_t scored_lo, scored_hi;  // candidate layouts scored by this chain (64-bit counter)
+    uint32_t steps_done;
+    uint32_t pad[7];
+};
+static_assert(sizeof(ChainState) == 320, "ChainState layout");
+
+}  // namespace sls
+}  // namespace tss
