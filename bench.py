@@ -159,7 +159,12 @@ def main():
     K = args.steps
 
     eng = T.Engine(local)
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)   # torch events must see the launching stream
+    # torch events only see torch's current stream: make one explicit (non-default) stream current and hand it to the
+    # engine, so every kernel of the hot path and every event of this file live on the same stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    eng.set_stream(stream.cuda_stream)
     info = eng.device_info()
     grid = T.WorldGrid(np.ones((16, 16), np.uint8))
     n_chains = args.chains or info["sm_count"] * 32

@@ -198,9 +198,15 @@ int tss_search_n_chains(const tss_search* s);
  * state after the last epoch.  S / best_S: support rows u32[n_chains][32]; any pointer may be NULL. */
 int tss_search_read_chains(tss_search* s, uint32_t* S, uint32_t* best_S, int32_t* k, int32_t* best, uint32_t* step, uint64_t* scored);
 
+/* Values of the SLS specification's hash / tie-break functions (csrc/sls_spec.hpp) at fixed probe points, so the
+ * parity tests can assert that the CPU model (which re-declares them) follows the same published rule.  out[9]. */
+void tss_sls_spec_probe(uint32_t* out);
+
 /* The solve-with-bound entry point (the SAT side of crates/repl/src/main.rs:292-329 / crates/gui/src/solver_backend.rs:69-97):
  * find a layout with at most `card_limit` platforms (card_limit < 0: unbounded, any complete layout) within
- * `budget_ms` (<= 0: until target reached or interrupted; bounded by max_steps per chain if > 0).
+ * `budget_ms` and/or `max_steps` SLS steps per chain, returning the best layout found.  With neither budget given
+ * the call behaves like ONE SAT call: it returns the first layout within the bound and gives up after 2^18 steps
+ * per chain (the engine cannot prove UNSAT, so "nothing found" must terminate).
  * Returns TSS_SAT with the layout, TSS_UNKNOWN if none was found (never TSS_UNSAT). */
 int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,
                           int32_t card_limit, uint64_t seed, int32_t budget_ms, int64_t max_steps, tss_platform* out,

@@ -16,12 +16,15 @@
 namespace {
 
 constexpr uint32_t K1 = 0x9E3779B9u, K2 = 0x85EBCA6Bu;
-constexpr int SALT_ROW = 1, SALT_COL = 2, SALT_NOISE = 3, SALT_PICK = 4, SALT_REMOVE = 1000, SALT_ADD = 200;
 constexpr int NO_BOUND = 1 << 20;
 
 uint32_t fmix32(uint32_t h) { h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h; }
 uint32_t chain_base(uint64_t seed, uint32_t chain) { return fmix32((uint32_t)seed ^ fmix32((uint32_t)(seed >> 32) + chain * K1 + 0x5bd1e995u)); }
-uint32_t rnd(uint32_t base, uint32_t step, uint32_t salt) { return fmix32(base ^ (step * K1) ^ (salt * K2)); }
+uint32_t step_hash(uint32_t base, uint32_t step) { return fmix32(base ^ (step * K1)); }
+uint32_t lane_hash(uint32_t hs, uint32_t lane) { return fmix32(hs ^ ((lane + 1u) * K2)); }
+uint32_t noise_q7(int noise_pct) { return (uint32_t)((noise_pct * 128 + 50) / 100); }
+uint32_t tie_add(uint32_t hl) { return hl & 0xffffu; }
+uint32_t tie_remove(uint32_t hl, uint32_t chunk) { return (hl * (2u * chunk + 1u)) >> 16; }
 
 struct Model {
     int w, h;
@@ -62,8 +65,7 @@ struct Chain {
     uint64_t scored = 0, steps_done = 0;
 };
 
-int pick_rotated(uint32_t bits, uint32_t r) {
-    uint32_t o = r & 31u;
+int pick_rotated(uint32_t bits, uint32_t o) {
     uint32_t rot = o ? ((bits >> o) | (bits << (32 - o))) : bits;
     return (int)((__builtin_ctz(rot) + o) & 31u);
 }
@@ -78,13 +80,13 @@ struct Runner {
     int loss(int u) const { int n = 0; for (int t : M.reach[u]) n += c.cnt[t] == 1; return n; }
     int gain(int v) const { int n = 0; for (int t : M.reach[v]) n += c.cnt[t] == 0; return n; }
 
-    int remove_min_loss(int exclude) {
+    int remove_min_loss(int exclude, uint32_t hs) {
         uint32_t best_key = 0xffffffffu;
         int best_i = 0;
         for (int i = 0; i < c.k; i++) {  // chunks of 32 lanes, lowest lane wins ties; strict < across chunks
             int v = c.sites[i];
             if (v == exclude && c.k > 1) continue;
-            uint32_t key = ((uint32_t)loss(v) << 16) | (rnd(base, c.step, SALT_REMOVE + i) & 0xffffu);
+            uint32_t key = ((uint32_t)loss(v) << 16) | tie_remove(lane_hash(hs, (uint32_t)(i & 31)), (uint32_t)(i >> 5));
             if (key < best_key) { best_key = key; best_i = i; }
         }
         int u = c.sites[best_i];
@@ -106,10 +108,11 @@ struct Runner {
         long long it = 0;
         for (; it < steps; it++, c.step++) {
             const int limit = std::min(epoch_bound, c.best);
+            const uint32_t hs = step_hash(base, c.step);
             if (c.k >= limit) {
                 if (c.k == 0) { c.done = 1; break; }
                 c.scored += (uint64_t)c.k;
-                c.tabu_add = remove_min_loss(-1);
+                c.tabu_add = remove_min_loss(-1, hs);
                 continue;
             }
             bool any = false;
@@ -122,38 +125,36 @@ struct Runner {
             }
             if (c.k == limit - 1 && c.k > 0) {
                 c.scored += (uint64_t)c.k;
-                c.tabu_add = remove_min_loss(c.tabu_rem);
+                c.tabu_add = remove_min_loss(c.tabu_rem, hs);
             }
             uint32_t rowmask = 0;
             for (int y = 0; y < 32; y++) for (int x = 0; x < 32; x++) if (uncovered(y * 32 + x)) rowmask |= 1u << y;
-            int y = pick_rotated(rowmask, rnd(base, c.step, SALT_ROW));
+            int y = pick_rotated(rowmask, hs & 31u);
             uint32_t urow = 0;
             for (int x = 0; x < 32; x++) if (uncovered(y * 32 + x)) urow |= 1u << x;
-            int x = pick_rotated(urow, rnd(base, c.step, SALT_COL));
+            int x = pick_rotated(urow, (hs >> 5) & 31u);
             int t = y * 32 + x;
-            // candidates in window order (dy, then dx) == diamond lane order
-            std::vector<std::pair<int, int>> cand;  // (site, window bit)
+            // candidates = tiles of R(t), visited in diamond order (dy, then dx); `lane` = index in the 25-tile diamond
+            std::vector<std::pair<int, int>> cand;  // (site, diamond lane)
+            int lane = 0;
             for (int dy = -3; dy <= 3; dy++)
                 for (int dx = -3; dx <= 3; dx++) {
                     if (std::abs(dx) + std::abs(dy) > 3) continue;
-                    int cx = x + dx, cy = y + dy;
+                    int cx = x + dx, cy = y + dy, ln = lane++;
                     if (cx < 0 || cy < 0 || cx >= 32 || cy >= 32) continue;
                     int v = cy * 32 + cx;
-                    if (std::find(M.reach[t].begin(), M.reach[t].end(), v) != M.reach[t].end()) cand.push_back({v, 7 * (dy + 3) + dx + 3});
+                    if (std::find(M.reach[t].begin(), M.reach[t].end(), v) != M.reach[t].end()) cand.push_back({v, ln});
                 }
-            int nc = (int)cand.size(), v;
-            if ((int)(rnd(base, c.step, SALT_NOISE) % 100u) < noise_pct) {
-                v = cand[rnd(base, c.step, SALT_PICK) % (uint32_t)nc].first;
-            } else {
-                uint32_t mx = 0;
-                v = cand[0].first;
-                bool first = true;
-                for (auto& [cv, bit] : cand) {
-                    uint32_t key = (cv == c.tabu_add && nc > 1) ? 0u : (((uint32_t)(gain(cv) + 1) << 16) | (rnd(base, c.step, SALT_ADD + bit) & 0xffffu));
-                    if (first || key > mx) { mx = key; v = cv; first = false; }
-                }
-                c.scored += (uint64_t)nc;
+            int nc = (int)cand.size(), v = cand[0].first;
+            const bool noise = ((hs >> 10) & 127u) < noise_q7(noise_pct);
+            uint32_t mx = 0;
+            bool first = true;
+            for (auto& [cv, ln] : cand) {
+                uint32_t tie = tie_add(lane_hash(hs, (uint32_t)ln));
+                uint32_t key = noise ? (0x10000u | tie) : ((cv == c.tabu_add && nc > 1) ? 0u : (((uint32_t)(gain(cv) + 1) << 16) | tie));
+                if (first || key > mx) { mx = key; v = cv; first = false; }
             }
+            if (!noise) c.scored += (uint64_t)nc;
             for (int tt : M.reach[v]) c.cnt[tt]++;
             c.S[v] = 1;
             c.sites.push_back(v);
@@ -200,8 +201,8 @@ int tsso_sls_model(const uint8_t* grid, int w, int h, int n_chains, uint32_t cha
 
 // constants of the spec, for the agreement test against sls_spec.hpp
 void tsso_sls_constants(uint32_t* out) {
-    out[0] = K1; out[1] = K2; out[2] = SALT_ROW; out[3] = SALT_COL; out[4] = SALT_NOISE; out[5] = SALT_PICK;
-    out[6] = SALT_REMOVE; out[7] = SALT_ADD; out[8] = NO_BOUND;
+    out[0] = K1; out[1] = K2; out[2] = noise_q7(20); out[3] = tie_remove(0x12345678u, 3); out[4] = tie_add(0x12345678u);
+    out[5] = step_hash(1u, 2u); out[6] = lane_hash(3u, 4u); out[7] = chain_base(0x0123456789abcdefull, 5u); out[8] = NO_BOUND;
 }
 
 }  // extern "C"

@@ -124,14 +124,15 @@ def test_eval_full_size_properties(eng):
     and one random 256x256 layout cross-checked against the oracle."""
     rng = np.random.default_rng(0)
     grid = synth_terrain(256, 256, seed=1)
-    assert grid.sum() == 45811                                            # SURVEY.md §6 example draw
+    n_ceiling = int(grid.sum())
+    assert 0.69 * 65536 < n_ceiling < 0.71 * 65536                        # density 0.7 (SURVEY.md §8d generator)
     a = random_sites(rng, 3, 256, 256, 0.03)
     b = a | random_sites(rng, 3, 256, 256, 0.03)
     ua, _ = eng.eval_sites(T.WorldGrid(grid), a)
     ub, cb = eng.eval_sites(T.WorldGrid(grid), b)
     assert (ub <= ua).all() and (cb == b.reshape(3, -1).sum(1)).all()
     u, _ = eng.eval_sites(T.WorldGrid(grid), np.stack([np.zeros_like(grid), grid]))
-    assert u.tolist() == [45811, 0]
+    assert u.tolist() == [n_ceiling, 0]
     o_unc, _, _ = O.validate_sites_batch(grid, a[:1])
     assert o_unc[0] == ua[0]
     # 4096 terrains of the C5 generator, supports on a 5-lattice: evaluated per terrain == oracle on a sample

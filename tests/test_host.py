@@ -43,15 +43,14 @@ def test_engine_needs_a_gpu_no_fallback():
 
 
 def test_sls_spec_constants_agree_with_model():
-    spec = open(os.path.join(ROOT, "timberborn_support_solver_b200", "csrc", "sls_spec.hpp")).read()
-    out = (C.c_uint32 * 9)()
-    O.lib().tsso_sls_constants(out)
-    want = {"K1": out[0], "K2": out[1], "SALT_ROW": out[2], "SALT_COL": out[3], "SALT_NOISE": out[4], "SALT_PICK": out[5],
-            "SALT_REMOVE": out[6], "SALT_ADD": out[7]}
-    for name, val in want.items():
-        m = re.search(rf"\b{name} = (0x[0-9A-Fa-f]+|\d+)", spec)
-        assert m and int(m.group(1), 0) == val, name
-    assert "NO_BOUND = 1 << 20" in spec and out[8] == 1 << 20
+    """The CPU model re-declares the SLS spec's hash / tie-break functions (oracle never includes product headers):
+    both sides evaluate them at the same probe points."""
+    model = (C.c_uint32 * 9)()
+    O.lib().tsso_sls_constants(model)
+    product = (C.c_uint32 * 9)()
+    T.load().tss_sls_spec_probe(product)
+    assert list(model) == list(product)
+    assert model[0] == 0x9E3779B9 and model[2] == 26 and model[8] == 1 << 20
 
 
 # ---- world -----------------------------------------------------------------------------------------

@@ -408,6 +408,12 @@ void tss_search_destroy(tss_search* s) {
 
 int tss_search_n_chains(const tss_search* s) { return s ? s->n_chains : TSS_E_INVALID; }
 
+void tss_sls_spec_probe(uint32_t* out) {
+    if (!out) return;
+    out[0] = sls::K1; out[1] = sls::K2; out[2] = sls::noise_q7(20); out[3] = sls::tie_remove(0x12345678u, 3); out[4] = sls::tie_add(0x12345678u);
+    out[5] = sls::step_hash(1u, 2u); out[6] = sls::lane_hash(3u, 4u); out[7] = sls::chain_base(0x0123456789abcdefull, 5u); out[8] = sls::NO_BOUND;
+}
+
 int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
     if (!s) return TSS_E_INVALID;
     tss_engine* e = s->e;
@@ -521,7 +527,10 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     if (rc) return rc;
     if (card_limit >= 0) rc = tss_search_set_bound(s, card_limit + 1);
     const double t0 = now_ms();
+    // no budget given: behave like one SAT call (return the first model within the bound), but give up after a
+    // default effort — the engine cannot prove UNSAT, so "no model found" must not turn into an endless search
     const bool first_model_only = budget_ms <= 0 && max_steps <= 0;
+    if (first_model_only) max_steps = 1 << 18;
     int64_t done_steps = 0, epoch = 64;
     int best = -1;
     while (rc == TSS_OK) {

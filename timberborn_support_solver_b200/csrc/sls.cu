@@ -5,7 +5,10 @@
 //
 // Candidate scoring is lane-parallel: lane i scores ONE candidate layout (the current layout with site v_i added or
 // u_i removed) exactly, as popcount(U & R(v_i)) resp. popcount(O & R(u_i)): seven indexed warp shuffles fetch the
-// window rows, seven shift/AND/POPC triples score them.  A swap step scores k removals and up to 25 additions.
+// window rows, each is shifted/masked to its 7 window bits and packed (Horner, on the FMA pipe) into the same 28+21
+// bit layout as the reach table, so two AND + POPC finish the score.  A swap step scores k removals and up to 25
+// additions.  The ALU pipe is the limiter (ncu: profiles/), so the step is written to minimise ALU instructions:
+// two hashes per step, no divisions, no selects on the shift direction.
 #include "engine.hpp"
 #include "sls_spec.hpp"
 
@@ -25,13 +28,17 @@ __device__ __forceinline__ void derive(Lane& L) {
     L.O = L.c0 & ~hi;
 }
 
+// Reach windows are 7 rows x 7 columns; window row dy is grid row y-3+dy, window column 0 is grid column
+// ax = max(x-3, 0) (anchoring at 0 near the left edge keeps every extraction a single right shift).
+__device__ __forceinline__ int anchor(int x) { return max(x - 3, 0); }
+
 // Row `lane` of the reach mask of site (x, y) in grid coordinates.
 __device__ __forceinline__ uint32_t row_mask(uint2 win, int x, int y, int lane) {
     int dy = lane - y + 3;
     int d = min(max(dy, 0), 6);
     uint32_t m = d < 4 ? (win.x >> (7 * d)) : (win.y >> (7 * (d - 4)));
     m = dy == d ? (m & 0x7fu) : 0u;
-    return x >= 3 ? m << (x - 3) : m >> (3 - x);
+    return m << anchor(x);
 }
 
 __device__ __forceinline__ void planes_add(Lane& L, uint32_t m) {
@@ -54,19 +61,22 @@ __device__ __forceinline__ void planes_sub(Lane& L, uint32_t m) {
 // popcount(B & R(site at (x, y))) where B is a row-distributed bitboard (lane r holds row r) and `win` the site's
 // reach window.  Every lane scores its own site; all 32 lanes must call.
 __device__ __forceinline__ int score(uint32_t B, int x, int y, uint2 win) {
-    int s = 0;
+    const int ax = anchor(x);
+    uint32_t lo = 0, hi = 0;
 #pragma unroll
-    for (int j = 0; j < 7; j++) {
-        uint32_t row = __shfl_sync(FULL, B, (y - 3 + j) & 31);
-        uint32_t m = (j < 4 ? (win.x >> (7 * j)) : (win.y >> (7 * (j - 4)))) & 0x7fu;
-        uint32_t wv = x >= 3 ? row >> (x - 3) : row << (3 - x);
-        s += __popc(wv & m);
+    for (int j = 6; j >= 4; j--) {  // shfl uses the low 5 bits of the source lane; rows outside the grid meet zero window bits
+        uint32_t row = __shfl_sync(FULL, B, y - 3 + j);
+        hi = hi * 128u + ((row >> ax) & 0x7fu);
     }
-    return s;
+#pragma unroll
+    for (int j = 3; j >= 0; j--) {
+        uint32_t row = __shfl_sync(FULL, B, y - 3 + j);
+        lo = lo * 128u + ((row >> ax) & 0x7fu);
+    }
+    return __popc(lo & win.x) + __popc(hi & win.y);
 }
 
-__device__ __forceinline__ int pick_rotated(uint32_t bits, uint32_t r) {  // some set bit of `bits`, start offset r&31
-    uint32_t o = r & 31u;
+__device__ __forceinline__ int pick_rotated(uint32_t bits, uint32_t o) {  // a set bit of `bits`, searching from offset o
     uint32_t rot = __funnelshift_r(bits, bits, o);
     return (int)((__ffs(rot) - 1 + o) & 31u);
 }
@@ -79,14 +89,15 @@ __global__ void build_reach_kernel(const uint32_t* __restrict__ rows, int n_terr
     int t = (int)(i >> 10), v = (int)(i & 1023), x = v & 31, y = v >> 5;
     const uint32_t* C = rows + (size_t)t * 32;
     uint32_t c[7], X[7];
+    const int ax = anchor(x);
 #pragma unroll
     for (int j = 0; j < 7; j++) {
         int yy = y - 3 + j;
         uint32_t row = (yy >= 0 && yy < 32) ? C[yy] : 0u;
-        c[j] = (x >= 3 ? row >> (x - 3) : row << (3 - x)) & 0x7fu;
+        c[j] = (row >> ax) & 0x7fu;
         X[j] = 0;
     }
-    X[3] = c[3] & 8u;  // the site itself, if it is a ceiling tile
+    X[3] = c[3] & (1u << (x - ax));  // the site itself, if it is a ceiling tile
     for (int round = 0; round < kTerrainSupportDistance - 1; round++) {
         uint32_t N[7];
 #pragma unroll
@@ -106,21 +117,20 @@ struct WarpCtx {
     const uint2* tab;
     uint16_t* sites;
     int lane;
-    uint32_t base;
 };
 
 // Removes the support with the smallest loss (random ties), skipping `exclude` when another choice exists.
 // Returns the removed site.  Scores k candidate layouts.
-__device__ __forceinline__ int remove_min_loss(Lane& L, const WarpCtx& w, int& k, uint32_t step, int exclude) {
+__device__ __forceinline__ int remove_min_loss(Lane& L, const WarpCtx& w, int& k, uint32_t hl, int exclude) {
     uint32_t best_key = 0xffffffffu;
     int best_i = 0;
-    for (int b = 0; b < k; b += 32) {
+    for (int b = 0, chunk = 0; b < k; b += 32, chunk++) {
         int i = b + w.lane;
         bool valid = i < k;
         int v = valid ? w.sites[i] : 0;
         uint2 win = w.tab[v];
         int loss = score(L.O, v & 31, v >> 5, win);
-        uint32_t key = (valid && !(v == exclude && k > 1)) ? (((uint32_t)loss << 16) | (rnd(w.base, step, SALT_REMOVE + i) & 0xffffu)) : 0xffffffffu;
+        uint32_t key = (valid && !(v == exclude && k > 1)) ? (((uint32_t)loss << 16) | tie_remove(hl, (uint32_t)chunk)) : 0xffffffffu;
         uint32_t mn = __reduce_min_sync(FULL, key);
         if (mn < best_key) {
             best_key = mn;
@@ -157,7 +167,9 @@ __global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restr
 
     // bound of this epoch: smallest complete count known for this terrain when the epoch started (group = terrain)
     const int epoch_bound = bounds[chains_per_terrain > 0 ? terrain : 0];
-    WarpCtx w{tab, sites_all[warp], lane, chain_base(seed, chain_offset + (uint32_t)chain)};
+    const uint32_t base = chain_base(seed, chain_offset + (uint32_t)chain);
+    const uint32_t nq7 = noise_q7(noise_pct);
+    WarpCtx w{tab, sites_all[warp], lane};
     Lane L;
     L.C = terrain_rows[(size_t)terrain * 32 + lane];
     L.S = st.S[lane];
@@ -179,27 +191,29 @@ __global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restr
     }
 
     // diamond of the 25 window positions within Manhattan distance 3 (a superset of every reach set)
-    int ldx, ldy, lbit;
+    int ldx, ldy;
     {
         int i = lane, r = (i >= 1) + (i >= 4) + (i >= 9) + (i >= 16) + (i >= 21) + (i >= 24);
         int start = r <= 4 ? r * r : (r == 5 ? 21 : 24);
         ldy = r - 3;
         ldx = (i - start) - (3 - abs(ldy));
-        lbit = 7 * (ldy + 3) + ldx + 3;
     }
+    const bool diamond = lane < 25, lhi = ldy >= 1;   // window rows 4..6 live in the second table word
+    const int lrowsh = 7 * ((ldy + 3) & 3);
 
     long long it = 0;
     for (; it < steps; it++, step++) {
         if ((it & 1023) == 1023 && *interrupt) break;
         const int limit = min(epoch_bound, best);
+        const uint32_t hs = step_hash(base, step);
+        const uint32_t hl = lane_hash(hs, (uint32_t)lane);
         if (k >= limit) {  // 1. too many supports for an improvement: drop one
             if (k == 0) { done = 1; break; }
             scored += (unsigned)k;
-            tabu_add = remove_min_loss(L, w, k, step, -1);
+            tabu_add = remove_min_loss(L, w, k, hl, -1);
             continue;
         }
-        const uint32_t rowmask = __ballot_sync(FULL, L.U != 0);
-        if (rowmask == 0) {  // 2. complete layout with k < limit supports
+        if (!__any_sync(FULL, L.U != 0)) {  // 2. complete layout with k < limit supports
             best = k;
             bestS = L.S;
             if (k <= target || k == 0) { done = 1; it++; step++; break; }
@@ -207,29 +221,27 @@ __global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restr
         }
         if (k == limit - 1 && k > 0) {  // 3. at capacity: swap = remove + add
             scored += (unsigned)k;
-            tabu_add = remove_min_loss(L, w, k, step, tabu_rem);
+            tabu_add = remove_min_loss(L, w, k, hl, tabu_rem);
         }
-        const uint32_t rowmask2 = __ballot_sync(FULL, L.U != 0);
-        const int y = pick_rotated(rowmask2, rnd(w.base, step, SALT_ROW));
+        const uint32_t rowmask = __ballot_sync(FULL, L.U != 0);
+        const int y = pick_rotated(rowmask, hs & 31u);
         const uint32_t Urow = __shfl_sync(FULL, L.U, y);
-        const int x = pick_rotated(Urow, rnd(w.base, step, SALT_COL));
+        const int x = pick_rotated(Urow, (hs >> 5) & 31u);
         const uint2 wt = tab[y * 32 + x];
-        const bool valid = lane < 25 && ((lbit < 28 ? (wt.x >> lbit) : (wt.y >> (lbit - 28))) & 1u);
-        const int cx = x + ldx, cy = y + ldy, cv = valid ? cy * 32 + cx : 0;
-        const uint32_t vmask = __ballot_sync(FULL, valid);
-        const int nc = __popc(vmask);
-        int chosen;
-        if ((int)(rnd(w.base, step, SALT_NOISE) % 100u) < noise_pct) {
-            chosen = __fns(vmask, 0, (int)(rnd(w.base, step, SALT_PICK) % (uint32_t)nc) + 1);
+        const int col = ldx + min(x, 3);  // window column of the candidate (window anchored at max(x-3, 0))
+        const bool valid = diamond && col >= 0 && (((lhi ? wt.y : wt.x) >> (lrowsh + col)) & 1u);
+        const int cv = valid ? (y + ldy) * 32 + x + ldx : 0;
+        const int nc = __popc(__ballot_sync(FULL, valid));
+        uint32_t key;
+        if (((hs >> 10) & 127u) < nq7) {  // noise: uniformly random site of R(t)
+            key = valid ? (0x10000u | tie_add(hl)) : 0u;
         } else {
-            const uint2 wc = tab[cv];
-            int g = score(L.U, cv & 31, cv >> 5, wc);
-            uint32_t key = (valid && !(cv == tabu_add && nc > 1)) ? (((uint32_t)(g + 1) << 16) | (rnd(w.base, step, SALT_ADD + lbit) & 0xffffu)) : 0u;
-            uint32_t mx = __reduce_max_sync(FULL, key);
-            chosen = __ffs(__ballot_sync(FULL, key == mx)) - 1;
+            int g = score(L.U, cv & 31, cv >> 5, tab[cv]);
+            key = (valid && !(cv == tabu_add && nc > 1)) ? (((uint32_t)(g + 1) << 16) | tie_add(hl)) : 0u;
             scored += (unsigned)nc;
         }
-        const int v = __shfl_sync(FULL, cv, chosen);
+        const uint32_t mx = __reduce_max_sync(FULL, key);
+        const int v = __shfl_sync(FULL, cv, __ffs(__ballot_sync(FULL, key == mx)) - 1);
         planes_add(L, row_mask(tab[v], v & 31, v >> 5, lane));
         derive(L);
         if (lane == (v >> 5)) L.S |= 1u << (v & 31);

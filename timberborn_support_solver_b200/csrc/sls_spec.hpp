@@ -16,9 +16,16 @@
 //   2. U empty               -> record (k, S) as the chain's best; done if k <= target
 //   3. otherwise, if k == L-1 -> remove the min-loss support other than the one just added (tabu)
 //      then pick a random uncovered tile t and add the site v in R(t) with the largest gain |U & R(v)| (random
-//      ties; with probability noise% a random site of R(t) instead), never the site just removed unless it is the
-//      only candidate.
-// Random numbers are counter based: rnd(salt) = fmix32(base ^ step*K1 ^ salt*K2), base keyed by (seed, global chain).
+//      ties; with probability ~noise% a uniformly random site of R(t) instead), never the site just removed unless
+//      it is the only candidate.
+//
+// Random numbers are counter based, two hashes per step:
+//   hs = fmix32(base ^ step*K1)          one word per (chain, step): bits 0-4 row rotation, 5-9 column rotation,
+//                                        10-16 noise draw (7 bits, compared with noise_q7 = round(noise% * 1.28))
+//   hl = fmix32(hs ^ (lane+1)*K2)        one word per lane: bits 0-15 break ties among ADD candidates (lane = index in
+//                                        the 25-tile diamond), bits 16-31 among REMOVE candidates (site list index i,
+//                                        lane = i % 32, for i >= 32 the word is multiplied by the odd number 2*(i/32)+1)
+// base is keyed by (seed, global chain index), so a run is reproducible for a fixed chain numbering.
 #pragma once
 #include <cstdint>
 
@@ -26,7 +33,6 @@ namespace tss {
 namespace sls {
 
 constexpr uint32_t K1 = 0x9E3779B9u, K2 = 0x85EBCA6Bu;
-constexpr int SALT_ROW = 1, SALT_COL = 2, SALT_NOISE = 3, SALT_PICK = 4, SALT_REMOVE = 1000, SALT_ADD = 200;
 constexpr int DEFAULT_NOISE_PCT = 20;
 constexpr int MAX_SITES = 1024;   // supports per chain (<= tiles of a 32x32 grid)
 constexpr int NO_BOUND = 1 << 20;
@@ -44,7 +50,11 @@ TSS_HD uint32_t fmix32(uint32_t h) {
 TSS_HD uint32_t chain_base(uint64_t seed, uint32_t chain) {
     return fmix32((uint32_t)seed ^ fmix32((uint32_t)(seed >> 32) + chain * K1 + 0x5bd1e995u));
 }
-TSS_HD uint32_t rnd(uint32_t base, uint32_t step, uint32_t salt) { return fmix32(base ^ (step * K1) ^ (salt * K2)); }
+TSS_HD uint32_t step_hash(uint32_t base, uint32_t step) { return fmix32(base ^ (step * K1)); }
+TSS_HD uint32_t lane_hash(uint32_t hs, uint32_t lane) { return fmix32(hs ^ ((lane + 1u) * K2)); }
+TSS_HD uint32_t noise_q7(int noise_pct) { return (uint32_t)((noise_pct * 128 + 50) / 100); }
+TSS_HD uint32_t tie_add(uint32_t hl) { return hl & 0xffffu; }
+TSS_HD uint32_t tie_remove(uint32_t hl, uint32_t chunk) { return (hl * (2u * chunk + 1u)) >> 16; }
 
 // Persistent per-chain state in HBM (one 320-byte record per chain).
 struct ChainState {
