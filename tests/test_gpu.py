@@ -287,6 +287,49 @@ def test_sls_bound_sharing_and_determinism(eng):
     assert (runs[0][1]["best"][runs[0][1]["best"] < (1 << 20)] <= 16).all()       # nobody reports a layout >= the bound
 
 
+@pytest.mark.parametrize("w,h", [(48, 40), (64, 64), (256, 256)])
+def test_sls_large_grids_window_decomposition(eng, w, h):
+    """C4 shape: grids larger than 32x32 are searched by window decomposition around the per-warp kernel.  The global
+    layout is complete after EVERY phase (oracle validate), counts never increase, the run is deterministic, and on
+    a grid that is a disjoint union of small terrains the count reaches the sum of the proven optima."""
+    grid = synth_terrain(w, h, seed=1)
+    g = T.WorldGrid(grid)
+    counts = []
+    s = eng.search(g, seed=3)
+    for phase in range(6):
+        s.run(1500, 0)
+        counts.append(s.best_count())
+        lay = s.best_layout()                               # re-validated by kernel (a) inside the engine
+        if phase in (0, 5):
+            sites = np.zeros((1, h, w), np.uint8)
+            for p in lay.platforms().values():
+                sites[0, p.y, p.x] = 1
+            unc, cnt, _ = O.validate_sites_batch(grid, sites)
+            assert unc[0] == 0 and cnt[0] == counts[-1]
+    s.close()
+    assert all(b <= a for a, b in zip(counts, counts[1:])) and counts[-1] < counts[0]
+    assert counts[-1] >= -(-int(grid.sum()) // 25)
+    assert counts[-1] < 0.2 * grid.sum()                    # far below "a support under every tile"
+    s2 = eng.search(g, seed=3)
+    for _ in range(6):
+        s2.run(1500, 0)
+    assert s2.best_count() == counts[-1]
+    s2.close()
+
+
+def test_sls_large_grid_reaches_sum_of_component_optima(eng, fixtures):
+    """Four copies of ex3 (optimum 4 each, proven) separated by empty space on a 64x40 grid: optimum 16."""
+    g = np.zeros((40, 64), np.uint8)
+    e3 = fixtures["ex3"]
+    for (ox, oy) in [(2, 1), (40, 3), (5, 25), (44, 28)]:
+        g[oy:oy + e3.shape[0], ox:ox + e3.shape[1]] = e3
+    res, lay = eng.solve_upper_bound(T.WorldGrid(g), card_limit=16, seed=1, max_steps=60000)
+    assert res == T.SAT and lay.platform_count() == 16
+    assert O.validate(g, [tup(p) for p in lay.platforms().values()]).is_valid
+    res, lay = eng.solve_upper_bound(T.WorldGrid(g), card_limit=15, seed=1, max_steps=8000)
+    assert res == T.INTERRUPTED
+
+
 def test_solve_batch_terrains(eng):
     """C5 shape (scaled down): per-terrain counts are complete layouts, never below the trivial lower bound, and
     agree with the oracle's proven optimum where that is cheap to prove."""

@@ -17,6 +17,15 @@ int sls_run(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls:
 int sls_best_reduce(tss_engine* e, const sls::ChainState* states, int chains_per_group, int n_chains, int n_groups, int2* out_dev,
                     int* bounds_dev);
 int run_peaks(tss_engine* e, double* out, int n_out);
+// lns.cu — window decomposition for grids larger than 32x32
+struct LnsSearch;
+int lns_create(tss_engine* e, const uint8_t* grid, int w, int h, int seeds, uint64_t seed, uint32_t chain_offset, int noise, LnsSearch** out);
+void lns_destroy(LnsSearch* s);
+int lns_phase(tss_engine* e, LnsSearch* s, long long steps);
+int lns_layout(tss_engine* e, LnsSearch* s, std::vector<uint32_t>& rows);
+int lns_count(const LnsSearch* s);
+unsigned long long lns_total(const LnsSearch* s, int i);
+int lns_chains(const LnsSearch* s);
 
 // u8 grids [n][w*h] -> rows32 [n][32] (one u32 per row, rows >= h are zero); w, h <= 32
 __global__ void pack_rows32_kernel(const uint8_t* __restrict__ bytes, int w, int h, long long n, uint32_t* __restrict__ out) {
@@ -74,6 +83,8 @@ struct tss_search {
     unsigned long long* totals_host = nullptr; // pinned [2]
     unsigned long long totals_seen[2] = {0, 0};
     bool dirty = false;
+    tss::LnsSearch* lns = nullptr;             // grids larger than 32x32: window decomposition (lns.cu)
+    int external_bound = tss::sls::NO_BOUND;
 };
 
 using namespace tss;
@@ -333,6 +344,7 @@ int tss_layout_to_assignment_impl(tss_engine* e, const Encoding& enc, const uint
 // ------------------------------------------------------------------------------------------------ kernel (b)
 static void search_free(tss_search* s) {
     if (!s) return;
+    if (s->lns) lns_destroy(s->lns);
     cudaFree(s->rows_dev); cudaFree(s->tabs_dev); cudaFree(s->states); cudaFree(s->totals_dev); cudaFree(s->best_dev); cudaFree(s->bounds_dev);
     if (s->best_host) cudaFreeHost(s->best_host);
     if (s->totals_host) cudaFreeHost(s->totals_host);
@@ -377,7 +389,7 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
         has_1x1 = has_1x1 || (defs[i].w == 1 && defs[i].h == 1);
     }
     if (!has_1x1) return e->fail(TSS_E_INVALID, "the platform set must contain 1x1 (src/encoder.rs:564-566)");
-    if (w > 32 || h > 32) return e->fail(TSS_E_UNSUPPORTED, "tss_search: grids larger than 32x32 are not accelerated yet (got %dx%d)", w, h);
+    if ((size_t)h * ((w + 31) / 32) * 20 > 200 * 1024) return e->fail(TSS_E_UNSUPPORTED, "tss_search: grid %dx%d exceeds the validator's shared-memory planes", w, h);
     TSS_CUDA(e, cudaSetDevice(e->device));
     tss_search* s = new tss_search();
     s->e = e; s->w = w; s->h = h;
@@ -385,6 +397,14 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
     s->seed = params ? params->seed : 0;
     s->chain_offset = params ? (uint32_t)params->chain_offset : 0;
     s->noise = (params && params->noise_pct >= 0) ? params->noise_pct : sls::DEFAULT_NOISE_PCT;
+    if (w > 32 || h > 32) {  // window decomposition: n_chains is read as chains per window (multiple of 4, default 8)
+        int seeds = (params && params->n_chains > 0) ? ((params->n_chains + 3) / 4) * 4 : 8;
+        int rc = lns_create(e, grid, w, h, seeds, s->seed, s->chain_offset, s->noise, &s->lns);
+        if (rc != TSS_OK) { delete s; return rc; }
+        s->n_chains = lns_chains(s->lns);
+        *out = s;
+        return TSS_OK;
+    }
     s->n_chains = (params && params->n_chains > 0) ? params->n_chains : e->prop.multiProcessorCount * 32;
     s->n_groups = 1;
     s->chains_per_terrain = 0;
@@ -420,6 +440,14 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
     if (steps <= 0) return e->fail(TSS_E_INVALID, "tss_search_run: steps must be positive");
     TSS_CUDA(e, cudaSetDevice(e->device));
     TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    if (s->lns) {  // one phase of the window decomposition
+        int rc = lns_phase(e, s->lns, steps);
+        if (rc) return rc;
+        TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+        s->dirty = true;
+        e->stats.n_solves++;
+        return TSS_OK;
+    }
     int chains_per_group = s->n_groups == 1 ? s->n_chains : s->chains_per_terrain;
     int rc = sls_run(e, s->rows_dev, s->tabs_dev, s->states, s->n_chains, s->chains_per_terrain, s->chain_offset, s->seed, steps,
                      s->bounds_dev, target_count < 0 ? -1 : target_count, s->noise, s->totals_dev);
@@ -440,10 +468,11 @@ static int search_sync(tss_search* s) {
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev0, e->ev1);
     e->stats.device_ms = ms;
-    e->stats.candidates_scored += s->totals_host[0] - s->totals_seen[0];
-    e->stats.sls_steps += s->totals_host[1] - s->totals_seen[1];
-    s->totals_seen[0] = s->totals_host[0];
-    s->totals_seen[1] = s->totals_host[1];
+    const unsigned long long t0 = s->lns ? lns_total(s->lns, 0) : s->totals_host[0], t1 = s->lns ? lns_total(s->lns, 1) : s->totals_host[1];
+    e->stats.candidates_scored += t0 - s->totals_seen[0];
+    e->stats.sls_steps += t1 - s->totals_seen[1];
+    s->totals_seen[0] = t0;
+    s->totals_seen[1] = t1;
     s->dirty = false;
     return TSS_OK;
 }
@@ -452,6 +481,12 @@ int tss_search_best_count(tss_search* s, int32_t* count) {
     if (!s || !count) return TSS_E_INVALID;
     int rc = search_sync(s);
     if (rc) return rc;
+    if (s->lns) {  // the global layout is always complete; a bound given from outside hides counts that do not beat it
+        int c = lns_count(s->lns);
+        *count = c < s->external_bound ? c : -1;
+        s->e->stats.best_count = *count;
+        return TSS_OK;
+    }
     int best = sls::NO_BOUND;
     for (int g = 0; g < s->n_groups; g++) best = s->best_host[g].x < best ? s->best_host[g].x : best;
     *count = best >= sls::NO_BOUND ? -1 : best;
@@ -465,6 +500,7 @@ int tss_search_set_bound(tss_search* s, int32_t count) {
     if (count < 0) return e->fail(TSS_E_INVALID, "tss_search_set_bound: negative bound");
     int rc = search_sync(s);
     if (rc) return rc;
+    if (s->lns) { s->external_bound = count < s->external_bound ? count : s->external_bound; return TSS_OK; }
     std::vector<int> nb((size_t)s->n_groups);
     TSS_CUDA(e, cudaMemcpy(nb.data(), s->bounds_dev, sizeof(int) * nb.size(), cudaMemcpyDeviceToHost));
     for (int& b : nb) b = b < count ? b : count;
@@ -475,6 +511,7 @@ int tss_search_set_bound(tss_search* s, int32_t count) {
 int tss_search_read_chains(tss_search* s, uint32_t* S, uint32_t* best_S, int32_t* k, int32_t* best, uint32_t* step, uint64_t* scored) {
     if (!s) return TSS_E_INVALID;
     tss_engine* e = s->e;
+    if (s->lns) return e->fail(TSS_E_UNSUPPORTED, "tss_search_read_chains: window-decomposed searches keep no per-chain state between phases");
     int rc = search_sync(s);
     if (rc) return rc;
     std::vector<sls::ChainState> st((size_t)s->n_chains);
@@ -495,14 +532,26 @@ int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_
     tss_engine* e = s->e;
     int rc = search_sync(s);
     if (rc) return rc;
-    int2 best = s->best_host[0];
-    if (best.x >= sls::NO_BOUND || best.y < 0) { *n_out = 0; return e->fail(TSS_E_INVALID, "tss_search_best_layout: no complete layout found yet"); }
-    sls::ChainState st;
-    TSS_CUDA(e, cudaMemcpy(&st, s->states + best.y, sizeof st, cudaMemcpyDeviceToHost));
     std::vector<tss_platform> plats;
-    for (int y = 0; y < s->h; y++)
-        for (int x = 0; x < s->w; x++)
-            if ((st.bestS[y] >> x) & 1u) plats.push_back(tss_platform{x, y, 1, 1, 0});
+    int2 best;
+    if (s->lns) {
+        std::vector<uint32_t> rows;
+        rc = lns_layout(e, s->lns, rows);
+        if (rc) return rc;
+        const int wpr = (s->w + 31) / 32;
+        for (int y = 0; y < s->h; y++)
+            for (int x = 0; x < s->w; x++)
+                if ((rows[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u) plats.push_back(tss_platform{x, y, 1, 1, 0});
+        best = make_int2((int)plats.size(), 0);
+    } else {
+        best = s->best_host[0];
+        if (best.x >= sls::NO_BOUND || best.y < 0) { *n_out = 0; return e->fail(TSS_E_INVALID, "tss_search_best_layout: no complete layout found yet"); }
+        sls::ChainState st;
+        TSS_CUDA(e, cudaMemcpy(&st, s->states + best.y, sizeof st, cudaMemcpyDeviceToHost));
+        for (int y = 0; y < s->h; y++)
+            for (int x = 0; x < s->w; x++)
+                if ((st.bestS[y] >> x) & 1u) plats.push_back(tss_platform{x, y, 1, 1, 0});
+    }
     *n_out = (int)plats.size();
     // every witness is re-validated by kernel (a) before it leaves the engine
     int unsupported = tss_validate(e, s->grid.data(), s->w, s->h, plats.data(), (int)plats.size(), nullptr, nullptr);
@@ -529,8 +578,9 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     const double t0 = now_ms();
     // no budget given: behave like one SAT call (return the first model within the bound), but give up after a
     // default effort — the engine cannot prove UNSAT, so "no model found" must not turn into an endless search
-    const bool first_model_only = budget_ms <= 0 && max_steps <= 0;
-    if (first_model_only) max_steps = 1 << 18;
+    const bool windowed = w > 32 || h > 32;  // the window-decomposed search always holds a complete layout: keep improving it
+    const bool first_model_only = budget_ms <= 0 && max_steps <= 0 && !(windowed && card_limit < 0);
+    if (budget_ms <= 0 && max_steps <= 0) max_steps = windowed ? (1 << 16) : (1 << 18);
     int64_t done_steps = 0, epoch = 64;
     int best = -1;
     while (rc == TSS_OK) {

@@ -25,7 +25,7 @@ struct Lane {
 __device__ __forceinline__ void derive(Lane& L) {
     uint32_t hi = L.c1 | L.c2 | L.c3 | L.c4;
     L.U = L.C & ~(L.c0 | hi);
-    L.O = L.c0 & ~hi;
+    L.O = L.c0 & ~hi & L.C;  // (in WINDOW mode tiles covered by frozen supports are not a loss)
 }
 
 // Reach windows are 7 rows x 7 columns; window row dy is grid row y-3+dy, window column 0 is grid column
@@ -148,7 +148,13 @@ __device__ __forceinline__ int remove_min_loss(Lane& L, const WarpCtx& w, int& k
     return u;
 }
 
+// WINDOW mode (large-neighbourhood search on grids larger than 32x32, lns.cu): the chain works on a 32x32 window of a
+// bigger grid.  `terrain_rows` is the true ceiling of the window (reach tables are built from it), `need_rows` the
+// tiles of the window NOT already covered by frozen supports outside the window's movable core, and only sites with
+// core_lo <= x, y < core_hi may receive supports (their reach never leaves the window).
+template <bool WINDOW>
 __global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restrict__ terrain_rows, const uint2* __restrict__ rtabs,
+                                                        const uint32_t* __restrict__ need_rows, int core_lo, int core_hi,
                                                         ChainState* __restrict__ states, int n_chains, int chains_per_terrain,
                                                         uint32_t chain_offset, uint64_t seed, long long steps,
                                                         const int* __restrict__ bounds, int target, int noise_pct,
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restr
     const uint32_t nq7 = noise_q7(noise_pct);
     WarpCtx w{tab, sites_all[warp], lane};
     Lane L;
-    L.C = terrain_rows[(size_t)terrain * 32 + lane];
+    L.C = WINDOW ? need_rows[(size_t)terrain * 32 + lane] : terrain_rows[(size_t)terrain * 32 + lane];  // tiles that need cover
     L.S = st.S[lane];
     uint32_t bestS = st.bestS[lane];
     int k = st.k, best = st.best, tabu_add = st.tabu_add, tabu_rem = st.tabu_rem, done = 0;
@@ -229,9 +235,11 @@ __global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restr
         const int x = pick_rotated(Urow, (hs >> 5) & 31u);
         const uint2 wt = tab[y * 32 + x];
         const int col = ldx + min(x, 3);  // window column of the candidate (window anchored at max(x-3, 0))
-        const bool valid = diamond && col >= 0 && (((lhi ? wt.y : wt.x) >> (lrowsh + col)) & 1u);
+        bool valid = diamond && col >= 0 && (((lhi ? wt.y : wt.x) >> (lrowsh + col)) & 1u);
+        if (WINDOW) valid = valid && x + ldx >= core_lo && x + ldx < core_hi && y + ldy >= core_lo && y + ldy < core_hi;
         const int cv = valid ? (y + ldy) * 32 + x + ldx : 0;
         const int nc = __popc(__ballot_sync(FULL, valid));
+        if (WINDOW && nc == 0) { done = 1; break; }  // cannot happen from a complete start layout; never spin on it
         uint32_t key;
         if (((hs >> 10) & 127u) < nq7) {  // noise: uniformly random site of R(t)
             key = valid ? (0x10000u | tie_add(hl)) : 0u;
@@ -318,8 +326,20 @@ int sls_run(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls:
             int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
             int noise_pct, unsigned long long* totals_dev) {
     int blocks = (n_chains + sls::WARPS - 1) / sls::WARPS;
-    sls::sls_kernel<<<blocks, sls::WARPS * 32, 0, e->stream>>>(rows_dev, tabs_dev, states, n_chains, chains_per_terrain, chain_offset, seed,
-                                                             steps, bounds_dev, target, noise_pct, e->interrupt_dev, totals_dev);
+    sls::sls_kernel<false><<<blocks, sls::WARPS * 32, 0, e->stream>>>(rows_dev, tabs_dev, nullptr, 0, 32, states, n_chains, chains_per_terrain,
+                                                                    chain_offset, seed, steps, bounds_dev, target, noise_pct, e->interrupt_dev,
+                                                                    totals_dev);
+    TSS_CHECK_LAUNCH(e);
+    e->stats.kernel_launches++;
+    return TSS_OK;
+}
+int sls_run_windows(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, const uint32_t* need_dev, int core_lo, int core_hi,
+                    sls::ChainState* states, int n_chains, int chains_per_window, uint32_t chain_offset, uint64_t seed, long long steps,
+                    const int* bounds_dev, unsigned long long* totals_dev, int noise_pct) {
+    int blocks = (n_chains + sls::WARPS - 1) / sls::WARPS;
+    sls::sls_kernel<true><<<blocks, sls::WARPS * 32, 0, e->stream>>>(rows_dev, tabs_dev, need_dev, core_lo, core_hi, states, n_chains,
+                                                                   chains_per_window, chain_offset, seed, steps, bounds_dev, 0, noise_pct,
+                                                                   e->interrupt_dev, totals_dev);
     TSS_CHECK_LAUNCH(e);
     e->stats.kernel_launches++;
     return TSS_OK;
