@@ -287,6 +287,61 @@ def test_sls_bound_sharing_and_determinism(eng):
     assert (runs[0][1]["best"][runs[0][1]["best"] < (1 << 20)] <= 16).all()       # nobody reports a layout >= the bound
 
 
+@pytest.mark.parametrize("name,optimum", [("ex1", 1), ("ex3", 1), ("ex2", 4)])
+def test_multi_platform_search_reaches_repl_optimum(eng, fixtures, name, optimum):
+    """BASELINE.json configs[0]/[2]: the REPL solves with PLATFORMS_DEFAULT (crates/repl/src/main.rs:254); the proven optima
+    (oracle CDCL loop, tests/test_oracle.py) are 1 / 1 / 4 platforms.  Witnesses pass the oracle's validate (coverage,
+    overlap, bounds) and the reference encoder's full default-8 CNF."""
+    g = T.WorldGrid(fixtures[name])
+    res, layout = eng.solve_upper_bound(g, T.PLATFORMS_DEFAULT, card_limit=optimum, seed=5, max_steps=60000)
+    assert res == T.SAT and layout.platform_count() == optimum
+    plats = [tup(p) for p in layout.platforms().values()]
+    assert O.validate(g.data, plats).is_valid
+    enc = T.Encoding.encode(T.PLATFORMS_DEFAULT, g)
+    a = eng.layout_to_assignment(enc, layout)
+    ref = O.Encoding(O.PLATFORMS_DEFAULT, g.data)
+    assert ref.cnf().count_falsified(a) == (0, -1)
+    assert sorted(ref.layout_from_assignment(a)) == sorted(plats)              # decode(encode(layout)) round trip
+    assert eng.upload_cnf(enc.cnf()).check(a[None])[0][0] == 0
+    res, layout = eng.solve_upper_bound(g, T.PLATFORMS_DEFAULT, card_limit=optimum - 1, seed=5, max_steps=2000)
+    assert res == T.INTERRUPTED
+
+
+def test_multi_platform_random_sets_match_exact_optimum(eng):
+    """Small random terrains x platform sets: the GPU count equals the optimum proven by the oracle loop; layouts are
+    valid (no overlap, in bounds, full coverage) under the oracle."""
+    rng = np.random.default_rng(8)
+    sets = [[(1, 1), (2, 2)], [(1, 1), (1, 3)], [(1, 1), (2, 3), (3, 3)], [(1, 1), (1, 2), (3, 3), (5, 5)]]
+    for i in range(8):
+        w, h = int(rng.integers(4, 10)), int(rng.integers(4, 10))
+        grid = (rng.random((h, w)) < 0.8).astype(np.uint8)
+        defs = sets[i % len(sets)]
+        exact = O.solver_loop(grid, defs)
+        assert exact["proved_optimal"]
+        res, layout = eng.solve_upper_bound(T.WorldGrid(grid), [T.PlatformDef(*d) for d in defs], card_limit=len(exact["best"]), seed=i, max_steps=40000)
+        assert res == T.SAT and layout.platform_count() == len(exact["best"]), (i, w, h, defs)
+        assert O.validate(grid, [tup(p) for p in layout.platforms().values()]).is_valid
+
+
+def test_multi_platform_solver_loop_like_the_repl(eng, fixtures):
+    """`load test/ex1.toml; solve` (configs[0]): default-8 set, unbounded first solve, tighten until the prover says UNSAT."""
+    import ctypes as C
+    from oracle.oracle import _p
+
+    def exact(cnf):
+        a = np.full(cnf.n_vars + 1, 2, np.uint8)
+        lits, offs = np.ascontiguousarray(cnf.lits, np.int32), np.ascontiguousarray(cnf.offsets, np.uint32)
+        r = O.lib().tsso_solve_csr(_p(lits), _p(offs, C.c_uint32), cnf.n_clauses, cnf.n_vars, _p(a, C.c_uint8), C.c_long(-1))
+        return {10: T.SAT, 20: T.UNSAT}.get(r, T.INTERRUPTED), a
+
+    g = T.WorldGrid(fixtures["ex1"])
+    enc = T.Encoding.encode(T.PLATFORMS_DEFAULT, g)
+    out = T.solver_loop(T.Project(T.World(g)), enc, T.PlatformLimits(), eng, exact_solver=exact, seed=2, budget_ms=0)
+    assert out["proved_optimal"] and out["best"].platform_count() == 1
+    assert out["steps"][-1] == dict(bound=0, result=T.UNSAT, source="exact")
+    assert all(s["source"] == "gpu" and s["valid"] for s in out["steps"][:-1])
+
+
 @pytest.mark.parametrize("w,h", [(48, 40), (64, 64), (256, 256)])
 def test_sls_large_grids_window_decomposition(eng, w, h):
     """C4 shape: grids larger than 32x32 are searched by window decomposition around the per-warp kernel.  The global

@@ -26,6 +26,14 @@ int lns_layout(tss_engine* e, LnsSearch* s, std::vector<uint32_t>& rows);
 int lns_count(const LnsSearch* s);
 unsigned long long lns_total(const LnsSearch* s, int i);
 int lns_chains(const LnsSearch* s);
+// sls_multi.cu — placements of several platform types
+size_t slsm_state_bytes();
+int slsm_max_keys();
+int slsm_init(tss_engine* e, void* states, int n);
+int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* keys_dev, int n_keys, void* states, int n_chains,
+             uint32_t chain_offset, uint64_t seed, long long steps, int* bounds_dev, int target, int noise_pct, unsigned long long* totals_dev,
+             int2* best_dev);
+int slsm_read_best(tss_engine* e, const void* states, int chain, std::vector<uint16_t>& codes, int count);
 
 // u8 grids [n][w*h] -> rows32 [n][32] (one u32 per row, rows >= h are zero); w, h <= 32
 __global__ void pack_rows32_kernel(const uint8_t* __restrict__ bytes, int w, int h, long long n, uint32_t* __restrict__ out) {
@@ -85,6 +93,12 @@ struct tss_search {
     bool dirty = false;
     tss::LnsSearch* lns = nullptr;             // grids larger than 32x32: window decomposition (lns.cu)
     int external_bound = tss::sls::NO_BOUND;
+    // platform sets beyond {1x1} on grids up to 32x32: placement search (sls_multi.cu)
+    bool multi = false;
+    std::vector<int2> key_dims;                // effective (w, h) per dims key: defs order, unflipped then flipped
+    std::vector<tss_platform> key_proto;       // def dims + rotated flag per key
+    int2* keys_dev = nullptr;
+    void* mstates = nullptr;
 };
 
 using namespace tss;
@@ -345,6 +359,8 @@ int tss_layout_to_assignment_impl(tss_engine* e, const Encoding& enc, const uint
 static void search_free(tss_search* s) {
     if (!s) return;
     if (s->lns) lns_destroy(s->lns);
+    cudaFree(s->keys_dev);
+    cudaFree(s->mstates);
     cudaFree(s->rows_dev); cudaFree(s->tabs_dev); cudaFree(s->states); cudaFree(s->totals_dev); cudaFree(s->best_dev); cudaFree(s->bounds_dev);
     if (s->best_host) cudaFreeHost(s->best_host);
     if (s->totals_host) cudaFreeHost(s->totals_host);
@@ -412,6 +428,42 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++)
             if (grid[(size_t)y * w + x]) rows[y] |= 1u << x;
+    // dims keys (both orientations of every def, src/encoder.rs:121-130); more than the single 1x1 key -> placement search
+    for (int i = 0; i < n_defs; i++)
+        for (int rot = 0; rot < 2; rot++) {
+            int2 d = rot ? make_int2(defs[i].h, defs[i].w) : make_int2(defs[i].w, defs[i].h);
+            bool seen = false;
+            for (auto& kd : s->key_dims) seen = seen || (kd.x == d.x && kd.y == d.y);
+            if (seen) continue;
+            s->key_dims.push_back(d);
+            s->key_proto.push_back(tss_platform{0, 0, defs[i].w, defs[i].h, rot});
+        }
+    bool fits = (int)s->key_dims.size() <= slsm_max_keys();
+    for (auto& kd : s->key_dims) fits = fits && kd.x <= 6 && kd.y <= 6;
+    if (s->key_dims.size() > 1 && fits) {
+        s->multi = true;
+        if (!(params && params->n_chains > 0)) s->n_chains = e->prop.multiProcessorCount * 16;
+        cudaError_t err = cudaMalloc(&s->rows_dev, sizeof rows);
+        if (err == cudaSuccess) err = cudaMalloc(&s->keys_dev, sizeof(int2) * s->key_dims.size());
+        if (err == cudaSuccess) err = cudaMalloc(&s->mstates, slsm_state_bytes() * (size_t)s->n_chains);
+        if (err == cudaSuccess) err = cudaMalloc(&s->totals_dev, sizeof(unsigned long long) * 2);
+        if (err == cudaSuccess) err = cudaMalloc(&s->best_dev, sizeof(int2));
+        if (err == cudaSuccess) err = cudaMalloc(&s->bounds_dev, sizeof(int));
+        if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->best_host, sizeof(int2), cudaHostAllocDefault);
+        if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->totals_host, sizeof(unsigned long long) * 2, cudaHostAllocDefault);
+        const int nb = sls::NO_BOUND;
+        if (err == cudaSuccess) err = cudaMemcpyAsync(s->rows_dev, rows, sizeof rows, cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(s->keys_dev, s->key_dims.data(), sizeof(int2) * s->key_dims.size(), cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(s->bounds_dev, &nb, sizeof nb, cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess) err = cudaMemsetAsync(s->totals_dev, 0, sizeof(unsigned long long) * 2, e->stream);
+        int rc = err == cudaSuccess ? slsm_init(e, s->mstates, s->n_chains) : e->fail(TSS_E_CUDA, "tss_search_create: %s", cudaGetErrorString(err));
+        if (rc == TSS_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = e->fail(TSS_E_CUDA, "tss_search_create: stream sync failed");
+        if (rc != TSS_OK) { search_free(s); return rc; }
+        s->best_host[0] = make_int2(sls::NO_BOUND, -1);
+        s->totals_host[0] = s->totals_host[1] = 0;
+        *out = s;
+        return TSS_OK;
+    }
     int rc = search_alloc(e, s, rows, 1);
     if (rc == TSS_OK) rc = search_init_device(e, s, 1);
     if (rc != TSS_OK) { search_free(s); return rc; }
@@ -444,6 +496,17 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
         int rc = lns_phase(e, s->lns, steps);
         if (rc) return rc;
         TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+        s->dirty = true;
+        e->stats.n_solves++;
+        return TSS_OK;
+    }
+    if (s->multi) {
+        int rc = slsm_run(e, s->rows_dev, s->w, s->h, s->keys_dev, (int)s->key_dims.size(), s->mstates, s->n_chains, s->chain_offset, s->seed, steps,
+                          s->bounds_dev, target_count < 0 ? -1 : target_count, s->noise, s->totals_dev, s->best_dev);
+        if (rc) return rc;
+        TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+        TSS_CUDA(e, cudaMemcpyAsync(s->best_host, s->best_dev, sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
+        TSS_CUDA(e, cudaMemcpyAsync(s->totals_host, s->totals_dev, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, e->stream));
         s->dirty = true;
         e->stats.n_solves++;
         return TSS_OK;
@@ -511,7 +574,7 @@ int tss_search_set_bound(tss_search* s, int32_t count) {
 int tss_search_read_chains(tss_search* s, uint32_t* S, uint32_t* best_S, int32_t* k, int32_t* best, uint32_t* step, uint64_t* scored) {
     if (!s) return TSS_E_INVALID;
     tss_engine* e = s->e;
-    if (s->lns) return e->fail(TSS_E_UNSUPPORTED, "tss_search_read_chains: window-decomposed searches keep no per-chain state between phases");
+    if (s->lns || s->multi) return e->fail(TSS_E_UNSUPPORTED, "tss_search_read_chains: only the 1x1 search on grids up to 32x32 exposes per-chain state");
     int rc = search_sync(s);
     if (rc) return rc;
     std::vector<sls::ChainState> st((size_t)s->n_chains);
@@ -543,6 +606,18 @@ int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_
             for (int x = 0; x < s->w; x++)
                 if ((rows[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u) plats.push_back(tss_platform{x, y, 1, 1, 0});
         best = make_int2((int)plats.size(), 0);
+    } else if (s->multi) {
+        best = s->best_host[0];
+        if (best.x >= sls::NO_BOUND || best.y < 0) { *n_out = 0; return e->fail(TSS_E_INVALID, "tss_search_best_layout: no complete layout found yet"); }
+        std::vector<uint16_t> codes;
+        rc = slsm_read_best(e, s->mstates, best.y, codes, best.x);
+        if (rc) return rc;
+        for (uint16_t code : codes) {
+            tss_platform p = s->key_proto[code >> 10];
+            p.x = code & 31;
+            p.y = (code >> 5) & 31;
+            plats.push_back(p);
+        }
     } else {
         best = s->best_host[0];
         if (best.x >= sls::NO_BOUND || best.y < 0) { *n_out = 0; return e->fail(TSS_E_INVALID, "tss_search_best_layout: no complete layout found yet"); }
@@ -554,10 +629,13 @@ int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_
     }
     *n_out = (int)plats.size();
     // every witness is re-validated by kernel (a) before it leaves the engine
-    int unsupported = tss_validate(e, s->grid.data(), s->w, s->h, plats.data(), (int)plats.size(), nullptr, nullptr);
-    if (unsupported < 0) return unsupported;
-    if (unsupported != 0 || (int)plats.size() != best.x)
-        return e->fail(TSS_E_CUDA, "internal error: SLS witness failed validation (%d unsupported tiles, %zu platforms, expected %d)", unsupported, plats.size(), best.x);
+    uint32_t offsets[2] = {0, (uint32_t)plats.size()};
+    int32_t res[4] = {0, 0, 0, 0};  // unsupported tiles, platforms, overlapping, out of bounds (platform_layout.rs:187-191)
+    rc = tss_eval_platforms(e, s->grid.data(), s->w, s->h, plats.data(), offsets, 1, res);
+    if (rc < 0) return rc;
+    if (res[0] != 0 || res[2] != 0 || res[3] != 0 || (int)plats.size() != best.x)
+        return e->fail(TSS_E_CUDA, "internal error: SLS witness failed validation (%d unsupported tiles, %d overlapping, %d out of bounds, %zu platforms, expected %d)",
+                       res[0], res[2], res[3], plats.size(), best.x);
     if ((int)plats.size() > cap || !out) return e->fail(TSS_E_CAPACITY, "tss_search_best_layout: need room for %zu platforms", plats.size());
     std::memcpy(out, plats.data(), sizeof(tss_platform) * plats.size());
     return TSS_OK;
