@@ -80,14 +80,15 @@ def cpu_validate_rate(grid, seconds=10.0, threads=None):
     import oracle.oracle as O
     threads = threads or os.cpu_count() or 1
     rng = np.random.default_rng(0)
-    n = 2048 * threads
+    n = 16384 * threads
     sites = (rng.random((n, grid.shape[0], grid.shape[1])) < 0.06).astype(np.uint8)
     done, t_total = 0, 0.0
     while t_total < seconds:
-        _, _, sec = O.validate_sites_batch(grid, sites, threads=threads)
+        _, _, sec = O.validate_sites_batch(grid, sites, threads=threads, flat=True)
         done += n
         t_total += sec
-    return done / t_total, threads, f"{done} random 1x1 layouts (6% density) on rect 16x16 through oracle validate, {threads} threads, {t_total:.1f} s"
+    return done / t_total, threads, (f"{done} random 1x1 layouts (6% density) on rect 16x16 through the oracle's flat-array port of "
+                                     f"PlatformLayout::validate, {threads} threads, {t_total:.1f} s")
 
 
 def cdcl_time_to_optimum(grid, optimum, conflict_budget=400000):
@@ -182,6 +183,7 @@ def main():
 
     for _ in range(W):
         step()
+    search.best_count()        # synchronises and folds the warm-up's device counters into the stats BEFORE the baseline snapshot
     torch.cuda.synchronize()
     s0 = eng.stats()
     sampler = ClockSampler(local)

@@ -269,6 +269,49 @@ double tsso_validate_sites_batch(const uint8_t* grid, int w, int h, const uint8_
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// Same computation as tsso_validate_sites_batch, restated the way a plain C port of platform_layout.rs:85-149 would be
+// written (flat byte grids instead of HashSet<Point>/HashMap): the stronger, fairer CPU baseline for kernel (a).
+// A test asserts it agrees with the structure-faithful version above.
+double tsso_validate_sites_batch_flat(const uint8_t* grid, int w, int h, const uint8_t* sites, long n, int threads,
+                                      int* out_uncovered, int* out_count) {
+    auto t0 = std::chrono::steady_clock::now();
+    std::atomic<long> next{0};
+    auto work = [&]() {
+        const long chunk = 256;
+        std::vector<uint8_t> sup((size_t)w * h), nxt((size_t)w * h);
+        while (true) {
+            long b = next.fetch_add(chunk);
+            if (b >= n) break;
+            for (long i = b; i < std::min(n, b + chunk); i++) {
+                const uint8_t* s = sites + (size_t)i * w * h;
+                int count = 0;
+                for (int t = 0; t < w * h; t++) { count += s[t] != 0; sup[t] = s[t] && grid[t]; }  // only terrain can be supported
+                for (int round = 0; round < TERRAIN_SUPPORT_DISTANCE - 1; round++) {
+                    nxt = sup;
+                    for (int y = 0; y < h; y++)
+                        for (int x = 0; x < w; x++) {
+                            if (!sup[y * w + x]) continue;
+                            if (x + 1 < w && grid[y * w + x + 1]) nxt[y * w + x + 1] = 1;
+                            if (y + 1 < h && grid[(y + 1) * w + x]) nxt[(y + 1) * w + x] = 1;
+                            if (x > 0 && grid[y * w + x - 1]) nxt[y * w + x - 1] = 1;
+                            if (y > 0 && grid[(y - 1) * w + x]) nxt[(y - 1) * w + x] = 1;
+                        }
+                    sup.swap(nxt);
+                }
+                int unc = 0;
+                for (int t = 0; t < w * h; t++) unc += grid[t] && !sup[t];
+                out_uncovered[i] = unc;
+                out_count[i] = count;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 // ---- solver_loop (crates/repl/src/main.rs:280-366).  steps: records of 4 longs (bound, result, count, valid) +
 // stats (conflicts) ; returns number of steps.  best layout written to out_plats.
 int tsso_solver_loop(const uint8_t* grid, int w, int h, const int* defs_wh, int n_defs, long initial_limit_1x1,

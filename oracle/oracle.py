@@ -256,13 +256,16 @@ def total_weight(platforms, weights):
     return int(lib().tsso_total_weight(_p(p), len(p), _p(wts), len(wts)))
 
 
-def validate_sites_batch(grid, sites, threads=1):
-    """sites: uint8[n, h, w] 1x1 support masks -> (uncovered int32[n], count int32[n], seconds)"""
+def validate_sites_batch(grid, sites, threads=1, flat=False):
+    """sites: uint8[n, h, w] 1x1 support masks -> (uncovered int32[n], count int32[n], seconds).
+    flat=False: structure-faithful restatement (sets/maps like the reference); flat=True: plain-C flat-array port."""
     g = _grid(grid)
     s = np.ascontiguousarray(sites, dtype=np.uint8).reshape(-1, g.shape[0], g.shape[1])
     unc = np.zeros(len(s), np.int32)
     cnt = np.zeros(len(s), np.int32)
-    sec = lib().tsso_validate_sites_batch(_p(g, C.c_uint8), g.shape[1], g.shape[0], _p(s, C.c_uint8), C.c_long(len(s)),
+    fn = lib().tsso_validate_sites_batch_flat if flat else lib().tsso_validate_sites_batch
+    fn.restype = C.c_double
+    sec = fn(_p(g, C.c_uint8), g.shape[1], g.shape[0], _p(s, C.c_uint8), C.c_long(len(s)),
                                           threads, _p(unc), _p(cnt))
     return unc, cnt, sec
 

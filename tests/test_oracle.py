@@ -280,6 +280,16 @@ def test_validate_reports(fixtures):
     assert v.unsupported.sum() == 19 and np.array_equal(v.unsupported, g)
 
 
+def test_flat_validate_port_agrees_with_structure_faithful_one(fixtures):
+    """bench.py's CPU baseline uses the flat-array port of validate; it must give what the set-based restatement gives."""
+    rng = np.random.default_rng(4)
+    for g in list(fixtures.values()) + [np.ones((16, 16), np.uint8), (rng.random((32, 32)) < 0.7).astype(np.uint8)]:
+        sites = (rng.random((64,) + g.shape) < 0.07).astype(np.uint8)
+        a = O.validate_sites_batch(g, sites, threads=2)
+        b = O.validate_sites_batch(g, sites, threads=2, flat=True)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
 def test_validate_geodesic_not_manhattan():
     """Support spreads only THROUGH ceiling tiles (platform_layout.rs:134-138): a gap blocks it."""
     g = rows_to_grid(["XXX XXX"])

@@ -126,11 +126,13 @@ int tss_engine_create(int device, tss_engine** out) {
     bool ok = cudaGetDeviceProperties(&e->prop, device) == cudaSuccess && cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess;
     void* flag = nullptr;
-    ok = ok && cudaHostAlloc(&flag, sizeof(int), cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&flag, 2 * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
     if (ok) {
         e->interrupt_host = (volatile int*)flag;
-        *e->interrupt_host = 0;
-        ok = cudaHostGetDevicePointer((void**)&e->interrupt_dev, flag, 0) == cudaSuccess;
+        e->interrupt_host[0] = 0;
+        e->interrupt_host[1] = 1;
+        ok = cudaMalloc((void**)&e->interrupt_dev, sizeof(int)) == cudaSuccess && cudaMemset(e->interrupt_dev, 0, sizeof(int)) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&e->irq_stream, cudaStreamNonBlocking) == cudaSuccess;
     }
     if (!ok) { cudaGetLastError(); tss_engine_destroy(e); return TSS_E_CUDA; }
     e->stream = e->own_stream;
@@ -138,12 +140,17 @@ int tss_engine_create(int device, tss_engine** out) {
     return TSS_OK;
 }
 
+static void search_free(tss_search* s);
+
 void tss_engine_destroy(tss_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+    if (e->cached_search) { search_free(e->cached_search); e->cached_search = nullptr; }
     for (auto& b : e->scratch) if (b.ptr) cudaFree(b.ptr);
     for (auto& b : e->staging) if (b.ptr) cudaFreeHost(b.ptr);
+    if (e->irq_stream) { cudaStreamSynchronize(e->irq_stream); cudaStreamDestroy(e->irq_stream); }
+    if (e->interrupt_dev) cudaFree(e->interrupt_dev);
     if (e->interrupt_host) cudaFreeHost((void*)e->interrupt_host);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -162,13 +169,22 @@ const char* tss_last_error(const tss_engine* e) { return e ? e->error.c_str() : 
 
 void tss_interrupt(tss_engine* e) {
     if (!e) return;
-    e->interrupt_flag.store(1);
-    if (e->interrupt_host) *e->interrupt_host = 1;
+    e->interrupt_flag.store(1);  // host loops (epochs, propagation rounds) see this at once
+    if (e->interrupt_dev && e->irq_stream) {  // running kernels see the device flag at their next poll
+        int cur = -1;
+        cudaGetDevice(&cur);  // callable from any thread: that thread's current device may be another GPU
+        if (cur != e->device) cudaSetDevice(e->device);
+        cudaMemcpyAsync(e->interrupt_dev, (const void*)(e->interrupt_host + 1), sizeof(int), cudaMemcpyHostToDevice, e->irq_stream);
+        if (cur >= 0 && cur != e->device) cudaSetDevice(cur);
+    }
 }
 void tss_clear_interrupt(tss_engine* e) {
     if (!e) return;
     e->interrupt_flag.store(0);
-    if (e->interrupt_host) *e->interrupt_host = 0;
+    if (e->interrupt_dev && e->irq_stream) {
+        cudaMemcpyAsync(e->interrupt_dev, (const void*)e->interrupt_host, sizeof(int), cudaMemcpyHostToDevice, e->irq_stream);
+        cudaStreamSynchronize(e->irq_stream);
+    }
 }
 int tss_get_stats(const tss_engine* e, tss_stats* out) {
     if (!e || !out) return TSS_E_INVALID;
@@ -650,8 +666,34 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     tss_search* s = nullptr;
     e->stats.interrupted = 0;
     e->stats.best_count = -1;
-    int rc = tss_search_create(e, grid, w, h, defs, n_defs, &p, &s);
-    if (rc) return rc;
+    int rc = TSS_OK;
+    bool only_1x1 = true;
+    for (int i = 0; i < n_defs; i++) only_1x1 = only_1x1 && defs && defs[i].w == 1 && defs[i].h == 1;
+    if (e->cached_search && grid && w > 0 && h > 0 && w <= 32 && h <= 32 && only_1x1) {
+        // reuse the engine's workspace: same buffers, fresh terrain / reach table / chain states (no allocation)
+        s = e->cached_search;
+        e->cached_search = nullptr;
+        s->w = w; s->h = h; s->seed = seed; s->chain_offset = 0; s->noise = sls::DEFAULT_NOISE_PCT;
+        s->grid.assign(grid, grid + (size_t)w * h);
+        s->totals_seen[0] = s->totals_seen[1] = 0;
+        s->dirty = false;
+        s->external_bound = sls::NO_BOUND;
+        uint32_t* rows = (uint32_t*)e->pin(2, sizeof(uint32_t) * 32);
+        if (!rows) rc = TSS_E_CUDA;
+        if (rc == TSS_OK) {
+            for (int y = 0; y < 32; y++) rows[y] = 0;
+            for (int y = 0; y < h; y++)
+                for (int x = 0; x < w; x++)
+                    if (grid[(size_t)y * w + x]) rows[y] |= 1u << x;
+            TSS_CUDA(e, cudaSetDevice(e->device));
+            cudaError_t err = cudaMemcpyAsync(s->rows_dev, rows, sizeof(uint32_t) * 32, cudaMemcpyHostToDevice, e->stream);
+            rc = err == cudaSuccess ? search_init_device(e, s, 1) : e->fail(TSS_E_CUDA, "tss_solve_upper_bound: %s", cudaGetErrorString(err));
+        }
+        if (rc != TSS_OK) { search_free(s); return rc; }
+    } else {
+        rc = tss_search_create(e, grid, w, h, defs, n_defs, &p, &s);
+        if (rc) return rc;
+    }
     if (card_limit >= 0) rc = tss_search_set_bound(s, card_limit + 1);
     const double t0 = now_ms();
     // no budget given: behave like one SAT call (return the first model within the bound), but give up after a
@@ -674,7 +716,7 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
         if (best == 0) break;
         if (first_model_only && best >= 0) break;
         if (budget_ms > 0 && now_ms() - t0 >= budget_ms) break;
-        if (epoch < 4096) epoch *= 2;
+        if (epoch < 8192) epoch *= 2;
     }
     int result = TSS_UNKNOWN;
     if (rc == TSS_OK && best >= 0) {
@@ -683,7 +725,12 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
         if (n_out) *n_out = n;
         if (rc == TSS_OK) result = TSS_SAT;
     }
-    tss_search_destroy(s);
+    if (!s->lns && !s->multi && s->n_groups == 1 && !e->cached_search && rc == TSS_OK) {
+        cudaStreamSynchronize(e->stream);
+        e->cached_search = s;  // keep the workspace for the next call
+    } else {
+        tss_search_destroy(s);
+    }
     return rc != TSS_OK ? rc : result;
 }
 

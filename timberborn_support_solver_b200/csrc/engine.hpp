@@ -27,9 +27,14 @@ struct tss_engine {
     cudaDeviceProp prop{};
     std::string error;
     tss_stats stats{};
-    volatile int* interrupt_host = nullptr;  // mapped pinned flag, polled by persistent kernels
-    int* interrupt_dev = nullptr;            // device alias of the same flag
+    // Interrupt flag polled by the search kernels.  It lives in DEVICE memory (an L2 hit per poll): polling a mapped
+    // host flag costs a PCIe round trip per warp and serialises (measured r1: 3.5 ms per poll round of 4736 warps).
+    // tss_interrupt() copies a pinned 1 into it on a dedicated non-blocking stream, from any thread.
+    volatile int* interrupt_host = nullptr;  // pinned {0, 1} source words
+    int* interrupt_dev = nullptr;            // device flag
+    cudaStream_t irq_stream = nullptr;
     std::atomic<int> interrupt_flag{0};
+    struct tss_search* cached_search = nullptr;  // workspace reused by tss_solve_upper_bound (no cudaMalloc per call)
     TssBuffer scratch[8];                    // device scratch slots
     TssBuffer staging[4];                    // pinned host staging slots
 
