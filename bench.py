@@ -168,7 +168,7 @@ def main():
     eng.set_stream(stream.cuda_stream)
     info = eng.device_info()
     grid = T.WorldGrid(np.ones((16, 16), np.uint8))
-    n_chains = args.chains or info["sm_count"] * 32
+    n_chains = args.chains or info["sm_count"] * 64      # 16-row grid: two chains per warp, 32 warps per SM
     search = eng.search(grid, seed=1, n_chains=n_chains, chain_offset=rank * n_chains)
     bound_t = torch.zeros(1, dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2

@@ -16,6 +16,10 @@ int sls_run(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls:
             int noise_pct, unsigned long long* totals_dev);
 int sls_best_reduce(tss_engine* e, const sls::ChainState* states, int chains_per_group, int n_chains, int n_groups, int2* out_dev,
                     int* bounds_dev);
+// sls_h16.cu — two chains per warp for grids of at most 16 rows (chains_per_terrain must be 0 or a multiple of 8)
+int sls_run_h16(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls::ChainState* states, int n_chains,
+                int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
+                int noise_pct, unsigned long long* totals_dev);
 int run_peaks(tss_engine* e, double* out, int n_out);
 // lns.cu — window decomposition for grids larger than 32x32
 struct LnsSearch;
@@ -437,7 +441,8 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
         *out = s;
         return TSS_OK;
     }
-    s->n_chains = (params && params->n_chains > 0) ? params->n_chains : e->prop.multiProcessorCount * 32;
+    // default: 32 warps per SM (8 CTAs of 4 warps); grids of <= 16 rows run two chains per warp
+    s->n_chains = (params && params->n_chains > 0) ? params->n_chains : e->prop.multiProcessorCount * (h <= 16 ? 64 : 32);
     s->n_groups = 1;
     s->chains_per_terrain = 0;
     uint32_t rows[32] = {0};
@@ -528,8 +533,10 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
         return TSS_OK;
     }
     int chains_per_group = s->n_groups == 1 ? s->n_chains : s->chains_per_terrain;
-    int rc = sls_run(e, s->rows_dev, s->tabs_dev, s->states, s->n_chains, s->chains_per_terrain, s->chain_offset, s->seed, steps,
-                     s->bounds_dev, target_count < 0 ? -1 : target_count, s->noise, s->totals_dev);
+    // grids of at most 16 rows: two chains per warp (same spec, same trajectories, half the instruction stream per chain)
+    const bool h16 = s->h <= 16 && (s->chains_per_terrain == 0 || s->chains_per_terrain % 8 == 0);
+    int rc = (h16 ? sls_run_h16 : sls_run)(e, s->rows_dev, s->tabs_dev, s->states, s->n_chains, s->chains_per_terrain, s->chain_offset, s->seed,
+                                           steps, s->bounds_dev, target_count < 0 ? -1 : target_count, s->noise, s->totals_dev);
     if (rc == TSS_OK) rc = sls_best_reduce(e, s->states, chains_per_group, s->n_chains, s->n_groups, s->best_dev, s->bounds_dev);
     if (rc) return rc;
     TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
@@ -740,7 +747,7 @@ int tss_solve_batch(tss_engine* e, const uint8_t* grids, int32_t w, int32_t h, i
     if (!grids || !out_counts || w <= 0 || h <= 0 || n < 0 || steps <= 0) return e->fail(TSS_E_INVALID, "tss_solve_batch: bad arguments");
     if (w > 32 || h > 32) return e->fail(TSS_E_UNSUPPORTED, "tss_solve_batch: terrains larger than 32x32 are not accelerated yet");
     TSS_CUDA(e, cudaSetDevice(e->device));
-    const int CPT = 4;                       // chains per terrain = one CTA
+    const int CPT = h <= 16 ? 8 : 4;         // chains per terrain = one CTA (two chains per warp when the grid has <= 16 rows)
     const int64_t CHUNK = 32768;             // terrains per pass (reach tables: 8 KB each)
     const size_t tiles = (size_t)w * h;
     e->stats.interrupted = 0;

@@ -1,0 +1,275 @@
+// Kernel (b), half-warp variant for grids of at most 16 rows (rect 16x16, test/ex1-3): TWO chains per warp.
+//
+// ncu on the one-chain-per-warp kernel (profiles/r1_sls_kernel.md) shows the ALU pipe as the limiter and most of a
+// step's ~340 warp instructions are per-chain "uniform" control work (hashes, picks, ballots, key building) that all
+// 32 lanes repeat.  With <= 16 grid rows only 16 lanes hold data, so each half-warp runs its own chain here: the same
+// instruction stream now advances two layouts.  The step rule, RNG and tie-breaks are EXACTLY those of sls_spec.hpp /
+// sls.cu (the parity tests replay both kernels against the same CPU model); only the lane mapping differs:
+//   lane = 16*half + row; removal candidates are scored 16 per pass, the 25 diamond cells in two passes of 16;
+//   the step is fully predicated (drop / record / swap flags per half) so both halves stay convergent for the shuffles.
+#include "engine.hpp"
+#include "sls_spec.hpp"
+
+namespace tss {
+namespace sls16 {
+
+using namespace tss::sls;
+
+constexpr int WARPS = 4;          // 8 chains per CTA
+constexpr int MAX_SITES16 = 512;  // tiles of a 32x16 grid
+constexpr unsigned FULL = 0xffffffffu;
+
+struct Lane {
+    uint32_t C, S, c0, c1, c2, c3, c4, U, O;
+};
+__device__ __forceinline__ void derive(Lane& L) {
+    uint32_t hi = L.c1 | L.c2 | L.c3 | L.c4;
+    L.U = L.C & ~(L.c0 | hi);
+    L.O = L.c0 & ~hi & L.C;
+}
+__device__ __forceinline__ int anchor(int x) { return max(x - 3, 0); }
+__device__ __forceinline__ uint32_t row_mask(uint2 win, int x, int y, int row) {
+    int dy = row - y + 3;
+    int d = min(max(dy, 0), 6);
+    uint32_t m = d < 4 ? (win.x >> (7 * d)) : (win.y >> (7 * (d - 4)));
+    m = dy == d ? (m & 0x7fu) : 0u;
+    return m << anchor(x);
+}
+__device__ __forceinline__ void planes_add(Lane& L, uint32_t m) {
+    uint32_t t;
+    t = L.c0 & m; L.c0 ^= m; m = t;
+    t = L.c1 & m; L.c1 ^= m; m = t;
+    t = L.c2 & m; L.c2 ^= m; m = t;
+    t = L.c3 & m; L.c3 ^= m; m = t;
+    L.c4 ^= m;
+}
+__device__ __forceinline__ void planes_sub(Lane& L, uint32_t m) {
+    uint32_t t;
+    t = ~L.c0 & m; L.c0 ^= m; m = t;
+    t = ~L.c1 & m; L.c1 ^= m; m = t;
+    t = ~L.c2 & m; L.c2 ^= m; m = t;
+    t = ~L.c3 & m; L.c3 ^= m; m = t;
+    L.c4 ^= m;
+}
+// popcount(B & R(site)) with B row-distributed inside each half-warp (width-16 shuffles: row index modulo 16; rows that
+// wrap around meet zero window bits because the grid has at most 16 rows)
+__device__ __forceinline__ int score16(uint32_t B, int x, int y, uint2 win) {
+    const int ax = anchor(x);
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 6; j >= 4; j--) {
+        uint32_t row = __shfl_sync(FULL, B, y - 3 + j, 16);
+        hi = hi * 128u + ((row >> ax) & 0x7fu);
+    }
+#pragma unroll
+    for (int j = 3; j >= 0; j--) {
+        uint32_t row = __shfl_sync(FULL, B, y - 3 + j, 16);
+        lo = lo * 128u + ((row >> ax) & 0x7fu);
+    }
+    return __popc(lo & win.x) + __popc(hi & win.y);
+}
+__device__ __forceinline__ uint32_t half_min(uint32_t v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o, 16));
+    return v;
+}
+__device__ __forceinline__ uint32_t half_max(uint32_t v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o, 16));
+    return v;
+}
+__device__ __forceinline__ int pick_rotated16(uint32_t bits16, uint32_t o) {  // spec: rotate the 32-bit row mask; rows >= 16 are empty
+    uint32_t rot = __funnelshift_r(bits16, bits16, o);
+    return (int)((__ffs(rot) - 1 + o) & 31u);
+}
+__device__ __forceinline__ void diamond_cell(int i, int& dx, int& dy) {
+    int r = (i >= 1) + (i >= 4) + (i >= 9) + (i >= 16) + (i >= 21) + (i >= 24);
+    int start = r <= 4 ? r * r : (r == 5 ? 21 : 24);
+    dy = r - 3;
+    dx = (i - start) - (3 - abs(dy));
+}
+
+__global__ void __launch_bounds__(WARPS * 32) sls_h16_kernel(const uint32_t* __restrict__ terrain_rows, const uint2* __restrict__ rtabs,
+                                                            ChainState* __restrict__ states, int n_chains, int chains_per_terrain,
+                                                            uint32_t chain_offset, uint64_t seed, long long steps,
+                                                            const int* __restrict__ bounds, int target, int noise_pct,
+                                                            const volatile int* interrupt, unsigned long long* __restrict__ totals) {
+    __shared__ uint2 tab[1024];
+    __shared__ uint16_t sites_all[WARPS * 2][MAX_SITES16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, row = lane & 15;
+    const int chain = (blockIdx.x * WARPS + warp) * 2 + half;
+    const int terrain = chains_per_terrain > 0 ? (blockIdx.x * WARPS * 2) / chains_per_terrain : 0;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) tab[i] = rtabs[(size_t)terrain * 1024 + i];
+    __syncthreads();
+    const bool exists = chain < n_chains;
+    ChainState& st = states[exists ? chain : 0];
+    if (!__any_sync(FULL, exists && !st.done)) return;
+
+    const int epoch_bound = bounds[chains_per_terrain > 0 ? terrain : 0];
+    const uint32_t base = chain_base(seed, chain_offset + (uint32_t)chain);
+    const uint32_t nq7 = noise_q7(noise_pct);
+    const unsigned hshift = half * 16;
+    uint16_t* sites = sites_all[warp * 2 + half];
+    Lane L;
+    L.C = terrain_rows[(size_t)terrain * 32 + row];
+    L.S = exists ? st.S[row] : 0u;
+    uint32_t bestS = exists ? st.bestS[row] : 0u;
+    int k = exists ? st.k : 0, best = exists ? st.best : 0, tabu_add = exists ? st.tabu_add : -1, tabu_rem = exists ? st.tabu_rem : -1;
+    int done = exists ? st.done : 1;
+    const int done_at_start = done;
+    uint32_t step = exists ? st.step : 0u;
+    unsigned long long scored = 0;
+    long long my_steps = 0;
+
+    {   // site list (row-major) and cover planes from S, per half
+        int c = __popc(L.S), off = c;
+        for (int o = 1; o < 16; o <<= 1) { int t = __shfl_up_sync(FULL, off, o, 16); if (row >= o) off += t; }
+        off -= c;
+        for (uint32_t bits = L.S; bits; bits &= bits - 1) sites[off++] = (uint16_t)(row * 32 + __ffs(bits) - 1);
+        __syncwarp();
+        L.c0 = L.c1 = L.c2 = L.c3 = L.c4 = 0;
+        const int kmax = max(k, __shfl_xor_sync(FULL, k, 16));
+        for (int i = 0; i < kmax; i++) {
+            int v = i < k ? sites[i] : 0;
+            planes_add(L, i < k ? row_mask(tab[v], v & 31, v >> 5, row) : 0u);
+        }
+        derive(L);
+    }
+
+    // the 25 diamond cells in two passes of 16 lanes: cell = 16*pass + row
+    int dx0, dy0, dx1, dy1;
+    diamond_cell(row, dx0, dy0);
+    diamond_cell(min(16 + row, 24), dx1, dy1);
+    const bool cell1 = 16 + row < 25;
+
+    for (long long it = 0; it < steps; it++) {
+        if ((it & 1023) == 1023 && *interrupt) break;
+        if (!__any_sync(FULL, !done)) break;
+        const bool active = !done;
+        const int limit = min(epoch_bound, best);
+        const uint32_t hs = step_hash(base, step);
+        bool inc = active;  // this chain consumes a step
+        // ---- classify the step (uniform per half)
+        const bool drop = active && k >= limit;
+        if (drop && k == 0) { done = 1; inc = false; }
+        const uint32_t ub = (__ballot_sync(FULL, L.U != 0) >> hshift) & 0xffffu;
+        const bool complete = active && !drop && ub == 0;
+        if (complete) {
+            best = k;
+            bestS = L.S;
+            if (k <= target || k == 0) done = 1;
+        }
+        const bool swap_rem = active && !drop && !complete && k == limit - 1 && k > 0;
+        const bool do_remove = (drop && k > 0) || swap_rem;
+        const bool do_add = active && !drop && !complete;
+        // ---- removal: min-loss support, random ties (tabu: the support just added, except when dropping)
+        if (__any_sync(FULL, do_remove)) {
+            const int exclude = drop ? -1 : tabu_rem;
+            const int kk = do_remove ? k : 0, kmax = max(kk, __shfl_xor_sync(FULL, kk, 16));
+            uint32_t best_key = 0xffffffffu;
+            int best_i = 0;
+            for (int b = 0; b < kmax; b += 16) {
+                const int i = b + row;
+                const bool valid = i < kk;
+                const int v = valid ? sites[i] : 0;
+                const int loss = score16(L.O, v & 31, v >> 5, tab[v]);
+                const uint32_t tie = tie_remove(lane_hash(hs, (uint32_t)(i & 31)), (uint32_t)(i >> 5));
+                const uint32_t key = (valid && !(v == exclude && kk > 1)) ? (((uint32_t)loss << 16) | tie) : 0xffffffffu;
+                const uint32_t mn = half_min(key);
+                const uint32_t eq = (__ballot_sync(FULL, key == mn) >> hshift) & 0xffffu;
+                if (mn < best_key) { best_key = mn; best_i = b + __ffs(eq) - 1; }
+            }
+            const int u = do_remove ? sites[best_i] : 0;
+            __syncwarp();
+            if (do_remove && row == 0) sites[best_i] = sites[k - 1];
+            __syncwarp();
+            planes_sub(L, do_remove ? row_mask(tab[u], u & 31, u >> 5, row) : 0u);
+            derive(L);
+            if (do_remove) {
+                if (row == (u >> 5)) L.S &= ~(1u << (u & 31));
+                scored += (unsigned)k;
+                k--;
+                tabu_add = u;
+            }
+        }
+        // ---- addition at a random uncovered tile
+        if (__any_sync(FULL, do_add)) {
+            const uint32_t rowmask = (__ballot_sync(FULL, L.U != 0) >> hshift) & 0xffffu;
+            const bool adding = do_add && rowmask != 0;   // (rowmask is never empty for an adding chain)
+            const int y = adding ? pick_rotated16(rowmask, hs & 31u) : 0;
+            const uint32_t Urow = __shfl_sync(FULL, L.U, y, 16);
+            const int x = adding ? pick_rotated16(Urow, (hs >> 5) & 31u) : 0;
+            const uint2 wt = tab[y * 32 + x];
+            const int xoff = min(x, 3);
+            // pass 0: cells 0..15, pass 1: cells 16..24
+            const int col0 = dx0 + xoff, col1 = dx1 + xoff;
+            const int r0 = dy0 + 3, r1 = dy1 + 3;
+            const bool v0 = adding && col0 >= 0 && ((((r0 >= 4) ? wt.y : wt.x) >> (7 * (r0 & 3) + col0)) & 1u);
+            const bool v1 = adding && cell1 && col1 >= 0 && ((((r1 >= 4) ? wt.y : wt.x) >> (7 * (r1 & 3) + col1)) & 1u);
+            const int cv0 = v0 ? (y + dy0) * 32 + x + dx0 : 0, cv1 = v1 ? (y + dy1) * 32 + x + dx1 : 0;
+            const uint32_t vb0 = (__ballot_sync(FULL, v0) >> hshift) & 0xffffu, vb1 = (__ballot_sync(FULL, v1) >> hshift) & 0xffffu;
+            const int nc = __popc(vb0) + __popc(vb1);
+            const bool noise = ((hs >> 10) & 127u) < nq7;
+            const uint32_t t0 = tie_add(lane_hash(hs, (uint32_t)row)), t1 = tie_add(lane_hash(hs, (uint32_t)(16 + row)));
+            uint32_t key0, key1;
+            if (__any_sync(FULL, adding && !noise)) {
+                const int g0 = score16(L.U, cv0 & 31, cv0 >> 5, tab[cv0]);
+                const int g1 = score16(L.U, cv1 & 31, cv1 >> 5, tab[cv1]);
+                key0 = noise ? (0x10000u | t0) : (((uint32_t)(g0 + 1) << 16) | t0);
+                key1 = noise ? (0x10000u | t1) : (((uint32_t)(g1 + 1) << 16) | t1);
+            } else {
+                key0 = 0x10000u | t0;
+                key1 = 0x10000u | t1;
+            }
+            const bool tabu0 = !noise && cv0 == tabu_add && nc > 1, tabu1 = !noise && cv1 == tabu_add && nc > 1;
+            key0 = (v0 && !tabu0) ? key0 : 0u;
+            key1 = (v1 && !tabu1) ? key1 : 0u;
+            const uint32_t mx = half_max(max(key0, key1));
+            // lowest diamond cell among the maxima (cells 0..15 before 16..24)
+            const uint32_t e0 = (__ballot_sync(FULL, key0 == mx) >> hshift) & 0xffffu, e1 = (__ballot_sync(FULL, key1 == mx) >> hshift) & 0xffffu;
+            const int src = (e0 ? __ffs(e0) : __ffs(e1)) - 1;
+            const int pick0 = __shfl_sync(FULL, cv0, src, 16), pick1 = __shfl_sync(FULL, cv1, src, 16);
+            const int v = e0 ? pick0 : pick1;
+            planes_add(L, adding ? row_mask(tab[v], v & 31, v >> 5, row) : 0u);
+            derive(L);
+            if (adding) {
+                if (row == (v >> 5)) L.S |= 1u << (v & 31);
+                if (row == 0) sites[k] = (uint16_t)v;
+                if (!noise) scored += (unsigned)nc;
+                k++;
+                tabu_rem = v;
+            }
+            __syncwarp();
+        }
+        if (inc) { step++; my_steps++; }
+    }
+
+    if (exists && !done_at_start) {
+        st.S[row] = L.S;
+        st.bestS[row] = bestS;
+        if (row == 0) {
+            st.k = k; st.best = best; st.step = step; st.tabu_add = tabu_add; st.tabu_rem = tabu_rem; st.done = done;
+            unsigned long long tot = ((unsigned long long)st.scored_hi << 32 | st.scored_lo) + scored;
+            st.scored_lo = (uint32_t)tot; st.scored_hi = (uint32_t)(tot >> 32);
+            st.steps_done += (uint32_t)my_steps;
+            atomicAdd(&totals[0], scored);
+            atomicAdd(&totals[1], (unsigned long long)my_steps);
+        }
+    }
+}
+
+}  // namespace sls16
+
+int sls_run_h16(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls::ChainState* states, int n_chains,
+                int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
+                int noise_pct, unsigned long long* totals_dev) {
+    const int per_cta = sls16::WARPS * 2;
+    int blocks = (n_chains + per_cta - 1) / per_cta;
+    sls16::sls_h16_kernel<<<blocks, sls16::WARPS * 32, 0, e->stream>>>(rows_dev, tabs_dev, states, n_chains, chains_per_terrain, chain_offset, seed,
+                                                                     steps, bounds_dev, target, noise_pct, e->interrupt_dev, totals_dev);
+    TSS_CHECK_LAUNCH(e);
+    e->stats.kernel_launches++;
+    return TSS_OK;
+}
+
+}  // namespace tss
