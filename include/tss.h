@@ -211,10 +211,12 @@ void tss_sls_spec_probe(uint32_t* out);
 int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,
                           int32_t card_limit, uint64_t seed, int32_t budget_ms, int64_t max_steps, tss_platform* out,
                           int32_t cap, int32_t* n_out);
-/* Terrain batch: n independent terrains [n][w*h], 1x1 supports; out_counts[n] = best count per
+/* Terrain batch: n independent terrains [n][w*h] (grids up to 32x32), 1x1 supports; `steps` SLS steps
+ * per chain, `chains_per_terrain` independent chains per terrain sharing their bound every 1024 steps (0 = one CTA
+ * = 4 chains, 8 for grids of <= 16 rows; otherwise rounded up to a multiple of that).  out_counts[n] = best count per
  * terrain; out_layouts (optional) = packed support rows [n][h*wpr]. */
 int tss_solve_batch(tss_engine* e, const uint8_t* grids, int32_t w, int32_t h, int64_t n, uint64_t seed, int64_t steps,
-                    int32_t* out_counts, uint32_t* out_layouts);
+                    int32_t chains_per_terrain, int32_t* out_counts, uint32_t* out_layouts);
 
 /* ------------------------------------------------------------------------------------------ measured peaks */
 /* Runs the integer-issue (LOP3 / POPC / SHFL) and shared-memory micro-benchmarks SURVEY.md §8(d) asks for.

@@ -25,6 +25,11 @@ uint32_t lane_hash(uint32_t hs, uint32_t lane) { return fmix32(hs ^ ((lane + 1u)
 uint32_t noise_q7(int noise_pct) { return (uint32_t)((noise_pct * 128 + 50) / 100); }
 uint32_t tie_add(uint32_t hl) { return hl & 0xffffu; }
 uint32_t tie_remove(uint32_t hl, uint32_t chunk) { return (hl * (2u * chunk + 1u)) >> 16; }
+constexpr uint32_t TABU_BIT = 0x40000000u;
+int tenure_of(uint32_t global_chain) { static const int t[4] = {3, 6, 12, 20}; return t[global_chain & 3u]; }
+int effective_tenure(int tenure, int k) { int c = k / 3; c = c < 2 ? 2 : c; return tenure < c ? tenure : c; }
+uint16_t stamp_reset(uint32_t step) { return (uint16_t)(step - 0x8000u); }
+bool is_tabu(uint32_t step, uint16_t stamp, int tenure) { return (uint16_t)((uint16_t)step - stamp) < (uint16_t)tenure; }
 
 struct Model {
     int w, h;
@@ -60,7 +65,8 @@ struct Chain {
     std::vector<uint8_t> S, bestS;  // [1024]
     std::vector<uint8_t> cnt;       // cover count per tile
     std::vector<int> sites;
-    int k = 0, best = NO_BOUND, tabu_add = -1, tabu_rem = -1, done = 0;
+    std::vector<uint16_t> stamp;    // step of the last flip of every site (16 bit), reset at the start of an epoch
+    int k = 0, best = NO_BOUND, done = 0;
     uint32_t step = 0;
     uint64_t scored = 0, steps_done = 0;
 };
@@ -74,19 +80,20 @@ struct Runner {
     const Model& M;
     Chain& c;
     uint32_t base;
-    Runner(const Model& m, Chain& ch, uint32_t b) : M(m), c(ch), base(b) {}
+    int tenure, ten = 1;  // chain tenure; effective tenure of the current step (fixed at the top of the step)
+    Runner(const Model& m, Chain& ch, uint32_t b, int t) : M(m), c(ch), base(b), tenure(t) {}
 
     bool uncovered(int t) const { return M.ceil[t] && c.cnt[t] == 0; }
     int loss(int u) const { int n = 0; for (int t : M.reach[u]) n += c.cnt[t] == 1; return n; }
     int gain(int v) const { int n = 0; for (int t : M.reach[v]) n += c.cnt[t] == 0; return n; }
 
-    int remove_min_loss(int exclude, uint32_t hs) {
+    int remove_min_loss(bool use_tabu, uint32_t hs) {
         uint32_t best_key = 0xffffffffu;
         int best_i = 0;
         for (int i = 0; i < c.k; i++) {  // chunks of 32 lanes, lowest lane wins ties; strict < across chunks
             int v = c.sites[i];
-            if (v == exclude && c.k > 1) continue;
-            uint32_t key = ((uint32_t)loss(v) << 16) | tie_remove(lane_hash(hs, (uint32_t)(i & 31)), (uint32_t)(i >> 5));
+            uint32_t young = (use_tabu && is_tabu(c.step, c.stamp[v], ten)) ? TABU_BIT : 0u;  // young supports only as a last resort
+            uint32_t key = young | ((uint32_t)loss(v) << 16) | tie_remove(lane_hash(hs, (uint32_t)(i & 31)), (uint32_t)(i >> 5));
             if (key < best_key) { best_key = key; best_i = i; }
         }
         int u = c.sites[best_i];
@@ -95,6 +102,7 @@ struct Runner {
         c.k--;
         for (int t : M.reach[u]) c.cnt[t]--;
         c.S[u] = 0;
+        c.stamp[u] = (uint16_t)c.step;
         return u;
     }
 
@@ -105,14 +113,16 @@ struct Runner {
         for (int t = 0; t < 1024; t++) if (c.S[t]) c.sites.push_back(t);
         c.cnt.assign(1024, 0);
         for (int s : c.sites) for (int t : M.reach[s]) c.cnt[t]++;
+        c.stamp.assign(1024, stamp_reset(c.step));
         long long it = 0;
         for (; it < steps; it++, c.step++) {
             const int limit = std::min(epoch_bound, c.best);
             const uint32_t hs = step_hash(base, c.step);
+            ten = effective_tenure(tenure, c.k);
             if (c.k >= limit) {
                 if (c.k == 0) { c.done = 1; break; }
                 c.scored += (uint64_t)c.k;
-                c.tabu_add = remove_min_loss(-1, hs);
+                remove_min_loss(false, hs);
                 continue;
             }
             bool any = false;
@@ -125,7 +135,7 @@ struct Runner {
             }
             if (c.k == limit - 1 && c.k > 0) {
                 c.scored += (uint64_t)c.k;
-                c.tabu_add = remove_min_loss(c.tabu_rem, hs);
+                remove_min_loss(true, hs);
             }
             uint32_t rowmask = 0;
             for (int y = 0; y < 32; y++) for (int x = 0; x < 32; x++) if (uncovered(y * 32 + x)) rowmask |= 1u << y;
@@ -151,7 +161,8 @@ struct Runner {
             bool first = true;
             for (auto& [cv, ln] : cand) {
                 uint32_t tie = tie_add(lane_hash(hs, (uint32_t)ln));
-                uint32_t key = noise ? (0x10000u | tie) : ((cv == c.tabu_add && nc > 1) ? 0u : (((uint32_t)(gain(cv) + 1) << 16) | tie));
+                uint32_t fresh = is_tabu(c.step, c.stamp[cv], ten) ? 0u : TABU_BIT;  // recently removed sites only as a last resort
+                uint32_t key = noise ? (0x10000u | tie) : (fresh | ((uint32_t)(gain(cv) + 1) << 16) | tie);
                 if (first || key > mx) { mx = key; v = cv; first = false; }
             }
             if (!noise) c.scored += (uint64_t)nc;
@@ -159,7 +170,7 @@ struct Runner {
             c.S[v] = 1;
             c.sites.push_back(v);
             c.k++;
-            c.tabu_rem = v;
+            c.stamp[v] = (uint16_t)c.step;
         }
         c.steps_done += (uint64_t)it;
     }
@@ -187,7 +198,7 @@ int tsso_sls_model(const uint8_t* grid, int w, int h, int n_chains, uint32_t cha
         long long steps = epochs[3 * e];
         int bound = (int)epochs[3 * e + 1], target = (int)epochs[3 * e + 2];
         if (share_bound) bound = std::min(bound, shared);
-        for (int i = 0; i < n_chains; i++) Runner(M, chains[i], chain_base(seed, chain_offset + (uint32_t)i)).run(steps, bound, target, noise_pct);
+        for (int i = 0; i < n_chains; i++) Runner(M, chains[i], chain_base(seed, chain_offset + (uint32_t)i), tenure_of(chain_offset + (uint32_t)i)).run(steps, bound, target, noise_pct);
         for (auto& c : chains) shared = std::min(shared, c.best);
     }
     for (int i = 0; i < n_chains; i++) {
@@ -201,7 +212,7 @@ int tsso_sls_model(const uint8_t* grid, int w, int h, int n_chains, uint32_t cha
 
 // constants of the spec, for the agreement test against sls_spec.hpp
 void tsso_sls_constants(uint32_t* out) {
-    out[0] = K1; out[1] = K2; out[2] = noise_q7(20); out[3] = tie_remove(0x12345678u, 3); out[4] = tie_add(0x12345678u);
+    out[0] = K1; out[1] = K2; out[2] = noise_q7(20); out[3] = tie_remove(0x12345678u, 3) + 1000u * (uint32_t)(tenure_of(0) + 2 * tenure_of(1) + 3 * tenure_of(2) + 4 * tenure_of(3)) + (is_tabu(70000u, stamp_reset(70000u), 20) ? 1u : 0u) + (is_tabu(65540u, (uint16_t)65530u, 12) ? 2u : 0u) + 100000u * (uint32_t)(effective_tenure(20, 14) + effective_tenure(3, 100) + effective_tenure(6, 2)); out[4] = tie_add(0x12345678u);
     out[5] = step_hash(1u, 2u); out[6] = lane_hash(3u, 4u); out[7] = chain_base(0x0123456789abcdefull, 5u); out[8] = NO_BOUND;
 }
 

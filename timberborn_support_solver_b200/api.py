@@ -514,13 +514,13 @@ class Engine:
             return SAT, PlatformLayout(Platform._from_c(out[i]) for i in range(n.value))
         return INTERRUPTED, None
 
-    def solve_batch(self, grids, seed=0, steps=2048, want_layouts=False):
+    def solve_batch(self, grids, seed=0, steps=2048, want_layouts=False, chains_per_terrain=0):
         """grids: uint8[n, h, w] -> counts int32[n] (and packed support rows uint32[n, h] if asked)"""
         g = _u8(grids)
         n, h, w = g.shape
         counts = np.zeros(n, np.int32)
         layouts = np.zeros((n, h), np.uint32) if want_layouts else None
-        self._check(self.lib.tss_solve_batch(self._h, _ptr(g, C.c_uint8), w, h, n, seed, steps, _ptr(counts, C.c_int32),
+        self._check(self.lib.tss_solve_batch(self._h, _ptr(g, C.c_uint8), w, h, n, seed, steps, chains_per_terrain, _ptr(counts, C.c_int32),
                                              _ptr(layouts, C.c_uint32) if want_layouts else None))
         return (counts, layouts) if want_layouts else counts
 

@@ -503,7 +503,9 @@ int tss_search_n_chains(const tss_search* s) { return s ? s->n_chains : TSS_E_IN
 
 void tss_sls_spec_probe(uint32_t* out) {
     if (!out) return;
-    out[0] = sls::K1; out[1] = sls::K2; out[2] = sls::noise_q7(20); out[3] = sls::tie_remove(0x12345678u, 3); out[4] = sls::tie_add(0x12345678u);
+    out[0] = sls::K1; out[1] = sls::K2; out[2] = sls::noise_q7(20); out[3] = sls::tie_remove(0x12345678u, 3) + 1000u * (uint32_t)(sls::tenure_of(0) + 2 * sls::tenure_of(1) + 3 * sls::tenure_of(2) + 4 * sls::tenure_of(3)) +
+             (sls::is_tabu(70000u, sls::stamp_reset(70000u), 20) ? 1u : 0u) + (sls::is_tabu(65540u, (uint16_t)65530u, 12) ? 2u : 0u) +
+             100000u * (uint32_t)(sls::effective_tenure(20, 14) + sls::effective_tenure(3, 100) + sls::effective_tenure(6, 2)); out[4] = sls::tie_add(0x12345678u);
     out[5] = sls::step_hash(1u, 2u); out[6] = sls::lane_hash(3u, 4u); out[7] = sls::chain_base(0x0123456789abcdefull, 5u); out[8] = sls::NO_BOUND;
 }
 
@@ -742,13 +744,15 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
 }
 
 int tss_solve_batch(tss_engine* e, const uint8_t* grids, int32_t w, int32_t h, int64_t n, uint64_t seed, int64_t steps,
-                    int32_t* out_counts, uint32_t* out_layouts) {
+                    int32_t chains_per_terrain, int32_t* out_counts, uint32_t* out_layouts) {
     if (!e) return TSS_E_INVALID;
-    if (!grids || !out_counts || w <= 0 || h <= 0 || n < 0 || steps <= 0) return e->fail(TSS_E_INVALID, "tss_solve_batch: bad arguments");
+    if (!grids || !out_counts || w <= 0 || h <= 0 || n < 0 || steps <= 0 || chains_per_terrain < 0)
+        return e->fail(TSS_E_INVALID, "tss_solve_batch: bad arguments");
     if (w > 32 || h > 32) return e->fail(TSS_E_UNSUPPORTED, "tss_solve_batch: terrains larger than 32x32 are not accelerated yet");
     TSS_CUDA(e, cudaSetDevice(e->device));
-    const int CPT = h <= 16 ? 8 : 4;         // chains per terrain = one CTA (two chains per warp when the grid has <= 16 rows)
-    const int64_t CHUNK = 32768;             // terrains per pass (reach tables: 8 KB each)
+    const int per_cta = h <= 16 ? 8 : 4;     // chains of one CTA (two chains per warp when the grid has <= 16 rows)
+    const int CPT = chains_per_terrain <= 0 ? per_cta : ((chains_per_terrain + per_cta - 1) / per_cta) * per_cta;
+    const int64_t CHUNK = 32768 / (CPT / per_cta) > 256 ? 32768 / (CPT / per_cta) : 256;  // terrains per pass (reach tables: 8 KB each)
     const size_t tiles = (size_t)w * h;
     e->stats.interrupted = 0;
     double dev_ms = 0;

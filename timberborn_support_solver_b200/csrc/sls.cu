@@ -116,12 +116,14 @@ __global__ void build_reach_kernel(const uint32_t* __restrict__ rows, int n_terr
 struct WarpCtx {
     const uint2* tab;
     uint16_t* sites;
-    int lane;
+    uint16_t* stamps;  // step of the last flip of every site (16 bit)
+    int lane, tenure;
 };
 
-// Removes the support with the smallest loss (random ties), skipping `exclude` when another choice exists.
-// Returns the removed site.  Scores k candidate layouts.
-__device__ __forceinline__ int remove_min_loss(Lane& L, const WarpCtx& w, int& k, uint32_t hl, int exclude) {
+// Removes the support with the smallest loss (random ties); supports added fewer than `tenure` steps ago are only
+// chosen when every support is that young (use_tabu = false when dropping).  Returns the removed site.  Scores k
+// candidate layouts.
+__device__ __forceinline__ int remove_min_loss(Lane& L, const WarpCtx& w, int& k, uint32_t hl, uint32_t step, int ten, bool use_tabu) {
     uint32_t best_key = 0xffffffffu;
     int best_i = 0;
     for (int b = 0, chunk = 0; b < k; b += 32, chunk++) {
@@ -130,7 +132,8 @@ __device__ __forceinline__ int remove_min_loss(Lane& L, const WarpCtx& w, int& k
         int v = valid ? w.sites[i] : 0;
         uint2 win = w.tab[v];
         int loss = score(L.O, v & 31, v >> 5, win);
-        uint32_t key = (valid && !(v == exclude && k > 1)) ? (((uint32_t)loss << 16) | tie_remove(hl, (uint32_t)chunk)) : 0xffffffffu;
+        const uint32_t young = (use_tabu && is_tabu(step, w.stamps[v], ten)) ? TABU_BIT : 0u;
+        uint32_t key = valid ? (young | ((uint32_t)loss << 16) | tie_remove(hl, (uint32_t)chunk)) : 0xffffffffu;
         uint32_t mn = __reduce_min_sync(FULL, key);
         if (mn < best_key) {
             best_key = mn;
@@ -139,7 +142,7 @@ __device__ __forceinline__ int remove_min_loss(Lane& L, const WarpCtx& w, int& k
     }
     int u = w.sites[best_i];
     __syncwarp();
-    if (w.lane == 0) w.sites[best_i] = w.sites[k - 1];
+    if (w.lane == 0) { w.sites[best_i] = w.sites[k - 1]; w.stamps[u] = (uint16_t)step; }
     __syncwarp();
     k--;
     planes_sub(L, row_mask(w.tab[u], u & 31, u >> 5, w.lane));
@@ -162,6 +165,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restr
                                                         unsigned long long* __restrict__ totals) {
     __shared__ uint2 tab[1024];
     __shared__ uint16_t sites_all[WARPS][MAX_SITES];
+    __shared__ uint16_t stamps_all[WARPS][1024];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chain = blockIdx.x * WARPS + warp;
     const int terrain = chains_per_terrain > 0 ? (blockIdx.x * WARPS) / chains_per_terrain : 0;
@@ -175,17 +179,18 @@ __global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restr
     const int epoch_bound = bounds[chains_per_terrain > 0 ? terrain : 0];
     const uint32_t base = chain_base(seed, chain_offset + (uint32_t)chain);
     const uint32_t nq7 = noise_q7(noise_pct);
-    WarpCtx w{tab, sites_all[warp], lane};
+    WarpCtx w{tab, sites_all[warp], stamps_all[warp], lane, tenure_of(chain_offset + (uint32_t)chain)};
     Lane L;
     L.C = WINDOW ? need_rows[(size_t)terrain * 32 + lane] : terrain_rows[(size_t)terrain * 32 + lane];  // tiles that need cover
     L.S = st.S[lane];
     uint32_t bestS = st.bestS[lane];
-    int k = st.k, best = st.best, tabu_add = st.tabu_add, tabu_rem = st.tabu_rem, done = 0;
+    int k = st.k, best = st.best, done = 0;
     uint32_t step = st.step;
     unsigned long long scored = 0;
 
-    // rebuild the site list (row-major) and the cover-count planes from S
+    // rebuild the site list (row-major) and the cover-count planes from S; flip stamps start "half a period ago"
     {
+        for (int i = lane; i < 1024; i += 32) w.stamps[i] = stamp_reset(step);
         int c = __popc(L.S), off = c;
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, off, o); if (lane >= o) off += t; }
         off -= c;
@@ -213,10 +218,11 @@ __global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restr
         const int limit = min(epoch_bound, best);
         const uint32_t hs = step_hash(base, step);
         const uint32_t hl = lane_hash(hs, (uint32_t)lane);
+        const int ten = effective_tenure(w.tenure, k);  // fixed for the whole step
         if (k >= limit) {  // 1. too many supports for an improvement: drop one
             if (k == 0) { done = 1; break; }
             scored += (unsigned)k;
-            tabu_add = remove_min_loss(L, w, k, hl, -1);
+            remove_min_loss(L, w, k, hl, step, ten, false);
             continue;
         }
         if (!__any_sync(FULL, L.U != 0)) {  // 2. complete layout with k < limit supports
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restr
         }
         if (k == limit - 1 && k > 0) {  // 3. at capacity: swap = remove + add
             scored += (unsigned)k;
-            tabu_add = remove_min_loss(L, w, k, hl, tabu_rem);
+            remove_min_loss(L, w, k, hl, step, ten, true);
         }
         const uint32_t rowmask = __ballot_sync(FULL, L.U != 0);
         const int y = pick_rotated(rowmask, hs & 31u);
@@ -245,7 +251,8 @@ __global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restr
             key = valid ? (0x10000u | tie_add(hl)) : 0u;
         } else {
             int g = score(L.U, cv & 31, cv >> 5, tab[cv]);
-            key = (valid && !(cv == tabu_add && nc > 1)) ? (((uint32_t)(g + 1) << 16) | tie_add(hl)) : 0u;
+            const uint32_t fresh = is_tabu(step, w.stamps[cv], ten) ? 0u : TABU_BIT;  // recently removed sites only as a last resort
+            key = valid ? (fresh | ((uint32_t)(g + 1) << 16) | tie_add(hl)) : 0u;
             scored += (unsigned)nc;
         }
         const uint32_t mx = __reduce_max_sync(FULL, key);
@@ -253,16 +260,15 @@ __global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restr
         planes_add(L, row_mask(tab[v], v & 31, v >> 5, lane));
         derive(L);
         if (lane == (v >> 5)) L.S |= 1u << (v & 31);
-        if (lane == 0) w.sites[k] = (uint16_t)v;
+        if (lane == 0) { w.sites[k] = (uint16_t)v; w.stamps[v] = (uint16_t)step; }
         __syncwarp();
         k++;
-        tabu_rem = v;
     }
 
     st.S[lane] = L.S;
     st.bestS[lane] = bestS;
     if (lane == 0) {
-        st.k = k; st.best = best; st.step = step; st.tabu_add = tabu_add; st.tabu_rem = tabu_rem; st.done = done;
+        st.k = k; st.best = best; st.step = step; st.done = done;
         unsigned long long tot = ((unsigned long long)st.scored_hi << 32 | st.scored_lo) + scored;
         st.scored_lo = (uint32_t)tot; st.scored_hi = (uint32_t)(tot >> 32);
         st.steps_done += (uint32_t)it;

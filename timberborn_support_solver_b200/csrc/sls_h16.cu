@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_h16_kernel(const uint32_t* __r
                                                             const volatile int* interrupt, unsigned long long* __restrict__ totals) {
     __shared__ uint2 tab[1024];
     __shared__ uint16_t sites_all[WARPS * 2][MAX_SITES16];
+    __shared__ uint16_t stamps_all[WARPS * 2][MAX_SITES16];   // flip step of every site (site ids < 512 for <= 16 rows)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, row = lane & 15;
     const int chain = (blockIdx.x * WARPS + warp) * 2 + half;
     const int terrain = chains_per_terrain > 0 ? (blockIdx.x * WARPS * 2) / chains_per_terrain : 0;
@@ -114,7 +115,9 @@ __global__ void __launch_bounds__(WARPS * 32) sls_h16_kernel(const uint32_t* __r
     L.C = terrain_rows[(size_t)terrain * 32 + row];
     L.S = exists ? st.S[row] : 0u;
     uint32_t bestS = exists ? st.bestS[row] : 0u;
-    int k = exists ? st.k : 0, best = exists ? st.best : 0, tabu_add = exists ? st.tabu_add : -1, tabu_rem = exists ? st.tabu_rem : -1;
+    int k = exists ? st.k : 0, best = exists ? st.best : 0;
+    const int tenure = tenure_of(chain_offset + (uint32_t)chain);
+    uint16_t* stamps = stamps_all[warp * 2 + half];
     int done = exists ? st.done : 1;
     const int done_at_start = done;
     uint32_t step = exists ? st.step : 0u;
@@ -122,6 +125,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_h16_kernel(const uint32_t* __r
     long long my_steps = 0;
 
     {   // site list (row-major) and cover planes from S, per half
+        for (int i = row; i < MAX_SITES16; i += 16) stamps[i] = stamp_reset(step);
         int c = __popc(L.S), off = c;
         for (int o = 1; o < 16; o <<= 1) { int t = __shfl_up_sync(FULL, off, o, 16); if (row >= o) off += t; }
         off -= c;
@@ -148,6 +152,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_h16_kernel(const uint32_t* __r
         const bool active = !done;
         const int limit = min(epoch_bound, best);
         const uint32_t hs = step_hash(base, step);
+        const int ten = effective_tenure(tenure, k);  // fixed for the whole step
         bool inc = active;  // this chain consumes a step
         // ---- classify the step (uniform per half)
         const bool drop = active && k >= limit;
@@ -162,9 +167,8 @@ __global__ void __launch_bounds__(WARPS * 32) sls_h16_kernel(const uint32_t* __r
         const bool swap_rem = active && !drop && !complete && k == limit - 1 && k > 0;
         const bool do_remove = (drop && k > 0) || swap_rem;
         const bool do_add = active && !drop && !complete;
-        // ---- removal: min-loss support, random ties (tabu: the support just added, except when dropping)
+        // ---- removal: min-loss support, random ties (supports younger than the tenure only as a last resort, except when dropping)
         if (__any_sync(FULL, do_remove)) {
-            const int exclude = drop ? -1 : tabu_rem;
             const int kk = do_remove ? k : 0, kmax = max(kk, __shfl_xor_sync(FULL, kk, 16));
             uint32_t best_key = 0xffffffffu;
             int best_i = 0;
@@ -174,14 +178,15 @@ __global__ void __launch_bounds__(WARPS * 32) sls_h16_kernel(const uint32_t* __r
                 const int v = valid ? sites[i] : 0;
                 const int loss = score16(L.O, v & 31, v >> 5, tab[v]);
                 const uint32_t tie = tie_remove(lane_hash(hs, (uint32_t)(i & 31)), (uint32_t)(i >> 5));
-                const uint32_t key = (valid && !(v == exclude && kk > 1)) ? (((uint32_t)loss << 16) | tie) : 0xffffffffu;
+                const uint32_t young = (!drop && is_tabu(step, stamps[v], ten)) ? TABU_BIT : 0u;
+                const uint32_t key = valid ? (young | ((uint32_t)loss << 16) | tie) : 0xffffffffu;
                 const uint32_t mn = half_min(key);
                 const uint32_t eq = (__ballot_sync(FULL, key == mn) >> hshift) & 0xffffu;
                 if (mn < best_key) { best_key = mn; best_i = b + __ffs(eq) - 1; }
             }
             const int u = do_remove ? sites[best_i] : 0;
             __syncwarp();
-            if (do_remove && row == 0) sites[best_i] = sites[k - 1];
+            if (do_remove && row == 0) { sites[best_i] = sites[k - 1]; stamps[u] = (uint16_t)step; }
             __syncwarp();
             planes_sub(L, do_remove ? row_mask(tab[u], u & 31, u >> 5, row) : 0u);
             derive(L);
@@ -189,7 +194,6 @@ __global__ void __launch_bounds__(WARPS * 32) sls_h16_kernel(const uint32_t* __r
                 if (row == (u >> 5)) L.S &= ~(1u << (u & 31));
                 scored += (unsigned)k;
                 k--;
-                tabu_add = u;
             }
         }
         // ---- addition at a random uncovered tile
@@ -215,15 +219,15 @@ __global__ void __launch_bounds__(WARPS * 32) sls_h16_kernel(const uint32_t* __r
             if (__any_sync(FULL, adding && !noise)) {
                 const int g0 = score16(L.U, cv0 & 31, cv0 >> 5, tab[cv0]);
                 const int g1 = score16(L.U, cv1 & 31, cv1 >> 5, tab[cv1]);
-                key0 = noise ? (0x10000u | t0) : (((uint32_t)(g0 + 1) << 16) | t0);
-                key1 = noise ? (0x10000u | t1) : (((uint32_t)(g1 + 1) << 16) | t1);
+                const uint32_t f0 = is_tabu(step, stamps[cv0], ten) ? 0u : TABU_BIT, f1 = is_tabu(step, stamps[cv1], ten) ? 0u : TABU_BIT;
+                key0 = noise ? (0x10000u | t0) : (f0 | ((uint32_t)(g0 + 1) << 16) | t0);
+                key1 = noise ? (0x10000u | t1) : (f1 | ((uint32_t)(g1 + 1) << 16) | t1);
             } else {
                 key0 = 0x10000u | t0;
                 key1 = 0x10000u | t1;
             }
-            const bool tabu0 = !noise && cv0 == tabu_add && nc > 1, tabu1 = !noise && cv1 == tabu_add && nc > 1;
-            key0 = (v0 && !tabu0) ? key0 : 0u;
-            key1 = (v1 && !tabu1) ? key1 : 0u;
+            key0 = v0 ? key0 : 0u;
+            key1 = v1 ? key1 : 0u;
             const uint32_t mx = half_max(max(key0, key1));
             // lowest diamond cell among the maxima (cells 0..15 before 16..24)
             const uint32_t e0 = (__ballot_sync(FULL, key0 == mx) >> hshift) & 0xffffu, e1 = (__ballot_sync(FULL, key1 == mx) >> hshift) & 0xffffu;
@@ -234,10 +238,9 @@ __global__ void __launch_bounds__(WARPS * 32) sls_h16_kernel(const uint32_t* __r
             derive(L);
             if (adding) {
                 if (row == (v >> 5)) L.S |= 1u << (v & 31);
-                if (row == 0) sites[k] = (uint16_t)v;
+                if (row == 0) { sites[k] = (uint16_t)v; stamps[v] = (uint16_t)step; }
                 if (!noise) scored += (unsigned)nc;
                 k++;
-                tabu_rem = v;
             }
             __syncwarp();
         }
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_h16_kernel(const uint32_t* __r
         st.S[row] = L.S;
         st.bestS[row] = bestS;
         if (row == 0) {
-            st.k = k; st.best = best; st.step = step; st.tabu_add = tabu_add; st.tabu_rem = tabu_rem; st.done = done;
+            st.k = k; st.best = best; st.step = step; st.done = done;
             unsigned long long tot = ((unsigned long long)st.scored_hi << 32 | st.scored_lo) + scored;
             st.scored_lo = (uint32_t)tot; st.scored_hi = (uint32_t)(tot >> 32);
             st.steps_done += (uint32_t)my_steps;

@@ -56,6 +56,19 @@ TSS_HD uint32_t noise_q7(int noise_pct) { return (uint32_t)((noise_pct * 128 + 5
 TSS_HD uint32_t tie_add(uint32_t hl) { return hl & 0xffffu; }
 TSS_HD uint32_t tie_remove(uint32_t hl, uint32_t chunk) { return (hl * (2u * chunk + 1u)) >> 16; }
 
+// Tabu with tenure (the single most effective ingredient on fragmented terrains): a site flipped
+// (added or removed) fewer than T steps ago is tabu — a recently added support is not removed, a recently removed site
+// not re-added — unless every candidate is tabu.  Implemented as a preference bit in the selection keys, so the fallback
+// needs no second pass.  The flip step of every site is kept as a 16-bit stamp per chain (reset at the start of an epoch
+// to "half a period ago"); the tenure is a portfolio parameter: chains use T = 3, 6, 12, 20 by global chain index.
+constexpr uint32_t TABU_BIT = 0x40000000u;
+TSS_HD int tenure_of(uint32_t global_chain) { return (global_chain & 3u) == 0 ? 3 : ((global_chain & 3u) == 1 ? 6 : ((global_chain & 3u) == 2 ? 12 : 20)); }
+// ... capped at a third of the current support count (with k = 14 supports a tenure of 20 would freeze the search) but
+// never below 2: the support added in the previous step is not removed, the site removed in this step not re-added.
+TSS_HD int effective_tenure(int tenure, int k) { int c = k / 3; c = c < 2 ? 2 : c; return tenure < c ? tenure : c; }
+TSS_HD uint16_t stamp_reset(uint32_t step) { return (uint16_t)(step - 0x8000u); }
+TSS_HD bool is_tabu(uint32_t step, uint16_t stamp, int tenure) { return (uint16_t)((uint16_t)step - stamp) < (uint16_t)tenure; }
+
 // Persistent per-chain state in HBM (one 320-byte record per chain).
 struct ChainState {
     uint32_t S[32];      // current supports, row r in S[r]
