@@ -5,10 +5,9 @@
 //   unsupported = ceiling & ~supported                           (:143-146)
 //
 // Two shapes:
-//   eval_small   grids up to 32x32: a layout is <= 32 u32 words in the COMPACT row format (row stride 1/2/4 bytes,
-//                so a 16x16 layout is 32 B); one word per lane, 32/SEG layouts per warp, vertical neighbours by
-//                funnel-shift + one warp shuffle, horizontal by masked shifts.  Pure register kernel, streaming
-//                layouts from HBM with a grid-stride loop (grid = multiple of the SM count).
+//   eval_thread  (eval_thread.cu) grids up to 32x32: a layout is <= 32 u32 words in the COMPACT row format (row stride
+//                1/2/4 bytes, so a 16x16 layout is 32 B); one layout per thread, all in registers, streaming layouts
+//                from HBM with a grid-stride loop (grid = multiple of the SM count).
 //   eval_tiled   any grid that fits shared memory (256x256 = 8 KB per plane): one CTA per layout, planes in
 //                shared memory.  Also evaluates general platform layouts (footprint stamping, overlap and
 //                out-of-bounds detection) and can export the four support layers (the terrain-layer variables
@@ -17,94 +16,8 @@
 
 namespace tss {
 
-// ------------------------------------------------------------------------------------------------ eval_small
-template <int ROWBITS>
-struct RowMasks;
-template <> struct RowMasks<8> { static constexpr uint32_t L = 0xFEFEFEFEu, R = 0x7F7F7F7Fu; };
-template <> struct RowMasks<16> { static constexpr uint32_t L = 0xFFFEFFFEu, R = 0x7FFF7FFFu; };
-template <> struct RowMasks<32> { static constexpr uint32_t L = 0xFFFFFFFFu, R = 0xFFFFFFFFu; };
-
-// One masked 4-neighbour dilation of the word held by this lane.  j = lane index within its SEG-lane segment.
-template <int ROWBITS, int SEG>
-__device__ __forceinline__ uint32_t dilate_word(uint32_t X, uint32_t C, int j) {
-    uint32_t l = (X << 1) & RowMasks<ROWBITS>::L;
-    uint32_t r = (X >> 1) & RowMasks<ROWBITS>::R;
-    uint32_t prev = 0, next = 0;
-    if (SEG > 1) {
-        prev = __shfl_up_sync(0xffffffffu, X, 1, SEG);
-        next = __shfl_down_sync(0xffffffffu, X, 1, SEG);
-        if (j == 0) prev = 0;
-        if (j == SEG - 1) next = 0;
-    }
-    uint32_t up, down;
-    if (ROWBITS == 32) { up = prev; down = next; }
-    else { up = __funnelshift_l(prev, X, ROWBITS); down = __funnelshift_r(X, next, ROWBITS); }
-    return (X | l | r | up | down) & C;
-}
-
-template <int ROWBITS, int SEG, bool PER_TERRAIN, int UNROLL>
-__global__ void __launch_bounds__(256) eval_small_kernel(const uint32_t* __restrict__ grid, const uint32_t* __restrict__ layouts,
-                                                        long long n, int wpl, int2* __restrict__ out) {
-    constexpr int LPW = 32 / SEG;  // layouts per warp
-    const int lane = threadIdx.x & 31, j = lane & (SEG - 1), sub = lane / SEG;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long ngroups = (n + LPW - 1) / LPW;
-    const bool word_ok = j < wpl;
-    uint32_t Cshared = 0;
-    if (!PER_TERRAIN && word_ok) Cshared = grid[j];
-
-    for (long long g0 = warp; g0 < ngroups; g0 += nwarps * UNROLL) {
-        uint32_t S[UNROLL], C[UNROLL];
-        long long idx[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {  // issue all loads first (memory-level parallelism)
-            long long g = g0 + (long long)u * nwarps;
-            idx[u] = g * LPW + sub;
-            bool ok = g < ngroups && idx[u] < n && word_ok;
-            S[u] = ok ? __ldg(layouts + idx[u] * wpl + j) : 0u;
-            C[u] = PER_TERRAIN ? (ok ? __ldg(grid + idx[u] * wpl + j) : 0u) : Cshared;
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            uint32_t X = S[u] & C[u];
-#pragma unroll
-            for (int round = 0; round < kTerrainSupportDistance - 1; round++) X = dilate_word<ROWBITS, SEG>(X, C[u], j);
-            uint32_t v = ((uint32_t)__popc(C[u] & ~X) << 16) | (uint32_t)__popc(S[u]);
-#pragma unroll
-            for (int o = SEG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (j == 0 && idx[u] < n && g0 + (long long)u * nwarps < ngroups) out[idx[u]] = make_int2((int)(v >> 16), (int)(v & 0xffffu));
-        }
-    }
-}
-
-template <int ROWBITS, int SEG>
-static int launch_small(tss_engine* e, const void* grid, const void* layouts, int64_t n, int wpl, bool per_terrain, int2* out) {
-    constexpr int LPW = 32 / SEG, UNROLL = 4, THREADS = 256;
-    long long ngroups = (n + LPW - 1) / LPW;
-    long long warps_needed = (ngroups + UNROLL - 1) / UNROLL;
-    long long blocks = (warps_needed * 32 + THREADS - 1) / THREADS;
-    long long max_blocks = (long long)e->prop.multiProcessorCount * 8;  // 8 CTAs x 256 threads = full occupancy, whole waves
-    if (blocks > max_blocks) blocks = max_blocks;
-    if (blocks < 1) blocks = 1;
-    if (per_terrain)
-        eval_small_kernel<ROWBITS, SEG, true, UNROLL><<<(unsigned)blocks, THREADS, 0, e->stream>>>((const uint32_t*)grid, (const uint32_t*)layouts, n, wpl, out);
-    else
-        eval_small_kernel<ROWBITS, SEG, false, UNROLL><<<(unsigned)blocks, THREADS, 0, e->stream>>>((const uint32_t*)grid, (const uint32_t*)layouts, n, wpl, out);
-    TSS_CHECK_LAUNCH(e);
-    e->stats.kernel_launches++;
-    return TSS_OK;
-}
-
-template <int ROWBITS>
-static int dispatch_seg(tss_engine* e, const void* grid, const void* layouts, int64_t n, int wpl, bool pt, int2* out) {
-    if (wpl <= 1) return launch_small<ROWBITS, 1>(e, grid, layouts, n, wpl, pt, out);
-    if (wpl <= 2) return launch_small<ROWBITS, 2>(e, grid, layouts, n, wpl, pt, out);
-    if (wpl <= 4) return launch_small<ROWBITS, 4>(e, grid, layouts, n, wpl, pt, out);
-    if (wpl <= 8) return launch_small<ROWBITS, 8>(e, grid, layouts, n, wpl, pt, out);
-    if (wpl <= 16) return launch_small<ROWBITS, 16>(e, grid, layouts, n, wpl, pt, out);
-    return launch_small<ROWBITS, 32>(e, grid, layouts, n, wpl, pt, out);
-}
+int launch_eval_small(tss_engine* e, const void* grid_dev, int w, int h, const void* layouts_dev, int64_t n, bool per_layout_terrain,
+                      int32_t* out_dev);  // eval_thread.cu: grids up to 32x32, one layout per thread
 
 // ------------------------------------------------------------------------------------------------ eval_tiled
 // Shared-memory planes of nw = h*wpr words.  One masked dilation round: dst = (src | shifts) & C.
@@ -261,14 +174,7 @@ int launch_eval_compact(tss_engine* e, const void* grid_dev, int w, int h, const
                         bool per_layout_terrain, int32_t* out_dev) {
     if (n <= 0) return TSS_OK;
     e->stats.layouts_evaluated += (uint64_t)n;
-    if (tss_is_small(w, h)) {
-        int wpl = (int)(tss_layout_bytes(w, h) / 4);
-        switch (tss_row_bits(w)) {
-            case 8: return dispatch_seg<8>(e, grid_dev, layouts_dev, n, wpl, per_layout_terrain, (int2*)out_dev);
-            case 16: return dispatch_seg<16>(e, grid_dev, layouts_dev, n, wpl, per_layout_terrain, (int2*)out_dev);
-            default: return dispatch_seg<32>(e, grid_dev, layouts_dev, n, wpl, per_layout_terrain, (int2*)out_dev);
-        }
-    }
+    if (tss_is_small(w, h)) return launch_eval_small(e, grid_dev, w, h, layouts_dev, n, per_layout_terrain, out_dev);
     int wpr = (w + 31) / 32, nw = h * wpr;
     size_t smem = (size_t)3 * nw * 4;
     if (smem > 200 * 1024) return e->fail(TSS_E_UNSUPPORTED, "grid %dx%d does not fit the shared-memory evaluator", w, h);
