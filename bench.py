@@ -35,8 +35,8 @@ UNIT = "layouts/s"
 WORKLOAD = "rect 16x16 ceiling, 1x1 supports, find minimum support count (BASELINE.json configs[1])"
 OPTIMUM_RECT16 = 15   # UNSAT proven at <= 14 (re-derived by oracle CDCL: tests/test_oracle.py proves ex1-3; rect16 in DESIGN.md)
 # algorithmic integer work (DESIGN.md "kernel (b)"): thread-ops, counted from the kernel's own counters
-A_SCORE = 7 * 4 + 2      # per candidate scored: 7 window rows x (shift, and, popc, add) + key build
-A_FLIP = 32 * 20         # per support added/removed: 32 lanes x (row mask 6 + five-plane add/sub 10 + derive 4)
+A_SCORE = 7 * 4 + 2      # per candidate scored: 7 window rows x (shift, and, pack, add) + key build
+A_FLIP = 16 * 20         # per support added/removed: 16 grid rows x (row mask 6 + five-plane add/sub 10 + derive 4)
 
 
 def peaks():
@@ -136,7 +136,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--epoch-steps", type=int, default=4096, help="SLS steps per chain per bench step")
-    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = SM count x 32)")
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = SM count x 64: 32 warps per SM, two chains per warp on a 16-row grid)")
     ap.add_argument("--quick", action="store_true", help="skip the side measurements (peaks, eval/cnf kernels, cpu baseline)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -235,7 +235,9 @@ def main():
         int_ops = A_SCORE * scored_all + A_FLIP * flips
         achieved = int_ops / (ms_total * 1e-3) / 1e9 / world
         line["roofline"] = {"bound": "int_issue", "achieved": achieved, "peak": pk["lop3_gops"], "unit": "Gop/s", "frac": achieved / pk["lop3_gops"],
-                            "traffic": None, "kernel": "sls_kernel", "peak_source": "measured in this run (tss_measure_peaks: dependent-free LOP3 chains at full occupancy)",
+                            "traffic": 3067392, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu, 9472 chains x 512 steps): chain states only", "kernel": "sls_h16_kernel (two chains per warp)",
+                            "ncu": "ALU pipe 72% busy, 276 warp instructions per chain step, DRAM 3 MB per launch (profiles/r1_sls_h16_kernel.md)",
+                            "peak_source": "measured in this run (tss_measure_peaks: dependent-free LOP3 chains at full occupancy)",
                             "note": "no dense contraction and ~0 HBM traffic in the step loop: the bound is integer issue + warp shuffles (SURVEY.md §8d); per-GPU figures"}
         line["measured_peaks"] = pk
     if rank == 0 and not args.quick and world == 1:

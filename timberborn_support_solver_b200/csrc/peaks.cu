@@ -114,7 +114,7 @@ int run_peaks(tss_engine* e, double* out, int n_out) {
     out[3] = thread_iters * 4 * 16 / (ms * 1e-3) / 1e9;  // GB/s
     // SM clock under load: cycles of a fixed spin / its event time
     long long* cyc = (long long*)((char*)sink + 16);
-    const int spin = 1 << 20;
+    const int spin = 1 << 17;
     if ((rc = timed(e, [&] { peak_clock_kernel<<<blocks, threads, 0, st>>>(cyc, spin); }, &ms))) return rc;
     long long host_cyc[2];
     TSS_CUDA(e, cudaMemcpy(host_cyc, cyc, sizeof host_cyc, cudaMemcpyDeviceToHost));
