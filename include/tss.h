@@ -198,6 +198,12 @@ int tss_search_n_chains(const tss_search* s);
  * state after the last epoch.  S / best_S: support rows u32[n_chains][32]; any pointer may be NULL. */
 int tss_search_read_chains(tss_search* s, uint32_t* S, uint32_t* best_S, int32_t* k, int32_t* best, uint32_t* step, uint64_t* scored);
 
+/* GUI objective (crates/gui/src/app.rs:53-62,235-245): minimise PlatformLayout::total_weight (platform_layout.rs:174-183)
+ * instead of the platform count.  weights = records (def_w, def_h, weight) keyed by canonical def dims, exactly the
+ * PlatformLimits.weights map; call before the first tss_search_run.  Afterwards tss_search_best_count /
+ * tss_search_set_bound speak total weight.  Needs a platform set beyond {1x1} on a grid up to 32x32. */
+int tss_search_set_weights(tss_search* s, const int32_t* weights, int32_t n_weights);
+
 /* Values of the SLS specification's hash / tie-break functions (csrc/sls_spec.hpp) at fixed probe points, so the
  * parity tests can assert that the CPU model (which re-declares them) follows the same published rule.  out[9]. */
 void tss_sls_spec_probe(uint32_t* out);
@@ -211,6 +217,11 @@ void tss_sls_spec_probe(uint32_t* out);
 int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,
                           int32_t card_limit, uint64_t seed, int32_t budget_ms, int64_t max_steps, tss_platform* out,
                           int32_t cap, int32_t* n_out);
+/* The GUI's weight-minimising solve (crates/gui/src/solver_backend.rs:69-97 with PlatformLimits.weight_limit): a layout of
+ * total weight <= weight_limit (< 0: unbounded), best found within the budget; *out_weight = its total weight. */
+int tss_solve_min_weight(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,
+                         const int32_t* weights, int32_t n_weights, int64_t weight_limit, uint64_t seed, int32_t budget_ms,
+                         int64_t max_steps, tss_platform* out, int32_t cap, int32_t* n_out, int64_t* out_weight);
 /* Terrain batch: n independent terrains [n][w*h] (grids up to 32x32), 1x1 supports; `steps` SLS steps
  * per chain, `chains_per_terrain` independent chains per terrain sharing their bound every 1024 steps (0 = one CTA
  * = 4 chains, 8 for grids of <= 16 rows; otherwise rounded up to a multiple of that).  out_counts[n] = best count per

@@ -324,6 +324,50 @@ def test_multi_platform_random_sets_match_exact_optimum(eng):
         assert O.validate(grid, [tup(p) for p in layout.platforms().values()]).is_valid
 
 
+GUI_WEIGHTS = {(1, 1): 5, (1, 2): 1, (1, 3): 1, (1, 4): 1, (1, 5): 1, (1, 6): 1, (3, 3): 2, (5, 5): 4}   # crates/gui/src/app.rs:53-62
+
+
+def oracle_min_weight(grid, defs, weights):
+    """The GUI loop (crates/gui/src/app.rs:235-245) on the oracle: solve, weight = total_weight(layout), weight_limit =
+    weight - 1, until the CDCL stand-in says UNSAT.  -> proven minimum total weight."""
+    enc = O.Encoding(defs, grid)
+    limit, best = None, None
+    while True:
+        r, a, _ = enc.with_limits(weights=weights, weight_limit=limit).solve()
+        if r != 10:
+            assert r == 20
+            return best
+        lay = O.trivial_optimization(grid, enc.layout_from_assignment(a))        # app.rs:157
+        best = O.total_weight(lay, weights)
+        if best <= 0:
+            return best
+        limit = best - 1
+
+
+def test_gui_weight_objective_matches_exact_minimum(eng, fixtures):
+    """§8f rank 2: the GUI minimises PlatformLayout::total_weight (platform_layout.rs:174-183) under a PB bound.  The GPU
+    search with the same weights reaches the minimum the oracle loop proves, with valid layouts whose total_weight is
+    what the engine reports."""
+    rng = np.random.default_rng(12)
+    cases = [("ex1", fixtures["ex1"], O.PLATFORMS_DEFAULT, GUI_WEIGHTS), ("ex3", fixtures["ex3"], O.PLATFORMS_DEFAULT, GUI_WEIGHTS)]
+    for i in range(4):
+        g = (rng.random((int(rng.integers(4, 9)), int(rng.integers(4, 9)))) < 0.8).astype(np.uint8)
+        defs = [(1, 1), (1, 3), (3, 3)] if i % 2 else [(1, 1), (1, 2), (2, 2)]
+        w = {d: int(rng.integers(1, 6)) for d in defs}
+        cases.append((f"rand{i}", g, defs, w))
+    for name, grid, defs, weights in cases:
+        want = oracle_min_weight(grid, defs, weights)
+        wdefs = {T.PlatformDef(*d): v for d, v in weights.items()}
+        res, layout, weight = eng.solve_min_weight(T.WorldGrid(grid), [T.PlatformDef(*d) for d in defs], wdefs, weight_limit=want, seed=3, max_steps=60000)
+        assert res == T.SAT and weight == want, (name, weight, want)
+        plats = [tup(p) for p in layout.platforms().values()]
+        assert O.validate(grid, plats).is_valid
+        assert O.total_weight(plats, weights) == weight == layout.total_weight(wdefs)
+        if want > 0:
+            res, layout, weight = eng.solve_min_weight(T.WorldGrid(grid), [T.PlatformDef(*d) for d in defs], wdefs, weight_limit=want - 1, seed=3, max_steps=3000)
+            assert res == T.INTERRUPTED, name
+
+
 def test_multi_platform_solver_loop_like_the_repl(eng, fixtures):
     """`load test/ex1.toml; solve` (configs[0]): default-8 set, unbounded first solve, tighten until the prover says UNSAT."""
     import ctypes as C
@@ -403,6 +447,40 @@ def test_solve_batch_terrains(eng):
     for t in range(12):
         r = O.solver_loop(small[t], O.PLATFORMS_1X1)
         assert r["proved_optimal"] and c2[t] == len(r["best"]), t
+
+
+def test_c5_full_size_batch_properties(eng):
+    """BASELINE.json configs[4] at full size: 100 000 synthetic 32x32 terrains through tss_solve_batch.  Too many for
+    the oracle, so: every reported layout is re-evaluated by kernel (a) in per-terrain mode (complete, count matches),
+    counts respect the trivial lower bound ceil(tiles/25), the run is deterministic, and a sample is validated by the
+    oracle."""
+    import torch
+    n = 100_000
+    lib = T.load()
+    grids = np.zeros((n, 32, 32), np.uint8)
+    import ctypes as C
+    for t in range(n):
+        lib.tss_world_synthetic(32, 32, 1, t, int(0.7 * (1 << 24)), grids[t].ctypes.data_as(C.POINTER(C.c_uint8)))
+    counts, layouts = eng.solve_batch(grids, seed=1, steps=1500, want_layouts=True)
+    assert counts.shape == (n,) and (counts > 0).all()
+    tiles = grids.reshape(n, -1).sum(1).astype(np.int64)
+    assert (counts >= (tiles + 24) // 25).all() and (counts <= tiles).all()
+    # per-terrain re-evaluation on the device (kernel a, per_layout_terrain): terrain rows and layout rows are both u32[32]
+    terr_rows = pack_rows(grids).reshape(n, 32)
+    g_dev = torch.from_numpy(terr_rows.view(np.int32)).cuda()
+    l_dev = torch.from_numpy(layouts.view(np.int32)).cuda()
+    out = torch.empty((n, 2), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    eng.eval_compact_dev(g_dev.data_ptr(), 32, 32, l_dev.data_ptr(), n, out.data_ptr(), per_layout_terrain=True)
+    torch.cuda.synchronize()   # device-wide: also waits for the engine's own stream
+    res = out.cpu().numpy()
+    assert (res[:, 0] == 0).all() and np.array_equal(res[:, 1], counts)
+    sites = ((layouts[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8)
+    for t in (0, 31337, 99_999):
+        unc, cnt, _ = O.validate_sites_batch(grids[t], sites[t][None])
+        assert unc[0] == 0 and cnt[0] == counts[t]
+    again = eng.solve_batch(grids[:4096], seed=1, steps=1500)
+    assert np.array_equal(again, counts[:4096])
 
 
 def test_solver_loop_gpu_then_exact_proof(eng, fixtures):

@@ -514,6 +514,19 @@ class Engine:
             return SAT, PlatformLayout(Platform._from_c(out[i]) for i in range(n.value))
         return INTERRUPTED, None
 
+    def solve_min_weight(self, grid: WorldGrid, defs, weights: dict, weight_limit: Optional[int] = None, seed=0, budget_ms=0, max_steps=0):
+        """GUI objective (crates/gui/src/app.rs:235-245): -> (SAT | INTERRUPTED, PlatformLayout | None, total weight | None)."""
+        defs = list(defs)
+        wts = np.array([[d.width, d.height, v] for d, v in weights.items()], np.int32).reshape(-1, 3)
+        out = (_Platform * (grid.data.size + 1))()
+        n, wt = C.c_int32(), C.c_int64()
+        rc = self._check(self.lib.tss_solve_min_weight(self._h, _ptr(grid.data, C.c_uint8), grid.width, grid.height, _defs_array(defs), len(defs),
+                                                       _ptr(wts, C.c_int32), len(wts), -1 if weight_limit is None else weight_limit, seed, budget_ms,
+                                                       max_steps, out, len(out), C.byref(n), C.byref(wt)))
+        if rc == _lib.TSS_SAT:
+            return SAT, PlatformLayout(Platform._from_c(out[i]) for i in range(n.value)), wt.value
+        return INTERRUPTED, None, None
+
     def solve_batch(self, grids, seed=0, steps=2048, want_layouts=False, chains_per_terrain=0):
         """grids: uint8[n, h, w] -> counts int32[n] (and packed support rows uint32[n, h] if asked)"""
         g = _u8(grids)

@@ -34,10 +34,10 @@ int lns_chains(const LnsSearch* s);
 size_t slsm_state_bytes();
 int slsm_max_keys();
 int slsm_init(tss_engine* e, void* states, int n);
-int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* keys_dev, int n_keys, void* states, int n_chains,
+int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* keys_dev, const int* costs_dev, int n_keys, void* states, int n_chains,
              uint32_t chain_offset, uint64_t seed, long long steps, int* bounds_dev, int target, int noise_pct, unsigned long long* totals_dev,
              int2* best_dev);
-int slsm_read_best(tss_engine* e, const void* states, int chain, std::vector<uint16_t>& codes, int count);
+int slsm_read_best(tss_engine* e, const void* states, int chain, std::vector<uint16_t>& codes);
 
 // u8 grids [n][w*h] -> rows32 [n][32] (one u32 per row, rows >= h are zero); w, h <= 32
 __global__ void pack_rows32_kernel(const uint8_t* __restrict__ bytes, int w, int h, long long n, uint32_t* __restrict__ out) {
@@ -101,7 +101,10 @@ struct tss_search {
     bool multi = false;
     std::vector<int2> key_dims;                // effective (w, h) per dims key: defs order, unflipped then flipped
     std::vector<tss_platform> key_proto;       // def dims + rotated flag per key
+    std::vector<int> key_costs;                // objective cost per key: 1 = platform count; GUI weights via tss_search_set_weights
+    bool weighted = false;
     int2* keys_dev = nullptr;
+    int* costs_dev = nullptr;
     void* mstates = nullptr;
 };
 
@@ -380,6 +383,7 @@ static void search_free(tss_search* s) {
     if (!s) return;
     if (s->lns) lns_destroy(s->lns);
     cudaFree(s->keys_dev);
+    cudaFree(s->costs_dev);
     cudaFree(s->mstates);
     cudaFree(s->rows_dev); cudaFree(s->tabs_dev); cudaFree(s->states); cudaFree(s->totals_dev); cudaFree(s->best_dev); cudaFree(s->bounds_dev);
     if (s->best_host) cudaFreeHost(s->best_host);
@@ -466,6 +470,8 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
         if (!(params && params->n_chains > 0)) s->n_chains = e->prop.multiProcessorCount * 16;
         cudaError_t err = cudaMalloc(&s->rows_dev, sizeof rows);
         if (err == cudaSuccess) err = cudaMalloc(&s->keys_dev, sizeof(int2) * s->key_dims.size());
+        if (err == cudaSuccess) err = cudaMalloc(&s->costs_dev, sizeof(int) * s->key_dims.size());
+        s->key_costs.assign(s->key_dims.size(), 1);
         if (err == cudaSuccess) err = cudaMalloc(&s->mstates, slsm_state_bytes() * (size_t)s->n_chains);
         if (err == cudaSuccess) err = cudaMalloc(&s->totals_dev, sizeof(unsigned long long) * 2);
         if (err == cudaSuccess) err = cudaMalloc(&s->best_dev, sizeof(int2));
@@ -475,6 +481,7 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
         const int nb = sls::NO_BOUND;
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->rows_dev, rows, sizeof rows, cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->keys_dev, s->key_dims.data(), sizeof(int2) * s->key_dims.size(), cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(s->costs_dev, s->key_costs.data(), sizeof(int) * s->key_costs.size(), cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->bounds_dev, &nb, sizeof nb, cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = cudaMemsetAsync(s->totals_dev, 0, sizeof(unsigned long long) * 2, e->stream);
         int rc = err == cudaSuccess ? slsm_init(e, s->mstates, s->n_chains) : e->fail(TSS_E_CUDA, "tss_search_create: %s", cudaGetErrorString(err));
@@ -524,7 +531,7 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
         return TSS_OK;
     }
     if (s->multi) {
-        int rc = slsm_run(e, s->rows_dev, s->w, s->h, s->keys_dev, (int)s->key_dims.size(), s->mstates, s->n_chains, s->chain_offset, s->seed, steps,
+        int rc = slsm_run(e, s->rows_dev, s->w, s->h, s->keys_dev, s->costs_dev, (int)s->key_dims.size(), s->mstates, s->n_chains, s->chain_offset, s->seed, steps,
                           s->bounds_dev, target_count < 0 ? -1 : target_count, s->noise, s->totals_dev, s->best_dev);
         if (rc) return rc;
         TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
@@ -635,8 +642,12 @@ int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_
         best = s->best_host[0];
         if (best.x >= sls::NO_BOUND || best.y < 0) { *n_out = 0; return e->fail(TSS_E_INVALID, "tss_search_best_layout: no complete layout found yet"); }
         std::vector<uint16_t> codes;
-        rc = slsm_read_best(e, s->mstates, best.y, codes, best.x);
+        rc = slsm_read_best(e, s->mstates, best.y, codes);
         if (rc) return rc;
+        int cost = 0;
+        for (uint16_t code : codes) cost += s->key_costs[code >> 10];
+        if (cost != best.x) return e->fail(TSS_E_CUDA, "internal error: best layout costs %d, chain reported %d", cost, best.x);
+        best.x = (int)codes.size();
         for (uint16_t code : codes) {
             tss_platform p = s->key_proto[code >> 10];
             p.x = code & 31;
@@ -664,6 +675,70 @@ int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_
     if ((int)plats.size() > cap || !out) return e->fail(TSS_E_CAPACITY, "tss_search_best_layout: need room for %zu platforms", plats.size());
     std::memcpy(out, plats.data(), sizeof(tss_platform) * plats.size());
     return TSS_OK;
+}
+
+int tss_search_set_weights(tss_search* s, const int32_t* weights, int32_t n_weights) {
+    if (!s) return TSS_E_INVALID;
+    tss_engine* e = s->e;
+    if (n_weights < 0 || (n_weights > 0 && !weights)) return e->fail(TSS_E_INVALID, "tss_search_set_weights: bad arguments");
+    if (!s->multi) return e->fail(TSS_E_UNSUPPORTED, "tss_search_set_weights: the weight objective needs a platform set beyond {1x1} on a grid up to 32x32");
+    int rc = search_sync(s);
+    if (rc) return rc;
+    // cost of a platform = sum of the weights of every def contained in its def (platform_layout.rs:174-183)
+    for (size_t k = 0; k < s->key_dims.size(); k++) {
+        Dims def{s->key_proto[k].def_w, s->key_proto[k].def_h};
+        long cost = 0;
+        for (int i = 0; i < n_weights; i++)
+            if (dims_le(Dims{weights[3 * i], weights[3 * i + 1]}, def)) cost += weights[3 * i + 2];
+        if (cost <= 0 || cost > 4096) return e->fail(TSS_E_UNSUPPORTED, "tss_search_set_weights: platform costs must be in 1..4096 (got %ld for %dx%d)", cost, def.w, def.h);
+        s->key_costs[k] = (int)cost;
+    }
+    s->weighted = true;
+    TSS_CUDA(e, cudaMemcpy(s->costs_dev, s->key_costs.data(), sizeof(int) * s->key_costs.size(), cudaMemcpyHostToDevice));
+    return TSS_OK;
+}
+
+int tss_solve_min_weight(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,
+                         const int32_t* weights, int32_t n_weights, int64_t weight_limit, uint64_t seed, int32_t budget_ms,
+                         int64_t max_steps, tss_platform* out, int32_t cap, int32_t* n_out, int64_t* out_weight) {
+    if (!e) return TSS_E_INVALID;
+    if (n_out) *n_out = 0;
+    e->stats.interrupted = 0;
+    e->stats.best_count = -1;
+    tss_search_params p{seed, 0, 0, -1, 0};
+    tss_search* s = nullptr;
+    int rc = tss_search_create(e, grid, w, h, defs, n_defs, &p, &s);
+    if (rc) return rc;
+    rc = tss_search_set_weights(s, weights, n_weights);
+    if (rc == TSS_OK && weight_limit >= 0) rc = tss_search_set_bound(s, (int32_t)(weight_limit + 1 < sls::NO_BOUND ? weight_limit + 1 : sls::NO_BOUND));
+    const double t0 = now_ms();
+    const bool first_model_only = budget_ms <= 0 && max_steps <= 0;
+    if (first_model_only) max_steps = 1 << 16;
+    int64_t done_steps = 0, epoch = 64;
+    int best = -1;
+    while (rc == TSS_OK) {
+        if (e->interrupted()) { e->stats.interrupted = 1; break; }
+        int64_t steps = epoch;
+        if (max_steps > 0 && done_steps + steps > max_steps) steps = max_steps - done_steps;
+        if (steps <= 0) break;
+        rc = tss_search_run(s, steps, 0);
+        if (rc == TSS_OK) rc = tss_search_best_count(s, &best);
+        if (rc) break;
+        done_steps += steps;
+        if (first_model_only && best >= 0) break;
+        if (budget_ms > 0 && now_ms() - t0 >= budget_ms) break;
+        if (epoch < 4096) epoch *= 2;
+    }
+    int result = TSS_UNKNOWN;
+    if (rc == TSS_OK && best >= 0) {
+        int n = 0;
+        rc = tss_search_best_layout(s, out, cap, &n);
+        if (n_out) *n_out = n;
+        if (out_weight) *out_weight = best;
+        if (rc == TSS_OK) result = TSS_SAT;
+    }
+    tss_search_destroy(s);
+    return rc != TSS_OK ? rc : result;
 }
 
 int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,

@@ -14,6 +14,13 @@
 // length <= 3 from the footprint never leave it) and counts popcount(U & reach) resp. popcount(O & reach).
 // A step: drop / swap as in sls_spec.hpp; addition candidates are 2 x 32 random in-bounds placements whose footprint
 // comes within 3 tiles of a random uncovered tile and does not overlap the current platforms.
+//
+// Objective: every dims key has an integer cost; the search minimises the total cost of the layout.  With all costs 1
+// this is the REPL's platform count.  With the GUI's weights (crates/gui/src/app.rs:53-62) the cost of a platform is
+// what PlatformLayout::total_weight charges for it — the sum of the weights of every def contained in its def
+// (platform_layout.rs:174-183) — and the bound is the GUI's `weight_limit = weight - 1` (app.rs:235-245).  The step rule
+// generalises "k == L-1 -> swap" to "no candidate is affordable (W + min cost >= L) -> remove first", candidates must be
+// affordable (W + cost < L) and are ranked by gain per cost.
 #include "engine.hpp"
 #include "sls_spec.hpp"
 
@@ -29,10 +36,11 @@ constexpr int WIN = 12;  // window rows / columns: footprint (<= 6) + 3 on each 
 struct MultiState {  // persistent per-chain state in HBM
     uint16_t items[MAX_ITEMS];       // key << 10 | y << 5 | x
     uint16_t best_items[MAX_ITEMS];
-    int32_t k, best;
+    int32_t k, best;      // platforms now; best OBJECTIVE value found (platform count, or total weight in weight mode)
     uint32_t step;
     int32_t tabu_add, tabu_rem, done;
-    uint32_t pad[2];
+    int32_t best_k;       // number of platforms in best_items
+    uint32_t pad[1];
 };
 
 struct Lane {
@@ -164,16 +172,20 @@ __device__ __forceinline__ int pick_rotated(uint32_t bits, uint32_t o) {
 }
 
 __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* __restrict__ terrain_rows, int W, int H,
-                                                              const int2* __restrict__ keys_g, int n_keys, MultiState* __restrict__ states,
+                                                              const int2* __restrict__ keys_g, const int* __restrict__ costs_g, int n_keys,
+                                                              MultiState* __restrict__ states,
                                                               int n_chains, uint32_t chain_offset, uint64_t seed, long long steps,
                                                               const int* __restrict__ bounds, int target, int noise_pct,
                                                               const volatile int* interrupt, unsigned long long* __restrict__ totals) {
     __shared__ uint16_t items_all[WARPS][MAX_ITEMS];
     __shared__ int2 keys[MAX_KEYS];
+    __shared__ int costs[MAX_KEYS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chain = blockIdx.x * WARPS + warp;
-    if (threadIdx.x < n_keys) keys[threadIdx.x] = keys_g[threadIdx.x];
+    if (threadIdx.x < n_keys) { keys[threadIdx.x] = keys_g[threadIdx.x]; costs[threadIdx.x] = costs_g[threadIdx.x]; }
     __syncthreads();
+    int cmin = costs[0];
+    for (int i = 1; i < n_keys; i++) cmin = min(cmin, costs[i]);
     if (chain >= n_chains) return;
     MultiState& st = states[chain];
     if (st.done) return;
@@ -191,6 +203,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
     unsigned long long scored = 0;
     for (int i = lane; i < k; i += 32) c.items[i] = st.items[i];
     __syncwarp();
+    int Wt = 0;  // total cost of the current layout
     for (int i = 0; i < k; i++) {
         int x, y, w, h;
         unpack(c, c.items[i], x, y, w, h);
@@ -198,9 +211,9 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
         placement_rows(L.C, lane, x, y, w, h, foot, reach);
         planes_add(L, reach);
         L.Occ |= foot;
+        Wt += costs[c.items[i] >> 10];
     }
     derive(L);
-    bool improved = false;
 
     long long it = 0;
     for (; it < steps; it++, step++) {
@@ -208,22 +221,24 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
         const int limit = min(epoch_bound, best);
         const uint32_t hs = sls::step_hash(base, step);
         const uint32_t hl = sls::lane_hash(hs, (uint32_t)lane);
-        if (k >= limit) {
+        if (Wt >= limit) {  // too expensive for an improvement: drop a platform
             if (k == 0) { done = 1; break; }
             scored += (unsigned)k;
             tabu_add = remove_min_loss(L, c, k, hl, -1);
+            Wt -= costs[tabu_add >> 10];
             continue;
         }
-        if (!__any_sync(FULL, L.U != 0)) {  // complete layout with k < limit platforms
-            best = k;
-            improved = true;
+        if (!__any_sync(FULL, L.U != 0)) {  // complete layout with total cost < limit
+            best = Wt;
             for (int i = lane; i < k; i += 32) st.best_items[i] = c.items[i];
-            if (k <= target || k == 0) { done = 1; it++; step++; break; }
+            if (lane == 0) st.best_k = k;
+            if (Wt <= target || k == 0) { done = 1; it++; step++; break; }
             continue;
         }
-        if (k == limit - 1 && k > 0) {
+        if (Wt + cmin >= limit && k > 0) {  // nothing is affordable: swap = remove + add
             scored += (unsigned)k;
             tabu_add = remove_min_loss(L, c, k, hl, tabu_rem);
+            Wt -= costs[tabu_add >> 10];
         }
         // a random uncovered tile, then two passes of 32 random placements near it
         const uint32_t rowmask = __ballot_sync(FULL, L.U != 0);
@@ -245,8 +260,10 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
             const int code = inb ? ((key << 10) | (y << 5) | x) : 0;
             bool ov;
             int g = score_placement(L.C, L.U, L.Occ, inb ? x : 0, inb ? y : 0, d.x, d.y, ov);
-            const bool ok = inb && !ov && g > 0 && code != tabu_add;
-            uint32_t kk = ok ? ((noise ? 0x10000u : ((uint32_t)g << 16)) | (r >> 16 ^ (r & 0xffffu))) : 0u;
+            const int cost = costs[key];
+            const bool ok = inb && !ov && g > 0 && code != tabu_add && Wt + cost < limit;
+            const uint32_t rank = cost == 1 ? (uint32_t)g : ((uint32_t)g * 64u) / (uint32_t)cost;  // gain per cost (< 2^14)
+            uint32_t kk = ok ? ((noise ? 0x10000u : (rank << 16)) | (r >> 16 ^ (r & 0xffffu))) : 0u;
             kk = ok ? (kk | 1u) : 0u;
             uint32_t mx = __reduce_max_sync(FULL, kk);
             scored += (unsigned)__popc(__ballot_sync(FULL, inb));
@@ -266,6 +283,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
         if (lane == 0) c.items[k] = (uint16_t)best_code;
         __syncwarp();
         k++;
+        Wt += costs[best_code >> 10];
         tabu_rem = best_code;
     }
 
@@ -275,13 +293,12 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
         atomicAdd(&totals[0], scored);
         atomicAdd(&totals[1], (unsigned long long)it);
     }
-    (void)improved;
 }
 
 __global__ void multi_init_kernel(MultiState* states, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    states[i].k = 0; states[i].best = sls::NO_BOUND; states[i].step = 0; states[i].tabu_add = -1; states[i].tabu_rem = -1; states[i].done = 0;
+    states[i].k = 0; states[i].best_k = 0; states[i].best = sls::NO_BOUND; states[i].step = 0; states[i].tabu_add = -1; states[i].tabu_rem = -1; states[i].done = 0;
 }
 
 // smallest best over all chains (ties: lowest chain); also folds it into bounds[0]
@@ -316,11 +333,11 @@ int slsm_init(tss_engine* e, void* states, int n) {
     e->stats.kernel_launches++;
     return TSS_OK;
 }
-int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* keys_dev, int n_keys, void* states, int n_chains,
+int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* keys_dev, const int* costs_dev, int n_keys, void* states, int n_chains,
              uint32_t chain_offset, uint64_t seed, long long steps, int* bounds_dev, int target, int noise_pct, unsigned long long* totals_dev,
              int2* best_dev) {
     int blocks = (n_chains + slsm::WARPS - 1) / slsm::WARPS;
-    slsm::sls_multi_kernel<<<blocks, slsm::WARPS * 32, 0, e->stream>>>(rows_dev, W, H, keys_dev, n_keys, (slsm::MultiState*)states, n_chains,
+    slsm::sls_multi_kernel<<<blocks, slsm::WARPS * 32, 0, e->stream>>>(rows_dev, W, H, keys_dev, costs_dev, n_keys, (slsm::MultiState*)states, n_chains,
                                                                      chain_offset, seed, steps, bounds_dev, target, noise_pct, e->interrupt_dev,
                                                                      totals_dev);
     TSS_CHECK_LAUNCH(e);
@@ -330,8 +347,11 @@ int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* 
     return TSS_OK;
 }
 // best items of one chain -> host codes (key << 10 | y << 5 | x)
-int slsm_read_best(tss_engine* e, const void* states, int chain, std::vector<uint16_t>& codes, int count) {
+int slsm_read_best(tss_engine* e, const void* states, int chain, std::vector<uint16_t>& codes) {
     const slsm::MultiState* st = (const slsm::MultiState*)states + chain;
+    int count = 0;
+    TSS_CUDA(e, cudaMemcpy(&count, &st->best_k, sizeof(int), cudaMemcpyDeviceToHost));
+    if (count < 0 || count > slsm::MAX_ITEMS) return e->fail(TSS_E_CUDA, "corrupt chain state (best_k = %d)", count);
     codes.resize((size_t)count);
     if (count > 0) TSS_CUDA(e, cudaMemcpy(codes.data(), st->best_items, sizeof(uint16_t) * (size_t)count, cudaMemcpyDeviceToHost));
     return TSS_OK;
