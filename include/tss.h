@@ -89,6 +89,16 @@ int tss_get_stats(const tss_engine* e, tss_stats* out);
 /* name[<=cap], SM count, max SM clock in kHz */
 int tss_device_info(const tss_engine* e, char* name, int cap, int* sm_count, int* clock_khz);
 
+/* ---------------------------------------------------------------------------- multi-GPU portfolio */
+/* One process per GPU.  Rank 0 makes an id (tss_comm_unique_id), the host passes its 128 bytes to the other ranks, every
+ * rank calls tss_comm_init.  From then on a search created with tss_search_create on this engine all-reduce-mins its
+ * device-resident bound over NCCL/NVLink after every tss_search_run — 4 bytes, in-stream, no host round trip — so all
+ * ranks must call tss_search_run the same number of times.  The one-shot tss_solve_* calls never communicate.
+ * NCCL is bound at run time (dlopen libnccl.so.2); TSS_E_UNSUPPORTED if it is not installed. */
+int tss_comm_unique_id(tss_engine* e, uint8_t* out_id128);
+int tss_comm_init(tss_engine* e, const uint8_t* id128, int32_t rank, int32_t world);
+int tss_comm_world(const tss_engine* e);
+
 /* --------------------------------------------------------------------------------- world (src/world.rs:49-79) */
 /* Parses `[world] grid = ["XX ", ...]`.  Ragged rows are left-aligned and padded false as world.rs:82-86 documents
  * (the reference's copy_from_slice at :73 would panic instead; *ragged reports that case).  err gets a message. */
@@ -191,6 +201,9 @@ int tss_search_best_count(tss_search* s, int32_t* count);
 /* Shares an externally known bound (e.g. the all-reduce-min over GPUs): chains only look for layouts with fewer
  * than `count` platforms from now on. */
 int tss_search_set_bound(tss_search* s, int32_t count);
+/* The bound the next epoch searches below: min(best counts of this search, bounds set from outside, and — with a
+ * communicator on the engine — the best counts of every rank's search); -1 if none yet.  (synchronises the stream) */
+int tss_search_global_best(tss_search* s, int32_t* count);
 /* Best layout (re-validated by kernel (a) before it is returned). */
 int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_t* n_out);
 int tss_search_n_chains(const tss_search* s);

@@ -1,0 +1,87 @@
+/* The drop-in boundary used from plain C (no Python, no torch): what a Rust/C host does through include/tss.h.
+ * Built and run by tests/test_gpu.py::test_c_abi_from_plain_c with `gcc c_abi_smoke.c -ltss`.
+ * Exit code 0 = every check passed; a failed check prints its line and exits 1. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "tss.h"
+
+#define CHECK(cond)                                                              \
+    do {                                                                         \
+        if (!(cond)) {                                                           \
+            fprintf(stderr, "c_abi_smoke: check failed at line %d: %s (%s)\n", __LINE__, #cond, e ? tss_last_error(e) : ""); \
+            return 1;                                                            \
+        }                                                                        \
+    } while (0)
+
+int main(void) {
+    tss_engine* e = NULL;
+    CHECK(tss_version() == TSS_VERSION);
+    CHECK(tss_engine_create(0, &e) == TSS_OK);
+
+    /* test/ex1.toml-shaped project through the loader (src/world.rs:49-79) */
+    const char* toml = "[world]\ngrid = [\n \"XXXXX\",\n \"XXXXX\",\n \"X  XX\",\n \"X   X\",\n \"X    \",\n \"XXX  \",\n]\n";
+    uint8_t grid[64];
+    int32_t w = 0, h = 0, ragged = 0;
+    char err[128];
+    CHECK(tss_world_parse_toml(toml, grid, sizeof grid, &w, &h, &ragged, err, sizeof err) == TSS_OK);
+    CHECK(w == 5 && h == 6 && !ragged);
+    CHECK(tss_world_parse_toml("[world]\ngrid = [\"X.X\"]\n", grid, sizeof grid, &w, &h, &ragged, err, sizeof err) == TSS_E_PARSE);
+    CHECK(tss_world_parse_toml(toml, grid, sizeof grid, &w, &h, &ragged, err, sizeof err) == TSS_OK);
+
+    /* solve with the REPL's platform set: optimum is one 5x5 */
+    const tss_dims defs[8] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {3, 3}, {5, 5}};
+    tss_platform plats[64];
+    int32_t n = 0;
+    CHECK(tss_solve_upper_bound(e, grid, w, h, defs, 8, 1, 7, 0, 20000, plats, 64, &n) == TSS_SAT);
+    CHECK(n == 1 && plats[0].def_w == 5 && plats[0].def_h == 5);
+    /* validate() on the GPU agrees, flags stay clear */
+    uint8_t unsupported[64], flags[64];
+    CHECK(tss_validate(e, grid, w, h, plats, n, unsupported, flags) == 0 && flags[0] == 0);
+    /* capacity error instead of a buffer overrun */
+    CHECK(tss_solve_upper_bound(e, grid, w, h, defs, 1, 3, 7, 0, 20000, plats, 2, &n) == TSS_E_CAPACITY && n == 3);
+    CHECK(strlen(tss_last_error(e)) > 0);
+    /* a platform set without 1x1 is rejected, not UB (src/encoder.rs:564-566) */
+    const tss_dims bad[1] = {{3, 3}};
+    CHECK(tss_solve_upper_bound(e, grid, w, h, bad, 1, -1, 7, 0, 100, plats, 64, &n) == TSS_E_INVALID);
+
+    /* encoder + CNF check of the witness (kernel c) */
+    tss_encoding* enc = NULL;
+    CHECK(tss_encoding_create(grid, w, h, defs, 8, &enc) == TSS_OK);
+    int32_t n_vars = 0, n_clauses = 0, n_dims = 0;
+    int64_t n_lits = 0;
+    CHECK(tss_encoding_sizes(enc, &n_vars, &n_clauses, &n_lits, &n_dims) == TSS_OK);
+    CHECK(n_vars == 466 && n_clauses == 1625 && n_lits == 3072 && n_dims == 13); /* SURVEY.md §6 */
+    int32_t* lits = malloc(sizeof(int32_t) * (size_t)n_lits);
+    uint32_t* offsets = malloc(sizeof(uint32_t) * (size_t)(n_clauses + 1));
+    uint8_t* assignment = malloc((size_t)n_vars + 1);
+    CHECK(lits && offsets && assignment);
+    CHECK(tss_encoding_cnf(enc, lits, offsets) == TSS_OK);
+    CHECK(tss_solve_upper_bound(e, grid, w, h, defs, 8, 1, 7, 0, 20000, plats, 64, &n) == TSS_SAT);
+    CHECK(tss_layout_to_assignment(e, enc, plats, n, assignment) == TSS_OK);
+    tss_cnf* cnf = NULL;
+    CHECK(tss_cnf_upload(e, lits, offsets, n_clauses, n_vars, &cnf) == TSS_OK);
+    int32_t n_falsified = -1, first = 0;
+    CHECK(tss_cnf_check(e, cnf, assignment, 1, &n_falsified, &first) == TSS_OK);
+    CHECK(n_falsified == 0 && first == -1);
+    tss_platform decoded[64];
+    int32_t n_dec = 0;
+    CHECK(tss_layout_from_assignment(enc, assignment, n_vars + 1, decoded, 64, &n_dec) == TSS_OK);
+    CHECK(n_dec == 1 && decoded[0].x == plats[0].x && decoded[0].y == plats[0].y && decoded[0].def_w == 5);
+
+    /* interrupt: a pending interrupt makes the next solve return UNKNOWN, clearing it restores service */
+    tss_interrupt(e);
+    CHECK(tss_solve_upper_bound(e, grid, w, h, defs, 1, 3, 7, 100, 0, plats, 64, &n) == TSS_UNKNOWN);
+    tss_stats st;
+    CHECK(tss_get_stats(e, &st) == TSS_OK && st.interrupted == 1);
+    tss_clear_interrupt(e);
+    CHECK(tss_solve_upper_bound(e, grid, w, h, defs, 1, 3, 7, 0, 20000, plats, 64, &n) == TSS_SAT && n == 3);
+
+    tss_cnf_destroy(cnf);
+    tss_encoding_destroy(enc);
+    free(lits); free(offsets); free(assignment);
+    tss_engine_destroy(e);
+    printf("c_abi_smoke ok\n");
+    return 0;
+}

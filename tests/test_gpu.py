@@ -530,6 +530,16 @@ def test_errors_and_edge_cases(eng):
     assert len(unc) == 0
 
 
+def test_c_abi_from_plain_c(tmp_path):
+    """The boundary from a C host: tests/c_abi_smoke.c (gcc, no Python in the loop) loads a project, solves with the
+    REPL's platform set, validates, checks the witness against the encoder's CNF, exercises the error and interrupt paths."""
+    import subprocess
+    from test_host import build_c_abi_smoke
+    out = subprocess.run([build_c_abi_smoke(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "c_abi_smoke ok" in out.stdout
+
+
 def test_measured_peaks_sane(eng):
     p = eng.measure_peaks()
     sm = eng.device_info()["sm_count"]

@@ -1,0 +1,56 @@
+"""Two-GPU test of the engine's native exchange (comm.cu): skipped on a single-GPU box.  Ranks are processes; the only
+thing the host moves between them is the 128-byte NCCL id (through a file here)."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, tmp, out):
+    import timberborn_support_solver_b200 as T
+    eng = T.Engine(rank)
+    id_path = os.path.join(tmp, "nccl_id")
+    if rank == 0:
+        with open(id_path + ".tmp", "wb") as f:
+            f.write(eng.comm_unique_id())
+        os.replace(id_path + ".tmp", id_path)
+    while not os.path.exists(id_path):
+        time.sleep(0.01)
+    eng.comm_init(open(id_path, "rb").read(), rank, world)
+    assert eng.comm_world() == world
+    grid = T.WorldGrid(np.ones((16, 16), np.uint8))
+    s = eng.search(grid, seed=5, n_chains=64, chain_offset=rank * 64)
+    hist = []
+    for _ in range(6):
+        s.run(300, 0)
+        hist.append((s.best_count(), s.global_best()))
+    chains = s.read_chains()
+    out.put((rank, hist, int(chains["best"].min())))
+    s.close()
+    eng.close()
+
+
+def test_native_nccl_portfolio_two_gpus(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, str(tmp_path), out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, h0, b0), (_, h1, b1) = res
+    for (l0, g0), (l1, g1) in zip(h0, h1):
+        assert g0 == g1                                             # every rank sees the same global bound after each epoch
+        locals_ = [x for x in (l0, l1) if x is not None]
+        if locals_:
+            assert g0 == min(locals_)                               # ... and it is the min over the ranks' best counts
+    assert h0[-1][1] == 15 == min(b0, b1)                           # the portfolio reaches the proven optimum of rect 16x16

@@ -169,3 +169,18 @@ def test_trivial_optimization_and_total_weight(fixtures):
         lay = T.PlatformLayout(T.Platform(x, y, T.PlatformDef(dw, dh), bool(r)) for x, y, dw, dh, r in plats)
         assert lay.total_weight(weights) == O.total_weight(plats, {k.dims(): v for k, v in weights.items()})
     assert T.PlatformLayout([T.Platform(0, 0, ONE), T.Platform(1, 0, ONE)]).platform_stats() == {ONE: 2}
+
+
+def build_c_abi_smoke(tmp_path):
+    """gcc (plain C, -std=c99 -pedantic) compiles tests/c_abi_smoke.c against include/tss.h and links libtss.so."""
+    import subprocess
+    exe = os.path.join(str(tmp_path), "c_abi_smoke")
+    pkg = os.path.dirname(T.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", exe, "-L", pkg, "-l:libtss.so", f"-Wl,-rpath,{pkg}"])
+    return exe
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    exe = build_c_abi_smoke(tmp_path)
+    assert os.path.exists(exe)

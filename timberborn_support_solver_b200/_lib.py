@@ -82,6 +82,10 @@ SIGNATURES = {
     "tss_search_set_bound": (C.c_int, [_vp, _i32]),
     "tss_search_best_layout": (C.c_int, [_vp, _P(Platform), _i32, _i32p]),
     "tss_search_n_chains": (C.c_int, [_vp]),
+    "tss_search_global_best": (C.c_int, [_vp, _i32p]),
+    "tss_comm_unique_id": (C.c_int, [_vp, _u8p]),
+    "tss_comm_init": (C.c_int, [_vp, _u8p, _i32, _i32]),
+    "tss_comm_world": (C.c_int, [_vp]),
     "tss_search_read_chains": (C.c_int, [_vp, _u32p, _u32p, _i32p, _i32p, _u32p, _P(C.c_uint64)]),
     "tss_sls_spec_probe": (None, [_u32p]),
     "tss_search_set_weights": (C.c_int, [_vp, _i32p, _i32]),

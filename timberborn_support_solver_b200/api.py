@@ -390,6 +390,13 @@ class Search:
     def set_bound(self, count: int):
         self.engine._check(self.engine.lib.tss_search_set_bound(self._h, count))
 
+    def global_best(self) -> Optional[int]:
+        """The bound the next epoch searches below (min over this search, outside bounds and — with a communicator on the
+        engine — every rank's search)."""
+        c = C.c_int32()
+        self.engine._check(self.engine.lib.tss_search_global_best(self._h, C.byref(c)))
+        return None if c.value < 0 else c.value
+
     def read_chains(self) -> dict:
         """Per-chain state after the last epoch (parity tests replay it on the CPU model)."""
         n = self.n_chains
@@ -429,6 +436,20 @@ class Engine:
         if rc < 0:
             raise TssError(rc, self.lib.tss_last_error(self._h).decode())
         return rc
+
+    # ---- multi-GPU portfolio (one process per GPU; the host only carries the 128-byte NCCL id between ranks)
+    def comm_unique_id(self) -> bytes:
+        buf = np.zeros(128, np.uint8)
+        self._check(self.lib.tss_comm_unique_id(self._h, _ptr(buf, C.c_uint8)))
+        return buf.tobytes()
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = np.frombuffer(unique_id, np.uint8).copy()
+        assert buf.size == 128
+        self._check(self.lib.tss_comm_init(self._h, _ptr(buf, C.c_uint8), rank, world))
+
+    def comm_world(self) -> int:
+        return self.lib.tss_comm_world(self._h)
 
     def set_stream(self, cuda_stream: int):
         self._check(self.lib.tss_engine_set_stream(self._h, C.c_void_p(cuda_stream)))

@@ -95,6 +95,7 @@ struct tss_search {
     unsigned long long* totals_host = nullptr; // pinned [2]
     unsigned long long totals_seen[2] = {0, 0};
     bool dirty = false;
+    bool share = false;                        // all-reduce-min the bound over the engine's communicator after every epoch
     tss::LnsSearch* lns = nullptr;             // grids larger than 32x32: window decomposition (lns.cu)
     int external_bound = tss::sls::NO_BOUND;
     // platform sets beyond {1x1} on grids up to 32x32: placement search (sls_multi.cu)
@@ -154,6 +155,7 @@ void tss_engine_destroy(tss_engine* e) {
     cudaSetDevice(e->device);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     if (e->cached_search) { search_free(e->cached_search); e->cached_search = nullptr; }
+    if (e->comm) { comm_destroy(e->comm); e->comm = nullptr; }
     for (auto& b : e->scratch) if (b.ptr) cudaFree(b.ptr);
     for (auto& b : e->staging) if (b.ptr) cudaFreeHost(b.ptr);
     if (e->irq_stream) { cudaStreamSynchronize(e->irq_stream); cudaStreamDestroy(e->irq_stream); }
@@ -437,6 +439,7 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
     s->seed = params ? params->seed : 0;
     s->chain_offset = params ? (uint32_t)params->chain_offset : 0;
     s->noise = (params && params->noise_pct >= 0) ? params->noise_pct : sls::DEFAULT_NOISE_PCT;
+    s->share = e->comm != nullptr;  // a portfolio created on an engine with a communicator shares its bound every epoch
     if (w > 32 || h > 32) {  // window decomposition: n_chains is read as chains per window (multiple of 4, default 8)
         int seeds = (params && params->n_chains > 0) ? ((params->n_chains + 3) / 4) * 4 : 8;
         int rc = lns_create(e, grid, w, h, seeds, s->seed, s->chain_offset, s->noise, &s->lns);
@@ -533,6 +536,7 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
     if (s->multi) {
         int rc = slsm_run(e, s->rows_dev, s->w, s->h, s->keys_dev, s->costs_dev, (int)s->key_dims.size(), s->mstates, s->n_chains, s->chain_offset, s->seed, steps,
                           s->bounds_dev, target_count < 0 ? -1 : target_count, s->noise, s->totals_dev, s->best_dev);
+        if (rc == TSS_OK && e->comm && s->share) rc = comm_allreduce_min(e, e->comm, s->bounds_dev, 1);
         if (rc) return rc;
         TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
         TSS_CUDA(e, cudaMemcpyAsync(s->best_host, s->best_dev, sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
@@ -547,6 +551,8 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
     int rc = (h16 ? sls_run_h16 : sls_run)(e, s->rows_dev, s->tabs_dev, s->states, s->n_chains, s->chains_per_terrain, s->chain_offset, s->seed,
                                            steps, s->bounds_dev, target_count < 0 ? -1 : target_count, s->noise, s->totals_dev);
     if (rc == TSS_OK) rc = sls_best_reduce(e, s->states, chains_per_group, s->n_chains, s->n_groups, s->best_dev, s->bounds_dev);
+    // multi-GPU portfolio: the one exchange of the path, in-stream on the device-resident bound (no host round trip)
+    if (rc == TSS_OK && e->comm && s->share && s->n_groups == 1) rc = comm_allreduce_min(e, e->comm, s->bounds_dev, 1);
     if (rc) return rc;
     TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
     TSS_CUDA(e, cudaMemcpyAsync(s->best_host, s->best_dev, sizeof(int2) * (size_t)s->n_groups, cudaMemcpyDeviceToHost, e->stream));
@@ -586,6 +592,18 @@ int tss_search_best_count(tss_search* s, int32_t* count) {
     for (int g = 0; g < s->n_groups; g++) best = s->best_host[g].x < best ? s->best_host[g].x : best;
     *count = best >= sls::NO_BOUND ? -1 : best;
     s->e->stats.best_count = *count;
+    return TSS_OK;
+}
+
+int tss_search_global_best(tss_search* s, int32_t* count) {
+    if (!s || !count) return TSS_E_INVALID;
+    tss_engine* e = s->e;
+    int rc = search_sync(s);
+    if (rc) return rc;
+    if (s->lns) return tss_search_best_count(s, count);
+    int b = sls::NO_BOUND;
+    TSS_CUDA(e, cudaMemcpy(&b, s->bounds_dev, sizeof(int), cudaMemcpyDeviceToHost));
+    *count = b >= sls::NO_BOUND ? -1 : b;
     return TSS_OK;
 }
 
@@ -709,6 +727,7 @@ int tss_solve_min_weight(tss_engine* e, const uint8_t* grid, int32_t w, int32_t 
     tss_search* s = nullptr;
     int rc = tss_search_create(e, grid, w, h, defs, n_defs, &p, &s);
     if (rc) return rc;
+    s->share = false;
     rc = tss_search_set_weights(s, weights, n_weights);
     if (rc == TSS_OK && weight_limit >= 0) rc = tss_search_set_bound(s, (int32_t)(weight_limit + 1 < sls::NO_BOUND ? weight_limit + 1 : sls::NO_BOUND));
     const double t0 = now_ms();
@@ -778,6 +797,7 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
         rc = tss_search_create(e, grid, w, h, defs, n_defs, &p, &s);
         if (rc) return rc;
     }
+    s->share = false;  // a one-shot solve runs a rank-local number of epochs: no collective inside
     if (card_limit >= 0) rc = tss_search_set_bound(s, card_limit + 1);
     const double t0 = now_ms();
     // no budget given: behave like one SAT call (return the first model within the bound), but give up after a

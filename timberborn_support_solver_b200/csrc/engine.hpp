@@ -12,6 +12,12 @@
 #include "../../include/tss.h"
 #include "host_model.hpp"
 
+namespace tss {
+struct Comm;
+void comm_destroy(Comm* c);
+int comm_allreduce_min(tss_engine* e, Comm* c, int* dev, int n);  // in-stream ncclAllReduce(min) on device ints
+}  // namespace tss
+
 // A growable device (or pinned host) scratch buffer owned by the engine.
 struct TssBuffer {
     void* ptr = nullptr;
@@ -35,6 +41,7 @@ struct tss_engine {
     cudaStream_t irq_stream = nullptr;
     std::atomic<int> interrupt_flag{0};
     struct tss_search* cached_search = nullptr;  // workspace reused by tss_solve_upper_bound (no cudaMalloc per call)
+    struct tss::Comm* comm = nullptr;            // NCCL communicator of a multi-GPU portfolio (comm.cu), or null
     TssBuffer scratch[8];                    // device scratch slots
     TssBuffer staging[4];                    // pinned host staging slots
 

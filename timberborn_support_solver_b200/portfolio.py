@@ -47,13 +47,18 @@ def allreduce_min(value: Optional[int], device=None) -> Optional[int]:
 class Portfolio:
     """Independent-seed SLS portfolio on one terrain across the ranks of the default process group."""
 
-    def __init__(self, make_search, chains_per_rank: int, device=None):
+    def __init__(self, make_search, chains_per_rank: int, device=None, native: bool = False):
         """make_search(chain_offset, n_chains) -> an object with run(steps, target), best_count(), set_bound(c),
-        best_layout() — Engine.search(...) on a GPU rank."""
+        best_layout() — Engine.search(...) on a GPU rank.
+
+        native=True: the engine has a communicator (Engine.comm_init) and all-reduce-mins the device-resident bound
+        itself inside run(); this class then only reads the global best.  native=False: the exchange goes through
+        torch.distributed (any backend — what the gloo tests exercise)."""
         dist = _dist()
         self.rank = dist.get_rank() if dist else 0
         self.world = dist.get_world_size() if dist else 1
         self.device = device
+        self.native = native
         self.search = make_search(self.rank * chains_per_rank, chains_per_rank)
         self.global_best: Optional[int] = None
         self.epochs = 0
@@ -61,10 +66,13 @@ class Portfolio:
     def epoch(self, steps: int, target: int = 0) -> Optional[int]:
         """One epoch on every rank followed by the all-reduce-min; returns the global best count."""
         self.search.run(steps, target)
-        local = self.search.best_count()
-        best = allreduce_min(local, self.device)
+        if self.native:
+            best = self.search.global_best()   # the engine already exchanged the bound in-stream (ncclAllReduce min)
+        else:
+            best = allreduce_min(self.search.best_count(), self.device)
+            if best is not None:
+                self.search.set_bound(best)    # chains now only look for layouts with fewer than `best` supports
         if best is not None:
-            self.search.set_bound(best)      # chains now only look for layouts with fewer than `best` supports
             self.global_best = best if self.global_best is None else min(self.global_best, best)
         self.epochs += 1
         return self.global_best
