@@ -547,3 +547,33 @@ def test_measured_peaks_sane(eng):
     # LOP3: at most 64 lanes/clk/SM (alu pipe, 16 lanes per SMSP) .. allow the 128-lane case too
     assert 0.2 * 64 * sm * p["sm_mhz"] / 1e3 < p["lop3_gops"] < 1.1 * 128 * sm * p["sm_mhz"] / 1e3
     assert p["popc_gops"] > 0 and p["shfl_gops"] > 0 and p["smem_gbs"] > 1000
+
+
+def test_error_paths_return_codes_not_crashes(eng):
+    """Error behaviour at the boundary: status codes + tss_last_error, never an abort."""
+    import ctypes as C
+    lib = T.load()
+    g = np.ones((4, 4), np.uint8)
+    gp = g.ctypes.data_as(C.POINTER(C.c_uint8))
+    n = C.c_int32()
+    assert lib.tss_solve_upper_bound(eng._h, None, 4, 4, None, 0, -1, 0, 0, 10, None, 0, C.byref(n)) == -1       # null grid
+    assert lib.tss_solve_upper_bound(eng._h, gp, 0, 4, None, 0, -1, 0, 0, 10, None, 0, C.byref(n)) == -1          # zero-sized grid
+    assert b"bad arguments" in lib.tss_last_error(eng._h)
+    big = np.ones((700, 700), np.uint8)
+    with pytest.raises(T.TssError) as e:
+        eng.search(T.WorldGrid(big))
+    assert e.value.code == -4                                                                                    # TSS_E_UNSUPPORTED
+    lits = np.array([1, -9], np.int32)
+    offs = np.array([0, 2], np.uint32)
+    h = C.c_void_p()
+    assert lib.tss_cnf_upload(eng._h, lits.ctypes.data_as(C.POINTER(C.c_int32)), offs.ctypes.data_as(C.POINTER(C.c_uint32)), 1, 3, C.byref(h)) == -1
+    assert b"out of range" in lib.tss_last_error(eng._h)
+    with pytest.raises(T.TssError):
+        eng.solve_min_weight(T.WorldGrid(g), T.PLATFORMS_DEFAULT[:1], {T.PlatformDef(1, 1): 5})                  # weight objective needs > 1 key
+    s = eng.search(T.WorldGrid(g), seed=1, n_chains=8)
+    with pytest.raises(T.TssError):
+        s.best_layout()                                                                                          # nothing found yet
+    with pytest.raises(T.TssError):
+        s.run(0, 0)
+    s.close()
+    assert eng.comm_world() == 1

@@ -297,3 +297,19 @@ def test_validate_geodesic_not_manhattan():
     assert v.unsupported.tolist() == [[0, 0, 0, 0, 1, 1, 1]]
     g = rows_to_grid(["XXXXXXX"])
     assert O.validate(g, sites([(3, 0)])).is_valid and not O.validate(g, sites([(2, 0)])).is_valid
+
+
+def test_survey_optimum_witnesses(fixtures, readme):
+    """The survey's independently derived optimum witnesses pass the oracle's validate and extend to
+    models of the oracle encoder's CNF under the at-most-optimum bound; dropping any support breaks coverage."""
+    terrains = {"rect16": np.ones((16, 16), np.uint8), "ex2": fixtures["ex2"], "readme": readme[0]}
+    for wit in golden("survey_witnesses")["witnesses"]:
+        g = terrains[wit["terrain"]]
+        sup = [tuple(p) for p in wit["supports"]]
+        assert len(sup) == wit["optimum"]
+        assert O.validate(g, sites(sup)).is_valid, wit["terrain"]
+        for i in range(len(sup)):
+            assert not O.validate(g, sites(sup[:i] + sup[i + 1:])).is_valid       # every support is needed
+        enc = O.Encoding(O.PLATFORMS_1X1, g)
+        r, a, _ = _solve_with_units(enc.with_limits({ONE: wit["optimum"]}), None, enc, sup, g)
+        assert r == 10

@@ -86,3 +86,16 @@ def test_single_process_paths():
     pf = P.Portfolio(lambda off, n: ScriptedSearch(off, n, [None, 5]), chains_per_rank=8)
     assert pf.epoch(10) is None and pf.epoch(10) == 5 and pf.search.bounds == [5]
     assert P.solve_batch_sharded(lambda g, lo: np.full(len(g), 3), np.zeros((4, 1, 1))).tolist() == [3, 3, 3, 3]
+
+
+class NativeScripted(ScriptedSearch):
+    """Stand-in for a search on an engine with a communicator: run() already exchanged the bound."""
+
+    def global_best(self):
+        return 7 if self.epoch >= 1 else None
+
+
+def test_native_exchange_path_reads_global_best_only():
+    pf = P.Portfolio(lambda off, n: NativeScripted(off, n, [9, 9, 9]), chains_per_rank=4, native=True)
+    assert pf.epoch(10) is None and pf.epoch(10) == 7 and pf.epoch(10) == 7
+    assert pf.search.bounds == []          # the engine owns the bound: nothing is pushed from the host
