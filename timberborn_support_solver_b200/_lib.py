@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtss.so")
+LIB_PATH = os.environ.get("TSS_LIB") or os.path.join(HERE, "libtss.so")   # TSS_LIB: load another BUILD of libtss (kernel experiments)
 
 TSS_OK, TSS_UNKNOWN, TSS_SAT, TSS_UNSAT = 0, 0, 10, 20
 TSS_E_INVALID, TSS_E_CAPACITY, TSS_E_CUDA, TSS_E_UNSUPPORTED, TSS_E_PARSE = -1, -2, -3, -4, -5

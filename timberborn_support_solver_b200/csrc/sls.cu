@@ -156,7 +156,7 @@ __device__ __forceinline__ int remove_min_loss(Lane& L, const WarpCtx& w, int& k
 // tiles of the window NOT already covered by frozen supports outside the window's movable core, and only sites with
 // core_lo <= x, y < core_hi may receive supports (their reach never leaves the window).
 template <bool WINDOW>
-__global__ void __launch_bounds__(WARPS * 32) sls_kernel(const uint32_t* __restrict__ terrain_rows, const uint2* __restrict__ rtabs,
+__global__ void __launch_bounds__(WARPS * 32, 8) sls_kernel(const uint32_t* __restrict__ terrain_rows, const uint2* __restrict__ rtabs,
                                                         const uint32_t* __restrict__ need_rows, int core_lo, int core_hi,
                                                         ChainState* __restrict__ states, int n_chains, int chains_per_terrain,
                                                         uint32_t chain_offset, uint64_t seed, long long steps,

@@ -89,7 +89,7 @@ __device__ __forceinline__ void diamond_cell(int i, int& dx, int& dy) {
     dx = (i - start) - (3 - abs(dy));
 }
 
-__global__ void __launch_bounds__(WARPS * 32) sls_h16_kernel(const uint32_t* __restrict__ terrain_rows, const uint2* __restrict__ rtabs,
+__global__ void __launch_bounds__(WARPS * 32, 8) sls_h16_kernel(const uint32_t* __restrict__ terrain_rows, const uint2* __restrict__ rtabs,
                                                             ChainState* __restrict__ states, int n_chains, int chains_per_terrain,
                                                             uint32_t chain_offset, uint64_t seed, long long steps,
                                                             const int* __restrict__ bounds, int target, int noise_pct,
