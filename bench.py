@@ -291,14 +291,52 @@ def main():
         line["e2e"] = {"value": (e1["candidates_scored"] - e0["candidates_scored"]) / t_e2e, "unit": UNIT,
                        "h2d_bytes_per_step": int(grid.data.size + 8), "d2h_bytes_per_step": int(20 * lay.platform_count() + 16 * 9 + 320),
                        "note": f"tss_solve_upper_bound from a host u8 grid to a host platform list, {steps_per_call} steps/chain per call, wall clock incl. allocation, copies, witness validation"}
-        # ---------------- kernel (c): CNF check of 8192 witnesses against the encoder's clauses
+        # ---------------- kernel (c): CNF check of 8192 witness assignments against the encoder's clauses (incl. the totalizer
+        # of the at-most-15 bound): the SLS witness, completed by unit propagation, replicated; every 64th copy has one
+        # support removed (those must come back falsified)
         enc = T.Encoding.encode(T.PLATFORMS_DEFAULT[:1], grid)
         cnf = enc.with_limits(T.PlatformLimits.new_unweighted({T.PlatformDef(1, 1): 15}))
         dev = eng.upload_cnf(cnf)
-        a = np.random.default_rng(0).integers(0, 2, (8192, cnf.n_vars + 1)).astype(np.uint8)
-        dev.check(a)
-        dev.check(a)
-        line["cnf_kernel"] = {"clause_evals_per_s": cnf.n_clauses * len(a) / (eng.stats()["device_ms"] * 1e-3), "clauses": cnf.n_clauses, "literals": int(len(cnf.lits)), "assignments": len(a)}
+        res, wit = eng.solve_upper_bound(grid, card_limit=OPTIMUM_RECT16, seed=300)
+        full = np.full((1, cnf.n_vars + 1), 2, np.uint8)
+        base_a = eng.layout_to_assignment(enc, wit)
+        full[0, : len(base_a)] = base_a
+        prop, conflict, rounds = dev.propagate(full)
+        prop[prop == 2] = 0
+        assert conflict[0] < 0 and dev.check(prop)[0][0] == 0
+        a = np.repeat(prop, 8192, axis=0)
+        first_support = int(enc.vars().plat_var[[p.y * 16 + p.x for p in wit.platforms().values()][0], 0])
+        a[::64, first_support] = 0
+        nf, _ = dev.check(a)
+        nf, _ = dev.check(a)
+        assert (nf[::64] > 0).all() and nf.reshape(-1, 64)[:, 1:].sum() == 0
+        line["cnf_kernel"] = {"clause_evals_per_s": cnf.n_clauses * len(a) / (eng.stats()["device_ms"] * 1e-3), "clauses": cnf.n_clauses,
+                              "literals": int(len(cnf.lits)), "assignments": len(a), "propagation_rounds": rounds,
+                              "input": "SLS witness completed by unit propagation x 8192, every 64th with one support removed"}
+        # ---------------- the other named configs, for context (parity-test cases, not the bench line): wall clock through the C ABI
+        others = {}
+        t0 = time.perf_counter()
+        ex1_rows = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))["ex1"]["grid"]   # test/ex1.toml
+        ex1 = T.WorldGrid.from_toml("[world]\ngrid = [\n" + "".join(f'    "{r}",\n' for r in ex1_rows) + "]\n")
+        res, lay3 = eng.solve_upper_bound(ex1, T.PLATFORMS_DEFAULT, card_limit=1, seed=1)
+        others["C1 ex1 default-8 (REPL set)"] = {"count": lay3.platform_count(), "proven_optimum": 1, "ms": (time.perf_counter() - t0) * 1e3}
+        g4 = T.WorldGrid.synthetic(256, 256, 1, 0)
+        s4 = eng.search(g4, seed=1, n_chains=16)
+        t0 = time.perf_counter()
+        for _ in range(24):
+            s4.run(4000, 0)
+        c4 = s4.best_count()
+        others["C4 256x256 p=0.7 (window decomposition, 24 phases x 4000 steps)"] = {"count": c4, "ceiling_tiles": int(g4.data.sum()), "ms": (time.perf_counter() - t0) * 1e3}
+        s4.close()
+        n5 = 16384
+        g5 = np.stack([T.WorldGrid.synthetic(32, 32, 1, t).data for t in range(n5)])
+        t0 = time.perf_counter()
+        c5 = eng.solve_batch(g5, seed=1, steps=2000)
+        dt5 = time.perf_counter() - t0
+        others["C5 batch of 32x32 p=0.7 terrains (16384 of the 100k, 2000 steps x 4 chains each)"] = {
+            "terrains_per_s": n5 / dt5, "mean_count": float(c5.mean()), "ms": dt5 * 1e3,
+            "note": "host Glucose stand-in needs minutes per terrain (3 sampled terrains: best 76/78/73 after 5 min each, GPU 73/73/67)"}
+        line["other_configs"] = others
         # ---------------- CPU baseline (bounded sample, rank 0, N = 1)
         rate, threads, sample = cpu_validate_rate(grid.data, seconds=10.0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}

@@ -53,6 +53,15 @@ __global__ void pack_rows32_kernel(const uint8_t* __restrict__ bytes, int w, int
         out[i] = v;
     }
 }
+
+// best layout rows of every terrain group: out[group][32] = states[best[group].y].bestS (zeros if the group found nothing)
+__global__ void gather_best_rows_kernel(const sls::ChainState* __restrict__ states, const int2* __restrict__ best, int n_groups,
+                                        uint32_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_groups * 32) return;
+    int c = best[i >> 5].y;
+    out[i] = c >= 0 ? states[c].bestS[i & 31] : 0u;
+}
 }  // namespace tss
 
 void* tss_engine::dev(int slot, size_t bytes) {
@@ -96,6 +105,7 @@ struct tss_search {
     unsigned long long totals_seen[2] = {0, 0};
     bool dirty = false;
     bool share = false;                        // all-reduce-min the bound over the engine's communicator after every epoch
+    int cap_terrains = 0, cap_chains = 0;      // allocated capacity of a batch workspace (tss_solve_batch reuses it)
     tss::LnsSearch* lns = nullptr;             // grids larger than 32x32: window decomposition (lns.cu)
     int external_bound = tss::sls::NO_BOUND;
     // platform sets beyond {1x1} on grids up to 32x32: placement search (sls_multi.cu)
@@ -155,6 +165,7 @@ void tss_engine_destroy(tss_engine* e) {
     cudaSetDevice(e->device);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     if (e->cached_search) { search_free(e->cached_search); e->cached_search = nullptr; }
+    if (e->cached_batch) { search_free(e->cached_batch); e->cached_batch = nullptr; }
     if (e->comm) { comm_destroy(e->comm); e->comm = nullptr; }
     for (auto& b : e->scratch) if (b.ptr) cudaFree(b.ptr);
     for (auto& b : e->staging) if (b.ptr) cudaFreeHost(b.ptr);
@@ -851,46 +862,67 @@ int tss_solve_batch(tss_engine* e, const uint8_t* grids, int32_t w, int32_t h, i
     const size_t tiles = (size_t)w * h;
     e->stats.interrupted = 0;
     double dev_ms = 0;
-    for (int64_t base = 0; base < n; base += CHUNK) {
-        if (e->interrupted()) { e->stats.interrupted = 1; return TSS_UNKNOWN; }
+    // one workspace for the whole call, kept on the engine for the next call (allocation dominated the first version)
+    const int nt_max = (int)(n < CHUNK ? n : CHUNK);
+    tss_search* s = e->cached_batch;
+    e->cached_batch = nullptr;
+    if (s && (s->cap_terrains < nt_max || s->cap_chains < nt_max * CPT)) { search_free(s); s = nullptr; }
+    if (!s && nt_max > 0) {
+        s = new tss_search();
+        s->e = e;
+        s->n_chains = s->cap_chains = nt_max * CPT;
+        s->n_groups = s->cap_terrains = nt_max;
+        int rc = search_alloc(e, s, nullptr, nt_max);
+        if (rc != TSS_OK) { search_free(s); return rc; }
+    }
+    int rc = TSS_OK;
+    for (int64_t base = 0; base < n && rc == TSS_OK; base += CHUNK) {
+        if (e->interrupted()) break;
         const int nt = (int)((n - base) < CHUNK ? (n - base) : CHUNK);
-        tss_search* s = new tss_search();
-        s->e = e; s->w = w; s->h = h; s->seed = seed; s->chain_offset = (uint32_t)(base * CPT);
+        s->w = w; s->h = h; s->seed = seed; s->chain_offset = (uint32_t)(base * CPT);
         s->n_chains = nt * CPT; s->n_groups = nt; s->chains_per_terrain = CPT;
-        int rc = search_alloc(e, s, nullptr, nt);
-        uint8_t* bytes = rc == TSS_OK ? (uint8_t*)e->dev(0, tiles * (size_t)nt) : nullptr;
-        if (rc == TSS_OK && !bytes) rc = TSS_E_CUDA;
-        if (rc == TSS_OK) {
-            cudaError_t err = cudaMemcpyAsync(bytes, grids + (size_t)base * tiles, tiles * (size_t)nt, cudaMemcpyHostToDevice, e->stream);
-            if (err != cudaSuccess) rc = e->fail(TSS_E_CUDA, "tss_solve_batch: %s", cudaGetErrorString(err));
-        }
-        if (rc == TSS_OK) {
-            pack_rows32_kernel<<<e->prop.multiProcessorCount * 8, 256, 0, e->stream>>>(bytes, w, h, nt, s->rows_dev);
-            e->stats.kernel_launches++;
-            rc = search_init_device(e, s, nt);
-        }
-        // epochs of 1024 steps so the four chains of a terrain share their bound and an interrupt is honoured
+        s->totals_seen[0] = s->totals_seen[1] = 0;
+        s->dirty = false;
+        uint8_t* bytes = (uint8_t*)e->dev(0, tiles * (size_t)nt);
+        if (!bytes) { rc = TSS_E_CUDA; break; }
+        cudaError_t err = cudaMemcpyAsync(bytes, grids + (size_t)base * tiles, tiles * (size_t)nt, cudaMemcpyHostToDevice, e->stream);
+        if (err != cudaSuccess) { rc = e->fail(TSS_E_CUDA, "tss_solve_batch: %s", cudaGetErrorString(err)); break; }
+        pack_rows32_kernel<<<e->prop.multiProcessorCount * 8, 256, 0, e->stream>>>(bytes, w, h, nt, s->rows_dev);
+        e->stats.kernel_launches++;
+        rc = search_init_device(e, s, nt);
+        // epochs of 1024 steps so the chains of a terrain share their bound and an interrupt is honoured
         for (int64_t done = 0; rc == TSS_OK && done < steps; done += 1024) {
             if (e->interrupted()) break;
             rc = tss_search_run(s, (steps - done) < 1024 ? (steps - done) : 1024, 0);
+        }
+        uint32_t* rows_dev = nullptr;
+        uint32_t* rows_host = nullptr;
+        if (rc == TSS_OK && out_layouts) {  // gather the winners' rows on the device: 128 B per terrain instead of every chain state
+            rows_dev = (uint32_t*)e->dev(1, sizeof(uint32_t) * 32 * (size_t)nt);
+            rows_host = (uint32_t*)e->pin(3, sizeof(uint32_t) * 32 * (size_t)nt);
+            if (!rows_dev || !rows_host) { rc = TSS_E_CUDA; break; }
+            gather_best_rows_kernel<<<(nt * 32 + 255) / 256, 256, 0, e->stream>>>(s->states, s->best_dev, nt, rows_dev);
+            e->stats.kernel_launches++;
+            err = cudaMemcpyAsync(rows_host, rows_dev, sizeof(uint32_t) * 32 * (size_t)nt, cudaMemcpyDeviceToHost, e->stream);
+            if (err != cudaSuccess) { rc = e->fail(TSS_E_CUDA, "tss_solve_batch: %s", cudaGetErrorString(err)); break; }
         }
         if (rc == TSS_OK) rc = search_sync(s);
         if (rc == TSS_OK) {
             dev_ms += e->stats.device_ms;
             for (int t = 0; t < nt; t++) out_counts[base + t] = s->best_host[t].x >= sls::NO_BOUND ? -1 : s->best_host[t].x;
-            if (out_layouts) {
-                std::vector<sls::ChainState> st((size_t)s->n_chains);
-                cudaError_t err = cudaMemcpy(st.data(), s->states, sizeof(sls::ChainState) * st.size(), cudaMemcpyDeviceToHost);
-                if (err != cudaSuccess) rc = e->fail(TSS_E_CUDA, "tss_solve_batch: %s", cudaGetErrorString(err));
-                for (int t = 0; t < nt && rc == TSS_OK; t++) {
-                    int c = s->best_host[t].y;
-                    for (int y = 0; y < h; y++) out_layouts[(size_t)(base + t) * h + y] = c >= 0 ? st[(size_t)c].bestS[y] : 0u;
-                }
-            }
+            if (out_layouts)
+                for (int t = 0; t < nt; t++)
+                    for (int y = 0; y < h; y++) out_layouts[(size_t)(base + t) * h + y] = rows_host[(size_t)t * 32 + y];
         }
-        search_free(s);
-        if (rc != TSS_OK) return rc;
     }
+    if (s) {
+        cudaStreamSynchronize(e->stream);
+        s->n_chains = s->cap_chains;
+        s->n_groups = s->cap_terrains;
+        e->cached_batch = s;
+    }
+    if (rc != TSS_OK) return rc;
+    if (e->interrupted()) e->stats.interrupted = 1;
     e->stats.device_ms = dev_ms;
     return e->interrupted() ? TSS_UNKNOWN : TSS_SAT;
 }
