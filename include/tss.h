@@ -93,7 +93,9 @@ int tss_device_info(const tss_engine* e, char* name, int cap, int* sm_count, int
 /* One process per GPU.  Rank 0 makes an id (tss_comm_unique_id), the host passes its 128 bytes to the other ranks, every
  * rank calls tss_comm_init.  From then on a search created with tss_search_create on this engine all-reduce-mins its
  * device-resident bound over NCCL/NVLink after every tss_search_run — 4 bytes, in-stream, no host round trip — so all
- * ranks must call tss_search_run the same number of times.  The one-shot tss_solve_* calls never communicate.
+ * ranks must call tss_search_run the same number of times.  On grids larger than 32x32 (window decomposition) every rank
+ * additionally adopts the best LAYOUT of all ranks after each phase (a second all-reduce-min over the bit-packed layout
+ * in which only the winner contributes its bits).  The one-shot tss_solve_* calls never communicate.
  * NCCL is bound at run time (dlopen libnccl.so.2); TSS_E_UNSUPPORTED if it is not installed. */
 int tss_comm_unique_id(tss_engine* e, uint8_t* out_id128);
 int tss_comm_init(tss_engine* e, const uint8_t* id128, int32_t rank, int32_t world);

@@ -67,6 +67,19 @@ int comm_allreduce_min(tss_engine* e, Comm* c, int* dev, int n) {
     return TSS_OK;
 }
 
+// in-stream all-reduce-min of n uint32 words: src -> dst (the window-decomposed portfolio ships the winner's layout this
+// way: losers contribute all-ones, so the min is the winner's bitboard — no broadcast root has to be known on the host)
+int comm_allreduce_min_u32(tss_engine* e, Comm* c, const uint32_t* src, uint32_t* dst, int n) {
+    if (!c || c->world <= 1) return TSS_OK;
+    NcclApi* api = nccl_api();
+    int r = api->AllReduce(src, dst, (size_t)n, 3 /* ncclUint32 */, kNcclMin, c->comm, e->stream);
+    if (r != 0) return e->fail(TSS_E_CUDA, "ncclAllReduce failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?");
+    e->stats.kernel_launches++;
+    return TSS_OK;
+}
+int comm_rank(const Comm* c) { return c ? c->rank : 0; }
+int comm_world(const Comm* c) { return c ? c->world : 1; }
+
 }  // namespace tss
 
 using namespace tss;

@@ -25,7 +25,7 @@ int run_peaks(tss_engine* e, double* out, int n_out);
 struct LnsSearch;
 int lns_create(tss_engine* e, const uint8_t* grid, int w, int h, int seeds, uint64_t seed, uint32_t chain_offset, int noise, LnsSearch** out);
 void lns_destroy(LnsSearch* s);
-int lns_phase(tss_engine* e, LnsSearch* s, long long steps);
+int lns_phase(tss_engine* e, LnsSearch* s, long long steps, bool share);
 int lns_layout(tss_engine* e, LnsSearch* s, std::vector<uint32_t>& rows);
 int lns_count(const LnsSearch* s);
 unsigned long long lns_total(const LnsSearch* s, int i);
@@ -537,7 +537,7 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
     TSS_CUDA(e, cudaSetDevice(e->device));
     TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     if (s->lns) {  // one phase of the window decomposition
-        int rc = lns_phase(e, s->lns, steps);
+        int rc = lns_phase(e, s->lns, steps, s->share);
         if (rc) return rc;
         TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
         s->dirty = true;

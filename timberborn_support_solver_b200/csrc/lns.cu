@@ -111,6 +111,23 @@ __global__ void popcount_kernel(const uint32_t* __restrict__ X, int nw, int* __r
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
 }
 
+// ---- multi-GPU portfolio: after a phase every rank adopts the best layout of all ranks, all in-stream.
+// key = count * 64 + rank (unique per rank); all-reduce-min(key) names the winner; every rank then contributes its
+// layout if it is the winner and all-ones otherwise, so a second all-reduce-min (u32) over the 8 KB bitboard delivers
+// the winner's layout everywhere without a host-known broadcast root.
+__global__ void share_key_kernel(const int* __restrict__ count, int rank, uint32_t* __restrict__ key) { key[0] = (uint32_t)count[0] * 64u + (uint32_t)rank; }
+__global__ void share_select_kernel(const uint32_t* __restrict__ S, const uint32_t* __restrict__ key, const uint32_t* __restrict__ gkey, int nw,
+                                    uint32_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nw) out[i] = key[0] == gkey[0] ? S[i] : 0xffffffffu;
+}
+__global__ void share_adopt_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ gkey, int nw, uint32_t* __restrict__ S,
+                                   int* __restrict__ count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nw) S[i] = in[i];
+    if (i == 0) count[0] = (int)(gkey[0] >> 6);
+}
+
 }  // namespace lns
 
 struct LnsSearch {
@@ -125,6 +142,7 @@ struct LnsSearch {
     int* bounds = nullptr;
     unsigned long long* totals = nullptr;
     int* count_dev = nullptr;
+    uint32_t* key_dev = nullptr;                 // [2]: this rank's (count, rank) key and the global minimum
     int* count_host = nullptr;                   // pinned
     unsigned long long* totals_host = nullptr;   // pinned [2]
 };
@@ -132,7 +150,7 @@ struct LnsSearch {
 void lns_destroy(LnsSearch* s) {
     if (!s) return;
     cudaFree(s->C); cudaFree(s->S); cudaFree(s->F); cudaFree(s->T); cudaFree(s->rows_win); cudaFree(s->need_win); cudaFree(s->tabs);
-    cudaFree(s->states); cudaFree(s->best); cudaFree(s->bounds); cudaFree(s->totals); cudaFree(s->count_dev);
+    cudaFree(s->states); cudaFree(s->best); cudaFree(s->bounds); cudaFree(s->totals); cudaFree(s->count_dev); cudaFree(s->key_dev);
     if (s->count_host) cudaFreeHost(s->count_host);
     if (s->totals_host) cudaFreeHost(s->totals_host);
     delete s;
@@ -151,7 +169,7 @@ int lns_create(tss_engine* e, const uint8_t* grid, int w, int h, int seeds, uint
     A((void**)&s->rows_win, sizeof(uint32_t) * 32 * (size_t)s->max_windows); A((void**)&s->need_win, sizeof(uint32_t) * 32 * (size_t)s->max_windows);
     A((void**)&s->tabs, sizeof(uint2) * 1024 * (size_t)s->max_windows); A((void**)&s->states, sizeof(sls::ChainState) * nch);
     A((void**)&s->best, sizeof(int2) * (size_t)s->max_windows); A((void**)&s->bounds, sizeof(int) * (size_t)s->max_windows);
-    A((void**)&s->totals, sizeof(unsigned long long) * 2); A((void**)&s->count_dev, sizeof(int));
+    A((void**)&s->totals, sizeof(unsigned long long) * 2); A((void**)&s->count_dev, sizeof(int)); A((void**)&s->key_dev, sizeof(uint32_t) * 2);
     if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->count_host, sizeof(int), cudaHostAllocDefault);
     if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->totals_host, sizeof(unsigned long long) * 2, cudaHostAllocDefault);
     // the start layout: a support under every ceiling tile (trivially complete)
@@ -167,7 +185,7 @@ int lns_create(tss_engine* e, const uint8_t* grid, int w, int h, int seeds, uint
 }
 
 // One phase, asynchronous on the engine stream.
-int lns_phase(tss_engine* e, LnsSearch* s, long long steps) {
+int lns_phase(tss_engine* e, LnsSearch* s, long long steps, bool share) {
     static const int OFF[4][2] = {{0, 0}, {-16, -16}, {0, -16}, {-16, 0}};
     const int ox = OFF[s->phase & 3][0], oy = OFF[s->phase & 3][1];
     const uint32_t colmask = ox == 0 ? lns::CORE_COLS : ((lns::CORE_COLS >> 16) | (lns::CORE_COLS << 16));  // rotate by the offset
@@ -194,6 +212,17 @@ int lns_phase(tss_engine* e, LnsSearch* s, long long steps) {
     lns::popcount_kernel<<<32, 256, 0, e->stream>>>(s->S, s->nw, s->count_dev);
     TSS_CHECK_LAUNCH(e);
     e->stats.kernel_launches += 2;
+    if (share && e->comm && comm_world(e->comm) > 1) {  // every rank continues from the best layout of all ranks
+        lns::share_key_kernel<<<1, 1, 0, e->stream>>>(s->count_dev, comm_rank(e->comm), s->key_dev);
+        rc = comm_allreduce_min_u32(e, e->comm, s->key_dev, s->key_dev + 1, 1);
+        if (rc) return rc;
+        lns::share_select_kernel<<<gb, tb, 0, e->stream>>>(s->S, s->key_dev, s->key_dev + 1, s->nw, s->F);
+        rc = comm_allreduce_min_u32(e, e->comm, s->F, s->T, s->nw);
+        if (rc) return rc;
+        lns::share_adopt_kernel<<<gb, tb, 0, e->stream>>>(s->T, s->key_dev + 1, s->nw, s->S, s->count_dev);
+        TSS_CHECK_LAUNCH(e);
+        e->stats.kernel_launches += 3;
+    }
     TSS_CUDA(e, cudaMemcpyAsync(s->count_host, s->count_dev, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     TSS_CUDA(e, cudaMemcpyAsync(s->totals_host, s->totals, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, e->stream));
     s->phase++;
