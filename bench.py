@@ -186,6 +186,10 @@ def main():
     def step():
         search.run(args.epoch_steps, 0)
 
+    # mean |R(s)| of the terrain (SURVEY.md §8d asks for it beside the rate): one-support layouts through kernel (a)
+    one_hot = np.eye(grid.data.size, dtype=np.uint8).reshape(-1, grid.height, grid.width)
+    unc1, _ = eng.eval_sites(grid, one_hot)
+    mean_reach = float((int(grid.data.sum()) - unc1[grid.data.reshape(-1) != 0]).mean())
     for _ in range(W):
         step()
     search.best_count()        # synchronises and folds the warm-up's device counters into the stats BEFORE the baseline snapshot
@@ -230,6 +234,7 @@ def main():
         "config": {"workload": WORKLOAD, "chains_per_gpu": n_chains, "epoch_steps": args.epoch_steps, "parallelism": f"portfolio x{world} (independent seeds, all-reduce-min of the bound per step)", "exchange": exchange,
                    "l2": "flushed between timed steps (256 MiB memset outside the event pairs); the kernel's working set is registers + 16 KB smem per CTA"},
         "gpu_launches": int(launches_all), "best_count": best, "sls_steps_per_s": steps_all / (ms_total * 1e-3),
+        "flips_per_s": 2.0 * steps_all / (ms_total * 1e-3), "candidates_per_step": scored_all / max(steps_all, 1.0), "mean_reach": mean_reach,
         "wall_ms_total": t_wall * 1e3, "clocks": sampler.summary(),
     }
 

@@ -46,7 +46,7 @@ def test_eval_sites_small_grids_match_validate(eng, w, h):
         sites = random_sites(rng, 257, h, w, 0.08)
         sites[0] = 0                 # empty layout: everything unsupported
         sites[1] = 1                 # a support everywhere
-        unc, cnt = eng.eval_sites(T.WorldGrid(grid) if grid.any() or True else None, sites)
+        unc, cnt = eng.eval_sites(T.WorldGrid(grid), sites)
         o_unc, o_cnt, _ = O.validate_sites_batch(grid, sites)
         assert np.array_equal(unc, o_unc) and np.array_equal(cnt, o_cnt), (w, h, density)
         assert unc[0] == grid.sum() and unc[1] == 0

@@ -102,6 +102,12 @@ def load() -> C.CDLL:
     """Loads libtss.so and applies the signatures.  Raises if the library is missing — there is no fallback."""
     global _lib
     if _lib is None:
+        if not os.path.exists(LIB_PATH) and not os.environ.get("TSS_LIB"):
+            try:  # a fresh checkout has no artefact yet: compile it in-tree (nvcc, sm_100a) — building is not a fallback
+                from . import build as _build
+                _build.build()
+            except Exception as exc:  # noqa: BLE001
+                raise ImportError(f"{LIB_PATH} is missing and could not be built: {exc}.  The GPU path has no CPU fallback.") from exc
         if not os.path.exists(LIB_PATH):
             raise ImportError(f"{LIB_PATH} is missing: build it with `python -m timberborn_support_solver_b200.build` "
                               "(nvcc, sm_100a).  The GPU path has no CPU fallback.")

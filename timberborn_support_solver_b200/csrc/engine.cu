@@ -113,7 +113,6 @@ struct tss_search {
     std::vector<int2> key_dims;                // effective (w, h) per dims key: defs order, unflipped then flipped
     std::vector<tss_platform> key_proto;       // def dims + rotated flag per key
     std::vector<int> key_costs;                // objective cost per key: 1 = platform count; GUI weights via tss_search_set_weights
-    bool weighted = false;
     int2* keys_dev = nullptr;
     int* costs_dev = nullptr;
     void* mstates = nullptr;
@@ -722,7 +721,6 @@ int tss_search_set_weights(tss_search* s, const int32_t* weights, int32_t n_weig
         if (cost <= 0 || cost > 4096) return e->fail(TSS_E_UNSUPPORTED, "tss_search_set_weights: platform costs must be in 1..4096 (got %ld for %dx%d)", cost, def.w, def.h);
         s->key_costs[k] = (int)cost;
     }
-    s->weighted = true;
     TSS_CUDA(e, cudaMemcpy(s->costs_dev, s->key_costs.data(), sizeof(int) * s->key_costs.size(), cudaMemcpyHostToDevice));
     return TSS_OK;
 }

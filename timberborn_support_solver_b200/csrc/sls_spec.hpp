@@ -14,10 +14,10 @@
 // A step with bound L (smallest complete count known at the start of the epoch, or the chain's own best):
 //   1. k >= L                -> drop the support with the smallest loss (tiles only it covers), random ties
 //   2. U empty               -> record (k, S) as the chain's best; done if k <= target
-//   3. otherwise, if k == L-1 -> remove the min-loss support other than the one just added (tabu)
-//      then pick a random uncovered tile t and add the site v in R(t) with the largest gain |U & R(v)| (random
-//      ties; with probability ~noise% a uniformly random site of R(t) instead), never the site just removed unless
-//      it is the only candidate.
+//   3. otherwise, if k == L-1 -> remove the min-loss support (supports added fewer than T steps ago only as a last
+//      resort), then pick a random uncovered tile t and add the site v in R(t) with the largest gain |U & R(v)| (random
+//      ties; sites removed fewer than T steps ago only as a last resort; with probability ~noise% a uniformly random
+//      site of R(t) instead).  T is the chain's tabu tenure, see below.
 //
 // Random numbers are counter based, two hashes per step:
 //   hs = fmix32(base ^ step*K1)          one word per (chain, step): bits 0-4 row rotation, 5-9 column rotation,
@@ -76,8 +76,8 @@ struct ChainState {
     int32_t k;           // current number of supports
     int32_t best;        // supports in bestS, NO_BOUND if none yet
     uint32_t step;       // RNG step counter (persists across epochs)
-    int32_t tabu_add;    // site removed last (not re-added immediately), -1 none
-    int32_t tabu_rem;    // site added last (not removed immediately), -1 none
+    int32_t tabu_add;    // unused since the tenure stamps (kept for the 320-byte layout), -1
+    int32_t tabu_rem;    // unused, -1
     int32_t done;        // reached the target or nothing left to do
     uint32_t scored_lo, scored_hi;  // candidate layouts scored by this chain (64-bit counter)
     uint32_t steps_done;
