@@ -250,18 +250,21 @@ def main():
                             "peak_source": "measured in this run (tss_measure_peaks: dependent-free LOP3 chains at full occupancy)",
                             "note": "no dense contraction and ~0 HBM traffic in the step loop: the bound is integer issue + warp shuffles (SURVEY.md §8d); per-GPU figures"}
         line["measured_peaks"] = pk
-    if rank == 0 and not args.quick and world == 1:
-        hbm_peak, hbm_src = peaks()
-        # ---------------- time-to-optimal: fresh portfolio -> first layout with 15 supports (incl. create + host round trips)
+    if rank == 0:
+        # ---------------- time-to-optimal: fresh portfolio -> first layout with 15 supports (incl. host round trips); one GPU finds
+        # it in a fraction of a millisecond, so this is per rank and identical at every N (the one-shot solve never communicates)
         tto = []
-        for seed in range(5):
+        for seed in range(7):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             res, lay = eng.solve_upper_bound(grid, card_limit=OPTIMUM_RECT16, seed=100 + seed)
             tto.append((time.perf_counter() - t0) * 1e3)
             assert res == T.SAT and lay.platform_count() == OPTIMUM_RECT16
-        line["time_to_optimal_ms"] = float(np.median(tto))
-        line["time_to_optimal_note"] = "tss_solve_upper_bound(card_limit=15) from host buffers: create portfolio, epochs of 64.. steps, witness re-validated; median of 5 seeds"
+        line["time_to_optimal_ms"] = float(np.median(tto[2:]))
+        line["time_to_optimal_note"] = ("tss_solve_upper_bound(card_limit=15) from host buffers on one GPU: terrain upload, reach table, epochs of 64.. "
+                                        "steps, witness re-validated by kernel (a); median of 5 calls after 2 warm-up calls")
+    if rank == 0 and not args.quick and world == 1:
+        hbm_peak, hbm_src = peaks()
         # ---------------- kernel (a): stream 4 Mi candidate layouts (32 B each, 128 MiB > L2) from HBM
         n_lay = 4 << 20
         lay_dev = torch.randint(0, 1 << 16, (n_lay, 16), dtype=torch.int32, device="cuda")
