@@ -136,7 +136,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--epoch-steps", type=int, default=4096, help="SLS steps per chain per bench step")
-    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = SM count x 64: 32 warps per SM, two chains per warp on a 16-row grid)")
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = fill the device: 3 CTAs x 128 one-thread chains per SM)")
+    ap.add_argument("--kernel", type=int, default=0, help="SLS kernel variant (tss.h TSS_KERNEL_*: 0 auto, 1 warp, 2 half-warp, 3 thread)")
     ap.add_argument("--quick", action="store_true", help="skip the side measurements (peaks, eval/cnf kernels, cpu baseline)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -168,7 +169,6 @@ def main():
     eng.set_stream(stream.cuda_stream)
     info = eng.device_info()
     grid = T.WorldGrid(np.ones((16, 16), np.uint8))
-    n_chains = args.chains or info["sm_count"] * 64      # 16-row grid: two chains per warp, 32 warps per SM
     exchange = "none (single GPU)"
     if world > 1:
         # the path's one real exchange: an all-reduce-min of the best-known count (4 bytes, latency bound).  The engine does
@@ -180,7 +180,12 @@ def main():
         dist.broadcast(idt, src=0)
         eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
         exchange = "ncclAllReduce(min, 1 x int32) in-stream inside tss_search_run, bound stays in HBM"
-    search = eng.search(grid, seed=1, n_chains=n_chains, chain_offset=rank * n_chains)
+    n_chains = args.chains
+    if not n_chains:                 # engine default: fills the device for the chosen kernel
+        probe = eng.search(grid, kernel=args.kernel)
+        n_chains = probe.n_chains
+        probe.close()
+    search = eng.search(grid, seed=1, n_chains=n_chains, chain_offset=rank * n_chains, kernel=args.kernel)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def step():

@@ -188,8 +188,15 @@ typedef struct tss_search_params {
     int32_t n_chains;      /* independent layouts searched in parallel (one per warp); 0 = fill the device */
     int32_t chain_offset;  /* global index of this engine's first chain (rank * n_chains in a multi-GPU portfolio) */
     int32_t noise_pct;     /* probability (percent) of a random instead of greedy add move; < 0 = default */
-    int32_t reserved;
+    int32_t kernel;        /* TSS_KERNEL_*: which of the equivalent SLS kernels runs (same step rule, same trajectories); 0 = auto */
 } tss_search_params;
+
+/* SLS kernel variants for grids up to 32x32 with 1x1 supports.  All three execute the published step rule bit for bit
+ * (tests replay each against the CPU model); they differ in how a chain is mapped to the hardware. */
+#define TSS_KERNEL_AUTO 0
+#define TSS_KERNEL_WARP 1      /* one chain per warp, any grid up to 32x32 */
+#define TSS_KERNEL_HALF_WARP 2 /* two chains per warp, grids of at most 16 rows */
+#define TSS_KERNEL_THREAD 3    /* one chain per thread, grids of at most 16 rows x 26 columns */
 
 /* Creates a portfolio on one terrain.  defs must contain 1x1 (encoder.rs:564-566). */
 int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,

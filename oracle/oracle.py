@@ -296,7 +296,12 @@ def sls_model(grid, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, shar
     """Replays kernel (b)'s published step rule on the CPU.  epochs: [(steps, bound, target)].
     -> dict(S uint8[n,32,32], bestS, k, best, step, scored, steps)"""
     g = _grid(grid)
-    ep = np.ascontiguousarray(epochs, dtype=np.int64).reshape(-1, 3)
+    split = []   # spec: an epoch is at most 32768 steps (the 16-bit tabu stamps never wrap inside one); longer runs are consecutive epochs
+    for steps_, bound_, target_ in epochs:
+        while steps_ > 0:
+            split.append((min(steps_, 32768), bound_, target_))
+            steps_ -= 32768
+    ep = np.ascontiguousarray(split, dtype=np.int64).reshape(-1, 3)
     S = np.zeros((n_chains, 32, 32), np.uint8)
     bestS = np.zeros((n_chains, 32, 32), np.uint8)
     k = np.zeros(n_chains, np.int32)

@@ -247,18 +247,33 @@ def test_sls_rect16_and_readme_terrain(eng, readme):
     assert res == T.SAT and layout.platform_count() == 14                        # one better than the README transcript reached
 
 
-@pytest.mark.parametrize("shape,seed", [((16, 16), 1), ((21, 16), 5), ((32, 32), 9), ((6, 5), 3), ((13, 29), 2), ((32, 16), 4), ((20, 17), 6)])
-def test_sls_trajectories_bit_exact_vs_model(eng, fixtures, shape, seed):
-    """The kernels (one chain per warp; two chains per warp for grids of <= 16 rows) and the scalar CPU model
-    (oracle/sls_model.cpp) execute the same published step rule with the same counter-based RNG: every chain's
-    supports, best layout, counters and step count agree bit for bit across epochs."""
+TRAJECTORY_CASES = [((16, 16), 1), ((21, 16), 5), ((32, 32), 9), ((6, 5), 3), ((13, 29), 2), ((32, 16), 4), ((20, 17), 6), ((26, 16), 7), ((9, 12), 8)]
+
+
+def _kernels_for(shape):
+    w, h = shape
+    ks = [T.KERNEL_WARP]
+    if h <= 16:
+        ks.append(T.KERNEL_HALF_WARP)
+    if h <= 16 and w <= 26:
+        ks.append(T.KERNEL_THREAD)
+    return ks
+
+
+@pytest.mark.parametrize("shape,seed,kernel", [(sh, sd, k) for sh, sd in TRAJECTORY_CASES for k in _kernels_for(sh)])
+def test_sls_trajectories_bit_exact_vs_model(eng, fixtures, shape, seed, kernel):
+    """The three kernels (one chain per warp; two chains per warp for grids of <= 16 rows; one chain per thread for grids
+    of <= 16 rows x 26 columns) and the scalar CPU model (oracle/sls_model.cpp) execute the same published step rule with
+    the same counter-based RNG: every chain's supports, best layout, counters and step count agree bit for bit across epochs."""
     w, h = shape
     grid = {(16, 16): np.ones((16, 16), np.uint8), (21, 16): fixtures["ex2"], (6, 5): fixtures["ex1"].T.copy()}.get(shape)
     if grid is None:
         grid = synth_terrain(w, h, seed=1, t=4)
     n_chains, offset = 23, 100      # odd: the last warp of the half-warp kernel runs a single chain
+    if kernel == T.KERNEL_THREAD:
+        n_chains = 150              # two CTAs, the second one partially filled
     epochs = [(50, 1 << 20, 0), (300, 1 << 20, 0), (1000, 1 << 20, 0)]
-    s = eng.search(T.WorldGrid(grid), seed=seed, n_chains=n_chains, chain_offset=offset)
+    s = eng.search(T.WorldGrid(grid), seed=seed, n_chains=n_chains, chain_offset=offset, kernel=kernel)
     for steps, _, target in epochs:
         s.run(steps, target)
     got = s.read_chains()
@@ -272,6 +287,28 @@ def test_sls_trajectories_bit_exact_vs_model(eng, fixtures, shape, seed):
     assert np.array_equal(unpack(got["bestS"]), want["bestS"])
     assert s.best_count() == int(want["best"].min())
     s.close()
+
+
+def test_sls_long_epochs_split_at_32768_steps(eng):
+    """A run longer than 32768 steps is executed as consecutive epochs (16-bit tabu stamps never wrap inside one): the
+    thread-per-chain kernel (recent-removal ring instead of stamps) and the half-warp kernel still agree with the model."""
+    grid = np.ones((8, 8), np.uint8)
+    epochs = [(40000, 1 << 20, -1)]
+    want = O.sls_model(grid, 40, epochs, seed=11, chain_offset=0, share_bound=True)
+    for kernel in (T.KERNEL_HALF_WARP, T.KERNEL_THREAD):
+        s = eng.search(T.WorldGrid(grid), seed=11, n_chains=40, kernel=kernel)
+        s.run(40000, -1)
+        got = s.read_chains()
+        assert np.array_equal(got["k"], want["k"]) and np.array_equal(got["step"], want["step"]) and np.array_equal(got["scored"], want["scored"])
+        assert np.array_equal(got["best"], want["best"])
+        s.close()
+
+
+def test_kernel_variant_rejected_when_grid_does_not_fit(eng):
+    with pytest.raises(T.TssError):
+        eng.search(T.WorldGrid(np.ones((20, 20), np.uint8)), n_chains=8, kernel=T.KERNEL_THREAD)
+    with pytest.raises(T.TssError):
+        eng.search(T.WorldGrid(np.ones((16, 30), np.uint8).T.copy()), n_chains=8, kernel=T.KERNEL_HALF_WARP)   # 30 rows
 
 
 def test_sls_bound_sharing_and_determinism(eng):

@@ -32,7 +32,7 @@ class Stats(C.Structure):  # tss_stats
 
 class SearchParams(C.Structure):  # tss_search_params
     _fields_ = [("seed", C.c_uint64), ("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("noise_pct", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("kernel", C.c_int32)]
 
 
 # every symbol include/tss.h declares: name -> (restype, argtypes)

@@ -24,6 +24,7 @@ from ._lib import Dims as _Dims
 from ._lib import Platform as _Platform
 
 SAT, UNSAT, INTERRUPTED = "Sat", "Unsat", "Interrupted"  # rustsat SolverResult
+KERNEL_AUTO, KERNEL_WARP, KERNEL_HALF_WARP, KERNEL_THREAD = 0, 1, 2, 3  # tss.h TSS_KERNEL_*: equivalent SLS kernels
 
 
 class TssError(RuntimeError):
@@ -362,10 +363,11 @@ class DeviceCnf:
 class Search:
     """A device-resident SLS portfolio on one terrain (kernel (b))."""
 
-    def __init__(self, engine: "Engine", grid: WorldGrid, defs=PLATFORMS_DEFAULT[:1], seed=0, n_chains=0, chain_offset=0, noise_pct=-1):
+    def __init__(self, engine: "Engine", grid: WorldGrid, defs=PLATFORMS_DEFAULT[:1], seed=0, n_chains=0, chain_offset=0, noise_pct=-1, kernel=0):
+        """kernel: KERNEL_AUTO / KERNEL_WARP / KERNEL_HALF_WARP / KERNEL_THREAD (tss.h TSS_KERNEL_*): equivalent SLS kernels."""
         self.engine, self.grid = engine, grid
         self._h = C.c_void_p()
-        params = _lib.SearchParams(seed, n_chains, chain_offset, noise_pct, 0)
+        params = _lib.SearchParams(seed, n_chains, chain_offset, noise_pct, kernel)
         defs = list(defs)
         engine._check(engine.lib.tss_search_create(engine._h, _ptr(grid.data, C.c_uint8), grid.width, grid.height, _defs_array(defs), len(defs),
                                                    C.byref(params), C.byref(self._h)))

@@ -17,6 +17,13 @@ int sls_run(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls:
 int sls_best_reduce(tss_engine* e, const sls::ChainState* states, int chains_per_group, int n_chains, int n_groups, int2* out_dev,
                     int* bounds_dev);
 // sls_h16.cu — two chains per warp for grids of at most 16 rows (chains_per_terrain must be 0 or a multiple of 8)
+// sls_t16.cu — one chain per thread for grids of at most 16 rows x 26 columns (chains_per_terrain 0 or a multiple of the CTA size)
+bool sls_t16_fits(int w, int h);
+int sls_t16_cta_chains();
+size_t sls_t16_list_words(int n_chains);
+int sls_run_t16(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls::ChainState* states, uint32_t* site_lists, int n_chains,
+                int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
+                int noise_pct, unsigned long long* totals_dev);
 int sls_run_h16(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls::ChainState* states, int n_chains,
                 int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
                 int noise_pct, unsigned long long* totals_dev);
@@ -97,6 +104,8 @@ struct tss_search {
     uint32_t* rows_dev = nullptr;
     uint2* tabs_dev = nullptr;
     tss::sls::ChainState* states = nullptr;
+    uint32_t* site_lists = nullptr;            // [16*26][n_chains rounded to 32] support lists of the thread-per-chain kernel (allocated on first use)
+    int kernel = TSS_KERNEL_AUTO;              // tss_search_params.kernel
     unsigned long long* totals_dev = nullptr;  // [2]
     int2* best_dev = nullptr;                  // [n_groups]
     int* bounds_dev = nullptr;                 // [n_groups]
@@ -397,6 +406,7 @@ static void search_free(tss_search* s) {
     cudaFree(s->keys_dev);
     cudaFree(s->costs_dev);
     cudaFree(s->mstates);
+    cudaFree(s->site_lists);
     cudaFree(s->rows_dev); cudaFree(s->tabs_dev); cudaFree(s->states); cudaFree(s->totals_dev); cudaFree(s->best_dev); cudaFree(s->bounds_dev);
     if (s->best_host) cudaFreeHost(s->best_host);
     if (s->totals_host) cudaFreeHost(s->totals_host);
@@ -431,6 +441,13 @@ static int search_init_device(tss_engine* e, tss_search* s, int n_terrains) {
     return TSS_OK;
 }
 
+// Chains that fill the device: 32 warps per SM for the warp kernels (two chains per warp on grids of <= 16 rows),
+// 3 CTAs of 128 threads per SM for the thread-per-chain kernel.
+static int default_chains(const tss_engine* e, int w, int h, int kernel) {
+    const bool thread_default = sls_t16_fits(w, h) && (kernel == TSS_KERNEL_AUTO || kernel == TSS_KERNEL_THREAD);
+    return e->prop.multiProcessorCount * (thread_default ? 3 * sls_t16_cta_chains() : (h <= 16 ? 64 : 32));
+}
+
 int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,
                       const tss_search_params* params, tss_search** out) {
     if (!e) return TSS_E_INVALID;
@@ -459,7 +476,15 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
         return TSS_OK;
     }
     // default: 32 warps per SM (8 CTAs of 4 warps); grids of <= 16 rows run two chains per warp
-    s->n_chains = (params && params->n_chains > 0) ? params->n_chains : e->prop.multiProcessorCount * (h <= 16 ? 64 : 32);
+    // (thread-per-chain kernel: 3 CTAs of 128 chains per SM)
+    s->kernel = params ? params->kernel : TSS_KERNEL_AUTO;
+    if (s->kernel < TSS_KERNEL_AUTO || s->kernel > TSS_KERNEL_THREAD || (s->kernel == TSS_KERNEL_HALF_WARP && h > 16) ||
+        (s->kernel == TSS_KERNEL_THREAD && !sls_t16_fits(w, h))) {
+        int k = s->kernel;
+        delete s;
+        return e->fail(TSS_E_UNSUPPORTED, "tss_search_create: kernel variant %d does not support a %dx%d grid", k, w, h);
+    }
+    s->n_chains = (params && params->n_chains > 0) ? params->n_chains : default_chains(e, w, h, s->kernel);
     s->n_groups = 1;
     s->chains_per_terrain = 0;
     uint32_t rows[32] = {0};
@@ -529,6 +554,19 @@ void tss_sls_spec_probe(uint32_t* out) {
     out[5] = sls::step_hash(1u, 2u); out[6] = sls::lane_hash(3u, 4u); out[7] = sls::chain_base(0x0123456789abcdefull, 5u); out[8] = sls::NO_BOUND;
 }
 
+// Which of the three equivalent SLS kernels (same spec, same trajectories) advances this portfolio.
+static int search_kernel(const tss_search* s) {
+    const int cpt = s->chains_per_terrain;
+    const bool t16_ok = sls_t16_fits(s->w, s->h) && (cpt == 0 || cpt % sls_t16_cta_chains() == 0);
+    const bool h16_ok = s->h <= 16 && (cpt == 0 || cpt % 8 == 0);
+    if (s->kernel == TSS_KERNEL_THREAD && t16_ok) return TSS_KERNEL_THREAD;
+    if (s->kernel == TSS_KERNEL_WARP) return TSS_KERNEL_WARP;
+    if (s->kernel == TSS_KERNEL_HALF_WARP && h16_ok) return TSS_KERNEL_HALF_WARP;
+    // auto: a chain per thread pays off once there are enough chains to fill warps
+    if (s->kernel == TSS_KERNEL_AUTO && t16_ok && s->n_chains >= 1024) return TSS_KERNEL_THREAD;
+    return h16_ok ? TSS_KERNEL_HALF_WARP : TSS_KERNEL_WARP;
+}
+
 int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
     if (!s) return TSS_E_INVALID;
     tss_engine* e = s->e;
@@ -556,14 +594,24 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
         return TSS_OK;
     }
     int chains_per_group = s->n_groups == 1 ? s->n_chains : s->chains_per_terrain;
-    // grids of at most 16 rows: two chains per warp (same spec, same trajectories, half the instruction stream per chain)
-    const bool h16 = s->h <= 16 && (s->chains_per_terrain == 0 || s->chains_per_terrain % 8 == 0);
-    int rc = (h16 ? sls_run_h16 : sls_run)(e, s->rows_dev, s->tabs_dev, s->states, s->n_chains, s->chains_per_terrain, s->chain_offset, s->seed,
-                                           steps, s->bounds_dev, target_count < 0 ? -1 : target_count, s->noise, s->totals_dev);
-    if (rc == TSS_OK) rc = sls_best_reduce(e, s->states, chains_per_group, s->n_chains, s->n_groups, s->best_dev, s->bounds_dev);
-    // multi-GPU portfolio: the one exchange of the path, in-stream on the device-resident bound (no host round trip)
-    if (rc == TSS_OK && e->comm && s->share && s->n_groups == 1) rc = comm_allreduce_min(e, e->comm, s->bounds_dev, 1);
-    if (rc) return rc;
+    const int variant = search_kernel(s);
+    if (variant == TSS_KERNEL_THREAD && !s->site_lists) TSS_CUDA(e, cudaMalloc(&s->site_lists, sizeof(uint32_t) * sls_t16_list_words(s->n_chains)));
+    // an epoch is at most 32768 steps (the tabu stamps are 16 bit, sls_spec.hpp): longer runs are consecutive epochs
+    for (long long left = steps; left > 0; left -= sls::MAX_EPOCH_STEPS) {
+        const long long chunk = left < sls::MAX_EPOCH_STEPS ? left : sls::MAX_EPOCH_STEPS;
+        const int target = target_count < 0 ? -1 : target_count;
+        int rc;
+        if (variant == TSS_KERNEL_THREAD)
+            rc = sls_run_t16(e, s->rows_dev, s->tabs_dev, s->states, s->site_lists, s->n_chains, s->chains_per_terrain, s->chain_offset, s->seed, chunk,
+                             s->bounds_dev, target, s->noise, s->totals_dev);
+        else
+            rc = (variant == TSS_KERNEL_HALF_WARP ? sls_run_h16 : sls_run)(e, s->rows_dev, s->tabs_dev, s->states, s->n_chains, s->chains_per_terrain,
+                                                                          s->chain_offset, s->seed, chunk, s->bounds_dev, target, s->noise, s->totals_dev);
+        if (rc == TSS_OK) rc = sls_best_reduce(e, s->states, chains_per_group, s->n_chains, s->n_groups, s->best_dev, s->bounds_dev);
+        // multi-GPU portfolio: the one exchange of the path, in-stream on the device-resident bound (no host round trip)
+        if (rc == TSS_OK && e->comm && s->share && s->n_groups == 1) rc = comm_allreduce_min(e, e->comm, s->bounds_dev, 1);
+        if (rc) return rc;
+    }
     TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
     TSS_CUDA(e, cudaMemcpyAsync(s->best_host, s->best_dev, sizeof(int2) * (size_t)s->n_groups, cudaMemcpyDeviceToHost, e->stream));
     TSS_CUDA(e, cudaMemcpyAsync(s->totals_host, s->totals_dev, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, e->stream));
@@ -781,6 +829,10 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     int rc = TSS_OK;
     bool only_1x1 = true;
     for (int i = 0; i < n_defs; i++) only_1x1 = only_1x1 && defs && defs[i].w == 1 && defs[i].h == 1;
+    if (e->cached_search && e->cached_search->n_chains != default_chains(e, w, h, TSS_KERNEL_AUTO)) {  // sized for another grid class
+        search_free(e->cached_search);
+        e->cached_search = nullptr;
+    }
     if (e->cached_search && grid && w > 0 && h > 0 && w <= 32 && h <= 32 && only_1x1) {
         // reuse the engine's workspace: same buffers, fresh terrain / reach table / chain states (no allocation)
         s = e->cached_search;

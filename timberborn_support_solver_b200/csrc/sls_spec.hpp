@@ -36,6 +36,7 @@ constexpr uint32_t K1 = 0x9E3779B9u, K2 = 0x85EBCA6Bu;
 constexpr int DEFAULT_NOISE_PCT = 20;
 constexpr int MAX_SITES = 1024;   // supports per chain (<= tiles of a 32x32 grid)
 constexpr int NO_BOUND = 1 << 20;
+constexpr long long MAX_EPOCH_STEPS = 32768;  // steps per epoch (kernel launch): the 16-bit tabu stamps never wrap inside one
 
 #if defined(__CUDACC__)
 #define TSS_HD __host__ __device__ __forceinline__
