@@ -15,16 +15,15 @@
 
 namespace {
 
-constexpr uint32_t K1 = 0x9E3779B9u, K2 = 0x85EBCA6Bu;
+constexpr uint32_t K1 = 0x9E3779B9u, K2 = 0x85EBCA6Bu, K3 = 0xC2B2AE35u;
 constexpr int NO_BOUND = 1 << 20;
 
 uint32_t fmix32(uint32_t h) { h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h; }
 uint32_t chain_base(uint64_t seed, uint32_t chain) { return fmix32((uint32_t)seed ^ fmix32((uint32_t)(seed >> 32) + chain * K1 + 0x5bd1e995u)); }
 uint32_t step_hash(uint32_t base, uint32_t step) { return fmix32(base ^ (step * K1)); }
-uint32_t lane_hash(uint32_t hs, uint32_t lane) { return fmix32(hs ^ ((lane + 1u) * K2)); }
 uint32_t noise_q7(int noise_pct) { return (uint32_t)((noise_pct * 128 + 50) / 100); }
-uint32_t tie_add(uint32_t hl) { return hl & 0xffffu; }
-uint32_t tie_remove(uint32_t hl, uint32_t chunk) { return (hl * (2u * chunk + 1u)) >> 16; }
+uint32_t tie_add(uint32_t hs, uint32_t cell) { return (hs * ((2u * cell + 1u) * K2)) >> 16; }
+uint32_t tie_remove(uint32_t hs, uint32_t i) { return (hs * ((2u * i + 1u) * K3)) >> 16; }
 constexpr uint32_t TABU_BIT = 0x40000000u;
 int tenure_of(uint32_t global_chain) { static const int t[4] = {3, 6, 12, 20}; return t[global_chain & 3u]; }
 int effective_tenure(int tenure, int k) { int c = k / 3; c = c < 2 ? 2 : c; return tenure < c ? tenure : c; }
@@ -90,10 +89,10 @@ struct Runner {
     int remove_min_loss(bool use_tabu, uint32_t hs) {
         uint32_t best_key = 0xffffffffu;
         int best_i = 0;
-        for (int i = 0; i < c.k; i++) {  // chunks of 32 lanes, lowest lane wins ties; strict < across chunks
+        for (int i = 0; i < c.k; i++) {  // lowest list index wins ties
             int v = c.sites[i];
             uint32_t young = (use_tabu && is_tabu(c.step, c.stamp[v], ten)) ? TABU_BIT : 0u;  // young supports only as a last resort
-            uint32_t key = young | ((uint32_t)loss(v) << 16) | tie_remove(lane_hash(hs, (uint32_t)(i & 31)), (uint32_t)(i >> 5));
+            uint32_t key = young | ((uint32_t)loss(v) << 16) | tie_remove(hs, (uint32_t)i);
             if (key < best_key) { best_key = key; best_i = i; }
         }
         int u = c.sites[best_i];
@@ -160,7 +159,7 @@ struct Runner {
             uint32_t mx = 0;
             bool first = true;
             for (auto& [cv, ln] : cand) {
-                uint32_t tie = tie_add(lane_hash(hs, (uint32_t)ln));
+                uint32_t tie = tie_add(hs, (uint32_t)ln);
                 uint32_t fresh = is_tabu(c.step, c.stamp[cv], ten) ? 0u : TABU_BIT;  // recently removed sites only as a last resort
                 uint32_t key = noise ? (0x10000u | tie) : (fresh | ((uint32_t)(gain(cv) + 1) << 16) | tie);
                 if (first || key > mx) { mx = key; v = cv; first = false; }
@@ -212,8 +211,8 @@ int tsso_sls_model(const uint8_t* grid, int w, int h, int n_chains, uint32_t cha
 
 // constants of the spec, for the agreement test against sls_spec.hpp
 void tsso_sls_constants(uint32_t* out) {
-    out[0] = K1; out[1] = K2; out[2] = noise_q7(20); out[3] = tie_remove(0x12345678u, 3) + 1000u * (uint32_t)(tenure_of(0) + 2 * tenure_of(1) + 3 * tenure_of(2) + 4 * tenure_of(3)) + (is_tabu(70000u, stamp_reset(70000u), 20) ? 1u : 0u) + (is_tabu(65540u, (uint16_t)65530u, 12) ? 2u : 0u) + 100000u * (uint32_t)(effective_tenure(20, 14) + effective_tenure(3, 100) + effective_tenure(6, 2)); out[4] = tie_add(0x12345678u);
-    out[5] = step_hash(1u, 2u); out[6] = lane_hash(3u, 4u); out[7] = chain_base(0x0123456789abcdefull, 5u); out[8] = NO_BOUND;
+    out[0] = K1; out[1] = K2; out[2] = noise_q7(20); out[3] = tie_remove(0x12345678u, 3) + 1000u * (uint32_t)(tenure_of(0) + 2 * tenure_of(1) + 3 * tenure_of(2) + 4 * tenure_of(3)) + (is_tabu(70000u, stamp_reset(70000u), 20) ? 1u : 0u) + (is_tabu(65540u, (uint16_t)65530u, 12) ? 2u : 0u) + 100000u * (uint32_t)(effective_tenure(20, 14) + effective_tenure(3, 100) + effective_tenure(6, 2)); out[4] = tie_add(0x12345678u, 7u);
+    out[5] = step_hash(1u, 2u); out[6] = tie_remove(3u, 40u) ^ K3; out[7] = chain_base(0x0123456789abcdefull, 5u); out[8] = NO_BOUND;
 }
 
 }  // extern "C"

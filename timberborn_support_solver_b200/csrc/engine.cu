@@ -550,8 +550,8 @@ void tss_sls_spec_probe(uint32_t* out) {
     if (!out) return;
     out[0] = sls::K1; out[1] = sls::K2; out[2] = sls::noise_q7(20); out[3] = sls::tie_remove(0x12345678u, 3) + 1000u * (uint32_t)(sls::tenure_of(0) + 2 * sls::tenure_of(1) + 3 * sls::tenure_of(2) + 4 * sls::tenure_of(3)) +
              (sls::is_tabu(70000u, sls::stamp_reset(70000u), 20) ? 1u : 0u) + (sls::is_tabu(65540u, (uint16_t)65530u, 12) ? 2u : 0u) +
-             100000u * (uint32_t)(sls::effective_tenure(20, 14) + sls::effective_tenure(3, 100) + sls::effective_tenure(6, 2)); out[4] = sls::tie_add(0x12345678u);
-    out[5] = sls::step_hash(1u, 2u); out[6] = sls::lane_hash(3u, 4u); out[7] = sls::chain_base(0x0123456789abcdefull, 5u); out[8] = sls::NO_BOUND;
+             100000u * (uint32_t)(sls::effective_tenure(20, 14) + sls::effective_tenure(3, 100) + sls::effective_tenure(6, 2)); out[4] = sls::tie_add(0x12345678u, 7u);
+    out[5] = sls::step_hash(1u, 2u); out[6] = sls::tie_remove(3u, 40u) ^ sls::K3; out[7] = sls::chain_base(0x0123456789abcdefull, 5u); out[8] = sls::NO_BOUND;
 }
 
 // Which of the three equivalent SLS kernels (same spec, same trajectories) advances this portfolio.

@@ -123,17 +123,17 @@ struct WarpCtx {
 // Removes the support with the smallest loss (random ties); supports added fewer than `tenure` steps ago are only
 // chosen when every support is that young (use_tabu = false when dropping).  Returns the removed site.  Scores k
 // candidate layouts.
-__device__ __forceinline__ int remove_min_loss(Lane& L, const WarpCtx& w, int& k, uint32_t hl, uint32_t step, int ten, bool use_tabu) {
+__device__ __forceinline__ int remove_min_loss(Lane& L, const WarpCtx& w, int& k, uint32_t hs, uint32_t step, int ten, bool use_tabu) {
     uint32_t best_key = 0xffffffffu;
     int best_i = 0;
-    for (int b = 0, chunk = 0; b < k; b += 32, chunk++) {
+    for (int b = 0; b < k; b += 32) {
         int i = b + w.lane;
         bool valid = i < k;
         int v = valid ? w.sites[i] : 0;
         uint2 win = w.tab[v];
         int loss = score(L.O, v & 31, v >> 5, win);
         const uint32_t young = (use_tabu && is_tabu(step, w.stamps[v], ten)) ? TABU_BIT : 0u;
-        uint32_t key = valid ? (young | ((uint32_t)loss << 16) | tie_remove(hl, (uint32_t)chunk)) : 0xffffffffu;
+        uint32_t key = valid ? (young | ((uint32_t)loss << 16) | tie_remove(hs, (uint32_t)i)) : 0xffffffffu;
         uint32_t mn = __reduce_min_sync(FULL, key);
         if (mn < best_key) {
             best_key = mn;
@@ -217,12 +217,12 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_kernel(const uint32_t* __re
         if ((it & 1023) == 1023 && *interrupt) break;
         const int limit = min(epoch_bound, best);
         const uint32_t hs = step_hash(base, step);
-        const uint32_t hl = lane_hash(hs, (uint32_t)lane);
+        const uint32_t tie = tie_add(hs, (uint32_t)lane);
         const int ten = effective_tenure(w.tenure, k);  // fixed for the whole step
         if (k >= limit) {  // 1. too many supports for an improvement: drop one
             if (k == 0) { done = 1; break; }
             scored += (unsigned)k;
-            remove_min_loss(L, w, k, hl, step, ten, false);
+            remove_min_loss(L, w, k, hs, step, ten, false);
             continue;
         }
         if (!__any_sync(FULL, L.U != 0)) {  // 2. complete layout with k < limit supports
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_kernel(const uint32_t* __re
         }
         if (k == limit - 1 && k > 0) {  // 3. at capacity: swap = remove + add
             scored += (unsigned)k;
-            remove_min_loss(L, w, k, hl, step, ten, true);
+            remove_min_loss(L, w, k, hs, step, ten, true);
         }
         const uint32_t rowmask = __ballot_sync(FULL, L.U != 0);
         const int y = pick_rotated(rowmask, hs & 31u);
@@ -248,11 +248,11 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_kernel(const uint32_t* __re
         if (WINDOW && nc == 0) { done = 1; break; }  // cannot happen from a complete start layout; never spin on it
         uint32_t key;
         if (((hs >> 10) & 127u) < nq7) {  // noise: uniformly random site of R(t)
-            key = valid ? (0x10000u | tie_add(hl)) : 0u;
+            key = valid ? (0x10000u | tie) : 0u;
         } else {
             int g = score(L.U, cv & 31, cv >> 5, tab[cv]);
             const uint32_t fresh = is_tabu(step, w.stamps[cv], ten) ? 0u : TABU_BIT;  // recently removed sites only as a last resort
-            key = valid ? (fresh | ((uint32_t)(g + 1) << 16) | tie_add(hl)) : 0u;
+            key = valid ? (fresh | ((uint32_t)(g + 1) << 16) | tie) : 0u;
             scored += (unsigned)nc;
         }
         const uint32_t mx = __reduce_max_sync(FULL, key);

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_h16_kernel(const uint32_t* 
                 const bool valid = i < kk;
                 const int v = valid ? sites[i] : 0;
                 const int loss = score16(L.O, v & 31, v >> 5, tab[v]);
-                const uint32_t tie = tie_remove(lane_hash(hs, (uint32_t)(i & 31)), (uint32_t)(i >> 5));
+                const uint32_t tie = tie_remove(hs, (uint32_t)i);
                 const uint32_t young = (!drop && is_tabu(step, stamps[v], ten)) ? TABU_BIT : 0u;
                 const uint32_t key = valid ? (young | ((uint32_t)loss << 16) | tie) : 0xffffffffu;
                 const uint32_t mn = half_min(key);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_h16_kernel(const uint32_t* 
             const uint32_t vb0 = (__ballot_sync(FULL, v0) >> hshift) & 0xffffu, vb1 = (__ballot_sync(FULL, v1) >> hshift) & 0xffffu;
             const int nc = __popc(vb0) + __popc(vb1);
             const bool noise = ((hs >> 10) & 127u) < nq7;
-            const uint32_t t0 = tie_add(lane_hash(hs, (uint32_t)row)), t1 = tie_add(lane_hash(hs, (uint32_t)(16 + row)));
+            const uint32_t t0 = tie_add(hs, (uint32_t)row), t1 = tie_add(hs, (uint32_t)(16 + row));
             uint32_t key0, key1;
             if (__any_sync(FULL, adding && !noise)) {
                 const int g0 = score16(L.U, cv0 & 31, cv0 >> 5, tab[cv0]);

@@ -147,7 +147,7 @@ __device__ __forceinline__ int remove_min_loss(Lane& L, const Ctx& c, int& k, ui
         unpack(c, code, x, y, w, h);
         bool ov;
         int loss = score_placement(L.C, L.O, 0u, x, y, w, h, ov);
-        uint32_t key = (valid && !(code == exclude && k > 1)) ? (((uint32_t)loss << 16) | sls::tie_remove(hl, (uint32_t)chunk)) : 0xffffffffu;
+        uint32_t key = (valid && !(code == exclude && k > 1)) ? (((uint32_t)loss << 16) | sls::tie_remove_hl(hl, (uint32_t)chunk)) : 0xffffffffu;
         uint32_t mn = __reduce_min_sync(FULL, key);
         if (mn < best_key) { best_key = mn; best_i = b + __ffs(__ballot_sync(FULL, key == mn)) - 1; }
     }

@@ -19,12 +19,13 @@
 //      ties; sites removed fewer than T steps ago only as a last resort; with probability ~noise% a uniformly random
 //      site of R(t) instead).  T is the chain's tabu tenure, see below.
 //
-// Random numbers are counter based, two hashes per step:
+// Random numbers are counter based, one hash per step plus one multiply per candidate:
 //   hs = fmix32(base ^ step*K1)          one word per (chain, step): bits 0-4 row rotation, 5-9 column rotation,
 //                                        10-16 noise draw (7 bits, compared with noise_q7 = round(noise% * 1.28))
-//   hl = fmix32(hs ^ (lane+1)*K2)        one word per lane: bits 0-15 break ties among ADD candidates (lane = index in
-//                                        the 25-tile diamond), bits 16-31 among REMOVE candidates (site list index i,
-//                                        lane = i % 32, for i >= 32 the word is multiplied by the odd number 2*(i/32)+1)
+//   tie_add(hs, c)    = (hs * ((2c+1)*K2)) >> 16   breaks ties among ADD candidates, c = index in the 25-tile diamond
+//   tie_remove(hs, i) = (hs * ((2i+1)*K3)) >> 16   breaks ties among REMOVE candidates, i = index in the site list
+//   (multiplicative hashing of the step word by distinct odd constants; candidates that still tie are resolved to the
+//   lowest index).  One multiply per candidate keeps the tie-break off the integer-ALU pipe, which bounds the kernels.
 // base is keyed by (seed, global chain index), so a run is reproducible for a fixed chain numbering.
 #pragma once
 #include <cstdint>
@@ -32,7 +33,7 @@
 namespace tss {
 namespace sls {
 
-constexpr uint32_t K1 = 0x9E3779B9u, K2 = 0x85EBCA6Bu;
+constexpr uint32_t K1 = 0x9E3779B9u, K2 = 0x85EBCA6Bu, K3 = 0xC2B2AE35u;
 constexpr int DEFAULT_NOISE_PCT = 20;
 constexpr int MAX_SITES = 1024;   // supports per chain (<= tiles of a 32x32 grid)
 constexpr int NO_BOUND = 1 << 20;
@@ -54,8 +55,9 @@ TSS_HD uint32_t chain_base(uint64_t seed, uint32_t chain) {
 TSS_HD uint32_t step_hash(uint32_t base, uint32_t step) { return fmix32(base ^ (step * K1)); }
 TSS_HD uint32_t lane_hash(uint32_t hs, uint32_t lane) { return fmix32(hs ^ ((lane + 1u) * K2)); }
 TSS_HD uint32_t noise_q7(int noise_pct) { return (uint32_t)((noise_pct * 128 + 50) / 100); }
-TSS_HD uint32_t tie_add(uint32_t hl) { return hl & 0xffffu; }
-TSS_HD uint32_t tie_remove(uint32_t hl, uint32_t chunk) { return (hl * (2u * chunk + 1u)) >> 16; }
+TSS_HD uint32_t tie_add(uint32_t hs, uint32_t cell) { return (hs * ((2u * cell + 1u) * K2)) >> 16; }
+TSS_HD uint32_t tie_remove(uint32_t hs, uint32_t i) { return (hs * ((2u * i + 1u) * K3)) >> 16; }
+TSS_HD uint32_t tie_remove_hl(uint32_t hl, uint32_t chunk) { return (hl * (2u * chunk + 1u)) >> 16; }  // placement search (sls_multi.cu)
 
 // Tabu with tenure (the single most effective ingredient on fragmented terrains): a site flipped
 // (added or removed) fewer than T steps ago is tabu — a recently added support is not removed, a recently removed site

@@ -32,72 +32,65 @@ using namespace tss::sls;
 constexpr int NT = 128;          // chains per CTA
 constexpr int MAXW = 26;         // 3 + w + 3 <= 32 bits
 constexpr uint32_t NONE = 0xffffu;
+constexpr int TAB_PAD = 128;     // table entries before / after the 512 real ones (candidate sites outside the grid index there)
+// boards, 16 rows each, back to back: rows outside [0, 16) of a board alias its neighbours — harmless, because out-of-grid
+// rows only ever meet zero window bits (reads) or a zero mask (no write)
+enum { B_C0 = 0, B_C1 = 1, B_C2 = 2, B_U = 3, B_O = 4, B_C3 = 5, B_C4 = 6, N_BOARDS = 7 };
 
-struct Board {
-    uint32_t w[16][NT];
-};
 struct Smem {
-    uint2 tab[512];              // reach windows of the 16x32 sites, anchored at x-3
-    uint32_t C[16];              // terrain rows, columns shifted by 3
-    Board U, O, c0, c1, c2, c3, c4;
-    uint16_t ring[32][NT];       // site removed at step s in slot s & 31 (NONE if none)
+    uint2 tab[512 + 2 * TAB_PAD];          // reach windows of the 16x32 sites, anchored at x-3; entry of site v at v + TAB_PAD
+    uint32_t C[16];                        // terrain rows, columns shifted by 3
+    uint32_t rows[N_BOARDS * 16][NT];      // [board][row][thread]: bank = thread, conflict free for any row index
+    uint16_t ring[32][NT];                 // site removed at step s in slot s & 31 (NONE if none)
 };
+constexpr int BOARD = 16 * NT;             // words between the same row of consecutive boards
 
 __device__ __forceinline__ int pick_rotated(uint32_t bits, uint32_t o) {
     uint32_t rot = __funnelshift_r(bits, bits, o);
     return (int)((__ffs(rot) - 1 + o) & 31u);
 }
 
-// popcount(B & R(site (x, y))): every thread scores its own site on its own board
-__device__ __forceinline__ int score(const Board& B, int tid, int x, int y, uint2 win) {
-    uint32_t lo = 0, hi = 0;
-#pragma unroll
-    for (int j = 6; j >= 4; j--) hi = hi * 128u + ((B.w[(y - 3 + j) & 15][tid] >> x) & 0x7fu);
-#pragma unroll
-    for (int j = 3; j >= 0; j--) lo = lo * 128u + ((B.w[(y - 3 + j) & 15][tid] >> x) & 0x7fu);
-    return __popc(lo & win.x) + __popc(hi & win.y);
-}
-
 // adds (ADD) or removes the cover of site v on the five count planes and refreshes U, O and the non-empty-row mask
 template <bool ADD>
 __device__ __forceinline__ void flip(Smem& sm, int tid, int v, uint32_t& rowmask) {
     const int x = v & 31, y = v >> 5;
-    const uint2 win = sm.tab[v];
+    const uint2 win = sm.tab[v + TAB_PAD];
+    uint32_t* p = &sm.rows[0][tid] + y * NT;  // row y of the first board
 #pragma unroll
     for (int j = 0; j < 7; j++) {
-        const int r = (y - 3 + j) & 15;
-        uint32_t m = ((j < 4 ? win.x >> (7 * j) : win.y >> (7 * (j - 4))) & 0x7fu) << x;
-        uint32_t a0 = sm.c0.w[r][tid], a1 = sm.c1.w[r][tid], a2 = sm.c2.w[r][tid], t;
-        if (ADD) {
-            t = a0 & m; a0 ^= m; m = t;
-            t = a1 & m; a1 ^= m; m = t;
-            t = a2 & m; a2 ^= m; m = t;
-        } else {
-            t = ~a0 & m; a0 ^= m; m = t;
-            t = ~a1 & m; a1 ^= m; m = t;
-            t = ~a2 & m; a2 ^= m; m = t;
+        const uint32_t m7 = (j < 4 ? win.x >> (7 * j) : win.y >> (7 * (j - 4))) & 0x7fu;
+        if (m7) {  // (rows outside the grid have no window bits: every access below is inside the boards)
+            const int off = (j - 3) * NT;
+            uint32_t m = m7 << x;
+            uint32_t a0 = p[B_C0 * BOARD + off], a1 = p[B_C1 * BOARD + off], a2 = p[B_C2 * BOARD + off], t;
+            uint32_t a3 = p[B_C3 * BOARD + off], a4 = p[B_C4 * BOARD + off];
+            if (ADD) {
+                t = a0 & m; a0 ^= m; m = t;
+                t = a1 & m; a1 ^= m; m = t;
+                t = a2 & m; a2 ^= m; m = t;
+            } else {
+                t = ~a0 & m; a0 ^= m; m = t;
+                t = ~a1 & m; a1 ^= m; m = t;
+                t = ~a2 & m; a2 ^= m; m = t;
+            }
+            p[B_C0 * BOARD + off] = a0; p[B_C1 * BOARD + off] = a1; p[B_C2 * BOARD + off] = a2;
+            if (m) {  // a count crossing 7 <-> 8: rare
+                if (ADD) { t = a3 & m; a3 ^= m; a4 ^= t; } else { t = ~a3 & m; a3 ^= m; a4 ^= t; }
+                p[B_C3 * BOARD + off] = a3; p[B_C4 * BOARD + off] = a4;
+            }
+            const uint32_t hi = a1 | a2 | a3 | a4, C = sm.C[y - 3 + j];
+            const uint32_t Un = C & ~(a0 | hi);
+            p[B_U * BOARD + off] = Un;
+            p[B_O * BOARD + off] = a0 & ~hi & C;
+            const uint32_t bit = 1u << (y - 3 + j);
+            rowmask = Un ? (rowmask | bit) : (rowmask & ~bit);
         }
-        sm.c0.w[r][tid] = a0; sm.c1.w[r][tid] = a1; sm.c2.w[r][tid] = a2;
-        uint32_t a3 = sm.c3.w[r][tid], a4 = sm.c4.w[r][tid];
-        if (m) {  // a count crossing 7 <-> 8: rare
-            if (ADD) { t = a3 & m; a3 ^= m; a4 ^= t; } else { t = ~a3 & m; a3 ^= m; a4 ^= t; }
-            sm.c3.w[r][tid] = a3; sm.c4.w[r][tid] = a4;
-        }
-        const uint32_t hi = a1 | a2 | a3 | a4, C = sm.C[r];
-        const uint32_t Un = C & ~(a0 | hi);
-        sm.U.w[r][tid] = Un;
-        sm.O.w[r][tid] = a0 & ~hi & C;
-        rowmask = Un ? (rowmask | (1u << r)) : (rowmask & ~(1u << r));
     }
 }
 
-__device__ __forceinline__ constexpr int cell_dy(int i) { return (i >= 1) + (i >= 4) + (i >= 9) + (i >= 16) + (i >= 21) + (i >= 24) - 3; }
-__device__ __forceinline__ constexpr int cell_dx(int i) {
-    const int r = cell_dy(i) + 3;
-    const int start = r <= 4 ? r * r : (r == 5 ? 21 : 24);
-    const int ady = r >= 3 ? r - 3 : 3 - r;
-    return (i - start) - (3 - ady);
-}
+__device__ __forceinline__ constexpr int cell_start(int r) { return r <= 4 ? r * r : (r == 5 ? 21 : 24); }   // first diamond cell of window row r
+__device__ __forceinline__ constexpr int iabs(int a) { return a < 0 ? -a : a; }
+__device__ __forceinline__ constexpr int cell_index(int dx, int dy) { return cell_start(dy + 3) + dx + (3 - iabs(dy)); }
 __device__ __forceinline__ uint32_t shift_static(uint32_t v, int s) { return s >= 0 ? v << s : v >> (-s); }
 
 // rows of the support bitboard of a site list (rare path: recording a best layout, writing the state back)
@@ -111,6 +104,48 @@ __device__ __noinline__ void list_to_rows(const uint32_t* sl, size_t stride, int
     for (int r = 0; r < 16; r++) out32[r] = rows[r];
 }
 
+// One ADD candidate: the site at offset (DX, DY) from the uncovered tile.  P = the 7-bit column slab of U for this DX
+// (P[j] = columns x+DX-3 .. x+DX+3 of row y-6+j).  Keys are unique per cell (the cell index sits in the low bits), so
+// the maximum is independent of the evaluation order and ties go to the lowest cell as the spec demands.
+template <int DX, int DY>
+__device__ __forceinline__ uint32_t add_key(const Smem& sm, const uint32_t (&P)[13], const uint2* tabt, uint2 wt, uint32_t fresh_lo, uint32_t fresh_hi,
+                                            uint32_t hs, bool noise) {
+    constexpr int cell = cell_index(DX, DY), bit = 7 * (DY + 3) + DX + 3;
+    const uint2 win = tabt[DY * 32 + DX];
+    const uint32_t lo = ((P[DY + 6] * 128u + P[DY + 5]) * 128u + P[DY + 4]) * 128u + P[DY + 3];
+    const uint32_t hi = (P[DY + 9] * 128u + P[DY + 8]) * 128u + P[DY + 7];
+    const uint32_t g = (uint32_t)(__popc(lo & win.x) + __popc(hi & win.y));
+    const uint32_t tie = ((hs * ((2u * cell + 1u) * K2)) >> 11) & 0x1fffe0u;             // tie_add(hs, cell) << 5
+    const uint32_t fresh = shift_static(bit < 28 ? fresh_lo : fresh_hi, 30 - (bit < 28 ? bit : bit - 28)) & TABU_BIT;
+    const uint32_t greedy = (fresh | tie) + g * (1u << 21) + ((1u << 21) | (31u - cell));
+    const uint32_t key = noise ? (tie | (1u << 21) | (31u - cell)) : greedy;
+    const bool valid = ((bit < 28 ? wt.x >> bit : wt.y >> (bit - 28)) & 1u) != 0;
+    return valid ? key : 0u;
+}
+
+template <int DX>
+__device__ __forceinline__ uint32_t add_column(const Smem& sm, const uint32_t (&R)[13], const uint2* tabt, uint2 wt, uint32_t fresh_lo, uint32_t fresh_hi,
+                                               uint32_t hs, bool noise) {
+    constexpr int M = 3 - iabs(DX);
+    uint32_t P[13];
+#pragma unroll
+    for (int j = 3 - M; j <= 9 + M; j++) P[j] = (R[j] >> (DX + 3)) & 0x7fu;
+    uint32_t mx = add_key<DX, 0>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise);
+    if (M >= 1) {
+        mx = max(mx, add_key<DX, (M >= 1 ? -1 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+        mx = max(mx, add_key<DX, (M >= 1 ? 1 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+    }
+    if (M >= 2) {
+        mx = max(mx, add_key<DX, (M >= 2 ? -2 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+        mx = max(mx, add_key<DX, (M >= 2 ? 2 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+    }
+    if (M >= 3) {
+        mx = max(mx, add_key<DX, (M >= 3 ? -3 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+        mx = max(mx, add_key<DX, (M >= 3 ? 3 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+    }
+    return mx;
+}
+
 __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restrict__ terrain_rows, const uint2* __restrict__ rtabs,
                                                        ChainState* __restrict__ states, uint32_t* __restrict__ site_lists, size_t stride,
                                                        int n_chains, int chains_per_terrain, uint32_t chain_offset, uint64_t seed,
@@ -121,17 +156,19 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
     const int tid = threadIdx.x;
     const int chain = blockIdx.x * NT + tid;
     const int terrain = chains_per_terrain > 0 ? (blockIdx.x * NT) / chains_per_terrain : 0;
-    for (int i = tid; i < 512; i += NT) {
-        const uint2 s = rtabs[(size_t)terrain * 1024 + i];
-        const int x = i & 31, sh = x < 3 ? 3 - x : 0;  // table windows are anchored at max(x-3, 0): re-anchor at x-3
-        sm.tab[i] = make_uint2(s.x << sh, s.y << sh);
+    for (int i = tid; i < 512 + 2 * TAB_PAD; i += NT) {
+        const int v = i - TAB_PAD;
+        uint2 s = make_uint2(0u, 0u);
+        if (v >= 0 && v < 512) {
+            s = rtabs[(size_t)terrain * 1024 + v];
+            const int x = v & 31, sh = x < 3 ? 3 - x : 0;  // table windows are anchored at max(x-3, 0): re-anchor at x-3
+            s = make_uint2(s.x << sh, s.y << sh);
+        }
+        sm.tab[i] = s;
     }
     if (tid < 16) sm.C[tid] = terrain_rows[(size_t)terrain * 32 + tid] << 3;
-#pragma unroll
-    for (int r = 0; r < 16; r++) {
-        sm.U.w[r][tid] = 0; sm.O.w[r][tid] = 0;
-        sm.c0.w[r][tid] = 0; sm.c1.w[r][tid] = 0; sm.c2.w[r][tid] = 0; sm.c3.w[r][tid] = 0; sm.c4.w[r][tid] = 0;
-    }
+#pragma unroll 8
+    for (int r = 0; r < N_BOARDS * 16; r++) sm.rows[r][tid] = 0;
 #pragma unroll
     for (int r = 0; r < 32; r++) sm.ring[r][tid] = (uint16_t)NONE;
     __syncthreads();
@@ -149,6 +186,8 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
         const uint32_t nq7 = noise_q7(noise_pct);
         const int tenure = tenure_of(chain_offset + (uint32_t)chain);
         uint32_t* sl = site_lists + chain;
+        uint32_t* const Ub = &sm.rows[B_U * 16][tid];
+        const uint32_t* const Ob = &sm.rows[B_O * 16][tid];
         int best = st.best, k = 0;
         uint32_t step = st.step, rowmask = 0;
 
@@ -156,7 +195,7 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
             const uint32_t reset = (uint32_t)stamp_reset(step) << 16;
             for (int y = 0; y < 16; y++)
                 for (uint32_t bits = st.S[y]; bits; bits &= bits - 1) sl[(size_t)(k++) * stride] = (uint32_t)(y * 32 + __ffs(bits) - 1) | reset;
-            for (int r = 0; r < 16; r++) { const uint32_t c = sm.C[r]; sm.U.w[r][tid] = c; rowmask |= c ? 1u << r : 0u; }
+            for (int r = 0; r < 16; r++) { const uint32_t c = sm.C[r]; Ub[r * NT] = c; rowmask |= c ? 1u << r : 0u; }
             for (int i = 0; i < k; i++) flip<true>(sm, tid, (int)(sl[(size_t)i * stride] & 0x1ffu), rowmask);
         }
 
@@ -176,20 +215,29 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
                 continue;
             }
             if (drop || (k == limit - 1 && k > 0)) {
-                // ---- removal: min-loss support, random ties; supports younger than the tenure only as a last resort (not when dropping)
-                uint32_t best_key = 0xffffffffu, best_e = 0;
-                int best_i = 0;
+                // ---- removal: min-loss support, random ties; supports younger than the tenure only as a last resort (not when
+                // dropping).  key = young | loss | tie | list index: unique, so the minimum is the spec's (lowest index wins ties)
+                const uint32_t stephi = (step << 16) | 0xffffu;             // stephi - entry = (age << 16) + (0xffff - site): no borrow
+                const uint32_t young_below = drop ? 0u : (uint32_t)ten << 16;
+                uint32_t best_key = 0xffffffffu, mult = K3;                 // mult = (2i+1) * K3
 #pragma unroll 2
-                for (int i = 0; i < k; i++) {
+                for (int i = 0; i < k; i++, mult += 2u * K3) {
                     const uint32_t e = sl[(size_t)i * stride];
-                    const int v = (int)(e & 0x1ffu);
-                    const int loss = score(sm.O, tid, v & 31, v >> 5, sm.tab[v]);
-                    const uint32_t tie = tie_remove(lane_hash(hs, (uint32_t)(i & 31)), (uint32_t)(i >> 5));
-                    const uint32_t young = (!drop && is_tabu(step, (uint16_t)(e >> 16), ten)) ? TABU_BIT : 0u;
-                    const uint32_t key = young | ((uint32_t)loss << 16) | tie;
-                    if (key < best_key) { best_key = key; best_i = i; best_e = e; }
+                    const int v = (int)(e & 0x1ffu), x = v & 31;
+                    const uint2 win = sm.tab[v + TAB_PAD];
+                    const uint32_t* p = Ob + (v >> 5) * NT;
+                    uint32_t lo = 0, hi = 0;
+#pragma unroll
+                    for (int j = 6; j >= 4; j--) hi = hi * 128u + ((p[(j - 3) * NT] >> x) & 0x7fu);
+#pragma unroll
+                    for (int j = 3; j >= 0; j--) lo = lo * 128u + ((p[(j - 3) * NT] >> x) & 0x7fu);
+                    const uint32_t loss = (uint32_t)(__popc(lo & win.x) + __popc(hi & win.y));
+                    const uint32_t tie = ((hs * mult) >> 7) & 0x1fffe00u;  // tie_remove(hs, i) << 9
+                    const uint32_t young = (stephi - e) < young_below ? TABU_BIT : 0u;
+                    best_key = min(best_key, (young | tie | (uint32_t)i) + loss * (1u << 25));
                 }
-                const int u = (int)(best_e & 0x1ffu);
+                const int best_i = (int)(best_key & 0x1ffu);
+                const int u = (int)(sl[(size_t)best_i * stride] & 0x1ffu);
                 const uint32_t last = sl[(size_t)(k - 1) * stride];
                 sl[(size_t)best_i * stride] = last;
                 sm.ring[step & 31u][tid] = (uint16_t)u;
@@ -200,43 +248,36 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
             if (!drop) {
                 // ---- addition at a random uncovered tile t: best-gain site of R(t)
                 const int y = pick_rotated(rowmask, hs & 31u);
-                const int x = pick_rotated(sm.U.w[y][tid] >> 3, (hs >> 5) & 31u);
-                const uint2 wt = sm.tab[y * 32 + x];
+                const uint32_t* Up = Ub + y * NT;
+                const int x = pick_rotated(Up[0] >> 3, (hs >> 5) & 31u);
+                const uint2* tabt = &sm.tab[y * 32 + x + TAB_PAD];
+                const uint2 wt = tabt[0];
                 uint32_t R[13];  // rows y-6 .. y+6 of U; bit b of R[j] = tile column b + x - 6
 #pragma unroll
-                for (int j = 0; j < 13; j++) R[j] = (sm.U.w[(y - 6 + j) & 15][tid] << 3) >> x;
+                for (int j = 0; j < 13; j++) R[j] = (Up[(j - 6) * NT] << 3) >> x;
                 unsigned long long tw = 0;  // sites removed fewer than `ten` steps ago, as a window around t
                 for (int j = 0; j < ten; j++) {
                     const uint32_t e = sm.ring[(step - (uint32_t)j) & 31u][tid];
                     const int dx3 = (int)(e & 31u) - x + 3, dy3 = (int)(e >> 5) - y + 3;
                     if ((unsigned)dx3 < 7u && (unsigned)dy3 < 7u) tw |= 1ull << (7 * dy3 + dx3);
                 }
-                const uint32_t tw_lo = (uint32_t)tw & 0x0fffffffu, tw_hi = (uint32_t)(tw >> 28);
+                const uint32_t fresh_lo = ~(uint32_t)tw, fresh_hi = ~(uint32_t)(tw >> 28);
                 const bool noise = ((hs >> 10) & 127u) < nq7;
-                uint32_t mx = 0;
-                int v = 0, nc = 0;
-#pragma unroll
-                for (int i = 0; i < 25; i++) {
-                    const int dx = cell_dx(i), dy = cell_dy(i), bit = 7 * (dy + 3) + dx + 3;
-                    const bool valid = ((bit < 28 ? wt.x >> bit : wt.y >> (bit - 28)) & 1u) != 0;
-                    const int cv = (y + dy) * 32 + x + dx;
-                    const uint2 win = sm.tab[valid ? cv : 0];
-                    uint32_t lo = 0, hi = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) lo |= shift_static(R[dy + 3 + j], 7 * j - (dx + 3)) & (0x7fu << (7 * j));
-#pragma unroll
-                    for (int j = 0; j < 3; j++) hi |= shift_static(R[dy + 7 + j], 7 * j - (dx + 3)) & (0x7fu << (7 * j));
-                    const int g = __popc(lo & win.x) + __popc(hi & win.y);
-                    const bool tabu = ((bit < 28 ? tw_lo >> bit : tw_hi >> (bit - 28)) & 1u) != 0;
-                    const uint32_t tie = tie_add(lane_hash(hs, (uint32_t)i));
-                    uint32_t key = noise ? (0x10000u | tie) : ((tabu ? 0u : TABU_BIT) | ((uint32_t)(g + 1) << 16) | tie);
-                    key = valid ? key : 0u;
-                    nc += valid ? 1 : 0;
-                    if (key > mx) { mx = key; v = cv; }
-                }
+                uint32_t mx = add_column<0>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise);
+                mx = max(mx, add_column<-1>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+                mx = max(mx, add_column<1>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+                mx = max(mx, add_column<-2>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+                mx = max(mx, add_column<2>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+                mx = max(mx, add_column<-3>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+                mx = max(mx, add_column<3>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+                // the winning cell from the key's low bits
+                const int cell = 31 - (int)(mx & 31u);
+                const int r = (cell >= 1) + (cell >= 4) + (cell >= 9) + (cell >= 16) + (cell >= 21) + (cell >= 24);
+                const int dy = r - 3, dx = cell - cell_start(r) - (3 - abs(dy));
+                const int v = (y + dy) * 32 + x + dx;
                 flip<true>(sm, tid, v, rowmask);
                 sl[(size_t)k * stride] = (uint32_t)v | (step << 16);
-                if (!noise) scored += (unsigned)nc;
+                if (!noise) scored += (unsigned)(__popc(wt.x) + __popc(wt.y));
                 k++;
             }
             step++; my_steps++;
