@@ -822,14 +822,18 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
                           int32_t cap, int32_t* n_out) {
     if (!e) return TSS_E_INVALID;
     if (n_out) *n_out = 0;
-    tss_search_params p{seed, 0, 0, -1, 0};
+    // One SAT-like call (no budget, no step count: return the first model within the bound) is latency bound: the
+    // half-warp kernel with 64 chains per SM steps every chain in ~3 us.  A call with an effort budget is throughput
+    // bound: the engine default (one chain per thread where the grid fits, 384 chains per SM).
+    const int kernel = (budget_ms <= 0 && max_steps <= 0 && h <= 16) ? TSS_KERNEL_HALF_WARP : TSS_KERNEL_AUTO;
+    tss_search_params p{seed, 0, 0, -1, kernel};
     tss_search* s = nullptr;
     e->stats.interrupted = 0;
     e->stats.best_count = -1;
     int rc = TSS_OK;
     bool only_1x1 = true;
     for (int i = 0; i < n_defs; i++) only_1x1 = only_1x1 && defs && defs[i].w == 1 && defs[i].h == 1;
-    if (e->cached_search && e->cached_search->n_chains != default_chains(e, w, h, TSS_KERNEL_AUTO)) {  // sized for another grid class
+    if (e->cached_search && w > 0 && h > 0 && e->cached_search->n_chains != default_chains(e, w, h, kernel)) {  // sized for another grid class / mode
         search_free(e->cached_search);
         e->cached_search = nullptr;
     }
@@ -838,6 +842,7 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
         s = e->cached_search;
         e->cached_search = nullptr;
         s->w = w; s->h = h; s->seed = seed; s->chain_offset = 0; s->noise = sls::DEFAULT_NOISE_PCT;
+        s->kernel = kernel;
         s->grid.assign(grid, grid + (size_t)w * h);
         s->totals_seen[0] = s->totals_seen[1] = 0;
         s->dirty = false;

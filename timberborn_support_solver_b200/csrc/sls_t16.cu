@@ -39,7 +39,7 @@ enum { B_C0 = 0, B_C1 = 1, B_C2 = 2, B_U = 3, B_O = 4, B_C3 = 5, B_C4 = 6, N_BOA
 
 struct Smem {
     uint2 tab[512 + 2 * TAB_PAD];          // reach windows of the 16x32 sites, anchored at x-3; entry of site v at v + TAB_PAD
-    uint32_t C[16];                        // terrain rows, columns shifted by 3
+    uint32_t C[24];                        // terrain rows, columns shifted by 3; row r at C[r + 3], zero outside the grid
     uint32_t rows[N_BOARDS * 16][NT];      // [board][row][thread]: bank = thread, conflict free for any row index
     uint16_t ring[32][NT];                 // site removed at step s in slot s & 31 (NONE if none)
 };
@@ -50,42 +50,52 @@ __device__ __forceinline__ int pick_rotated(uint32_t bits, uint32_t o) {
     return (int)((__ffs(rot) - 1 + o) & 31u);
 }
 
-// adds (ADD) or removes the cover of site v on the five count planes and refreshes U, O and the non-empty-row mask
+// adds (ADD) or removes the cover of site v on the five count planes and refreshes U, O and the non-empty-row mask.
+// Branch free: rows of the window without reach bits (m = 0) recompute what is already there; rows outside the grid read
+// a neighbouring board (never written: the stores are predicated on m != 0) and meet C = 0.
+// rowmask is kept in padded coordinates: bit r + 3 = row r has an uncovered tile.
 template <bool ADD>
 __device__ __forceinline__ void flip(Smem& sm, int tid, int v, uint32_t& rowmask) {
     const int x = v & 31, y = v >> 5;
     const uint2 win = sm.tab[v + TAB_PAD];
     uint32_t* p = &sm.rows[0][tid] + y * NT;  // row y of the first board
+    uint32_t nz = 0;
 #pragma unroll
     for (int j = 0; j < 7; j++) {
         const uint32_t m7 = (j < 4 ? win.x >> (7 * j) : win.y >> (7 * (j - 4))) & 0x7fu;
-        if (m7) {  // (rows outside the grid have no window bits: every access below is inside the boards)
-            const int off = (j - 3) * NT;
-            uint32_t m = m7 << x;
-            uint32_t a0 = p[B_C0 * BOARD + off], a1 = p[B_C1 * BOARD + off], a2 = p[B_C2 * BOARD + off], t;
-            uint32_t a3 = p[B_C3 * BOARD + off], a4 = p[B_C4 * BOARD + off];
-            if (ADD) {
-                t = a0 & m; a0 ^= m; m = t;
-                t = a1 & m; a1 ^= m; m = t;
-                t = a2 & m; a2 ^= m; m = t;
-            } else {
-                t = ~a0 & m; a0 ^= m; m = t;
-                t = ~a1 & m; a1 ^= m; m = t;
-                t = ~a2 & m; a2 ^= m; m = t;
-            }
+        const int off = (j - 3) * NT;
+        uint32_t m = m7 << x;
+        uint32_t a0 = p[B_C0 * BOARD + off], a1 = p[B_C1 * BOARD + off], a2 = p[B_C2 * BOARD + off], t;
+        uint32_t a3 = p[B_C3 * BOARD + off], a4 = p[B_C4 * BOARD + off];
+        if (ADD) {
+            t = a0 & m; a0 ^= m; m = t;
+            t = a1 & m; a1 ^= m; m = t;
+            t = a2 & m; a2 ^= m; m = t;
+        } else {
+            t = ~a0 & m; a0 ^= m; m = t;
+            t = ~a1 & m; a1 ^= m; m = t;
+            t = ~a2 & m; a2 ^= m; m = t;
+        }
+        if (m) {  // a count crossing 7 <-> 8: rare
+            if (ADD) { t = a3 & m; a3 ^= m; a4 ^= t; } else { t = ~a3 & m; a3 ^= m; a4 ^= t; }
+            p[B_C3 * BOARD + off] = a3; p[B_C4 * BOARD + off] = a4;
+        }
+        const uint32_t hi = a1 | a2 | a3 | a4, C = sm.C[y + j];  // C[r + 3] = row r
+        const uint32_t Un = C & ~(a0 | hi);
+        if (m7) {
             p[B_C0 * BOARD + off] = a0; p[B_C1 * BOARD + off] = a1; p[B_C2 * BOARD + off] = a2;
-            if (m) {  // a count crossing 7 <-> 8: rare
-                if (ADD) { t = a3 & m; a3 ^= m; a4 ^= t; } else { t = ~a3 & m; a3 ^= m; a4 ^= t; }
-                p[B_C3 * BOARD + off] = a3; p[B_C4 * BOARD + off] = a4;
-            }
-            const uint32_t hi = a1 | a2 | a3 | a4, C = sm.C[y - 3 + j];
-            const uint32_t Un = C & ~(a0 | hi);
             p[B_U * BOARD + off] = Un;
             p[B_O * BOARD + off] = a0 & ~hi & C;
-            const uint32_t bit = 1u << (y - 3 + j);
-            rowmask = Un ? (rowmask | bit) : (rowmask & ~bit);
         }
+        nz |= Un ? 1u << j : 0u;
     }
+    rowmask = (rowmask & ~(0x7fu << y)) | (nz << y);
+}
+
+__device__ __forceinline__ uint32_t shl_clamped(uint32_t v, int n) {  // PTX shl: shift counts above 31 (incl. "negative" ones) give 0
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
 }
 
 __device__ __forceinline__ constexpr int cell_start(int r) { return r <= 4 ? r * r : (r == 5 ? 21 : 24); }   // first diamond cell of window row r
@@ -109,39 +119,38 @@ __device__ __noinline__ void list_to_rows(const uint32_t* sl, size_t stride, int
 // the maximum is independent of the evaluation order and ties go to the lowest cell as the spec demands.
 template <int DX, int DY>
 __device__ __forceinline__ uint32_t add_key(const Smem& sm, const uint32_t (&P)[13], const uint2* tabt, uint2 wt, uint32_t fresh_lo, uint32_t fresh_hi,
-                                            uint32_t hs, bool noise) {
+                                            uint32_t hs, uint32_t gmul) {
     constexpr int cell = cell_index(DX, DY), bit = 7 * (DY + 3) + DX + 3;
     const uint2 win = tabt[DY * 32 + DX];
     const uint32_t lo = ((P[DY + 6] * 128u + P[DY + 5]) * 128u + P[DY + 4]) * 128u + P[DY + 3];
     const uint32_t hi = (P[DY + 9] * 128u + P[DY + 8]) * 128u + P[DY + 7];
     const uint32_t g = (uint32_t)(__popc(lo & win.x) + __popc(hi & win.y));
     const uint32_t tie = ((hs * ((2u * cell + 1u) * K2)) >> 11) & 0x1fffe0u;             // tie_add(hs, cell) << 5
-    const uint32_t fresh = shift_static(bit < 28 ? fresh_lo : fresh_hi, 30 - (bit < 28 ? bit : bit - 28)) & TABU_BIT;
-    const uint32_t greedy = (fresh | tie) + g * (1u << 21) + ((1u << 21) | (31u - cell));
-    const uint32_t key = noise ? (tie | (1u << 21) | (31u - cell)) : greedy;
+    const uint32_t fresh = shift_static(bit < 28 ? fresh_lo : fresh_hi, 30 - (bit < 28 ? bit : bit - 28)) & TABU_BIT;  // (all zero in a noise step)
+    const uint32_t key = (fresh | tie) + g * gmul + ((1u << 21) | (31u - cell));   // gmul = 1 << 21, or 0 in a noise step
     const bool valid = ((bit < 28 ? wt.x >> bit : wt.y >> (bit - 28)) & 1u) != 0;
     return valid ? key : 0u;
 }
 
 template <int DX>
 __device__ __forceinline__ uint32_t add_column(const Smem& sm, const uint32_t (&R)[13], const uint2* tabt, uint2 wt, uint32_t fresh_lo, uint32_t fresh_hi,
-                                               uint32_t hs, bool noise) {
+                                               uint32_t hs, uint32_t gmul) {
     constexpr int M = 3 - iabs(DX);
     uint32_t P[13];
 #pragma unroll
     for (int j = 3 - M; j <= 9 + M; j++) P[j] = (R[j] >> (DX + 3)) & 0x7fu;
-    uint32_t mx = add_key<DX, 0>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise);
+    uint32_t mx = add_key<DX, 0>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, gmul);
     if (M >= 1) {
-        mx = max(mx, add_key<DX, (M >= 1 ? -1 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise));
-        mx = max(mx, add_key<DX, (M >= 1 ? 1 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+        mx = max(mx, add_key<DX, (M >= 1 ? -1 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, gmul));
+        mx = max(mx, add_key<DX, (M >= 1 ? 1 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, gmul));
     }
     if (M >= 2) {
-        mx = max(mx, add_key<DX, (M >= 2 ? -2 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise));
-        mx = max(mx, add_key<DX, (M >= 2 ? 2 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+        mx = max(mx, add_key<DX, (M >= 2 ? -2 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, gmul));
+        mx = max(mx, add_key<DX, (M >= 2 ? 2 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, gmul));
     }
     if (M >= 3) {
-        mx = max(mx, add_key<DX, (M >= 3 ? -3 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise));
-        mx = max(mx, add_key<DX, (M >= 3 ? 3 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+        mx = max(mx, add_key<DX, (M >= 3 ? -3 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, gmul));
+        mx = max(mx, add_key<DX, (M >= 3 ? 3 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, gmul));
     }
     return mx;
 }
@@ -166,7 +175,7 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
         }
         sm.tab[i] = s;
     }
-    if (tid < 16) sm.C[tid] = terrain_rows[(size_t)terrain * 32 + tid] << 3;
+    if (tid < 24) sm.C[tid] = (tid >= 3 && tid < 19) ? terrain_rows[(size_t)terrain * 32 + tid - 3] << 3 : 0u;
 #pragma unroll 8
     for (int r = 0; r < N_BOARDS * 16; r++) sm.rows[r][tid] = 0;
 #pragma unroll
@@ -195,7 +204,7 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
             const uint32_t reset = (uint32_t)stamp_reset(step) << 16;
             for (int y = 0; y < 16; y++)
                 for (uint32_t bits = st.S[y]; bits; bits &= bits - 1) sl[(size_t)(k++) * stride] = (uint32_t)(y * 32 + __ffs(bits) - 1) | reset;
-            for (int r = 0; r < 16; r++) { const uint32_t c = sm.C[r]; Ub[r * NT] = c; rowmask |= c ? 1u << r : 0u; }
+            for (int r = 0; r < 16; r++) { const uint32_t c = sm.C[r + 3]; Ub[r * NT] = c; rowmask |= c ? 8u << r : 0u; }
             for (int i = 0; i < k; i++) flip<true>(sm, tid, (int)(sl[(size_t)i * stride] & 0x1ffu), rowmask);
         }
 
@@ -247,7 +256,7 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
             }
             if (!drop) {
                 // ---- addition at a random uncovered tile t: best-gain site of R(t)
-                const int y = pick_rotated(rowmask, hs & 31u);
+                const int y = pick_rotated(rowmask >> 3, hs & 31u);
                 const uint32_t* Up = Ub + y * NT;
                 const int x = pick_rotated(Up[0] >> 3, (hs >> 5) & 31u);
                 const uint2* tabt = &sm.tab[y * 32 + x + TAB_PAD];
@@ -255,21 +264,26 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
                 uint32_t R[13];  // rows y-6 .. y+6 of U; bit b of R[j] = tile column b + x - 6
 #pragma unroll
                 for (int j = 0; j < 13; j++) R[j] = (Up[(j - 6) * NT] << 3) >> x;
-                unsigned long long tw = 0;  // sites removed fewer than `ten` steps ago, as a window around t
+                const bool noise = ((hs >> 10) & 127u) < nq7;
+                uint32_t tw_lo = 0, tw_hi = 0;  // sites removed fewer than `ten` steps ago, as a window around t (rows 0-3 / 4-6)
                 for (int j = 0; j < ten; j++) {
                     const uint32_t e = sm.ring[(step - (uint32_t)j) & 31u][tid];
                     const int dx3 = (int)(e & 31u) - x + 3, dy3 = (int)(e >> 5) - y + 3;
-                    if ((unsigned)dx3 < 7u && (unsigned)dy3 < 7u) tw |= 1ull << (7 * dy3 + dx3);
+                    if ((unsigned)dx3 < 7u && (unsigned)dy3 < 7u) {
+                        const int bit = 7 * dy3 + dx3;
+                        tw_lo |= shl_clamped(1u, bit);       // (bits 28..31 of tw_lo are never looked at)
+                        tw_hi |= shl_clamped(1u, bit - 28);
+                    }
                 }
-                const uint32_t fresh_lo = ~(uint32_t)tw, fresh_hi = ~(uint32_t)(tw >> 28);
-                const bool noise = ((hs >> 10) & 127u) < nq7;
-                uint32_t mx = add_column<0>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise);
-                mx = max(mx, add_column<-1>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise));
-                mx = max(mx, add_column<1>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise));
-                mx = max(mx, add_column<-2>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise));
-                mx = max(mx, add_column<2>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise));
-                mx = max(mx, add_column<-3>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise));
-                mx = max(mx, add_column<3>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, noise));
+                const uint32_t fresh_lo = noise ? 0u : ~tw_lo, fresh_hi = noise ? 0u : ~tw_hi;
+                const uint32_t gmul = noise ? 0u : 1u << 21;
+                uint32_t mx = add_column<0>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, gmul);
+                mx = max(mx, add_column<-1>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, gmul));
+                mx = max(mx, add_column<1>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, gmul));
+                mx = max(mx, add_column<-2>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, gmul));
+                mx = max(mx, add_column<2>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, gmul));
+                mx = max(mx, add_column<-3>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, gmul));
+                mx = max(mx, add_column<3>(sm, R, tabt, wt, fresh_lo, fresh_hi, hs, gmul));
                 // the winning cell from the key's low bits
                 const int cell = 31 - (int)(mx & 31u);
                 const int r = (cell >= 1) + (cell >= 4) + (cell >= 9) + (cell >= 16) + (cell >= 21) + (cell >= 24);
