@@ -36,7 +36,15 @@ WORKLOAD = "rect 16x16 ceiling, 1x1 supports, find minimum support count (BASELI
 OPTIMUM_RECT16 = 15   # UNSAT proven at <= 14 (re-derived by oracle CDCL: tests/test_oracle.py proves ex1-3; rect16 in DESIGN.md)
 # algorithmic integer work (DESIGN.md "kernel (b)"): thread-ops, counted from the kernel's own counters
 A_SCORE = 7 * 4 + 2      # per candidate scored: 7 window rows x (shift, and, pack, add) + key build
-A_FLIP = 16 * 20         # per support added/removed: 16 grid rows x (row mask 6 + five-plane add/sub 10 + derive 4)
+A_FLIP = 7 * 20          # per support added/removed: 7 window rows x (row mask 6 + five-plane add/sub 10 + derive 4)
+KERNEL_NAMES = {1: "sls_kernel (one chain per warp)", 2: "sls_h16_kernel (two chains per warp)", 3: "sls_t16_kernel (one chain per thread)"}
+# per-launch DRAM traffic and issue statistics of each variant from its committed ncu capture (profiles/)
+KERNEL_NCU = {
+    2: {"traffic": 3067392, "traffic_note": "dram bytes of one launch (ncu, 9472 chains x 512 steps): chain states only",
+        "ncu": "ALU pipe 72% busy, 276 warp instructions per chain step (profiles/r1_sls_h16_kernel.md)"},
+    3: {"traffic": 11070464, "traffic_note": "dram bytes of one launch (ncu, 56832 chains x 512 steps): chain states + site lists",
+        "ncu": "ALU pipe 70% busy, issue slots 69% busy, 76 warp instructions per chain step (profiles/r1_sls_t16_kernel.md)"},
+}
 
 
 def peaks():
@@ -237,7 +245,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitboards / bool", "data": "synthetic",
         "config": {"workload": WORKLOAD, "chains_per_gpu": n_chains, "epoch_steps": args.epoch_steps, "parallelism": f"portfolio x{world} (independent seeds, all-reduce-min of the bound per step)", "exchange": exchange,
-                   "l2": "flushed between timed steps (256 MiB memset outside the event pairs); the kernel's working set is registers + 16 KB smem per CTA"},
+                   "l2": "flushed between timed steps (256 MiB memset outside the event pairs); the kernel's working set is registers + the CTA's shared memory (boards, reach table), HBM is touched at epoch start/end only"},
         "gpu_launches": int(launches_all), "best_count": best, "sls_steps_per_s": steps_all / (ms_total * 1e-3),
         "flips_per_s": 2.0 * steps_all / (ms_total * 1e-3), "candidates_per_step": scored_all / max(steps_all, 1.0), "mean_reach": mean_reach,
         "wall_ms_total": t_wall * 1e3, "clocks": sampler.summary(),
@@ -249,12 +257,37 @@ def main():
         flips = 2.0 * steps_all                      # a swap step removes one support and adds one
         int_ops = A_SCORE * scored_all + A_FLIP * flips
         achieved = int_ops / (ms_total * 1e-3) / 1e9 / world
+        variant = args.kernel or (3 if n_chains >= 1024 else 2)      # engine's auto rule for a 16x16 grid (engine.cu search_kernel)
+        ncu = KERNEL_NCU.get(variant, {"traffic": None, "traffic_note": "no capture for this variant", "ncu": ""})
         line["roofline"] = {"bound": "int_issue", "achieved": achieved, "peak": pk["lop3_gops"], "unit": "Gop/s", "frac": achieved / pk["lop3_gops"],
-                            "traffic": 3067392, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu, 9472 chains x 512 steps): chain states only", "kernel": "sls_h16_kernel (two chains per warp)",
-                            "ncu": "ALU pipe 72% busy, 276 warp instructions per chain step, DRAM 3 MB per launch (profiles/r1_sls_h16_kernel.md)",
+                            "traffic": ncu["traffic"], "traffic_note": ncu["traffic_note"], "kernel": KERNEL_NAMES[variant], "ncu": ncu["ncu"],
+                            "algorithmic_ops": f"{A_SCORE} thread-ops per candidate scored + {A_FLIP} per support added/removed (DESIGN.md kernel (b))",
                             "peak_source": "measured in this run (tss_measure_peaks: dependent-free LOP3 chains at full occupancy)",
-                            "note": "no dense contraction and ~0 HBM traffic in the step loop: the bound is integer issue + warp shuffles (SURVEY.md §8d); per-GPU figures"}
+                            "note": "no dense contraction and ~0 HBM traffic in the step loop: the bound is integer issue (SURVEY.md §8d); per-GPU figures"}
         line["measured_peaks"] = pk
+    # ---------------- e2e through the C ABI with HOST buffers (grid in, layout out) on every rank at once: a fixed step budget
+    # per call; terrain upload, reach table, epochs with their host round trips, witness validation and the layout copy back
+    # are all inside the timed region.  Whole-job value = candidates of all ranks / slowest rank's wall time.
+    steps_per_call, n_calls = 16384, 5
+    eng.solve_upper_bound(grid, card_limit=None, seed=199, max_steps=steps_per_call)      # workspace warm-up (allocation)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = eng.stats()
+    t0 = time.perf_counter()
+    for i in range(n_calls):
+        res, lay = eng.solve_upper_bound(grid, card_limit=None, seed=200 + 16 * rank + i, max_steps=steps_per_call)
+    t_e2e = time.perf_counter() - t0
+    e1 = eng.stats()
+    e2e_t = torch.tensor([float(e1["candidates_scored"] - e0["candidates_scored"]), t_e2e], dtype=torch.float64, device="cuda")
+    e2e_max = e2e_t.clone()
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(e2e_max, op=dist.ReduceOp.MAX)
+    line["e2e"] = {"value": float(e2e_t[0].item()) / float(e2e_max[1].item()), "unit": UNIT,
+                   "h2d_bytes_per_step": int(grid.data.size + 8), "d2h_bytes_per_step": int(20 * lay.platform_count() + 16 * 9 + 320),
+                   "note": f"tss_solve_upper_bound from a host u8 grid to a host platform list on each of the {world} rank(s), {steps_per_call} steps/chain per call, "
+                           f"{n_calls} calls, wall clock incl. copies, epoch round trips and witness validation; sum over ranks / slowest rank"}
     if rank == 0:
         # ---------------- time-to-optimal: fresh portfolio -> first layout with 15 supports (incl. host round trips); one GPU finds
         # it in a fraction of a millisecond, so this is per rank and identical at every N (the one-shot solve never communicates)
@@ -292,18 +325,6 @@ def main():
         line["eval_kernel"] = {"layouts_per_s": n_lay / (ms * 1e-3), "ms": ms, "n": n_lay, "bytes_per_layout": 40,
                                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src},
                                "int_gops": 19 * 16 * n_lay / (ms * 1e-3) / 1e9, "int_note": "A_eval = 19 ops x 16 row words per layout (SURVEY.md §8d accounting)"}
-        # ---------------- e2e through the C ABI with HOST buffers (grid in, layout out), fixed step budget per call
-        steps_per_call = 16384
-        e0 = eng.stats()
-        t0 = time.perf_counter()
-        n_calls = 5
-        for i in range(n_calls):
-            res, lay = eng.solve_upper_bound(grid, card_limit=None, seed=200 + i, max_steps=steps_per_call)
-        t_e2e = time.perf_counter() - t0
-        e1 = eng.stats()
-        line["e2e"] = {"value": (e1["candidates_scored"] - e0["candidates_scored"]) / t_e2e, "unit": UNIT,
-                       "h2d_bytes_per_step": int(grid.data.size + 8), "d2h_bytes_per_step": int(20 * lay.platform_count() + 16 * 9 + 320),
-                       "note": f"tss_solve_upper_bound from a host u8 grid to a host platform list, {steps_per_call} steps/chain per call, wall clock incl. allocation, copies, witness validation"}
         # ---------------- kernel (c): CNF check of 8192 witness assignments against the encoder's clauses (incl. the totalizer
         # of the at-most-15 bound): the SLS witness, completed by unit propagation, replicated; every 64th copy has one
         # support removed (those must come back falsified)
@@ -353,10 +374,6 @@ def main():
         # ---------------- CPU baseline (bounded sample, rank 0, N = 1)
         rate, threads, sample = cpu_validate_rate(grid.data, seconds=10.0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
-    else:
-        if rank == 0:
-            line["e2e"] = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
-                           "note": "multi-GPU / --quick run: device-timed portfolio only (the C-ABI e2e leg is measured at N = 1)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     search.close()
