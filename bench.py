@@ -349,11 +349,16 @@ def main():
                               "input": "SLS witness completed by unit propagation x 8192, every 64th with one support removed"}
         # ---------------- the other named configs, for context (parity-test cases, not the bench line): wall clock through the C ABI
         others = {}
-        t0 = time.perf_counter()
         ex1_rows = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))["ex1"]["grid"]   # test/ex1.toml
         ex1 = T.WorldGrid.from_toml("[world]\ngrid = [\n" + "".join(f'    "{r}",\n' for r in ex1_rows) + "]\n")
-        res, lay3 = eng.solve_upper_bound(ex1, T.PLATFORMS_DEFAULT, card_limit=1, seed=1)
-        others["C1 ex1 default-8 (REPL set)"] = {"count": lay3.platform_count(), "proven_optimum": 1, "ms": (time.perf_counter() - t0) * 1e3}
+        t1s = []
+        for i in range(7):
+            t0 = time.perf_counter()
+            res, lay3 = eng.solve_upper_bound(ex1, T.PLATFORMS_DEFAULT, card_limit=1, seed=1 + i)
+            t1s.append((time.perf_counter() - t0) * 1e3)
+            assert res == T.SAT and lay3.platform_count() == 1
+        others["C1 ex1 default-8 (REPL set)"] = {"count": lay3.platform_count(), "proven_optimum": 1, "ms": float(np.median(t1s[2:])),
+                                                 "note": "tss_solve_upper_bound(card_limit=1) from host buffers, median of 5 calls after 2 warm-up calls"}
         g4 = T.WorldGrid.synthetic(256, 256, 1, 0)
         s4 = eng.search(g4, seed=1, n_chains=16)
         t0 = time.perf_counter()

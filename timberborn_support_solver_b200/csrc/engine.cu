@@ -174,6 +174,7 @@ void tss_engine_destroy(tss_engine* e) {
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     if (e->cached_search) { search_free(e->cached_search); e->cached_search = nullptr; }
     if (e->cached_batch) { search_free(e->cached_batch); e->cached_batch = nullptr; }
+    if (e->cached_multi) { search_free(e->cached_multi); e->cached_multi = nullptr; }
     if (e->comm) { comm_destroy(e->comm); e->comm = nullptr; }
     for (auto& b : e->scratch) if (b.ptr) cudaFree(b.ptr);
     for (auto& b : e->staging) if (b.ptr) cudaFreeHost(b.ptr);
@@ -506,16 +507,26 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
     if (s->key_dims.size() > 1 && fits) {
         s->multi = true;
         if (!(params && params->n_chains > 0)) s->n_chains = e->prop.multiProcessorCount * 16;
-        cudaError_t err = cudaMalloc(&s->rows_dev, sizeof rows);
-        if (err == cudaSuccess) err = cudaMalloc(&s->keys_dev, sizeof(int2) * s->key_dims.size());
-        if (err == cudaSuccess) err = cudaMalloc(&s->costs_dev, sizeof(int) * s->key_dims.size());
         s->key_costs.assign(s->key_dims.size(), 1);
-        if (err == cudaSuccess) err = cudaMalloc(&s->mstates, slsm_state_bytes() * (size_t)s->n_chains);
-        if (err == cudaSuccess) err = cudaMalloc(&s->totals_dev, sizeof(unsigned long long) * 2);
-        if (err == cudaSuccess) err = cudaMalloc(&s->best_dev, sizeof(int2));
-        if (err == cudaSuccess) err = cudaMalloc(&s->bounds_dev, sizeof(int));
-        if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->best_host, sizeof(int2), cudaHostAllocDefault);
-        if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->totals_host, sizeof(unsigned long long) * 2, cudaHostAllocDefault);
+        cudaError_t err = cudaSuccess;
+        tss_search* old = e->cached_multi;  // workspace of an earlier one-shot solve: same buffers, no allocation
+        if (old && old->n_chains == s->n_chains) {
+            e->cached_multi = nullptr;
+            s->rows_dev = old->rows_dev; s->keys_dev = old->keys_dev; s->costs_dev = old->costs_dev; s->mstates = old->mstates;
+            s->totals_dev = old->totals_dev; s->best_dev = old->best_dev; s->bounds_dev = old->bounds_dev;
+            s->best_host = old->best_host; s->totals_host = old->totals_host;
+            delete old;
+        } else {
+            err = cudaMalloc(&s->rows_dev, sizeof rows);
+            if (err == cudaSuccess) err = cudaMalloc(&s->keys_dev, sizeof(int2) * (size_t)slsm_max_keys());
+            if (err == cudaSuccess) err = cudaMalloc(&s->costs_dev, sizeof(int) * (size_t)slsm_max_keys());
+            if (err == cudaSuccess) err = cudaMalloc(&s->mstates, slsm_state_bytes() * (size_t)s->n_chains);
+            if (err == cudaSuccess) err = cudaMalloc(&s->totals_dev, sizeof(unsigned long long) * 2);
+            if (err == cudaSuccess) err = cudaMalloc(&s->best_dev, sizeof(int2));
+            if (err == cudaSuccess) err = cudaMalloc(&s->bounds_dev, sizeof(int));
+            if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->best_host, sizeof(int2), cudaHostAllocDefault);
+            if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->totals_host, sizeof(unsigned long long) * 2, cudaHostAllocDefault);
+        }
         const int nb = sls::NO_BOUND;
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->rows_dev, rows, sizeof rows, cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->keys_dev, s->key_dims.data(), sizeof(int2) * s->key_dims.size(), cudaMemcpyHostToDevice, e->stream);
@@ -898,6 +909,9 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     if (!s->lns && !s->multi && s->n_groups == 1 && !e->cached_search && rc == TSS_OK) {
         cudaStreamSynchronize(e->stream);
         e->cached_search = s;  // keep the workspace for the next call
+    } else if (s->multi && !e->cached_multi && rc == TSS_OK) {
+        cudaStreamSynchronize(e->stream);
+        e->cached_multi = s;   // (tss_search_create adopts its buffers)
     } else {
         tss_search_destroy(s);
     }

@@ -45,6 +45,7 @@ struct tss_engine {
     std::atomic<int> interrupt_flag{0};
     struct tss_search* cached_search = nullptr;  // workspace reused by tss_solve_upper_bound (no cudaMalloc per call)
     struct tss_search* cached_batch = nullptr;   // workspace reused by tss_solve_batch
+    struct tss_search* cached_multi = nullptr;   // workspace of the placement search (platform sets beyond {1x1}) of a one-shot solve
     struct tss::Comm* comm = nullptr;            // NCCL communicator of a multi-GPU portfolio (comm.cu), or null
     TssBuffer scratch[8];                    // device scratch slots
     TssBuffer staging[4];                    // pinned host staging slots
