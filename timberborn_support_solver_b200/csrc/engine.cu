@@ -15,7 +15,7 @@ int sls_run(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls:
             int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
             int noise_pct, unsigned long long* totals_dev);
 int sls_best_reduce(tss_engine* e, const sls::ChainState* states, int chains_per_group, int n_chains, int n_groups, int2* out_dev,
-                    int* bounds_dev);
+                    int* bounds_dev, unsigned long long* key_dev);
 // sls_h16.cu — two chains per warp for grids of at most 16 rows (chains_per_terrain must be 0 or a multiple of 8)
 // sls_t16.cu — one chain per thread for grids of at most 16 rows x 26 columns (chains_per_terrain 0 or a multiple of the CTA size)
 bool sls_t16_fits(int w, int h);
@@ -107,6 +107,7 @@ struct tss_search {
     uint32_t* site_lists = nullptr;            // [16*26][n_chains rounded to 32] support lists of the thread-per-chain kernel (allocated on first use)
     int kernel = TSS_KERNEL_AUTO;              // tss_search_params.kernel
     unsigned long long* totals_dev = nullptr;  // [2]
+    unsigned long long* reduce_key_dev = nullptr;  // [1] running (best << 32 | chain) minimum of the wide best-reduce, ~0 between epochs
     int2* best_dev = nullptr;                  // [n_groups]
     int* bounds_dev = nullptr;                 // [n_groups]
     int2* best_host = nullptr;                 // pinned [n_groups]
@@ -408,6 +409,7 @@ static void search_free(tss_search* s) {
     cudaFree(s->costs_dev);
     cudaFree(s->mstates);
     cudaFree(s->site_lists);
+    cudaFree(s->reduce_key_dev);
     cudaFree(s->rows_dev); cudaFree(s->tabs_dev); cudaFree(s->states); cudaFree(s->totals_dev); cudaFree(s->best_dev); cudaFree(s->bounds_dev);
     if (s->best_host) cudaFreeHost(s->best_host);
     if (s->totals_host) cudaFreeHost(s->totals_host);
@@ -420,6 +422,7 @@ static int search_alloc(tss_engine* e, tss_search* s, const uint32_t* rows32_hos
     TSS_CUDA(e, cudaMalloc(&s->tabs_dev, sizeof(uint2) * 1024 * (size_t)n_terrains));
     TSS_CUDA(e, cudaMalloc(&s->states, sizeof(sls::ChainState) * (size_t)s->n_chains));
     TSS_CUDA(e, cudaMalloc(&s->totals_dev, sizeof(unsigned long long) * 2));
+    TSS_CUDA(e, cudaMalloc(&s->reduce_key_dev, sizeof(unsigned long long)));
     TSS_CUDA(e, cudaMalloc(&s->best_dev, sizeof(int2) * (size_t)s->n_groups));
     TSS_CUDA(e, cudaMalloc(&s->bounds_dev, sizeof(int) * (size_t)s->n_groups));
     TSS_CUDA(e, cudaHostAlloc((void**)&s->best_host, sizeof(int2) * (size_t)s->n_groups, cudaHostAllocDefault));
@@ -430,6 +433,7 @@ static int search_alloc(tss_engine* e, tss_search* s, const uint32_t* rows32_hos
 
 static int search_init_device(tss_engine* e, tss_search* s, int n_terrains) {
     TSS_CUDA(e, cudaMemsetAsync(s->totals_dev, 0, sizeof(unsigned long long) * 2, e->stream));
+    TSS_CUDA(e, cudaMemsetAsync(s->reduce_key_dev, 0xff, sizeof(unsigned long long), e->stream));
     std::vector<int> nb((size_t)s->n_groups, sls::NO_BOUND);
     TSS_CUDA(e, cudaMemcpyAsync(s->bounds_dev, nb.data(), sizeof(int) * nb.size(), cudaMemcpyHostToDevice, e->stream));
     for (int g = 0; g < s->n_groups; g++) s->best_host[g] = make_int2(sls::NO_BOUND, -1);
@@ -618,7 +622,7 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
         else
             rc = (variant == TSS_KERNEL_HALF_WARP ? sls_run_h16 : sls_run)(e, s->rows_dev, s->tabs_dev, s->states, s->n_chains, s->chains_per_terrain,
                                                                           s->chain_offset, s->seed, chunk, s->bounds_dev, target, s->noise, s->totals_dev);
-        if (rc == TSS_OK) rc = sls_best_reduce(e, s->states, chains_per_group, s->n_chains, s->n_groups, s->best_dev, s->bounds_dev);
+        if (rc == TSS_OK) rc = sls_best_reduce(e, s->states, chains_per_group, s->n_chains, s->n_groups, s->best_dev, s->bounds_dev, s->reduce_key_dev);
         // multi-GPU portfolio: the one exchange of the path, in-stream on the device-resident bound (no host round trip)
         if (rc == TSS_OK && e->comm && s->share && s->n_groups == 1) rc = comm_allreduce_min(e, e->comm, s->bounds_dev, 1);
         if (rc) return rc;

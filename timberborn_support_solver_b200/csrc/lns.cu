@@ -20,7 +20,7 @@ int sls_run_windows(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_d
                     sls::ChainState* states, int n_chains, int chains_per_window, uint32_t chain_offset, uint64_t seed, long long steps,
                     const int* bounds_dev, unsigned long long* totals_dev, int noise_pct);
 int sls_best_reduce(tss_engine* e, const sls::ChainState* states, int chains_per_group, int n_chains, int n_groups, int2* out_dev,
-                    int* bounds_dev);
+                    int* bounds_dev, unsigned long long* key_dev);
 
 namespace lns {
 
@@ -205,7 +205,7 @@ int lns_phase(tss_engine* e, LnsSearch* s, long long steps, bool share) {
     rc = sls_run_windows(e, s->rows_win, s->tabs, s->need_win, lns::CORE_LO, lns::CORE_HI, s->states, n_chains, s->seeds, s->chain_offset, s->seed,
                          steps, s->bounds, s->totals, s->noise);
     if (rc) return rc;
-    rc = sls_best_reduce(e, s->states, s->seeds, n_chains, n_windows, s->best, s->bounds);
+    rc = sls_best_reduce(e, s->states, s->seeds, n_chains, n_windows, s->best, s->bounds, nullptr);
     if (rc) return rc;
     lns::writeback_windows_kernel<<<(n_windows * 32 + 127) / 128, 128, 0, e->stream>>>(s->S, s->h, s->wpr, ox, oy, nwx, n_windows, s->best, s->states);
     TSS_CUDA(e, cudaMemsetAsync(s->count_dev, 0, sizeof(int), e->stream));

@@ -122,8 +122,8 @@ __device__ __forceinline__ uint32_t add_key(const Smem& sm, const uint32_t (&P)[
                                             uint32_t hs, uint32_t gmul) {
     constexpr int cell = cell_index(DX, DY), bit = 7 * (DY + 3) + DX + 3;
     const uint2 win = tabt[DY * 32 + DX];
-    const uint32_t lo = ((P[DY + 6] * 128u + P[DY + 5]) * 128u + P[DY + 4]) * 128u + P[DY + 3];
-    const uint32_t hi = (P[DY + 9] * 128u + P[DY + 8]) * 128u + P[DY + 7];
+    const uint32_t lo = (P[DY + 6] * 128u + P[DY + 5]) * 16384u + (P[DY + 4] * 128u + P[DY + 3]);   // (tree, not Horner: shorter dependency chains)
+    const uint32_t hi = P[DY + 9] * 16384u + (P[DY + 8] * 128u + P[DY + 7]);
     const uint32_t g = (uint32_t)(__popc(lo & win.x) + __popc(hi & win.y));
     const uint32_t tie = ((hs * ((2u * cell + 1u) * K2)) >> 11) & 0x1fffe0u;             // tie_add(hs, cell) << 5
     const uint32_t fresh = shift_static(bit < 28 ? fresh_lo : fresh_hi, 30 - (bit < 28 ? bit : bit - 28)) & TABU_BIT;  // (all zero in a noise step)
@@ -235,11 +235,11 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
                     const int v = (int)(e & 0x1ffu), x = v & 31;
                     const uint2 win = sm.tab[v + TAB_PAD];
                     const uint32_t* p = Ob + (v >> 5) * NT;
-                    uint32_t lo = 0, hi = 0;
+                    uint32_t r7[7];
 #pragma unroll
-                    for (int j = 6; j >= 4; j--) hi = hi * 128u + ((p[(j - 3) * NT] >> x) & 0x7fu);
-#pragma unroll
-                    for (int j = 3; j >= 0; j--) lo = lo * 128u + ((p[(j - 3) * NT] >> x) & 0x7fu);
+                    for (int j = 0; j < 7; j++) r7[j] = (p[(j - 3) * NT] >> x) & 0x7fu;
+                    const uint32_t lo = (r7[3] * 128u + r7[2]) * 16384u + (r7[1] * 128u + r7[0]);
+                    const uint32_t hi = r7[6] * 16384u + (r7[5] * 128u + r7[4]);
                     const uint32_t loss = (uint32_t)(__popc(lo & win.x) + __popc(hi & win.y));
                     const uint32_t tie = ((hs * mult) >> 7) & 0x1fffe00u;  // tie_remove(hs, i) << 9
                     const uint32_t young = (stephi - e) < young_below ? TABU_BIT : 0u;
