@@ -137,6 +137,161 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def setup_dist():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the GPU path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return torch, dist, world, rank, local
+
+
+def comm_init(eng, torch, dist, rank, world):
+    """The engine's own NCCL communicator: torch.distributed only carries the 128-byte id."""
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(eng.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, src=0)
+    eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+
+
+def run_c5(args):
+    """BASELINE.json configs[4]: batch of 100k synthetic 32x32 terrains (p = 0.7), contiguous shards per GPU, no data-path
+    collective; one all-gather of the per-terrain counts at the end.  A step = one pass over the whole batch."""
+    import ctypes as C
+    torch, dist, world, rank, local = setup_dist()
+    import timberborn_support_solver_b200 as T
+    eng = T.Engine(local)
+    n_total = args.terrains
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    lib = T.load()
+    grids = np.zeros((hi - lo, 32, 32), np.uint8)
+    for i, t in enumerate(range(lo, hi)):
+        lib.tss_world_synthetic(32, 32, 1, t, int(0.7 * (1 << 24)), grids[i].ctypes.data_as(C.POINTER(C.c_uint8)))
+    W, K = max(args.warmup, 1), args.steps
+    for _ in range(W):
+        eng.solve_batch(grids[: min(len(grids), 8192)], seed=1, steps=args.batch_steps)
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s0 = eng.stats()
+    dev_ms, t0 = 0.0, time.perf_counter()
+    for _ in range(K):
+        counts, layouts = eng.solve_batch(grids, seed=1, steps=args.batch_steps, want_layouts=True)
+        dev_ms += eng.stats()["device_ms"]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    s1 = eng.stats()
+    sampler.stop_flag = True
+    sampler.join()
+    # final gather: 4 bytes per terrain
+    cd = torch.from_numpy(counts).cuda()
+    if world > 1:
+        sizes = [(r + 1) * n_total // world - r * n_total // world for r in range(world)]
+        parts = [torch.empty(sz, dtype=torch.int32, device="cuda") for sz in sizes]
+        dist.all_gather(parts, cd)
+        allc = torch.cat(parts)
+    else:
+        allc = cd
+    tt = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(s1["candidates_scored"] - s0["candidates_scored"]), float(s1["kernel_launches"] - s0["kernel_launches"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        dev_ms_max, wall_ms_max = (float(x) for x in tt.tolist())
+        tiles = grids.reshape(len(grids), -1).sum(1)
+        # every reported layout of rank 0's shard re-evaluated by kernel (a) in per-terrain mode: complete, count matches
+        terr_rows = (grids.astype(np.uint32) << np.arange(32, dtype=np.uint32)).sum(2, dtype=np.uint32)
+        g_dev, l_dev = torch.from_numpy(terr_rows.view(np.int32)).cuda(), torch.from_numpy(layouts.view(np.int32)).cuda()
+        out = torch.empty((len(grids), 2), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        eng.eval_compact_dev(g_dev.data_ptr(), 32, 32, l_dev.data_ptr(), len(grids), out.data_ptr(), per_layout_terrain=True)
+        torch.cuda.synchronize()
+        res = out.cpu().numpy()
+        ok = bool((res[:, 0] == 0).all() and np.array_equal(res[:, 1], counts))
+        line = {"metric": "terrains solved/sec (per-terrain best support count)", "value": n_total * K / (dev_ms_max * 1e-3), "unit": "terrains/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u32 bitboards / bool", "data": "synthetic",
+                "config": {"workload": f"batch of {n_total} synthetic 32x32 terrains (p=0.7), 1x1 supports (BASELINE.json configs[4])", "sls_steps_per_chain": args.batch_steps,
+                           "chains_per_terrain": 4, "parallelism": f"terrain shards x{world}, no data-path collective, final all-gather of counts",
+                           "l2": "inputs larger than L2 (100 MB of terrains, 800 MB of reach tables per pass)"},
+                "e2e": {"value": n_total * K / (wall_ms_max * 1e-3), "unit": "terrains/s", "h2d_bytes_per_step": int(grids.size), "d2h_bytes_per_step": int(counts.nbytes + layouts.nbytes),
+                        "note": "tss_solve_batch from host u8 grids to host counts + layouts, wall clock, slowest rank"},
+                "gpu_launches": int(tot[1].item()), "candidates_per_s": float(tot[0].item()) / (dev_ms_max * 1e-3), "mean_count": float(allc.float().mean().item()),
+                "mean_ceiling_tiles": float(tiles.mean()), "witnesses_revalidated_by_kernel_a": ok, "clocks": sampler.summary(),
+                "cpu_baseline": {"value": None, "unit": "terrains/s", "cores": 1, "kind": "port",
+                                 "sample": "not timed in this mode: the oracle's CDCL loop needs minutes per terrain (3 sampled terrains: best 76/78/73 after 5 min each, GPU 73/73/67)"}}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_c4(args):
+    """BASELINE.json configs[3]: synthetic 256x256 ceiling (p = 0.7), window-decomposed SLS portfolio, one seed set per GPU,
+    all-reduce-min of (count, rank) + the winner's layout after every phase.  A step = one phase."""
+    torch, dist, world, rank, local = setup_dist()
+    import timberborn_support_solver_b200 as T
+    eng = T.Engine(local)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    if world > 1:
+        comm_init(eng, torch, dist, rank, world)
+    g = T.WorldGrid.synthetic(256, 256, 1, 0)
+    s = eng.search(g, seed=1, n_chains=16, chain_offset=rank * 1000000)
+    W, K = max(args.warmup, 3), args.steps
+    for _ in range(W):
+        s.run(args.phase_steps, 0)
+    s.best_count()
+    s0 = eng.stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for a, b in evs:
+        a.record()
+        s.run(args.phase_steps, 0)
+        b.record()
+    torch.cuda.synchronize()
+    count = s.global_best()
+    s1 = eng.stats()
+    sampler.stop_flag = True
+    sampler.join()
+    lay = s.best_layout()            # re-validated by kernel (a) inside the engine
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tt = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(s1["candidates_scored"] - s0["candidates_scored"]), float(s1["kernel_launches"] - s0["kernel_launches"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ms = float(tt.item())
+        line = {"metric": METRIC, "value": float(tot[0].item()) / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitboards / bool", "data": "synthetic",
+                "config": {"workload": "synthetic 256x256 random ceiling mask (density 0.7), 1x1 supports, SLS portfolio with all-reduce-min bound (BASELINE.json configs[3])",
+                           "phase_steps": args.phase_steps, "chains_per_window": 16, "parallelism": f"portfolio x{world}: window decomposition per GPU, winner's layout shipped after every phase"},
+                "gpu_launches": int(tot[1].item()), "best_count": count, "layout_platforms": lay.platform_count(), "ceiling_tiles": int(g.data.sum()),
+                "phases_total": W + K, "clocks": sampler.summary(),
+                "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8, "note": "not measured in this mode (device-resident portfolio)"}}
+        print(json.dumps(line), flush=True)
+    s.close()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,9 +302,17 @@ def main():
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = fill the device: 3 CTAs x 128 one-thread chains per SM)")
     ap.add_argument("--kernel", type=int, default=0, help="SLS kernel variant (tss.h TSS_KERNEL_*: 0 auto, 1 warp, 2 half-warp, 3 thread)")
     ap.add_argument("--quick", action="store_true", help="skip the side measurements (peaks, eval/cnf kernels, cpu baseline)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"], help="c2 = the bench line (rect 16x16); c4 / c5 = the other named configs, for context")
+    ap.add_argument("--terrains", type=int, default=100000, help="c5: terrains in the batch")
+    ap.add_argument("--batch-steps", type=int, default=2000, help="c5: SLS steps per chain")
+    ap.add_argument("--phase-steps", type=int, default=4000, help="c4: SLS steps per window-decomposition phase")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "c5":
+        return run_c5(args)
+    if args.workload == "c4":
+        return run_c4(args)
 
     import torch
     import torch.distributed as dist
