@@ -219,6 +219,11 @@ int tss_search_n_chains(const tss_search* s);
 /* Introspection for the parity tests (the CPU model in oracle/sls_model.cpp replays the same trajectories): per-chain
  * state after the last epoch.  S / best_S: support rows u32[n_chains][32]; any pointer may be NULL. */
 int tss_search_read_chains(tss_search* s, uint32_t* S, uint32_t* best_S, int32_t* k, int32_t* best, uint32_t* step, uint64_t* scored);
+/* Warm start: replaces every chain's CURRENT layout by the given support rows (u32[n_chains][32], row r of chain c at
+ * S[c*32 + r], bit x = support at (x, r); bits outside the grid are an error).  Best layouts, bounds and step counters are
+ * kept; the next epoch continues from these layouts (the drivers' natural seed is the layout of the previous solve,
+ * crates/repl/src/main.rs:331-346).  Only for the 1x1 search on grids up to 32x32. */
+int tss_search_write_chains(tss_search* s, const uint32_t* S);
 
 /* GUI objective (crates/gui/src/app.rs:53-62,235-245): minimise PlatformLayout::total_weight (platform_layout.rs:174-183)
  * instead of the platform count.  weights = records (def_w, def_h, weight) keyed by canonical def dims, exactly the

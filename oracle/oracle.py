@@ -292,7 +292,7 @@ def solver_loop(grid, defs, initial_limit=None, conflict_budget=-1):
 
 
 # --------------------------------------------------------------------------- SLS model (oracle/sls_model.cpp)
-def sls_model(grid, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, share_bound=True):
+def sls_model(grid, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, share_bound=True, init_S=None):
     """Replays kernel (b)'s published step rule on the CPU.  epochs: [(steps, bound, target)].
     -> dict(S uint8[n,32,32], bestS, k, best, step, scored, steps)"""
     g = _grid(grid)
@@ -302,6 +302,7 @@ def sls_model(grid, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, shar
             split.append((min(steps_, 32768), bound_, target_))
             steps_ -= 32768
     ep = np.ascontiguousarray(split, dtype=np.int64).reshape(-1, 3)
+    init = None if init_S is None else np.ascontiguousarray(init_S, np.uint8).reshape(n_chains, 32, 32)
     S = np.zeros((n_chains, 32, 32), np.uint8)
     bestS = np.zeros((n_chains, 32, 32), np.uint8)
     k = np.zeros(n_chains, np.int32)
@@ -310,7 +311,7 @@ def sls_model(grid, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, shar
     scored = np.zeros(n_chains, np.uint64)
     steps = np.zeros(n_chains, np.uint64)
     rc = lib().tsso_sls_model(_p(g, C.c_uint8), g.shape[1], g.shape[0], n_chains, C.c_uint32(chain_offset), C.c_uint64(seed), noise_pct,
-                              _p(ep, C.c_longlong), len(ep), int(share_bound), _p(S, C.c_uint8), _p(bestS, C.c_uint8), _p(k), _p(best),
+                              _p(ep, C.c_longlong), len(ep), int(share_bound), _p(init, C.c_uint8) if init is not None else None, _p(S, C.c_uint8), _p(bestS, C.c_uint8), _p(k), _p(best),
                               _p(step, C.c_uint32), _p(scored, C.c_uint64), _p(steps, C.c_uint64))
     assert rc == 0
     return dict(S=S, bestS=bestS, k=k, best=best, step=step, scored=scored, steps=steps)

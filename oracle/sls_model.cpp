@@ -183,15 +183,21 @@ extern "C" {
 // epochs: records (steps, epoch_bound, target); between epochs the caller-visible state is what the kernel persists.
 // If share_bound != 0 the bound of epoch e+1 is min(given bound, best over all chains after epoch e) — the
 // portfolio's all-reduce-min.
+// init_S (nullable): u8[n_chains][1024] start layouts.
 // Outputs per chain: S and bestS as u8[1024] (index y*32+x), k, best, step, scored (u64), steps_done (u64).
 int tsso_sls_model(const uint8_t* grid, int w, int h, int n_chains, uint32_t chain_offset, uint64_t seed, int noise_pct,
-                   const long long* epochs, int n_epochs, int share_bound, uint8_t* out_S, uint8_t* out_bestS, int* out_k,
+                   const long long* epochs, int n_epochs, int share_bound, const uint8_t* init_S, uint8_t* out_S, uint8_t* out_bestS, int* out_k,
                    int* out_best, uint32_t* out_step, uint64_t* out_scored, uint64_t* out_steps) {
     if (w > 32 || h > 32) return -1;
     Model M;
     M.build(grid, w, h);
     std::vector<Chain> chains(n_chains);
     for (auto& c : chains) { c.S.assign(1024, 0); c.bestS.assign(1024, 0); c.cnt.assign(1024, 0); }
+    if (init_S)  // warm start (tss_search_write_chains): current layouts given, k = number of supports
+        for (int i = 0; i < n_chains; i++) {
+            chains[i].S.assign(init_S + (size_t)i * 1024, init_S + (size_t)(i + 1) * 1024);
+            chains[i].k = (int)std::count(chains[i].S.begin(), chains[i].S.end(), (uint8_t)1);
+        }
     int shared = NO_BOUND;
     for (int e = 0; e < n_epochs; e++) {
         long long steps = epochs[3 * e];

@@ -304,6 +304,41 @@ def test_sls_long_epochs_split_at_32768_steps(eng):
         s.close()
 
 
+@pytest.mark.parametrize("shape,kernel", [((16, 16), k) for k in (1, 2, 3)] + [((21, 16), k) for k in (2, 3)] + [((32, 32), 1)])
+def test_sls_warm_start_dense_layouts_bit_exact(eng, fixtures, shape, kernel):
+    """tss_search_write_chains: chains start from given layouts.  Dense starts (every tile / every other tile a support)
+    drive the cover counts up to 25 per tile, i.e. through all five count planes (the thread kernel keeps the two high
+    planes in global memory), and the chains then shed supports one by one: still bit-identical with the CPU model."""
+    w, h = shape
+    grid = {(16, 16): np.ones((16, 16), np.uint8), (21, 16): fixtures["ex2"]}.get(shape)
+    if grid is None:
+        grid = synth_terrain(w, h, seed=1, t=2)
+    n_chains = 40 if kernel == T.KERNEL_THREAD else 10
+    rng = np.random.default_rng(5)
+    init = np.zeros((n_chains, 32, 32), np.uint8)
+    for c in range(n_chains):
+        dens = [1.0, 0.5, 0.25, 0.1][c % 4]
+        init[c, :h, :w] = (rng.random((h, w)) < dens) & ((grid != 0) | (c % 8 >= 4))     # some chains also get supports under non-ceiling tiles
+    rows = (init.astype(np.uint32) << np.arange(32, dtype=np.uint32)).sum(2, dtype=np.uint32)
+    epochs = [(120, 1 << 20, -1), (200, 1 << 20, -1)]
+    s = eng.search(T.WorldGrid(grid), seed=4, n_chains=n_chains, chain_offset=7, kernel=kernel)
+    s.write_chains(rows)
+    for steps, _, target in epochs:
+        s.run(steps, target)
+    got = s.read_chains()
+    want = O.sls_model(grid, n_chains, epochs, seed=4, chain_offset=7, share_bound=True, init_S=init)
+    unpack = lambda r: ((r[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8)
+    for key in ("k", "best", "step", "scored"):
+        assert np.array_equal(got[key], want[key]), key
+    assert np.array_equal(unpack(got["S"]), want["S"]) and np.array_equal(unpack(got["bestS"]), want["bestS"])
+    s.close()
+    with pytest.raises(T.TssError):   # supports outside the grid are rejected
+        s2 = eng.search(T.WorldGrid(np.ones((5, 5), np.uint8)), n_chains=2)
+        bad = np.zeros((2, 32), np.uint32)
+        bad[1, 2] = 1 << 7
+        s2.write_chains(bad)
+
+
 def test_kernel_variant_rejected_when_grid_does_not_fit(eng):
     with pytest.raises(T.TssError):
         eng.search(T.WorldGrid(np.ones((20, 20), np.uint8)), n_chains=8, kernel=T.KERNEL_THREAD)

@@ -409,6 +409,12 @@ class Search:
                                                                    _ptr(best, C.c_int32), _ptr(step, C.c_uint32), _ptr(scored, C.c_uint64)))
         return dict(S=S, bestS=bestS, k=k, best=best, step=step, scored=scored)
 
+    def write_chains(self, S):
+        """Warm start: S uint32[n_chains, 32] support rows become every chain's current layout."""
+        S = np.ascontiguousarray(S, np.uint32)
+        assert S.shape == (self.n_chains, 32)
+        self.engine._check(self.engine.lib.tss_search_write_chains(self._h, _ptr(S, C.c_uint32)))
+
     def best_layout(self) -> PlatformLayout:
         out = (_Platform * (self.grid.data.size + 1))()
         n = C.c_int32()

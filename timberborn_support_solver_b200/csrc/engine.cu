@@ -713,6 +713,29 @@ int tss_search_read_chains(tss_search* s, uint32_t* S, uint32_t* best_S, int32_t
     return TSS_OK;
 }
 
+int tss_search_write_chains(tss_search* s, const uint32_t* S) {
+    if (!s) return TSS_E_INVALID;
+    tss_engine* e = s->e;
+    if (!S) return e->fail(TSS_E_INVALID, "tss_search_write_chains: null layout");
+    if (s->lns || s->multi) return e->fail(TSS_E_UNSUPPORTED, "tss_search_write_chains: only the 1x1 search on grids up to 32x32 takes a warm start");
+    int rc = search_sync(s);
+    if (rc) return rc;
+    const uint32_t colmask = s->w >= 32 ? 0xffffffffu : ((1u << s->w) - 1u);
+    for (size_t c = 0; c < (size_t)s->n_chains; c++)
+        for (int r = 0; r < 32; r++)
+            if (S[c * 32 + r] & (r < s->h ? ~colmask : 0xffffffffu)) return e->fail(TSS_E_INVALID, "tss_search_write_chains: chain %zu has a support outside the grid (row %d)", c, r);
+    std::vector<sls::ChainState> st((size_t)s->n_chains);
+    TSS_CUDA(e, cudaMemcpy(st.data(), s->states, sizeof(sls::ChainState) * st.size(), cudaMemcpyDeviceToHost));
+    for (size_t c = 0; c < st.size(); c++) {
+        int k = 0;
+        for (int r = 0; r < 32; r++) { st[c].S[r] = S[c * 32 + r]; k += __builtin_popcount(S[c * 32 + r]); }
+        st[c].k = k;
+        st[c].done = 0;
+    }
+    TSS_CUDA(e, cudaMemcpy(s->states, st.data(), sizeof(sls::ChainState) * st.size(), cudaMemcpyHostToDevice));
+    return TSS_OK;
+}
+
 int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_t* n_out) {
     if (!s || !n_out) return TSS_E_INVALID;
     tss_engine* e = s->e;
