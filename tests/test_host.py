@@ -184,3 +184,30 @@ def build_c_abi_smoke(tmp_path):
 def test_header_is_plain_c_and_links(tmp_path):
     exe = build_c_abi_smoke(tmp_path)
     assert os.path.exists(exe)
+
+
+def test_render_world_matches_the_repl_printout_rules():
+    """crates/repl/src/main.rs:390-480: glyph + two spaces per tile; 1x1 = '☐', larger platforms as an outline (interior
+    blank, straight runs as lines), ceiling '▒', unsupported ceiling yellow, overlapping platforms red, tiles outside the
+    grid dropped.  Expected strings derived by hand from the reference's match arms and its NSWE glyph table."""
+    grid = np.ones((5, 6), np.uint8)
+    grid[4, :] = 0
+    world = T.World(T.WorldGrid(grid))
+    lay = T.PlatformLayout([T.Platform(0, 0, T.PlatformDef(3, 3)), T.Platform(4, 0, T.PlatformDef(1, 3)), T.Platform(3, 3, T.PlatformDef(1, 3), rotated=True),
+                            T.Platform(5, 1, T.PlatformDef(1, 1))])
+    text = T.render_world(world, lay)
+    want = ["┌  ─  ┐  ▒  ╷  ▒  ",
+            "│     │  ▒  │  ☐  ",
+            "└  ─  ┘  ▒  ╵  ▒  ",
+            "▒  ▒  ▒  ╶  ─  ╴  ",
+            "                  "]
+    assert text == "".join(r + "\n" for r in want)
+    # no layout: the terrain alone (main.rs:244)
+    assert T.render_world(world).splitlines()[0] == "▒  " * 6 and T.render_world(world).splitlines()[4] == "   " * 6
+    # colours and clipping: an out-of-bounds 1x2 platform keeps its in-grid tile, drawn red because it overlaps another one
+    a, b = T.Platform(5, 3, T.PlatformDef(1, 2), rotated=True), T.Platform(5, 3, T.PlatformDef(1, 1))
+    val = T.ValidationResult({(0, 0)}, {a}, {a})
+    text = T.render_world(world, T.PlatformLayout([a]), val, color=True)
+    rows = text.splitlines()
+    assert rows[0].startswith("\x1b[33m▒\x1b[39m  ▒  ") and rows[3].endswith("\x1b[31m╶\x1b[39m  ")
+    assert b.overlaps(a)

@@ -327,6 +327,50 @@ class PlatformLayout:
         return int(_lib.load().tss_layout_total_weight(_plat_array(plats), len(plats), _ptr(wts, C.c_int32), len(wts)))
 
 
+# Box-drawing glyph by the directions a platform tile CONNECTS to, index = N<<3 | S<<2 | W<<1 | E
+# (crates/repl/src/main.rs:524-549)
+_BOX = " ╶╴─╷┌┐┬╵└┘┴│├┤┼"
+
+
+def render_world(world: World, layout: Optional[PlatformLayout] = None, validation: Optional[ValidationResult] = None, color: bool = False) -> str:
+    """The REPL's map printout (crates/repl/src/main.rs:390-480): one glyph + two spaces per tile, one line per grid row.
+    Empty = ' ', ceiling = '▒' (yellow when unsupported), 1x1 platform = '☐', larger platforms as an outline of box
+    characters (interior blank, straight runs drawn as │ / ─), overlapping platforms red.  Platform tiles outside the
+    grid are dropped.  `color` adds the ANSI sequences owo-colors emits (ESC[33m / ESC[31m ... ESC[39m)."""
+    g = world.grid()
+    h, w = g.height, g.width
+    unsupported = validation.unsupported_terrain if validation else set()
+    overlapping = validation.overlapping_platforms if validation else set()
+    paint = (lambda t, c: f"\x1b[{c}m{t}\x1b[39m") if color else (lambda t, c: t)
+    cells = [[" "] * w for _ in range(h)]
+    for y in range(h):
+        for x in range(w):
+            if g.data[y, x]:
+                cells[y][x] = paint("▒", 33) if (x, y) in unsupported else "▒"
+    for plat in (layout.platforms().values() if layout else ()):
+        pw, ph = plat.dims()
+        red = plat in overlapping
+        for ry in range(ph):
+            for rx in range(pw):
+                x, y = plat.x + rx, plat.y + ry
+                if not (0 <= x < w and 0 <= y < h):
+                    continue
+                # open = no platform tile of this platform in that direction
+                n_open, s_open, w_open, e_open = ry == 0, ry == ph - 1, rx == 0, rx == pw - 1
+                if n_open and s_open and w_open and e_open:
+                    glyph = "☐"
+                else:
+                    if not (n_open or s_open or w_open or e_open):      # interior: blank
+                        n_open = s_open = w_open = e_open = True
+                    elif not (n_open or s_open):                          # vertical run: ignore the sides
+                        w_open = e_open = True
+                    elif not (w_open or e_open):                          # horizontal run
+                        n_open = s_open = True
+                    glyph = _BOX[(not n_open) << 3 | (not s_open) << 2 | (not w_open) << 1 | (not e_open)]
+                cells[y][x] = paint(glyph, 31) if red else glyph
+    return "".join("".join(c + "  " for c in row) + "\n" for row in cells)
+
+
 # ------------------------------------------------------------------------------------------------- engine
 class DeviceCnf:
     def __init__(self, engine: "Engine", cnf: Cnf):
