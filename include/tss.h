@@ -219,6 +219,11 @@ int tss_search_n_chains(const tss_search* s);
 /* Introspection for the parity tests (the CPU model in oracle/sls_model.cpp replays the same trajectories): per-chain
  * state after the last epoch.  S / best_S: support rows u32[n_chains][32]; any pointer may be NULL. */
 int tss_search_read_chains(tss_search* s, uint32_t* S, uint32_t* best_S, int32_t* k, int32_t* best, uint32_t* step, uint64_t* scored);
+/* Same for the placement search (platform sets beyond {1x1}): items / best_items u16[n_chains][1024], a placement is
+ * key << 10 | y << 5 | x with key indexing key_dims (effective (w, h) per dims key: defs order, unflipped then flipped,
+ * src/encoder.rs:121-130; room for 16 entries); best = best objective value (platform count or total weight). */
+int tss_search_read_placements(tss_search* s, uint16_t* items, int32_t* k, uint16_t* best_items, int32_t* best_k, int32_t* best, uint32_t* step,
+                               tss_dims* key_dims, int32_t* n_keys);
 /* Warm start: replaces every chain's CURRENT layout by the given support rows (u32[n_chains][32], row r of chain c at
  * S[c*32 + r], bit x = support at (x, r); bits outside the grid are an error).  Best layouts, bounds and step counters are
  * kept; the next epoch continues from these layouts (the drivers' natural seed is the layout of the previous solve,

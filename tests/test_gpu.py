@@ -416,6 +416,46 @@ def oracle_min_weight(grid, defs, weights):
         limit = best - 1
 
 
+@pytest.mark.parametrize("case", ["ex1", "ex3", "ex2", "random-set", "weights"])
+def test_placement_search_trajectories_bit_exact_vs_model(eng, fixtures, case):
+    """The placement search (platform sets beyond {1x1}: what the REPL solves) against its scalar CPU model
+    (oracle/slsm_model.cpp): every chain's placements in list order, best layout, objective value and step counter agree
+    bit for bit across epochs, and so do the engine's candidate / step counters."""
+    defs, weights = list(T.PLATFORMS_DEFAULT), None
+    if case in ("ex1", "ex3", "ex2"):
+        grid = fixtures[case]
+    elif case == "random-set":
+        grid = synth_terrain(20, 17, seed=3, t=1)
+        defs = [T.PlatformDef(1, 1), T.PlatformDef(2, 3), T.PlatformDef(2, 2), T.PlatformDef(1, 4), T.PlatformDef(4, 4)]
+    else:
+        grid = synth_terrain(14, 12, seed=5, t=2, density_q24=int(0.85 * (1 << 24)))
+        weights = {T.PlatformDef(1, 1): 3, T.PlatformDef(1, 3): 2, T.PlatformDef(3, 3): 4, T.PlatformDef(5, 5): 7}
+    n_chains, offset, seed = 6, 50, 9
+    epochs = [(40, 1 << 20, 0), (150, 1 << 20, 0), (400, 1 << 20, 0)]
+    s = eng.search(T.WorldGrid(grid), defs, seed=seed, n_chains=n_chains, chain_offset=offset)
+    if weights:
+        s.set_weights(weights)
+    st0 = eng.stats()
+    for steps, _, target in epochs:
+        s.run(steps, target)
+    got = s.read_placements()
+    st1 = eng.stats()
+    key_dims = got["key_dims"]
+    costs = [1] * len(key_dims)
+    if weights:   # cost of a platform = sum of the weights of every def that fits inside its def (platform_layout.rs:174-183)
+        canon = lambda w, h: (min(w, h), max(w, h))
+        costs = [sum(v for d, v in weights.items() if canon(d.width, d.height)[0] <= canon(w, h)[0] and canon(d.width, d.height)[1] <= canon(w, h)[1])
+                 for w, h in key_dims]
+    want = O.slsm_model(grid, key_dims, costs, n_chains, epochs, seed=seed, chain_offset=offset, share_bound=True)
+    for key in ("k", "best", "best_k", "step"):
+        assert np.array_equal(got[key], want[key]), key
+    assert np.array_equal(got["items"], want["items"]) and np.array_equal(got["best_items"], want["best_items"])
+    assert st1["candidates_scored"] - st0["candidates_scored"] == want["scored_total"]
+    assert st1["sls_steps"] - st0["sls_steps"] == want["steps_total"]
+    assert (want["best"] < (1 << 20)).any()       # the comparison covered complete layouts, not just the greedy build-up
+    s.close()
+
+
 def test_gui_weight_objective_matches_exact_minimum(eng, fixtures):
     """§8f rank 2: the GUI minimises PlatformLayout::total_weight (platform_layout.rs:174-183) under a PB bound.  The GPU
     search with the same weights reaches the minimum the oracle loop proves, with valid layouts whose total_weight is

@@ -88,6 +88,7 @@ SIGNATURES = {
     "tss_comm_world": (C.c_int, [_vp]),
     "tss_search_read_chains": (C.c_int, [_vp, _u32p, _u32p, _i32p, _i32p, _u32p, _P(C.c_uint64)]),
     "tss_search_write_chains": (C.c_int, [_vp, _u32p]),
+    "tss_search_read_placements": (C.c_int, [_vp, _P(C.c_uint16), _i32p, _P(C.c_uint16), _i32p, _i32p, _u32p, _P(Dims), _i32p]),
     "tss_sls_spec_probe": (None, [_u32p]),
     "tss_search_set_weights": (C.c_int, [_vp, _i32p, _i32]),
     "tss_solve_min_weight": (C.c_int, [_vp, _u8p, _i32, _i32, _P(Dims), _i32, _i32p, _i32, _i64, _u64, _i32, _i64, _P(Platform), _i32, _i32p, _i64p]),

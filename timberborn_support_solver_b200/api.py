@@ -453,6 +453,23 @@ class Search:
                                                                    _ptr(best, C.c_int32), _ptr(step, C.c_uint32), _ptr(scored, C.c_uint64)))
         return dict(S=S, bestS=bestS, k=k, best=best, step=step, scored=scored)
 
+    def set_weights(self, weights: dict):
+        """GUI objective (crates/gui/src/app.rs:53-62): {PlatformDef: weight}; the search then minimises total_weight."""
+        wts = np.array([[d.width, d.height, v] for d, v in weights.items()], np.int32).reshape(-1, 3)
+        self.engine._check(self.engine.lib.tss_search_set_weights(self._h, _ptr(wts, C.c_int32), len(wts)))
+
+    def read_placements(self) -> dict:
+        """Per-chain state of the placement search (platform sets beyond {1x1}) after the last epoch."""
+        n = self.n_chains
+        items, best_items = np.zeros((n, 1024), np.uint16), np.zeros((n, 1024), np.uint16)
+        k, best_k, best = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        step = np.zeros(n, np.uint32)
+        kd = (_Dims * 16)()
+        nk = C.c_int32()
+        self.engine._check(self.engine.lib.tss_search_read_placements(self._h, _ptr(items, C.c_uint16), _ptr(k, C.c_int32), _ptr(best_items, C.c_uint16),
+                                                                       _ptr(best_k, C.c_int32), _ptr(best, C.c_int32), _ptr(step, C.c_uint32), kd, C.byref(nk)))
+        return dict(items=items, k=k, best_items=best_items, best_k=best_k, best=best, step=step, key_dims=[(kd[i].w, kd[i].h) for i in range(nk.value)])
+
     def write_chains(self, S):
         """Warm start: S uint32[n_chains, 32] support rows become every chain's current layout."""
         S = np.ascontiguousarray(S, np.uint32)

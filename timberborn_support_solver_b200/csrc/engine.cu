@@ -45,6 +45,8 @@ int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* 
              uint32_t chain_offset, uint64_t seed, long long steps, int* bounds_dev, int target, int noise_pct, unsigned long long* totals_dev,
              int2* best_dev);
 int slsm_read_best(tss_engine* e, const void* states, int chain, std::vector<uint16_t>& codes);
+int slsm_read_states(tss_engine* e, const void* states, int n_chains, uint16_t* items, int32_t* k, uint16_t* best_items, int32_t* best_k,
+                     int32_t* best, uint32_t* step);
 
 // u8 grids [n][w*h] -> rows32 [n][32] (one u32 per row, rows >= h are zero); w, h <= 32
 __global__ void pack_rows32_kernel(const uint8_t* __restrict__ bytes, int w, int h, long long n, uint32_t* __restrict__ out) {
@@ -711,6 +713,19 @@ int tss_search_read_chains(tss_search* s, uint32_t* S, uint32_t* best_S, int32_t
         if (scored) scored[c] = ((uint64_t)st[c].scored_hi << 32) | st[c].scored_lo;
     }
     return TSS_OK;
+}
+
+int tss_search_read_placements(tss_search* s, uint16_t* items, int32_t* k, uint16_t* best_items, int32_t* best_k, int32_t* best, uint32_t* step,
+                               tss_dims* key_dims, int32_t* n_keys) {
+    if (!s) return TSS_E_INVALID;
+    tss_engine* e = s->e;
+    if (!s->multi) return e->fail(TSS_E_UNSUPPORTED, "tss_search_read_placements: only the placement search (platform sets beyond 1x1 on grids up to 32x32)");
+    int rc = search_sync(s);
+    if (rc) return rc;
+    if (n_keys) *n_keys = (int32_t)s->key_dims.size();
+    if (key_dims)
+        for (size_t i = 0; i < s->key_dims.size(); i++) key_dims[i] = tss_dims{s->key_dims[i].x, s->key_dims[i].y};
+    return slsm_read_states(e, s->mstates, s->n_chains, items, k, best_items, best_k, best, step);
 }
 
 int tss_search_write_chains(tss_search* s, const uint32_t* S) {

@@ -357,4 +357,22 @@ int slsm_read_best(tss_engine* e, const void* states, int chain, std::vector<uin
     return TSS_OK;
 }
 
+// every chain's state -> host arrays (parity tests replay the search on the CPU model); any pointer may be null
+int slsm_read_states(tss_engine* e, const void* states, int n_chains, uint16_t* items, int32_t* k, uint16_t* best_items, int32_t* best_k,
+                     int32_t* best, uint32_t* step) {
+    std::vector<slsm::MultiState> st((size_t)n_chains);
+    TSS_CUDA(e, cudaMemcpy(st.data(), states, sizeof(slsm::MultiState) * st.size(), cudaMemcpyDeviceToHost));
+    for (size_t c = 0; c < st.size(); c++) {
+        const int kc = st[c].k, bk = st[c].best_k;
+        if (kc < 0 || kc > slsm::MAX_ITEMS || bk < 0 || bk > slsm::MAX_ITEMS) return e->fail(TSS_E_CUDA, "corrupt chain state (k = %d, best_k = %d)", kc, bk);
+        if (items) for (int i = 0; i < slsm::MAX_ITEMS; i++) items[c * slsm::MAX_ITEMS + i] = i < kc ? st[c].items[i] : 0;
+        if (best_items) for (int i = 0; i < slsm::MAX_ITEMS; i++) best_items[c * slsm::MAX_ITEMS + i] = i < bk ? st[c].best_items[i] : 0;
+        if (k) k[c] = kc;
+        if (best_k) best_k[c] = bk;
+        if (best) best[c] = st[c].best;
+        if (step) step[c] = st[c].step;
+    }
+    return TSS_OK;
+}
+
 }  // namespace tss
