@@ -17,6 +17,13 @@ template <> struct RowMasksT<8> { static constexpr uint32_t L = 0xFEFEFEFEu, R =
 template <> struct RowMasksT<16> { static constexpr uint32_t L = 0xFFFEFFFEu, R = 0x7FFF7FFFu; };
 template <> struct RowMasksT<32> { static constexpr uint32_t L = 0xFFFFFFFFu, R = 0xFFFFFFFFu; };
 
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+
 template <int WORDS>
 __device__ __forceinline__ void load_words(const uint32_t* __restrict__ p, int wpl, bool vec, uint32_t (&v)[WORDS]) {
     if (WORDS >= 4 && vec) {  // wpl == WORDS and 16-byte aligned bases: layouts are WORDS*4 bytes apart
@@ -51,10 +58,13 @@ __global__ void __launch_bounds__(128) eval_thread_kernel(const uint32_t* __rest
 #pragma unroll
             for (int i = 0; i < WORDS; i++) {
                 const uint32_t x = X[i], next = i + 1 < WORDS ? X[i + 1] : 0u;
-                const uint32_t l = (x << 1) & RowMasksT<ROWBITS>::L, r = (x >> 1) & RowMasksT<ROWBITS>::R;
                 const uint32_t up = ROWBITS == 32 ? prev_old : __funnelshift_l(prev_old, x, ROWBITS);
                 const uint32_t down = ROWBITS == 32 ? next : __funnelshift_r(x, next, ROWBITS);
-                X[i] = (x | l | r | up | down) & C[i];
+                // four 3-input logic ops per word: the row-boundary masks ride along as the third operand
+                uint32_t t = lop3<0xF8>(x, x << 1, RowMasksT<ROWBITS>::L);   // x | ((x << 1) & L)
+                t = lop3<0xF8>(t, x >> 1, RowMasksT<ROWBITS>::R);            // t | ((x >> 1) & R)
+                t = lop3<0xFE>(t, up, down);                                 // t | up | down
+                X[i] = t & C[i];
                 prev_old = x;
             }
         }
