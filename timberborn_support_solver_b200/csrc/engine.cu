@@ -1,5 +1,7 @@
 // Engine, device buffers and the C ABI entry points that touch the GPU (include/tss.h).  Host-only entry points
 // (world / encoder / layout decode) live in capi_host.cpp.
+#include <cstdlib>
+
 #include "engine.hpp"
 
 #include <chrono>
@@ -63,6 +65,31 @@ __global__ void pack_rows32_kernel(const uint8_t* __restrict__ bytes, int w, int
     }
 }
 
+// bounds[i] = min(bounds[i], value) (value = NO_BOUND with reset: a plain fill) — in-stream, no host round trip
+__global__ void bound_min_kernel(int* __restrict__ bounds, int n, int value, bool reset) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) bounds[i] = reset ? value : min(bounds[i], value);
+}
+
+// One-shot solves: the best chain's layout fetched AND re-validated on the device in the same stream as the epoch
+// (kernel (a) in its one-warp form: lane r = row r, validate()'s three ceiling-masked dilations with shuffles,
+// src/encoder/platform_layout.rs:127-141).  out[0..31] = support rows, out[32] = unsupported tiles, out[33] = supports.
+__global__ void witness_kernel(const sls::ChainState* __restrict__ states, const int2* __restrict__ best, const uint32_t* __restrict__ terrain_rows,
+                               uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x, c = best[0].y;
+    const uint32_t S = c >= 0 ? states[c].bestS[lane] : 0u, C = terrain_rows[lane];
+    uint32_t X = S & C;
+    for (int round = 0; round < kTerrainSupportDistance - 1; round++) {
+        uint32_t up = __shfl_up_sync(0xffffffffu, X, 1), down = __shfl_down_sync(0xffffffffu, X, 1);
+        if (lane == 0) up = 0;
+        if (lane == 31) down = 0;
+        X = (X | (X << 1) | (X >> 1) | up | down) & C;
+    }
+    const int unc = __reduce_add_sync(0xffffffffu, __popc(C & ~X)), cnt = __reduce_add_sync(0xffffffffu, __popc(S));
+    out[lane] = S;
+    if (lane == 0) { out[32] = (uint32_t)unc; out[33] = (uint32_t)cnt; }
+}
+
 // best layout rows of every terrain group: out[group][32] = states[best[group].y].bestS (zeros if the group found nothing)
 __global__ void gather_best_rows_kernel(const sls::ChainState* __restrict__ states, const int2* __restrict__ best, int n_groups,
                                         uint32_t* __restrict__ out) {
@@ -109,6 +136,8 @@ struct tss_search {
     uint32_t* site_lists = nullptr;            // [16*26][n_chains rounded to 32] support lists of the thread-per-chain kernel (allocated on first use)
     int kernel = TSS_KERNEL_AUTO;              // tss_search_params.kernel
     unsigned long long* totals_dev = nullptr;  // [2]
+    uint32_t* witness_dev = nullptr;           // [34] rows + check of the best layout (witness_kernel)
+    uint32_t* witness_host = nullptr;          // pinned copy
     unsigned long long* reduce_key_dev = nullptr;  // [1] running (best << 32 | chain) minimum of the wide best-reduce, ~0 between epochs
     int2* best_dev = nullptr;                  // [n_groups]
     int* bounds_dev = nullptr;                 // [n_groups]
@@ -116,6 +145,7 @@ struct tss_search {
     unsigned long long* totals_host = nullptr; // pinned [2]
     unsigned long long totals_seen[2] = {0, 0};
     bool dirty = false;
+    bool timed = false;                        // ev0 / ev1 bracket an epoch of this search
     bool share = false;                        // all-reduce-min the bound over the engine's communicator after every epoch
     int cap_terrains = 0, cap_chains = 0;      // allocated capacity of a batch workspace (tss_solve_batch reuses it)
     tss::LnsSearch* lns = nullptr;             // grids larger than 32x32: window decomposition (lns.cu)
@@ -412,6 +442,8 @@ static void search_free(tss_search* s) {
     cudaFree(s->mstates);
     cudaFree(s->site_lists);
     cudaFree(s->reduce_key_dev);
+    cudaFree(s->witness_dev);
+    if (s->witness_host) cudaFreeHost(s->witness_host);
     cudaFree(s->rows_dev); cudaFree(s->tabs_dev); cudaFree(s->states); cudaFree(s->totals_dev); cudaFree(s->best_dev); cudaFree(s->bounds_dev);
     if (s->best_host) cudaFreeHost(s->best_host);
     if (s->totals_host) cudaFreeHost(s->totals_host);
@@ -425,6 +457,8 @@ static int search_alloc(tss_engine* e, tss_search* s, const uint32_t* rows32_hos
     TSS_CUDA(e, cudaMalloc(&s->states, sizeof(sls::ChainState) * (size_t)s->n_chains));
     TSS_CUDA(e, cudaMalloc(&s->totals_dev, sizeof(unsigned long long) * 2));
     TSS_CUDA(e, cudaMalloc(&s->reduce_key_dev, sizeof(unsigned long long)));
+    TSS_CUDA(e, cudaMalloc(&s->witness_dev, sizeof(uint32_t) * 34));
+    TSS_CUDA(e, cudaHostAlloc((void**)&s->witness_host, sizeof(uint32_t) * 34, cudaHostAllocDefault));
     TSS_CUDA(e, cudaMalloc(&s->best_dev, sizeof(int2) * (size_t)s->n_groups));
     TSS_CUDA(e, cudaMalloc(&s->bounds_dev, sizeof(int) * (size_t)s->n_groups));
     TSS_CUDA(e, cudaHostAlloc((void**)&s->best_host, sizeof(int2) * (size_t)s->n_groups, cudaHostAllocDefault));
@@ -436,23 +470,23 @@ static int search_alloc(tss_engine* e, tss_search* s, const uint32_t* rows32_hos
 static int search_init_device(tss_engine* e, tss_search* s, int n_terrains) {
     TSS_CUDA(e, cudaMemsetAsync(s->totals_dev, 0, sizeof(unsigned long long) * 2, e->stream));
     TSS_CUDA(e, cudaMemsetAsync(s->reduce_key_dev, 0xff, sizeof(unsigned long long), e->stream));
-    std::vector<int> nb((size_t)s->n_groups, sls::NO_BOUND);
-    TSS_CUDA(e, cudaMemcpyAsync(s->bounds_dev, nb.data(), sizeof(int) * nb.size(), cudaMemcpyHostToDevice, e->stream));
+    bound_min_kernel<<<(s->n_groups + 255) / 256, 256, 0, e->stream>>>(s->bounds_dev, s->n_groups, sls::NO_BOUND, true);
+    TSS_CHECK_LAUNCH(e);
+    e->stats.kernel_launches++;
     for (int g = 0; g < s->n_groups; g++) s->best_host[g] = make_int2(sls::NO_BOUND, -1);
     s->totals_host[0] = s->totals_host[1] = 0;
     int rc = sls_build_reach(e, s->rows_dev, n_terrains, s->tabs_dev);
     if (rc) return rc;
-    rc = sls_init_states(e, s->states, s->n_chains);
-    if (rc) return rc;
-    TSS_CUDA(e, cudaStreamSynchronize(e->stream));  // nb is a host temporary
-    return TSS_OK;
+    s->dirty = true;                                      // everything here is in-stream: the first reader synchronises
+    return sls_init_states(e, s->states, s->n_chains);
 }
 
 // Chains that fill the device: 32 warps per SM for the warp kernels (two chains per warp on grids of <= 16 rows),
 // 3 CTAs of 128 threads per SM for the thread-per-chain kernel.
 static int default_chains(const tss_engine* e, int w, int h, int kernel) {
     const bool thread_default = sls_t16_fits(w, h) && (kernel == TSS_KERNEL_AUTO || kernel == TSS_KERNEL_THREAD);
-    return e->prop.multiProcessorCount * (thread_default ? 3 * sls_t16_cta_chains() : (h <= 16 ? 64 : 32));
+    const int per_sm = thread_default ? 3 * sls_t16_cta_chains() : (h <= 16 ? 64 : 32);
+    return e->prop.multiProcessorCount * per_sm;
 }
 
 int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,
@@ -595,6 +629,7 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
         if (rc) return rc;
         TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
         s->dirty = true;
+        s->timed = true;
         e->stats.n_solves++;
         return TSS_OK;
     }
@@ -607,6 +642,7 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
         TSS_CUDA(e, cudaMemcpyAsync(s->best_host, s->best_dev, sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
         TSS_CUDA(e, cudaMemcpyAsync(s->totals_host, s->totals_dev, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, e->stream));
         s->dirty = true;
+        s->timed = true;
         e->stats.n_solves++;
         return TSS_OK;
     }
@@ -633,6 +669,7 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
     TSS_CUDA(e, cudaMemcpyAsync(s->best_host, s->best_dev, sizeof(int2) * (size_t)s->n_groups, cudaMemcpyDeviceToHost, e->stream));
     TSS_CUDA(e, cudaMemcpyAsync(s->totals_host, s->totals_dev, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, e->stream));
     s->dirty = true;
+    s->timed = true;
     e->stats.n_solves++;
     return TSS_OK;
 }
@@ -641,9 +678,12 @@ static int search_sync(tss_search* s) {
     tss_engine* e = s->e;
     if (!s->dirty) return TSS_OK;
     TSS_CUDA(e, cudaStreamSynchronize(e->stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
-    e->stats.device_ms = ms;
+    if (s->timed) {  // (an epoch recorded both events; never query unrecorded ones: the error would stick)
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) cudaGetLastError();
+        e->stats.device_ms = ms;
+        s->timed = false;
+    }
     const unsigned long long t0 = s->lns ? lns_total(s->lns, 0) : s->totals_host[0], t1 = s->lns ? lns_total(s->lns, 1) : s->totals_host[1];
     e->stats.candidates_scored += t0 - s->totals_seen[0];
     e->stats.sls_steps += t1 - s->totals_seen[1];
@@ -689,10 +729,11 @@ int tss_search_set_bound(tss_search* s, int32_t count) {
     int rc = search_sync(s);
     if (rc) return rc;
     if (s->lns) { s->external_bound = count < s->external_bound ? count : s->external_bound; return TSS_OK; }
-    std::vector<int> nb((size_t)s->n_groups);
-    TSS_CUDA(e, cudaMemcpy(nb.data(), s->bounds_dev, sizeof(int) * nb.size(), cudaMemcpyDeviceToHost));
-    for (int& b : nb) b = b < count ? b : count;
-    TSS_CUDA(e, cudaMemcpy(s->bounds_dev, nb.data(), sizeof(int) * nb.size(), cudaMemcpyHostToDevice));
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    bound_min_kernel<<<(s->n_groups + 255) / 256, 256, 0, e->stream>>>(s->bounds_dev, s->n_groups, count, false);   // in-stream, before the next epoch
+    TSS_CHECK_LAUNCH(e);
+    e->stats.kernel_launches++;
+    s->dirty = true;
     return TSS_OK;
 }
 
@@ -875,18 +916,22 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
                           int32_t cap, int32_t* n_out) {
     if (!e) return TSS_E_INVALID;
     if (n_out) *n_out = 0;
-    // One SAT-like call (no budget, no step count: return the first model within the bound) is latency bound: the
-    // half-warp kernel with 64 chains per SM steps every chain in ~3 us.  A call with an effort budget is throughput
-    // bound: the engine default (one chain per thread where the grid fits, 384 chains per SM).
-    const int kernel = (budget_ms <= 0 && max_steps <= 0 && h <= 16) ? TSS_KERNEL_HALF_WARP : TSS_KERNEL_AUTO;
-    tss_search_params p{seed, 0, 0, -1, kernel};
+    // One SAT-like call (no budget, no step count: return the first model within the bound) is latency bound: few
+    // chains per SM step fastest (measured on rect 16x16, profiles/tto_sweep.py: 16 chains per SM on the half-warp kernel
+    // 0.23 ms, 64 per SM 0.34 ms, 128 per SM 0.50 ms per call).  A call with an effort budget is throughput bound: the
+    // engine default (one chain per thread where the grid fits, 384 chains per SM).
+    const bool latency_mode = budget_ms <= 0 && max_steps <= 0 && h <= 16;
+    const int kernel = latency_mode ? TSS_KERNEL_HALF_WARP : TSS_KERNEL_AUTO;
+    const int want_chains = (w > 0 && h > 0) ? (latency_mode ? e->prop.multiProcessorCount * 16 : default_chains(e, w, h, kernel)) : 0;
+    bool only_1x1 = true;
+    for (int i = 0; i < n_defs; i++) only_1x1 = only_1x1 && defs && defs[i].w == 1 && defs[i].h == 1;
+    // (the window-decomposed and the placement search read n_chains differently: leave their defaults)
+    tss_search_params p{seed, (only_1x1 && w <= 32 && h <= 32) ? want_chains : 0, 0, -1, kernel};
     tss_search* s = nullptr;
     e->stats.interrupted = 0;
     e->stats.best_count = -1;
     int rc = TSS_OK;
-    bool only_1x1 = true;
-    for (int i = 0; i < n_defs; i++) only_1x1 = only_1x1 && defs && defs[i].w == 1 && defs[i].h == 1;
-    if (e->cached_search && w > 0 && h > 0 && e->cached_search->n_chains != default_chains(e, w, h, kernel)) {  // sized for another grid class / mode
+    if (e->cached_search && w > 0 && h > 0 && e->cached_search->n_chains != want_chains) {  // sized for another grid class / mode
         search_free(e->cached_search);
         e->cached_search = nullptr;
     }
@@ -926,6 +971,7 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     if (budget_ms <= 0 && max_steps <= 0) max_steps = windowed ? (1 << 16) : (1 << 18);
     int64_t done_steps = 0, epoch = 64;
     int best = -1;
+    const bool in_stream_witness = !s->lns && !s->multi && s->n_groups == 1;   // 1x1 supports on a grid up to 32x32
     while (rc == TSS_OK) {
         if (e->interrupted()) { e->stats.interrupted = 1; break; }
         int64_t steps = epoch;
@@ -933,6 +979,12 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
         if (steps <= 0) break;
         rc = tss_search_run(s, steps, 0);
         if (rc) break;
+        if (in_stream_witness) {  // best layout + its validation ride in the same stream: one synchronisation per epoch
+            witness_kernel<<<1, 32, 0, e->stream>>>(s->states, s->best_dev, s->rows_dev, s->witness_dev);
+            e->stats.kernel_launches++;
+            cudaError_t err = cudaMemcpyAsync(s->witness_host, s->witness_dev, sizeof(uint32_t) * 34, cudaMemcpyDeviceToHost, e->stream);
+            if (err != cudaSuccess) { rc = e->fail(TSS_E_CUDA, "tss_solve_upper_bound: %s", cudaGetErrorString(err)); break; }
+        }
         rc = tss_search_best_count(s, &best);
         if (rc) break;
         done_steps += steps;
@@ -942,7 +994,24 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
         if (epoch < 8192) epoch *= 2;
     }
     int result = TSS_UNKNOWN;
-    if (rc == TSS_OK && best >= 0) {
+    if (rc == TSS_OK && best >= 0 && in_stream_witness) {
+        // the witness of the last epoch, already validated on the device (witness_kernel): unsupported tiles, supports
+        const uint32_t* wr = s->witness_host;
+        if (wr[32] != 0 || (int)wr[33] != best)
+            rc = e->fail(TSS_E_CUDA, "internal error: SLS witness failed validation (%u unsupported tiles, %u supports, expected %d)", wr[32], wr[33], best);
+        if (rc == TSS_OK) {
+            if (n_out) *n_out = best;
+            if (best > cap || !out) rc = e->fail(TSS_E_CAPACITY, "tss_solve_upper_bound: need room for %d platforms", best);
+        }
+        if (rc == TSS_OK) {
+            int n = 0;
+            for (int y = 0; y < h; y++)
+                for (int x = 0; x < w; x++)
+                    if ((wr[y] >> x) & 1u) out[n++] = tss_platform{x, y, 1, 1, 0};
+            e->stats.layouts_evaluated++;
+            result = TSS_SAT;
+        }
+    } else if (rc == TSS_OK && best >= 0) {
         int n = 0;
         rc = tss_search_best_layout(s, out, cap, &n);
         if (n_out) *n_out = n;
