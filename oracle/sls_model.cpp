@@ -107,6 +107,7 @@ struct Runner {
 
     void run(long long steps, int epoch_bound, int target, int noise_pct) {
         if (c.done) return;
+        if (target >= 0 && epoch_bound <= target) return;  // a layout within the target is already known: the epoch does nothing
         // epoch start: site list in row-major order
         c.sites.clear();
         for (int t = 0; t < 1024; t++) if (c.S[t]) c.sites.push_back(t);

@@ -126,6 +126,7 @@ struct Runner {
 
     void run(long long steps, int epoch_bound, int target, int noise_pct) {
         if (c.done) return;
+        if (target >= 0 && epoch_bound <= target) return;  // a layout within the target is already known: the epoch does nothing
         std::memset(cnt, 0, sizeof cnt);
         std::memset(occ, 0, sizeof occ);
         int Wt = 0, cmin = costs[0];

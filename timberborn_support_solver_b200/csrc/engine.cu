@@ -47,6 +47,8 @@ int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* 
              uint32_t chain_offset, uint64_t seed, long long steps, int* bounds_dev, int target, int noise_pct, unsigned long long* totals_dev,
              int2* best_dev);
 int slsm_read_best(tss_engine* e, const void* states, int chain, std::vector<uint16_t>& codes);
+int slsm_witness(tss_engine* e, const void* states, const int2* best_dev, const int2* keys_dev, uint16_t* codes_dev, int4* plats_dev, uint32_t* offsets_dev);
+int slsm_max_items();
 int slsm_read_states(tss_engine* e, const void* states, int n_chains, uint16_t* items, int32_t* k, uint16_t* best_items, int32_t* best_k,
                      int32_t* best, uint32_t* step);
 
@@ -158,6 +160,12 @@ struct tss_search {
     int2* keys_dev = nullptr;
     int* costs_dev = nullptr;
     void* mstates = nullptr;
+    // in-stream witness of one-shot solves: codes u16[1024], (x, y, w, h) records, misc = offsets[2] + evaluator result[4]
+    uint16_t* mw_codes_dev = nullptr;
+    int4* mw_plats_dev = nullptr;
+    uint32_t* mw_misc_dev = nullptr;
+    uint16_t* mw_codes_host = nullptr;         // pinned
+    uint32_t* mw_misc_host = nullptr;          // pinned [8]
 };
 
 using namespace tss;
@@ -440,6 +448,9 @@ static void search_free(tss_search* s) {
     cudaFree(s->keys_dev);
     cudaFree(s->costs_dev);
     cudaFree(s->mstates);
+    cudaFree(s->mw_codes_dev); cudaFree(s->mw_plats_dev); cudaFree(s->mw_misc_dev);
+    if (s->mw_codes_host) cudaFreeHost(s->mw_codes_host);
+    if (s->mw_misc_host) cudaFreeHost(s->mw_misc_host);
     cudaFree(s->site_lists);
     cudaFree(s->reduce_key_dev);
     cudaFree(s->witness_dev);
@@ -555,6 +566,8 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
             s->rows_dev = old->rows_dev; s->keys_dev = old->keys_dev; s->costs_dev = old->costs_dev; s->mstates = old->mstates;
             s->totals_dev = old->totals_dev; s->best_dev = old->best_dev; s->bounds_dev = old->bounds_dev;
             s->best_host = old->best_host; s->totals_host = old->totals_host;
+            s->mw_codes_dev = old->mw_codes_dev; s->mw_plats_dev = old->mw_plats_dev; s->mw_misc_dev = old->mw_misc_dev;
+            s->mw_codes_host = old->mw_codes_host; s->mw_misc_host = old->mw_misc_host;
             delete old;
         } else {
             err = cudaMalloc(&s->rows_dev, sizeof rows);
@@ -566,6 +579,11 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
             if (err == cudaSuccess) err = cudaMalloc(&s->bounds_dev, sizeof(int));
             if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->best_host, sizeof(int2), cudaHostAllocDefault);
             if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->totals_host, sizeof(unsigned long long) * 2, cudaHostAllocDefault);
+            if (err == cudaSuccess) err = cudaMalloc(&s->mw_codes_dev, sizeof(uint16_t) * (size_t)slsm_max_items());
+            if (err == cudaSuccess) err = cudaMalloc(&s->mw_plats_dev, sizeof(int4) * (size_t)slsm_max_items());
+            if (err == cudaSuccess) err = cudaMalloc(&s->mw_misc_dev, sizeof(uint32_t) * 8);
+            if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->mw_codes_host, sizeof(uint16_t) * (size_t)slsm_max_items(), cudaHostAllocDefault);
+            if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->mw_misc_host, sizeof(uint32_t) * 8, cudaHostAllocDefault);
         }
         const int nb = sls::NO_BOUND;
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->rows_dev, rows, sizeof rows, cudaMemcpyHostToDevice, e->stream);
@@ -926,7 +944,10 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     bool only_1x1 = true;
     for (int i = 0; i < n_defs; i++) only_1x1 = only_1x1 && defs && defs[i].w == 1 && defs[i].h == 1;
     // (the window-decomposed and the placement search read n_chains differently: leave their defaults)
-    tss_search_params p{seed, (only_1x1 && w <= 32 && h <= 32) ? want_chains : 0, 0, -1, kernel};
+    // placement search (platform sets beyond {1x1}): 4 chains per SM when only the first model is asked for (measured on
+    // test/ex1-3 with the default-8 set, profiles/c1_timing.py: 0.15 / 0.14 / 0.51 ms against 0.21 / 0.19 / 0.88 ms at 16 per SM)
+    const int multi_chains = (budget_ms <= 0 && max_steps <= 0 && w <= 32 && h <= 32) ? e->prop.multiProcessorCount * 4 : 0;
+    tss_search_params p{seed, (only_1x1 && w <= 32 && h <= 32) ? want_chains : multi_chains, 0, -1, kernel};
     tss_search* s = nullptr;
     e->stats.interrupted = 0;
     e->stats.best_count = -1;
@@ -969,16 +990,36 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     const bool windowed = w > 32 || h > 32;  // the window-decomposed search always holds a complete layout: keep improving it
     const bool first_model_only = budget_ms <= 0 && max_steps <= 0 && !(windowed && card_limit < 0);
     if (budget_ms <= 0 && max_steps <= 0) max_steps = windowed ? (1 << 16) : (1 << 18);
-    int64_t done_steps = 0, epoch = 64;
+    // (a placement-search step costs ~5 us of latency: start with short epochs when the first model is all that is asked for)
+    int64_t done_steps = 0, epoch = (s->multi && first_model_only) ? 16 : 64;
     int best = -1;
     const bool in_stream_witness = !s->lns && !s->multi && s->n_groups == 1;   // 1x1 supports on a grid up to 32x32
+    // First-model mode: chains stop at the first layout within the limit (target = card_limit).  (Queueing several epochs
+    // per synchronisation — later ones do nothing once the bound is within the target, sls_spec.hpp — was measured and lost:
+    // ~20 us of launch / event / copy calls per queued epoch against ~15 us per synchronisation.)
+    const int target = first_model_only ? (card_limit >= 0 ? card_limit : sls::NO_BOUND - 1) : 0;
+    const int burst = 1;
     while (rc == TSS_OK) {
         if (e->interrupted()) { e->stats.interrupted = 1; break; }
-        int64_t steps = epoch;
-        if (max_steps > 0 && done_steps + steps > max_steps) steps = max_steps - done_steps;
-        if (steps <= 0) break;
-        rc = tss_search_run(s, steps, 0);
-        if (rc) break;
+        int queued = 0;
+        for (int b = 0; b < burst && rc == TSS_OK; b++) {
+            int64_t steps = epoch;
+            if (max_steps > 0 && done_steps + steps > max_steps) steps = max_steps - done_steps;
+            if (steps <= 0) break;
+            rc = tss_search_run(s, steps, target);
+            done_steps += steps;
+            queued++;
+            if (epoch < 8192) epoch *= 2;
+        }
+        if (rc || !queued) break;
+        if (s->multi) {  // placements of the best chain + their validation by the platform evaluator, in-stream
+            rc = slsm_witness(e, s->mstates, s->best_dev, s->keys_dev, s->mw_codes_dev, s->mw_plats_dev, s->mw_misc_dev);
+            if (rc == TSS_OK) rc = launch_eval_platforms(e, s->rows_dev, w, h, s->mw_plats_dev, s->mw_misc_dev, 1, (int32_t*)(s->mw_misc_dev + 4), nullptr, nullptr, nullptr);
+            if (rc) break;
+            cudaError_t err = cudaMemcpyAsync(s->mw_codes_host, s->mw_codes_dev, sizeof(uint16_t) * (size_t)slsm_max_items(), cudaMemcpyDeviceToHost, e->stream);
+            if (err == cudaSuccess) err = cudaMemcpyAsync(s->mw_misc_host, s->mw_misc_dev, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, e->stream);
+            if (err != cudaSuccess) { rc = e->fail(TSS_E_CUDA, "tss_solve_upper_bound: %s", cudaGetErrorString(err)); break; }
+        }
         if (in_stream_witness) {  // best layout + its validation ride in the same stream: one synchronisation per epoch
             witness_kernel<<<1, 32, 0, e->stream>>>(s->states, s->best_dev, s->rows_dev, s->witness_dev);
             e->stats.kernel_launches++;
@@ -987,11 +1028,9 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
         }
         rc = tss_search_best_count(s, &best);
         if (rc) break;
-        done_steps += steps;
         if (best == 0) break;
         if (first_model_only && best >= 0) break;
         if (budget_ms > 0 && now_ms() - t0 >= budget_ms) break;
-        if (epoch < 8192) epoch *= 2;
     }
     int result = TSS_UNKNOWN;
     if (rc == TSS_OK && best >= 0 && in_stream_witness) {
@@ -1009,6 +1048,29 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
                 for (int x = 0; x < w; x++)
                     if ((wr[y] >> x) & 1u) out[n++] = tss_platform{x, y, 1, 1, 0};
             e->stats.layouts_evaluated++;
+            result = TSS_SAT;
+        }
+    } else if (rc == TSS_OK && best >= 0 && s->multi) {
+        // misc = {0, n, -, -, unsupported tiles, platforms, overlapping, out of bounds} (platform_layout.rs:187-191)
+        const uint32_t* m = s->mw_misc_host;
+        const int n = (int)m[1];
+        int cost = 0;
+        for (int i = 0; i < n && i < slsm_max_items(); i++) cost += s->key_costs[s->mw_codes_host[i] >> 10];
+        if (m[4] != 0 || m[6] != 0 || m[7] != 0 || (int)m[5] != n || cost != best)
+            rc = e->fail(TSS_E_CUDA, "internal error: SLS witness failed validation (%u unsupported tiles, %u overlapping, %u out of bounds, %d platforms costing %d, expected %d)",
+                         m[4], m[6], m[7], n, cost, best);
+        if (rc == TSS_OK) {
+            if (n_out) *n_out = n;
+            if (n > cap || !out) rc = e->fail(TSS_E_CAPACITY, "tss_solve_upper_bound: need room for %d platforms", n);
+        }
+        if (rc == TSS_OK) {
+            for (int i = 0; i < n; i++) {
+                const uint16_t code = s->mw_codes_host[i];
+                tss_platform pl = s->key_proto[code >> 10];
+                pl.x = code & 31;
+                pl.y = (code >> 5) & 31;
+                out[i] = pl;
+            }
             result = TSS_SAT;
         }
     } else if (rc == TSS_OK && best >= 0) {

@@ -169,6 +169,9 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_kernel(const uint32_t* __re
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chain = blockIdx.x * WARPS + warp;
     const int terrain = chains_per_terrain > 0 ? (blockIdx.x * WARPS) / chains_per_terrain : 0;
+    // a layout within the target is already known for this terrain (found in an earlier epoch): nothing to do.  Lets a host
+    // queue several epochs back to back without a round trip in between (one-shot solves, sls_spec.hpp).
+    if (target >= 0 && bounds[chains_per_terrain > 0 ? terrain : 0] <= target) return;
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) tab[i] = rtabs[(size_t)terrain * 1024 + i];
     __syncthreads();
     if (chain >= n_chains) return;

@@ -100,6 +100,9 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_h16_kernel(const uint32_t* 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, row = lane & 15;
     const int chain = (blockIdx.x * WARPS + warp) * 2 + half;
     const int terrain = chains_per_terrain > 0 ? (blockIdx.x * WARPS * 2) / chains_per_terrain : 0;
+    // a layout within the target is already known for this terrain (found in an earlier epoch): nothing to do.  Lets a host
+    // queue several epochs back to back without a round trip in between (one-shot solves, sls_spec.hpp).
+    if (target >= 0 && bounds[chains_per_terrain > 0 ? terrain : 0] <= target) return;
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) tab[i] = rtabs[(size_t)terrain * 1024 + i];
     __syncthreads();
     const bool exists = chain < n_chains;

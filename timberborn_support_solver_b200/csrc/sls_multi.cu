@@ -182,6 +182,9 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
     __shared__ int costs[MAX_KEYS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chain = blockIdx.x * WARPS + warp;
+    // a layout within the target is already known for this terrain (found in an earlier epoch): nothing to do.  Lets a host
+    // queue several epochs back to back without a round trip in between (one-shot solves, sls_spec.hpp).
+    if (target >= 0 && bounds[0] <= target) return;
     if (threadIdx.x < n_keys) { keys[threadIdx.x] = keys_g[threadIdx.x]; costs[threadIdx.x] = costs_g[threadIdx.x]; }
     __syncthreads();
     int cmin = costs[0];
@@ -322,6 +325,21 @@ __global__ void multi_best_kernel(const MultiState* __restrict__ states, int n_c
     }
 }
 
+// One-shot solves: the best chain's placements as codes + count and as the (x, y, w, h) records / offsets the platform
+// evaluator (kernel (a)) reads, all on the device so fetching and re-validating the witness stay in the epoch's stream.
+__global__ void multi_witness_kernel(const MultiState* __restrict__ states, const int2* __restrict__ best, const int2* __restrict__ keys,
+                                     uint16_t* __restrict__ codes, int4* __restrict__ plats, uint32_t* __restrict__ offsets) {
+    const int c = best[0].y;
+    const int n = c >= 0 ? states[c].best_k : 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int code = states[c].best_items[i];
+        const int2 d = keys[code >> 10];
+        codes[i] = (uint16_t)code;
+        plats[i] = make_int4(code & 31, (code >> 5) & 31, d.x, d.y);
+    }
+    if (threadIdx.x == 0) { offsets[0] = 0; offsets[1] = (uint32_t)n; }
+}
+
 }  // namespace slsm
 
 size_t slsm_state_bytes() { return sizeof(slsm::MultiState); }
@@ -346,6 +364,13 @@ int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* 
     e->stats.kernel_launches += 2;
     return TSS_OK;
 }
+int slsm_witness(tss_engine* e, const void* states, const int2* best_dev, const int2* keys_dev, uint16_t* codes_dev, int4* plats_dev, uint32_t* offsets_dev) {
+    slsm::multi_witness_kernel<<<1, 128, 0, e->stream>>>((const slsm::MultiState*)states, best_dev, keys_dev, codes_dev, plats_dev, offsets_dev);
+    TSS_CHECK_LAUNCH(e);
+    e->stats.kernel_launches++;
+    return TSS_OK;
+}
+int slsm_max_items() { return slsm::MAX_ITEMS; }
 // best items of one chain -> host codes (key << 10 | y << 5 | x)
 int slsm_read_best(tss_engine* e, const void* states, int chain, std::vector<uint16_t>& codes) {
     const slsm::MultiState* st = (const slsm::MultiState*)states + chain;

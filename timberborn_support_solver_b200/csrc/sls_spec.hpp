@@ -19,6 +19,9 @@
 //      ties; sites removed fewer than T steps ago only as a last resort; with probability ~noise% a uniformly random
 //      site of R(t) instead).  T is the chain's tabu tenure, see below.
 //
+// An epoch whose bound is already <= its target (a layout within the target was found in an earlier epoch, or the caller
+// asked for nothing better than what is known) does nothing.
+//
 // Random numbers are counter based, one hash per step plus one multiply per candidate:
 //   hs = fmix32(base ^ step*K1)          one word per (chain, step): bits 0-4 row rotation, 5-9 column rotation,
 //                                        10-16 noise draw (7 bits, compared with noise_q7 = round(noise% * 1.28))

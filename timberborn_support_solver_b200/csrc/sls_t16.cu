@@ -165,6 +165,9 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
     const int tid = threadIdx.x;
     const int chain = blockIdx.x * NT + tid;
     const int terrain = chains_per_terrain > 0 ? (blockIdx.x * NT) / chains_per_terrain : 0;
+    // a layout within the target is already known for this terrain (found in an earlier epoch): nothing to do.  Lets a host
+    // queue several epochs back to back without a round trip in between (one-shot solves, sls_spec.hpp).
+    if (target >= 0 && bounds[chains_per_terrain > 0 ? terrain : 0] <= target) return;
     for (int i = tid; i < 512 + 2 * TAB_PAD; i += NT) {
         const int v = i - TAB_PAD;
         uint2 s = make_uint2(0u, 0u);
