@@ -42,8 +42,8 @@ KERNEL_NAMES = {1: "sls_kernel (one chain per warp)", 2: "sls_h16_kernel (two ch
 KERNEL_NCU = {
     2: {"traffic": 3067392, "traffic_note": "dram bytes of one launch (ncu, 9472 chains x 512 steps): chain states only",
         "ncu": "ALU pipe 72% busy, 276 warp instructions per chain step (profiles/r1_sls_h16_kernel.md)"},
-    3: {"traffic": 11070464, "traffic_note": "dram bytes of one launch (ncu, 56832 chains x 512 steps): chain states + site lists",
-        "ncu": "ALU pipe 70% busy, issue slots 69% busy, 76 warp instructions per chain step (profiles/r1_sls_t16_kernel.md)"},
+    3: {"traffic": 11065344, "traffic_note": "dram bytes of one launch (ncu, 56832 chains x 512 steps): chain states + site lists",
+        "ncu": "ALU pipe 75.5% busy, issue slots 72% busy, 73 warp instructions per chain step, 17.8 shared-memory wavefronts per chain step (profiles/r1_sls_t16_kernel.md)"},
 }
 
 
