@@ -248,7 +248,7 @@ def run_c4(args):
     if world > 1:
         comm_init(eng, torch, dist, rank, world)
     g = T.WorldGrid.synthetic(256, 256, 1, 0)
-    s = eng.search(g, seed=1, n_chains=16, chain_offset=rank * 1000000)
+    s = eng.search(g, seed=1, n_chains=args.chains, chain_offset=rank * 1000000)     # 0 = one wave of chains over the windows
     W, K = max(args.warmup, 3), args.steps
     for _ in range(W):
         s.run(args.phase_steps, 0)
@@ -281,7 +281,7 @@ def run_c4(args):
         line = {"metric": METRIC, "value": float(tot[0].item()) / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitboards / bool", "data": "synthetic",
                 "config": {"workload": "synthetic 256x256 random ceiling mask (density 0.7), 1x1 supports, SLS portfolio with all-reduce-min bound (BASELINE.json configs[3])",
-                           "phase_steps": args.phase_steps, "chains_per_window": 16, "parallelism": f"portfolio x{world}: window decomposition per GPU, winner's layout shipped after every phase"},
+                           "phase_steps": args.phase_steps, "chains_total": s.n_chains, "parallelism": f"portfolio x{world}: window decomposition per GPU, winner's layout shipped after every phase"},
                 "gpu_launches": int(tot[1].item()), "best_count": count, "layout_platforms": lay.platform_count(), "ceiling_tiles": int(g.data.sum()),
                 "phases_total": W + K, "clocks": sampler.summary(),
                 "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8, "note": "not measured in this mode (device-resident portfolio)"}}
