@@ -191,7 +191,8 @@ int tss_engine_create(int device, tss_engine** out) {
     e->device = device;
     e->stats.best_count = -1;
     bool ok = cudaGetDeviceProperties(&e->prop, device) == cudaSuccess && cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess;
+              cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess &&
+              cudaEventCreate(&e->ev2) == cudaSuccess && cudaEventCreate(&e->ev3) == cudaSuccess;
     void* flag = nullptr;
     ok = ok && cudaHostAlloc(&flag, 2 * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
     if (ok) {
@@ -223,6 +224,8 @@ void tss_engine_destroy(tss_engine* e) {
     if (e->interrupt_dev) cudaFree(e->interrupt_dev);
     if (e->interrupt_host) cudaFreeHost((void*)e->interrupt_host);
     if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev2) cudaEventDestroy(e->ev2);
+    if (e->ev3) cudaEventDestroy(e->ev3);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -1134,6 +1137,7 @@ int tss_solve_batch(tss_engine* e, const uint8_t* grids, int32_t w, int32_t h, i
         if (!bytes) { rc = TSS_E_CUDA; break; }
         cudaError_t err = cudaMemcpyAsync(bytes, grids + (size_t)base * tiles, tiles * (size_t)nt, cudaMemcpyHostToDevice, e->stream);
         if (err != cudaSuccess) { rc = e->fail(TSS_E_CUDA, "tss_solve_batch: %s", cudaGetErrorString(err)); break; }
+        cudaEventRecord(e->ev2, e->stream);  // device time of the pass: terrains resident in HBM -> counts / layouts ready
         pack_rows32_kernel<<<e->prop.multiProcessorCount * 8, 256, 0, e->stream>>>(bytes, w, h, nt, s->rows_dev);
         e->stats.kernel_launches++;
         rc = search_init_device(e, s, nt);
@@ -1153,9 +1157,12 @@ int tss_solve_batch(tss_engine* e, const uint8_t* grids, int32_t w, int32_t h, i
             err = cudaMemcpyAsync(rows_host, rows_dev, sizeof(uint32_t) * 32 * (size_t)nt, cudaMemcpyDeviceToHost, e->stream);
             if (err != cudaSuccess) { rc = e->fail(TSS_E_CUDA, "tss_solve_batch: %s", cudaGetErrorString(err)); break; }
         }
+        if (rc == TSS_OK) cudaEventRecord(e->ev3, e->stream);
         if (rc == TSS_OK) rc = search_sync(s);
         if (rc == TSS_OK) {
-            dev_ms += e->stats.device_ms;
+            float pass_ms = 0;
+            if (cudaEventElapsedTime(&pass_ms, e->ev2, e->ev3) != cudaSuccess) cudaGetLastError();
+            dev_ms += pass_ms;
             for (int t = 0; t < nt; t++) out_counts[base + t] = s->best_host[t].x >= sls::NO_BOUND ? -1 : s->best_host[t].x;
             if (out_layouts)
                 for (int t = 0; t < nt; t++)

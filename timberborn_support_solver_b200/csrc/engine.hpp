@@ -32,7 +32,8 @@ struct tss_engine {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;  // own_stream or a caller-provided one
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the last kernel-level operation (epoch, evaluation)
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;  // bracket a whole multi-epoch pass (tss_solve_batch chunk)
     cudaDeviceProp prop{};
     std::string error;
     tss_stats stats{};

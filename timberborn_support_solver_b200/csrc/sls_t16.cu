@@ -10,8 +10,9 @@
 // The step rule, RNG and tie-breaks are EXACTLY those of sls_spec.hpp: the parity tests replay this kernel against the
 // same CPU model as sls.cu / sls_h16.cu (bit-identical trajectories).  Implementation choices that differ:
 //   * columns are stored shifted left by 3 and the reach windows re-anchored at x-3 when the table is loaded, so a
-//     window row is always `(row >> x) & 0x7f` (no anchor clamp); rows are addressed modulo 16 (rows outside the grid
-//     meet zero window bits);
+//     window row is always `(row >> x) & 0x7f` (no anchor clamp); the boards sit back to back and a row is one LDS at an
+//     immediate offset from the site's row: rows outside the grid alias a neighbouring board, which is harmless because
+//     they only ever meet zero window bits (reads) or a zero mask (no write);
 //   * the site list lives in global memory as [index][chain] words (coalesced across the warp, L1 resident) and carries
 //     the step at which each support was added — for a current support that IS its last flip, so the "young support"
 //     test of the spec needs no per-site stamp array;
@@ -19,8 +20,13 @@
 //     of the sites removed in the last 32 steps (one slot per step), folded once per step into a 7x7 window mask
 //     around the chosen uncovered tile.  Equivalent to the spec's 16-bit stamps for epochs of at most 32768 steps —
 //     the engine never launches longer ones (tss_search_run splits them).
-//   * add candidates: the 13x13 neighbourhood of the uncovered tile is fetched once into registers; the 25 diamond
-//     cells are then scored with static shifts in a fully unrolled loop.
+//   * add candidates: the 13x13 neighbourhood of the uncovered tile is fetched once into registers; per column offset a
+//     7-bit slab is masked once and the 25 diamond cells are scored with static shifts, packing on the FMA pipe;
+//   * selection keys carry the candidate's index in their low bits, so min / max are single instructions, independent of
+//     the evaluation order, and ties go to the lowest index as the spec demands.
+// ncu (profiles/r1_sls_t16_kernel.md): 73 warp instructions per chain step, ALU pipe 75 %, issue slots 72 %, shared-memory
+// wavefronts 17.8 per chain step (a third of them bank-conflict replays of the random 8-byte reach-table reads).
+// Tried and dropped: the two high count planes in global memory for 4 CTAs per SM (slower: 277 vs 335 G candidates/s).
 #include "engine.hpp"
 #include "sls_spec.hpp"
 
