@@ -313,3 +313,42 @@ def test_survey_optimum_witnesses(fixtures, readme):
         enc = O.Encoding(O.PLATFORMS_1X1, g)
         r, a, _ = _solve_with_units(enc.with_limits({ONE: wit["optimum"]}), None, enc, sup, g)
         assert r == 10
+
+
+# ------------------------------------------------------------------------------------------------ SLS models (CPU side)
+def test_sls_model_layouts_validate_and_reach_known_optima(fixtures):
+    """The scalar models of kernel (b) are the yardstick the GPU trajectories are compared with; here they are checked
+    on their own against the restated reference: every best layout they report passes validate() (platform_layout.rs:85-149)
+    with exactly the reported count, never undercuts the proven optimum, and reaches it on the small fixtures."""
+    for name, optimum in (("ex1", 3), ("ex3", 4)):
+        grid = fixtures[name]
+        r = O.sls_model(grid, 12, [(400, 1 << 20, 0), (1500, 1 << 20, 0)], seed=2, share_bound=True)
+        found = r["best"] < (1 << 20)
+        assert found.any() and int(r["best"][found].min()) == optimum
+        for c in np.nonzero(found)[0]:
+            ys, xs = np.nonzero(r["bestS"][c][: grid.shape[0], : grid.shape[1]])
+            v = O.validate(grid, [(int(x), int(y), 1, 1, 0) for x, y in zip(xs, ys)])
+            assert v.is_valid and len(xs) == r["best"][c] >= optimum
+            assert r["bestS"][c].sum() == len(xs)       # nothing outside the grid
+
+
+def test_placement_model_layouts_validate_and_reach_repl_optima(fixtures):
+    key_dims = []
+    for d in O.PLATFORMS_DEFAULT:      # dims keys: defs order, unflipped then flipped (src/encoder.rs:121-130)
+        for dims in ((d[0], d[1]), (d[1], d[0])):
+            if dims not in key_dims:
+                key_dims.append(dims)
+    for name, optimum in (("ex1", 1), ("ex3", 1), ("ex2", 4)):
+        grid = fixtures[name]
+        r = O.slsm_model(grid, key_dims, [1] * len(key_dims), 8, [(100, 1 << 20, 0), (400, 1 << 20, 0)], seed=3)
+        found = r["best"] < (1 << 20)
+        assert found.any() and int(r["best"][found].min()) >= optimum
+        if optimum == 1:    # (ex2's four 5x5 platforms take the GPU's thousands of chains; 8 model chains stop at 5)
+            assert int(r["best"][found].min()) == optimum
+        for c in np.nonzero(found)[0]:
+            plats = []
+            for code in r["best_items"][c][: r["best_k"][c]]:
+                w, h = key_dims[int(code) >> 10]
+                plats.append((int(code) & 31, (int(code) >> 5) & 31, min(w, h), max(w, h), int(w > h)))   # canonical def + rotated flag
+            v = O.validate(grid, plats)
+            assert v.is_valid and len(plats) == r["best"][c] >= optimum
