@@ -78,13 +78,18 @@ struct Runner {
     const Terrain& T;
     const int* keys;   // (w, h) per key
     const int* costs;
+    std::vector<int> order;  // keys by area, largest first (stable)
     int n_keys;
     Chain& c;
     uint32_t base;
     uint8_t cnt[1024], occ[1024];
     uint64_t scored = 0, steps_done = 0;
 
-    Runner(const Terrain& t, const int* k, const int* cs, int nk, Chain& ch, uint32_t b) : T(t), keys(k), costs(cs), n_keys(nk), c(ch), base(b) {}
+    Runner(const Terrain& t, const int* k, const int* cs, int nk, Chain& ch, uint32_t b) : T(t), keys(k), costs(cs), n_keys(nk), c(ch), base(b) {
+        order.resize(nk);
+        for (int i = 0; i < nk; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int bb) { return keys[2 * a] * keys[2 * a + 1] > keys[2 * bb] * keys[2 * bb + 1]; });
+    }
 
     void dims(int code, int& x, int& y, int& w, int& h) const { x = code & 31; y = (code >> 5) & 31; w = keys[2 * (code >> 10)]; h = keys[2 * (code >> 10) + 1]; }
     void apply(int code, int sign) {
@@ -178,7 +183,8 @@ struct Runner {
                 int mx_code = 0, n_inb = 0;
                 for (int l = 0; l < 32; l++) {  // the kernel's 32 lanes, lowest lane wins ties
                     const uint32_t r = lane_hash(hl[l], (uint32_t)(pass + 40));
-                    const int key = (int)(((r & 0xffffu) * (uint32_t)n_keys) >> 16);
+                    const uint32_t u = r & 0xffffu;  // pass 0: uniform key; pass 1: squared draw over the keys sorted by area (largest first)
+                    const int key = pass == 0 ? (int)((u * (uint32_t)n_keys) >> 16) : order[(((u * u) >> 16) * (uint32_t)n_keys) >> 16];
                     const int w = keys[2 * key], h = keys[2 * key + 1];
                     const int x = tx - 3 - (w - 1) + (int)((((r >> 16) & 0xffu) * (uint32_t)(w + 6)) >> 8);
                     const int y = ty - 3 - (h - 1) + (int)(((r >> 24) * (uint32_t)(h + 6)) >> 8);

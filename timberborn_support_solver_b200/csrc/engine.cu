@@ -1,5 +1,6 @@
 // Engine, device buffers and the C ABI entry points that touch the GPU (include/tss.h).  Host-only entry points
 // (world / encoder / layout decode) live in capi_host.cpp.
+#include <algorithm>
 #include <cstdlib>
 
 #include "engine.hpp"
@@ -43,7 +44,7 @@ int lns_chains(const LnsSearch* s);
 size_t slsm_state_bytes();
 int slsm_max_keys();
 int slsm_init(tss_engine* e, void* states, int n);
-int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* keys_dev, const int* costs_dev, int n_keys, void* states, int n_chains,
+int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* keys_dev, const int* costs_dev, const int* order_dev, int n_keys, void* states, int n_chains,
              uint32_t chain_offset, uint64_t seed, long long steps, int* bounds_dev, int target, int noise_pct, unsigned long long* totals_dev,
              int2* best_dev);
 int slsm_read_best(tss_engine* e, const void* states, int chain, std::vector<uint16_t>& codes);
@@ -580,7 +581,7 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
         } else {
             err = cudaMalloc(&s->rows_dev, sizeof rows);
             if (err == cudaSuccess) err = cudaMalloc(&s->keys_dev, sizeof(int2) * (size_t)slsm_max_keys());
-            if (err == cudaSuccess) err = cudaMalloc(&s->costs_dev, sizeof(int) * (size_t)slsm_max_keys());
+            if (err == cudaSuccess) err = cudaMalloc(&s->costs_dev, sizeof(int) * 2 * (size_t)slsm_max_keys());   // costs | keys ordered by area
             if (err == cudaSuccess) err = cudaMalloc(&s->mstates, slsm_state_bytes() * (size_t)s->n_chains);
             if (err == cudaSuccess) err = cudaMalloc(&s->totals_dev, sizeof(unsigned long long) * 2);
             if (err == cudaSuccess) err = cudaMalloc(&s->best_dev, sizeof(int2));
@@ -597,6 +598,10 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->rows_dev, rows, sizeof rows, cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->keys_dev, s->key_dims.data(), sizeof(int2) * s->key_dims.size(), cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->costs_dev, s->key_costs.data(), sizeof(int) * s->key_costs.size(), cudaMemcpyHostToDevice, e->stream);
+        std::vector<int> order(s->key_dims.size());   // keys by area, largest first (stable): the second candidate pass draws from the front
+        for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return s->key_dims[a].x * s->key_dims[a].y > s->key_dims[b].x * s->key_dims[b].y; });
+        if (err == cudaSuccess) err = cudaMemcpyAsync(s->costs_dev + slsm_max_keys(), order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->bounds_dev, &nb, sizeof nb, cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = cudaMemsetAsync(s->totals_dev, 0, sizeof(unsigned long long) * 2, e->stream);
         int rc = err == cudaSuccess ? slsm_init(e, s->mstates, s->n_chains) : e->fail(TSS_E_CUDA, "tss_search_create: %s", cudaGetErrorString(err));
@@ -660,7 +665,7 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
         return TSS_OK;
     }
     if (s->multi) {
-        int rc = slsm_run(e, s->rows_dev, s->w, s->h, s->keys_dev, s->costs_dev, (int)s->key_dims.size(), s->mstates, s->n_chains, s->chain_offset, s->seed, steps,
+        int rc = slsm_run(e, s->rows_dev, s->w, s->h, s->keys_dev, s->costs_dev, s->costs_dev + slsm_max_keys(), (int)s->key_dims.size(), s->mstates, s->n_chains, s->chain_offset, s->seed, steps,
                           s->bounds_dev, target_count < 0 ? -1 : target_count, s->noise, s->totals_dev, s->best_dev);
         if (rc == TSS_OK && e->comm && s->share) rc = comm_allreduce_min(e, e->comm, s->bounds_dev, 1);
         if (rc) return rc;

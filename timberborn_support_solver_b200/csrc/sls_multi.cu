@@ -13,7 +13,10 @@
 // around it with warp shuffles, dilates the footprint three times inside that window in registers (geodesic paths of
 // length <= 3 from the footprint never leave it) and counts popcount(U & reach) resp. popcount(O & reach).
 // A step: drop / swap as in sls_spec.hpp; addition candidates are 2 x 32 random in-bounds placements whose footprint
-// comes within 3 tiles of a random uncovered tile and does not overlap the current platforms.
+// comes within 3 tiles of a random uncovered tile and does not overlap the current platforms.  The first pass draws the
+// dims key uniformly, the second one from the keys sorted by area (largest first) with a squared uniform draw, i.e.
+// biased towards large platforms: with the count objective a well placed large platform replaces several small ones, and
+// uniform draws find e.g. the four 5x5 platforms of test/ex2.toml only with thousands of chains.
 //
 // Objective: every dims key has an integer cost; the search minimises the total cost of the layout.  With all costs 1
 // this is the REPL's platform count.  With the GUI's weights (crates/gui/src/app.rs:53-62) the cost of a platform is
@@ -172,7 +175,8 @@ __device__ __forceinline__ int pick_rotated(uint32_t bits, uint32_t o) {
 }
 
 __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* __restrict__ terrain_rows, int W, int H,
-                                                              const int2* __restrict__ keys_g, const int* __restrict__ costs_g, int n_keys,
+                                                              const int2* __restrict__ keys_g, const int* __restrict__ costs_g,
+                                                              const int* __restrict__ order_g, int n_keys,
                                                               MultiState* __restrict__ states,
                                                               int n_chains, uint32_t chain_offset, uint64_t seed, long long steps,
                                                               const int* __restrict__ bounds, int target, int noise_pct,
@@ -180,12 +184,13 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
     __shared__ uint16_t items_all[WARPS][MAX_ITEMS];
     __shared__ int2 keys[MAX_KEYS];
     __shared__ int costs[MAX_KEYS];
+    __shared__ int order[MAX_KEYS];   // keys by area, largest first
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chain = blockIdx.x * WARPS + warp;
     // a layout within the target is already known for this terrain (found in an earlier epoch): nothing to do.  Lets a host
     // queue several epochs back to back without a round trip in between (one-shot solves, sls_spec.hpp).
     if (target >= 0 && bounds[0] <= target) return;
-    if (threadIdx.x < n_keys) { keys[threadIdx.x] = keys_g[threadIdx.x]; costs[threadIdx.x] = costs_g[threadIdx.x]; }
+    if (threadIdx.x < n_keys) { keys[threadIdx.x] = keys_g[threadIdx.x]; costs[threadIdx.x] = costs_g[threadIdx.x]; order[threadIdx.x] = order_g[threadIdx.x]; }
     __syncthreads();
     int cmin = costs[0];
     for (int i = 1; i < n_keys; i++) cmin = min(cmin, costs[i]);
@@ -254,7 +259,8 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
 #pragma unroll 1
         for (int pass = 0; pass < 2; pass++) {
             const uint32_t r = sls::lane_hash(hl, (uint32_t)(pass + 40));
-            const int key = (int)(((r & 0xffffu) * (uint32_t)n_keys) >> 16);
+            const uint32_t u = r & 0xffffu;
+            const int key = pass == 0 ? (int)((u * (uint32_t)n_keys) >> 16) : order[(((u * u) >> 16) * (uint32_t)n_keys) >> 16];
             const int2 d = keys[key];
             // footprint intersects the 7x7 box around t: x in [tx-3-(w-1), tx+3], y in [ty-3-(h-1), ty+3]
             const int x = tx - 3 - (d.x - 1) + (int)((((r >> 16) & 0xffu) * (uint32_t)(d.x + 6)) >> 8);
@@ -351,11 +357,11 @@ int slsm_init(tss_engine* e, void* states, int n) {
     e->stats.kernel_launches++;
     return TSS_OK;
 }
-int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* keys_dev, const int* costs_dev, int n_keys, void* states, int n_chains,
+int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* keys_dev, const int* costs_dev, const int* order_dev, int n_keys, void* states, int n_chains,
              uint32_t chain_offset, uint64_t seed, long long steps, int* bounds_dev, int target, int noise_pct, unsigned long long* totals_dev,
              int2* best_dev) {
     int blocks = (n_chains + slsm::WARPS - 1) / slsm::WARPS;
-    slsm::sls_multi_kernel<<<blocks, slsm::WARPS * 32, 0, e->stream>>>(rows_dev, W, H, keys_dev, costs_dev, n_keys, (slsm::MultiState*)states, n_chains,
+    slsm::sls_multi_kernel<<<blocks, slsm::WARPS * 32, 0, e->stream>>>(rows_dev, W, H, keys_dev, costs_dev, order_dev, n_keys, (slsm::MultiState*)states, n_chains,
                                                                      chain_offset, seed, steps, bounds_dev, target, noise_pct, e->interrupt_dev,
                                                                      totals_dev);
     TSS_CHECK_LAUNCH(e);
