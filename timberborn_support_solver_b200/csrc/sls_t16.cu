@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
                 const uint32_t stephi = (step << 16) | 0xffffu;             // stephi - entry = (age << 16) + (0xffff - site): no borrow
                 const uint32_t young_below = drop ? 0u : (uint32_t)ten << 16;
                 uint32_t best_key = 0xffffffffu, mult = K3;                 // mult = (2i+1) * K3
-#pragma unroll 2
+#pragma unroll 4
                 for (int i = 0; i < k; i++, mult += 2u * K3) {
                     const uint32_t e = sl[(size_t)i * stride];
                     const int v = (int)(e & 0x1ffu), x = v & 31;
