@@ -507,7 +507,15 @@ def main():
         nf, _ = dev.check(a)
         nf, _ = dev.check(a)
         assert (nf[::64] > 0).all() and nf.reshape(-1, 64)[:, 1:].sum() == 0
-        line["cnf_kernel"] = {"clause_evals_per_s": cnf.n_clauses * len(a) / (eng.stats()["device_ms"] * 1e-3), "clauses": cnf.n_clauses,
+        cnf_ms = eng.stats()["device_ms"]
+        nbw = (len(a) + 31) // 32
+        cnf_bytes = 2 * (cnf.n_vars + 1) * nbw * 4 + 8 * len(a)      # both bit-sliced planes read once + (count, first) per assignment written
+        cnf_ops = len(cnf.lits) * nbw * 32                           # one logic op per literal per 32 assignments (DESIGN.md A_cnf), as thread-ops
+        line["cnf_kernel"] = {"clause_evals_per_s": cnf.n_clauses * len(a) / (cnf_ms * 1e-3), "clauses": cnf.n_clauses, "ms": cnf_ms,
+                              "roofline": {"bound": "hbm", "achieved": cnf_bytes / (cnf_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                           "frac": cnf_bytes / (cnf_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                                           "note": "algorithmic bytes = both assignment planes once + results; the working set (13 MB) is L2 resident and the launch lasts ~15 us, so this is a latency-sized kernel, not a bandwidth one",
+                                           "int_gops": cnf_ops / (cnf_ms * 1e-3) / 1e9},
                               "literals": int(len(cnf.lits)), "assignments": len(a), "propagation_rounds": rounds,
                               "input": "SLS witness completed by unit propagation x 8192, every 64th with one support removed"}
         # ---------------- the other named configs, for context (parity-test cases, not the bench line): wall clock through the C ABI
@@ -523,7 +531,7 @@ def main():
         others["C1 ex1 default-8 (REPL set)"] = {"count": lay3.platform_count(), "proven_optimum": 1, "ms": float(np.median(t1s[2:])),
                                                  "note": "tss_solve_upper_bound(card_limit=1) from host buffers, median of 5 calls after 2 warm-up calls"}
         g4 = T.WorldGrid.synthetic(256, 256, 1, 0)
-        s4 = eng.search(g4, seed=1, n_chains=16)
+        s4 = eng.search(g4, seed=1)          # default: one wave of chains over the windows
         t0 = time.perf_counter()
         for _ in range(24):
             s4.run(4000, 0)
