@@ -339,6 +339,29 @@ def test_sls_warm_start_dense_layouts_bit_exact(eng, fixtures, shape, kernel):
         s2.write_chains(bad)
 
 
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+def test_sls_degenerate_terrains_match_model(eng, kernel):
+    """No ceiling at all (the empty layout is complete at once, chains finish), a single tile, a one-row corridor, a
+    terrain of isolated tiles (every tile needs its own support): every kernel variant agrees with the CPU model."""
+    cases = [np.zeros((4, 7), np.uint8), np.pad(np.ones((1, 1), np.uint8), ((2, 3), (4, 1))), np.ones((1, 26), np.uint8),
+             (np.indices((16, 16)).sum(0) % 2 == 0).astype(np.uint8) * (np.indices((16, 16))[0] % 2 == 0)]
+    for grid in cases:
+        grid = np.ascontiguousarray(grid, np.uint8)
+        epochs = [(30, 1 << 20, 0), (200, 1 << 20, 0)]
+        s = eng.search(T.WorldGrid(grid), seed=2, n_chains=33, chain_offset=3, kernel=kernel)
+        for steps, _, target in epochs:
+            s.run(steps, target)
+        got = s.read_chains()
+        want = O.sls_model(grid, 33, epochs, seed=2, chain_offset=3, share_bound=True)
+        for key in ("k", "best", "step", "scored"):
+            assert np.array_equal(got[key], want[key]), (key, grid.shape)
+        unpack = lambda r: ((r[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8)
+        assert np.array_equal(unpack(got["S"]), want["S"]) and np.array_equal(unpack(got["bestS"]), want["bestS"])
+        best = s.best_count()
+        assert best == int(want["best"].min()) and best == {0: 0, 1: 1, 26: 4}.get(int(grid.sum()), best)
+        s.close()
+
+
 def test_kernel_variant_rejected_when_grid_does_not_fit(eng):
     with pytest.raises(T.TssError):
         eng.search(T.WorldGrid(np.ones((20, 20), np.uint8)), n_chains=8, kernel=T.KERNEL_THREAD)
