@@ -362,6 +362,33 @@ def test_sls_degenerate_terrains_match_model(eng, kernel):
         s.close()
 
 
+@pytest.mark.parametrize("case", ["rect16", "ex2", "random26x16", "random12x9-dense"])
+def test_sls_kernel_variants_agree_at_scale(eng, fixtures, case):
+    """The CPU model is too slow for thousands of chains x tens of thousands of steps; at that scale the independent kernel
+    implementations (thread per chain vs half-warp vs warp) are compared with each other instead: identical chain states,
+    counters and bounds after every epoch, including an epoch longer than the 32768-step split."""
+    grid = {"rect16": np.ones((16, 16), np.uint8), "ex2": fixtures["ex2"], "random26x16": synth_terrain(26, 16, seed=7, t=1),
+            "random12x9-dense": synth_terrain(12, 9, seed=8, t=2, density_q24=int(0.93 * (1 << 24)))}[case]
+    n_chains = 2048 + 77
+    runs = {}
+    for kernel in (T.KERNEL_THREAD, T.KERNEL_HALF_WARP, T.KERNEL_WARP):
+        if kernel == T.KERNEL_WARP and case != "ex2":
+            continue                                # (one three-way comparison is enough; the warp kernel is the slowest)
+        s = eng.search(T.WorldGrid(grid), seed=21, n_chains=n_chains, chain_offset=5, kernel=kernel)
+        snaps = []
+        for steps in (700, 6000, 40000):
+            s.run(steps, 0)
+            snaps.append((s.best_count(), s.global_best()))
+        st = s.read_chains()
+        runs[kernel] = (snaps, st)
+        s.close()
+    ref_snaps, ref = runs[T.KERNEL_THREAD]
+    for kernel, (snaps, st) in runs.items():
+        assert snaps == ref_snaps, kernel
+        for key in ("S", "bestS", "k", "best", "step", "scored"):
+            assert np.array_equal(st[key], ref[key]), (kernel, key)
+
+
 def test_kernel_variant_rejected_when_grid_does_not_fit(eng):
     with pytest.raises(T.TssError):
         eng.search(T.WorldGrid(np.ones((20, 20), np.uint8)), n_chains=8, kernel=T.KERNEL_THREAD)
