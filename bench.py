@@ -420,7 +420,7 @@ def main():
         flips = 2.0 * steps_all                      # a swap step removes one support and adds one
         int_ops = A_SCORE * scored_all + A_FLIP * flips
         achieved = int_ops / (ms_total * 1e-3) / 1e9 / world
-        variant = args.kernel or (3 if n_chains >= 1024 else 2)      # engine's auto rule for a 16x16 grid (engine.cu search_kernel)
+        variant = args.kernel or (3 if n_chains >= info["sm_count"] * 48 else 2)      # engine's auto rule for a 16x16 grid (engine.cu search_kernel)
         ncu = KERNEL_NCU.get(variant, {"traffic": None, "traffic_note": "no capture for this variant", "ncu": ""})
         line["roofline"] = {"bound": "int_issue", "achieved": achieved, "peak": pk["lop3_gops"], "unit": "Gop/s", "frac": achieved / pk["lop3_gops"],
                             "traffic": ncu["traffic"], "traffic_note": ncu["traffic_note"], "kernel": KERNEL_NAMES[variant], "ncu": ncu["ncu"],

@@ -644,8 +644,10 @@ static int search_kernel(const tss_search* s) {
     if (s->kernel == TSS_KERNEL_THREAD && t16_ok) return TSS_KERNEL_THREAD;
     if (s->kernel == TSS_KERNEL_WARP) return TSS_KERNEL_WARP;
     if (s->kernel == TSS_KERNEL_HALF_WARP && h16_ok) return TSS_KERNEL_HALF_WARP;
-    // auto: a chain per thread pays off once there are enough chains to fill warps
-    if (s->kernel == TSS_KERNEL_AUTO && t16_ok && s->n_chains >= 1024) return TSS_KERNEL_THREAD;
+    // auto: a chain per thread pays off once the device is well filled — a thread-kernel warp steps its 32 chains in
+    // ~2.4 us whatever the load, the half-warp kernel steps few chains in ~1.1 us (measured on rect 16x16,
+    // profiles/crossover.py: equal at ~7000 chains; 2048 chains 48 vs 25 ms, 16384 chains 49 vs 102 ms per 20000 steps)
+    if (s->kernel == TSS_KERNEL_AUTO && t16_ok && s->n_chains >= s->e->prop.multiProcessorCount * 48) return TSS_KERNEL_THREAD;
     return h16_ok ? TSS_KERNEL_HALF_WARP : TSS_KERNEL_WARP;
 }
 
