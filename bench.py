@@ -520,7 +520,8 @@ def main():
                               "input": "SLS witness completed by unit propagation x 8192, every 64th with one support removed"}
         # ---------------- the other named configs, for context (parity-test cases, not the bench line): wall clock through the C ABI
         others = {}
-        ex1_rows = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))["ex1"]["grid"]   # test/ex1.toml
+        fx = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))
+        ex1_rows = fx["ex1"]["grid"]   # test/ex1.toml
         ex1 = T.WorldGrid.from_toml("[world]\ngrid = [\n" + "".join(f'    "{r}",\n' for r in ex1_rows) + "]\n")
         t1s = []
         for i in range(7):
@@ -530,6 +531,17 @@ def main():
             assert res == T.SAT and lay3.platform_count() == 1
         others["C1 ex1 default-8 (REPL set)"] = {"count": lay3.platform_count(), "proven_optimum": 1, "ms": float(np.median(t1s[2:])),
                                                  "note": "tss_solve_upper_bound(card_limit=1) from host buffers, median of 5 calls after 2 warm-up calls"}
+        ex2 = np.array([[1 if (i < len(r) and r[i] == "X") else 0 for i in range(max(len(q) for q in fx["ex2"]["grid"]))] for r in fx["ex2"]["grid"]], np.uint8)
+        ex2[8:10, 8:10] = 1          # README terrain = test/ex2.toml with (8,8),(9,8),(8,9),(9,9) set to ceiling
+        t3s = []
+        for i in range(7):
+            t0 = time.perf_counter()
+            res, lay2 = eng.solve_upper_bound(T.WorldGrid(ex2), card_limit=14, seed=40 + i)
+            t3s.append((time.perf_counter() - t0) * 1e3)
+            assert res == T.SAT and lay2.platform_count() == 14
+        others["C3 README 21x16 terrain, 1x1 supports"] = {"count": 14, "proven_optimum": 14, "ms": float(np.median(t3s[2:])),
+                                                         "note": "tss_solve_upper_bound(card_limit=14) from host buffers, median of 5 calls after 2 warm-up calls; the README transcript "
+                                                                 "stops at 15 (README.md:117-119); the oracle's CDCL loop (Glucose stand-in, 1 thread, build container) finds 14 after 1.2 s and proves it 10 s later"}
         g4 = T.WorldGrid.synthetic(256, 256, 1, 0)
         s4 = eng.search(g4, seed=1)          # default: one wave of chains over the windows
         t0 = time.perf_counter()
