@@ -27,6 +27,9 @@ size_t sls_t16_list_words(int n_chains);
 int sls_run_t16(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls::ChainState* states, uint32_t* site_lists, int n_chains,
                 int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
                 int noise_pct, unsigned long long* totals_dev);
+int sls_run_h16_oneshot(tss_engine* e, const uint32_t* rows32_host, int bound, uint32_t* rows_dev, uint2* tabs_dev, sls::ChainState* states,
+                        int n_chains, uint64_t seed, long long steps, int* bounds_dev, int2* best_dev, unsigned long long* key_dev,
+                        unsigned int* ticket_dev, int target, int noise_pct, unsigned long long* totals_dev, uint32_t* result_host_mapped);
 int sls_run_h16(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls::ChainState* states, int n_chains,
                 int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
                 int noise_pct, unsigned long long* totals_dev);
@@ -139,6 +142,9 @@ struct tss_search {
     uint32_t* site_lists = nullptr;            // [16*26][n_chains rounded to 32] support lists of the thread-per-chain kernel (allocated on first use)
     int kernel = TSS_KERNEL_AUTO;              // tss_search_params.kernel
     unsigned long long* totals_dev = nullptr;  // [2]
+    unsigned int* ticket_dev = nullptr;        // CTAs finished in a fused one-shot launch (sls_h16.cu OneShot), 0 between launches
+    uint32_t* oneshot_host = nullptr;          // mapped pinned [40]: result block of a fused one-shot launch
+    uint32_t* oneshot_host_dev = nullptr;      // ... its device-side address
     uint32_t* witness_dev = nullptr;           // [34] rows + check of the best layout (witness_kernel)
     uint32_t* witness_host = nullptr;          // pinned copy
     unsigned long long* reduce_key_dev = nullptr;  // [1] running (best << 32 | chain) minimum of the wide best-reduce, ~0 between epochs
@@ -458,6 +464,8 @@ static void search_free(tss_search* s) {
     cudaFree(s->site_lists);
     cudaFree(s->reduce_key_dev);
     cudaFree(s->witness_dev);
+    cudaFree(s->ticket_dev);
+    if (s->oneshot_host) cudaFreeHost(s->oneshot_host);
     if (s->witness_host) cudaFreeHost(s->witness_host);
     cudaFree(s->rows_dev); cudaFree(s->tabs_dev); cudaFree(s->states); cudaFree(s->totals_dev); cudaFree(s->best_dev); cudaFree(s->bounds_dev);
     if (s->best_host) cudaFreeHost(s->best_host);
@@ -473,6 +481,10 @@ static int search_alloc(tss_engine* e, tss_search* s, const uint32_t* rows32_hos
     TSS_CUDA(e, cudaMalloc(&s->totals_dev, sizeof(unsigned long long) * 2));
     TSS_CUDA(e, cudaMalloc(&s->reduce_key_dev, sizeof(unsigned long long)));
     TSS_CUDA(e, cudaMalloc(&s->witness_dev, sizeof(uint32_t) * 34));
+    TSS_CUDA(e, cudaMalloc(&s->ticket_dev, sizeof(unsigned int)));
+    TSS_CUDA(e, cudaMemsetAsync(s->ticket_dev, 0, sizeof(unsigned int), e->stream));
+    TSS_CUDA(e, cudaHostAlloc((void**)&s->oneshot_host, sizeof(uint32_t) * 40, cudaHostAllocMapped));
+    TSS_CUDA(e, cudaHostGetDevicePointer((void**)&s->oneshot_host_dev, s->oneshot_host, 0));
     TSS_CUDA(e, cudaHostAlloc((void**)&s->witness_host, sizeof(uint32_t) * 34, cudaHostAllocDefault));
     TSS_CUDA(e, cudaMalloc(&s->best_dev, sizeof(int2) * (size_t)s->n_groups));
     TSS_CUDA(e, cudaMalloc(&s->bounds_dev, sizeof(int) * (size_t)s->n_groups));
@@ -971,6 +983,8 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
         search_free(e->cached_search);
         e->cached_search = nullptr;
     }
+    int64_t fused_steps = 0;   // steps already executed by the fused first epoch
+    int fused_best = -1;
     if (e->cached_search && grid && w > 0 && h > 0 && w <= 32 && h <= 32 && only_1x1) {
         // reuse the engine's workspace: same buffers, fresh terrain / reach table / chain states (no allocation)
         s = e->cached_search;
@@ -978,19 +992,57 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
         s->w = w; s->h = h; s->seed = seed; s->chain_offset = 0; s->noise = sls::DEFAULT_NOISE_PCT;
         s->kernel = kernel;
         s->grid.assign(grid, grid + (size_t)w * h);
-        s->totals_seen[0] = s->totals_seen[1] = 0;
-        s->dirty = false;
         s->external_bound = sls::NO_BOUND;
-        uint32_t* rows = (uint32_t*)e->pin(2, sizeof(uint32_t) * 32);
-        if (!rows) rc = TSS_E_CUDA;
-        if (rc == TSS_OK) {
-            for (int y = 0; y < 32; y++) rows[y] = 0;
-            for (int y = 0; y < h; y++)
-                for (int x = 0; x < w; x++)
-                    if (grid[(size_t)y * w + x]) rows[y] |= 1u << x;
-            TSS_CUDA(e, cudaSetDevice(e->device));
-            cudaError_t err = cudaMemcpyAsync(s->rows_dev, rows, sizeof(uint32_t) * 32, cudaMemcpyHostToDevice, e->stream);
-            rc = err == cudaSuccess ? search_init_device(e, s, 1) : e->fail(TSS_E_CUDA, "tss_solve_upper_bound: %s", cudaGetErrorString(err));
+        uint32_t rows_now[32];
+        for (int y = 0; y < 32; y++) rows_now[y] = 0;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++)
+                if (grid[(size_t)y * w + x]) rows_now[y] |= 1u << x;
+        TSS_CUDA(e, cudaSetDevice(e->device));
+        if (latency_mode && s->n_chains % 8 == 0 && !e->interrupted()) {
+            // the whole first epoch in ONE launch and ONE synchronisation (sls_h16.cu OneShot): rows travel as kernel
+            // parameters, the reach table is derived per CTA, chains start in registers, the last CTA publishes the winner
+            // and its validation into mapped host memory
+            fused_steps = 64;
+            rc = search_sync(s);   // (nothing in flight on a cached workspace; folds counters if there was)
+            if (rc == TSS_OK) {
+                cudaEventRecord(e->ev0, e->stream);
+                rc = sls_run_h16_oneshot(e, rows_now, card_limit >= 0 ? card_limit + 1 : sls::NO_BOUND, s->rows_dev, s->tabs_dev, s->states, s->n_chains, seed,
+                                         fused_steps, s->bounds_dev, s->best_dev, s->reduce_key_dev, s->ticket_dev,
+                                         card_limit >= 0 ? card_limit : sls::NO_BOUND - 1, s->noise, s->totals_dev, s->oneshot_host_dev);
+                cudaEventRecord(e->ev1, e->stream);
+            }
+            if (rc == TSS_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = e->fail(TSS_E_CUDA, "tss_solve_upper_bound: fused epoch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (rc == TSS_OK) {
+                const volatile uint32_t* r = s->oneshot_host;
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) cudaGetLastError();
+                e->stats.device_ms = ms;
+                e->stats.n_solves++;
+                const unsigned long long t0 = ((unsigned long long)r[37] << 32) | r[36], t1 = ((unsigned long long)r[39] << 32) | r[38];
+                e->stats.candidates_scored += t0 - s->totals_seen[0];
+                e->stats.sls_steps += t1 - s->totals_seen[1];
+                s->totals_seen[0] = t0; s->totals_seen[1] = t1;
+                s->totals_host[0] = t0; s->totals_host[1] = t1;
+                s->best_host[0] = make_int2((int)r[34], (int)r[35]);
+                s->dirty = false;
+                if ((int)r[34] < sls::NO_BOUND) {
+                    fused_best = (int)r[34];
+                    e->stats.best_count = fused_best;
+                    if (r[32] != 0 || (int)r[33] != fused_best)
+                        rc = e->fail(TSS_E_CUDA, "internal error: SLS witness failed validation (%u unsupported tiles, %u supports, expected %d)", r[32], r[33], fused_best);
+                }
+            }
+        } else {
+            s->totals_seen[0] = s->totals_seen[1] = 0;
+            s->dirty = false;
+            uint32_t* rows = (uint32_t*)e->pin(2, sizeof(uint32_t) * 32);
+            if (!rows) rc = TSS_E_CUDA;
+            if (rc == TSS_OK) {
+                for (int y = 0; y < 32; y++) rows[y] = rows_now[y];
+                cudaError_t err = cudaMemcpyAsync(s->rows_dev, rows, sizeof(uint32_t) * 32, cudaMemcpyHostToDevice, e->stream);
+                rc = err == cudaSuccess ? search_init_device(e, s, 1) : e->fail(TSS_E_CUDA, "tss_solve_upper_bound: %s", cudaGetErrorString(err));
+            }
         }
         if (rc != TSS_OK) { search_free(s); return rc; }
     } else {
@@ -998,7 +1050,7 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
         if (rc) return rc;
     }
     s->share = false;  // a one-shot solve runs a rank-local number of epochs: no collective inside
-    if (card_limit >= 0) rc = tss_search_set_bound(s, card_limit + 1);
+    if (card_limit >= 0 && fused_steps == 0) rc = tss_search_set_bound(s, card_limit + 1);   // (the fused epoch took its bound as a parameter)
     const double t0 = now_ms();
     // no budget given: behave like one SAT call (return the first model within the bound), but give up after a
     // default effort — the engine cannot prove UNSAT, so "no model found" must not turn into an endless search
@@ -1006,15 +1058,16 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     const bool first_model_only = budget_ms <= 0 && max_steps <= 0 && !(windowed && card_limit < 0);
     if (budget_ms <= 0 && max_steps <= 0) max_steps = windowed ? (1 << 16) : (1 << 18);
     // (a placement-search step costs ~5 us of latency: start with short epochs when the first model is all that is asked for)
-    int64_t done_steps = 0, epoch = (s->multi && first_model_only) ? 16 : 64;
-    int best = -1;
+    int64_t done_steps = fused_steps, epoch = (s->multi && first_model_only) ? 16 : (fused_steps ? 128 : 64);
+    int best = fused_best;
     const bool in_stream_witness = !s->lns && !s->multi && s->n_groups == 1;   // 1x1 supports on a grid up to 32x32
     // First-model mode: chains stop at the first layout within the limit (target = card_limit).  (Queueing several epochs
     // per synchronisation — later ones do nothing once the bound is within the target, sls_spec.hpp — was measured and lost:
     // ~20 us of launch / event / copy calls per queued epoch against ~15 us per synchronisation.)
     const int target = first_model_only ? (card_limit >= 0 ? card_limit : sls::NO_BOUND - 1) : 0;
     const int burst = 1;
-    while (rc == TSS_OK) {
+    const bool fused_hit = fused_best >= 0;   // first_model_only holds in latency mode: the fused epoch's layout is the answer
+    while (rc == TSS_OK && !fused_hit) {
         if (e->interrupted()) { e->stats.interrupted = 1; break; }
         int queued = 0;
         for (int b = 0; b < burst && rc == TSS_OK; b++) {
@@ -1049,8 +1102,9 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     }
     int result = TSS_UNKNOWN;
     if (rc == TSS_OK && best >= 0 && in_stream_witness) {
-        // the witness of the last epoch, already validated on the device (witness_kernel): unsupported tiles, supports
-        const uint32_t* wr = s->witness_host;
+        // the witness of the last epoch, already validated on the device (witness_kernel / the fused epoch's last CTA):
+        // rows, unsupported tiles, supports
+        const uint32_t* wr = fused_hit ? s->oneshot_host : s->witness_host;
         if (wr[32] != 0 || (int)wr[33] != best)
             rc = e->fail(TSS_E_CUDA, "internal error: SLS witness failed validation (%u unsupported tiles, %u supports, expected %d)", wr[32], wr[33], best);
         if (rc == TSS_OK) {

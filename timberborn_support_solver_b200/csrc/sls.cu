@@ -86,31 +86,7 @@ __device__ __forceinline__ int pick_rotated(uint32_t bits, uint32_t o) {  // a s
 __global__ void build_reach_kernel(const uint32_t* __restrict__ rows, int n_terrains, uint2* __restrict__ out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)n_terrains * 1024) return;
-    int t = (int)(i >> 10), v = (int)(i & 1023), x = v & 31, y = v >> 5;
-    const uint32_t* C = rows + (size_t)t * 32;
-    uint32_t c[7], X[7];
-    const int ax = anchor(x);
-#pragma unroll
-    for (int j = 0; j < 7; j++) {
-        int yy = y - 3 + j;
-        uint32_t row = (yy >= 0 && yy < 32) ? C[yy] : 0u;
-        c[j] = (row >> ax) & 0x7fu;
-        X[j] = 0;
-    }
-    X[3] = c[3] & (1u << (x - ax));  // the site itself, if it is a ceiling tile
-    for (int round = 0; round < kTerrainSupportDistance - 1; round++) {
-        uint32_t N[7];
-#pragma unroll
-        for (int j = 0; j < 7; j++) {
-            uint32_t v2 = X[j] | (X[j] << 1) | (X[j] >> 1);
-            if (j > 0) v2 |= X[j - 1];
-            if (j < 6) v2 |= X[j + 1];
-            N[j] = v2 & c[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 7; j++) X[j] = N[j];
-    }
-    out[i] = make_uint2(X[0] | (X[1] << 7) | (X[2] << 14) | (X[3] << 21), X[4] | (X[5] << 7) | (X[6] << 14));
+    out[i] = reach_window(rows + (size_t)(i >> 10) * 32, (int)(i & 1023));
 }
 
 struct WarpCtx {

@@ -89,11 +89,32 @@ __device__ __forceinline__ void diamond_cell(int i, int& dx, int& dy) {
     dx = (i - start) - (3 - abs(dy));
 }
 
+// ONESHOT = the whole first epoch of a one-shot solve in ONE launch (tss_solve_upper_bound, latency mode): the terrain
+// rows arrive as kernel parameters (no upload), every CTA derives the reach table in its own shared memory (CTA 0 also
+// stores it for follow-up epochs), chains start empty in registers (no init kernel), and the last CTA to finish — a
+// ticket counter, no cooperative launch — folds the best count, fetches the winner's layout, re-validates it
+// (kernel (a) in one-warp form) and writes the results straight into mapped host memory.  The host enqueues one kernel
+// and synchronises once; the instances are small, so launch and round-trip overhead is what there is to save.
+struct OneShot {
+    uint32_t rows[32];            // terrain rows (row r, bit x = ceiling at (x, r))
+    int bound;                    // chains look for fewer than this many supports (card_limit + 1, or NO_BOUND)
+    uint32_t* rows_out;           // [32]   kept on the device for follow-up epochs
+    uint2* tabs_out;              // [1024]
+    int* bounds_out;              // [1]
+    int2* best_out;               // [1]
+    unsigned long long* key;      // running (best << 32 | chain) minimum, ~0 between launches
+    unsigned int* ticket;         // CTAs finished, 0 between launches
+    uint32_t* result_host;        // mapped host memory: [0..31] rows of the best layout, [32] unsupported tiles, [33] supports,
+                                  // [34] best count, [35] winner chain, [36..39] totals (candidates, steps) as two u64
+};
+
+template <bool ONESHOT>
 __global__ void __launch_bounds__(WARPS * 32, 8) sls_h16_kernel(const uint32_t* __restrict__ terrain_rows, const uint2* __restrict__ rtabs,
                                                             ChainState* __restrict__ states, int n_chains, int chains_per_terrain,
                                                             uint32_t chain_offset, uint64_t seed, long long steps,
                                                             const int* __restrict__ bounds, int target, int noise_pct,
-                                                            const volatile int* interrupt, unsigned long long* __restrict__ totals) {
+                                                            const volatile int* interrupt, unsigned long long* __restrict__ totals,
+                                                            const OneShot os) {
     __shared__ uint2 tab[1024];
     __shared__ uint16_t sites_all[WARPS * 2][MAX_SITES16];
     __shared__ uint16_t stamps_all[WARPS * 2][MAX_SITES16];   // flip step of every site (site ids < 512 for <= 16 rows)
@@ -102,28 +123,43 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_h16_kernel(const uint32_t* 
     const int terrain = chains_per_terrain > 0 ? (blockIdx.x * WARPS * 2) / chains_per_terrain : 0;
     // a layout within the target is already known for this terrain (found in an earlier epoch): nothing to do.  Lets a host
     // queue several epochs back to back without a round trip in between (one-shot solves, sls_spec.hpp).
-    if (target >= 0 && bounds[chains_per_terrain > 0 ? terrain : 0] <= target) return;
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) tab[i] = rtabs[(size_t)terrain * 1024 + i];
+    __shared__ uint32_t crows[32];
+    if (ONESHOT) {
+        if (threadIdx.x < 32) {
+            crows[threadIdx.x] = os.rows[threadIdx.x];
+            if (blockIdx.x == 0) os.rows_out[threadIdx.x] = os.rows[threadIdx.x];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+            const uint2 win = i < 512 ? reach_window(crows, i) : make_uint2(0u, 0u);   // (at most 16 rows: sites 512.. have no ceiling)
+            tab[i] = win;
+            if (blockIdx.x == 0) os.tabs_out[i] = win;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) os.bounds_out[0] = os.bound;
+    } else {
+        if (target >= 0 && bounds[chains_per_terrain > 0 ? terrain : 0] <= target) return;
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) tab[i] = rtabs[(size_t)terrain * 1024 + i];
+    }
     __syncthreads();
     const bool exists = chain < n_chains;
     ChainState& st = states[exists ? chain : 0];
-    if (!__any_sync(FULL, exists && !st.done)) return;
+    if (!ONESHOT && !__any_sync(FULL, exists && !st.done)) return;   // (a one-shot launch has every warp take part in the final ticket)
 
-    const int epoch_bound = bounds[chains_per_terrain > 0 ? terrain : 0];
+    const int epoch_bound = ONESHOT ? os.bound : bounds[chains_per_terrain > 0 ? terrain : 0];
     const uint32_t base = chain_base(seed, chain_offset + (uint32_t)chain);
     const uint32_t nq7 = noise_q7(noise_pct);
     const unsigned hshift = half * 16;
     uint16_t* sites = sites_all[warp * 2 + half];
     Lane L;
-    L.C = terrain_rows[(size_t)terrain * 32 + row];
-    L.S = exists ? st.S[row] : 0u;
-    uint32_t bestS = exists ? st.bestS[row] : 0u;
-    int k = exists ? st.k : 0, best = exists ? st.best : 0;
+    L.C = ONESHOT ? crows[row] : terrain_rows[(size_t)terrain * 32 + row];
+    L.S = (exists && !ONESHOT) ? st.S[row] : 0u;
+    uint32_t bestS = (exists && !ONESHOT) ? st.bestS[row] : 0u;
+    int k = (exists && !ONESHOT) ? st.k : 0, best = exists ? (ONESHOT ? NO_BOUND : st.best) : 0;
     const int tenure = tenure_of(chain_offset + (uint32_t)chain);
     uint16_t* stamps = stamps_all[warp * 2 + half];
-    int done = exists ? st.done : 1;
+    int done = exists ? (ONESHOT ? 0 : st.done) : 1;
     const int done_at_start = done;
-    uint32_t step = exists ? st.step : 0u;
+    uint32_t step = (exists && !ONESHOT) ? st.step : 0u;
     unsigned long long scored = 0;
     long long my_steps = 0;
 
@@ -253,13 +289,52 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_h16_kernel(const uint32_t* 
     if (exists && !done_at_start) {
         st.S[row] = L.S;
         st.bestS[row] = bestS;
+        if (ONESHOT) { st.S[16 + row] = 0u; st.bestS[16 + row] = 0u; }   // (a fresh record: no init kernel ran)
         if (row == 0) {
             st.k = k; st.best = best; st.step = step; st.done = done;
-            unsigned long long tot = ((unsigned long long)st.scored_hi << 32 | st.scored_lo) + scored;
+            unsigned long long tot = ONESHOT ? scored : ((unsigned long long)st.scored_hi << 32 | st.scored_lo) + scored;
             st.scored_lo = (uint32_t)tot; st.scored_hi = (uint32_t)(tot >> 32);
-            st.steps_done += (uint32_t)my_steps;
+            st.steps_done = (ONESHOT ? 0u : st.steps_done) + (uint32_t)my_steps;
+            if (ONESHOT) { st.tabu_add = -1; st.tabu_rem = -1; }
             atomicAdd(&totals[0], scored);
             atomicAdd(&totals[1], (unsigned long long)my_steps);
+            if (ONESHOT && best < NO_BOUND) atomicMin(os.key, ((unsigned long long)(uint32_t)best << 32) | (uint32_t)chain);
+        }
+    }
+    if (ONESHOT) {
+        // the last CTA to arrive publishes the result: every CTA's writes above are fenced before its ticket
+        __shared__ bool last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last = atomicAdd(os.ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (last && warp == 0) {
+            __threadfence();
+            const unsigned long long key = *(volatile unsigned long long*)os.key;
+            const int bcount = key == ~0ull ? NO_BOUND : (int)(key >> 32), bchain = key == ~0ull ? -1 : (int)(key & 0xffffffffu);
+            // the winner's layout (written by another CTA: read around L1) and validate()'s three ceiling-masked dilations on it
+            const uint32_t S = bchain >= 0 ? __ldcg(&states[bchain].bestS[lane]) : 0u, C = crows[lane];
+            uint32_t X = S & C;
+            for (int round = 0; round < 3; round++) {
+                uint32_t up = __shfl_up_sync(FULL, X, 1), down = __shfl_down_sync(FULL, X, 1);
+                if (lane == 0) up = 0;
+                if (lane == 31) down = 0;
+                X = (X | (X << 1) | (X >> 1) | up | down) & C;
+            }
+            const int unc = __reduce_add_sync(FULL, __popc(C & ~X)), cnt = __reduce_add_sync(FULL, __popc(S));
+            os.result_host[lane] = S;
+            if (lane == 0) {
+                os.best_out[0] = make_int2(bcount, bchain);
+                if (bcount < os.bound) os.bounds_out[0] = bcount;
+                const unsigned long long t0 = *(volatile unsigned long long*)&totals[0], t1 = *(volatile unsigned long long*)&totals[1];
+                os.result_host[32] = (uint32_t)unc; os.result_host[33] = (uint32_t)cnt;
+                os.result_host[34] = (uint32_t)bcount; os.result_host[35] = (uint32_t)bchain;
+                os.result_host[36] = (uint32_t)t0; os.result_host[37] = (uint32_t)(t0 >> 32);
+                os.result_host[38] = (uint32_t)t1; os.result_host[39] = (uint32_t)(t1 >> 32);
+                *os.key = ~0ull;       // re-armed for the next launch
+                *os.ticket = 0u;
+                __threadfence_system();
+            }
         }
     }
 }
@@ -271,8 +346,26 @@ int sls_run_h16(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, 
                 int noise_pct, unsigned long long* totals_dev) {
     const int per_cta = sls16::WARPS * 2;
     int blocks = (n_chains + per_cta - 1) / per_cta;
-    sls16::sls_h16_kernel<<<blocks, sls16::WARPS * 32, 0, e->stream>>>(rows_dev, tabs_dev, states, n_chains, chains_per_terrain, chain_offset, seed,
-                                                                     steps, bounds_dev, target, noise_pct, e->interrupt_dev, totals_dev);
+    sls16::sls_h16_kernel<false><<<blocks, sls16::WARPS * 32, 0, e->stream>>>(rows_dev, tabs_dev, states, n_chains, chains_per_terrain, chain_offset, seed,
+                                                                            steps, bounds_dev, target, noise_pct, e->interrupt_dev, totals_dev,
+                                                                            sls16::OneShot{});
+    TSS_CHECK_LAUNCH(e);
+    e->stats.kernel_launches++;
+    return TSS_OK;
+}
+
+// The fused first epoch of a one-shot solve (see sls16::OneShot).  n_chains must be a multiple of 8 (whole CTAs);
+// result_host is mapped pinned memory of at least 40 words; key_dev must hold ~0 and ticket_dev 0 (both re-arm themselves).
+int sls_run_h16_oneshot(tss_engine* e, const uint32_t* rows32_host, int bound, uint32_t* rows_dev, uint2* tabs_dev, sls::ChainState* states,
+                        int n_chains, uint64_t seed, long long steps, int* bounds_dev, int2* best_dev, unsigned long long* key_dev,
+                        unsigned int* ticket_dev, int target, int noise_pct, unsigned long long* totals_dev, uint32_t* result_host_mapped) {
+    if (n_chains <= 0 || n_chains % (sls16::WARPS * 2) != 0) return e->fail(TSS_E_INVALID, "one-shot launch needs whole CTAs of chains");
+    sls16::OneShot os;
+    for (int r = 0; r < 32; r++) os.rows[r] = rows32_host[r];
+    os.bound = bound; os.rows_out = rows_dev; os.tabs_out = tabs_dev; os.bounds_out = bounds_dev; os.best_out = best_dev;
+    os.key = key_dev; os.ticket = ticket_dev; os.result_host = result_host_mapped;
+    sls16::sls_h16_kernel<true><<<n_chains / (sls16::WARPS * 2), sls16::WARPS * 32, 0, e->stream>>>(nullptr, nullptr, states, n_chains, 0, 0u, seed, steps, nullptr,
+                                                                                                target, noise_pct, e->interrupt_dev, totals_dev, os);
     TSS_CHECK_LAUNCH(e);
     e->stats.kernel_launches++;
     return TSS_OK;

@@ -91,5 +91,36 @@ struct ChainState {
 };
 static_assert(sizeof(ChainState) == 320, "ChainState layout");
 
+#if defined(__CUDACC__)
+// Reach window of site v = (x, y) on a terrain given as 32 row words: validate()'s three ceiling-masked dilations
+// (src/encoder/platform_layout.rs:127-141) run inside the site's own 7x7 window (geodesic paths of length <= 3 never
+// leave it).  Window row dy is grid row y-3+dy, window column 0 is grid column max(x-3, 0).
+__device__ __forceinline__ uint2 reach_window(const uint32_t* C, int v) {
+    const int x = v & 31, y = v >> 5, ax = x - 3 > 0 ? x - 3 : 0;
+    uint32_t c[7], X[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        const int yy = y - 3 + j;
+        const uint32_t row = (yy >= 0 && yy < 32) ? C[yy] : 0u;
+        c[j] = (row >> ax) & 0x7fu;
+        X[j] = 0;
+    }
+    X[3] = c[3] & (1u << (x - ax));  // the site itself, if it is a ceiling tile
+    for (int round = 0; round < 3; round++) {  // TERRAIN_SUPPORT_DISTANCE - 1 (src/lib.rs:12)
+        uint32_t N[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            uint32_t v2 = X[j] | (X[j] << 1) | (X[j] >> 1);
+            if (j > 0) v2 |= X[j - 1];
+            if (j < 6) v2 |= X[j + 1];
+            N[j] = v2 & c[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 7; j++) X[j] = N[j];
+    }
+    return make_uint2(X[0] | (X[1] << 7) | (X[2] << 14) | (X[3] << 21), X[4] | (X[5] << 7) | (X[6] << 14));
+}
+#endif
+
 }  // namespace sls
 }  // namespace tss
