@@ -389,6 +389,35 @@ def test_sls_kernel_variants_agree_at_scale(eng, fixtures, case):
             assert np.array_equal(st[key], ref[key]), (kernel, key)
 
 
+def test_fused_one_shot_launch_equals_the_epoch_by_epoch_path(fixtures):
+    """tss_solve_upper_bound in latency mode runs its first epoch as ONE fused launch once the engine holds a workspace
+    (rows as kernel parameters, per-CTA reach table, chains started in registers, last-CTA reduce + validation).  Same
+    spec, same seeds: it returns exactly the layout of the first (unfused) call and of the persistent-portfolio API."""
+    e = T.Engine(0)
+    n_chains = e.device_info()["sm_count"] * 16
+    for grid, limit in ((np.ones((16, 16), np.uint8), 15), (fixtures["ex2"], 14), (fixtures["ex1"], 3)):
+        g = T.WorldGrid(grid)
+        for seed in (11, 12):
+            e2 = T.Engine(0)                                                     # no workspace yet: epoch-by-epoch path
+            res_a, lay_a = e2.solve_upper_bound(g, card_limit=limit, seed=seed)
+            launches_a = e2.stats()["kernel_launches"]
+            res_b, lay_b = e2.solve_upper_bound(g, card_limit=limit, seed=seed)  # workspace cached: fused launch
+            launches_b = e2.stats()["kernel_launches"] - launches_a
+            e2.close()
+            assert res_a == res_b == T.SAT and launches_b < launches_a
+            pa, pb = sorted(lay_a.platforms()), sorted(lay_b.platforms())
+            assert pa == pb and len(pa) <= limit
+            s = e.search(g, seed=seed, n_chains=n_chains, kernel=T.KERNEL_HALF_WARP)
+            s.set_bound(limit + 1)
+            steps = 64
+            while s.best_count() is None:
+                s.run(steps, limit)
+                steps *= 2
+            assert sorted(s.best_layout().platforms()) == pa
+            s.close()
+    e.close()
+
+
 def test_kernel_variant_rejected_when_grid_does_not_fit(eng):
     with pytest.raises(T.TssError):
         eng.search(T.WorldGrid(np.ones((20, 20), np.uint8)), n_chains=8, kernel=T.KERNEL_THREAD)
