@@ -409,7 +409,7 @@ def test_fused_one_shot_launch_equals_the_epoch_by_epoch_path(fixtures):
             assert pa == pb and len(pa) <= limit
             s = e.search(g, seed=seed, n_chains=n_chains, kernel=T.KERNEL_HALF_WARP)
             s.set_bound(limit + 1)
-            steps = 64
+            steps = 32
             while s.best_count() is None:
                 s.run(steps, limit)
                 steps *= 2

@@ -1003,7 +1003,7 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
             // the whole first epoch in ONE launch and ONE synchronisation (sls_h16.cu OneShot): rows travel as kernel
             // parameters, the reach table is derived per CTA, chains start in registers, the last CTA publishes the winner
             // and its validation into mapped host memory
-            fused_steps = 64;
+            fused_steps = 32;   // (profiles/steps_to_optimum.py: the fastest of SM x 16 chains needs 16-32 steps on rect 16x16 and test/ex2)
             rc = search_sync(s);   // (nothing in flight on a cached workspace; folds counters if there was)
             if (rc == TSS_OK) {
                 cudaEventRecord(e->ev0, e->stream);
@@ -1058,7 +1058,7 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     const bool first_model_only = budget_ms <= 0 && max_steps <= 0 && !(windowed && card_limit < 0);
     if (budget_ms <= 0 && max_steps <= 0) max_steps = windowed ? (1 << 16) : (1 << 18);
     // (a placement-search step costs ~5 us of latency: start with short epochs when the first model is all that is asked for)
-    int64_t done_steps = fused_steps, epoch = (s->multi && first_model_only) ? 16 : (fused_steps ? 128 : 64);
+    int64_t done_steps = fused_steps, epoch = (s->multi && first_model_only) ? 16 : (fused_steps ? 2 * fused_steps : (first_model_only && !s->lns ? 32 : 64));
     int best = fused_best;
     const bool in_stream_witness = !s->lns && !s->multi && s->n_groups == 1;   // 1x1 supports on a grid up to 32x32
     // First-model mode: chains stop at the first layout within the limit (target = card_limit).  (Queueing several epochs
