@@ -70,6 +70,7 @@ typedef struct tss_stats {
     double   device_ms;           /* device time of the kernels of the last call (CUDA events on the engine stream) */
     int32_t  best_count;          /* best platform count of the last solve (-1 if none) */
     int32_t  interrupted;         /* last solve ended by tss_interrupt */
+    int64_t  last_solve_steps;    /* SLS steps per chain the last tss_solve_upper_bound call ran before it returned */
 } tss_stats;
 
 /* ------------------------------------------------------------------------------------------------ engine */
@@ -244,7 +245,9 @@ void tss_sls_spec_probe(uint32_t* out);
  * find a layout with at most `card_limit` platforms (card_limit < 0: unbounded, any complete layout) within
  * `budget_ms` and/or `max_steps` SLS steps per chain, returning the best layout found.  With neither budget given
  * the call behaves like ONE SAT call: it returns the first layout within the bound and gives up after 2^18 steps
- * per chain (the engine cannot prove UNSAT, so "nothing found" must terminate).
+ * per chain (the engine cannot prove UNSAT, so "nothing found" must terminate).  A NEGATIVE `max_steps` (with no
+ * `budget_ms`) is the same SAT-like call with the give-up point moved to -max_steps steps per chain: the bound-tightening
+ * loop uses it to hand an instance it cannot answer quickly to the exact solver after a bounded, small effort.
  * Returns TSS_SAT with the layout, TSS_UNKNOWN if none was found (never TSS_UNSAT). */
 int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,
                           int32_t card_limit, uint64_t seed, int32_t budget_ms, int64_t max_steps, tss_platform* out,

@@ -686,20 +686,31 @@ class GpuBoundSolver:
         return self.engine.stats()
 
 
-def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, engine: Engine, exact_solver=None, seed=0, budget_ms=50,
+def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, engine: Engine, exact_solver=None, seed=0, budget_ms=None,
                 on_solution=None):
     """crates/repl/src/main.rs:280-366 with the GPU engine as the SAT side and an optional exact solver
     (`exact_solver(cnf) -> (SAT|UNSAT|INTERRUPTED, assignment)`, Glucose in the reference) for the proof.
+
+    budget_ms=None (default): every iteration is ONE SAT-like call (first layout within the bound) whose give-up point
+    adapts to the run — 64x the steps the previous successful call needed, at least 4096 per chain — so the iteration the
+    GPU cannot answer (one below the optimum) costs milliseconds before the prover takes over, not the engine's default
+    2^18 steps.  budget_ms=0 keeps that default effort; budget_ms > 0 improves for that long in every iteration.
 
     Returns dict(best=PlatformLayout|None, proved_optimal=bool, steps=[...])."""
     one = PlatformDef(1, 1)
     limits = PlatformLimits(dict(limits.card_limits), dict(limits.weights), limits.weight_limit)
     steps, best, proved = [], None, False
+    give_up = 4096
     while True:
         cnf = encoding.with_limits(limits)                      # main.rs:292-293
-        solver = GpuBoundSolver(engine, encoding, limits, seed=seed, budget_ms=budget_ms)
+        if budget_ms is None:
+            solver = GpuBoundSolver(engine, encoding, limits, seed=seed, budget_ms=0, max_steps=-give_up)
+        else:
+            solver = GpuBoundSolver(engine, encoding, limits, seed=seed, budget_ms=budget_ms)
         solver.add_cnf(cnf)                                     # solver_runner.rs:12
         result = solver.solve()
+        if result == SAT:
+            give_up = max(4096, 64 * int(engine.stats()["last_solve_steps"]))
         source = "gpu"
         assignment = solver.full_solution() if result == SAT else None
         if result != SAT and exact_solver is not None:          # the GPU found nothing in budget: ask the prover

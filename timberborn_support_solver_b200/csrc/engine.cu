@@ -1056,7 +1056,8 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     // default effort — the engine cannot prove UNSAT, so "no model found" must not turn into an endless search
     const bool windowed = w > 32 || h > 32;  // the window-decomposed search always holds a complete layout: keep improving it
     const bool first_model_only = budget_ms <= 0 && max_steps <= 0 && !(windowed && card_limit < 0);
-    if (budget_ms <= 0 && max_steps <= 0) max_steps = windowed ? (1 << 16) : (1 << 18);
+    if (budget_ms <= 0 && max_steps < 0) max_steps = -max_steps;   // SAT-like call with a caller-chosen give-up point
+    else if (budget_ms <= 0 && max_steps == 0) max_steps = windowed ? (1 << 16) : (1 << 18);
     // (a placement-search step costs ~5 us of latency: start with short epochs when the first model is all that is asked for)
     int64_t done_steps = fused_steps, epoch = (s->multi && first_model_only) ? 16 : (fused_steps ? 2 * fused_steps : (first_model_only && !s->lns ? 32 : 64));
     int best = fused_best;
@@ -1100,6 +1101,7 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
         if (first_model_only && best >= 0) break;
         if (budget_ms > 0 && now_ms() - t0 >= budget_ms) break;
     }
+    e->stats.last_solve_steps = done_steps;
     int result = TSS_UNKNOWN;
     if (rc == TSS_OK && best >= 0 && in_stream_witness) {
         // the witness of the last epoch, already validated on the device (witness_kernel / the fused epoch's last CTA):
