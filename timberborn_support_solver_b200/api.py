@@ -692,7 +692,7 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
     (`exact_solver(cnf) -> (SAT|UNSAT|INTERRUPTED, assignment)`, Glucose in the reference) for the proof.
 
     budget_ms=None (default): every iteration is ONE SAT-like call (first layout within the bound) whose give-up point
-    adapts to the run — 64x the steps the previous successful call needed, at least 4096 per chain — so the iteration the
+    adapts to the run — 32x the steps the previous successful call needed, at least 1024 per chain — so the iteration the
     GPU cannot answer (one below the optimum) costs milliseconds before the prover takes over, not the engine's default
     2^18 steps.  budget_ms=0 keeps that default effort; budget_ms > 0 improves for that long in every iteration.
 
@@ -700,7 +700,7 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
     one = PlatformDef(1, 1)
     limits = PlatformLimits(dict(limits.card_limits), dict(limits.weights), limits.weight_limit)
     steps, best, proved = [], None, False
-    give_up = 4096
+    give_up = 1024
     while True:
         cnf = encoding.with_limits(limits)                      # main.rs:292-293
         if budget_ms is None:
@@ -710,7 +710,7 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
         solver.add_cnf(cnf)                                     # solver_runner.rs:12
         result = solver.solve()
         if result == SAT:
-            give_up = max(4096, 64 * int(engine.stats()["last_solve_steps"]))
+            give_up = max(1024, 32 * int(engine.stats()["last_solve_steps"]))
         source = "gpu"
         assignment = solver.full_solution() if result == SAT else None
         if result != SAT and exact_solver is not None:          # the GPU found nothing in budget: ask the prover

@@ -226,23 +226,31 @@ int tss_cnf_propagate(tss_engine* e, const tss_cnf* c, uint8_t* assignments, int
     int nbw;
     int rc = cnf_stage(e, c, assignments, n, &pos, &neg, &nbw);
     if (rc) return rc;
-    int* outs = (int*)e->dev(3, sizeof(int) * ((size_t)nbw * 64 + 1));
-    int* flag_host = (int*)e->pin(0, sizeof(int));
+    constexpr int BATCH = 8;  // rounds queued per host round trip, each with its own "changed" flag
+    int* outs = (int*)e->dev(3, sizeof(int) * ((size_t)nbw * 64 + BATCH));
+    int* flag_host = (int*)e->pin(0, sizeof(int) * BATCH);
     if (!outs || !flag_host) return TSS_E_CUDA;
     int *cnt = outs, *first = outs + (size_t)nbw * 32, *changed = outs + (size_t)nbw * 64;
     const unsigned grid = grid_for(e, (long long)c->n_clauses * nbw);
     int rounds = 0;
     TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    for (; c->n_clauses > 0 && rounds <= c->n_vars; rounds++) {  // every productive round assigns >= 1 variable
+    // every productive round assigns >= 1 variable; a round that changes nothing is the fixpoint (later rounds of the same
+    // batch are no-ops), so the reported round count is exactly that of a round-by-round loop
+    for (bool fix = false; c->n_clauses > 0 && rounds <= c->n_vars && !fix;) {
         if (e->interrupted()) break;
-        TSS_CUDA(e, cudaMemsetAsync(changed, 0, sizeof(int), e->stream));
-        cnf_propagate_kernel<<<grid, 256, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos, neg, changed);
-        TSS_CHECK_LAUNCH(e);
-        e->stats.kernel_launches++;
-        e->stats.clauses_checked += (uint64_t)c->n_clauses * (uint64_t)n;
-        TSS_CUDA(e, cudaMemcpyAsync(flag_host, changed, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        TSS_CUDA(e, cudaMemsetAsync(changed, 0, sizeof(int) * BATCH, e->stream));
+        for (int b = 0; b < BATCH; b++) {
+            cnf_propagate_kernel<<<grid, 256, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos, neg, changed + b);
+            TSS_CHECK_LAUNCH(e);
+        }
+        e->stats.kernel_launches += BATCH;
+        TSS_CUDA(e, cudaMemcpyAsync(flag_host, changed, sizeof(int) * BATCH, cudaMemcpyDeviceToHost, e->stream));
         TSS_CUDA(e, cudaStreamSynchronize(e->stream));
-        if (!*flag_host) { rounds++; break; }
+        for (int b = 0; b < BATCH && !fix; b++) {
+            rounds++;
+            e->stats.clauses_checked += (uint64_t)c->n_clauses * (uint64_t)n;
+            fix = flag_host[b] == 0;
+        }
     }
     if (out_rounds) *out_rounds = rounds;
     // conflicts at the fixpoint = clauses whose literals are all False (True wins a forced clash, so the clause that
