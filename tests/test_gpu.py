@@ -395,9 +395,10 @@ def test_fused_one_shot_launch_equals_the_epoch_by_epoch_path(fixtures):
     spec, same seeds: it returns exactly the layout of the first (unfused) call and of the persistent-portfolio API."""
     e = T.Engine(0)
     n_chains = e.device_info()["sm_count"] * 16
+    second_epoch_needed = 0
     for grid, limit in ((np.ones((16, 16), np.uint8), 15), (fixtures["ex2"], 14), (fixtures["ex1"], 3)):
         g = T.WorldGrid(grid)
-        for seed in (11, 12):
+        for seed in ((11, 12) if limit != 14 else range(11, 23)):   # (ex2 at 14 sometimes needs more than the fused 32 steps)
             e2 = T.Engine(0)                                                     # no workspace yet: epoch-by-epoch path
             res_a, lay_a = e2.solve_upper_bound(g, card_limit=limit, seed=seed)
             launches_a = e2.stats()["kernel_launches"]
@@ -414,7 +415,17 @@ def test_fused_one_shot_launch_equals_the_epoch_by_epoch_path(fixtures):
                 s.run(steps, limit)
                 steps *= 2
             assert sorted(s.best_layout().platforms()) == pa
+            second_epoch_needed += steps > 64
             s.close()
+    # an infeasible bound with a give-up point: fused epoch, follow-up epochs, then UNKNOWN after exactly that many steps
+    e2 = T.Engine(0)
+    g = T.WorldGrid(np.ones((16, 16), np.uint8))
+    e2.solve_upper_bound(g, card_limit=15, seed=1)
+    res, lay = e2.solve_upper_bound(g, card_limit=14, seed=1, max_steps=-300)
+    assert res == T.INTERRUPTED and lay is None and e2.stats()["last_solve_steps"] == 300
+    res, lay = e2.solve_upper_bound(g, card_limit=15, seed=2)          # the workspace is intact afterwards
+    assert res == T.SAT and lay.platform_count() == 15
+    e2.close()
     e.close()
 
 

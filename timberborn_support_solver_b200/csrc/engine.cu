@@ -1066,21 +1066,16 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     // per synchronisation — later ones do nothing once the bound is within the target, sls_spec.hpp — was measured and lost:
     // ~20 us of launch / event / copy calls per queued epoch against ~15 us per synchronisation.)
     const int target = first_model_only ? (card_limit >= 0 ? card_limit : sls::NO_BOUND - 1) : 0;
-    const int burst = 1;
     const bool fused_hit = fused_best >= 0;   // first_model_only holds in latency mode: the fused epoch's layout is the answer
     while (rc == TSS_OK && !fused_hit) {
         if (e->interrupted()) { e->stats.interrupted = 1; break; }
-        int queued = 0;
-        for (int b = 0; b < burst && rc == TSS_OK; b++) {
-            int64_t steps = epoch;
-            if (max_steps > 0 && done_steps + steps > max_steps) steps = max_steps - done_steps;
-            if (steps <= 0) break;
-            rc = tss_search_run(s, steps, target);
-            done_steps += steps;
-            queued++;
-            if (epoch < 8192) epoch *= 2;
-        }
-        if (rc || !queued) break;
+        int64_t steps = epoch;
+        if (max_steps > 0 && done_steps + steps > max_steps) steps = max_steps - done_steps;
+        if (steps <= 0) break;
+        rc = tss_search_run(s, steps, target);
+        if (rc) break;
+        done_steps += steps;
+        if (epoch < 8192) epoch *= 2;
         if (s->multi) {  // placements of the best chain + their validation by the platform evaluator, in-stream
             rc = slsm_witness(e, s->mstates, s->best_dev, s->keys_dev, s->mw_codes_dev, s->mw_plats_dev, s->mw_misc_dev);
             if (rc == TSS_OK) rc = launch_eval_platforms(e, s->rows_dev, w, h, s->mw_plats_dev, s->mw_misc_dev, 1, (int32_t*)(s->mw_misc_dev + 4), nullptr, nullptr, nullptr);
