@@ -417,6 +417,21 @@ def test_fused_one_shot_launch_equals_the_epoch_by_epoch_path(fixtures):
             assert sorted(s.best_layout().platforms()) == pa
             second_epoch_needed += steps > 64
             s.close()
+    # the placement search (platform sets beyond {1x1}) has the same fused first epoch once a workspace of that set is cached
+    for name, limit in (("ex1", 1), ("ex3", 1), ("ex2", 4)):
+        g = T.WorldGrid(fixtures[name])
+        for seed in (3, 4, 5):
+            e2 = T.Engine(0)
+            res_a, lay_a = e2.solve_upper_bound(g, T.PLATFORMS_DEFAULT, card_limit=limit, seed=seed)
+            launches_a = e2.stats()["kernel_launches"]
+            res_b, lay_b = e2.solve_upper_bound(g, T.PLATFORMS_DEFAULT, card_limit=limit, seed=seed)
+            launches_b = e2.stats()["kernel_launches"] - launches_a
+            res_c, lay_c = e2.solve_upper_bound(g, T.PLATFORMS_DEFAULT[:4], card_limit=None, seed=seed)   # another platform set: no fused launch, fresh keys
+            e2.close()
+            assert res_a == res_b == res_c == T.SAT and launches_b < launches_a
+            assert sorted(lay_a.platforms().values()) == sorted(lay_b.platforms().values()) and lay_b.platform_count() <= limit
+            assert O.validate(g.data, [tup(p) for p in lay_c.platforms().values()]).is_valid
+            assert all(p.definition in T.PLATFORMS_DEFAULT[:4] for p in lay_c.platforms().values())
     # an infeasible bound with a give-up point: fused epoch, follow-up epochs, then UNKNOWN after exactly that many steps
     e2 = T.Engine(0)
     g = T.WorldGrid(np.ones((16, 16), np.uint8))

@@ -51,6 +51,10 @@ int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* 
              uint32_t chain_offset, uint64_t seed, long long steps, int* bounds_dev, int target, int noise_pct, unsigned long long* totals_dev,
              int2* best_dev);
 int slsm_read_best(tss_engine* e, const void* states, int chain, std::vector<uint16_t>& codes);
+int slsm_run_oneshot(tss_engine* e, const uint32_t* rows32_host, int bound, uint32_t* rows_dev, int W, int H, const int2* keys_dev, const int* costs_dev,
+                     const int* order_dev, int n_keys, void* states, int n_chains, uint64_t seed, long long steps, int* bounds_dev, int2* best_dev,
+                     unsigned long long* key_dev, unsigned int* ticket_dev, int target, int noise_pct, unsigned long long* totals_dev,
+                     uint32_t* result_host_mapped);
 int slsm_witness(tss_engine* e, const void* states, const int2* best_dev, const int2* keys_dev, uint16_t* codes_dev, int4* plats_dev, uint32_t* offsets_dev);
 int slsm_max_items();
 int slsm_read_states(tss_engine* e, const void* states, int n_chains, uint16_t* items, int32_t* k, uint16_t* best_items, int32_t* best_k,
@@ -508,6 +512,21 @@ static int search_init_device(tss_engine* e, tss_search* s, int n_terrains) {
     return sls_init_states(e, s->states, s->n_chains);
 }
 
+// dims keys of a platform set: both orientations of every def in defs order, unflipped first (src/encoder.rs:121-130)
+static void build_keys(const tss_dims* defs, int n_defs, std::vector<int2>& key_dims, std::vector<tss_platform>& key_proto) {
+    key_dims.clear();
+    key_proto.clear();
+    for (int i = 0; i < n_defs; i++)
+        for (int rot = 0; rot < 2; rot++) {
+            int2 d = rot ? make_int2(defs[i].h, defs[i].w) : make_int2(defs[i].w, defs[i].h);
+            bool seen = false;
+            for (auto& kd : key_dims) seen = seen || (kd.x == d.x && kd.y == d.y);
+            if (seen) continue;
+            key_dims.push_back(d);
+            key_proto.push_back(tss_platform{0, 0, defs[i].w, defs[i].h, rot});
+        }
+}
+
 // Chains that fill the device: 32 warps per SM for the warp kernels (two chains per warp on grids of <= 16 rows),
 // 3 CTAs of 128 threads per SM for the thread-per-chain kernel.
 static int default_chains(const tss_engine* e, int w, int h, int kernel) {
@@ -564,16 +583,8 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++)
             if (grid[(size_t)y * w + x]) rows[y] |= 1u << x;
-    // dims keys (both orientations of every def, src/encoder.rs:121-130); more than the single 1x1 key -> placement search
-    for (int i = 0; i < n_defs; i++)
-        for (int rot = 0; rot < 2; rot++) {
-            int2 d = rot ? make_int2(defs[i].h, defs[i].w) : make_int2(defs[i].w, defs[i].h);
-            bool seen = false;
-            for (auto& kd : s->key_dims) seen = seen || (kd.x == d.x && kd.y == d.y);
-            if (seen) continue;
-            s->key_dims.push_back(d);
-            s->key_proto.push_back(tss_platform{0, 0, defs[i].w, defs[i].h, rot});
-        }
+    // more than the single 1x1 key -> placement search
+    build_keys(defs, n_defs, s->key_dims, s->key_proto);
     bool fits = (int)s->key_dims.size() <= slsm_max_keys();
     for (auto& kd : s->key_dims) fits = fits && kd.x <= 6 && kd.y <= 6;
     if (s->key_dims.size() > 1 && fits) {
@@ -589,6 +600,8 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
             s->best_host = old->best_host; s->totals_host = old->totals_host;
             s->mw_codes_dev = old->mw_codes_dev; s->mw_plats_dev = old->mw_plats_dev; s->mw_misc_dev = old->mw_misc_dev;
             s->mw_codes_host = old->mw_codes_host; s->mw_misc_host = old->mw_misc_host;
+            s->reduce_key_dev = old->reduce_key_dev; s->ticket_dev = old->ticket_dev;
+            s->oneshot_host = old->oneshot_host; s->oneshot_host_dev = old->oneshot_host_dev;
             delete old;
         } else {
             err = cudaMalloc(&s->rows_dev, sizeof rows);
@@ -605,7 +618,14 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
             if (err == cudaSuccess) err = cudaMalloc(&s->mw_misc_dev, sizeof(uint32_t) * 8);
             if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->mw_codes_host, sizeof(uint16_t) * (size_t)slsm_max_items(), cudaHostAllocDefault);
             if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->mw_misc_host, sizeof(uint32_t) * 8, cudaHostAllocDefault);
+            if (err == cudaSuccess) err = cudaMalloc(&s->reduce_key_dev, sizeof(unsigned long long));
+            if (err == cudaSuccess) err = cudaMalloc(&s->ticket_dev, sizeof(unsigned int));
+            if (err == cudaSuccess) err = cudaMemsetAsync(s->reduce_key_dev, 0xff, sizeof(unsigned long long), e->stream);
+            if (err == cudaSuccess) err = cudaMemsetAsync(s->ticket_dev, 0, sizeof(unsigned int), e->stream);
+            if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->oneshot_host, sizeof(uint32_t) * (16 + (size_t)slsm_max_items() / 2), cudaHostAllocMapped);
+            if (err == cudaSuccess) err = cudaHostGetDevicePointer((void**)&s->oneshot_host_dev, s->oneshot_host, 0);
         }
+        s->totals_seen[0] = s->totals_seen[1] = 0;
         const int nb = sls::NO_BOUND;
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->rows_dev, rows, sizeof rows, cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->keys_dev, s->key_dims.data(), sizeof(int2) * s->key_dims.size(), cudaMemcpyHostToDevice, e->stream);
@@ -1045,7 +1065,65 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
             }
         }
         if (rc != TSS_OK) { search_free(s); return rc; }
-    } else {
+    } else if (!only_1x1 && multi_chains > 0 && grid && defs && w > 0 && h > 0 && e->cached_multi && e->cached_multi->n_chains == multi_chains &&
+               !e->interrupted()) {
+        // placement search, first-model mode, workspace of the SAME platform set cached (keys, costs and their order are
+        // already on the device): the first epoch as one fused launch (sls_multi.cu OneShotM)
+        std::vector<int2> kd;
+        std::vector<tss_platform> kp;
+        build_keys(defs, n_defs, kd, kp);
+        tss_search* c = e->cached_multi;
+        bool same = kd.size() == c->key_dims.size();
+        for (size_t i = 0; same && i < kd.size(); i++) same = kd[i].x == c->key_dims[i].x && kd[i].y == c->key_dims[i].y && c->key_costs[i] == 1;
+        if (same) {
+            s = c;
+            e->cached_multi = nullptr;
+            s->w = w; s->h = h; s->seed = seed; s->chain_offset = 0; s->noise = sls::DEFAULT_NOISE_PCT;
+            s->grid.assign(grid, grid + (size_t)w * h);
+            s->external_bound = sls::NO_BOUND;
+            uint32_t rows_now[32];
+            for (int y = 0; y < 32; y++) rows_now[y] = 0;
+            for (int y = 0; y < h; y++)
+                for (int x = 0; x < w; x++)
+                    if (grid[(size_t)y * w + x]) rows_now[y] |= 1u << x;
+            fused_steps = 16;
+            rc = cudaSetDevice(e->device) == cudaSuccess ? search_sync(s) : e->fail(TSS_E_CUDA, "tss_solve_upper_bound: cudaSetDevice failed");
+            if (rc == TSS_OK) {
+                cudaEventRecord(e->ev0, e->stream);
+                rc = slsm_run_oneshot(e, rows_now, card_limit >= 0 ? card_limit + 1 : sls::NO_BOUND, s->rows_dev, w, h, s->keys_dev, s->costs_dev,
+                                      s->costs_dev + slsm_max_keys(), (int)s->key_dims.size(), s->mstates, s->n_chains, seed, fused_steps, s->bounds_dev,
+                                      s->best_dev, s->reduce_key_dev, s->ticket_dev, card_limit >= 0 ? card_limit : sls::NO_BOUND - 1, s->noise,
+                                      s->totals_dev, s->oneshot_host_dev);
+                cudaEventRecord(e->ev1, e->stream);
+            }
+            if (rc == TSS_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = e->fail(TSS_E_CUDA, "tss_solve_upper_bound: fused epoch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (rc == TSS_OK) {
+                const volatile uint32_t* r = s->oneshot_host;
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) cudaGetLastError();
+                e->stats.device_ms = ms;
+                e->stats.n_solves++;
+                const unsigned long long t0 = ((unsigned long long)r[7] << 32) | r[6], t1 = ((unsigned long long)r[9] << 32) | r[8];
+                e->stats.candidates_scored += t0 - s->totals_seen[0];
+                e->stats.sls_steps += t1 - s->totals_seen[1];
+                s->totals_seen[0] = t0; s->totals_seen[1] = t1;
+                s->totals_host[0] = t0; s->totals_host[1] = t1;
+                s->best_host[0] = make_int2((int)r[0], (int)r[1]);
+                s->dirty = false;
+                if ((int)r[0] < sls::NO_BOUND) {   // hand the witness to the common tail in the layout of the in-stream witness buffers
+                    fused_best = (int)r[0];
+                    e->stats.best_count = fused_best;
+                    const int n = (int)r[2] < slsm_max_items() ? (int)r[2] : slsm_max_items();
+                    const volatile uint16_t* codes = reinterpret_cast<const volatile uint16_t*>(s->oneshot_host + 16);
+                    for (int i = 0; i < n; i++) s->mw_codes_host[i] = codes[i];
+                    s->mw_misc_host[0] = 0; s->mw_misc_host[1] = r[2];
+                    s->mw_misc_host[4] = r[3]; s->mw_misc_host[5] = r[2]; s->mw_misc_host[6] = r[4]; s->mw_misc_host[7] = r[5];
+                }
+            }
+            if (rc != TSS_OK) { search_free(s); return rc; }
+        }
+    }
+    if (!s) {
         rc = tss_search_create(e, grid, w, h, defs, n_defs, &p, &s);
         if (rc) return rc;
     }
@@ -1059,7 +1137,7 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     if (budget_ms <= 0 && max_steps < 0) max_steps = -max_steps;   // SAT-like call with a caller-chosen give-up point
     else if (budget_ms <= 0 && max_steps == 0) max_steps = windowed ? (1 << 16) : (1 << 18);
     // (a placement-search step costs ~5 us of latency: start with short epochs when the first model is all that is asked for)
-    int64_t done_steps = fused_steps, epoch = (s->multi && first_model_only) ? 16 : (fused_steps ? 2 * fused_steps : (first_model_only && !s->lns ? 32 : 64));
+    int64_t done_steps = fused_steps, epoch = fused_steps ? 2 * fused_steps : ((s->multi && first_model_only) ? 16 : (first_model_only && !s->lns ? 32 : 64));
     int best = fused_best;
     const bool in_stream_witness = !s->lns && !s->multi && s->n_groups == 1;   // 1x1 supports on a grid up to 32x32
     // First-model mode: chains stop at the first layout within the limit (target = card_limit).  (Queueing several epochs

@@ -174,13 +174,33 @@ __device__ __forceinline__ int pick_rotated(uint32_t bits, uint32_t o) {
     return (int)((__ffs(rot) - 1 + o) & 31u);
 }
 
+// ONESHOT = the first epoch of a one-shot solve in ONE launch (tss_solve_upper_bound, first-model mode, workspace of the same
+// platform set cached): terrain rows and bound arrive as kernel parameters, chains start empty in registers (no init
+// kernel), and the last CTA to finish — a ticket counter — folds the best objective, fetches the winner's placements,
+// re-validates them (footprints in bounds and pairwise disjoint, validate()'s three dilations: kernel (a) in one-warp
+// form) and writes everything into mapped host memory.  One launch, one synchronisation.
+struct OneShotM {
+    uint32_t rows[32];            // terrain rows
+    int bound;                    // chains look for an objective below this (card_limit + 1, or NO_BOUND)
+    uint32_t* rows_out;           // [32] kept on the device for follow-up epochs
+    int* bounds_out;              // [1]
+    int2* best_out;               // [1]
+    unsigned long long* key;      // running (best << 32 | chain) minimum, ~0 between launches
+    unsigned int* ticket;         // CTAs finished, 0 between launches
+    uint32_t* result_host;        // mapped host memory: [0] best objective, [1] winner chain, [2] placements n, [3] unsupported tiles,
+                                  // [4] overlapping, [5] out of bounds, [6..9] totals (candidates, steps) as two u64,
+                                  // from word 16: the n placement codes as u16
+};
+
+template <bool ONESHOT>
 __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* __restrict__ terrain_rows, int W, int H,
                                                               const int2* __restrict__ keys_g, const int* __restrict__ costs_g,
                                                               const int* __restrict__ order_g, int n_keys,
                                                               MultiState* __restrict__ states,
                                                               int n_chains, uint32_t chain_offset, uint64_t seed, long long steps,
                                                               const int* __restrict__ bounds, int target, int noise_pct,
-                                                              const volatile int* interrupt, unsigned long long* __restrict__ totals) {
+                                                              const volatile int* interrupt, unsigned long long* __restrict__ totals,
+                                                              const OneShotM os) {
     __shared__ uint16_t items_all[WARPS][MAX_ITEMS];
     __shared__ int2 keys[MAX_KEYS];
     __shared__ int costs[MAX_KEYS];
@@ -189,25 +209,30 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
     const int chain = blockIdx.x * WARPS + warp;
     // a layout within the target is already known for this terrain (found in an earlier epoch): nothing to do.  Lets a host
     // queue several epochs back to back without a round trip in between (one-shot solves, sls_spec.hpp).
-    if (target >= 0 && bounds[0] <= target) return;
+    if (!ONESHOT && target >= 0 && bounds[0] <= target) return;
     if (threadIdx.x < n_keys) { keys[threadIdx.x] = keys_g[threadIdx.x]; costs[threadIdx.x] = costs_g[threadIdx.x]; order[threadIdx.x] = order_g[threadIdx.x]; }
     __syncthreads();
     int cmin = costs[0];
     for (int i = 1; i < n_keys; i++) cmin = min(cmin, costs[i]);
-    if (chain >= n_chains) return;
+    if (!ONESHOT && chain >= n_chains) return;   // (a one-shot launch has whole CTAs of chains: everyone takes part in the ticket)
     MultiState& st = states[chain];
-    if (st.done) return;
+    if (!ONESHOT && st.done) return;
+    if (ONESHOT && blockIdx.x == 0 && threadIdx.x < 32) {
+        os.rows_out[threadIdx.x] = os.rows[threadIdx.x];
+        if (threadIdx.x == 0) os.bounds_out[0] = os.bound;
+    }
 
-    const int epoch_bound = bounds[0];
+    const int epoch_bound = ONESHOT ? os.bound : bounds[0];
     const uint32_t base = sls::chain_base(seed, chain_offset + (uint32_t)chain);
     const uint32_t nq7 = sls::noise_q7(noise_pct);
     Ctx c{items_all[warp], keys, lane, W, H};
     Lane L;
-    L.C = terrain_rows[lane];
+    L.C = ONESHOT ? os.rows[lane] : terrain_rows[lane];
     L.Occ = 0;
     L.c0 = L.c1 = L.c2 = L.c3 = L.c4 = 0;
-    int k = st.k, best = st.best, tabu_add = st.tabu_add, tabu_rem = st.tabu_rem, done = 0;
-    uint32_t step = st.step;
+    int k = ONESHOT ? 0 : st.k, best = ONESHOT ? sls::NO_BOUND : st.best, tabu_add = ONESHOT ? -1 : st.tabu_add, tabu_rem = ONESHOT ? -1 : st.tabu_rem, done = 0;
+    uint32_t step = ONESHOT ? 0u : st.step;
+    if (ONESHOT && lane == 0) st.best_k = 0;
     unsigned long long scored = 0;
     for (int i = lane; i < k; i += 32) c.items[i] = st.items[i];
     __syncwarp();
@@ -301,6 +326,56 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
         st.k = k; st.best = best; st.step = step; st.tabu_add = tabu_add; st.tabu_rem = tabu_rem; st.done = done;
         atomicAdd(&totals[0], scored);
         atomicAdd(&totals[1], (unsigned long long)it);
+        if (ONESHOT && best < sls::NO_BOUND) atomicMin(os.key, ((unsigned long long)(uint32_t)best << 32) | (uint32_t)chain);
+    }
+    if (ONESHOT) {
+        __shared__ bool last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last = atomicAdd(os.ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (last && warp == 0) {
+            __threadfence();
+            const unsigned long long key = *(volatile unsigned long long*)os.key;
+            const int bobj = key == ~0ull ? sls::NO_BOUND : (int)(key >> 32), bchain = key == ~0ull ? -1 : (int)(key & 0xffffffffu);
+            const MultiState* win = bchain >= 0 ? states + bchain : nullptr;
+            const int n = win ? __ldcg(&win->best_k) : 0;
+            uint16_t* codes_host = reinterpret_cast<uint16_t*>(os.result_host + 16);
+            // validate()'s view of the winner (platform_layout.rs:85-149): footprints stamped row by row (lane = row), overlap and
+            // bounds flags, then three ceiling-masked dilations from the ceiling under the footprints
+            uint32_t occ = 0, overlap = 0, oob = 0;
+            for (int i = 0; i < n; i++) {
+                const int code = __ldcg(&win->best_items[i]);
+                const int2 d = keys[code >> 10];
+                const int x = code & 31, y = (code >> 5) & 31;
+                if (x + d.x > W || y + d.y > H) oob = 1;
+                const uint32_t sp = (lane >= y && lane < y + d.y) ? span(x, d.x) : 0u;
+                overlap |= occ & sp;
+                occ |= sp;
+                if (lane == (i & 31)) codes_host[i] = (uint16_t)code;
+            }
+            uint32_t X = occ & L.C;
+            for (int round = 0; round < 3; round++) {
+                uint32_t up = __shfl_up_sync(FULL, X, 1), down = __shfl_down_sync(FULL, X, 1);
+                if (lane == 0) up = 0;
+                if (lane == 31) down = 0;
+                X = (X | (X << 1) | (X >> 1) | up | down) & L.C;
+            }
+            const int unc = __reduce_add_sync(FULL, __popc(L.C & ~X));
+            const bool any_overlap = __any_sync(FULL, overlap != 0);
+            if (lane == 0) {
+                os.best_out[0] = make_int2(bobj, bchain);
+                if (bobj < os.bound) os.bounds_out[0] = bobj;
+                const unsigned long long t0 = *(volatile unsigned long long*)&totals[0], t1 = *(volatile unsigned long long*)&totals[1];
+                os.result_host[0] = (uint32_t)bobj; os.result_host[1] = (uint32_t)bchain; os.result_host[2] = (uint32_t)n;
+                os.result_host[3] = (uint32_t)unc; os.result_host[4] = any_overlap ? 1u : 0u; os.result_host[5] = oob;
+                os.result_host[6] = (uint32_t)t0; os.result_host[7] = (uint32_t)(t0 >> 32);
+                os.result_host[8] = (uint32_t)t1; os.result_host[9] = (uint32_t)(t1 >> 32);
+                *os.key = ~0ull;
+                *os.ticket = 0u;
+                __threadfence_system();
+            }
+        }
     }
 }
 
@@ -361,15 +436,34 @@ int slsm_run(tss_engine* e, const uint32_t* rows_dev, int W, int H, const int2* 
              uint32_t chain_offset, uint64_t seed, long long steps, int* bounds_dev, int target, int noise_pct, unsigned long long* totals_dev,
              int2* best_dev) {
     int blocks = (n_chains + slsm::WARPS - 1) / slsm::WARPS;
-    slsm::sls_multi_kernel<<<blocks, slsm::WARPS * 32, 0, e->stream>>>(rows_dev, W, H, keys_dev, costs_dev, order_dev, n_keys, (slsm::MultiState*)states, n_chains,
-                                                                     chain_offset, seed, steps, bounds_dev, target, noise_pct, e->interrupt_dev,
-                                                                     totals_dev);
+    slsm::sls_multi_kernel<false><<<blocks, slsm::WARPS * 32, 0, e->stream>>>(rows_dev, W, H, keys_dev, costs_dev, order_dev, n_keys, (slsm::MultiState*)states, n_chains,
+                                                                            chain_offset, seed, steps, bounds_dev, target, noise_pct, e->interrupt_dev,
+                                                                            totals_dev, slsm::OneShotM{});
     TSS_CHECK_LAUNCH(e);
     slsm::multi_best_kernel<<<1, 256, 0, e->stream>>>((const slsm::MultiState*)states, n_chains, best_dev, bounds_dev);
     TSS_CHECK_LAUNCH(e);
     e->stats.kernel_launches += 2;
     return TSS_OK;
 }
+// The fused first epoch of a one-shot solve (see slsm::OneShotM).  n_chains must be a multiple of 4 (whole CTAs);
+// result_host_mapped: mapped pinned memory of 16 + 512 words; key_dev holds ~0 and ticket_dev 0 (both re-arm themselves).
+int slsm_run_oneshot(tss_engine* e, const uint32_t* rows32_host, int bound, uint32_t* rows_dev, int W, int H, const int2* keys_dev, const int* costs_dev,
+                     const int* order_dev, int n_keys, void* states, int n_chains, uint64_t seed, long long steps, int* bounds_dev, int2* best_dev,
+                     unsigned long long* key_dev, unsigned int* ticket_dev, int target, int noise_pct, unsigned long long* totals_dev,
+                     uint32_t* result_host_mapped) {
+    if (n_chains <= 0 || n_chains % slsm::WARPS != 0) return e->fail(TSS_E_INVALID, "one-shot launch needs whole CTAs of chains");
+    slsm::OneShotM os;
+    for (int r = 0; r < 32; r++) os.rows[r] = rows32_host[r];
+    os.bound = bound; os.rows_out = rows_dev; os.bounds_out = bounds_dev; os.best_out = best_dev; os.key = key_dev; os.ticket = ticket_dev;
+    os.result_host = result_host_mapped;
+    slsm::sls_multi_kernel<true><<<n_chains / slsm::WARPS, slsm::WARPS * 32, 0, e->stream>>>(nullptr, W, H, keys_dev, costs_dev, order_dev, n_keys, (slsm::MultiState*)states,
+                                                                                            n_chains, 0u, seed, steps, nullptr, target, noise_pct, e->interrupt_dev,
+                                                                                            totals_dev, os);
+    TSS_CHECK_LAUNCH(e);
+    e->stats.kernel_launches++;
+    return TSS_OK;
+}
+
 int slsm_witness(tss_engine* e, const void* states, const int2* best_dev, const int2* keys_dev, uint16_t* codes_dev, int4* plats_dev, uint32_t* offsets_dev) {
     slsm::multi_witness_kernel<<<1, 128, 0, e->stream>>>((const slsm::MultiState*)states, best_dev, keys_dev, codes_dev, plats_dev, offsets_dev);
     TSS_CHECK_LAUNCH(e);
