@@ -972,7 +972,12 @@ int tss_solve_min_weight(tss_engine* e, const uint8_t* grid, int32_t w, int32_t 
         if (out_weight) *out_weight = best;
         if (rc == TSS_OK) result = TSS_SAT;
     }
-    tss_search_destroy(s);
+    if (s->multi && !e->cached_multi && rc == TSS_OK) {
+        cudaStreamSynchronize(e->stream);
+        e->cached_multi = s;   // the GUI tightens weight_limit call after call (app.rs:235-245): the next tss_search_create adopts these buffers
+    } else {
+        tss_search_destroy(s);
+    }
     return rc != TSS_OK ? rc : result;
 }
 
