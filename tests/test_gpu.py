@@ -647,6 +647,29 @@ def test_sls_large_grid_reaches_sum_of_component_optima(eng, fixtures):
     assert res == T.INTERRUPTED
 
 
+def test_large_grid_with_larger_platforms_merges_supports(eng):
+    """Grids larger than 32x32 are searched with 1x1 supports; with a platform set that holds larger platforms the engine
+    merges supports that fit under one footprint into that platform.  The result passes the reference's validate()
+    (complete, footprints disjoint and in bounds), only uses platforms of the set, and needs fewer platforms than the
+    1x1 layout of the same search."""
+    grid = synth_terrain(96, 72, seed=4, t=1, density_q24=int(0.85 * (1 << 24)))
+    g = T.WorldGrid(grid)
+    counts = {}
+    for name, defs in (("1x1", T.PLATFORMS_DEFAULT[:1]), ("default-8", T.PLATFORMS_DEFAULT)):
+        s = eng.search(g, defs, seed=5)
+        for _ in range(4):
+            s.run(1500, 0)
+        lay = s.best_layout()                                   # re-validated by kernel (a) (platform evaluator) inside the engine
+        s.close()
+        plats = list(lay.platforms().values())
+        assert O.validate(grid, [tup(p) for p in plats]).is_valid
+        assert all(p.definition in defs for p in plats)
+        counts[name] = len(plats)
+    assert counts["default-8"] < 0.8 * counts["1x1"]
+    res, lay = eng.solve_upper_bound(g, T.PLATFORMS_DEFAULT, seed=5, max_steps=3000)
+    assert res == T.SAT and O.validate(grid, [tup(p) for p in lay.platforms().values()]).is_valid and lay.platform_count() < 0.8 * counts["1x1"]
+
+
 def test_solve_batch_terrains(eng):
     """C5 shape (scaled down): per-terrain counts are complete layouts, never below the trivial lower bound, and
     agree with the oracle's proven optimum where that is cheap to prove."""

@@ -563,6 +563,7 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
         int seeds = (params && params->n_chains > 0) ? ((params->n_chains + 3) / 4) * 4 : fill;
         int rc = lns_create(e, grid, w, h, seeds, s->seed, s->chain_offset, s->noise, &s->lns);
         if (rc != TSS_OK) { delete s; return rc; }
+        build_keys(defs, n_defs, s->key_dims, s->key_proto);   // (platform sets beyond {1x1}: the 1x1 layout is merged afterwards, merge_supports)
         s->n_chains = lns_chains(s->lns);
         *out = s;
         return TSS_OK;
@@ -857,6 +858,65 @@ int tss_search_write_chains(tss_search* s, const uint32_t* S) {
     return TSS_OK;
 }
 
+// Grids larger than 32x32 are searched with 1x1 supports only (window decomposition).  When the platform set holds larger
+// platforms, supports that fit under one footprint are merged into that platform: its reach contains the reach of every
+// support under it (validate() dilates from all ceiling tiles under a footprint, platform_layout.rs:116-141), so the
+// layout stays complete, and footprints are kept pairwise disjoint and in bounds.  Greedy: larger platforms first, per
+// platform size the anchors holding most supports first.  A valid, tighter bound — not a search over placements.
+static void merge_supports(int w, int h, const std::vector<int2>& key_dims, const std::vector<tss_platform>& key_proto, std::vector<tss_platform>& plats) {
+    if (key_dims.size() <= 1 || plats.empty()) return;
+    std::vector<uint8_t> sup((size_t)w * h, 0), occ((size_t)w * h, 0);
+    for (auto& p : plats) sup[(size_t)p.y * w + p.x] = 1;
+    std::vector<int> order(key_dims.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key_dims[a].x * key_dims[a].y > key_dims[b].x * key_dims[b].y; });
+    std::vector<tss_platform> merged;
+    std::vector<int> pre((size_t)(w + 1) * (h + 1));
+    for (int key : order) {
+        const int pw = key_dims[key].x, ph = key_dims[key].y;
+        if (pw * ph <= 1 || pw > w || ph > h) continue;
+        for (;;) {  // rounds: recount after every batch of non-conflicting merges
+            std::fill(pre.begin(), pre.end(), 0);
+            for (int y = 0; y < h; y++)
+                for (int x = 0; x < w; x++)
+                    pre[(size_t)(y + 1) * (w + 1) + x + 1] = sup[(size_t)y * w + x] + pre[(size_t)y * (w + 1) + x + 1] + pre[(size_t)(y + 1) * (w + 1) + x] - pre[(size_t)y * (w + 1) + x];
+            auto inside = [&](int x, int y) { return pre[(size_t)(y + ph) * (w + 1) + x + pw] - pre[(size_t)y * (w + 1) + x + pw] - pre[(size_t)(y + ph) * (w + 1) + x] + pre[(size_t)y * (w + 1) + x]; };
+            std::vector<std::pair<int, int>> cand;  // (supports under the footprint, anchor)
+            for (int y = 0; y + ph <= h; y++)
+                for (int x = 0; x + pw <= w; x++) {
+                    const int c = inside(x, y);
+                    if (c >= 2) cand.push_back({c, y * w + x});
+                }
+            if (cand.empty()) break;
+            std::stable_sort(cand.begin(), cand.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
+            int placed = 0;
+            for (auto& [c0, anchor] : cand) {
+                const int x = anchor % w, y = anchor / w;
+                int c = 0;
+                bool free_ = true;
+                for (int yy = y; yy < y + ph && free_; yy++)
+                    for (int xx = x; xx < x + pw; xx++) {
+                        if (occ[(size_t)yy * w + xx]) { free_ = false; break; }
+                        c += sup[(size_t)yy * w + xx];
+                    }
+                if (!free_ || c < 2) continue;   // (an earlier merge of this round took its supports or its tiles)
+                for (int yy = y; yy < y + ph; yy++)
+                    for (int xx = x; xx < x + pw; xx++) { occ[(size_t)yy * w + xx] = 1; sup[(size_t)yy * w + xx] = 0; }
+                tss_platform p = key_proto[key];
+                p.x = x; p.y = y;
+                merged.push_back(p);
+                placed++;
+            }
+            if (!placed) break;
+        }
+    }
+    if (merged.empty()) return;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            if (sup[(size_t)y * w + x]) merged.push_back(tss_platform{x, y, 1, 1, 0});
+    plats.swap(merged);
+}
+
 int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_t* n_out) {
     if (!s || !n_out) return TSS_E_INVALID;
     tss_engine* e = s->e;
@@ -872,6 +932,7 @@ int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_
         for (int y = 0; y < s->h; y++)
             for (int x = 0; x < s->w; x++)
                 if ((rows[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u) plats.push_back(tss_platform{x, y, 1, 1, 0});
+        merge_supports(s->w, s->h, s->key_dims, s->key_proto, plats);
         best = make_int2((int)plats.size(), 0);
     } else if (s->multi) {
         best = s->best_host[0];
