@@ -863,6 +863,58 @@ int tss_search_write_chains(tss_search* s, const uint32_t* S) {
 // support under it (validate() dilates from all ceiling tiles under a footprint, platform_layout.rs:116-141), so the
 // layout stays complete, and footprints are kept pairwise disjoint and in bounds.  Greedy: larger platforms first, per
 // platform size the anchors holding most supports first.  A valid, tighter bound — not a search over placements.
+// tiles supported by one platform: validate()'s rule restricted to its own window (footprint + 3 on every side)
+static void platform_reach(const std::vector<uint8_t>& grid, int w, int h, const tss_platform& p, std::vector<int>& out) {
+    const Dims d = platform_dims(p);
+    const int x0 = std::max(p.x - 3, 0), y0 = std::max(p.y - 3, 0), x1 = std::min(p.x + d.w + 3, w), y1 = std::min(p.y + d.h + 3, h);
+    const int bw = x1 - x0, bh = y1 - y0;
+    std::vector<uint8_t> cur((size_t)bw * bh, 0), nxt;
+    for (int y = std::max(p.y, 0); y < std::min(p.y + d.h, h); y++)
+        for (int x = std::max(p.x, 0); x < std::min(p.x + d.w, w); x++)
+            if (grid[(size_t)y * w + x]) cur[(size_t)(y - y0) * bw + (x - x0)] = 1;
+    for (int round = 0; round < kTerrainSupportDistance - 1; round++) {
+        nxt = cur;
+        for (int y = 0; y < bh; y++)
+            for (int x = 0; x < bw; x++) {
+                if (!cur[(size_t)y * bw + x]) continue;
+                const int nx[4] = {x + 1, x, x - 1, x}, ny[4] = {y, y + 1, y, y - 1};
+                for (int k = 0; k < 4; k++)
+                    if (nx[k] >= 0 && nx[k] < bw && ny[k] >= 0 && ny[k] < bh && grid[(size_t)(ny[k] + y0) * w + nx[k] + x0]) nxt[(size_t)ny[k] * bw + nx[k]] = 1;
+            }
+        cur.swap(nxt);
+    }
+    out.clear();
+    for (int y = 0; y < bh; y++)
+        for (int x = 0; x < bw; x++)
+            if (cur[(size_t)y * bw + x]) out.push_back((y + y0) * w + x + x0);
+}
+
+// Drops platforms every tile of whose reach is also supported by another platform (smallest platforms first): the
+// merged platforms reach further than the supports they replaced, which makes many neighbours redundant.
+static void prune_redundant(const std::vector<uint8_t>& grid, int w, int h, std::vector<tss_platform>& plats) {
+    std::vector<std::vector<int>> reach(plats.size());
+    std::vector<uint16_t> cover((size_t)w * h, 0);
+    for (size_t i = 0; i < plats.size(); i++) {
+        platform_reach(grid, w, h, plats[i], reach[i]);
+        for (int t : reach[i]) cover[(size_t)t]++;
+    }
+    std::vector<size_t> order(plats.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return plats[a].def_w * plats[a].def_h < plats[b].def_w * plats[b].def_h; });
+    std::vector<uint8_t> drop(plats.size(), 0);
+    for (size_t i : order) {
+        bool redundant = true;
+        for (int t : reach[i]) redundant = redundant && cover[(size_t)t] >= 2;
+        if (!redundant) continue;
+        drop[i] = 1;
+        for (int t : reach[i]) cover[(size_t)t]--;
+    }
+    std::vector<tss_platform> kept;
+    for (size_t i = 0; i < plats.size(); i++)
+        if (!drop[i]) kept.push_back(plats[i]);
+    plats.swap(kept);
+}
+
 static void merge_supports(int w, int h, const std::vector<int2>& key_dims, const std::vector<tss_platform>& key_proto, std::vector<tss_platform>& plats) {
     if (key_dims.size() <= 1 || plats.empty()) return;
     std::vector<uint8_t> sup((size_t)w * h, 0), occ((size_t)w * h, 0);
@@ -932,7 +984,10 @@ int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_
         for (int y = 0; y < s->h; y++)
             for (int x = 0; x < s->w; x++)
                 if ((rows[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u) plats.push_back(tss_platform{x, y, 1, 1, 0});
-        merge_supports(s->w, s->h, s->key_dims, s->key_proto, plats);
+        if (s->key_dims.size() > 1) {
+            merge_supports(s->w, s->h, s->key_dims, s->key_proto, plats);
+            prune_redundant(s->grid, s->w, s->h, plats);
+        }
         best = make_int2((int)plats.size(), 0);
     } else if (s->multi) {
         best = s->best_host[0];
