@@ -57,6 +57,8 @@ int slsm_run_oneshot(tss_engine* e, const uint32_t* rows32_host, int bound, uint
                      uint32_t* result_host_mapped);
 int slsm_witness(tss_engine* e, const void* states, const int2* best_dev, const int2* keys_dev, uint16_t* codes_dev, int4* plats_dev, uint32_t* offsets_dev);
 int slsm_max_items();
+// greedy.cu — parallel greedy placement cover for grids larger than 32x32 (platform sets beyond {1x1})
+int greedy_cover(tss_engine* e, const uint32_t* C_rows_host, int w, int h, const std::vector<int2>& keys, std::vector<int4>& out);
 int slsm_read_states(tss_engine* e, const void* states, int n_chains, uint16_t* items, int32_t* k, uint16_t* best_items, int32_t* best_k,
                      int32_t* best, uint32_t* step);
 
@@ -172,6 +174,8 @@ struct tss_search {
     int* costs_dev = nullptr;
     void* mstates = nullptr;
     // in-stream witness of one-shot solves: codes u16[1024], (x, y, w, h) records, misc = offsets[2] + evaluator result[4]
+    std::vector<tss_platform> greedy_plats;    // grids > 32x32, platform sets beyond {1x1}: the greedy placement cover (computed once, it only depends on the terrain)
+    bool greedy_done = false;
     uint16_t* mw_codes_dev = nullptr;
     int4* mw_plats_dev = nullptr;
     uint32_t* mw_misc_dev = nullptr;
@@ -985,8 +989,28 @@ int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_
             for (int x = 0; x < s->w; x++)
                 if ((rows[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u) plats.push_back(tss_platform{x, y, 1, 1, 0});
         if (s->key_dims.size() > 1) {
+            // two constructors for a layout with larger platforms, the better one wins: the searched 1x1 layout with supports
+            // merged under footprints, and a greedy placement cover of the terrain (greedy.cu)
             merge_supports(s->w, s->h, s->key_dims, s->key_proto, plats);
             prune_redundant(s->grid, s->w, s->h, plats);
+            if (!s->greedy_done) {
+                bool fits = true;
+                for (auto& kd : s->key_dims) fits = fits && kd.x <= 6 && kd.y <= 6;
+                if (fits && (int)s->key_dims.size() <= 16) {
+                    BitGrid bg = BitGrid::from_bytes(s->grid.data(), s->w, s->h);
+                    std::vector<int4> placed;
+                    rc = greedy_cover(e, bg.rows.data(), s->w, s->h, s->key_dims, placed);
+                    if (rc) return rc;
+                    for (auto& q : placed) {
+                        tss_platform pl = s->key_proto[(size_t)q.z];
+                        pl.x = q.x; pl.y = q.y;
+                        s->greedy_plats.push_back(pl);
+                    }
+                    prune_redundant(s->grid, s->w, s->h, s->greedy_plats);
+                }
+                s->greedy_done = true;
+            }
+            if (!s->greedy_plats.empty() && s->greedy_plats.size() < plats.size()) plats = s->greedy_plats;
         }
         best = make_int2((int)plats.size(), 0);
     } else if (s->multi) {
