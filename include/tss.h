@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TSS_VERSION 100
+#define TSS_VERSION 101
 
 /* status codes; solve results follow IPASIR / rustsat SolverResult (crates/repl/src/main.rs:326-339) */
 #define TSS_OK 0
