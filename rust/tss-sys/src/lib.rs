@@ -1,0 +1,123 @@
+//! Raw bindings to `include/tss.h` (ABI version 101).  Every entry point cites, in the header, the reference
+//! interface it stands behind; this file only mirrors types and signatures.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int};
+
+pub const TSS_VERSION: c_int = 101;
+pub const TSS_OK: c_int = 0;
+pub const TSS_SAT: c_int = 10; // IPASIR / rustsat SolverResult::Sat
+pub const TSS_UNSAT: c_int = 20; // never returned by the GPU engine
+pub const TSS_UNKNOWN: c_int = 0; // SolverResult::Interrupted
+pub const TSS_KERNEL_AUTO: i32 = 0;
+
+#[repr(C)]
+#[derive(Copy, Clone, Default, Debug, PartialEq, Eq)]
+pub struct tss_platform {
+    pub x: i32,
+    pub y: i32,
+    pub def_w: i32, // canonical PlatformDef dims, w <= h (src/platform.rs:11-32)
+    pub def_h: i32,
+    pub rotated: i32, // effective dims = (def_h, def_w) when set (src/platform.rs:111-113)
+}
+
+#[repr(C)]
+#[derive(Copy, Clone, Default, Debug)]
+pub struct tss_dims {
+    pub w: i32,
+    pub h: i32,
+}
+
+#[repr(C)]
+#[derive(Copy, Clone, Default, Debug)]
+pub struct tss_stats {
+    pub layouts_evaluated: u64,
+    pub candidates_scored: u64,
+    pub sls_steps: u64,
+    pub clauses_checked: u64,
+    pub kernel_launches: u64,
+    pub n_solves: u64,
+    pub device_ms: f64,
+    pub best_count: i32,
+    pub interrupted: i32,
+    pub last_solve_steps: i64,
+}
+
+#[repr(C)]
+#[derive(Copy, Clone, Default, Debug)]
+pub struct tss_search_params {
+    pub seed: u64,
+    pub n_chains: i32,
+    pub chain_offset: i32,
+    pub noise_pct: i32,
+    pub kernel: i32,
+}
+
+#[repr(C)]
+pub struct tss_engine {
+    _p: [u8; 0],
+}
+#[repr(C)]
+pub struct tss_cnf {
+    _p: [u8; 0],
+}
+#[repr(C)]
+pub struct tss_search {
+    _p: [u8; 0],
+}
+
+unsafe extern "C" {
+    pub fn tss_version() -> c_int;
+    pub fn tss_engine_create(device: c_int, out: *mut *mut tss_engine) -> c_int;
+    pub fn tss_engine_destroy(e: *mut tss_engine);
+    pub fn tss_last_error(e: *const tss_engine) -> *const c_char;
+    pub fn tss_interrupt(e: *mut tss_engine);
+    pub fn tss_clear_interrupt(e: *mut tss_engine);
+    pub fn tss_get_stats(e: *const tss_engine, out: *mut tss_stats) -> c_int;
+
+    // the SAT side of crates/repl/src/main.rs:292-329 / crates/gui/src/solver_backend.rs:69-97
+    pub fn tss_solve_upper_bound(
+        e: *mut tss_engine, grid: *const u8, w: i32, h: i32, defs: *const tss_dims, n_defs: i32, card_limit: i32, seed: u64,
+        budget_ms: i32, max_steps: i64, out: *mut tss_platform, cap: i32, n_out: *mut i32,
+    ) -> c_int;
+    // the GUI's weight objective (crates/gui/src/app.rs:235-245)
+    pub fn tss_solve_min_weight(
+        e: *mut tss_engine, grid: *const u8, w: i32, h: i32, defs: *const tss_dims, n_defs: i32, weights: *const i32, n_weights: i32,
+        weight_limit: i64, seed: u64, budget_ms: i32, max_steps: i64, out: *mut tss_platform, cap: i32, n_out: *mut i32,
+        out_weight: *mut i64,
+    ) -> c_int;
+
+    // PlatformLayout::validate (src/encoder/platform_layout.rs:85-149) on the GPU
+    pub fn tss_validate(
+        e: *mut tss_engine, grid: *const u8, w: i32, h: i32, plats: *const tss_platform, n: i32, out_unsupported: *mut u8,
+        out_flags: *mut u8,
+    ) -> c_int;
+
+    // the CNF the exact solver receives: upload once, verify GPU witnesses against it (kernel (c))
+    pub fn tss_cnf_upload(
+        e: *mut tss_engine, lits: *const i32, offsets: *const u32, n_clauses: i32, n_vars: i32, out: *mut *mut tss_cnf,
+    ) -> c_int;
+    pub fn tss_cnf_destroy(c: *mut tss_cnf);
+    pub fn tss_cnf_check(
+        e: *mut tss_engine, c: *const tss_cnf, assignments: *const u8, n: i64, out_n_falsified: *mut i32,
+        out_first_falsified: *mut i32,
+    ) -> c_int;
+    pub fn tss_cnf_propagate(
+        e: *mut tss_engine, c: *const tss_cnf, assignments: *mut u8, n: i64, out_conflict: *mut i32, out_rounds: *mut i32,
+    ) -> c_int;
+
+    // a persistent portfolio instead of one-shot calls
+    pub fn tss_search_create(
+        e: *mut tss_engine, grid: *const u8, w: i32, h: i32, defs: *const tss_dims, n_defs: i32, params: *const tss_search_params,
+        out: *mut *mut tss_search,
+    ) -> c_int;
+    pub fn tss_search_destroy(s: *mut tss_search);
+    pub fn tss_search_run(s: *mut tss_search, steps: i64, target_count: i32) -> c_int;
+    pub fn tss_search_best_count(s: *mut tss_search, count: *mut i32) -> c_int;
+    pub fn tss_search_set_bound(s: *mut tss_search, count: i32) -> c_int;
+    pub fn tss_search_write_chains(s: *mut tss_search, rows: *const u32) -> c_int;
+    pub fn tss_search_best_layout(s: *mut tss_search, out: *mut tss_platform, cap: i32, n_out: *mut i32) -> c_int;
+
+    // multi-GPU portfolio: the host only ships the 128-byte NCCL id
+    pub fn tss_comm_unique_id(e: *mut tss_engine, out128: *mut u8) -> c_int;
+    pub fn tss_comm_init(e: *mut tss_engine, id128: *const u8, rank: i32, world: i32) -> c_int;
+}
