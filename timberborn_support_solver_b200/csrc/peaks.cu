@@ -101,7 +101,7 @@ int run_peaks(tss_engine* e, double* out, int n_out) {
     if (!sink) return TSS_E_CUDA;
     const int blocks = e->prop.multiProcessorCount * 8, threads = 256;
     const double thread_iters = (double)blocks * threads * PEAK_ITERS;
-    double ms;
+    double ms = 0.0;
     int rc;
     cudaStream_t st = e->stream;
     if ((rc = timed(e, [&] { peak_lop3_kernel<<<blocks, threads, 0, st>>>(sink, 17u); }, &ms))) return rc;
