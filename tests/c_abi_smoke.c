@@ -78,6 +78,32 @@ int main(void) {
     tss_clear_interrupt(e);
     CHECK(tss_solve_upper_bound(e, grid, w, h, defs, 1, 3, 7, 0, 20000, plats, 64, &n) == TSS_SAT && n == 3);
 
+    /* the SAT-like call the bound-tightening loop makes: first layout within the bound, one fused launch once the engine
+     * holds a workspace; an infeasible bound (ex1 needs 3 supports) with a give-up point comes back UNKNOWN after exactly
+     * that many steps per chain — timed here as a plain C host sees it */
+    CHECK(tss_solve_upper_bound(e, grid, w, h, defs, 1, 3, 8, 0, 0, plats, 64, &n) == TSS_SAT && n == 3);
+    CHECK(tss_solve_upper_bound(e, grid, w, h, defs, 1, 3, 9, 0, 0, plats, 64, &n) == TSS_SAT && n == 3);
+    CHECK(tss_get_stats(e, &st) == TSS_OK && st.last_solve_steps > 0 && st.last_solve_steps <= 96);
+    CHECK(tss_solve_upper_bound(e, grid, w, h, defs, 1, 2, 9, 0, -500, plats, 64, &n) == TSS_UNKNOWN && n == 0);
+    CHECK(tss_get_stats(e, &st) == TSS_OK && st.last_solve_steps == 500);
+
+    /* a persistent portfolio with a warm start: every chain begins from the layout just found */
+    tss_search* search = NULL;
+    tss_search_params params = {11, 16, 0, -1, TSS_KERNEL_AUTO};
+    CHECK(tss_search_create(e, grid, w, h, defs, 1, &params, &search) == TSS_OK);
+    CHECK(tss_solve_upper_bound(e, grid, w, h, defs, 1, 3, 9, 0, 0, plats, 64, &n) == TSS_SAT && n == 3);
+    uint32_t rows[16 * 32];
+    memset(rows, 0, sizeof rows);
+    for (int c = 0; c < 16; c++)
+        for (int i = 0; i < n; i++) rows[c * 32 + plats[i].y] |= 1u << plats[i].x;
+    CHECK(tss_search_write_chains(search, rows) == TSS_OK);
+    CHECK(tss_search_run(search, 8, 0) == TSS_OK);
+    int32_t best = -1;
+    CHECK(tss_search_best_count(search, &best) == TSS_OK && best == 3);   /* complete at once: the warm start is recorded as the best layout */
+    rows[5] = 1u << 9;                                                     /* a support outside the 5x6 grid is rejected */
+    CHECK(tss_search_write_chains(search, rows) == TSS_E_INVALID);
+    tss_search_destroy(search);
+
     tss_cnf_destroy(cnf);
     tss_encoding_destroy(enc);
     free(lits); free(offsets); free(assignment);
