@@ -64,18 +64,24 @@ __device__ __forceinline__ uint32_t batch_mask(long long n, int bw) {
 }
 
 // Clause evaluation.  falsified bit = no literal of the clause is True.
+// Thread = one word of the batch (32 assignments), blockIdx.y strides over the clauses: the clause's literals are uniform
+// across the block (broadcast loads), the plane reads of a warp are 32 consecutive words, and there is no per-element
+// index arithmetic (the first version recovered (clause, word) from a flat 64-bit index with a division: 156 instructions
+// per clause and word, now ~30).
 __global__ void cnf_check_kernel(const int32_t* __restrict__ lits, const uint32_t* __restrict__ offsets, int n_clauses, int nbw,
                                  long long n, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ neg,
                                  int* __restrict__ n_falsified, int* __restrict__ first_falsified) {
-    long long total = (long long)n_clauses * nbw;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i / nbw), bw = (int)(i % nbw);
+    const int bw = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bw >= nbw) return;
+    const uint32_t mask = batch_mask(n, bw);
+    for (int c = blockIdx.y; c < n_clauses; c += gridDim.y) {
         uint32_t sat = 0;
-        for (uint32_t k = offsets[c]; k < offsets[c + 1]; k++) {
-            int l = lits[k];
-            sat |= l > 0 ? pos[(long long)l * nbw + bw] : neg[(long long)(-l) * nbw + bw];
+        const uint32_t k1 = offsets[c + 1];
+        for (uint32_t k = offsets[c]; k < k1; k++) {  // (loading four literals at a time to overlap the plane reads was measured: slower)
+            const int l = lits[k];
+            sat |= (l > 0 ? pos : neg)[(size_t)(l > 0 ? l : -l) * nbw + bw];
         }
-        uint32_t bad = ~sat & batch_mask(n, bw);
+        uint32_t bad = ~sat & mask;
         while (bad) {
             int b = __ffs(bad) - 1;
             bad &= bad - 1;
@@ -88,9 +94,9 @@ __global__ void cnf_check_kernel(const int32_t* __restrict__ lits, const uint32_
 // One unit-propagation round over all clauses (in place, monotone).
 __global__ void cnf_propagate_kernel(const int32_t* __restrict__ lits, const uint32_t* __restrict__ offsets, int n_clauses, int nbw,
                                      long long n, uint32_t* __restrict__ pos, uint32_t* __restrict__ neg, int* __restrict__ changed) {
-    long long total = (long long)n_clauses * nbw;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i / nbw), bw = (int)(i % nbw);
+    const int bw = blockIdx.x * blockDim.x + threadIdx.x;   // (same mapping as cnf_check_kernel)
+    if (bw >= nbw) return;
+    for (int c = blockIdx.y; c < n_clauses; c += gridDim.y) {
         const uint32_t k0 = offsets[c], k1 = offsets[c + 1];
         uint32_t sat = 0, un1 = 0, un2 = 0;
         for (uint32_t k = k0; k < k1; k++) {
@@ -122,6 +128,17 @@ __global__ void cnf_relax_kernel(const uint32_t* __restrict__ pos, const uint32_
         pos2[i] = p | u;
         neg2[i] = (q & ~p) | u;  // True wins a forced clash
     }
+}
+
+// clause kernels: x = words of the batch (block of 32..128 threads), y = clause slices filling the device
+static void clause_geometry(tss_engine* e, int n_clauses, int nbw, dim3& grid, dim3& block) {
+    const int bx = nbw >= 128 ? 128 : ((nbw + 31) / 32) * 32;
+    const int gx = (nbw + bx - 1) / bx;
+    long long gy = (long long)e->prop.multiProcessorCount * 16 * 256 / ((long long)gx * bx);
+    gy = gy < 1 ? 1 : (gy > n_clauses ? n_clauses : gy);
+    if (gy > 65535) gy = 65535;
+    grid = dim3((unsigned)gx, (unsigned)(gy < 1 ? 1 : gy), 1);
+    block = dim3((unsigned)bx, 1, 1);
 }
 
 static unsigned grid_for(tss_engine* e, long long total) {
@@ -197,7 +214,9 @@ int tss_cnf_check(tss_engine* e, const tss_cnf* c, const uint8_t* assignments, i
     TSS_CUDA(e, cudaMemsetAsync(first, 0x7f, sizeof(int) * (size_t)nbw * 32, e->stream));
     TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     if (c->n_clauses > 0) {
-        cnf_check_kernel<<<grid_for(e, (long long)c->n_clauses * nbw), 256, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos, neg, cnt, first);
+        dim3 cg, cb;
+        clause_geometry(e, c->n_clauses, nbw, cg, cb);
+        cnf_check_kernel<<<cg, cb, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos, neg, cnt, first);
         TSS_CHECK_LAUNCH(e);
         e->stats.kernel_launches++;
     }
@@ -231,7 +250,8 @@ int tss_cnf_propagate(tss_engine* e, const tss_cnf* c, uint8_t* assignments, int
     int* flag_host = (int*)e->pin(0, sizeof(int) * BATCH);
     if (!outs || !flag_host) return TSS_E_CUDA;
     int *cnt = outs, *first = outs + (size_t)nbw * 32, *changed = outs + (size_t)nbw * 64;
-    const unsigned grid = grid_for(e, (long long)c->n_clauses * nbw);
+    dim3 cg(1, 1, 1), cb(32, 1, 1);
+    if (c->n_clauses > 0) clause_geometry(e, c->n_clauses, nbw, cg, cb);
     int rounds = 0;
     TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     // every productive round assigns >= 1 variable; a round that changes nothing is the fixpoint (later rounds of the same
@@ -240,7 +260,7 @@ int tss_cnf_propagate(tss_engine* e, const tss_cnf* c, uint8_t* assignments, int
         if (e->interrupted()) break;
         TSS_CUDA(e, cudaMemsetAsync(changed, 0, sizeof(int) * BATCH, e->stream));
         for (int b = 0; b < BATCH; b++) {
-            cnf_propagate_kernel<<<grid, 256, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos, neg, changed + b);
+            cnf_propagate_kernel<<<cg, cb, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos, neg, changed + b);
             TSS_CHECK_LAUNCH(e);
         }
         e->stats.kernel_launches += BATCH;
@@ -267,7 +287,7 @@ int tss_cnf_propagate(tss_engine* e, const tss_cnf* c, uint8_t* assignments, int
         if (!pos2 || !neg2) return TSS_E_CUDA;
         cnf_relax_kernel<<<grid_for(e, (long long)(c->n_vars + 1) * nbw), 256, 0, e->stream>>>(pos, neg, pos2, neg2, (long long)(c->n_vars + 1) * nbw);
         TSS_CHECK_LAUNCH(e);
-        cnf_check_kernel<<<grid, 256, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos2, neg2, cnt, first);
+        cnf_check_kernel<<<cg, cb, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos2, neg2, cnt, first);
         TSS_CHECK_LAUNCH(e);
         e->stats.kernel_launches += 2;
     }
