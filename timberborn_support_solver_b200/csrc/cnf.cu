@@ -68,25 +68,42 @@ __device__ __forceinline__ uint32_t batch_mask(long long n, int bw) {
 // across the block (broadcast loads), the plane reads of a warp are 32 consecutive words, and there is no per-element
 // index arithmetic (the first version recovered (clause, word) from a flat 64-bit index with a division: 156 instructions
 // per clause and word, now ~30).
+constexpr int CHECK_WPT = 4;  // words of the batch per thread: four independent plane reads in flight per literal
 __global__ void cnf_check_kernel(const int32_t* __restrict__ lits, const uint32_t* __restrict__ offsets, int n_clauses, int nbw,
                                  long long n, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ neg,
                                  int* __restrict__ n_falsified, int* __restrict__ first_falsified) {
-    const int bw = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bw >= nbw) return;
-    const uint32_t mask = batch_mask(n, bw);
+    // (with one word per thread a warp had a single plane read in flight: ~54 warps x 128 B per ~600-cycle L2 round trip
+    // = 2.9 TB/s, which is what it measured; staging the CSR slice in shared memory did not help, more loads in flight do)
+    int bw[CHECK_WPT];
+    uint32_t mask[CHECK_WPT];
+#pragma unroll
+    for (int j = 0; j < CHECK_WPT; j++) {
+        bw[j] = (blockIdx.x * CHECK_WPT + j) * blockDim.x + threadIdx.x;
+        mask[j] = bw[j] < nbw ? batch_mask(n, bw[j]) : 0u;
+        bw[j] = bw[j] < nbw ? bw[j] : 0;   // (masked out: read word 0 instead of branching)
+    }
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < CHECK_WPT; j++) any |= mask[j];
+    if (!any) return;
     for (int c = blockIdx.y; c < n_clauses; c += gridDim.y) {
-        uint32_t sat = 0;
+        uint32_t sat[CHECK_WPT] = {};
         const uint32_t k1 = offsets[c + 1];
-        for (uint32_t k = offsets[c]; k < k1; k++) {  // (loading four literals at a time to overlap the plane reads was measured: slower)
+        for (uint32_t k = offsets[c]; k < k1; k++) {
             const int l = lits[k];
-            sat |= (l > 0 ? pos : neg)[(size_t)(l > 0 ? l : -l) * nbw + bw];
+            const uint32_t* row = (l > 0 ? pos : neg) + (size_t)(l > 0 ? l : -l) * nbw;
+#pragma unroll
+            for (int j = 0; j < CHECK_WPT; j++) sat[j] |= row[bw[j]];
         }
-        uint32_t bad = ~sat & mask;
-        while (bad) {
-            int b = __ffs(bad) - 1;
-            bad &= bad - 1;
-            atomicAdd(&n_falsified[bw * 32 + b], 1);
-            atomicMin(&first_falsified[bw * 32 + b], c);
+#pragma unroll
+        for (int j = 0; j < CHECK_WPT; j++) {
+            uint32_t bad = ~sat[j] & mask[j];
+            while (bad) {
+                int b = __ffs(bad) - 1;
+                bad &= bad - 1;
+                atomicAdd(&n_falsified[bw[j] * 32 + b], 1);
+                atomicMin(&first_falsified[bw[j] * 32 + b], c);
+            }
         }
     }
 }
@@ -131,9 +148,9 @@ __global__ void cnf_relax_kernel(const uint32_t* __restrict__ pos, const uint32_
 }
 
 // clause kernels: x = words of the batch (block of 32..128 threads), y = clause slices filling the device
-static void clause_geometry(tss_engine* e, int n_clauses, int nbw, dim3& grid, dim3& block) {
+static void clause_geometry(tss_engine* e, int n_clauses, int nbw, dim3& grid, dim3& block, int words_per_thread = 1) {
     const int bx = nbw >= 128 ? 128 : ((nbw + 31) / 32) * 32;
-    const int gx = (nbw + bx - 1) / bx;
+    const int gx = (nbw + bx * words_per_thread - 1) / (bx * words_per_thread);
     long long gy = (long long)e->prop.multiProcessorCount * 16 * 256 / ((long long)gx * bx);
     gy = gy < 1 ? 1 : (gy > n_clauses ? n_clauses : gy);
     if (gy > 65535) gy = 65535;
@@ -215,7 +232,7 @@ int tss_cnf_check(tss_engine* e, const tss_cnf* c, const uint8_t* assignments, i
     TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     if (c->n_clauses > 0) {
         dim3 cg, cb;
-        clause_geometry(e, c->n_clauses, nbw, cg, cb);
+        clause_geometry(e, c->n_clauses, nbw, cg, cb, CHECK_WPT);
         cnf_check_kernel<<<cg, cb, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos, neg, cnt, first);
         TSS_CHECK_LAUNCH(e);
         e->stats.kernel_launches++;
@@ -287,7 +304,9 @@ int tss_cnf_propagate(tss_engine* e, const tss_cnf* c, uint8_t* assignments, int
         if (!pos2 || !neg2) return TSS_E_CUDA;
         cnf_relax_kernel<<<grid_for(e, (long long)(c->n_vars + 1) * nbw), 256, 0, e->stream>>>(pos, neg, pos2, neg2, (long long)(c->n_vars + 1) * nbw);
         TSS_CHECK_LAUNCH(e);
-        cnf_check_kernel<<<cg, cb, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos2, neg2, cnt, first);
+        dim3 kg, kb;
+        clause_geometry(e, c->n_clauses, nbw, kg, kb, CHECK_WPT);
+        cnf_check_kernel<<<kg, kb, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos2, neg2, cnt, first);
         TSS_CHECK_LAUNCH(e);
         e->stats.kernel_launches += 2;
     }
