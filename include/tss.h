@@ -142,6 +142,14 @@ int tss_layout_to_assignment(tss_engine* e, const tss_encoding* enc, const tss_p
                              uint8_t* assignment /* [n_vars_base + 1] */);
 /* run_trivial_optimization (platform_layout.rs:151-172): drop platforms under no ceiling tile; returns new count */
 int tss_layout_trivial_optimization(const uint8_t* grid, int32_t w, int32_t h, tss_platform* plats, int32_t n);
+/* Host-side post-pass for layouts of 1x1 supports when the platform set holds larger platforms (what the engine applies to
+ * its window-decomposed search on grids larger than 32x32): supports that fit under one footprint are merged into that
+ * platform — validate() supports everything a platform's footprint covers plus three dilations, so its reach contains
+ * theirs (platform_layout.rs:116-141) — footprints stay in bounds and pairwise disjoint (encoder.rs:546-609), then
+ * platforms whose reach the others already cover are dropped.  A complete layout stays complete.  plats: n platforms in,
+ * result out (capacity cap); returns the new count, TSS_E_CAPACITY if it does not fit (cannot happen for cap >= n). */
+int tss_layout_merge_supports(const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs, tss_platform* plats, int32_t n,
+                              int32_t cap);
 /* total_weight (platform_layout.rs:174-183); weights are records (def_w, def_h, weight) */
 int64_t tss_layout_total_weight(const tss_platform* plats, int32_t n, const int32_t* weights, int32_t n_weights);
 /* Platform::overlaps (src/platform.rs:86-97) */

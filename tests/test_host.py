@@ -211,3 +211,31 @@ def test_render_world_matches_the_repl_printout_rules():
     rows = text.splitlines()
     assert rows[0].startswith("\x1b[33m▒\x1b[39m  ▒  ") and rows[3].endswith("\x1b[31m╶\x1b[39m  ")
     assert b.overlaps(a)
+
+
+def test_merge_supports_keeps_layouts_complete_and_disjoint():
+    """tss_layout_merge_supports (host side of what the engine does on grids larger than 32x32): a complete layout of 1x1
+    supports stays complete under the reference's validate(), footprints stay disjoint and in bounds, only platforms of the
+    set appear, and the platform count drops."""
+    rng = np.random.default_rng(3)
+    for (w, h, dens) in ((48, 40, 0.8), (70, 33, 0.6), (20, 20, 1.0)):
+        grid = (rng.random((h, w)) < dens).astype(np.uint8)
+        # a complete start: supports on a 4 x 4 lattice plus one under every tile that lattice leaves unsupported
+        sites = np.zeros_like(grid)
+        sites[1::4, 1::4] = grid[1::4, 1::4]
+        unc = O.validate(grid, [(int(x), int(y), 1, 1, 0) for y, x in zip(*np.nonzero(sites))]).unsupported
+        sites |= (unc != 0).astype(np.uint8)
+        plats = [T.Platform(int(x), int(y), T.PlatformDef(1, 1)) for y, x in zip(*np.nonzero(sites))]
+        assert O.validate(grid, [(p.x, p.y, 1, 1, 0) for p in plats]).is_valid
+        lay = T.PlatformLayout(plats)
+        lay.merge_supports(T.World(T.WorldGrid(grid)), T.PLATFORMS_DEFAULT)
+        out = list(lay.platforms().values())
+        v = O.validate(grid, [(p.x, p.y, p.definition.width, p.definition.height, int(p.rotated)) for p in out])
+        assert v.is_valid and len(out) < len(plats)
+        assert all(p.definition in T.PLATFORMS_DEFAULT for p in out) and any(p.definition != T.PlatformDef(1, 1) for p in out)
+    # with the 1x1-only set nothing changes; layouts that already hold larger platforms are refused
+    lay = T.PlatformLayout(plats)
+    lay.merge_supports(T.World(T.WorldGrid(grid)), T.PLATFORMS_DEFAULT[:1])
+    assert sorted(lay.platforms()) == sorted((p.x, p.y) for p in plats)
+    with pytest.raises(T.TssError):
+        T.PlatformLayout([T.Platform(0, 0, T.PlatformDef(3, 3))]).merge_supports(T.World(T.WorldGrid(grid)), T.PLATFORMS_DEFAULT)

@@ -62,6 +62,7 @@ SIGNATURES = {
     "tss_layout_from_assignment": (C.c_int, [_vp, _u8p, _i32, _P(Platform), _i32, _i32p]),
     "tss_layout_to_assignment": (C.c_int, [_vp, _vp, _P(Platform), _i32, _u8p]),
     "tss_layout_trivial_optimization": (C.c_int, [_u8p, _i32, _i32, _P(Platform), _i32]),
+    "tss_layout_merge_supports": (C.c_int, [_u8p, _i32, _i32, _P(Dims), _i32, _P(Platform), _i32, _i32]),
     "tss_layout_total_weight": (_i64, [_P(Platform), _i32, _i32p, _i32]),
     "tss_platform_overlaps": (C.c_int, [_P(Platform), _P(Platform)]),
     "tss_validate": (C.c_int, [_vp, _u8p, _i32, _i32, _P(Platform), _i32, _u8p, _u8p]),

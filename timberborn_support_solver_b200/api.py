@@ -321,6 +321,18 @@ class PlatformLayout:
             raise TssError(n)
         self._platforms = {(arr[i].x, arr[i].y): Platform._from_c(arr[i]) for i in range(n)}
 
+    def merge_supports(self, world: World, defs) -> None:
+        """A layout of 1x1 supports, re-expressed with the larger platforms of `defs` where supports fit under one footprint
+        (host-side; the engine applies it to its window-decomposed search on grids larger than 32x32)."""
+        g = world.grid()
+        plats = list(self._platforms.values())
+        arr = _plat_array(plats)
+        defs = list(defs)
+        n = _lib.load().tss_layout_merge_supports(_ptr(g.data, C.c_uint8), g.width, g.height, _defs_array(defs), len(defs), arr, len(plats), len(plats))
+        if n < 0:
+            raise TssError(n)
+        self._platforms = {(arr[i].x, arr[i].y): Platform._from_c(arr[i]) for i in range(n)}
+
     def total_weight(self, weights: dict) -> int:
         plats = list(self._platforms.values())
         wts = np.array([[d.width, d.height, v] for d, v in weights.items()], np.int32).reshape(-1, 3)

@@ -973,6 +973,28 @@ static void merge_supports(int w, int h, const std::vector<int2>& key_dims, cons
     plats.swap(merged);
 }
 
+int tss_layout_merge_supports(const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs, tss_platform* plats, int32_t n,
+                              int32_t cap) {
+    if (!grid || w <= 0 || h <= 0 || n < 0 || (n > 0 && !plats) || (n_defs > 0 && !defs)) return TSS_E_INVALID;
+    std::vector<int2> key_dims;
+    std::vector<tss_platform> key_proto;
+    build_keys(defs, n_defs, key_dims, key_proto);
+    std::vector<tss_platform> supports, others;
+    for (int i = 0; i < n; i++) {
+        const tss_platform& p = plats[i];
+        const bool one = p.def_w == 1 && p.def_h == 1;
+        if (one && (p.x < 0 || p.y < 0 || p.x >= w || p.y >= h)) return TSS_E_INVALID;
+        (one ? supports : others).push_back(p);
+    }
+    if (!others.empty()) return TSS_E_UNSUPPORTED;   // only layouts of 1x1 supports are merged
+    std::vector<uint8_t> g(grid, grid + (size_t)w * h);
+    merge_supports(w, h, key_dims, key_proto, supports);
+    prune_redundant(g, w, h, supports);
+    if ((int)supports.size() > cap) return TSS_E_CAPACITY;
+    for (size_t i = 0; i < supports.size(); i++) plats[i] = supports[i];
+    return (int)supports.size();
+}
+
 int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_t* n_out) {
     if (!s || !n_out) return TSS_E_INVALID;
     tss_engine* e = s->e;
