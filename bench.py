@@ -283,6 +283,20 @@ def run_c4(args):
     sampler.join()
     lay = s.best_layout()            # re-validated by kernel (a) inside the engine
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # e2e: the same terrain through the one-shot C-ABI call with HOST buffers on every rank (workspace creation, terrain
+    # upload, K phases, layout download + validation inside the timed region)
+    e0 = eng.stats()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res, lay_e2e = eng.solve_upper_bound(g, card_limit=None, seed=50 + rank, max_steps=K * args.phase_steps)
+    t_e2e = time.perf_counter() - t0
+    e1 = eng.stats()
+    e2e_t = torch.tensor([float(e1["candidates_scored"] - e0["candidates_scored"]), t_e2e], dtype=torch.float64, device="cuda")
+    e2e_max = e2e_t.clone()
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(e2e_max, op=dist.ReduceOp.MAX)
     tt = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(s1["candidates_scored"] - s0["candidates_scored"]), float(s1["kernel_launches"] - s0["kernel_launches"])], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -296,7 +310,10 @@ def run_c4(args):
                            "phase_steps": args.phase_steps, "chains_total": s.n_chains, "parallelism": f"portfolio x{world}: window decomposition per GPU, winner's layout shipped after every phase"},
                 "gpu_launches": int(tot[1].item()), "best_count": count, "layout_platforms": lay.platform_count(), "ceiling_tiles": int(g.data.sum()),
                 "phases_total": W + K, "clocks": sampler.summary(),
-                "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8, "note": "not measured in this mode (device-resident portfolio)"}}
+                "e2e": {"value": float(e2e_t[0].item()) / float(e2e_max[1].item()), "unit": UNIT, "h2d_bytes_per_step": int(g.data.size // max(K, 1)),
+                        "d2h_bytes_per_step": int(20 * lay_e2e.platform_count() // max(K, 1)), "count": lay_e2e.platform_count(),
+                        "note": f"tss_solve_upper_bound from a host u8 grid to a host platform list on each of the {world} rank(s): workspace creation, upload, "
+                                f"{K} phases of {args.phase_steps} steps, layout download and validation; wall clock, sum over ranks / slowest rank"}}
         print(json.dumps(line), flush=True)
     s.close()
     eng.close()
