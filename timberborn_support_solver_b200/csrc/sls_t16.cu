@@ -26,7 +26,8 @@
 //     the evaluation order, and ties go to the lowest index as the spec demands.
 // ncu (profiles/r1_sls_t16_kernel.md): 73 warp instructions per chain step, ALU pipe 75 %, issue slots 72 %, shared-memory
 // wavefronts 17.8 per chain step (a third of them bank-conflict replays of the random 8-byte reach-table reads).
-// Tried and dropped: the two high count planes in global memory for 4 CTAs per SM (slower: 277 vs 335 G candidates/s).
+// Tried and dropped: the two high count planes in global memory for 4 CTAs per SM (slower: 277 vs 335 G candidates/s);
+// skipping their shared-memory loads until some count reaches 8 (326 vs 334 G: the branches cost more than the loads).
 #include "engine.hpp"
 #include "sls_spec.hpp"
 
