@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TSS_VERSION 101
+#define TSS_VERSION 102
 
 /* status codes; solve results follow IPASIR / rustsat SolverResult (crates/repl/src/main.rs:326-339) */
 #define TSS_OK 0
@@ -71,6 +71,9 @@ typedef struct tss_stats {
     int32_t  best_count;          /* best platform count of the last solve (-1 if none) */
     int32_t  interrupted;         /* last solve ended by tss_interrupt */
     int64_t  last_solve_steps;    /* SLS steps per chain the last tss_solve_upper_bound call ran before it returned */
+    uint64_t sls_flips;           /* supports (platforms) added + removed by the SLS kernels: one flip = one candidate layout
+                                     evaluated incrementally (the unit of SURVEY.md §8(d)); candidates_scored counts the neighbour
+                                     layouts scored to CHOOSE those flips */
 } tss_stats;
 
 /* ------------------------------------------------------------------------------------------------ engine */

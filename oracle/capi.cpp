@@ -207,6 +207,51 @@ int tsso_cnf_count_falsified(void* c, const uint8_t* assignment, int* first) {
     return n;
 }
 
+// Unit propagation to the fixpoint, the specification kernel (c)'s tss_cnf_propagate is compared with (tss.h).  What a SAT
+// solver does with the encoder's clauses once the platform variables are decided (src/encoder.rs:500-544: T-layer
+// implications; crates/repl/src/solver_runner.rs:12-16 hands exactly these clauses to the solver).  Synchronous rounds:
+// every clause is looked at against the state at the START of the round; a clause with no true literal and exactly one
+// unassigned literal assigns it.  Two clauses may force opposite values of one variable in the same round: the variable
+// keeps both marks, counts as assigned, and reads as True ("True wins"), so the clause that wanted False is reported
+// as the conflict.  rounds = rounds executed including the last one that changed nothing.  conflict = lowest index of a
+// clause whose literals are all false at the fixpoint, or -1.  assignment: u8[n_vars+1] 0 F / 1 T / 2 unassigned, in/out.
+int tsso_cnf_propagate(void* c, uint8_t* assignment, int* conflict, int* rounds) {
+    auto& inst = ((CnfHandle*)c)->inst;
+    const int nv = inst.n_vars;
+    std::vector<uint8_t> pos((size_t)nv + 1, 0), neg((size_t)nv + 1, 0);
+    for (int v = 1; v <= nv; v++) { pos[v] = assignment[v] == 1; neg[v] = assignment[v] == 0; }
+    int r = 0;
+    for (bool changed = true; changed;) {
+        changed = false;
+        r++;
+        std::vector<uint8_t> npos = pos, nneg = neg;
+        for (auto& cl : inst.clauses) {
+            bool sat = false;
+            int n_open = 0, open_lit = 0;
+            for (int l : cl) {
+                const int v = std::abs(l);
+                if (l > 0 ? pos[v] : neg[v]) sat = true;
+                if (!pos[v] && !neg[v]) { n_open++; open_lit = l; }
+            }
+            if (sat || n_open != 1) continue;
+            const int v = std::abs(open_lit);
+            if (open_lit > 0) npos[v] = 1; else nneg[v] = 1;
+            changed = true;
+        }
+        pos.swap(npos); neg.swap(nneg);
+    }
+    for (int v = 1; v <= nv; v++) assignment[v] = pos[v] ? 1 : (neg[v] ? 0 : 2);
+    int first = -1;
+    for (size_t i = 0; i < inst.clauses.size() && first < 0; i++) {
+        bool all_false = true;
+        for (int l : inst.clauses[i]) { const uint8_t a = assignment[std::abs(l)]; if (a == 2 || (l > 0 ? a == 1 : a == 0)) { all_false = false; break; } }
+        if (all_false) first = (int)i;
+    }
+    if (conflict) *conflict = first;
+    if (rounds) *rounds = r;
+    return 0;
+}
+
 // ---- layout
 int tsso_layout_from_assignment(void* h, const uint8_t* assignment, int n, int* out_plats, int cap) {
     Assignment a(assignment, assignment + n);

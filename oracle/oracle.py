@@ -168,6 +168,15 @@ class Cnf:
         n = lib().tsso_cnf_count_falsified(self._h, _p(a, C.c_uint8), C.byref(first))
         return n, first.value
 
+    def propagate(self, assignment):
+        """Unit propagation to the fixpoint in synchronous rounds (oracle/capi.cpp tsso_cnf_propagate).
+        -> (assignment uint8[n_vars+1], conflict clause index or -1, rounds)"""
+        a = np.ascontiguousarray(assignment, dtype=np.uint8).copy()
+        assert len(a) == self.n_vars + 1
+        conflict, rounds = C.c_int(), C.c_int()
+        lib().tsso_cnf_propagate(self._h, _p(a, C.c_uint8), C.byref(conflict), C.byref(rounds))
+        return a, conflict.value, rounds.value
+
     def dimacs(self) -> str:
         lines = [f"p cnf {self.n_vars} {self.n_clauses}"]
         lines += [" ".join(map(str, c)) + " 0" for c in self.clauses()]
@@ -315,6 +324,32 @@ def sls_model(grid, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, shar
                               _p(step, C.c_uint32), _p(scored, C.c_uint64), _p(steps, C.c_uint64))
     assert rc == 0
     return dict(S=S, bestS=bestS, k=k, best=best, step=step, scored=scored, steps=steps)
+
+
+def sls_flat(grid, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, share_bound=True, init_S=None, threads=1, want_layouts=True):
+    """The same step rule as sls_model through the flat-array CPU port (oracle/sls_flat.cpp), chains spread over `threads`
+    host threads.  -> sls_model's dict plus flips (supports added + removed per chain) and seconds (wall time of the epochs)."""
+    g = _grid(grid)
+    split = []
+    for steps_, bound_, target_ in epochs:
+        while steps_ > 0:
+            split.append((min(steps_, 32768), bound_, target_))
+            steps_ -= 32768
+    ep = np.ascontiguousarray(split, dtype=np.int64).reshape(-1, 3)
+    init = None if init_S is None else np.ascontiguousarray(init_S, np.uint8).reshape(n_chains, 32, 32)
+    S = np.zeros((n_chains, 32, 32), np.uint8) if want_layouts else None
+    bestS = np.zeros((n_chains, 32, 32), np.uint8) if want_layouts else None
+    k = np.zeros(n_chains, np.int32)
+    best = np.zeros(n_chains, np.int32)
+    step = np.zeros(n_chains, np.uint32)
+    scored, steps, flips = np.zeros(n_chains, np.uint64), np.zeros(n_chains, np.uint64), np.zeros(n_chains, np.uint64)
+    sec = C.c_double()
+    rc = lib().tsso_sls_flat(_p(g, C.c_uint8), g.shape[1], g.shape[0], n_chains, C.c_uint32(chain_offset), C.c_uint64(seed), noise_pct,
+                             _p(ep, C.c_longlong), len(ep), int(share_bound), _p(init, C.c_uint8) if init is not None else None, int(threads),
+                             _p(S, C.c_uint8) if want_layouts else None, _p(bestS, C.c_uint8) if want_layouts else None, _p(k), _p(best),
+                             _p(step, C.c_uint32), _p(scored, C.c_uint64), _p(steps, C.c_uint64), _p(flips, C.c_uint64), C.byref(sec))
+    assert rc == 0
+    return dict(S=S, bestS=bestS, k=k, best=best, step=step, scored=scored, steps=steps, flips=flips, seconds=sec.value)
 
 
 def slsm_model(grid, key_dims, costs, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, share_bound=True):

@@ -6,7 +6,7 @@ import pytest
 
 import oracle.oracle as O
 import timberborn_support_solver_b200 as T
-from conftest import rows_to_grid, synth_terrain
+from conftest import golden, rows_to_grid, synth_terrain
 
 pytestmark = pytest.mark.gpu
 ONE = T.PlatformDef(1, 1)
@@ -146,27 +146,6 @@ def test_eval_full_size_properties(eng):
 
 
 # =============================================================================== kernel (c): CNF check / propagate
-def py_unit_propagate(clauses, a):
-    a = a.copy()
-    changed = True
-    while changed:
-        changed = False
-        for cl in clauses:
-            vals = [(a[abs(l)] == (1 if l > 0 else 0)) if a[abs(l)] != 2 else None for l in cl]
-            if any(v is True for v in vals):
-                continue
-            un = [l for l, v in zip(cl, vals) if v is None]
-            if len(un) == 1:
-                a[abs(un[0])] = 1 if un[0] > 0 else 0
-                changed = True
-    conflict = -1
-    for i, cl in enumerate(clauses):
-        if all(a[abs(l)] != 2 and a[abs(l)] != (1 if l > 0 else 0) for l in cl):
-            conflict = i
-            break
-    return a, conflict
-
-
 @pytest.mark.parametrize("name,defs", [("ex1", "1x1"), ("ex3", "1x1"), ("ex1", "default"), ("ex3", "default")])
 def test_cnf_check_matches_oracle(eng, fixtures, name, defs):
     d = T.PLATFORMS_DEFAULT[:1] if defs == "1x1" else T.PLATFORMS_DEFAULT
@@ -189,33 +168,105 @@ def test_cnf_check_matches_oracle(eng, fixtures, name, defs):
     assert nf[2] == 0 and first[2] == -1
 
 
-def test_cnf_propagate_matches_reference_semantics(eng, fixtures):
+def _plat_only_assignment(enc, cnf, supports):
+    """platform variables decided (the given 1x1 supports True, every other tile False), terrain-layer and cardinality
+    variables open: what unit propagation has to complete (src/encoder.rs:500-544)"""
+    a = np.full(cnf.n_vars + 1, 2, np.uint8)
+    pv = enc.vars().plat_var[:, 0]
+    a[pv] = 0
+    w = enc.vars().width
+    for x, y in supports:
+        a[pv[y * w + x]] = 1
+    return a
+
+
+def _check_propagation(eng, g, enc, cnf, ocnf, batch, layouts, bound):
+    """kernel (c) propagation == the oracle's (oracle/capi.cpp tsso_cnf_propagate): full assignment, conflict verdict and
+    the number of synchronous rounds; and SURVEY.md §7 step 1: validate(layout) and count <= bound <=> no conflict."""
+    dev = eng.upload_cnf(cnf)
+    out, conflict, rounds = dev.propagate(np.stack(batch))
+    want_rounds, n_clean = 0, 0
+    for i, a in enumerate(batch):
+        want, wc, wr = ocnf.propagate(a)
+        want_rounds = max(want_rounds, wr)
+        assert np.array_equal(out[i][1:], want[1:]), i          # the whole propagated assignment, conflict or not
+        assert (conflict[i] >= 0) == (wc >= 0), i
+        if wc >= 0:                                              # the reported clause is falsified at the fixpoint (any such clause is a valid witness)
+            cl = cnf.clauses()[int(conflict[i])]
+            assert all(out[i][abs(l)] == (0 if l > 0 else 1) for l in cl), i
+        else:
+            n_clean += 1
+        plats = [(x, y, 1, 1, 0) for x, y in layouts[i]]
+        ok = O.validate(g, plats).is_valid and len(plats) <= bound
+        assert ok == (conflict[i] < 0), i
+    assert rounds == want_rounds
+    return n_clean
+
+
+def test_cnf_propagate_matches_oracle_random(eng, fixtures):
     g = fixtures["ex1"]
+    h, w = g.shape
     enc = T.Encoding.encode(T.PLATFORMS_DEFAULT[:1], T.WorldGrid(g))
     cnf = enc.with_limits(T.PlatformLimits.new_unweighted({ONE: 3}))
-    clauses = cnf.clauses()
-    dev = eng.upload_cnf(cnf)
+    ocnf = O.Encoding(O.PLATFORMS_1X1, g).with_limits({(1, 1): 3})
+    assert cnf.clauses() == ocnf.clauses()
     rng = np.random.default_rng(2)
-    h, w = g.shape
-    batch = []
+    batch, layouts = [], []
     for i in range(40):
-        a = np.full(cnf.n_vars + 1, 2, np.uint8)
-        pv = enc.vars().plat_var[:, 0]
-        a[pv] = 0
         k = int(rng.integers(0, 5))
-        a[rng.choice(pv, k, replace=False)] = 1          # platform vars fixed, everything else open
-        batch.append(a)
-    out, conflict, rounds = dev.propagate(np.stack(batch))
-    assert rounds >= 2
-    for i, a in enumerate(batch):
-        want, wc = py_unit_propagate(clauses, a)
-        assert (conflict[i] >= 0) == (wc >= 0), i
-        if wc < 0:
-            assert np.array_equal(out[i][1:], want[1:]), i
-        # validate(layout) <=> no UP conflict with platform vars fixed (and <= 3 platforms here)
-        plats = [(int(t % w), int(t // w), 1, 1, 0) for t in range(w * h) if a[enc.vars().plat_var[t, 0]] == 1]
-        ok = O.validate(g, plats).is_valid and len(plats) <= 3
-        assert ok == (conflict[i] < 0), i
+        tiles = rng.choice(w * h, k, replace=False)
+        layouts.append([(int(t % w), int(t // w)) for t in tiles])
+        batch.append(_plat_only_assignment(enc, cnf, layouts[-1]))
+    # valid layouts too (the conflict-free side): every 3-support layout the exhaustive search finds on this 30-tile terrain
+    import itertools
+    ceil = [(x, y) for y in range(h) for x in range(w) if g[y, x]]
+    for combo in itertools.combinations(ceil, 3):
+        if len(batch) >= 40 + 24:
+            break
+        if O.validate(g, [(x, y, 1, 1, 0) for x, y in combo]).is_valid:
+            layouts.append(list(combo))
+            batch.append(_plat_only_assignment(enc, cnf, combo))
+    n_clean = _check_propagation(eng, g, enc, cnf, ocnf, batch, layouts, 3)
+    assert n_clean >= 10
+
+
+def test_cnf_propagate_on_optimum_witnesses(eng, fixtures, readme):
+    """The conflict-free side on real witnesses: the survey's three optimum layouts, the four README layouts and fresh SLS
+    witnesses, with ONLY the platform variables fixed — propagation has to derive every terrain layer and every totalizer
+    variable of the at-most-n bound; the result must equal the oracle's propagation variable for variable."""
+    terrains = {"rect16": np.ones((16, 16), np.uint8), "ex2": fixtures["ex2"], "readme": readme[0]}
+    cases = [(w["terrain"], [tuple(p) for p in w["supports"]], w["optimum"]) for w in golden("survey_witnesses")["witnesses"]]
+    cases += [("readme", [tuple(p) for p in lay["supports"]], len(lay["supports"])) for lay in readme[1]]
+    for name, opt in (("rect16", 15), ("readme", 14), ("ex2", 14)):
+        res, lay = eng.solve_upper_bound(T.WorldGrid(terrains[name]), card_limit=opt, seed=5, max_steps=200000)
+        assert res == T.SAT
+        cases.append((name, [(p.x, p.y) for p in lay.platforms().values()], opt))
+    n_clean = 0
+    for name, sup, bound in cases:
+        g = terrains[name]
+        enc = T.Encoding.encode(T.PLATFORMS_DEFAULT[:1], T.WorldGrid(g))
+        cnf = enc.with_limits(T.PlatformLimits.new_unweighted({ONE: bound}))
+        ocnf = O.Encoding(O.PLATFORMS_1X1, g).with_limits({(1, 1): bound})
+        assert cnf.clauses() == ocnf.clauses()
+        # the witness itself, the witness with one support dropped (coverage conflict), and against a bound one too small
+        batch = [_plat_only_assignment(enc, cnf, sup), _plat_only_assignment(enc, cnf, sup[1:])]
+        n_clean += _check_propagation(eng, g, enc, cnf, ocnf, batch, [sup, sup[1:]], bound)
+        # propagation alone leaves the terrain layers of covered tiles open (T_l -> OR of T_l+1 is not unit); the model the exact
+        # solver is handed takes them from the evaluator's support layers (tss_layout_to_assignment), then propagation fills
+        # in the totalizer: the recipe of api.GpuBoundSolver.solve and of the Rust shim (INTEGRATION.md)
+        lay = T.PlatformLayout(T.Platform(x, y, ONE, False) for x, y in sup)
+        full = np.full((1, cnf.n_vars + 1), 2, np.uint8)
+        base = eng.layout_to_assignment(enc, lay)
+        full[0, : len(base)] = base
+        prop, conflict, _ = eng.upload_cnf(cnf).propagate(full)
+        want, wc, _ = ocnf.propagate(full[0])
+        assert conflict[0] < 0 and wc < 0 and np.array_equal(prop[0][1:], want[1:])
+        prop[prop == 2] = 0
+        assert ocnf.count_falsified(prop[0]) == (0, -1)
+        tight = enc.with_limits(T.PlatformLimits.new_unweighted({ONE: bound - 1}))
+        otight = O.Encoding(O.PLATFORMS_1X1, g).with_limits({(1, 1): bound - 1})
+        assert _check_propagation(eng, g, enc, tight, otight, [_plat_only_assignment(enc, tight, sup)], [sup], bound - 1) == 0
+    assert n_clean == len(cases) >= 10
 
 
 # =============================================================================== kernel (b): batched SLS
@@ -240,11 +291,18 @@ def test_sls_reaches_proven_optimum(eng, fixtures, name, optimum):
 
 
 def test_sls_rect16_and_readme_terrain(eng, readme):
-    res, layout = eng.solve_upper_bound(T.WorldGrid(np.ones((16, 16))), card_limit=15, seed=1, max_steps=200000)
-    assert res == T.SAT and layout.platform_count() == 15                        # optimum 15, UNSAT <= 14
-    grid, _ = readme
-    res, layout = eng.solve_upper_bound(T.WorldGrid(grid), card_limit=14, seed=1, max_steps=200000)
-    assert res == T.SAT and layout.platform_count() == 14                        # one better than the README transcript reached
+    optima = {k: v["optimum"] for k, v in golden("proofs").items()}      # proven by tests/golden/make_proofs.py (oracle CDCL and z3)
+    for grid, key in ((np.ones((16, 16), np.uint8), "rect16/1x1"), (readme[0], "readme/1x1")):
+        opt = optima[key]
+        g = T.WorldGrid(grid)
+        res, layout = eng.solve_upper_bound(g, card_limit=opt, seed=1, max_steps=200000)
+        assert res == T.SAT and layout.platform_count() == opt                   # rect 16x16: 15; README terrain: 14, one better than its transcript reached
+        plats = [tup(p) for p in layout.platforms().values()]
+        assert O.validate(g.data, plats).is_valid                                # the reference's coverage check
+        enc = T.Encoding.encode(T.PLATFORMS_DEFAULT[:1], g)
+        a = eng.layout_to_assignment(enc, layout)
+        assert O.Encoding(O.PLATFORMS_1X1, g.data).cnf().count_falsified(a) == (0, -1)   # the reference encoder's CNF
+        assert eng.upload_cnf(enc.cnf()).check(a[None])[0][0] == 0               # same, on the GPU (kernel c)
 
 
 TRAJECTORY_CASES = [((16, 16), 1), ((21, 16), 5), ((32, 32), 9), ((6, 5), 3), ((13, 29), 2), ((32, 16), 4), ((20, 17), 6), ((26, 16), 7), ((9, 12), 8)]
@@ -274,10 +332,16 @@ def test_sls_trajectories_bit_exact_vs_model(eng, fixtures, shape, seed, kernel)
         n_chains = 150              # two CTAs, the second one partially filled
     epochs = [(50, 1 << 20, 0), (300, 1 << 20, 0), (1000, 1 << 20, 0)]
     s = eng.search(T.WorldGrid(grid), seed=seed, n_chains=n_chains, chain_offset=offset, kernel=kernel)
+    flips0 = eng.stats()["sls_flips"]
     for steps, _, target in epochs:
         s.run(steps, target)
     got = s.read_chains()
     want = O.sls_model(grid, n_chains, epochs, seed=seed, chain_offset=offset, share_bound=True)
+    # the flat-array CPU port (bench.py's CPU arm) replays the same trajectories and counts flips (supports added + removed,
+    # the unit of the bench line): the kernels' device-wide flip counter must equal its sum over the chains
+    flat = O.sls_flat(grid, n_chains, epochs, seed=seed, chain_offset=offset, share_bound=True, threads=2)
+    assert all(np.array_equal(flat[key], want[key]) for key in ("S", "bestS", "k", "best", "step", "scored", "steps"))
+    assert eng.stats()["sls_flips"] - flips0 == int(flat["flips"].sum())
     unpack = lambda rows: ((rows[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8)
     assert np.array_equal(got["k"], want["k"])
     assert np.array_equal(got["best"], want["best"])

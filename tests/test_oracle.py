@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle.oracle as O
-from conftest import golden, rows_to_grid
+from conftest import golden, rows_to_grid, synth_terrain
 
 ONE = (1, 1)
 
@@ -202,6 +202,29 @@ def test_solver_loop_ex2_1x1(fixtures):
     assert r["proved_optimal"] and len(r["best"]) == 14
 
 
+def test_committed_proofs(fixtures, readme):
+    """tests/golden/proofs.json (written by make_proofs.py: oracle CDCL and z3 QF_FD, SAT at the optimum and UNSAT one below
+    on the oracle encoder's CNF) is what bench.py and the GPU tests call "proven optimum".  The file must hold a complete
+    proof by BOTH solvers for every instance; the cheap ones are re-derived here, the long ones (rect 16x16 UNSAT@14: minutes)
+    by `python tests/golden/make_proofs.py`."""
+    proofs = golden("proofs")
+    want = {"ex1/1x1": 3, "ex1/default8": 1, "ex3/1x1": 4, "ex3/default8": 1, "ex2/1x1": 14, "ex2/default8": 4, "readme/1x1": 14,
+            "rect16/1x1": 15, "rect8/1x1": 4}                       # SURVEY.md §6
+    assert {k: v["optimum"] for k, v in proofs.items()} == want
+    terrains = dict(fixtures, readme=readme[0], rect16=np.ones((16, 16), np.uint8), rect8=np.ones((8, 8), np.uint8))
+    for key, rec in proofs.items():
+        assert rec["proved"]
+        sat, unsat = rec["solves"]
+        assert (sat["bound"], unsat["bound"]) == (rec["optimum"], rec["optimum"] - 1)
+        for solver in ("cdcl", "z3"):
+            assert sat[solver]["result"] == "sat" and unsat[solver]["result"] == "unsat", (key, solver)
+        assert rec["ceiling_tiles"] == int(terrains[rec["instance"]].sum())
+        if unsat["cdcl"]["seconds"] < 0.5:                          # re-derive the cheap ones
+            enc = O.Encoding(O.PLATFORMS_1X1 if rec["platform_set"] == "1x1" else O.PLATFORMS_DEFAULT, terrains[rec["instance"]])
+            assert enc.with_limits({ONE: rec["optimum"]}).solve()[0] == 10
+            assert enc.with_limits({ONE: rec["optimum"] - 1}).solve()[0] == 20
+
+
 def test_z3_agrees_with_cdcl(fixtures):
     """Independent exact solver (z3 QF_FD) on the same DIMACS: SAT at the optimum, UNSAT one below."""
     z3 = pytest.importorskip("z3")
@@ -315,6 +338,33 @@ def test_survey_optimum_witnesses(fixtures, readme):
         assert r == 10
 
 
+def test_unit_propagation_decides_validity_from_platform_vars(fixtures, readme):
+    """oracle/capi.cpp tsso_cnf_propagate (the yardstick for kernel (c)'s propagation): with only the platform variables
+    decided, propagation over the encoder's clauses (src/encoder.rs:500-544) ends in a conflict exactly when validate()
+    rejects the layout or the at-most-n bound is exceeded; the covered tiles' layer variables stay open (their
+    implications are not unit), so a conflict-free fixpoint is not yet a model."""
+    terrains = {"rect16": np.ones((16, 16), np.uint8), "ex2": fixtures["ex2"], "readme": readme[0]}
+    for wit in golden("survey_witnesses")["witnesses"]:
+        g = terrains[wit["terrain"]]
+        w = g.shape[1]
+        sup = [tuple(p) for p in wit["supports"]]
+        enc = O.Encoding(O.PLATFORMS_1X1, g)
+        for bound, drop, want_conflict in ((wit["optimum"], 0, False), (wit["optimum"], 1, True), (wit["optimum"] - 1, 0, True)):
+            cnf = enc.with_limits({ONE: bound})
+            a = np.full(cnf.n_vars + 1, 2, np.uint8)
+            a[enc.plat_var[:, 0]] = 0
+            for x, y in sup[drop:]:
+                a[enc.plat_var[y * w + x, 0]] = 1
+            out, conflict, rounds = cnf.propagate(a)
+            assert (conflict >= 0) == want_conflict and rounds >= 2
+            assert (out[a != 2] == a[a != 2]).all()                      # decided variables are never changed
+            if conflict >= 0:
+                cl = cnf.clauses()[conflict]
+                assert all(out[abs(l)] == (0 if l > 0 else 1) for l in cl)
+            else:
+                assert (out == 2).sum() > 1                               # open layer variables remain
+
+
 # ------------------------------------------------------------------------------------------------ SLS models (CPU side)
 def test_sls_model_layouts_validate_and_reach_known_optima(fixtures):
     """The scalar models of kernel (b) are the yardstick the GPU trajectories are compared with; here they are checked
@@ -330,6 +380,29 @@ def test_sls_model_layouts_validate_and_reach_known_optima(fixtures):
             v = O.validate(grid, [(int(x), int(y), 1, 1, 0) for x, y in zip(xs, ys)])
             assert v.is_valid and len(xs) == r["best"][c] >= optimum
             assert r["bestS"][c].sum() == len(xs)       # nothing outside the grid
+
+
+@pytest.mark.parametrize("shape,seed", [((16, 16), 1), ((21, 16), 5), ((32, 32), 9), ((6, 5), 3), ((13, 29), 2)])
+def test_sls_flat_port_replays_the_model(fixtures, shape, seed):
+    """oracle/sls_flat.cpp (the CPU arm of bench.py: incremental cover counts, flat arrays, host threads) and
+    oracle/sls_model.cpp (written for obviousness) execute the same step rule: identical trajectories, counters and layouts,
+    with and without warm starts, whatever the thread count; flips = supports added + removed."""
+    w, h = shape
+    grid = {(16, 16): np.ones((16, 16), np.uint8), (21, 16): fixtures["ex2"], (6, 5): fixtures["ex1"].T.copy()}.get(shape)
+    if grid is None:
+        grid = synth_terrain(w, h, seed=1, t=4)
+    epochs = [(50, 1 << 20, 0), (300, 1 << 20, 0), (700, 1 << 20, 0)]
+    init = np.zeros((9, 32, 32), np.uint8)
+    init[:, :h:2, :w:2] = 1
+    for init_S in (None, init):
+        a = O.sls_model(grid, 9, epochs, seed=seed, chain_offset=40, init_S=init_S)
+        for threads in (1, 4):
+            b = O.sls_flat(grid, 9, epochs, seed=seed, chain_offset=40, init_S=init_S, threads=threads)
+            for key in ("S", "bestS", "k", "best", "step", "scored", "steps"):
+                assert np.array_equal(a[key], b[key]), (key, threads)
+            k0 = 0 if init_S is None else init_S.reshape(9, -1).sum(1)
+            assert ((b["flips"].astype(np.int64) - (b["k"] - k0)) % 2 == 0).all()     # adds - removes = change of k
+            assert (b["flips"] <= 2 * b["steps"]).all() and b["flips"].sum() > 0
 
 
 def test_placement_model_layouts_validate_and_reach_repl_optima(fixtures):

@@ -27,7 +27,8 @@ class Dims(C.Structure):  # tss_dims
 class Stats(C.Structure):  # tss_stats
     _fields_ = [("layouts_evaluated", C.c_uint64), ("candidates_scored", C.c_uint64), ("sls_steps", C.c_uint64),
                 ("clauses_checked", C.c_uint64), ("kernel_launches", C.c_uint64), ("n_solves", C.c_uint64),
-                ("device_ms", C.c_double), ("best_count", C.c_int32), ("interrupted", C.c_int32), ("last_solve_steps", C.c_int64)]
+                ("device_ms", C.c_double), ("best_count", C.c_int32), ("interrupted", C.c_int32), ("last_solve_steps", C.c_int64),
+                ("sls_flips", C.c_uint64)]
 
 
 class SearchParams(C.Structure):  # tss_search_params

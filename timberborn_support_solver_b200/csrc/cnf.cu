@@ -8,8 +8,9 @@
 //                32*bw+b.  pos = assigned True, neg = assigned False, neither = DontCare/unassigned.  One clause
 //                evaluation is one LOP per literal for 32 assignments; consecutive threads take consecutive batch
 //                words of the same clause, so plane reads are coalesced 128 B lines when the batch is >= 1024.
-//   propagation  assigning a literal is ONE atomicOr on ONE plane, so concurrent readers only ever see a subset of
-//                the final (monotone) state: rounds can update in place and the fixpoint is order-independent.
+//   propagation  assigning a literal is ONE atomicOr on ONE plane (monotone, so the fixpoint is order independent);
+//                rounds are synchronous — read the planes of the previous round, OR into a copy — so the number of
+//                rounds is a property of the instance and equals the oracle's (oracle/capi.cpp tsso_cnf_propagate).
 #include "engine.hpp"
 
 struct tss_cnf {
@@ -108,9 +109,13 @@ __global__ void cnf_check_kernel(const int32_t* __restrict__ lits, const uint32_
     }
 }
 
-// One unit-propagation round over all clauses (in place, monotone).
+// One unit-propagation round over all clauses.  SYNCHRONOUS: every clause is evaluated against the planes as they stood at
+// the start of the round (pos / neg, read only) and its forced literal is OR-ed into the next state (pos_n / neg_n, which
+// the host initialises as a copy), so the outcome of a round does not depend on how the clause slices are scheduled and
+// the number of rounds to the fixpoint is a property of the instance (the oracle's tsso_cnf_propagate counts the same).
 __global__ void cnf_propagate_kernel(const int32_t* __restrict__ lits, const uint32_t* __restrict__ offsets, int n_clauses, int nbw,
-                                     long long n, uint32_t* __restrict__ pos, uint32_t* __restrict__ neg, int* __restrict__ changed) {
+                                     long long n, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ neg,
+                                     uint32_t* __restrict__ pos_n, uint32_t* __restrict__ neg_n, int* __restrict__ changed) {
     const int bw = blockIdx.x * blockDim.x + threadIdx.x;   // (same mapping as cnf_check_kernel)
     if (bw >= nbw) return;
     for (int c = blockIdx.y; c < n_clauses; c += gridDim.y) {
@@ -130,7 +135,7 @@ __global__ void cnf_propagate_kernel(const int32_t* __restrict__ lits, const uin
             int l = lits[k], v = l > 0 ? l : -l;
             uint32_t u = ~(pos[(long long)v * nbw + bw] | neg[(long long)v * nbw + bw]) & unit;
             if (u) {
-                atomicOr(l > 0 ? &pos[(long long)v * nbw + bw] : &neg[(long long)v * nbw + bw], u);
+                atomicOr(l > 0 ? &pos_n[(long long)v * nbw + bw] : &neg_n[(long long)v * nbw + bw], u);
                 unit &= ~u;
                 *changed = 1;
             }
@@ -265,7 +270,10 @@ int tss_cnf_propagate(tss_engine* e, const tss_cnf* c, uint8_t* assignments, int
     constexpr int BATCH = 8;  // rounds queued per host round trip, each with its own "changed" flag
     int* outs = (int*)e->dev(3, sizeof(int) * ((size_t)nbw * 64 + BATCH));
     int* flag_host = (int*)e->pin(0, sizeof(int) * BATCH);
-    if (!outs || !flag_host) return TSS_E_CUDA;
+    const size_t plane_bytes = sizeof(uint32_t) * (size_t)(c->n_vars + 1) * nbw;
+    uint32_t* pos_b = (uint32_t*)e->dev(4, plane_bytes);   // the other half of the double buffer (slots 4, 5; reused by the conflict check below)
+    uint32_t* neg_b = (uint32_t*)e->dev(5, plane_bytes);
+    if (!outs || !flag_host || !pos_b || !neg_b) return TSS_E_CUDA;
     int *cnt = outs, *first = outs + (size_t)nbw * 32, *changed = outs + (size_t)nbw * 64;
     dim3 cg(1, 1, 1), cb(32, 1, 1);
     if (c->n_clauses > 0) clause_geometry(e, c->n_clauses, nbw, cg, cb);
@@ -277,8 +285,13 @@ int tss_cnf_propagate(tss_engine* e, const tss_cnf* c, uint8_t* assignments, int
         if (e->interrupted()) break;
         TSS_CUDA(e, cudaMemsetAsync(changed, 0, sizeof(int) * BATCH, e->stream));
         for (int b = 0; b < BATCH; b++) {
-            cnf_propagate_kernel<<<cg, cb, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos, neg, changed + b);
+            // next state starts as a copy of the current one; the round ORs the forced literals into it; then they swap roles
+            TSS_CUDA(e, cudaMemcpyAsync(pos_b, pos, plane_bytes, cudaMemcpyDeviceToDevice, e->stream));
+            TSS_CUDA(e, cudaMemcpyAsync(neg_b, neg, plane_bytes, cudaMemcpyDeviceToDevice, e->stream));
+            cnf_propagate_kernel<<<cg, cb, 0, e->stream>>>(c->lits, c->offsets, c->n_clauses, nbw, n, pos, neg, pos_b, neg_b, changed + b);
             TSS_CHECK_LAUNCH(e);
+            std::swap(pos, pos_b);
+            std::swap(neg, neg_b);
         }
         e->stats.kernel_launches += BATCH;
         TSS_CUDA(e, cudaMemcpyAsync(flag_host, changed, sizeof(int) * BATCH, cudaMemcpyDeviceToHost, e->stream));
@@ -297,11 +310,8 @@ int tss_cnf_propagate(tss_engine* e, const tss_cnf* c, uint8_t* assignments, int
     if (c->n_clauses > 0) {
         // a clause is in conflict only if it has no unassigned literal: evaluate with "unassigned counts as True"
         // by checking against pos|~assigned is wrong for negatives, so run the check on dedicated planes:
-        // reuse cnf_check_kernel with pos' = pos | unassigned, neg' = neg | unassigned (scratch slots 4, 5)
-        size_t pbytes = sizeof(uint32_t) * (size_t)(c->n_vars + 1) * nbw;
-        uint32_t* pos2 = (uint32_t*)e->dev(4, pbytes);
-        uint32_t* neg2 = (uint32_t*)e->dev(5, pbytes);
-        if (!pos2 || !neg2) return TSS_E_CUDA;
+        // reuse cnf_check_kernel with pos' = pos | unassigned, neg' = neg | unassigned
+        uint32_t *pos2 = pos_b, *neg2 = neg_b;   // the idle half of the double buffer
         cnf_relax_kernel<<<grid_for(e, (long long)(c->n_vars + 1) * nbw), 256, 0, e->stream>>>(pos, neg, pos2, neg2, (long long)(c->n_vars + 1) * nbw);
         TSS_CHECK_LAUNCH(e);
         dim3 kg, kb;
@@ -311,7 +321,7 @@ int tss_cnf_propagate(tss_engine* e, const tss_cnf* c, uint8_t* assignments, int
         e->stats.kernel_launches += 2;
     }
     TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
-    uint8_t* a = (uint8_t*)e->scratch[0].ptr;
+    uint8_t* a = (uint8_t*)e->scratch[0].ptr;   // (pos / neg: whichever half of the double buffer holds the fixpoint)
     cnf_unpack_kernel<<<grid_for(e, (long long)(c->n_vars + 1) * nbw), 256, 0, e->stream>>>(pos, neg, n, c->n_vars, nbw, a);
     TSS_CHECK_LAUNCH(e);
     e->stats.kernel_launches++;

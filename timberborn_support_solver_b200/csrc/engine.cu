@@ -147,9 +147,9 @@ struct tss_search {
     tss::sls::ChainState* states = nullptr;
     uint32_t* site_lists = nullptr;            // [16*26][n_chains rounded to 32] support lists of the thread-per-chain kernel (allocated on first use)
     int kernel = TSS_KERNEL_AUTO;              // tss_search_params.kernel
-    unsigned long long* totals_dev = nullptr;  // [2]
+    unsigned long long* totals_dev = nullptr;  // [3]: candidates scored, steps, flips (supports added + removed)
     unsigned int* ticket_dev = nullptr;        // CTAs finished in a fused one-shot launch (sls_h16.cu OneShot), 0 between launches
-    uint32_t* oneshot_host = nullptr;          // mapped pinned [40]: result block of a fused one-shot launch
+    uint32_t* oneshot_host = nullptr;          // mapped pinned [48]: result block of a fused one-shot launch
     uint32_t* oneshot_host_dev = nullptr;      // ... its device-side address
     uint32_t* witness_dev = nullptr;           // [34] rows + check of the best layout (witness_kernel)
     uint32_t* witness_host = nullptr;          // pinned copy
@@ -157,8 +157,8 @@ struct tss_search {
     int2* best_dev = nullptr;                  // [n_groups]
     int* bounds_dev = nullptr;                 // [n_groups]
     int2* best_host = nullptr;                 // pinned [n_groups]
-    unsigned long long* totals_host = nullptr; // pinned [2]
-    unsigned long long totals_seen[2] = {0, 0};
+    unsigned long long* totals_host = nullptr; // pinned [3]
+    unsigned long long totals_seen[3] = {0, 0, 0};
     bool dirty = false;
     bool timed = false;                        // ev0 / ev1 bracket an epoch of this search
     bool share = false;                        // all-reduce-min the bound over the engine's communicator after every epoch
@@ -486,30 +486,30 @@ static int search_alloc(tss_engine* e, tss_search* s, const uint32_t* rows32_hos
     TSS_CUDA(e, cudaMalloc(&s->rows_dev, sizeof(uint32_t) * 32 * (size_t)n_terrains));
     TSS_CUDA(e, cudaMalloc(&s->tabs_dev, sizeof(uint2) * 1024 * (size_t)n_terrains));
     TSS_CUDA(e, cudaMalloc(&s->states, sizeof(sls::ChainState) * (size_t)s->n_chains));
-    TSS_CUDA(e, cudaMalloc(&s->totals_dev, sizeof(unsigned long long) * 2));
+    TSS_CUDA(e, cudaMalloc(&s->totals_dev, sizeof(unsigned long long) * 3));
     TSS_CUDA(e, cudaMalloc(&s->reduce_key_dev, sizeof(unsigned long long)));
     TSS_CUDA(e, cudaMalloc(&s->witness_dev, sizeof(uint32_t) * 34));
     TSS_CUDA(e, cudaMalloc(&s->ticket_dev, sizeof(unsigned int)));
     TSS_CUDA(e, cudaMemsetAsync(s->ticket_dev, 0, sizeof(unsigned int), e->stream));
-    TSS_CUDA(e, cudaHostAlloc((void**)&s->oneshot_host, sizeof(uint32_t) * 40, cudaHostAllocMapped));
+    TSS_CUDA(e, cudaHostAlloc((void**)&s->oneshot_host, sizeof(uint32_t) * 48, cudaHostAllocMapped));
     TSS_CUDA(e, cudaHostGetDevicePointer((void**)&s->oneshot_host_dev, s->oneshot_host, 0));
     TSS_CUDA(e, cudaHostAlloc((void**)&s->witness_host, sizeof(uint32_t) * 34, cudaHostAllocDefault));
     TSS_CUDA(e, cudaMalloc(&s->best_dev, sizeof(int2) * (size_t)s->n_groups));
     TSS_CUDA(e, cudaMalloc(&s->bounds_dev, sizeof(int) * (size_t)s->n_groups));
     TSS_CUDA(e, cudaHostAlloc((void**)&s->best_host, sizeof(int2) * (size_t)s->n_groups, cudaHostAllocDefault));
-    TSS_CUDA(e, cudaHostAlloc((void**)&s->totals_host, sizeof(unsigned long long) * 2, cudaHostAllocDefault));
+    TSS_CUDA(e, cudaHostAlloc((void**)&s->totals_host, sizeof(unsigned long long) * 3, cudaHostAllocDefault));
     if (rows32_host) TSS_CUDA(e, cudaMemcpyAsync(s->rows_dev, rows32_host, sizeof(uint32_t) * 32 * (size_t)n_terrains, cudaMemcpyHostToDevice, e->stream));
     return TSS_OK;
 }
 
 static int search_init_device(tss_engine* e, tss_search* s, int n_terrains) {
-    TSS_CUDA(e, cudaMemsetAsync(s->totals_dev, 0, sizeof(unsigned long long) * 2, e->stream));
+    TSS_CUDA(e, cudaMemsetAsync(s->totals_dev, 0, sizeof(unsigned long long) * 3, e->stream));
     TSS_CUDA(e, cudaMemsetAsync(s->reduce_key_dev, 0xff, sizeof(unsigned long long), e->stream));
     bound_min_kernel<<<(s->n_groups + 255) / 256, 256, 0, e->stream>>>(s->bounds_dev, s->n_groups, sls::NO_BOUND, true);
     TSS_CHECK_LAUNCH(e);
     e->stats.kernel_launches++;
     for (int g = 0; g < s->n_groups; g++) s->best_host[g] = make_int2(sls::NO_BOUND, -1);
-    s->totals_host[0] = s->totals_host[1] = 0;
+    s->totals_host[0] = s->totals_host[1] = s->totals_host[2] = 0;
     int rc = sls_build_reach(e, s->rows_dev, n_terrains, s->tabs_dev);
     if (rc) return rc;
     s->dirty = true;                                      // everything here is in-stream: the first reader synchronises
@@ -613,11 +613,11 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
             if (err == cudaSuccess) err = cudaMalloc(&s->keys_dev, sizeof(int2) * (size_t)slsm_max_keys());
             if (err == cudaSuccess) err = cudaMalloc(&s->costs_dev, sizeof(int) * 2 * (size_t)slsm_max_keys());   // costs | keys ordered by area
             if (err == cudaSuccess) err = cudaMalloc(&s->mstates, slsm_state_bytes() * (size_t)s->n_chains);
-            if (err == cudaSuccess) err = cudaMalloc(&s->totals_dev, sizeof(unsigned long long) * 2);
+            if (err == cudaSuccess) err = cudaMalloc(&s->totals_dev, sizeof(unsigned long long) * 3);
             if (err == cudaSuccess) err = cudaMalloc(&s->best_dev, sizeof(int2));
             if (err == cudaSuccess) err = cudaMalloc(&s->bounds_dev, sizeof(int));
             if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->best_host, sizeof(int2), cudaHostAllocDefault);
-            if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->totals_host, sizeof(unsigned long long) * 2, cudaHostAllocDefault);
+            if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->totals_host, sizeof(unsigned long long) * 3, cudaHostAllocDefault);
             if (err == cudaSuccess) err = cudaMalloc(&s->mw_codes_dev, sizeof(uint16_t) * (size_t)slsm_max_items());
             if (err == cudaSuccess) err = cudaMalloc(&s->mw_plats_dev, sizeof(int4) * (size_t)slsm_max_items());
             if (err == cudaSuccess) err = cudaMalloc(&s->mw_misc_dev, sizeof(uint32_t) * 8);
@@ -630,7 +630,7 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
             if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->oneshot_host, sizeof(uint32_t) * (16 + (size_t)slsm_max_items() / 2), cudaHostAllocMapped);
             if (err == cudaSuccess) err = cudaHostGetDevicePointer((void**)&s->oneshot_host_dev, s->oneshot_host, 0);
         }
-        s->totals_seen[0] = s->totals_seen[1] = 0;
+        s->totals_seen[0] = s->totals_seen[1] = s->totals_seen[2] = 0;
         const int nb = sls::NO_BOUND;
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->rows_dev, rows, sizeof rows, cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->keys_dev, s->key_dims.data(), sizeof(int2) * s->key_dims.size(), cudaMemcpyHostToDevice, e->stream);
@@ -640,12 +640,12 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return s->key_dims[a].x * s->key_dims[a].y > s->key_dims[b].x * s->key_dims[b].y; });
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->costs_dev + slsm_max_keys(), order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(s->bounds_dev, &nb, sizeof nb, cudaMemcpyHostToDevice, e->stream);
-        if (err == cudaSuccess) err = cudaMemsetAsync(s->totals_dev, 0, sizeof(unsigned long long) * 2, e->stream);
+        if (err == cudaSuccess) err = cudaMemsetAsync(s->totals_dev, 0, sizeof(unsigned long long) * 3, e->stream);
         int rc = err == cudaSuccess ? slsm_init(e, s->mstates, s->n_chains) : e->fail(TSS_E_CUDA, "tss_search_create: %s", cudaGetErrorString(err));
         if (rc == TSS_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = e->fail(TSS_E_CUDA, "tss_search_create: stream sync failed");
         if (rc != TSS_OK) { search_free(s); return rc; }
         s->best_host[0] = make_int2(sls::NO_BOUND, -1);
-        s->totals_host[0] = s->totals_host[1] = 0;
+        s->totals_host[0] = s->totals_host[1] = s->totals_host[2] = 0;
         *out = s;
         return TSS_OK;
     }
@@ -710,7 +710,7 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
         if (rc) return rc;
         TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
         TSS_CUDA(e, cudaMemcpyAsync(s->best_host, s->best_dev, sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
-        TSS_CUDA(e, cudaMemcpyAsync(s->totals_host, s->totals_dev, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, e->stream));
+        TSS_CUDA(e, cudaMemcpyAsync(s->totals_host, s->totals_dev, sizeof(unsigned long long) * 3, cudaMemcpyDeviceToHost, e->stream));
         s->dirty = true;
         s->timed = true;
         e->stats.n_solves++;
@@ -737,7 +737,7 @@ int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
     }
     TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
     TSS_CUDA(e, cudaMemcpyAsync(s->best_host, s->best_dev, sizeof(int2) * (size_t)s->n_groups, cudaMemcpyDeviceToHost, e->stream));
-    TSS_CUDA(e, cudaMemcpyAsync(s->totals_host, s->totals_dev, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaMemcpyAsync(s->totals_host, s->totals_dev, sizeof(unsigned long long) * 3, cudaMemcpyDeviceToHost, e->stream));
     s->dirty = true;
     s->timed = true;
     e->stats.n_solves++;
@@ -755,10 +755,13 @@ static int search_sync(tss_search* s) {
         s->timed = false;
     }
     const unsigned long long t0 = s->lns ? lns_total(s->lns, 0) : s->totals_host[0], t1 = s->lns ? lns_total(s->lns, 1) : s->totals_host[1];
+    const unsigned long long t2 = s->lns ? lns_total(s->lns, 2) : s->totals_host[2];
     e->stats.candidates_scored += t0 - s->totals_seen[0];
     e->stats.sls_steps += t1 - s->totals_seen[1];
+    e->stats.sls_flips += t2 - s->totals_seen[2];
     s->totals_seen[0] = t0;
     s->totals_seen[1] = t1;
+    s->totals_seen[2] = t2;
     s->dirty = false;
     return TSS_OK;
 }
@@ -1207,10 +1210,12 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
                 e->stats.device_ms = ms;
                 e->stats.n_solves++;
                 const unsigned long long t0 = ((unsigned long long)r[37] << 32) | r[36], t1 = ((unsigned long long)r[39] << 32) | r[38];
+                const unsigned long long t2 = ((unsigned long long)r[41] << 32) | r[40];
                 e->stats.candidates_scored += t0 - s->totals_seen[0];
                 e->stats.sls_steps += t1 - s->totals_seen[1];
-                s->totals_seen[0] = t0; s->totals_seen[1] = t1;
-                s->totals_host[0] = t0; s->totals_host[1] = t1;
+                e->stats.sls_flips += t2 - s->totals_seen[2];
+                s->totals_seen[0] = t0; s->totals_seen[1] = t1; s->totals_seen[2] = t2;
+                s->totals_host[0] = t0; s->totals_host[1] = t1; s->totals_host[2] = t2;
                 s->best_host[0] = make_int2((int)r[34], (int)r[35]);
                 s->dirty = false;
                 if ((int)r[34] < sls::NO_BOUND) {
@@ -1221,7 +1226,7 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
                 }
             }
         } else {
-            s->totals_seen[0] = s->totals_seen[1] = 0;
+            s->totals_seen[0] = s->totals_seen[1] = s->totals_seen[2] = 0;
             s->dirty = false;
             uint32_t* rows = (uint32_t*)e->pin(2, sizeof(uint32_t) * 32);
             if (!rows) rc = TSS_E_CUDA;
@@ -1271,10 +1276,12 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
                 e->stats.device_ms = ms;
                 e->stats.n_solves++;
                 const unsigned long long t0 = ((unsigned long long)r[7] << 32) | r[6], t1 = ((unsigned long long)r[9] << 32) | r[8];
+                const unsigned long long t2 = ((unsigned long long)r[11] << 32) | r[10];
                 e->stats.candidates_scored += t0 - s->totals_seen[0];
                 e->stats.sls_steps += t1 - s->totals_seen[1];
-                s->totals_seen[0] = t0; s->totals_seen[1] = t1;
-                s->totals_host[0] = t0; s->totals_host[1] = t1;
+                e->stats.sls_flips += t2 - s->totals_seen[2];
+                s->totals_seen[0] = t0; s->totals_seen[1] = t1; s->totals_seen[2] = t2;
+                s->totals_host[0] = t0; s->totals_host[1] = t1; s->totals_host[2] = t2;
                 s->best_host[0] = make_int2((int)r[0], (int)r[1]);
                 s->dirty = false;
                 if ((int)r[0] < sls::NO_BOUND) {   // hand the witness to the common tail in the layout of the in-stream witness buffers
@@ -1434,7 +1441,7 @@ int tss_solve_batch(tss_engine* e, const uint8_t* grids, int32_t w, int32_t h, i
         const int nt = (int)((n - base) < CHUNK ? (n - base) : CHUNK);
         s->w = w; s->h = h; s->seed = seed; s->chain_offset = (uint32_t)(base * CPT);
         s->n_chains = nt * CPT; s->n_groups = nt; s->chains_per_terrain = CPT;
-        s->totals_seen[0] = s->totals_seen[1] = 0;
+        s->totals_seen[0] = s->totals_seen[1] = s->totals_seen[2] = 0;
         s->dirty = false;
         uint8_t* bytes = (uint8_t*)e->dev(0, tiles * (size_t)nt);
         if (!bytes) { rc = TSS_E_CUDA; break; }

@@ -144,7 +144,7 @@ struct LnsSearch {
     int* count_dev = nullptr;
     uint32_t* key_dev = nullptr;                 // [2]: this rank's (count, rank) key and the global minimum
     int* count_host = nullptr;                   // pinned
-    unsigned long long* totals_host = nullptr;   // pinned [2]
+    unsigned long long* totals_host = nullptr;   // pinned [3]
 };
 
 void lns_destroy(LnsSearch* s) {
@@ -169,17 +169,17 @@ int lns_create(tss_engine* e, const uint8_t* grid, int w, int h, int seeds, uint
     A((void**)&s->rows_win, sizeof(uint32_t) * 32 * (size_t)s->max_windows); A((void**)&s->need_win, sizeof(uint32_t) * 32 * (size_t)s->max_windows);
     A((void**)&s->tabs, sizeof(uint2) * 1024 * (size_t)s->max_windows); A((void**)&s->states, sizeof(sls::ChainState) * nch);
     A((void**)&s->best, sizeof(int2) * (size_t)s->max_windows); A((void**)&s->bounds, sizeof(int) * (size_t)s->max_windows);
-    A((void**)&s->totals, sizeof(unsigned long long) * 2); A((void**)&s->count_dev, sizeof(int)); A((void**)&s->key_dev, sizeof(uint32_t) * 2);
+    A((void**)&s->totals, sizeof(unsigned long long) * 3); A((void**)&s->count_dev, sizeof(int)); A((void**)&s->key_dev, sizeof(uint32_t) * 2);
     if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->count_host, sizeof(int), cudaHostAllocDefault);
-    if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->totals_host, sizeof(unsigned long long) * 2, cudaHostAllocDefault);
+    if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->totals_host, sizeof(unsigned long long) * 3, cudaHostAllocDefault);
     // the start layout: a support under every ceiling tile (trivially complete)
     if (err == cudaSuccess) err = cudaMemcpyAsync(s->C, bg.rows.data(), nwb, cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(s->S, bg.rows.data(), nwb, cudaMemcpyHostToDevice, e->stream);
-    if (err == cudaSuccess) err = cudaMemsetAsync(s->totals, 0, sizeof(unsigned long long) * 2, e->stream);
+    if (err == cudaSuccess) err = cudaMemsetAsync(s->totals, 0, sizeof(unsigned long long) * 3, e->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
     if (err != cudaSuccess) { lns_destroy(s); return e->fail(TSS_E_CUDA, "lns_create: %s", cudaGetErrorString(err)); }
     s->count_host[0] = bg.count();
-    s->totals_host[0] = s->totals_host[1] = 0;
+    s->totals_host[0] = s->totals_host[1] = s->totals_host[2] = 0;
     *out = s;
     return TSS_OK;
 }
@@ -224,7 +224,7 @@ int lns_phase(tss_engine* e, LnsSearch* s, long long steps, bool share) {
         e->stats.kernel_launches += 3;
     }
     TSS_CUDA(e, cudaMemcpyAsync(s->count_host, s->count_dev, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    TSS_CUDA(e, cudaMemcpyAsync(s->totals_host, s->totals, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaMemcpyAsync(s->totals_host, s->totals, sizeof(unsigned long long) * 3, cudaMemcpyDeviceToHost, e->stream));
     s->phase++;
     return TSS_OK;
 }

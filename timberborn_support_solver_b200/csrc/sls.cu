@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_kernel(const uint32_t* __re
     int k = st.k, best = st.best, done = 0;
     uint32_t step = st.step;
     unsigned long long scored = 0;
+    uint32_t flips = 0;   // supports added + removed (the unit of SURVEY.md §8(d): one flip = one candidate layout evaluated incrementally)
 
     // rebuild the site list (row-major) and the cover-count planes from S; flip stamps start "half a period ago"
     {
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_kernel(const uint32_t* __re
             if (k == 0) { done = 1; break; }
             scored += (unsigned)k;
             remove_min_loss(L, w, k, hs, step, ten, false);
+            flips++;
             continue;
         }
         if (!__any_sync(FULL, L.U != 0)) {  // 2. complete layout with k < limit supports
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_kernel(const uint32_t* __re
         if (k == limit - 1 && k > 0) {  // 3. at capacity: swap = remove + add
             scored += (unsigned)k;
             remove_min_loss(L, w, k, hs, step, ten, true);
+            flips++;
         }
         const uint32_t rowmask = __ballot_sync(FULL, L.U != 0);
         const int y = pick_rotated(rowmask, hs & 31u);
@@ -242,6 +245,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_kernel(const uint32_t* __re
         if (lane == 0) { w.sites[k] = (uint16_t)v; w.stamps[v] = (uint16_t)step; }
         __syncwarp();
         k++;
+        flips++;
     }
 
     st.S[lane] = L.S;
@@ -253,6 +257,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_kernel(const uint32_t* __re
         st.steps_done += (uint32_t)it;
         atomicAdd(&totals[0], scored);
         atomicAdd(&totals[1], (unsigned long long)it);
+        atomicAdd(&totals[2], (unsigned long long)flips);
     }
 }
 

@@ -105,7 +105,7 @@ struct OneShot {
     unsigned long long* key;      // running (best << 32 | chain) minimum, ~0 between launches
     unsigned int* ticket;         // CTAs finished, 0 between launches
     uint32_t* result_host;        // mapped host memory: [0..31] rows of the best layout, [32] unsupported tiles, [33] supports,
-                                  // [34] best count, [35] winner chain, [36..39] totals (candidates, steps) as two u64
+                                  // [34] best count, [35] winner chain, [36..41] totals (candidates, steps, flips) as three u64
 };
 
 template <bool ONESHOT>
@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_h16_kernel(const uint32_t* 
     uint32_t step = (exists && !ONESHOT) ? st.step : 0u;
     unsigned long long scored = 0;
     long long my_steps = 0;
+    uint32_t flips = 0;   // supports added + removed
 
     {   // site list (row-major) and cover planes from S, per half
         for (int i = row; i < MAX_SITES16; i += 16) stamps[i] = stamp_reset(step);
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_h16_kernel(const uint32_t* 
                 if (row == (u >> 5)) L.S &= ~(1u << (u & 31));
                 scored += (unsigned)k;
                 k--;
+                flips++;
             }
         }
         // ---- addition at a random uncovered tile
@@ -280,6 +282,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_h16_kernel(const uint32_t* 
                 if (row == 0) { sites[k] = (uint16_t)v; stamps[v] = (uint16_t)step; }
                 if (!noise) scored += (unsigned)nc;
                 k++;
+                flips++;
             }
             __syncwarp();
         }
@@ -298,6 +301,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_h16_kernel(const uint32_t* 
             if (ONESHOT) { st.tabu_add = -1; st.tabu_rem = -1; }
             atomicAdd(&totals[0], scored);
             atomicAdd(&totals[1], (unsigned long long)my_steps);
+            atomicAdd(&totals[2], (unsigned long long)flips);
             if (ONESHOT && best < NO_BOUND) atomicMin(os.key, ((unsigned long long)(uint32_t)best << 32) | (uint32_t)chain);
         }
     }
@@ -327,6 +331,8 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_h16_kernel(const uint32_t* 
                 os.best_out[0] = make_int2(bcount, bchain);
                 if (bcount < os.bound) os.bounds_out[0] = bcount;
                 const unsigned long long t0 = *(volatile unsigned long long*)&totals[0], t1 = *(volatile unsigned long long*)&totals[1];
+                const unsigned long long t2 = *(volatile unsigned long long*)&totals[2];
+                os.result_host[40] = (uint32_t)t2; os.result_host[41] = (uint32_t)(t2 >> 32);
                 os.result_host[32] = (uint32_t)unc; os.result_host[33] = (uint32_t)cnt;
                 os.result_host[34] = (uint32_t)bcount; os.result_host[35] = (uint32_t)bchain;
                 os.result_host[36] = (uint32_t)t0; os.result_host[37] = (uint32_t)(t0 >> 32);

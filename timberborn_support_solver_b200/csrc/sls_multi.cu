@@ -188,7 +188,7 @@ struct OneShotM {
     unsigned long long* key;      // running (best << 32 | chain) minimum, ~0 between launches
     unsigned int* ticket;         // CTAs finished, 0 between launches
     uint32_t* result_host;        // mapped host memory: [0] best objective, [1] winner chain, [2] placements n, [3] unsupported tiles,
-                                  // [4] overlapping, [5] out of bounds, [6..9] totals (candidates, steps) as two u64,
+                                  // [4] overlapping, [5] out of bounds, [6..11] totals (candidates, steps, flips) as three u64,
                                   // from word 16: the n placement codes as u16
 };
 
@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
     uint32_t step = ONESHOT ? 0u : st.step;
     if (ONESHOT && lane == 0) st.best_k = 0;
     unsigned long long scored = 0;
+    uint32_t flips = 0;   // platforms added + removed
     for (int i = lane; i < k; i += 32) c.items[i] = st.items[i];
     __syncwarp();
     int Wt = 0;  // total cost of the current layout
@@ -259,6 +260,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
             scored += (unsigned)k;
             tabu_add = remove_min_loss(L, c, k, hl, -1);
             Wt -= costs[tabu_add >> 10];
+            flips++;
             continue;
         }
         if (!__any_sync(FULL, L.U != 0)) {  // complete layout with total cost < limit
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
             scored += (unsigned)k;
             tabu_add = remove_min_loss(L, c, k, hl, tabu_rem);
             Wt -= costs[tabu_add >> 10];
+            flips++;
         }
         // a random uncovered tile, then two passes of 32 random placements near it
         const uint32_t rowmask = __ballot_sync(FULL, L.U != 0);
@@ -319,6 +322,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
         k++;
         Wt += costs[best_code >> 10];
         tabu_rem = best_code;
+        flips++;
     }
 
     for (int i = lane; i < k; i += 32) st.items[i] = c.items[i];
@@ -326,6 +330,7 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
         st.k = k; st.best = best; st.step = step; st.tabu_add = tabu_add; st.tabu_rem = tabu_rem; st.done = done;
         atomicAdd(&totals[0], scored);
         atomicAdd(&totals[1], (unsigned long long)it);
+        atomicAdd(&totals[2], (unsigned long long)flips);
         if (ONESHOT && best < sls::NO_BOUND) atomicMin(os.key, ((unsigned long long)(uint32_t)best << 32) | (uint32_t)chain);
     }
     if (ONESHOT) {
@@ -371,6 +376,8 @@ __global__ void __launch_bounds__(WARPS * 32) sls_multi_kernel(const uint32_t* _
                 os.result_host[3] = (uint32_t)unc; os.result_host[4] = any_overlap ? 1u : 0u; os.result_host[5] = oob;
                 os.result_host[6] = (uint32_t)t0; os.result_host[7] = (uint32_t)(t0 >> 32);
                 os.result_host[8] = (uint32_t)t1; os.result_host[9] = (uint32_t)(t1 >> 32);
+                const unsigned long long t2 = *(volatile unsigned long long*)&totals[2];
+                os.result_host[10] = (uint32_t)t2; os.result_host[11] = (uint32_t)(t2 >> 32);
                 *os.key = ~0ull;
                 *os.ticket = 0u;
                 __threadfence_system();

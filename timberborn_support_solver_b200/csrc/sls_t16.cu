@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
     const bool run = !done;
     unsigned long long scored = 0;
     long long my_steps = 0;
+    uint32_t flips = 0;   // supports added + removed
 
     if (run) {
         const int epoch_bound = bounds[chains_per_terrain > 0 ? terrain : 0];
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
                 flip<false>(sm, tid, u, rowmask);
                 scored += (unsigned)k;
                 k--;
+                flips++;
             }
             if (!drop) {
                 // ---- addition at a random uncovered tile t: best-gain site of R(t)
@@ -303,6 +305,7 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
                 sl[(size_t)k * stride] = (uint32_t)v | (step << 16);
                 if (!noise) scored += (unsigned)(__popc(wt.x) + __popc(wt.y));
                 k++;
+                flips++;
             }
             step++; my_steps++;
         }
@@ -314,10 +317,10 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
         st.steps_done += (uint32_t)my_steps;
     }
     // one pair of atomics per warp
-    unsigned long long a = scored, b = (unsigned long long)my_steps;
+    unsigned long long a = scored, b = (unsigned long long)my_steps, c = (unsigned long long)flips;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-    if ((tid & 31) == 0 && (a | b)) { atomicAdd(&totals[0], a); atomicAdd(&totals[1], b); }
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+    if ((tid & 31) == 0 && (a | b)) { atomicAdd(&totals[0], a); atomicAdd(&totals[1], b); atomicAdd(&totals[2], c); }
 }
 
 }  // namespace slst
