@@ -4,16 +4,19 @@
 Workload (BASELINE.json configs[1]): rect 16x16 ceiling, 1x1 supports, find the minimum support count.
 One "step" = one epoch of the hot path on one GPU: the SLS kernel (b) advances every chain of the portfolio by
 `--epoch-steps` steps, the best-reduce kernel folds the chains' best counts into the device-resident bound and (N > 1)
-one NCCL all-reduce-min over NVLink shares that bound between the ranks.  value = candidate layouts evaluated per
-second over all ranks (every candidate is scored exactly: its uncovered-tile count is computed, incrementally).
+one NCCL all-reduce-min over NVLink shares that bound between the ranks.
 
-Beside it, on rank 0 at N = 1: time-to-optimal (fresh portfolio -> first layout with the proven optimum of 15),
-the full-evaluation kernel (a) streaming 4 Mi candidate layouts from HBM, the CNF kernel (c), the measured
-integer-issue / shared-memory peaks, the end-to-end number through the C ABI with host buffers, and a bounded CPU
-baseline (the oracle's `validate`, i.e. the reference's own layout check, on the host cores).
+Unit: ONE SLS FLIP — a support added or removed — is one candidate layout evaluated incrementally.
+value = flips per second over all ranks, counted by the kernels themselves (tss_stats.sls_flips).  The neighbour layouts a
+chain scores to CHOOSE each flip (all k removals, up to 25 additions) are reported beside it, never added to it.
+`--impl reference` runs the SAME step rule, the same chains and the same unit on the host cores (oracle/sls_flat.cpp, a
+flat-array CPU port that reproduces the kernels' trajectories bit for bit) and never touches the GPU: the reference itself
+(Rust + Glucose) cannot be built here, so the CPU arm is the oracle port, on all host threads.
 
-`--impl reference` times the reference's CPU path instead (oracle port: `validate` throughput on all host threads
-for the same metric, plus the CDCL bound-tightening loop's time to the same optimum) and never touches the GPU.
+Beside the line, on rank 0 at N = 1: time-to-optimal with the same starting bound on both arms, the REPL's bound-tightening
+loop end to end (GPU-seeded against CPU-only), the full-evaluation kernel (a), the CNF kernel (c), the measured
+integer-issue / shared-memory peaks, and a bounded CPU baseline.  On every N: the two other multi-GPU configs BASELINE.json
+names (C5: the 100k-terrain batch, strong scaling; C4: the 256x256 portfolio, quality at equal phases).
 """
 from __future__ import annotations
 
@@ -33,18 +36,42 @@ sys.path.insert(0, ROOT)
 METRIC = "candidate layouts evaluated/sec"
 UNIT = "layouts/s"
 WORKLOAD = "rect 16x16 ceiling, 1x1 supports, find minimum support count (BASELINE.json configs[1])"
-OPTIMUM_RECT16 = 15   # UNSAT proven at <= 14 (re-derived by oracle CDCL: tests/test_oracle.py proves ex1-3; rect16 in DESIGN.md)
-# algorithmic integer work (DESIGN.md "kernel (b)"): thread-ops, counted from the kernel's own counters
+NO_BOUND = 1 << 20
+# algorithmic integer work of one flip = one reach-window derivation (7 words x 3 rounds x 5 ops = 105 ops)
+# + |R(s)| compare/adds on the cover counters; |R| is measured on the terrain (mean_reach)
+A_FLIP_SURVEY = 105
+# the kernel's OWN accounting of what it executes per unit (DESIGN.md "kernel (b)"): thread-ops per neighbour layout scored
+# and per flip.  Reported as roofline.alu_frac_kernel_ops, i.e. how busy the ALU pipe is, NOT as the algorithmic fraction.
 A_SCORE = 7 * 4 + 2      # per candidate scored: 7 window rows x (shift, and, pack, add) + key build
 A_FLIP = 7 * 20          # per support added/removed: 7 window rows x (row mask 6 + five-plane add/sub 10 + derive 4)
-KERNEL_NAMES = {1: "sls_kernel (one chain per warp)", 2: "sls_h16_kernel (two chains per warp)", 3: "sls_t16_kernel (one chain per thread)"}
-# per-launch DRAM traffic and issue statistics of each variant from its committed ncu capture (profiles/)
+KERNEL_NAMES = {1: "sls_kernel (one chain per warp)", 2: "sls_h16_kernel (two chains per warp)", 3: "sls_t16_kernel (one chain per thread)",
+                4: "sls_p16_kernel (one chain per thread, two grid rows per word)"}
+# per-launch DRAM traffic of each variant, PASTED from its committed ncu capture (profiles/): not measured per run
 KERNEL_NCU = {
-    2: {"traffic": 3067392, "traffic_note": "dram bytes of one launch (ncu, 9472 chains x 512 steps): chain states only",
-        "ncu": "ALU pipe 72% busy, 276 warp instructions per chain step (profiles/r1_sls_h16_kernel.md)"},
-    3: {"traffic": 11065344, "traffic_note": "dram bytes of one launch (ncu, 56832 chains x 512 steps): chain states + site lists",
-        "ncu": "ALU pipe 75.5% busy, issue slots 72% busy, 73 warp instructions per chain step, 17.8 shared-memory wavefronts per chain step (profiles/r1_sls_t16_kernel.md)"},
+    2: {"traffic": 3067392, "traffic_note": "pasted from profiles/r1_sls_h16_kernel.md (ncu --set full, 9472 chains x 512 steps): chain states only"},
+    3: {"traffic": 11065344, "traffic_note": "pasted from profiles/r1_sls_t16_kernel.md (ncu --set full, 56832 chains x 512 steps): chain states + site lists"},
 }
+
+
+def proven_optimum(key):
+    """tests/golden/proofs.json: SAT at the optimum and UNSAT one below by the oracle CDCL AND z3 (make_proofs.py)."""
+    rec = json.load(open(os.path.join(ROOT, "tests", "golden", "proofs.json")))[key]
+    assert rec["proved"]
+    return int(rec["optimum"])
+
+
+OPTIMUM_RECT16 = proven_optimum("rect16/1x1")
+
+
+def workload_config(args):
+    """`config` of the JSON line: identical on both arms (the driver compares them)."""
+    return {"workload": WORKLOAD,
+            "unit_of_work": "one SLS flip (a support added or removed) = one candidate layout evaluated incrementally (SURVEY.md §8(d))",
+            "step_rule": "csrc/sls_spec.hpp (min-loss removal, max-gain addition at a random uncovered tile, 20% noise, tabu tenures 3/6/12/20, counter-based RNG); "
+                         "chains are seeded (seed 1, global chain index) and reproduce bit for bit on both arms",
+            "epoch_steps": args.epoch_steps,
+            "l2": "the GPU arm flushes L2 between timed steps (256 MiB memset outside the event pairs); a chain's working set lives in registers / shared memory "
+                  "(GPU) or L1/L2 (CPU), HBM / DRAM is touched at epoch start and end only"}
 
 
 def peaks():
@@ -100,15 +127,55 @@ def cpu_validate_rate(grid, seconds=10.0, threads=None):
 
 
 def cdcl_time_to_optimum(grid, optimum, conflict_budget=400000):
-    """Oracle CDCL bound-tightening loop (Glucose stand-in): seconds until the first layout with `optimum` platforms."""
+    """Oracle CDCL (Glucose stand-in), 1 thread like the reference (solver_runner.rs:15).
+    -> ms of ONE solve handed the bound `optimum` (the same starting bound the GPU arm gets), and ms of the REPL's
+    bound-tightening loop from its unbounded first solve until the first layout with `optimum` platforms."""
     import oracle.oracle as O
-    r = O.solver_loop(grid, O.PLATFORMS_1X1, conflict_budget=conflict_budget)
-    t = 0.0
-    for s in r["steps"]:
+    cnf = O.Encoding(O.PLATFORMS_1X1, grid).with_limits({(1, 1): optimum})
+    r, _, st = cnf.solve(conflict_budget=conflict_budget)
+    given = st["seconds"] * 1e3 if r == 10 else None
+    loop = O.solver_loop(grid, O.PLATFORMS_1X1, conflict_budget=conflict_budget)
+    t, unbounded = 0.0, None
+    for s in loop["steps"]:
         t += s["seconds"]
         if s["result"] == 10 and s["count"] <= optimum:
-            return t, True
-    return t, False
+            unbounded = t * 1e3
+            break
+    return given, unbounded
+
+
+def cpu_flips(grid, epoch_steps, warm, timed, threads=None, chains_per_thread=32):
+    """The SLS step rule on the host cores (oracle/sls_flat.cpp): chains 0.. of seed 1 — the very chains the GPU arm runs —
+    `warm` untimed epochs then `timed` epochs.  -> (flips/s over the timed epochs, per-epoch ms, threads, chains, best, sample)"""
+    import oracle.oracle as O
+    threads = threads or os.cpu_count() or 1
+    n = chains_per_thread * threads
+    r = O.sls_flat(grid, n, [(epoch_steps, NO_BOUND, 0)] * (warm + timed), seed=1, threads=threads, want_layouts=False)
+    sec = float(r["epoch_seconds"][warm:].sum())
+    flips = int(r["epoch_flips"][-1]) - (int(r["epoch_flips"][warm - 1]) if warm else 0)
+    best = int(r["best"].min())
+    sample = (f"{n} chains x {timed} epochs x {epoch_steps} steps of the same step rule and seeds on {threads} host threads "
+              f"(oracle/sls_flat.cpp, flat-array port, trajectories identical to the kernels'), {flips} flips in {sec:.2f} s after {warm} warm-up epochs; best count {best}")
+    return flips / sec, [float(x) * 1e3 for x in r["epoch_seconds"][warm:]], threads, n, best, sample
+
+
+def repl_loop_cpu(name_defs):
+    """crates/repl/src/main.rs:280-366 on the CPU alone (oracle encoder + CDCL stand-in, 1 thread): wall ms per instance."""
+    import oracle.oracle as O
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))
+    out = {}
+    for name, label in name_defs:
+        rows = fx[name]["grid"]
+        w = max(len(r) for r in rows)
+        grid = np.array([[1 if (i < len(r) and r[i] == "X") else 0 for i in range(w)] for r in rows], np.uint8)
+        t0 = time.perf_counter()
+        r = O.solver_loop(grid, O.PLATFORMS_DEFAULT if label == "default-8" else O.PLATFORMS_1X1, conflict_budget=20_000_000)
+        ms = (time.perf_counter() - t0) * 1e3
+        out[f"{name} {label}"] = {"ms": ms, "solves": len(r["steps"]), "optimum": len(r["best"]), "proved": bool(r["proved_optimal"])}
+    return out
+
+
+REPL_INSTANCES = [("ex1", "default-8"), ("ex3", "default-8"), ("ex2", "default-8"), ("ex2", "1x1")]
 
 
 def run_reference(args):
@@ -116,23 +183,24 @@ def run_reference(args):
     if rank != 0:
         return
     grid = np.ones((16, 16), np.uint8)
-    per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
-    rates = []
-    sample = ""
-    for i in range(args.warmup + args.steps):
-        rate, threads, sample = cpu_validate_rate(grid, seconds=per_step)
-        if i >= args.warmup:
-            rates.append(rate)
-    value = float(np.mean(rates))
-    t_opt, reached = cdcl_time_to_optimum(grid, OPTIMUM_RECT16)
+    W, K = max(args.warmup, 3), args.steps
+    value, epoch_ms, threads, n_chains, best, sample = cpu_flips(grid, args.epoch_steps, W, K)
+    given, unbounded = cdcl_time_to_optimum(grid, OPTIMUM_RECT16)
+    vrate, vthreads, vsample = cpu_validate_rate(grid, seconds=3.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitboards / bool",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "note": "reference = CPU path (Rust + Glucose cannot be built here: oracle port)"},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": float(np.mean(epoch_ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitboards / bool",
+        "data": "synthetic", "config": workload_config(args),
+        "run": {"chains": n_chains, "threads": threads, "note": "reference = CPU path; the reference's own code (Rust + rustsat-glucose) cannot be built here, so this arm is the oracle port"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "time_to_optimal_ms": t_opt * 1e3 if reached else None,
-        "time_to_optimal_note": "oracle CDCL bound-tightening loop (Glucose stand-in), 1 thread, time to the first layout with 15 supports; UNSAT proof not included",
+        "best_count": best,
+        "time_to_optimal_ms": given,
+        "time_to_optimal": {"given_bound_ms": given, "from_unbounded_ms": unbounded, "optimum": OPTIMUM_RECT16,
+                            "note": "oracle CDCL (Glucose stand-in), 1 solver thread as in the reference (solver_runner.rs:15): one solve handed the bound 15 / the REPL loop "
+                                    "from its unbounded first solve to the first layout with 15 supports; the UNSAT proof of 14 (minutes, tests/golden/proofs.json) is not included"},
+        "repl_loop": repl_loop_cpu(REPL_INSTANCES),
+        "validate_layouts_per_s": vrate, "validate_sample": vsample,
     }
     print(json.dumps(line), flush=True)
 
@@ -292,13 +360,13 @@ def run_c4(args):
     res, lay_e2e = eng.solve_upper_bound(g, card_limit=None, seed=50 + rank, max_steps=K * args.phase_steps)
     t_e2e = time.perf_counter() - t0
     e1 = eng.stats()
-    e2e_t = torch.tensor([float(e1["candidates_scored"] - e0["candidates_scored"]), t_e2e], dtype=torch.float64, device="cuda")
+    e2e_t = torch.tensor([float(e1["sls_flips"] - e0["sls_flips"]), t_e2e], dtype=torch.float64, device="cuda")
     e2e_max = e2e_t.clone()
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.SUM)
         dist.all_reduce(e2e_max, op=dist.ReduceOp.MAX)
     tt = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(s1["candidates_scored"] - s0["candidates_scored"]), float(s1["kernel_launches"] - s0["kernel_launches"])], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(s1["sls_flips"] - s0["sls_flips"]), float(s1["kernel_launches"] - s0["kernel_launches"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -321,6 +389,114 @@ def run_c4(args):
         dist.destroy_process_group()
 
 
+def side_c5(eng, torch, dist, world, rank, n_total, steps):
+    """BASELINE.json configs[4] at this N (strong scaling: the batch is fixed, ranks take contiguous shards, no data-path
+    collective): device time of one pass with the shard's terrains resident in HBM, and the same through tss_solve_batch from
+    host buffers.  Returns the dict rank 0 reports (None elsewhere)."""
+    import ctypes as C
+    import timberborn_support_solver_b200 as T
+    lib = T.load()
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    grids = np.zeros((hi - lo, 32, 32), np.uint8)
+    for i, t in enumerate(range(lo, hi)):
+        lib.tss_world_synthetic(32, 32, 1, t, int(0.7 * (1 << 24)), grids[i].ctypes.data_as(C.POINTER(C.c_uint8)))
+    eng.solve_batch(grids[: min(len(grids), 4096)], seed=1, steps=steps)            # workspace allocation + warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    counts = eng.solve_batch(grids, seed=1, steps=steps)
+    wall = time.perf_counter() - t0
+    dev_ms = eng.stats()["device_ms"]
+    t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    acc = torch.tensor([float(counts.sum()), float(len(counts))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return None
+    dev_ms_max, wall_ms_max = (float(x) for x in t.tolist())
+    return {"workload": f"batch of {n_total} synthetic 32x32 terrains (p=0.7), 1x1 supports, {steps} SLS steps per chain (BASELINE.json configs[4])",
+            "scaling": "strong", "terrains_per_s": n_total / (dev_ms_max * 1e-3), "ms": dev_ms_max,
+            "e2e": {"terrains_per_s": n_total / (wall_ms_max * 1e-3), "ms": wall_ms_max, "h2d_bytes": int(n_total * 1024), "d2h_bytes": int(n_total * 4),
+                    "note": "tss_solve_batch from host u8 grids to host counts, wall clock, slowest rank"},
+            "mean_count": float(acc[0].item() / acc[1].item()), "terrains": int(acc[1].item())}
+
+
+def side_c4(eng, torch, dist, world, rank, phases, phase_steps):
+    """BASELINE.json configs[3] at this N: 256x256 window-decomposed portfolio, every rank its own seeds, per-window best of all
+    ranks combined after every phase.  Quality at equal phases (= equal time: per-rank work does not depend on N)."""
+    import timberborn_support_solver_b200 as T
+    g = T.WorldGrid.synthetic(256, 256, 1, 0)
+    s = eng.search(g, seed=1, chain_offset=rank * 1000000)
+    s.run(phase_steps, 0)                  # warm-up phase (allocations, first descent from the all-supports layout)
+    s.best_count()
+    f0 = eng.stats()
+    evs = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs[0].record()
+    for _ in range(phases):
+        s.run(phase_steps, 0)
+    evs[1].record()
+    torch.cuda.synchronize()
+    count = s.global_best()
+    f1 = eng.stats()
+    lay = s.best_layout()                  # re-validated by kernel (a) inside the engine
+    assert lay.platform_count() == count
+    t = torch.tensor([evs[0].elapsed_time(evs[1])], dtype=torch.float64, device="cuda")
+    acc = torch.tensor([float(f1["sls_flips"] - f0["sls_flips"]), float(f1["candidates_scored"] - f0["candidates_scored"])], dtype=torch.float64, device="cuda")
+    cmin = torch.tensor([float(count)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        dist.all_reduce(cmin, op=dist.ReduceOp.MIN)
+    n_chains = s.n_chains
+    s.close()
+    if rank != 0:
+        return None
+    ms = float(t.item())
+    return {"workload": "synthetic 256x256 random ceiling (p=0.7), 1x1 supports, window-decomposed SLS portfolio (BASELINE.json configs[3])",
+            "scaling": "weak (own seeds per rank; per-window best of all ranks adopted after every phase)", "best_count": int(cmin.item()),
+            "ceiling_tiles": int(g.data.sum()), "trivial_lower_bound": int(-(-int(g.data.sum()) // 25)), "phases": phases + 1, "phase_steps": phase_steps,
+            "ms": ms, "flips_per_s": float(acc[0].item()) / (ms * 1e-3), "neighbour_scores_per_s": float(acc[1].item()) / (ms * 1e-3), "chains_per_gpu": n_chains}
+
+
+def oracle_exact(cnf):
+    """The exact solver of the REPL loop (rustsat-glucose in the reference; here the oracle's CDCL stand-in, as on the CPU arm)."""
+    import ctypes as C
+    import oracle.oracle as O
+    import timberborn_support_solver_b200 as T
+    a = np.full(cnf.n_vars + 1, 2, np.uint8)
+    lits, offs = np.ascontiguousarray(cnf.lits, np.int32), np.ascontiguousarray(cnf.offsets, np.uint32)
+    r = O.lib().tsso_solve_csr(O._p(lits), O._p(offs, C.c_uint32), cnf.n_clauses, cnf.n_vars, O._p(a, C.c_uint8), C.c_long(-1))
+    return {10: T.SAT, 20: T.UNSAT}.get(r, T.INTERRUPTED), a
+
+
+def repl_loop_gpu(eng, name_defs):
+    """crates/repl/src/main.rs:280-366 with the GPU engine answering the SAT iterations (and its packing lower bound ending the
+    loop when it meets the count) and the exact solver called only for what is left: wall ms per instance, host buffers."""
+    import timberborn_support_solver_b200 as T
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))
+    out = {}
+    for name, label in name_defs:
+        rows = fx[name]["grid"]
+        w = max(len(r) for r in rows)
+        grid = T.WorldGrid(np.array([[1 if (i < len(r) and r[i] == "X") else 0 for i in range(w)] for r in rows], np.uint8))
+        defs = T.PLATFORMS_DEFAULT if label == "default-8" else T.PLATFORMS_DEFAULT[:1]
+        ts, res = [], None
+        for rep in range(3):
+            t0 = time.perf_counter()
+            enc = T.Encoding.encode(defs, grid)
+            res = T.solver_loop(T.Project(T.World(grid)), enc, T.PlatformLimits(), eng, exact_solver=oracle_exact, seed=rep)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        out[f"{name} {label}"] = {"ms": float(min(ts)), "gpu_solves": sum(1 for st in res["steps"] if st["source"] == "gpu"),
+                                  "exact_solves": sum(1 for st in res["steps"] if st["source"] == "exact"), "optimum": res["best"].platform_count(),
+                                  "proved": bool(res["proved_optimal"]), "lower_bound": res.get("lower_bound")}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -328,13 +504,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--epoch-steps", type=int, default=4096, help="SLS steps per chain per bench step")
-    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = fill the device: 3 CTAs x 128 one-thread chains per SM)")
-    ap.add_argument("--kernel", type=int, default=0, help="SLS kernel variant (tss.h TSS_KERNEL_*: 0 auto, 1 warp, 2 half-warp, 3 thread)")
-    ap.add_argument("--quick", action="store_true", help="skip the side measurements (peaks, eval/cnf kernels, cpu baseline)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"], help="c2 = the bench line (rect 16x16); c4 / c5 = the other named configs, for context")
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = fill the device for the chosen kernel)")
+    ap.add_argument("--kernel", type=int, default=0, help="SLS kernel variant (tss.h TSS_KERNEL_*: 0 auto, 1 warp, 2 half-warp, 3 thread, 4 thread / row pairs)")
+    ap.add_argument("--quick", action="store_true", help="skip the side measurements (peaks, eval/cnf kernels, other configs, cpu baseline)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"], help="c2 = the bench line (rect 16x16); c4 / c5 = the other named configs on their own")
     ap.add_argument("--terrains", type=int, default=100000, help="c5: terrains in the batch")
     ap.add_argument("--batch-steps", type=int, default=2000, help="c5: SLS steps per chain")
     ap.add_argument("--phase-steps", type=int, default=4000, help="c4: SLS steps per window-decomposition phase")
+    ap.add_argument("--c4-phases", type=int, default=15, help="c4 side measurement of the default line: timed phases")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -374,11 +551,7 @@ def main():
         # the path's one real exchange: an all-reduce-min of the best-known count (4 bytes, latency bound).  The engine does
         # it itself, in-stream on the device-resident bound (ncclAllReduce inside tss_search_run); torch.distributed only
         # carries the 128-byte NCCL id from rank 0 to the other ranks.
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(eng.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, src=0)
-        eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        comm_init(eng, torch, dist, rank, world)
         exchange = "ncclAllReduce(min, 1 x int32) in-stream inside tss_search_run, bound stays in HBM"
     n_chains = args.chains
     if not n_chains:                 # engine default: fills the device for the chosen kernel
@@ -386,6 +559,7 @@ def main():
         n_chains = probe.n_chains
         probe.close()
     search = eng.search(grid, seed=1, n_chains=n_chains, chain_offset=rank * n_chains, kernel=args.kernel)
+    variant = search.kernel_variant()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def step():
@@ -421,45 +595,48 @@ def main():
     best = search.best_count()
     s1 = eng.stats()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    scored = s1["candidates_scored"] - s0["candidates_scored"]
-    sls_steps = s1["sls_steps"] - s0["sls_steps"]
-    launches = s1["kernel_launches"] - s0["kernel_launches"]
-    tot = torch.tensor([float(scored), float(sls_steps), float(launches)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(s1[k] - s0[k]) for k in ("sls_flips", "candidates_scored", "sls_steps", "kernel_launches")], dtype=torch.float64, device="cuda")
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    scored_all, steps_all, launches_all = (float(x) for x in tot.tolist())
+    flips_all, scored_all, steps_all, launches_all = (float(x) for x in tot.tolist())
     ms_total = float(tmax.item())
-    value = scored_all / (ms_total * 1e-3)
+    sec = ms_total * 1e-3
+    value = flips_all / sec
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitboards / bool", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "chains_per_gpu": n_chains, "epoch_steps": args.epoch_steps, "parallelism": f"portfolio x{world} (independent seeds, all-reduce-min of the bound per step)", "exchange": exchange,
-                   "l2": "flushed between timed steps (256 MiB memset outside the event pairs); the kernel's working set is registers + the CTA's shared memory (boards, reach table), HBM is touched at epoch start/end only"},
-        "gpu_launches": int(launches_all), "best_count": best, "sls_steps_per_s": steps_all / (ms_total * 1e-3),
-        "flips_per_s": 2.0 * steps_all / (ms_total * 1e-3), "candidates_per_step": scored_all / max(steps_all, 1.0), "mean_reach": mean_reach,
+        "config": workload_config(args),
+        "run": {"chains_per_gpu": n_chains, "kernel": KERNEL_NAMES.get(variant, str(variant)), "parallelism": f"portfolio x{world} (independent seeds, all-reduce-min of the bound per step)", "exchange": exchange},
+        "gpu_launches": int(launches_all), "best_count": best, "proven_optimum": OPTIMUM_RECT16,
+        "sls_steps_per_s": steps_all / sec, "flips_per_step": flips_all / max(steps_all, 1.0),
+        "neighbour_scores_per_s": scored_all / sec, "neighbour_scores_per_flip": scored_all / max(flips_all, 1.0), "mean_reach": mean_reach,
         "wall_ms_total": t_wall * 1e3, "clocks": sampler.summary(),
     }
 
     if rank == 0:
-        # ---------------- roofline of the dominant kernel (SLS): algorithmic integer thread-ops / event time vs measured LOP3 issue peak
+        # ---------------- roofline of the dominant kernel (SLS) against the measured LOP3 issue peak.
+        # achieved / frac: SURVEY.md §8(d)'s ALGORITHMIC work — (105 + |R|) integer ops per flip — per second.  The search
+        # rule (score every removal and every addition in reach before each flip) executes far more than that:
+        # alu_frac_kernel_ops is the kernel's own op count over the same peak, i.e. how busy the ALU pipe is.
         pk = eng.measure_peaks()
-        flips = 2.0 * steps_all                      # a swap step removes one support and adds one
-        int_ops = A_SCORE * scored_all + A_FLIP * flips
-        achieved = int_ops / (ms_total * 1e-3) / 1e9 / world
-        variant = args.kernel or (3 if n_chains >= info["sm_count"] * 48 else 2)      # engine's auto rule for a 16x16 grid (engine.cu search_kernel)
-        ncu = KERNEL_NCU.get(variant, {"traffic": None, "traffic_note": "no capture for this variant", "ncu": ""})
+        a_flip = A_FLIP_SURVEY + mean_reach
+        achieved = flips_all * a_flip / sec / 1e9 / world
+        kernel_ops = (A_SCORE * scored_all + A_FLIP * flips_all) / sec / 1e9 / world
+        ncu = KERNEL_NCU.get(variant, {"traffic": None, "traffic_note": "no ncu capture pasted for this variant"})
         line["roofline"] = {"bound": "int_issue", "achieved": achieved, "peak": pk["lop3_gops"], "unit": "Gop/s", "frac": achieved / pk["lop3_gops"],
-                            "traffic": ncu["traffic"], "traffic_note": ncu["traffic_note"], "kernel": KERNEL_NAMES[variant], "ncu": ncu["ncu"],
-                            "algorithmic_ops": f"{A_SCORE} thread-ops per candidate scored + {A_FLIP} per support added/removed (DESIGN.md kernel (b))",
+                            "traffic": ncu["traffic"], "traffic_note": ncu["traffic_note"], "kernel": KERNEL_NAMES.get(variant, str(variant)),
+                            "algorithmic_ops": f"SURVEY.md §8(d): A_flip = 105 + |R| = {a_flip:.1f} integer ops per flip (|R| = mean_reach), flips counted by the kernel",
+                            "alu_frac_kernel_ops": kernel_ops / pk["lop3_gops"],
+                            "kernel_ops": f"{A_SCORE} thread-ops per neighbour layout scored + {A_FLIP} per flip (DESIGN.md kernel (b)): what the step rule executes, = ALU pipe utilisation",
                             "peak_source": "measured in this run (tss_measure_peaks: dependent-free LOP3 chains at full occupancy)",
                             "note": "no dense contraction and ~0 HBM traffic in the step loop: the bound is integer issue (SURVEY.md §8d); per-GPU figures"}
         line["measured_peaks"] = pk
     # ---------------- e2e through the C ABI with HOST buffers (grid in, layout out) on every rank at once: a fixed step budget
     # per call; terrain upload, reach table, epochs with their host round trips, witness validation and the layout copy back
-    # are all inside the timed region.  Whole-job value = candidates of all ranks / slowest rank's wall time.
+    # are all inside the timed region.  Whole-job value = flips of all ranks / slowest rank's wall time.
     steps_per_call, n_calls = 16384, 5
     eng.solve_upper_bound(grid, card_limit=None, seed=199, max_steps=steps_per_call)      # workspace warm-up (allocation)
     if world > 1:
@@ -471,18 +648,26 @@ def main():
         res, lay = eng.solve_upper_bound(grid, card_limit=None, seed=200 + 16 * rank + i, max_steps=steps_per_call)
     t_e2e = time.perf_counter() - t0
     e1 = eng.stats()
-    e2e_t = torch.tensor([float(e1["candidates_scored"] - e0["candidates_scored"]), t_e2e], dtype=torch.float64, device="cuda")
+    e2e_t = torch.tensor([float(e1["sls_flips"] - e0["sls_flips"]), t_e2e], dtype=torch.float64, device="cuda")
     e2e_max = e2e_t.clone()
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.SUM)
         dist.all_reduce(e2e_max, op=dist.ReduceOp.MAX)
     line["e2e"] = {"value": float(e2e_t[0].item()) / float(e2e_max[1].item()), "unit": UNIT,
-                   "h2d_bytes_per_step": int(grid.data.size + 8), "d2h_bytes_per_step": int(20 * lay.platform_count() + 16 * 9 + 320),
+                   "h2d_bytes_per_step": int(grid.data.size + 8), "d2h_bytes_per_step": int(20 * lay.platform_count() + 16 * 9 + 288),
                    "note": f"tss_solve_upper_bound from a host u8 grid to a host platform list on each of the {world} rank(s), {steps_per_call} steps/chain per call, "
                            f"{n_calls} calls, wall clock incl. copies, epoch round trips and witness validation; sum over ranks / slowest rank"}
+    search.close()
+    # ---------------- the two other multi-GPU configs BASELINE.json names, on EVERY N (all ranks take part)
+    if not args.quick:
+        others = {}
+        c5 = side_c5(eng, torch, dist, world, rank, args.terrains, args.batch_steps)
+        c4 = side_c4(eng, torch, dist, world, rank, args.c4_phases, args.phase_steps)
+        if rank == 0:
+            others["c5"], others["c4"] = c5, c4
+            line["other_configs"] = others
     if rank == 0:
-        # ---------------- time-to-optimal: fresh portfolio -> first layout with 15 supports (incl. host round trips); one GPU finds
-        # it in a fraction of a millisecond, so this is per rank and identical at every N (the one-shot solve never communicates)
+        # ---------------- time-to-optimal, both starting points (per rank, identical at every N: a one-shot solve never communicates)
         tto = []
         for seed in range(7):
             torch.cuda.synchronize()
@@ -490,9 +675,22 @@ def main():
             res, lay = eng.solve_upper_bound(grid, card_limit=OPTIMUM_RECT16, seed=100 + seed)
             tto.append((time.perf_counter() - t0) * 1e3)
             assert res == T.SAT and lay.platform_count() == OPTIMUM_RECT16
+        tun = []
+        for seed in range(5):                # the REPL schedule: first solve unbounded, then bound = found - 1 (main.rs:346), until 15 is on the table
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            limit, count = None, None
+            while count is None or count > OPTIMUM_RECT16:
+                res, lay = eng.solve_upper_bound(grid, card_limit=limit, seed=300 + seed)
+                assert res == T.SAT
+                count = lay.platform_count()
+                limit = count - 1
+            tun.append((time.perf_counter() - t0) * 1e3)
         line["time_to_optimal_ms"] = float(np.median(tto[2:]))
-        line["time_to_optimal_note"] = ("tss_solve_upper_bound(card_limit=15) from host buffers on one GPU: terrain upload, reach table, epochs of 64.. "
-                                        "steps, witness re-validated by kernel (a); median of 5 calls after 2 warm-up calls")
+        line["time_to_optimal"] = {"given_bound_ms": float(np.median(tto[2:])), "from_unbounded_ms": float(np.median(tun[1:])), "optimum": OPTIMUM_RECT16,
+                                   "note": "tss_solve_upper_bound from host buffers on one GPU (terrain upload, reach table, fused first epoch, witness re-validated by kernel (a)): "
+                                           "one call handed the bound 15 (median of 5 after 2 warm-up calls) / the REPL schedule from an unbounded first call, bound = found - 1, "
+                                           "until a layout with 15 supports (median of 4 after 1 warm-up run); same two starting points as the CPU arm"}
     if rank == 0 and not args.quick and world == 1:
         hbm_peak, hbm_src = peaks()
         # ---------------- kernel (a): stream 4 Mi candidate layouts (32 B each, 128 MiB > L2) from HBM
@@ -514,10 +712,12 @@ def main():
             ts.append(a.elapsed_time(b))
         ms = float(np.mean(ts))
         gbs = n_lay * (32 + 8) / (ms * 1e-3) / 1e9
+        vrate, vthreads, vsample = cpu_validate_rate(grid.data, seconds=5.0)
         line["eval_kernel"] = {"layouts_per_s": n_lay / (ms * 1e-3), "ms": ms, "n": n_lay, "bytes_per_layout": 40,
                                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src},
-                               "int_gops": 19 * 16 * n_lay / (ms * 1e-3) / 1e9, "int_note": "A_eval = 19 ops x 16 row words per layout (SURVEY.md §8d accounting)"}
-        # ---------------- kernel (c): CNF check of 8192 witness assignments against the encoder's clauses (incl. the totalizer
+                               "int_gops": 19 * 16 * n_lay / (ms * 1e-3) / 1e9, "int_note": "A_eval = 19 ops x 16 row words per layout (SURVEY.md §8d accounting)",
+                               "cpu_validate_layouts_per_s": vrate, "cpu_validate_cores": vthreads, "cpu_validate_sample": vsample}
+        # ---------------- kernel (c): CNF check of 131072 witness assignments against the encoder's clauses (incl. the totalizer
         # of the at-most-15 bound): the SLS witness, completed by unit propagation, replicated; every 64th copy has one
         # support removed (those must come back falsified)
         enc = T.Encoding.encode(T.PLATFORMS_DEFAULT[:1], grid)
@@ -530,7 +730,7 @@ def main():
         prop, conflict, rounds = dev.propagate(full)
         prop[prop == 2] = 0
         assert conflict[0] < 0 and dev.check(prop)[0][0] == 0
-        a = np.repeat(prop, 131072, axis=0)     # 4096 words per variable and polarity: long enough a launch (0.17 ms) to time the kernel, not its launch
+        a = np.repeat(prop, 131072, axis=0)     # 4096 words per variable and polarity: long enough a launch to time the kernel, not its launch
         first_support = int(enc.vars().plat_var[[p.y * 16 + p.x for p in wit.platforms().values()][0], 0])
         a[::64, first_support] = 0
         nf, _ = dev.check(a)
@@ -545,12 +745,14 @@ def main():
                               "roofline": {"bound": "hbm", "achieved": cnf_bytes / (cnf_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                            "frac": cnf_bytes / (cnf_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                                            "plane_reads_gbs": cnf_reads / (cnf_ms * 1e-3) / 1e9, "int_gops": cnf_ops / (cnf_ms * 1e-3) / 1e9,
-                                           "note": "algorithmic bytes = both bit-sliced assignment planes once + results; the planes (84 MB) are L2 resident at this size "
-                                                   "and every literal reads one plane word, so the kernel runs on L2 bandwidth and load latency (plane_reads_gbs), with one logic op per word"},
+                                           "note": "algorithmic bytes = both bit-sliced assignment planes once + results"},
                               "literals": int(len(cnf.lits)), "assignments": len(a), "propagation_rounds": rounds,
                               "input": "SLS witness completed by unit propagation x 131072, every 64th with one support removed"}
-        # ---------------- the other named configs, for context (parity-test cases, not the bench line): wall clock through the C ABI
-        others = {}
+        # ---------------- the REPL flow end to end (BASELINE.json configs[0] and [2]): `load test/exN.toml; solve`
+        line["repl_loop"] = {"gpu_seeded": repl_loop_gpu(eng, REPL_INSTANCES), "cpu": repl_loop_cpu(REPL_INSTANCES),
+                             "note": "crates/repl/src/main.rs:280-366 end to end, wall ms: the loop with the GPU engine answering the SAT iterations and the exact solver "
+                                     "(oracle CDCL standing in for Glucose, as on the CPU side) called only for the proof, against the same loop on the CPU alone (1 solver thread)"}
+        # ---------------- single-solve latencies of the other named instances through the C ABI
         fx = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))
         ex1_rows = fx["ex1"]["grid"]   # test/ex1.toml
         ex1 = T.WorldGrid.from_toml("[world]\ngrid = [\n" + "".join(f'    "{r}",\n' for r in ex1_rows) + "]\n")
@@ -560,46 +762,29 @@ def main():
             res, lay3 = eng.solve_upper_bound(ex1, T.PLATFORMS_DEFAULT, card_limit=1, seed=1 + i)
             t1s.append((time.perf_counter() - t0) * 1e3)
             assert res == T.SAT and lay3.platform_count() == 1
-        others["C1 ex1 default-8 (REPL set)"] = {"count": lay3.platform_count(), "proven_optimum": 1, "ms": float(np.median(t1s[2:])),
-                                                 "note": "tss_solve_upper_bound(card_limit=1) from host buffers, median of 5 calls after 2 warm-up calls"}
+        line["other_configs"]["c1"] = {"workload": "test/ex1.toml with the REPL's default-8 platform set (BASELINE.json configs[0])", "count": lay3.platform_count(),
+                                       "proven_optimum": proven_optimum("ex1/default8"), "ms": float(np.median(t1s[2:])),
+                                       "note": "tss_solve_upper_bound(card_limit=1) from host buffers, median of 5 calls after 2 warm-up calls"}
         ex2 = np.array([[1 if (i < len(r) and r[i] == "X") else 0 for i in range(max(len(q) for q in fx["ex2"]["grid"]))] for r in fx["ex2"]["grid"]], np.uint8)
         ex2[8:10, 8:10] = 1          # README terrain = test/ex2.toml with (8,8),(9,8),(8,9),(9,9) set to ceiling
+        opt3 = proven_optimum("readme/1x1")
         t3s = []
         for i in range(7):
             t0 = time.perf_counter()
-            res, lay2 = eng.solve_upper_bound(T.WorldGrid(ex2), card_limit=14, seed=40 + i)
+            res, lay2 = eng.solve_upper_bound(T.WorldGrid(ex2), card_limit=opt3, seed=40 + i)
             t3s.append((time.perf_counter() - t0) * 1e3)
-            assert res == T.SAT and lay2.platform_count() == 14
-        others["C3 README 21x16 terrain, 1x1 supports"] = {"count": 14, "proven_optimum": 14, "ms": float(np.median(t3s[2:])),
-                                                         "note": "tss_solve_upper_bound(card_limit=14) from host buffers, median of 5 calls after 2 warm-up calls; the README transcript "
-                                                                 "stops at 15 (README.md:117-119); the oracle's CDCL loop (Glucose stand-in, 1 thread, build container) finds 14 after 1.2 s and proves it 10 s later"}
-        g4 = T.WorldGrid.synthetic(256, 256, 1, 0)
-        s4 = eng.search(g4, seed=1)          # default: one wave of chains over the windows
-        t0 = time.perf_counter()
-        for _ in range(24):
-            s4.run(4000, 0)
-        c4 = s4.best_count()
-        others["C4 256x256 p=0.7 (window decomposition, 24 phases x 4000 steps)"] = {"count": c4, "ceiling_tiles": int(g4.data.sum()), "ms": (time.perf_counter() - t0) * 1e3}
-        s4.close()
-        n5 = 16384
-        g5 = np.stack([T.WorldGrid.synthetic(32, 32, 1, t).data for t in range(n5)])
-        t0 = time.perf_counter()
-        c5 = eng.solve_batch(g5, seed=1, steps=2000)
-        dt5 = time.perf_counter() - t0
-        others["C5 batch of 32x32 p=0.7 terrains (16384 of the 100k, 2000 steps x 4 chains each)"] = {
-            "terrains_per_s": n5 / dt5, "mean_count": float(c5.mean()), "ms": dt5 * 1e3,
-            "note": "host Glucose stand-in needs minutes per terrain (3 sampled terrains: best 76/78/73 after 5 min each, GPU 73/73/67)"}
-        line["other_configs"] = others
-        # ---------------- CPU baseline (bounded sample, rank 0, N = 1)
-        rate, threads, sample = cpu_validate_rate(grid.data, seconds=10.0)
-        t_opt, reached = cdcl_time_to_optimum(grid.data, OPTIMUM_RECT16)      # the bound-tightening loop itself, 1 thread like the reference
+            assert res == T.SAT and lay2.platform_count() == opt3
+        line["other_configs"]["c3"] = {"workload": "README 21x16 terrain, 1x1 supports (BASELINE.json configs[2])", "count": opt3, "proven_optimum": opt3, "ms": float(np.median(t3s[2:])),
+                                       "note": "tss_solve_upper_bound(card_limit=14) from host buffers, median of 5 calls after 2 warm-up calls; the README transcript stops at 15 (README.md:117-119)"}
+        # ---------------- CPU baseline (bounded sample, rank 0, N = 1): the same step rule, chains and unit on the host cores
+        rate, epoch_ms, threads, n_cpu, cpu_best, sample = cpu_flips(grid.data, args.epoch_steps, 3, 12)
+        given, unbounded = cdcl_time_to_optimum(grid.data, OPTIMUM_RECT16)      # 1 thread like the reference
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                                "time_to_optimal_ms": t_opt * 1e3 if reached else None,
-                                "time_to_optimal_note": "oracle CDCL bound-tightening loop (Glucose stand-in, crates/repl/src/main.rs:280-366), 1 solver thread as in the reference "
-                                                        "(solver_runner.rs:15), time to the first layout with 15 supports on rect 16x16; the UNSAT proof of 14 (minutes) is not included"}
+                                "time_to_optimal": {"given_bound_ms": given, "from_unbounded_ms": unbounded,
+                                                    "note": "oracle CDCL (Glucose stand-in, crates/repl/src/main.rs:280-366), 1 solver thread as in the reference (solver_runner.rs:15); "
+                                                            "the UNSAT proof of 14 (minutes, tests/golden/proofs.json) is not included"}}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    search.close()
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -228,6 +228,9 @@ int tss_search_global_best(tss_search* s, int32_t* count);
 /* Best layout (re-validated by kernel (a) before it is returned). */
 int tss_search_best_layout(tss_search* s, tss_platform* out, int32_t cap, int32_t* n_out);
 int tss_search_n_chains(const tss_search* s);
+/* Which TSS_KERNEL_* variant advances this portfolio (what TSS_KERNEL_AUTO resolved to); 0 for the window-decomposed and the
+ * placement search, which have a single kernel each. */
+int tss_search_kernel(const tss_search* s);
 /* Introspection for the parity tests (the CPU model in oracle/sls_model.cpp replays the same trajectories): per-chain
  * state after the last epoch.  S / best_S: support rows u32[n_chains][32]; any pointer may be NULL. */
 int tss_search_read_chains(tss_search* s, uint32_t* S, uint32_t* best_S, int32_t* k, int32_t* best, uint32_t* step, uint64_t* scored);

@@ -344,12 +344,15 @@ def sls_flat(grid, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, share
     step = np.zeros(n_chains, np.uint32)
     scored, steps, flips = np.zeros(n_chains, np.uint64), np.zeros(n_chains, np.uint64), np.zeros(n_chains, np.uint64)
     sec = C.c_double()
+    ep_sec, ep_flips = np.zeros(len(ep), np.float64), np.zeros(len(ep), np.uint64)
     rc = lib().tsso_sls_flat(_p(g, C.c_uint8), g.shape[1], g.shape[0], n_chains, C.c_uint32(chain_offset), C.c_uint64(seed), noise_pct,
                              _p(ep, C.c_longlong), len(ep), int(share_bound), _p(init, C.c_uint8) if init is not None else None, int(threads),
                              _p(S, C.c_uint8) if want_layouts else None, _p(bestS, C.c_uint8) if want_layouts else None, _p(k), _p(best),
-                             _p(step, C.c_uint32), _p(scored, C.c_uint64), _p(steps, C.c_uint64), _p(flips, C.c_uint64), C.byref(sec))
+                             _p(step, C.c_uint32), _p(scored, C.c_uint64), _p(steps, C.c_uint64), _p(flips, C.c_uint64), C.byref(sec),
+                             _p(ep_sec, C.c_double), _p(ep_flips, C.c_uint64))
     assert rc == 0
-    return dict(S=S, bestS=bestS, k=k, best=best, step=step, scored=scored, steps=steps, flips=flips, seconds=sec.value)
+    return dict(S=S, bestS=bestS, k=k, best=best, step=step, scored=scored, steps=steps, flips=flips, seconds=sec.value,
+                epoch_seconds=ep_sec, epoch_flips=ep_flips)
 
 
 def slsm_model(grid, key_dims, costs, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, share_bound=True):

@@ -187,10 +187,12 @@ extern "C" {
 
 // Same contract as tsso_sls_model (oracle/sls_model.cpp) plus: chains are distributed over `threads` host threads inside
 // every epoch (they only meet at the epoch boundary, where the bound is shared), out_flips = supports added + removed per
-// chain (the unit of SURVEY.md §8(d)), *out_seconds = wall time of the epochs alone (terrain tables and chain setup excluded).
+// chain (the unit of SURVEY.md §8(d)), *out_seconds = wall time of the epochs alone (terrain tables and chain setup excluded);
+// out_epoch_seconds / out_epoch_flips (optional, [n_epochs]): wall time of every epoch and the cumulative flips after it.
 int tsso_sls_flat(const uint8_t* grid, int w, int h, int n_chains, uint32_t chain_offset, uint64_t seed, int noise_pct,
                   const long long* epochs, int n_epochs, int share_bound, const uint8_t* init_S, int threads, uint8_t* out_S, uint8_t* out_bestS,
-                  int* out_k, int* out_best, uint32_t* out_step, uint64_t* out_scored, uint64_t* out_steps, uint64_t* out_flips, double* out_seconds) {
+                  int* out_k, int* out_best, uint32_t* out_step, uint64_t* out_scored, uint64_t* out_steps, uint64_t* out_flips, double* out_seconds,
+                  double* out_epoch_seconds, uint64_t* out_epoch_flips) {
     if (w > 32 || h > 32 || n_chains <= 0) return -1;
     static Terrain T;   // (one at a time: test / bench helper)
     T.build(grid, w, h);
@@ -221,7 +223,10 @@ int tsso_sls_flat(const uint8_t* grid, int w, int h, int n_chains, uint32_t chai
         for (int t = 1; t < threads; t++) pool.emplace_back(work);
         work();
         for (auto& th : pool) th.join();
-        seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const double es = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        seconds += es;
+        if (out_epoch_seconds) out_epoch_seconds[e] = es;
+        if (out_epoch_flips) { uint64_t f = 0; for (auto& c : chains) f += c.flips; out_epoch_flips[e] = f; }   // cumulative
         for (auto& c : chains) shared = std::min(shared, c.best);
     }
     for (int i = 0; i < n_chains; i++) {

@@ -11,6 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TSS_LIB") or os.path.join(HERE, "libtss.so")   # TSS_LIB: load another BUILD of libtss (kernel experiments)
 
+TSS_VERSION = 102   # include/tss.h
 TSS_OK, TSS_UNKNOWN, TSS_SAT, TSS_UNSAT = 0, 0, 10, 20
 TSS_E_INVALID, TSS_E_CAPACITY, TSS_E_CUDA, TSS_E_UNSUPPORTED, TSS_E_PARSE = -1, -2, -3, -4, -5
 ERROR_NAMES = {-1: "TSS_E_INVALID", -2: "TSS_E_CAPACITY", -3: "TSS_E_CUDA", -4: "TSS_E_UNSUPPORTED", -5: "TSS_E_PARSE"}
@@ -84,6 +85,7 @@ SIGNATURES = {
     "tss_search_set_bound": (C.c_int, [_vp, _i32]),
     "tss_search_best_layout": (C.c_int, [_vp, _P(Platform), _i32, _i32p]),
     "tss_search_n_chains": (C.c_int, [_vp]),
+    "tss_search_kernel": (C.c_int, [_vp]),
     "tss_search_global_best": (C.c_int, [_vp, _i32p]),
     "tss_comm_unique_id": (C.c_int, [_vp, _u8p]),
     "tss_comm_init": (C.c_int, [_vp, _u8p, _i32, _i32]),
@@ -116,9 +118,21 @@ def load() -> C.CDLL:
             raise ImportError(f"{LIB_PATH} is missing: build it with `python -m timberborn_support_solver_b200.build` "
                               "(nvcc, sm_100a).  The GPU path has no CPU fallback.")
         lib = C.CDLL(LIB_PATH)
+        if not os.environ.get("TSS_LIB") and (any(not hasattr(lib, name) for name in SIGNATURES) or lib.tss_version() != TSS_VERSION):
+            # a stale artefact of an older source tree (a declared symbol is missing / other ABI version): rebuild it in-tree
+            # once and load the new file; still no fallback — if that fails the import fails
+            from . import build as _build
+            import shutil
+            import tempfile
+            _build.build(force=True)
+            tmp = os.path.join(tempfile.mkdtemp(prefix="tss_"), "libtss.so")   # (dlopen caches by path: load the fresh build under another name)
+            shutil.copy(LIB_PATH, tmp)
+            lib = C.CDLL(tmp)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
             fn.restype = res
             fn.argtypes = args
+        if lib.tss_version() != TSS_VERSION:
+            raise ImportError(f"{LIB_PATH} has ABI version {lib.tss_version()}, this package binds {TSS_VERSION}")
         _lib = lib
     return _lib

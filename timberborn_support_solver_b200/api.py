@@ -436,6 +436,10 @@ class Search:
 
     __del__ = close
 
+    def kernel_variant(self) -> int:
+        """TSS_KERNEL_* the engine runs this portfolio with (what auto resolved to)"""
+        return int(self.engine.lib.tss_search_kernel(self._h))
+
     def run(self, steps: int, target_count: int = 0):
         """One epoch: `steps` SLS steps per chain, asynchronous on the engine stream."""
         self.engine._check(self.engine.lib.tss_search_run(self._h, steps, target_count))
@@ -668,9 +672,20 @@ class GpuBoundSolver:
         return self.engine.interrupt
 
     def solve(self) -> str:  # Solve::solve
+        """SAT with a CNF-verified witness, or INTERRUPTED = "the GPU could not answer within its budget" (which is also what a
+        real interrupt returns).  The search is steered by the 1x1 card limit (= the platform count, what the REPL tightens,
+        main.rs:346) or by the weight limit (the GUI's objective, app.rs:235-245); limits on other platform types alone are
+        only enforced by the CNF check below, so such instances go to the exact solver."""
         one = PlatformDef(1, 1)
         bound = self.limits.card_limits.get(one)
-        res, layout = self.engine.solve_upper_bound(self.encoding._grid, self.encoding.defs, bound, self.seed, self.budget_ms, self.max_steps)
+        self.engine.clear_interrupt()      # the flag is sticky by design (InterruptSolver::interrupt may fire before solve starts a kernel): one solve, one flag
+        if any(d != one for d in self.limits.card_limits):
+            return INTERRUPTED             # card limits the search cannot steer by: leave the instance to the exact solver
+        if self.limits.weight_limit is not None and self.limits.weights:
+            res, layout, _ = self.engine.solve_min_weight(self.encoding._grid, self.encoding.defs, self.limits.weights, self.limits.weight_limit,
+                                                          self.seed, self.budget_ms, self.max_steps)
+        else:
+            res, layout = self.engine.solve_upper_bound(self.encoding._grid, self.encoding.defs, bound, self.seed, self.budget_ms, self.max_steps)
         if res != SAT:
             return INTERRUPTED
         a = self.engine.layout_to_assignment(self.encoding, layout)
@@ -713,6 +728,7 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
     limits = PlatformLimits(dict(limits.card_limits), dict(limits.weights), limits.weight_limit)
     steps, best, proved = [], None, False
     give_up = 1024
+    engine.clear_interrupt()
     while True:
         cnf = encoding.with_limits(limits)                      # main.rs:292-293
         if budget_ms is None:

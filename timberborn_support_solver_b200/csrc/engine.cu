@@ -688,15 +688,19 @@ static int search_kernel(const tss_search* s) {
     return h16_ok ? TSS_KERNEL_HALF_WARP : TSS_KERNEL_WARP;
 }
 
+int tss_search_kernel(const tss_search* s) { return !s ? TSS_E_INVALID : ((s->lns || s->multi) ? 0 : search_kernel(s)); }
+
 int tss_search_run(tss_search* s, int64_t steps, int32_t target_count) {
     if (!s) return TSS_E_INVALID;
     tss_engine* e = s->e;
     if (steps <= 0) return e->fail(TSS_E_INVALID, "tss_search_run: steps must be positive");
     TSS_CUDA(e, cudaSetDevice(e->device));
     TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    if (s->lns) {  // one phase of the window decomposition
-        int rc = lns_phase(e, s->lns, steps, s->share);
-        if (rc) return rc;
+    if (s->lns) {  // one phase of the window decomposition (a phase is one epoch per window: at most MAX_EPOCH_STEPS, see below)
+        for (long long left = steps; left > 0; left -= sls::MAX_EPOCH_STEPS) {
+            int rc = lns_phase(e, s->lns, left < sls::MAX_EPOCH_STEPS ? left : sls::MAX_EPOCH_STEPS, s->share);
+            if (rc) return rc;
+        }
         TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
         s->dirty = true;
         s->timed = true;
@@ -1169,7 +1173,9 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     e->stats.interrupted = 0;
     e->stats.best_count = -1;
     int rc = TSS_OK;
-    if (e->cached_search && w > 0 && h > 0 && e->cached_search->n_chains != want_chains) {  // sized for another grid class / mode
+    if (e->cached_search && only_1x1 && w > 0 && h > 0 && w <= 32 && h <= 32 && e->cached_search->n_chains != want_chains) {  // sized for another grid class / mode
+        // (calls that do not use the 1x1 workspace — other platform sets, grids beyond 32x32 — leave it alone: a REPL / GUI that
+        // alternates platform sets must not pay a free + cudaMalloc per call)
         search_free(e->cached_search);
         e->cached_search = nullptr;
     }
@@ -1177,6 +1183,7 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
     int fused_best = -1;
     if (e->cached_search && grid && w > 0 && h > 0 && w <= 32 && h <= 32 && only_1x1) {
         // reuse the engine's workspace: same buffers, fresh terrain / reach table / chain states (no allocation)
+        TSS_CUDA(e, cudaSetDevice(e->device));   // (before the workspace is detached: an early return must not leak it)
         s = e->cached_search;
         e->cached_search = nullptr;
         s->w = w; s->h = h; s->seed = seed; s->chain_offset = 0; s->noise = sls::DEFAULT_NOISE_PCT;
@@ -1188,7 +1195,6 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
         for (int y = 0; y < h; y++)
             for (int x = 0; x < w; x++)
                 if (grid[(size_t)y * w + x]) rows_now[y] |= 1u << x;
-        TSS_CUDA(e, cudaSetDevice(e->device));
         if (latency_mode && s->n_chains % 8 == 0 && !e->interrupted()) {
             // the whole first epoch in ONE launch and ONE synchronisation (sls_h16.cu OneShot): rows travel as kernel
             // parameters, the reach table is derived per CTA, chains start in registers, the last CTA publishes the winner

@@ -80,7 +80,7 @@ __global__ void extract_windows_kernel(const uint32_t* __restrict__ C, const uin
         st.S[lane] = score;
         st.bestS[lane] = score;
         if (lane == 0) {
-            st.k = k; st.best = k; st.step = phase << 20; st.tabu_add = -1; st.tabu_rem = -1; st.done = 0;
+            st.k = k; st.best = k; st.step = phase << 20; st.done = 0;
             st.scored_lo = st.scored_hi = 0; st.steps_done = 0;
         }
     }

@@ -1,7 +1,7 @@
 // Kernel (b): batched stochastic local search over support sites (see sls_spec.hpp for the algorithm).
 // One layout per warp, lane r = grid row r, cover counts as five bit-planes in registers, reach windows of all
 // sites in an 8 KB shared-memory table per CTA, counter-based RNG.  No HBM traffic inside the step loop: the chain
-// state (320 B) is read at the start of an epoch and written back at its end.
+// state (288 B) is read at the start of an epoch and written back at its end.
 //
 // Candidate scoring is lane-parallel: lane i scores ONE candidate layout (the current layout with site v_i added or
 // u_i removed) exactly, as popcount(U & R(v_i)) resp. popcount(O & R(u_i)): seven indexed warp shuffles fetch the
@@ -314,9 +314,9 @@ __global__ void init_states_kernel(ChainState* states, int n) {
     if (i >= n) return;
     ChainState s;
     for (int r = 0; r < 32; r++) { s.S[r] = 0; s.bestS[r] = 0; }
-    s.k = 0; s.best = NO_BOUND; s.step = 0; s.tabu_add = -1; s.tabu_rem = -1; s.done = 0;
+    s.k = 0; s.best = NO_BOUND; s.step = 0; s.done = 0;
     s.scored_lo = s.scored_hi = 0; s.steps_done = 0;
-    for (int r = 0; r < 7; r++) s.pad[r] = 0;
+    s.reserved = 0;
     states[i] = s;
 }
 

@@ -298,7 +298,6 @@ __global__ void __launch_bounds__(WARPS * 32, 8) sls_h16_kernel(const uint32_t* 
             unsigned long long tot = ONESHOT ? scored : ((unsigned long long)st.scored_hi << 32 | st.scored_lo) + scored;
             st.scored_lo = (uint32_t)tot; st.scored_hi = (uint32_t)(tot >> 32);
             st.steps_done = (ONESHOT ? 0u : st.steps_done) + (uint32_t)my_steps;
-            if (ONESHOT) { st.tabu_add = -1; st.tabu_rem = -1; }
             atomicAdd(&totals[0], scored);
             atomicAdd(&totals[1], (unsigned long long)my_steps);
             atomicAdd(&totals[2], (unsigned long long)flips);

@@ -75,21 +75,19 @@ TSS_HD int effective_tenure(int tenure, int k) { int c = k / 3; c = c < 2 ? 2 : 
 TSS_HD uint16_t stamp_reset(uint32_t step) { return (uint16_t)(step - 0x8000u); }
 TSS_HD bool is_tabu(uint32_t step, uint16_t stamp, int tenure) { return (uint16_t)((uint16_t)step - stamp) < (uint16_t)tenure; }
 
-// Persistent per-chain state in HBM (one 320-byte record per chain).
+// Persistent per-chain state in HBM (one 288-byte record per chain, read once at the start of an epoch and written back at its end).
 struct ChainState {
     uint32_t S[32];      // current supports, row r in S[r]
     uint32_t bestS[32];  // best complete layout found by this chain
     int32_t k;           // current number of supports
     int32_t best;        // supports in bestS, NO_BOUND if none yet
     uint32_t step;       // RNG step counter (persists across epochs)
-    int32_t tabu_add;    // unused since the tenure stamps (kept for the 320-byte layout), -1
-    int32_t tabu_rem;    // unused, -1
     int32_t done;        // reached the target or nothing left to do
     uint32_t scored_lo, scored_hi;  // candidate layouts scored by this chain (64-bit counter)
     uint32_t steps_done;
-    uint32_t pad[7];
+    uint32_t reserved;   // (keeps the record a multiple of 16 bytes)
 };
-static_assert(sizeof(ChainState) == 320, "ChainState layout");
+static_assert(sizeof(ChainState) == 288, "ChainState layout");
 
 #if defined(__CUDACC__)
 // Reach window of site v = (x, y) on a terrain given as 32 row words: validate()'s three ceiling-masked dilations

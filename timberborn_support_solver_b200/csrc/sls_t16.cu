@@ -332,11 +332,8 @@ size_t sls_t16_list_words(int n_chains) { return (size_t)16 * slst::MAXW * (((si
 int sls_run_t16(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls::ChainState* states, uint32_t* site_lists, int n_chains,
                 int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
                 int noise_pct, unsigned long long* totals_dev) {
-    static bool attr_set[64] = {false};
-    if (e->device < 64 && !attr_set[e->device]) {
-        TSS_CUDA(e, cudaFuncSetAttribute(slst::sls_t16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(slst::Smem)));
-        attr_set[e->device] = true;
-    }
+    // (idempotent and cheap; several engines / host threads may get here at once, so no "already set" cache)
+    TSS_CUDA(e, cudaFuncSetAttribute(slst::sls_t16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(slst::Smem)));
     const size_t stride = ((size_t)n_chains + 31) & ~(size_t)31;
     const int blocks = (n_chains + slst::NT - 1) / slst::NT;
     slst::sls_t16_kernel<<<blocks, slst::NT, sizeof(slst::Smem), e->stream>>>(rows_dev, tabs_dev, states, site_lists, stride, n_chains,
