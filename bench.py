@@ -400,7 +400,7 @@ def side_c5(eng, torch, dist, world, rank, n_total, steps):
     grids = np.zeros((hi - lo, 32, 32), np.uint8)
     for i, t in enumerate(range(lo, hi)):
         lib.tss_world_synthetic(32, 32, 1, t, int(0.7 * (1 << 24)), grids[i].ctypes.data_as(C.POINTER(C.c_uint8)))
-    eng.solve_batch(grids[: min(len(grids), 4096)], seed=1, steps=steps)            # workspace allocation + warm-up
+    eng.solve_batch(grids[: min(len(grids), 32768)], seed=1, steps=64)              # workspace allocation (one full chunk) + warm-up
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

@@ -271,12 +271,58 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
 int tss_solve_min_weight(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs,
                          const int32_t* weights, int32_t n_weights, int64_t weight_limit, uint64_t seed, int32_t budget_ms,
                          int64_t max_steps, tss_platform* out, int32_t cap, int32_t* n_out, int64_t* out_weight);
+/* LOWER bound on the platform count of any complete layout (not in the reference): a packing of ceiling
+ * tiles no two of which a single platform of the set can support — validate()'s rule, src/encoder/platform_layout.rs:104-141,
+ * applied to every in-bounds placement of every dims key — so every layout needs one platform per packed tile.  Randomized
+ * greedy restarts on the GPU (`restarts` <= 0: 16 per SM), the winning packing is re-verified on the device before it is
+ * returned.  out_xy[2*i], out_xy[2*i+1] = packed tile i (capacity `cap` tiles); *n_out = the bound.  When
+ * tss_solve_upper_bound reaches this count the bound-tightening loop (crates/repl/src/main.rs:280-366) is finished without
+ * the exact solver.  Grids up to 32x32; TSS_E_UNSUPPORTED beyond. */
+int tss_lower_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs, uint64_t seed,
+                    int32_t restarts, int32_t* out_xy, int32_t cap, int32_t* n_out);
 /* Terrain batch: n independent terrains [n][w*h] (grids up to 32x32), 1x1 supports; `steps` SLS steps
  * per chain, `chains_per_terrain` independent chains per terrain sharing their bound every 1024 steps (0 = one CTA
  * = 4 chains, 8 for grids of <= 16 rows; otherwise rounded up to a multiple of that).  out_counts[n] = best count per
  * terrain; out_layouts (optional) = packed support rows [n][h*wpr]. */
 int tss_solve_batch(tss_engine* e, const uint8_t* grids, int32_t w, int32_t h, int64_t n, uint64_t seed, int64_t steps,
                     int32_t chains_per_terrain, int32_t* out_counts, uint32_t* out_layouts);
+
+/* -------------------------------------------------- instance bridge: from a bare CNF back to terrain, platform set and limits */
+/* The drivers hand their solver nothing but the clauses (`run_solver(GlucoseSimp::default(), cnf)`,
+ * crates/repl/src/solver_runner.rs:8-20; `SolverBackend::start`, crates/gui/src/solver_backend.rs:69-97), while the GPU
+ * search works on the terrain.  The lib crate's side of this boundary owns `Encoding::encode` / `with_limits`
+ * (src/encoder.rs:435,619): every tss_encoding_with_limits call that returns clauses records (encoding, limits, CNF) in a
+ * small process-wide registry (the last 8 instances), and a solver finds its instance again from the clauses it was given —
+ * so the drivers need no extra call and build unchanged. */
+typedef struct tss_instance_info {
+    int32_t w, h, n_defs;            /* terrain size and platform set of the encoding */
+    int32_t card_limit_1x1;          /* n of "at most n platforms" (PlatformLimits.card_limits[1x1], main.rs:346), -1 if none */
+    int32_t n_other_card_limits;     /* card limits on other platform types (the search does not steer by those) */
+    int32_t has_weight_limit;
+    int64_t weight_limit;            /* PlatformLimits.weight_limit (crates/gui/src/app.rs:235-245) */
+    int32_t n_weights;
+    int32_t exact;                   /* 1: the whole CNF equals the recorded one; 0: only its base clauses match (limits of the latest record) */
+} tss_instance_info;
+/* Looks up the CNF a solver received in add_cnf.  TSS_SAT: found — *enc_out is a NEW handle (tss_encoding_destroy), *info the
+ * limits, weights (optional, capacity weights_cap records of (def_w, def_h, weight)) the PlatformLimits.weights map.
+ * TSS_UNKNOWN: not one of the recorded instances (solve on the exact solver alone). */
+int tss_instance_find(const int32_t* lits, const uint32_t* offsets, int32_t n_clauses, int32_t n_vars, tss_encoding** enc_out,
+                      tss_instance_info* info, int32_t* weights, int32_t weights_cap);
+/* terrain (u8[w*h]) and platform defs of an encoding */
+int tss_encoding_terrain(const tss_encoding* enc, uint8_t* grid, size_t cap, int32_t* w, int32_t* h);
+int tss_encoding_defs(const tss_encoding* enc, tss_dims* defs, int32_t cap, int32_t* n);
+int tss_cnf_num_vars(const tss_cnf* c);
+/* GPU layout -> full model of an uploaded CNF, verified: platform variables from the layout, terrain-layer variables from
+ * validate()'s support layers (tss_layout_to_assignment — unit propagation alone cannot decide those), the variables the
+ * limits added (totalizer / PB auxiliaries) by unit propagation, then every clause checked (kernel (c)).  assignment:
+ * u8[n_vars(c) + 1].  TSS_SAT: it is a model; TSS_UNKNOWN: it is not (e.g. the layout exceeds a limit). */
+int tss_witness_for_cnf(tss_engine* e, const tss_cnf* c, const tss_encoding* enc, const tss_platform* plats, int32_t n, uint8_t* assignment);
+/* Solve::solve as the GPU answers it: ONE SAT-like search within the instance's limit (platform count, or total weight when
+ * the instance carries a weight limit) that gives up after `give_up_steps` SLS steps per chain (<= 0: the engine default),
+ * then tss_witness_for_cnf.  TSS_SAT with a verified model in `assignment`, or TSS_UNKNOWN — never TSS_UNSAT: the caller
+ * then asks its exact solver, which stays the only prover of UNSAT. */
+int tss_solve_instance(tss_engine* e, const tss_cnf* c, const tss_encoding* enc, const tss_instance_info* info, const int32_t* weights,
+                       uint64_t seed, int64_t give_up_steps, uint8_t* assignment);
 
 /* ------------------------------------------------------------------------------------------ measured peaks */
 /* Runs the integer-issue (LOP3 / POPC / SHFL) and shared-memory micro-benchmarks SURVEY.md §8(d) asks for.

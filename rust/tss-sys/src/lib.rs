@@ -1,9 +1,9 @@
-//! Raw bindings to `include/tss.h` (ABI version 101).  Every entry point cites, in the header, the reference
+//! Raw bindings to `include/tss.h` (ABI version 102).  Every entry point cites, in the header, the reference
 //! interface it stands behind; this file only mirrors types and signatures.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int};
 
-pub const TSS_VERSION: c_int = 101;
+pub const TSS_VERSION: c_int = 102;
 pub const TSS_OK: c_int = 0;
 pub const TSS_SAT: c_int = 10; // IPASIR / rustsat SolverResult::Sat
 pub const TSS_UNSAT: c_int = 20; // never returned by the GPU engine
@@ -40,6 +40,21 @@ pub struct tss_stats {
     pub best_count: i32,
     pub interrupted: i32,
     pub last_solve_steps: i64,
+    pub sls_flips: u64,
+}
+
+#[repr(C)]
+#[derive(Copy, Clone, Default, Debug)]
+pub struct tss_instance_info {
+    pub w: i32,
+    pub h: i32,
+    pub n_defs: i32,
+    pub card_limit_1x1: i32,      // n of "at most n platforms" (main.rs:346), -1 if none
+    pub n_other_card_limits: i32,
+    pub has_weight_limit: i32,
+    pub weight_limit: i64,
+    pub n_weights: i32,
+    pub exact: i32,
 }
 
 #[repr(C)]
@@ -54,6 +69,10 @@ pub struct tss_search_params {
 
 #[repr(C)]
 pub struct tss_engine {
+    _p: [u8; 0],
+}
+#[repr(C)]
+pub struct tss_encoding {
     _p: [u8; 0],
 }
 #[repr(C)]
@@ -103,6 +122,34 @@ unsafe extern "C" {
     ) -> c_int;
     pub fn tss_cnf_propagate(
         e: *mut tss_engine, c: *const tss_cnf, assignments: *mut u8, n: i64, out_conflict: *mut i32, out_rounds: *mut i32,
+    ) -> c_int;
+
+    // the lib crate's side: Encoding::encode / with_limits (src/encoder.rs:435,619); with_limits records the instance
+    pub fn tss_encoding_create(grid: *const u8, w: i32, h: i32, defs: *const tss_dims, n_defs: i32, out: *mut *mut tss_encoding) -> c_int;
+    pub fn tss_encoding_destroy(enc: *mut tss_encoding);
+    pub fn tss_encoding_sizes(enc: *const tss_encoding, n_vars: *mut i32, n_clauses: *mut i32, n_lits: *mut i64, n_dims: *mut i32) -> c_int;
+    pub fn tss_encoding_var_maps(enc: *const tss_encoding, plat_var: *mut i32, terr_var: *mut i32) -> c_int;
+    pub fn tss_encoding_with_limits(
+        enc: *const tss_encoding, card: *const i32, n_card: i32, weights: *const i32, n_weights: i32, has_weight_limit: i32, weight_limit: i64,
+        n_vars: *mut i32, n_clauses: *mut i32, n_lits: *mut i64, lits: *mut i32, offsets: *mut u32,
+    ) -> c_int;
+    pub fn tss_layout_from_assignment(enc: *const tss_encoding, assignment: *const u8, n: i32, out: *mut tss_platform, cap: i32, n_out: *mut i32) -> c_int;
+    pub fn tss_layout_to_assignment(e: *mut tss_engine, enc: *const tss_encoding, plats: *const tss_platform, n: i32, assignment: *mut u8) -> c_int;
+
+    // the solver's side: from the clauses back to the instance, then Solve::solve on the GPU (csrc/instance.cpp)
+    pub fn tss_instance_find(
+        lits: *const i32, offsets: *const u32, n_clauses: i32, n_vars: i32, enc_out: *mut *mut tss_encoding, info: *mut tss_instance_info,
+        weights: *mut i32, weights_cap: i32,
+    ) -> c_int;
+    pub fn tss_witness_for_cnf(e: *mut tss_engine, c: *const tss_cnf, enc: *const tss_encoding, plats: *const tss_platform, n: i32, assignment: *mut u8) -> c_int;
+    pub fn tss_solve_instance(
+        e: *mut tss_engine, c: *const tss_cnf, enc: *const tss_encoding, info: *const tss_instance_info, weights: *const i32, seed: u64,
+        give_up_steps: i64, assignment: *mut u8,
+    ) -> c_int;
+    // packing lower bound: when the count meets it the loop needs no proof
+    pub fn tss_lower_bound(
+        e: *mut tss_engine, grid: *const u8, w: i32, h: i32, defs: *const tss_dims, n_defs: i32, seed: u64, restarts: i32, out_xy: *mut i32, cap: i32,
+        n_out: *mut i32,
     ) -> c_int;
 
     // a persistent portfolio instead of one-shot calls

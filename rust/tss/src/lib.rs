@@ -1,50 +1,59 @@
-//! `GpuSeeded<S>` — the drop-in the reference's drivers can use in place of `GlucoseSimp`
+//! `GpuSeeded<S>` — the drop-in the reference's drivers use in place of `GlucoseSimp`
 //! (`crates/repl/src/main.rs:17,295`, `crates/gui/src/main.rs:2,26`): a type that is
 //! `Solve + Interrupt + SolveStats + Default + Send`, owns an exact solver `S` and a `tss_engine`, answers
 //! `solve()` from the GPU when it can and from `S` otherwise.  `S` stays the only prover of UNSAT.
 //!
+//! The drivers change ONE line (`use tss::GpuSeeded as GlucoseSimp;`): the solver is handed a bare `Cnf`
+//! (`crates/repl/src/solver_runner.rs:8-20`) and finds terrain, platform set, variable map and limits again through the
+//! instance registry that the lib crate's `Encoding::with_limits` fills (`tss_instance_find`, see `lib-patch/encoder_ffi.rs`).
+//!
 //! SOURCE ONLY — not compiled in this repository (no Rust toolchain in the build image); the rustsat 0.7 trait
-//! surface is written from memory and must be checked against the pinned crate.  The same call sequence is
-//! exercised, tested and timed from Python (`timberborn_support_solver_b200/api.py`: `GpuBoundSolver`,
-//! `solver_loop`) and from C (`tests/c_abi_smoke.c`).
+//! surface is written from memory and must be checked against the pinned crate.  The call sequence below is EXACTLY the
+//! one `tools/tss_repl.cpp` performs (tss_cnf_upload -> tss_instance_find -> tss_solve_instance), which the GPU test suite
+//! runs on test/ex1-3 (tests/test_gpu.py::test_cpp_repl_driver_*); `tss_solve_instance` itself is host C++ over the public
+//! C ABI (csrc/instance.cpp), so the recipe is exercised without a Rust toolchain.
+//!
+//! Without a usable CUDA device `Default` logs a warning and the value is "exact solver only" — acceptable degradation of
+//! the wrapper (the drivers must keep working on a laptop); libtss itself has no CPU fallback.
 use std::ffi::CStr;
 use std::ptr;
-use std::sync::atomic::{AtomicPtr, Ordering};
 use std::sync::Arc;
 
-use anyhow::{anyhow, Result};
+use anyhow::Result;
 use rustsat::instances::Cnf;
 use rustsat::solvers::{Interrupt, InterruptSolver, Solve, SolveStats, SolverResult, SolverStats};
-use rustsat::types::{Assignment, Clause, Lit, TernaryVal};
+use rustsat::types::{Assignment, Lit, TernaryVal};
 use tss_sys as ffi;
 
-/// What a bare CNF does not carry: the terrain and the platform set.  Handed over once, next to
-/// `Encoding::encode` (`crates/repl/src/main.rs:254`, `crates/gui/src/app.rs:180-184`).
-#[derive(Clone, Default)]
-pub struct Terrain {
-    pub grid: Vec<u8>, // Grid<bool>.data, row-major x + y * width (src/math/grid.rs:66-68)
-    pub w: i32,
-    pub h: i32,
-    pub defs: Vec<ffi::tss_dims>,   // PlatformDef dims in the order given to the encoder
-    pub plat_var_1x1: Vec<u32>,     // variable of P_1x1 at every tile, row-major (EncodingVars, src/encoder.rs:184-206)
-    pub terr_vars: Vec<[u32; 4]>,   // T_0..T_3 per tile, 0 = absent
+/// Owns the engine.  Shared (`Arc`) between the solver and every interrupter it handed out, so an interrupter that fires
+/// from another thread (main.rs:298-323) can never outlive the engine it points at: the engine is destroyed when the last
+/// holder drops.  `tss_interrupt` is the one entry point documented as callable concurrently with a running solve.
+struct EngineHandle(*mut ffi::tss_engine);
+unsafe impl Send for EngineHandle {}
+unsafe impl Sync for EngineHandle {}
+impl Drop for EngineHandle {
+    fn drop(&mut self) {
+        if !self.0.is_null() {
+            unsafe { ffi::tss_engine_destroy(self.0) };
+        }
+    }
 }
 
 pub struct GpuSeeded<S = rustsat_glucose::simp::Glucose> {
     inner: S,
-    engine: *mut ffi::tss_engine,
-    shared: Arc<AtomicPtr<ffi::tss_engine>>, // for the interrupter (another thread, main.rs:298-323)
-    cnf: *mut ffi::tss_cnf,
+    engine: Option<Arc<EngineHandle>>,
+    cnf: *mut ffi::tss_cnf,              // the clauses as uploaded in add_cnf (kernel (c) verifies witnesses against them)
+    enc: *mut ffi::tss_encoding,         // the instance those clauses belong to (tss_instance_find), or null
+    info: ffi::tss_instance_info,
+    weights: Vec<i32>,                   // (def_w, def_h, weight) records of PlatformLimits.weights
     n_vars: i32,
-    terrain: Terrain,
-    bound: Option<i32>,            // n of "sum P_1x1 <= n" (Encoding::with_limits, src/encoder.rs:643-652)
     witness: Option<Assignment>,
-    give_up: i64,                  // steps per chain before the exact solver takes over
+    give_up: i64,                        // steps per chain before the exact solver takes over
     seed: u64,
 }
 
-// The engine is only ever driven from the thread that owns the solver; tss_interrupt is the one call made from
-// elsewhere and is documented as thread safe (include/tss.h).
+// The engine is only ever driven from the thread that owns the solver (tokio moves the solver into the blocking task and
+// back, solver_runner.rs:15-17); tss_interrupt is the one call made from elsewhere.
 unsafe impl<S: Send> Send for GpuSeeded<S> {}
 
 fn last_error(e: *const ffi::tss_engine) -> String {
@@ -53,21 +62,21 @@ fn last_error(e: *const ffi::tss_engine) -> String {
 
 impl<S: Default> Default for GpuSeeded<S> {
     fn default() -> Self {
-        let mut engine = ptr::null_mut();
-        // no usable CUDA device: engine stays null and every solve() goes straight to the exact solver (logged, never a panic —
-        // the drivers log solver errors and carry on, crates/gui/src/app.rs:160-173)
-        if unsafe { ffi::tss_engine_create(-1, &mut engine) } != ffi::TSS_OK {
-            log::warn!("tss: no CUDA device, solving on the CPU only");
-            engine = ptr::null_mut();
-        }
+        let mut raw = ptr::null_mut();
+        let engine = if unsafe { ffi::tss_engine_create(-1, &mut raw) } == ffi::TSS_OK {
+            Some(Arc::new(EngineHandle(raw)))
+        } else {
+            log::warn!("tss: no usable CUDA device, solving with the exact solver only");
+            None
+        };
         GpuSeeded {
             inner: S::default(),
             engine,
-            shared: Arc::new(AtomicPtr::new(engine)),
             cnf: ptr::null_mut(),
+            enc: ptr::null_mut(),
+            info: ffi::tss_instance_info::default(),
+            weights: vec![0; 3 * 16],
             n_vars: 0,
-            terrain: Terrain::default(),
-            bound: None,
             witness: None,
             give_up: 1024,
             seed: 0,
@@ -77,60 +86,15 @@ impl<S: Default> Default for GpuSeeded<S> {
 
 impl<S> Drop for GpuSeeded<S> {
     fn drop(&mut self) {
-        self.shared.store(ptr::null_mut(), Ordering::SeqCst);
         unsafe {
             if !self.cnf.is_null() {
                 ffi::tss_cnf_destroy(self.cnf);
             }
-            if !self.engine.is_null() {
-                ffi::tss_engine_destroy(self.engine);
+            if !self.enc.is_null() {
+                ffi::tss_encoding_destroy(self.enc);
             }
         }
-    }
-}
-
-impl<S> GpuSeeded<S> {
-    /// Terrain, platform set, variable map and the current cardinality bound of the instance about to be added.
-    pub fn set_terrain(&mut self, terrain: Terrain, bound: Option<usize>) {
-        self.terrain = terrain;
-        self.bound = bound.map(|b| b as i32);
-    }
-
-    /// GPU layout -> full assignment: platform variables from the layout, terrain-layer variables from validate()'s
-    /// dilation rounds, auxiliary cardinality variables by unit propagation on the uploaded CNF (kernel (c)); the
-    /// result is checked against every clause the exact solver received before it is trusted.
-    fn verified_assignment(&mut self, plats: &[ffi::tss_platform]) -> Result<Option<Assignment>> {
-        let n = (self.n_vars + 1) as usize;
-        let mut a = vec![2u8; n]; // 0 = false, 1 = true, 2 = unassigned
-        for v in &self.terrain.plat_var_1x1 {
-            a[*v as usize + 1] = 0;
-        }
-        for p in plats {
-            // 1x1 supports only in this sketch; larger platforms set P_dims at the anchor and, through the encoder's DAG
-            // implications (src/encoder.rs:450-458), every smaller dims variable: see tss_layout_to_assignment
-            let tile = (p.y * self.terrain.w + p.x) as usize;
-            a[self.terrain.plat_var_1x1[tile] as usize + 1] = 1;
-        }
-        let (mut conflict, mut rounds) = (-1i32, 0i32);
-        let rc = unsafe { ffi::tss_cnf_propagate(self.engine, self.cnf, a.as_mut_ptr(), 1, &mut conflict, &mut rounds) };
-        if rc < 0 {
-            return Err(anyhow!("tss_cnf_propagate: {}", last_error(self.engine)));
-        }
-        if conflict >= 0 {
-            return Ok(None);
-        }
-        for v in a.iter_mut() {
-            if *v == 2 {
-                *v = 0;
-            }
-        }
-        let (mut n_false, mut first) = (0i32, -1i32);
-        let rc = unsafe { ffi::tss_cnf_check(self.engine, self.cnf, a.as_ptr(), 1, &mut n_false, &mut first) };
-        if rc < 0 || n_false != 0 {
-            return Ok(None);
-        }
-        let vals: Vec<TernaryVal> = a[1..].iter().map(|&b| if b == 1 { TernaryVal::True } else { TernaryVal::False }).collect();
-        Ok(Some(Assignment::from(vals)))
+        // the engine goes when the last Arc (this one or an interrupter's) is dropped
     }
 }
 
@@ -140,7 +104,7 @@ impl<S: Solve> Solve for GpuSeeded<S> {
     }
 
     fn add_cnf(&mut self, cnf: Cnf) -> Result<()> {
-        if !self.engine.is_null() {
+        if let Some(engine) = &self.engine {
             // CSR with DIMACS-signed literals: Lit(idx, negated) -> +/-(idx + 1)
             let (mut lits, mut offsets, mut n_vars) = (Vec::<i32>::new(), vec![0u32], 0i32);
             for clause in cnf.iter() {
@@ -152,12 +116,19 @@ impl<S: Solve> Solve for GpuSeeded<S> {
                 offsets.push(lits.len() as u32);
             }
             self.n_vars = n_vars;
-            let rc = unsafe {
-                ffi::tss_cnf_upload(self.engine, lits.as_ptr(), offsets.as_ptr(), (offsets.len() - 1) as i32, n_vars, &mut self.cnf)
-            };
+            let n_clauses = (offsets.len() - 1) as i32;
+            let rc = unsafe { ffi::tss_cnf_upload(engine.0, lits.as_ptr(), offsets.as_ptr(), n_clauses, n_vars, &mut self.cnf) };
             if rc != ffi::TSS_OK {
-                log::warn!("tss_cnf_upload: {}", last_error(self.engine));
+                log::warn!("tss_cnf_upload: {}", last_error(engine.0)); // logged, never fatal (crates/gui/src/app.rs:160-173)
                 self.cnf = ptr::null_mut();
+            } else {
+                // which instance is this?  (recorded by Encoding::with_limits, lib-patch/encoder_ffi.rs)
+                let rc = unsafe {
+                    ffi::tss_instance_find(lits.as_ptr(), offsets.as_ptr(), n_clauses, n_vars, &mut self.enc, &mut self.info, self.weights.as_mut_ptr(), 16)
+                };
+                if rc != ffi::TSS_SAT {
+                    self.enc = ptr::null_mut(); // not one of ours: the exact solver handles it alone
+                }
             }
         }
         self.inner.add_cnf(cnf)
@@ -167,33 +138,29 @@ impl<S: Solve> Solve for GpuSeeded<S> {
     where
         C: AsRef<rustsat::types::Cl> + ?Sized,
     {
+        self.enc = ptr::null_mut(); // clauses beyond the recorded instance: the GPU's view would be stale
         self.inner.add_clause_ref(clause)
     }
 
     fn solve(&mut self) -> Result<SolverResult> {
         self.witness = None;
-        if !self.engine.is_null() && !self.cnf.is_null() && !self.terrain.grid.is_empty() {
-            let t = &self.terrain;
-            let mut plats = vec![ffi::tss_platform::default(); t.grid.len() + 1];
-            let mut n = 0i32;
-            // ONE SAT-like call: the first layout within the bound, give up after `give_up` steps per chain
-            let rc = unsafe {
-                ffi::tss_solve_upper_bound(
-                    self.engine, t.grid.as_ptr(), t.w, t.h, t.defs.as_ptr(), t.defs.len() as i32, self.bound.unwrap_or(-1), self.seed, 0,
-                    -self.give_up, plats.as_mut_ptr(), plats.len() as i32, &mut n,
-                )
-            };
+        if let (Some(engine), false, false) = (&self.engine, self.cnf.is_null(), self.enc.is_null()) {
+            let mut a = vec![2u8; self.n_vars as usize + 1]; // 0 = false, 1 = true, 2 = unassigned; slot 0 unused
+            unsafe { ffi::tss_clear_interrupt(engine.0) };
+            // ONE SAT-like call within the instance's limit, giving up after `give_up` steps per chain; the witness is built
+            // with tss_layout_to_assignment (platform + terrain-layer variables), completed by unit propagation (totalizer
+            // auxiliaries) and checked against every uploaded clause before it is trusted — all inside tss_solve_instance
+            let rc = unsafe { ffi::tss_solve_instance(engine.0, self.cnf, self.enc, &self.info, self.weights.as_ptr(), self.seed, self.give_up, a.as_mut_ptr()) };
             self.seed = self.seed.wrapping_add(1);
             if rc == ffi::TSS_SAT {
                 let mut st = ffi::tss_stats::default();
-                unsafe { ffi::tss_get_stats(self.engine, &mut st) };
+                unsafe { ffi::tss_get_stats(engine.0, &mut st) };
                 self.give_up = (32 * st.last_solve_steps).max(1024);
-                if let Some(a) = self.verified_assignment(&plats[..n as usize])? {
-                    self.witness = Some(a);
-                    return Ok(SolverResult::Sat);
-                }
+                let vals: Vec<TernaryVal> = a[1..].iter().map(|&b| if b == 1 { TernaryVal::True } else { TernaryVal::False }).collect();
+                self.witness = Some(Assignment::from(vals));
+                return Ok(SolverResult::Sat);
             } else if rc < 0 {
-                log::warn!("tss_solve_upper_bound: {}", last_error(self.engine)); // logged, never fatal (app.rs:160-173)
+                log::warn!("tss_solve_instance: {}", last_error(engine.0));
             }
         }
         self.inner.solve() // the exact solver: every UNSAT answer comes from here
@@ -214,26 +181,24 @@ impl<S: Solve> Solve for GpuSeeded<S> {
     }
 }
 
-/// Interrupts both sides: `tss_interrupt` is safe from any thread while a solve runs (include/tss.h).
+/// Interrupts both sides.  Holds its own reference to the engine, so it stays valid whatever happens to the solver.
 pub struct Both<I> {
-    engine: Arc<AtomicPtr<ffi::tss_engine>>,
+    engine: Option<Arc<EngineHandle>>,
     inner: I,
 }
 impl<I: InterruptSolver> InterruptSolver for Both<I> {
     fn interrupt(&mut self) {
-        let e = self.engine.load(Ordering::SeqCst);
-        if !e.is_null() {
-            unsafe { ffi::tss_interrupt(e) };
+        if let Some(e) = &self.engine {
+            unsafe { ffi::tss_interrupt(e.0) };
         }
         self.inner.interrupt();
     }
 }
-unsafe impl<I: Send> Send for Both<I> {}
 
 impl<S: Interrupt> Interrupt for GpuSeeded<S> {
     type Interrupter = Both<S::Interrupter>;
     fn interrupter(&mut self) -> Self::Interrupter {
-        Both { engine: self.shared.clone(), inner: self.inner.interrupter() }
+        Both { engine: self.engine.clone(), inner: self.inner.interrupter() }
     }
 }
 
@@ -242,6 +207,3 @@ impl<S: SolveStats> SolveStats for GpuSeeded<S> {
         self.inner.stats() // engine counters are available through tss_get_stats
     }
 }
-
-#[allow(unused)]
-fn _clause_type_is_used(_: Clause) {}

@@ -1,6 +1,8 @@
 """Parity tests proper: the CUDA path (through the C ABI of libtss) against the oracle on the same seeded inputs,
 against the committed golden fixtures, and through size-independent properties at BASELINE.json's full sizes.
 Bit-exact everywhere: the path is integer / boolean only (no floating point)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -807,11 +809,141 @@ def test_solver_loop_gpu_then_exact_proof(eng, fixtures):
         g = T.WorldGrid(fixtures[name])
         proj = T.Project(T.World(g))
         enc = T.Encoding.encode(T.PLATFORMS_DEFAULT[:1], g)
-        out = T.solver_loop(proj, enc, T.PlatformLimits(), eng, exact_solver=exact, seed=1, budget_ms=0)
+        out = T.solver_loop(proj, enc, T.PlatformLimits(), eng, exact_solver=exact, seed=1, budget_ms=0, use_lower_bound=False)
         assert out["proved_optimal"] and out["best"].platform_count() == optimum
         assert all(s["valid"] for s in out["steps"] if s["result"] == T.SAT)
         assert out["steps"][-1]["result"] == T.UNSAT and out["steps"][-1]["source"] == "exact"
         assert [s["source"] for s in out["steps"][:-1]] == ["gpu"] * (len(out["steps"]) - 1)
+
+
+# =============================================================================== packing lower bound (tss_lower_bound)
+def _key_dims(defs):
+    out = []
+    for d in defs:      # dims keys: defs order, unflipped then flipped (src/encoder.rs:121-130)
+        for dims in ((d.width, d.height), (d.height, d.width)):
+            if dims not in out:
+                out.append(dims)
+    return out
+
+
+def _check_packing(g, defs, tiles):
+    """The bound's witness against the reference's own rule: every in-bounds placement of every dims key, validated ALONE by
+    the oracle's validate() (platform_layout.rs:85-149), supports at most one packed tile — so a layout needs >= len(tiles)."""
+    h, w = g.shape
+    packed = np.zeros_like(g)
+    for x, y in tiles:
+        assert g[y, x] == 1                                  # ceiling tiles only
+        packed[y, x] = 1
+    assert packed.sum() == len(tiles)
+    for kw, kh in _key_dims(defs):
+        for y in range(h - kh + 1):
+            for x in range(w - kw + 1):
+                plat = (x, y, min(kw, kh), max(kw, kh), int(kw > kh))
+                v = O.validate(g, [plat])
+                assert not v.out_of_bounds
+                supported = g & (1 - v.unsupported)
+                assert int((supported & packed).sum()) <= 1, (plat, tiles)
+
+
+@pytest.mark.parametrize("name", ["ex1", "ex3", "ex2", "rect8", "rand20x14"])
+@pytest.mark.parametrize("pset", ["1x1", "default8", "1x1+3x3"])
+def test_lower_bound_packing_is_sound(eng, fixtures, name, pset):
+    g = {"rect8": np.ones((8, 8), np.uint8), "rand20x14": synth_terrain(20, 14, seed=3, t=1)}.get(name)
+    if g is None:
+        g = fixtures[name]
+    defs = {"1x1": T.PLATFORMS_DEFAULT[:1], "default8": T.PLATFORMS_DEFAULT, "1x1+3x3": (T.PlatformDef(1, 1), T.PlatformDef(3, 3))}[pset]
+    tiles = eng.lower_bound(T.WorldGrid(g), defs, seed=1)
+    assert len(tiles) >= 1
+    _check_packing(g, defs, tiles)
+    key = f"{name}/{pset}"
+    proofs = golden("proofs")
+    if key in proofs:
+        assert len(tiles) <= proofs[key]["optimum"]          # a lower bound never exceeds the proven optimum
+    # the bound is monotone in the platform set: more platform types can only lower it
+    if pset != "1x1":
+        assert len(tiles) <= len(eng.lower_bound(T.WorldGrid(g), T.PLATFORMS_DEFAULT[:1], seed=1))
+
+
+def test_lower_bound_edge_cases(eng):
+    assert eng.lower_bound(T.WorldGrid(np.zeros((4, 5), np.uint8))) == []                         # no ceiling: nothing to support
+    assert eng.lower_bound(T.WorldGrid(np.ones((1, 1), np.uint8))) == [(0, 0)]
+    two = np.zeros((1, 32), np.uint8)
+    two[0, 0] = two[0, 31] = 1                                                                    # two islands: one support each
+    assert sorted(eng.lower_bound(T.WorldGrid(two))) == [(0, 0), (31, 0)]
+    line = np.ones((1, 32), np.uint8)                                                             # a corridor: tiles 7 apart, ceil(32/7) = 5
+    tiles = eng.lower_bound(T.WorldGrid(line))
+    assert len(tiles) == 5 and all(b[0] - a[0] >= 7 for a, b in zip(sorted(tiles), sorted(tiles)[1:]))
+    with pytest.raises(T.TssError):
+        eng.lower_bound(T.WorldGrid(np.ones((33, 8), np.uint8)))
+    full = np.ones((32, 32), np.uint8)
+    tiles = eng.lower_bound(T.WorldGrid(full))
+    assert len(tiles) >= 32 * 32 // 85 + 1 and len(tiles) <= 41                                   # radius-6 balls hold <= 85 tiles; optimum >= 1024/25
+
+
+def test_solver_loop_ends_on_the_lower_bound_without_the_exact_solver(eng, fixtures):
+    """BASELINE.json configs[0]: the REPL's own run (default-8 set) on test/ex1.toml and ex3.toml — optimum 1, and any ceiling
+    tile is a packing of size 1: the loop is finished by the GPU alone, the exact solver is never called."""
+    calls = []
+
+    def exact(cnf):
+        calls.append(cnf.n_vars)
+        raise AssertionError("the exact solver must not be needed")
+
+    for name in ("ex1", "ex3"):
+        g = T.WorldGrid(fixtures[name])
+        enc = T.Encoding.encode(T.PLATFORMS_DEFAULT, g)
+        out = T.solver_loop(T.Project(T.World(g)), enc, T.PlatformLimits(), eng, exact_solver=exact, seed=4)
+        assert out["proved_optimal"] and out["best"].platform_count() == golden("proofs")[f"{name}/default8"]["optimum"] == out["lower_bound"] == 1
+        assert out["steps"][-1]["source"] == "lower bound" and not calls
+        assert all(s["valid"] for s in out["steps"] if s["result"] == T.SAT)
+
+
+# =============================================================================== the C++ driver over the C ABI (tools/tss_repl.cpp)
+def _run_repl(tmp_path, grid, *args):
+    import subprocess
+    import sys
+    proj = tmp_path / "project.toml"
+    proj.write_text(T.WorldGrid(grid).to_toml())
+    exe = os.path.join(os.path.dirname(T.__file__), "tss_repl")
+    exact = f"{sys.executable} {os.path.join(os.path.dirname(__file__), 'exact_dimacs.py')}"
+    out = subprocess.run([exe, str(proj), "--exact", exact, *args], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    summary = [ln for ln in out.stdout.splitlines() if ln.startswith("# best=")][-1]
+    fields = dict(kv.split("=", 1) for kv in summary[2:].replace('verdict="', "verdict=").replace('" gpu', " gpu").split(" ") if "=" in kv)
+    counts = [int(ln.split("(")[1].split()[0]) for ln in out.stdout.splitlines() if ln.startswith("Solution found")]
+    return out.stdout, fields, counts
+
+
+@pytest.mark.parametrize("name,pset,key", [("ex1", "default", "ex1/default8"), ("ex3", "default", "ex3/default8"), ("ex2", "default", "ex2/default8"),
+                                           ("ex1", "1x1", "ex1/1x1"), ("ex3", "1x1", "ex3/1x1")])
+def test_cpp_repl_driver_reaches_the_proven_optimum(eng, fixtures, tmp_path, name, pset, key):
+    """BASELINE.json configs[0]: `load test/exN.toml; solve` through tools/tss_repl.cpp — the REPL's loop (main.rs:280-366) in C++
+    over the C ABI, performing the Rust shim's call sequence (upload the clauses, find the instance from them, SAT-like GPU
+    solve, witness verified against those clauses), the oracle CDCL standing in for Glucose as `--exact`.  It must end with
+    the proven optimum, strictly decreasing counts (bound = found - 1), and the REPL's closing lines."""
+    optimum = golden("proofs")[key]["optimum"]
+    text, f, counts = _run_repl(tmp_path, fixtures[name], "--platforms", pset, "--seed", "3")
+    assert int(f["best"]) == optimum and counts[-1] == optimum
+    assert all(b < a for a, b in zip(counts, counts[1:]))
+    assert "No solution found for the current constraints" in text and text.rstrip().splitlines()[-2] == "Done"
+    assert f["verdict"].startswith("optimal") and "FAILED" not in text
+    if optimum == 1:                       # default-8 on ex1 / ex3: the lower bound closes the loop, the exact solver is never started
+        assert int(f["exact_solves"]) == 0 and int(f["lower_bound"]) == 1
+
+
+def test_cpp_repl_driver_limits_and_errors(eng, fixtures, tmp_path):
+    # `solve -l 1:2` on ex1 with 1x1 supports: 3 are needed (proofs.json) -> UNSAT straight from the exact solver
+    text, f, counts = _run_repl(tmp_path, fixtures["ex1"], "--platforms", "1x1", "-l", "1:2", "--no-lower-bound")
+    assert counts == [] and f["verdict"] == "unsatisfiable" and int(f["exact_solves"]) == 1
+    # a limit on another platform type is left to the exact solver (the search cannot steer by it), and still honoured
+    text, f, counts = _run_repl(tmp_path, fixtures["ex1"], "-l", "5:0,3:0")
+    assert int(f["best"]) >= 2 and int(f["gpu_solves"]) >= 1 and int(f["exact_solves"]) >= 1
+    import subprocess
+    exe = os.path.join(os.path.dirname(T.__file__), "tss_repl")
+    bad = tmp_path / "bad.toml"
+    bad.write_text('[world]\ngrid = ["XZ"]\n')
+    r = subprocess.run([exe, str(bad)], capture_output=True, text=True)
+    assert r.returncode == 1 and "Error parsing file" in r.stderr                   # src/world.rs:49-79: any other character is an error
 
 
 def test_interrupt_returns_unknown(eng):

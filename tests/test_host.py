@@ -239,3 +239,57 @@ def test_merge_supports_keeps_layouts_complete_and_disjoint():
     assert sorted(lay.platforms()) == sorted((p.x, p.y) for p in plats)
     with pytest.raises(T.TssError):
         T.PlatformLayout([T.Platform(0, 0, T.PlatformDef(3, 3))]).merge_supports(T.World(T.WorldGrid(grid)), T.PLATFORMS_DEFAULT)
+
+
+# ---- instance bridge (tss_instance_find): from the clauses a solver is handed back to terrain / platform set / limits ----
+def test_instance_registry_finds_the_instance_from_its_clauses(fixtures):
+    """The drivers hand their solver a bare Cnf (crates/repl/src/solver_runner.rs:8-20).  with_limits records every instance it
+    lowers; the solver side finds it again from the clauses alone — exactly (same CNF) or by its base clauses — and an
+    unrelated CNF is not found."""
+    from timberborn_support_solver_b200 import _lib
+    lib = T.load()
+    g = T.WorldGrid(fixtures["ex1"])
+    enc = T.Encoding.encode(T.PLATFORMS_DEFAULT, g)
+    other = T.Encoding.encode(T.PLATFORMS_DEFAULT[:1], T.WorldGrid(fixtures["ex3"]))
+    weights = {T.PlatformDef(1, 1): 5, T.PlatformDef(3, 3): 2}
+    cnf_w = enc.with_limits(T.PlatformLimits({}, weights, 11))
+    cnf_o = other.with_limits(T.PlatformLimits.new_unweighted({ONE: 4}))
+    cnf = enc.with_limits(T.PlatformLimits.new_unweighted({ONE: 2, T.PlatformDef(5, 5): 1}))
+
+    def find(c):
+        lits, offs = np.ascontiguousarray(c.lits, np.int32), np.ascontiguousarray(c.offsets, np.uint32)
+        h, info, wts = C.c_void_p(), _lib.InstanceInfo(), np.zeros((16, 3), np.int32)
+        rc = lib.tss_instance_find(lits.ctypes.data_as(C.POINTER(C.c_int32)), offs.ctypes.data_as(C.POINTER(C.c_uint32)), c.n_clauses, c.n_vars,
+                                   C.byref(h), C.byref(info), wts.ctypes.data_as(C.POINTER(C.c_int32)), 16)
+        terrain = None
+        if rc == 10:
+            out = np.zeros(info.w * info.h, np.uint8)
+            w, hh = C.c_int32(), C.c_int32()
+            assert lib.tss_encoding_terrain(h, out.ctypes.data_as(C.POINTER(C.c_uint8)), out.size, C.byref(w), C.byref(hh)) == 0
+            terrain = out.reshape(hh.value, w.value)
+            defs, n = (_lib.Dims * 16)(), C.c_int32()
+            assert lib.tss_encoding_defs(h, defs, 16, C.byref(n)) == 0 and n.value == info.n_defs
+            lib.tss_encoding_destroy(h)
+        return rc, info, wts, terrain
+
+    rc, info, wts, terrain = find(cnf)
+    assert rc == 10 and info.exact == 1 and (info.w, info.h, info.n_defs) == (g.width, g.height, 8)
+    assert info.card_limit_1x1 == 2 and info.n_other_card_limits == 1 and not info.has_weight_limit
+    assert np.array_equal(terrain, g.data)
+    rc, info, wts, terrain = find(cnf_w)                       # an older record is still there, with its own limits
+    assert rc == 10 and info.exact == 1 and info.card_limit_1x1 == -1 and info.has_weight_limit and info.weight_limit == 11
+    assert sorted(map(tuple, wts[: info.n_weights].tolist())) == [(1, 1, 5), (3, 3, 2)]
+    rc, info, _, terrain = find(cnf_o)
+    assert rc == 10 and info.n_defs == 1 and info.card_limit_1x1 == 4 and np.array_equal(terrain, fixtures["ex3"])
+    # the same base clauses with the limits lowered by "someone else" (here: one more clause): found by its base, flagged inexact
+    ext = T.Cnf(cnf.n_vars + 1, np.append(cnf.lits, np.int32(cnf.n_vars + 1)), np.append(cnf.offsets, np.uint32(len(cnf.lits) + 1)))
+    rc, info, _, _ = find(ext)
+    assert rc == 10 and info.exact == 0 and info.card_limit_1x1 == 2
+    # unrelated clauses
+    junk = T.Cnf(3, np.array([1, -2, 3], np.int32), np.array([0, 2, 3], np.uint32))
+    assert find(junk)[0] == 0
+    # the encoding handle may be destroyed by its owner: the registry keeps the instance alive
+    del enc
+    import gc
+    gc.collect()
+    assert find(cnf)[0] == 10

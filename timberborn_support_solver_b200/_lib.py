@@ -32,6 +32,11 @@ class Stats(C.Structure):  # tss_stats
                 ("sls_flips", C.c_uint64)]
 
 
+class InstanceInfo(C.Structure):  # tss_instance_info
+    _fields_ = [("w", C.c_int32), ("h", C.c_int32), ("n_defs", C.c_int32), ("card_limit_1x1", C.c_int32), ("n_other_card_limits", C.c_int32),
+                ("has_weight_limit", C.c_int32), ("weight_limit", C.c_int64), ("n_weights", C.c_int32), ("exact", C.c_int32)]
+
+
 class SearchParams(C.Structure):  # tss_search_params
     _fields_ = [("seed", C.c_uint64), ("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("noise_pct", C.c_int32),
                 ("kernel", C.c_int32)]
@@ -97,7 +102,14 @@ SIGNATURES = {
     "tss_search_set_weights": (C.c_int, [_vp, _i32p, _i32]),
     "tss_solve_min_weight": (C.c_int, [_vp, _u8p, _i32, _i32, _P(Dims), _i32, _i32p, _i32, _i64, _u64, _i32, _i64, _P(Platform), _i32, _i32p, _i64p]),
     "tss_solve_upper_bound": (C.c_int, [_vp, _u8p, _i32, _i32, _P(Dims), _i32, _i32, _u64, _i32, _i64, _P(Platform), _i32, _i32p]),
+    "tss_lower_bound": (C.c_int, [_vp, _u8p, _i32, _i32, _P(Dims), _i32, _u64, _i32, _i32p, _i32, _i32p]),
     "tss_solve_batch": (C.c_int, [_vp, _u8p, _i32, _i32, _i64, _u64, _i64, _i32, _i32p, _u32p]),
+    "tss_instance_find": (C.c_int, [_i32p, _u32p, _i32, _i32, _P(_vp), _P(InstanceInfo), _i32p, _i32]),
+    "tss_encoding_terrain": (C.c_int, [_vp, _u8p, _sz, _i32p, _i32p]),
+    "tss_encoding_defs": (C.c_int, [_vp, _P(Dims), _i32, _i32p]),
+    "tss_cnf_num_vars": (C.c_int, [_vp]),
+    "tss_witness_for_cnf": (C.c_int, [_vp, _vp, _vp, _P(Platform), _i32, _u8p]),
+    "tss_solve_instance": (C.c_int, [_vp, _vp, _vp, _P(InstanceInfo), _i32p, _u64, _i64, _u8p]),
     "tss_measure_peaks": (C.c_int, [_vp, _P(C.c_double), _i32]),
 }
 

@@ -633,6 +633,16 @@ class Engine:
             return SAT, PlatformLayout(Platform._from_c(out[i]) for i in range(n.value)), wt.value
         return INTERRUPTED, None, None
 
+    def lower_bound(self, grid: WorldGrid, defs=PLATFORMS_DEFAULT[:1], seed=0, restarts=0):
+        """Packing lower bound (tss_lower_bound): -> list of (x, y) ceiling tiles no two of which one platform of `defs` can
+        support; its length bounds the platform count of every complete layout from below."""
+        defs = list(defs)
+        out = np.zeros((grid.data.size + 1, 2), np.int32)
+        n = C.c_int32()
+        self._check(self.lib.tss_lower_bound(self._h, _ptr(grid.data, C.c_uint8), grid.width, grid.height, _defs_array(defs), len(defs), seed, restarts,
+                                             _ptr(out, C.c_int32), len(out), C.byref(n)))
+        return [(int(x), int(y)) for x, y in out[: n.value]]
+
     def solve_batch(self, grids, seed=0, steps=2048, want_layouts=False, chains_per_terrain=0):
         """grids: uint8[n, h, w] -> counts int32[n] (and packed support rows uint32[n, h] if asked)"""
         g = _u8(grids)
@@ -714,7 +724,7 @@ class GpuBoundSolver:
 
 
 def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, engine: Engine, exact_solver=None, seed=0, budget_ms=None,
-                on_solution=None):
+                on_solution=None, use_lower_bound=True):
     """crates/repl/src/main.rs:280-366 with the GPU engine as the SAT side and an optional exact solver
     (`exact_solver(cnf) -> (SAT|UNSAT|INTERRUPTED, assignment)`, Glucose in the reference) for the proof.
 
@@ -723,13 +733,28 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
     GPU cannot answer (one below the optimum) costs milliseconds before the prover takes over, not the engine's default
     2^18 steps.  budget_ms=0 keeps that default effort; budget_ms > 0 improves for that long in every iteration.
 
-    Returns dict(best=PlatformLayout|None, proved_optimal=bool, steps=[...])."""
+    use_lower_bound: ask the engine for its packing lower bound first (tss_lower_bound); when the count reaches it the loop
+    ends with `proved_optimal` and no exact-solver call.
+
+    Returns dict(best=PlatformLayout|None, proved_optimal=bool, steps=[...], lower_bound=int|None)."""
     one = PlatformDef(1, 1)
     limits = PlatformLimits(dict(limits.card_limits), dict(limits.weights), limits.weight_limit)
     steps, best, proved = [], None, False
     give_up = 1024
     engine.clear_interrupt()
+    # packing lower bound (not in the reference): once the count meets it — or the next bound falls below it — the loop is
+    # finished and nothing is left for the exact solver to prove.  Only when the count is the sole limit (the REPL's case).
+    lower = None
+    g = encoding._grid
+    only_count = not limits.weights and limits.weight_limit is None and all(d == one for d in limits.card_limits)
+    if use_lower_bound and only_count and g.width <= 32 and g.height <= 32:
+        lower = len(engine.lower_bound(g, encoding.defs, seed=seed))
     while True:
+        bound_now = limits.card_limits.get(one)
+        if lower is not None and best is not None and bound_now is not None and bound_now < lower:
+            steps.append(dict(bound=bound_now, result=UNSAT, source="lower bound"))
+            proved = True
+            break
         cnf = encoding.with_limits(limits)                      # main.rs:292-293
         if budget_ms is None:
             solver = GpuBoundSolver(engine, encoding, limits, seed=seed, budget_ms=0, max_steps=-give_up)
@@ -759,4 +784,4 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
         if count == 0:                                          # main.rs:341-344
             break
         limits.card_limits[one] = count - 1                     # main.rs:346
-    return dict(best=best, proved_optimal=proved, steps=steps)
+    return dict(best=best, proved_optimal=proved, steps=steps, lower_bound=lower)

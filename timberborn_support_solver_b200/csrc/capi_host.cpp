@@ -3,15 +3,11 @@
 #include <cstring>
 #include <new>
 
+#include "encoding_handle.hpp"
 #include "engine.hpp"
 #include "host_model.hpp"
 
 using namespace tss;
-
-struct tss_encoding {
-    Encoding enc;
-    std::vector<uint8_t> grid;
-};
 
 extern "C" int tss_layout_to_assignment_impl(tss_engine* e, const Encoding& enc, const uint8_t* grid, const tss_platform* plats, int32_t n_plats,
                                   uint8_t* assignment);
@@ -57,13 +53,15 @@ int tss_world_synthetic(int32_t w, int32_t h, uint64_t seed, uint64_t t, uint32_
 
 int tss_encoding_create(const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs, tss_encoding** out) {
     if (!out || !grid || !defs || n_defs <= 0 || w <= 0 || h <= 0) return TSS_E_INVALID;
-    tss_encoding* enc = new (std::nothrow) tss_encoding();
-    if (!enc) return TSS_E_INVALID;
+    auto data = std::make_shared<tss_encoding_data>();
     std::vector<Dims> d;
     for (int i = 0; i < n_defs; i++) d.push_back(Dims{defs[i].w, defs[i].h});
-    std::string msg = Encoding::encode(grid, w, h, d, enc->enc);
-    if (!msg.empty()) { delete enc; return TSS_E_INVALID; }
-    enc->grid.assign(grid, grid + (size_t)w * h);
+    std::string msg = Encoding::encode(grid, w, h, d, data->enc);
+    if (!msg.empty()) return TSS_E_INVALID;
+    data->grid.assign(grid, grid + (size_t)w * h);
+    tss_encoding* enc = new (std::nothrow) tss_encoding();
+    if (!enc) return TSS_E_INVALID;
+    enc->d = std::move(data);
     *out = enc;
     return TSS_OK;
 }
@@ -72,29 +70,29 @@ void tss_encoding_destroy(tss_encoding* enc) { delete enc; }
 
 int tss_encoding_sizes(const tss_encoding* enc, int32_t* n_vars, int32_t* n_clauses, int64_t* n_lits, int32_t* n_dims) {
     if (!enc) return TSS_E_INVALID;
-    if (n_vars) *n_vars = enc->enc.base.n_vars;
-    if (n_clauses) *n_clauses = enc->enc.base.n_clauses();
-    if (n_lits) *n_lits = (int64_t)enc->enc.base.lits.size();
-    if (n_dims) *n_dims = enc->enc.K();
+    if (n_vars) *n_vars = enc->d->enc.base.n_vars;
+    if (n_clauses) *n_clauses = enc->d->enc.base.n_clauses();
+    if (n_lits) *n_lits = (int64_t)enc->d->enc.base.lits.size();
+    if (n_dims) *n_dims = enc->d->enc.K();
     return TSS_OK;
 }
 
 int tss_encoding_dims(const tss_encoding* enc, tss_dims* out_dims) {
     if (!enc || !out_dims) return TSS_E_INVALID;
-    for (int k = 0; k < enc->enc.K(); k++) out_dims[k] = tss_dims{enc->enc.keys[k].w, enc->enc.keys[k].h};
+    for (int k = 0; k < enc->d->enc.K(); k++) out_dims[k] = tss_dims{enc->d->enc.keys[k].w, enc->d->enc.keys[k].h};
     return TSS_OK;
 }
 
 int tss_encoding_var_maps(const tss_encoding* enc, int32_t* plat_var, int32_t* terr_var) {
     if (!enc) return TSS_E_INVALID;
-    if (plat_var) std::memcpy(plat_var, enc->enc.plat_var.data(), enc->enc.plat_var.size() * sizeof(int32_t));
-    if (terr_var) std::memcpy(terr_var, enc->enc.terr_var.data(), enc->enc.terr_var.size() * sizeof(int32_t));
+    if (plat_var) std::memcpy(plat_var, enc->d->enc.plat_var.data(), enc->d->enc.plat_var.size() * sizeof(int32_t));
+    if (terr_var) std::memcpy(terr_var, enc->d->enc.terr_var.data(), enc->d->enc.terr_var.size() * sizeof(int32_t));
     return TSS_OK;
 }
 
 int tss_encoding_cnf(const tss_encoding* enc, int32_t* lits, uint32_t* offsets) {
     if (!enc || !offsets) return TSS_E_INVALID;
-    const Cnf& f = enc->enc.base;
+    const Cnf& f = enc->d->enc.base;
     if (lits) std::memcpy(lits, f.lits.data(), f.lits.size() * sizeof(int32_t));
     std::memcpy(offsets, f.offsets.data(), f.offsets.size() * sizeof(uint32_t));
     return TSS_OK;
@@ -109,13 +107,14 @@ int tss_encoding_with_limits(const tss_encoding* enc, const int32_t* card, int32
     lim.weights = entries(weights, n_weights);
     lim.has_weight_limit = has_weight_limit != 0;
     lim.weight_limit = (long)weight_limit;
-    Cnf f = enc->enc.with_limits(lim);
+    Cnf f = enc->d->enc.with_limits(lim);
     if (n_vars) *n_vars = f.n_vars;
     if (n_clauses) *n_clauses = f.n_clauses();
     if (n_lits) *n_lits = (int64_t)f.lits.size();
     if (lits && offsets) {
         std::memcpy(lits, f.lits.data(), f.lits.size() * sizeof(int32_t));
         std::memcpy(offsets, f.offsets.data(), f.offsets.size() * sizeof(uint32_t));
+        instance_record(enc->d, lim, f);   // the solver that receives these clauses can find its instance again (tss_instance_find)
     }
     return TSS_OK;
 }
@@ -123,7 +122,7 @@ int tss_encoding_with_limits(const tss_encoding* enc, const int32_t* card, int32
 int tss_layout_from_assignment(const tss_encoding* enc, const uint8_t* assignment, int32_t n_assignment, tss_platform* out, int32_t cap,
                                int32_t* n_out) {
     if (!enc || !assignment || !n_out) return TSS_E_INVALID;
-    std::vector<tss_platform> p = enc->enc.layout_from_assignment(assignment, n_assignment);
+    std::vector<tss_platform> p = enc->d->enc.layout_from_assignment(assignment, n_assignment);
     *n_out = (int32_t)p.size();
     if ((int32_t)p.size() > cap || (!out && !p.empty())) return TSS_E_CAPACITY;
     if (!p.empty()) std::memcpy(out, p.data(), p.size() * sizeof(tss_platform));
@@ -133,7 +132,7 @@ int tss_layout_from_assignment(const tss_encoding* enc, const uint8_t* assignmen
 int tss_layout_to_assignment(tss_engine* e, const tss_encoding* enc, const tss_platform* plats, int32_t n_plats, uint8_t* assignment) {
     if (!e) return TSS_E_INVALID;
     if (!enc || !assignment || n_plats < 0 || (!plats && n_plats > 0)) return e->fail(TSS_E_INVALID, "tss_layout_to_assignment: bad arguments");
-    return tss_layout_to_assignment_impl(e, enc->enc, enc->grid.data(), plats, n_plats, assignment);
+    return tss_layout_to_assignment_impl(e, enc->d->enc, enc->d->grid.data(), plats, n_plats, assignment);
 }
 
 int tss_layout_trivial_optimization(const uint8_t* grid, int32_t w, int32_t h, tss_platform* plats, int32_t n) {

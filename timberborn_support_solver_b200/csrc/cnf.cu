@@ -196,6 +196,8 @@ int tss_cnf_upload(tss_engine* e, const int32_t* lits, const uint32_t* offsets, 
     return TSS_OK;
 }
 
+int tss_cnf_num_vars(const tss_cnf* c) { return c ? c->n_vars : TSS_E_INVALID; }
+
 void tss_cnf_destroy(tss_cnf* c) {
     if (!c) return;
     cudaFree(c->lits);

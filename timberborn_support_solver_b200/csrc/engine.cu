@@ -34,6 +34,9 @@ int sls_run_h16(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, 
                 int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
                 int noise_pct, unsigned long long* totals_dev);
 int run_peaks(tss_engine* e, double* out, int n_out);
+// lb.cu — packing lower bound
+int lb_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::vector<int2>& key_dims, uint64_t seed, int restarts,
+           uint32_t* out_rows32, int* out_count);
 // lns.cu — window decomposition for grids larger than 32x32
 struct LnsSearch;
 int lns_create(tss_engine* e, const uint8_t* grid, int w, int h, int seeds, uint64_t seed, uint32_t chain_offset, int noise, LnsSearch** out);
@@ -1413,6 +1416,39 @@ int tss_solve_upper_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t
         tss_search_destroy(s);
     }
     return rc != TSS_OK ? rc : result;
+}
+
+int tss_lower_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs, uint64_t seed,
+                    int32_t restarts, int32_t* out_xy, int32_t cap, int32_t* n_out) {
+    if (!e) return TSS_E_INVALID;
+    if (n_out) *n_out = 0;
+    if (!grid || !n_out || w <= 0 || h <= 0 || (!defs && n_defs > 0) || cap < 0 || (cap > 0 && !out_xy)) return e->fail(TSS_E_INVALID, "tss_lower_bound: bad arguments");
+    if (w > 32 || h > 32) return e->fail(TSS_E_UNSUPPORTED, "tss_lower_bound: grids larger than 32x32 are not supported");
+    bool has_1x1 = n_defs == 0;
+    for (int i = 0; i < n_defs; i++) {
+        if (defs[i].w <= 0 || defs[i].h <= 0) return e->fail(TSS_E_INVALID, "tss_lower_bound: empty platform dimensions");
+        has_1x1 = has_1x1 || (defs[i].w == 1 && defs[i].h == 1);
+    }
+    if (!has_1x1) return e->fail(TSS_E_INVALID, "the platform set must contain 1x1 (src/encoder.rs:564-566)");
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    std::vector<int2> key_dims;
+    std::vector<tss_platform> key_proto;
+    const tss_dims one{1, 1};
+    build_keys(n_defs ? defs : &one, n_defs ? n_defs : 1, key_dims, key_proto);
+    uint32_t rows[32] = {0}, pack[32];
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            if (grid[(size_t)y * w + x]) rows[y] |= 1u << x;
+    int count = 0;
+    int rc = lb_run(e, rows, w, h, key_dims, seed, restarts, pack, &count);
+    if (rc) return rc;
+    *n_out = count;
+    if (count > cap) return cap == 0 ? TSS_OK : e->fail(TSS_E_CAPACITY, "tss_lower_bound: need room for %d tiles", count);
+    int n = 0;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            if ((pack[y] >> x) & 1u) { out_xy[2 * n] = x; out_xy[2 * n + 1] = y; n++; }
+    return TSS_OK;
 }
 
 int tss_solve_batch(tss_engine* e, const uint8_t* grids, int32_t w, int32_t h, int64_t n, uint64_t seed, int64_t steps,

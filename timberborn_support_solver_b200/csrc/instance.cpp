@@ -1,0 +1,152 @@
+// The solver side of the drop-in boundary (include/tss.h "instance bridge"): what a `Solve + Interrupt` implementation needs
+// to answer `solve()` from the GPU when all it was given is a CNF (crates/repl/src/solver_runner.rs:8-20,
+// crates/gui/src/solver_backend.rs:69-97).  Host C++ only; every GPU step goes through the public C ABI, so this file is
+// also the reference for the call sequence of the Rust shim (rust/tss/src/lib.rs) and of tools/tss_repl.cpp.
+#include <algorithm>
+#include <cstring>
+#include <deque>
+#include <mutex>
+
+#include "encoding_handle.hpp"
+#include "engine.hpp"
+
+using namespace tss;
+
+namespace {
+
+struct Record {
+    std::shared_ptr<const tss_encoding_data> d;
+    PlatformLimits limits;
+    Cnf cnf;   // what with_limits returned (base clauses first, then the lowered limits)
+};
+std::mutex g_mutex;
+std::deque<Record> g_records;   // most recent first
+constexpr size_t kMaxRecords = 8;
+
+bool same_prefix(const Cnf& base, const int32_t* lits, const uint32_t* offsets, int n_clauses) {
+    if (base.n_clauses() > n_clauses) return false;
+    const size_t nl = base.lits.size();
+    if (offsets[base.n_clauses()] != nl) return false;
+    return std::memcmp(base.offsets.data(), offsets, sizeof(uint32_t) * base.offsets.size()) == 0 &&
+           (nl == 0 || std::memcmp(base.lits.data(), lits, sizeof(int32_t) * nl) == 0);
+}
+
+}  // namespace
+
+namespace tss {
+void instance_record(const std::shared_ptr<const tss_encoding_data>& d, const PlatformLimits& limits, const Cnf& cnf) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    g_records.push_front(Record{d, limits, cnf});
+    if (g_records.size() > kMaxRecords) g_records.pop_back();
+}
+}  // namespace tss
+
+extern "C" {
+
+int tss_cnf_num_vars(const tss_cnf* c);   // cnf.cu
+
+int tss_instance_find(const int32_t* lits, const uint32_t* offsets, int32_t n_clauses, int32_t n_vars, tss_encoding** enc_out,
+                      tss_instance_info* info, int32_t* weights, int32_t weights_cap) {
+    if (!offsets || n_clauses < 0 || !enc_out || !info || (offsets[n_clauses] > 0 && !lits)) return TSS_E_INVALID;
+    *enc_out = nullptr;
+    std::memset(info, 0, sizeof *info);
+    std::lock_guard<std::mutex> lock(g_mutex);
+    const Record* hit = nullptr;
+    bool exact = false;
+    for (const Record& r : g_records) {   // the whole CNF as recorded (most recent first) ...
+        if (r.cnf.n_vars == n_vars && r.cnf.n_clauses() == n_clauses && same_prefix(r.cnf, lits, offsets, n_clauses)) { hit = &r; exact = true; break; }
+    }
+    if (!hit)
+        for (const Record& r : g_records) {   // ... else the same base clauses (limits lowered by someone else's encoder): limits of the latest record
+            if (r.d->enc.base.n_vars <= n_vars && same_prefix(r.d->enc.base, lits, offsets, n_clauses)) { hit = &r; break; }
+        }
+    if (!hit) return TSS_UNKNOWN;
+    tss_encoding* enc = new (std::nothrow) tss_encoding();
+    if (!enc) return TSS_E_INVALID;
+    enc->d = hit->d;
+    *enc_out = enc;
+    info->w = hit->d->enc.w;
+    info->h = hit->d->enc.h;
+    info->n_defs = (int32_t)hit->d->enc.defs.size();
+    info->card_limit_1x1 = -1;
+    for (const auto& c : hit->limits.card_limits) {
+        if (c.def.w == 1 && c.def.h == 1) info->card_limit_1x1 = (int32_t)c.value;
+        else info->n_other_card_limits++;
+    }
+    info->has_weight_limit = hit->limits.has_weight_limit;
+    info->weight_limit = hit->limits.weight_limit;
+    info->n_weights = (int32_t)hit->limits.weights.size();
+    info->exact = exact;
+    if (weights)
+        for (int i = 0; i < info->n_weights && i < weights_cap; i++) {
+            weights[3 * i] = hit->limits.weights[(size_t)i].def.w;
+            weights[3 * i + 1] = hit->limits.weights[(size_t)i].def.h;
+            weights[3 * i + 2] = (int32_t)hit->limits.weights[(size_t)i].value;
+        }
+    return TSS_SAT;
+}
+
+int tss_encoding_terrain(const tss_encoding* enc, uint8_t* grid, size_t cap, int32_t* w, int32_t* h) {
+    if (!enc || !w || !h) return TSS_E_INVALID;
+    *w = enc->d->enc.w;
+    *h = enc->d->enc.h;
+    if (!grid || cap < enc->d->grid.size()) return TSS_E_CAPACITY;
+    std::memcpy(grid, enc->d->grid.data(), enc->d->grid.size());
+    return TSS_OK;
+}
+
+int tss_encoding_defs(const tss_encoding* enc, tss_dims* defs, int32_t cap, int32_t* n) {
+    if (!enc || !n) return TSS_E_INVALID;
+    *n = (int32_t)enc->d->enc.defs.size();
+    if (!defs || cap < *n) return TSS_E_CAPACITY;
+    for (int i = 0; i < *n; i++) defs[i] = tss_dims{enc->d->enc.defs[(size_t)i].w, enc->d->enc.defs[(size_t)i].h};
+    return TSS_OK;
+}
+
+int tss_witness_for_cnf(tss_engine* e, const tss_cnf* c, const tss_encoding* enc, const tss_platform* plats, int32_t n, uint8_t* assignment) {
+    if (!e) return TSS_E_INVALID;
+    if (!c || !enc || !assignment || n < 0 || (n > 0 && !plats)) return e->fail(TSS_E_INVALID, "tss_witness_for_cnf: bad arguments");
+    const int nv = tss_cnf_num_vars(c), nb = enc->d->enc.base.n_vars;
+    if (nv < nb) return e->fail(TSS_E_INVALID, "tss_witness_for_cnf: the CNF has %d variables, the encoding %d", nv, nb);
+    // platform variables from the layout (every dims key contained in a platform, encoder.rs:449-458), terrain layers from the
+    // evaluator's support layers (kernel (a)); whatever the limits added (totalizer / PB auxiliaries) starts unassigned
+    int rc = tss_layout_to_assignment(e, enc, plats, n, assignment);
+    if (rc < 0) return rc;
+    std::memset(assignment + nb + 1, 2, (size_t)(nv - nb));
+    int32_t conflict = -1;
+    rc = tss_cnf_propagate(e, c, assignment, 1, &conflict, nullptr);   // ... and is implied: unit propagation assigns it (kernel (c))
+    if (rc < 0) return rc;
+    if (conflict >= 0) return TSS_UNKNOWN;                              // e.g. more platforms than the bound allows
+    for (int v = 1; v <= nv; v++)
+        if (assignment[v] == 2) assignment[v] = 0;
+    int32_t n_falsified = 0;
+    rc = tss_cnf_check(e, c, assignment, 1, &n_falsified, nullptr);     // the model against every clause the exact solver received
+    if (rc < 0) return rc;
+    return n_falsified == 0 ? TSS_SAT : TSS_UNKNOWN;
+}
+
+int tss_solve_instance(tss_engine* e, const tss_cnf* c, const tss_encoding* enc, const tss_instance_info* info, const int32_t* weights,
+                       uint64_t seed, int64_t give_up_steps, uint8_t* assignment) {
+    if (!e) return TSS_E_INVALID;
+    if (!c || !enc || !info || !assignment) return e->fail(TSS_E_INVALID, "tss_solve_instance: bad arguments");
+    if (info->n_other_card_limits > 0) return TSS_UNKNOWN;   // limits the search cannot steer by: leave the instance to the exact solver
+    const Encoding& E = enc->d->enc;
+    std::vector<tss_dims> defs;
+    for (const Dims& d : E.defs) defs.push_back(tss_dims{d.w, d.h});
+    std::vector<tss_platform> plats((size_t)E.w * E.h + 1);
+    int32_t n = 0;
+    const int64_t max_steps = give_up_steps > 0 ? -give_up_steps : 0;   // a SAT-like call with a give-up point (tss.h)
+    int rc;
+    if (info->has_weight_limit && info->n_weights > 0 && weights) {
+        int64_t wt = 0;
+        rc = tss_solve_min_weight(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), weights, info->n_weights, info->weight_limit, seed, 0,
+                                  give_up_steps > 0 ? give_up_steps : 0, plats.data(), (int32_t)plats.size(), &n, &wt);
+    } else {
+        rc = tss_solve_upper_bound(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), info->card_limit_1x1, seed, 0, max_steps,
+                                   plats.data(), (int32_t)plats.size(), &n);
+    }
+    if (rc != TSS_SAT) return rc;
+    return tss_witness_for_cnf(e, c, enc, plats.data(), n, assignment);
+}
+
+}  // extern "C"
