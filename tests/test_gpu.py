@@ -666,7 +666,7 @@ def test_multi_platform_solver_loop_like_the_repl(eng, fixtures):
     enc = T.Encoding.encode(T.PLATFORMS_DEFAULT, g)
     out = T.solver_loop(T.Project(T.World(g)), enc, T.PlatformLimits(), eng, exact_solver=exact, seed=2, budget_ms=0)
     assert out["proved_optimal"] and out["best"].platform_count() == 1
-    assert out["steps"][-1] == dict(bound=0, result=T.UNSAT, source="exact")
+    assert out["steps"][-1] == dict(bound=0, result=T.UNSAT, source="lower bound")      # optimum 1 = the packing lower bound: no proof needed
     assert all(s["source"] == "gpu" and s["valid"] for s in out["steps"][:-1])
 
 
