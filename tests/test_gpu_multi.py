@@ -29,7 +29,7 @@ def _worker(rank, world, tmp, out):
         hist.append((s.best_count(), s.global_best()))
     chains = s.read_chains()
     s.close()
-    # window-decomposed portfolio on a larger grid (C4 shape): every rank adopts the best layout of all ranks after each phase
+    # window-decomposed portfolio on a larger grid (C4 shape): after each phase every rank holds, per window, the best result of all ranks
     big = T.WorldGrid.synthetic(96, 80, 1, 3)
     s = eng.search(big, seed=9, n_chains=8, chain_offset=rank * 100000)
     counts = []
@@ -37,8 +37,17 @@ def _worker(rank, world, tmp, out):
         s.run(1200, 0)
         counts.append(s.global_best())
     lay = sorted((p.x, p.y) for p in s.best_layout().platforms().values())     # validated by kernel (a) inside the engine
-    out.put((rank, hist, int(chains["best"].min()), counts, lay))
     s.close()
+    single = None
+    if rank == 0:       # the same phases on ONE GPU (an engine without a communicator, rank 0's seeds): what the second GPU has to beat
+        solo = T.Engine(0)
+        s1 = solo.search(big, seed=9, n_chains=8, chain_offset=0)
+        for _ in range(5):
+            s1.run(1200, 0)
+        single = s1.best_count()
+        s1.close()
+        solo.close()
+    out.put((rank, hist, int(chains["best"].min()), counts, lay, single))
     eng.close()
 
 
@@ -56,9 +65,11 @@ def test_native_nccl_portfolio_two_gpus(tmp_path):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (_, h0, b0, c0, lay0), (_, h1, b1, c1, lay1) = res
+    (_, h0, b0, c0, lay0, single), (_, h1, b1, c1, lay1, _) = res
     assert c0 == c1 and all(b <= a for a, b in zip(c0, c0[1:])) and len(lay0) == c0[-1]   # same counts on every rank, never increasing
-    assert lay0 == lay1                                              # ... and the very same layout (the winner's, shipped by all-reduce-min)
+    assert lay0 == lay1                                              # ... and the very same layout (assembled window by window from the winners)
+    assert c0[-1] <= single, (c0, single)                            # two GPUs combine per window: at equal phases never worse than one
+    print("C4-shaped portfolio, 5 phases: two GPUs", c0, "one GPU", single)
     for (l0, g0), (l1, g1) in zip(h0, h1):
         assert g0 == g1                                             # every rank sees the same global bound after each epoch
         locals_ = [x for x in (l0, l1) if x is not None]

@@ -77,6 +77,17 @@ int comm_allreduce_min_u32(tss_engine* e, Comm* c, const uint32_t* src, uint32_t
     e->stats.kernel_launches++;
     return TSS_OK;
 }
+// in-stream all-reduce-SUM of n uint32 words: src -> dst.  The window-decomposed portfolio assembles its next layout this way:
+// every bit of the result is contributed by exactly one rank (the winner of that window; rank 0 for the frozen supports), so
+// the sum is a bitwise OR without carries.
+int comm_allreduce_sum_u32(tss_engine* e, Comm* c, const uint32_t* src, uint32_t* dst, int n) {
+    if (!c || c->world <= 1) return TSS_OK;
+    NcclApi* api = nccl_api();
+    int r = api->AllReduce(src, dst, (size_t)n, 3 /* ncclUint32 */, 0 /* ncclSum */, c->comm, e->stream);
+    if (r != 0) return e->fail(TSS_E_CUDA, "ncclAllReduce failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?");
+    e->stats.kernel_launches++;
+    return TSS_OK;
+}
 int comm_rank(const Comm* c) { return c ? c->rank : 0; }
 int comm_world(const Comm* c) { return c ? c->world : 1; }
 

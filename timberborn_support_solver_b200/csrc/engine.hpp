@@ -17,6 +17,7 @@ struct Comm;
 void comm_destroy(Comm* c);
 int comm_allreduce_min(tss_engine* e, Comm* c, int* dev, int n);  // in-stream ncclAllReduce(min) on device ints
 int comm_allreduce_min_u32(tss_engine* e, Comm* c, const uint32_t* src, uint32_t* dst, int n);
+int comm_allreduce_sum_u32(tss_engine* e, Comm* c, const uint32_t* src, uint32_t* dst, int n);
 int comm_rank(const Comm* c);
 int comm_world(const Comm* c);
 }  // namespace tss

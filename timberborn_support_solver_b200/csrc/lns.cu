@@ -111,21 +111,30 @@ __global__ void popcount_kernel(const uint32_t* __restrict__ X, int nw, int* __r
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
 }
 
-// ---- multi-GPU portfolio: after a phase every rank adopts the best layout of all ranks, all in-stream.
-// key = count * 64 + rank (unique per rank); all-reduce-min(key) names the winner; every rank then contributes its
-// layout if it is the winner and all-ones otherwise, so a second all-reduce-min (u32) over the 8 KB bitboard delivers
-// the winner's layout everywhere without a host-known broadcast root.
-__global__ void share_key_kernel(const int* __restrict__ count, int rank, uint32_t* __restrict__ key) { key[0] = (uint32_t)count[0] * 64u + (uint32_t)rank; }
-__global__ void share_select_kernel(const uint32_t* __restrict__ S, const uint32_t* __restrict__ key, const uint32_t* __restrict__ gkey, int nw,
-                                    uint32_t* __restrict__ out) {
+// ---- multi-GPU portfolio: windows are independent sub-problems within a phase (cores never interact), and every rank starts
+// the phase from the same layout with the same window grid but its own chain seeds.  So the ranks' results COMBINE: per window
+// the rank whose best chain holds the fewest core supports wins (key = count * 64 + rank, one all-reduce-min over the window
+// keys), every rank writes the cores of the windows it won into a zeroed bitboard (rank 0 adds the frozen supports, which
+// are the same everywhere), and one all-reduce-sum — each bit has exactly one contributor, so the sum is an OR — gives every
+// rank the same next layout: per window the best of (ranks x chains) attempts.  All in-stream, no host round trip.
+__global__ void window_keys_kernel(const int2* __restrict__ best, int n_windows, int rank, uint32_t* __restrict__ keys) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nw) out[i] = key[0] == gkey[0] ? S[i] : 0xffffffffu;
+    if (i < n_windows) keys[i] = best[i].y >= 0 ? (uint32_t)best[i].x * 64u + (uint32_t)rank : 0xffffffffu;
 }
-__global__ void share_adopt_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ gkey, int nw, uint32_t* __restrict__ S,
-                                   int* __restrict__ count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nw) S[i] = in[i];
-    if (i == 0) count[0] = (int)(gkey[0] >> 6);
+// one warp per window: OR the best chain's core supports into `G` if this rank won the window
+__global__ void contribute_windows_kernel(uint32_t* __restrict__ G, int h, int wpr, int ox, int oy, int nwx, int n_windows, const int2* __restrict__ best,
+                                          const sls::ChainState* __restrict__ states, const uint32_t* __restrict__ gkeys, int rank) {
+    const int win = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (win >= n_windows) return;
+    const int chain = best[win].y;
+    if (chain < 0 || (int)(gkeys[win] & 63u) != rank || lane < CORE_LO || lane >= CORE_HI) return;
+    const int gx0 = ox + 32 * (win % nwx), gy = oy + 32 * (win / nwx) + lane;
+    if (gy < 0 || gy >= h) return;
+    const uint32_t row = states[chain].bestS[lane] & CORE_COLS;
+    const int wq = gx0 >> 5, sh = gx0 & 31;
+    const uint32_t val_lo = row << sh, val_hi = sh ? (row >> (32 - sh)) : 0u;
+    if (wq >= 0 && wq < wpr && val_lo) atomicOr(&G[gy * wpr + wq], val_lo);
+    if (sh && wq + 1 >= 0 && wq + 1 < wpr && val_hi) atomicOr(&G[gy * wpr + wq + 1], val_hi);
 }
 
 }  // namespace lns
@@ -142,7 +151,8 @@ struct LnsSearch {
     int* bounds = nullptr;
     unsigned long long* totals = nullptr;
     int* count_dev = nullptr;
-    uint32_t* key_dev = nullptr;                 // [2]: this rank's (count, rank) key and the global minimum
+    uint32_t* key_dev = nullptr;                 // [2 * max_windows]: this rank's per-window (count, rank) keys and their minima over the ranks
+    uint32_t* G = nullptr;                       // this rank's contribution to the next layout (multi-GPU portfolio)
     int* count_host = nullptr;                   // pinned
     unsigned long long* totals_host = nullptr;   // pinned [3]
 };
@@ -150,7 +160,7 @@ struct LnsSearch {
 void lns_destroy(LnsSearch* s) {
     if (!s) return;
     cudaFree(s->C); cudaFree(s->S); cudaFree(s->F); cudaFree(s->T); cudaFree(s->rows_win); cudaFree(s->need_win); cudaFree(s->tabs);
-    cudaFree(s->states); cudaFree(s->best); cudaFree(s->bounds); cudaFree(s->totals); cudaFree(s->count_dev); cudaFree(s->key_dev);
+    cudaFree(s->states); cudaFree(s->best); cudaFree(s->bounds); cudaFree(s->totals); cudaFree(s->count_dev); cudaFree(s->key_dev); cudaFree(s->G);
     if (s->count_host) cudaFreeHost(s->count_host);
     if (s->totals_host) cudaFreeHost(s->totals_host);
     delete s;
@@ -169,7 +179,7 @@ int lns_create(tss_engine* e, const uint8_t* grid, int w, int h, int seeds, uint
     A((void**)&s->rows_win, sizeof(uint32_t) * 32 * (size_t)s->max_windows); A((void**)&s->need_win, sizeof(uint32_t) * 32 * (size_t)s->max_windows);
     A((void**)&s->tabs, sizeof(uint2) * 1024 * (size_t)s->max_windows); A((void**)&s->states, sizeof(sls::ChainState) * nch);
     A((void**)&s->best, sizeof(int2) * (size_t)s->max_windows); A((void**)&s->bounds, sizeof(int) * (size_t)s->max_windows);
-    A((void**)&s->totals, sizeof(unsigned long long) * 3); A((void**)&s->count_dev, sizeof(int)); A((void**)&s->key_dev, sizeof(uint32_t) * 2);
+    A((void**)&s->totals, sizeof(unsigned long long) * 3); A((void**)&s->count_dev, sizeof(int)); A((void**)&s->key_dev, sizeof(uint32_t) * 2 * (size_t)s->max_windows); A((void**)&s->G, nwb);
     if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->count_host, sizeof(int), cudaHostAllocDefault);
     if (err == cudaSuccess) err = cudaHostAlloc((void**)&s->totals_host, sizeof(unsigned long long) * 3, cudaHostAllocDefault);
     // the start layout: a support under every ceiling tile (trivially complete)
@@ -207,22 +217,28 @@ int lns_phase(tss_engine* e, LnsSearch* s, long long steps, bool share) {
     if (rc) return rc;
     rc = sls_best_reduce(e, s->states, s->seeds, n_chains, n_windows, s->best, s->bounds, nullptr);
     if (rc) return rc;
-    lns::writeback_windows_kernel<<<(n_windows * 32 + 127) / 128, 128, 0, e->stream>>>(s->S, s->h, s->wpr, ox, oy, nwx, n_windows, s->best, s->states);
+    const bool combine = share && e->comm && comm_world(e->comm) > 1;
+    if (!combine) {
+        lns::writeback_windows_kernel<<<(n_windows * 32 + 127) / 128, 128, 0, e->stream>>>(s->S, s->h, s->wpr, ox, oy, nwx, n_windows, s->best, s->states);
+        e->stats.kernel_launches++;
+    } else {  // per window the best of all ranks (see the kernels above)
+        const int rank = comm_rank(e->comm);
+        uint32_t *keys = s->key_dev, *gkeys = s->key_dev + s->max_windows;
+        lns::window_keys_kernel<<<(n_windows + 127) / 128, 128, 0, e->stream>>>(s->best, n_windows, rank, keys);
+        rc = comm_allreduce_min_u32(e, e->comm, keys, gkeys, n_windows);
+        if (rc) return rc;
+        if (rank == 0) lns::gap_supports_kernel<<<gb, tb, 0, e->stream>>>(s->S, s->C, s->G, s->nw, s->wpr, oy, colmask);   // the frozen supports, once
+        else TSS_CUDA(e, cudaMemsetAsync(s->G, 0, sizeof(uint32_t) * (size_t)s->nw, e->stream));
+        lns::contribute_windows_kernel<<<(n_windows * 32 + 127) / 128, 128, 0, e->stream>>>(s->G, s->h, s->wpr, ox, oy, nwx, n_windows, s->best, s->states, gkeys, rank);
+        TSS_CHECK_LAUNCH(e);
+        rc = comm_allreduce_sum_u32(e, e->comm, s->G, s->S, s->nw);
+        if (rc) return rc;
+        e->stats.kernel_launches += 3;
+    }
     TSS_CUDA(e, cudaMemsetAsync(s->count_dev, 0, sizeof(int), e->stream));
     lns::popcount_kernel<<<32, 256, 0, e->stream>>>(s->S, s->nw, s->count_dev);
     TSS_CHECK_LAUNCH(e);
-    e->stats.kernel_launches += 2;
-    if (share && e->comm && comm_world(e->comm) > 1) {  // every rank continues from the best layout of all ranks
-        lns::share_key_kernel<<<1, 1, 0, e->stream>>>(s->count_dev, comm_rank(e->comm), s->key_dev);
-        rc = comm_allreduce_min_u32(e, e->comm, s->key_dev, s->key_dev + 1, 1);
-        if (rc) return rc;
-        lns::share_select_kernel<<<gb, tb, 0, e->stream>>>(s->S, s->key_dev, s->key_dev + 1, s->nw, s->F);
-        rc = comm_allreduce_min_u32(e, e->comm, s->F, s->T, s->nw);
-        if (rc) return rc;
-        lns::share_adopt_kernel<<<gb, tb, 0, e->stream>>>(s->T, s->key_dev + 1, s->nw, s->S, s->count_dev);
-        TSS_CHECK_LAUNCH(e);
-        e->stats.kernel_launches += 3;
-    }
+    e->stats.kernel_launches++;
     TSS_CUDA(e, cudaMemcpyAsync(s->count_host, s->count_dev, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     TSS_CUDA(e, cudaMemcpyAsync(s->totals_host, s->totals, sizeof(unsigned long long) * 3, cudaMemcpyDeviceToHost, e->stream));
     s->phase++;
