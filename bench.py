@@ -236,8 +236,9 @@ def run_c5(args):
     torch, dist, world, rank, local = setup_dist()
     import timberborn_support_solver_b200 as T
     eng = T.Engine(local)
+    from timberborn_support_solver_b200.portfolio import shard_range
     n_total = args.terrains
-    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    lo, hi = shard_range(n_total, rank, world)
     lib = T.load()
     grids = np.zeros((hi - lo, 32, 32), np.uint8)
     for i, t in enumerate(range(lo, hi)):
@@ -263,7 +264,7 @@ def run_c5(args):
     # final gather: 4 bytes per terrain
     cd = torch.from_numpy(counts).cuda()
     if world > 1:
-        sizes = [(r + 1) * n_total // world - r * n_total // world for r in range(world)]
+        sizes = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
         parts = [torch.empty(sz, dtype=torch.int32, device="cuda") for sz in sizes]
         dist.all_gather(parts, cd)
         allc = torch.cat(parts)
@@ -395,8 +396,9 @@ def side_c5(eng, torch, dist, world, rank, n_total, steps):
     host buffers.  Returns the dict rank 0 reports (None elsewhere)."""
     import ctypes as C
     import timberborn_support_solver_b200 as T
+    from timberborn_support_solver_b200.portfolio import shard_range
     lib = T.load()
-    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    lo, hi = shard_range(n_total, rank, world)          # contiguous, balanced ranges of terrains (SURVEY.md §8e)
     grids = np.zeros((hi - lo, 32, 32), np.uint8)
     for i, t in enumerate(range(lo, hi)):
         lib.tss_world_synthetic(32, 32, 1, t, int(0.7 * (1 << 24)), grids[i].ctypes.data_as(C.POINTER(C.c_uint8)))
