@@ -26,7 +26,11 @@
 //     the evaluation order, and ties go to the lowest index as the spec demands.
 // ncu (profiles/r1_sls_t16_kernel.md): 73 warp instructions per chain step, ALU pipe 75 %, issue slots 72 %, shared-memory
 // wavefronts 17.8 per chain step (a third of them bank-conflict replays of the random 8-byte reach-table reads).
-// Tried and dropped: the two high count planes in global memory for 4 CTAs per SM (slower: 277 vs 335 G candidates/s);
+// r2: windows as one byte per row assembled with PRMT (the per-row `& 0x7f` and the multiply-packs are gone): 73 -> 65 warp
+// instructions per chain step, 23.7 -> 24.6 G flips/s.  The kernel sits at ~75 % of BOTH the ALU pipe and the shared-memory pipe
+// (0.75 wavefronts per clock and SM), which is why more resident warps do not help:
+// Tried and dropped: the two high count planes in global memory for 4 CTAs per SM (r1: 277 vs 335 G candidates/s; r2, with a
+// per-chain "never carried into them" flag so that they are not even read: 22.2 G flips/s at 3 CTAs, 20.4 G at 4 CTAs vs 24.6 G);
 // skipping their shared-memory loads until some count reaches 8 (326 vs 334 G: the branches cost more than the loads).
 #include "engine.hpp"
 #include "sls_spec.hpp"
@@ -69,7 +73,7 @@ __device__ __forceinline__ void flip(Smem& sm, int tid, int v, uint32_t& rowmask
     uint32_t nz = 0;
 #pragma unroll
     for (int j = 0; j < 7; j++) {
-        const uint32_t m7 = (j < 4 ? win.x >> (7 * j) : win.y >> (7 * (j - 4))) & 0x7fu;
+        const uint32_t m7 = (j < 4 ? win.x >> (8 * j) : win.y >> (8 * (j - 4))) & 0xffu;
         const int off = (j - 3) * NT;
         uint32_t m = m7 << x;
         uint32_t a0 = p[B_C0 * BOARD + off], a1 = p[B_C1 * BOARD + off], a2 = p[B_C2 * BOARD + off], t;
@@ -109,6 +113,11 @@ __device__ __forceinline__ constexpr int cell_start(int r) { return r <= 4 ? r *
 __device__ __forceinline__ constexpr int iabs(int a) { return a < 0 ? -a : a; }
 __device__ __forceinline__ constexpr int cell_index(int dx, int dy) { return cell_start(dy + 3) + dx + (3 - iabs(dy)); }
 __device__ __forceinline__ uint32_t shift_static(uint32_t v, int s) { return s >= 0 ? v << s : v >> (-s); }
+// low bytes of four / three words as one word (the fourth byte of pack3 is a copy of a's: it only ever meets a zero table byte)
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+__device__ __forceinline__ uint32_t pack3(uint32_t a, uint32_t b, uint32_t c) { return __byte_perm(__byte_perm(a, b, 0x0040), c, 0x0410); }
 
 // rows of the support bitboard of a site list (rare path: recording a best layout, writing the state back)
 __device__ __noinline__ void list_to_rows(const uint32_t* sl, size_t stride, int k, uint32_t* out32) {
@@ -127,15 +136,15 @@ __device__ __noinline__ void list_to_rows(const uint32_t* sl, size_t stride, int
 template <int DX, int DY>
 __device__ __forceinline__ uint32_t add_key(const Smem& sm, const uint32_t (&P)[13], const uint2* tabt, uint2 wt, uint32_t fresh_lo, uint32_t fresh_hi,
                                             uint32_t hs, uint32_t gmul) {
-    constexpr int cell = cell_index(DX, DY), bit = 7 * (DY + 3) + DX + 3;
+    constexpr int cell = cell_index(DX, DY), bit = 8 * (DY + 3) + DX + 3;   // position in the byte-per-row window (rows 0-3 / 4-6)
     const uint2 win = tabt[DY * 32 + DX];
-    const uint32_t lo = (P[DY + 6] * 128u + P[DY + 5]) * 16384u + (P[DY + 4] * 128u + P[DY + 3]);   // (tree, not Horner: shorter dependency chains)
-    const uint32_t hi = P[DY + 9] * 16384u + (P[DY + 8] * 128u + P[DY + 7]);
+    const uint32_t lo = pack4(P[DY + 3], P[DY + 4], P[DY + 5], P[DY + 6]);
+    const uint32_t hi = pack3(P[DY + 7], P[DY + 8], P[DY + 9]);
     const uint32_t g = (uint32_t)(__popc(lo & win.x) + __popc(hi & win.y));
     const uint32_t tie = ((hs * ((2u * cell + 1u) * K2)) >> 11) & 0x1fffe0u;             // tie_add(hs, cell) << 5
-    const uint32_t fresh = shift_static(bit < 28 ? fresh_lo : fresh_hi, 30 - (bit < 28 ? bit : bit - 28)) & TABU_BIT;  // (all zero in a noise step)
+    const uint32_t fresh = shift_static(bit < 32 ? fresh_lo : fresh_hi, 30 - (bit < 32 ? bit : bit - 32)) & TABU_BIT;  // (all zero in a noise step)
     const uint32_t key = (fresh | tie) + g * gmul + ((1u << 21) | (31u - cell));   // gmul = 1 << 21, or 0 in a noise step
-    const bool valid = ((bit < 28 ? wt.x >> bit : wt.y >> (bit - 28)) & 1u) != 0;
+    const bool valid = ((bit < 32 ? wt.x >> bit : wt.y >> (bit - 32)) & 1u) != 0;
     return valid ? key : 0u;
 }
 
@@ -145,7 +154,7 @@ __device__ __forceinline__ uint32_t add_column(const Smem& sm, const uint32_t (&
     constexpr int M = 3 - iabs(DX);
     uint32_t P[13];
 #pragma unroll
-    for (int j = 3 - M; j <= 9 + M; j++) P[j] = (R[j] >> (DX + 3)) & 0x7fu;
+    for (int j = 3 - M; j <= 9 + M; j++) P[j] = R[j] >> (DX + 3);   // (only the low byte is used; its bit 7 meets a zero table bit)
     uint32_t mx = add_key<DX, 0>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, gmul);
     if (M >= 1) {
         mx = max(mx, add_key<DX, (M >= 1 ? -1 : 0)>(sm, P, tabt, wt, fresh_lo, fresh_hi, hs, gmul));
@@ -182,6 +191,10 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
             s = rtabs[(size_t)terrain * 1024 + v];
             const int x = v & 31, sh = x < 3 ? 3 - x : 0;  // table windows are anchored at max(x-3, 0): re-anchor at x-3
             s = make_uint2(s.x << sh, s.y << sh);
+            // ... and spread the 7-bit rows to one BYTE per row (rows 0-3 in .x, rows 4-6 in .y): windows cut out of the boards
+            // are then assembled with byte permutes, and bit 7 of every byte (zero here) masks whatever the cut left there
+            s = make_uint2((s.x & 0x7fu) | ((s.x & 0x3f80u) << 1) | ((s.x & 0x1fc000u) << 2) | ((s.x & 0xfe00000u) << 3),
+                           (s.y & 0x7fu) | ((s.y & 0x3f80u) << 1) | ((s.y & 0x1fc000u) << 2));
         }
         sm.tab[i] = s;
     }
@@ -248,9 +261,9 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
                     const uint32_t* p = Ob + (v >> 5) * NT;
                     uint32_t r7[7];
 #pragma unroll
-                    for (int j = 0; j < 7; j++) r7[j] = (p[(j - 3) * NT] >> x) & 0x7fu;
-                    const uint32_t lo = (r7[3] * 128u + r7[2]) * 16384u + (r7[1] * 128u + r7[0]);
-                    const uint32_t hi = r7[6] * 16384u + (r7[5] * 128u + r7[4]);
+                    for (int j = 0; j < 7; j++) r7[j] = p[(j - 3) * NT] >> x;
+                    const uint32_t lo = pack4(r7[0], r7[1], r7[2], r7[3]);
+                    const uint32_t hi = pack3(r7[4], r7[5], r7[6]);
                     const uint32_t loss = (uint32_t)(__popc(lo & win.x) + __popc(hi & win.y));
                     const uint32_t tie = ((hs * mult) >> 7) & 0x1fffe00u;  // tie_remove(hs, i) << 9
                     const uint32_t young = (stephi - e) < young_below ? TABU_BIT : 0u;
@@ -277,14 +290,14 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
 #pragma unroll
                 for (int j = 0; j < 13; j++) R[j] = (Up[(j - 6) * NT] << 3) >> x;
                 const bool noise = ((hs >> 10) & 127u) < nq7;
-                uint32_t tw_lo = 0, tw_hi = 0;  // sites removed fewer than `ten` steps ago, as a window around t (rows 0-3 / 4-6)
+                uint32_t tw_lo = 0, tw_hi = 0;  // sites removed fewer than `ten` steps ago, as a byte-per-row window around t (rows 0-3 / 4-6)
                 for (int j = 0; j < ten; j++) {
                     const uint32_t e = sm.ring[(step - (uint32_t)j) & 31u][tid];
                     const int dx3 = (int)(e & 31u) - x + 3, dy3 = (int)(e >> 5) - y + 3;
                     if ((unsigned)dx3 < 7u && (unsigned)dy3 < 7u) {
-                        const int bit = 7 * dy3 + dx3;
-                        tw_lo |= shl_clamped(1u, bit);       // (bits 28..31 of tw_lo are never looked at)
-                        tw_hi |= shl_clamped(1u, bit - 28);
+                        const int bit = 8 * dy3 + dx3;       // byte-per-row window, like the reach table
+                        tw_lo |= shl_clamped(1u, bit);
+                        tw_hi |= shl_clamped(1u, bit - 32);
                     }
                 }
                 const uint32_t fresh_lo = noise ? 0u : ~tw_lo, fresh_hi = noise ? 0u : ~tw_hi;
