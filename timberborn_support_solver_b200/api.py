@@ -643,6 +643,17 @@ class Engine:
                                              _ptr(out, C.c_int32), len(out), C.byref(n)))
         return [(int(x), int(y)) for x, y in out[: n.value]]
 
+    def lower_bound_lp(self, grid: WorldGrid, defs=PLATFORMS_DEFAULT[:1], max_pivots=0):
+        """Fractional packing lower bound (tss_lower_bound_lp), certified in integers.
+        -> dict(bound, weights int32[h, w], total, max_load, pivots, optimal, constraints); bound = ceil(total / max_load)."""
+        defs = list(defs)
+        wts = np.zeros((grid.height, grid.width), np.int32)
+        total, max_load, bound = C.c_int64(), C.c_int64(), C.c_int32()
+        info = (C.c_int32 * 3)()
+        self._check(self.lib.tss_lower_bound_lp(self._h, _ptr(grid.data, C.c_uint8), grid.width, grid.height, _defs_array(defs), len(defs), max_pivots,
+                                                _ptr(wts, C.c_int32), C.byref(total), C.byref(max_load), C.byref(bound), info))
+        return dict(bound=bound.value, weights=wts, total=total.value, max_load=max_load.value, pivots=info[0], optimal=bool(info[1]), constraints=info[2])
+
     def solve_batch(self, grids, seed=0, steps=2048, want_layouts=False, chains_per_terrain=0):
         """grids: uint8[n, h, w] -> counts int32[n] (and packed support rows uint32[n, h] if asked)"""
         g = _u8(grids)
@@ -748,7 +759,7 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
     g = encoding._grid
     only_count = not limits.weights and limits.weight_limit is None and all(d == one for d in limits.card_limits)
     if use_lower_bound and only_count and g.width <= 32 and g.height <= 32:
-        lower = len(engine.lower_bound(g, encoding.defs, seed=seed))
+        lower = max(len(engine.lower_bound(g, encoding.defs, seed=seed)), engine.lower_bound_lp(g, encoding.defs)["bound"])
     while True:
         bound_now = limits.card_limits.get(one)
         if lower is not None and best is not None and bound_now is not None and bound_now < lower:

@@ -34,6 +34,9 @@ int sls_run_h16(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, 
                 int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
                 int noise_pct, unsigned long long* totals_dev);
 int run_peaks(tss_engine* e, double* out, int n_out);
+// lp.cu — fractional packing lower bound
+int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::vector<int2>& key_dims, int max_pivots, int* out_weights,
+           unsigned long long* totals, int* info);
 // lb.cu — packing lower bound
 int lb_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::vector<int2>& key_dims, uint64_t seed, int restarts,
            uint32_t* out_rows32, int* out_count);
@@ -1448,6 +1451,41 @@ int tss_lower_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, co
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++)
             if ((pack[y] >> x) & 1u) { out_xy[2 * n] = x; out_xy[2 * n + 1] = y; n++; }
+    return TSS_OK;
+}
+
+int tss_lower_bound_lp(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs, int32_t max_pivots,
+                       int32_t* out_weights, int64_t* out_total, int64_t* out_max_load, int32_t* out_bound, int32_t* out_info) {
+    if (!e) return TSS_E_INVALID;
+    if (out_bound) *out_bound = 0;
+    if (!grid || !out_bound || w <= 0 || h <= 0 || (!defs && n_defs > 0)) return e->fail(TSS_E_INVALID, "tss_lower_bound_lp: bad arguments");
+    if (w > 32 || h > 32) return e->fail(TSS_E_UNSUPPORTED, "tss_lower_bound_lp: grids larger than 32x32 are not supported");
+    bool has_1x1 = n_defs == 0;
+    for (int i = 0; i < n_defs; i++) {
+        if (defs[i].w <= 0 || defs[i].h <= 0) return e->fail(TSS_E_INVALID, "tss_lower_bound_lp: empty platform dimensions");
+        has_1x1 = has_1x1 || (defs[i].w == 1 && defs[i].h == 1);
+    }
+    if (!has_1x1) return e->fail(TSS_E_INVALID, "the platform set must contain 1x1 (src/encoder.rs:564-566)");
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    std::vector<int2> key_dims;
+    std::vector<tss_platform> key_proto;
+    const tss_dims one{1, 1};
+    build_keys(n_defs ? defs : &one, n_defs ? n_defs : 1, key_dims, key_proto);
+    uint32_t rows[32] = {0};
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            if (grid[(size_t)y * w + x]) rows[y] |= 1u << x;
+    int weights[1024], info[3];
+    unsigned long long totals[2];
+    int rc = lp_run(e, rows, w, h, key_dims, max_pivots, weights, totals, info);
+    if (rc) return rc;
+    if (out_weights)
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) out_weights[(size_t)y * w + x] = weights[y * 32 + x];
+    if (out_total) *out_total = (int64_t)totals[0];
+    if (out_max_load) *out_max_load = (int64_t)totals[1];
+    if (out_info) { out_info[0] = info[0]; out_info[1] = info[1]; out_info[2] = info[2]; }
+    *out_bound = totals[1] > 0 ? (int32_t)((totals[0] + totals[1] - 1) / totals[1]) : 0;   // ceil(total / max load): exact
     return TSS_OK;
 }
 

@@ -1,0 +1,248 @@
+// FRACTIONAL packing lower bound (the LP dual of the support-placement relaxation), solved on the GPU and certified in
+// integer arithmetic.  Not in the reference; it is the strengthening of lb.cu's integral packing that closes the proof on
+// test/ex2.toml and the README terrain with 1x1 supports (LP optimum 13.2 / 13.13 -> bound 14 = the optimum), where the
+// reference spends "minutes (or even hours)" (README.md:31) and the exact solver here ~10 s on the UNSAT call alone.
+//
+//     maximise  sum_t y_t   subject to   sum_{t in reach(p)} y_t <= 1  for every in-bounds placement p,   y >= 0
+//
+// reach(p) = validate()'s rule for the single platform p: the ceiling under its footprint plus three ceiling-masked
+// 4-neighbour dilations (src/encoder/platform_layout.rs:104-141).  Any complete layout L satisfies
+// |L| >= sum_{p in L} sum_{t in reach(p)} y_t >= sum_t y_t, so ceil(sum y) bounds the platform count from below (an integral
+// y is lb.cu's packing).  Weak duality needs y to be FEASIBLE, nothing else, so the certificate never trusts the floating
+// point solve: the solution is rounded to integer weights k_t = floor(y_t * 2^20), a second kernel recomputes every
+// placement's load sum_{t in reach(p)} k_t from the reach bitboards in 64-bit integers, and the bound is
+// ceil(sum k / max load) — exact, whatever the simplex did (a primal simplex iterate is feasible at every pivot, so an
+// iteration cap only weakens the bound).
+//
+// Kernels: lp_reach_kernel (one warp per placement: footprint, dilations -> 32 row words), lp_init_kernel (dense condensed
+// tableau [m + 1][n + 1] in doubles: constraints x ceiling tiles, right-hand side, objective row), lp_simplex_kernel (ONE CTA
+// of 1024 threads: Dantzig entering column, ratio test, rank-1 update with the pivot row staged in shared memory; the
+// instances are a few hundred columns, launch-free pivoting beats a multi-CTA update here), lp_certify_kernel (integer loads).
+#include "engine.hpp"
+
+namespace tss {
+namespace lp {
+
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr int MAX_KEYS = 16;
+constexpr int THREADS = 1024;
+constexpr int MAX_COLS = 1024;                 // ceiling tiles of a 32x32 grid
+constexpr double EPS = 1e-9;
+constexpr long long SCALE = 1ll << 20;         // integer weights k_t = floor(y_t * SCALE)
+
+struct Keys {
+    int n;
+    int w[MAX_KEYS], h[MAX_KEYS];
+};
+
+__device__ __forceinline__ uint32_t dilate(uint32_t X, uint32_t C, int lane) {
+    uint32_t up = __shfl_up_sync(FULL, X, 1), down = __shfl_down_sync(FULL, X, 1);
+    if (lane == 0) up = 0;
+    if (lane == 31) down = 0;
+    return (X | (X << 1) | (X >> 1) | up | down) & C;
+}
+
+// reach rows of every placement (key, anchor): out[(key * 1024 + y * 32 + x) * 32 + row]; all zero if the footprint leaves
+// the grid (forbidden, src/encoder.rs:601-609) or covers no ceiling.  nonempty[placement] = 1 if it supports anything.
+__global__ void __launch_bounds__(128) lp_reach_kernel(const uint32_t* __restrict__ rows, int W, int H, Keys keys, uint32_t* __restrict__ out,
+                                                       uint8_t* __restrict__ nonempty) {
+    const int lane = threadIdx.x & 31, p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= keys.n * 1024) return;
+    const int k = p >> 10, x = p & 31, y = (p >> 5) & 31, w = keys.w[k], h = keys.h[k];
+    const uint32_t C = rows[lane];
+    uint32_t X = 0;
+    if (x + w <= W && y + h <= H && lane >= y && lane < y + h) X = ((w >= 32 ? FULL : ((1u << w) - 1u)) << x) & C;
+#pragma unroll
+    for (int r = 0; r < kTerrainSupportDistance - 1; r++) X = dilate(X, C, lane);
+    out[(size_t)p * 32 + lane] = X;
+    const bool any = __any_sync(FULL, X != 0);
+    if (lane == 0) nonempty[p] = any ? 1 : 0;
+}
+
+// condensed tableau, row-major with leading dimension ld = n + 1: rows 0..m-1 = constraints (column j = tile col_site[j],
+// column n = right-hand side), row m = objective (-1 per tile, value 0)
+__global__ void lp_init_kernel(const uint32_t* __restrict__ reach, const int* __restrict__ cons, int m, const int* __restrict__ col_site, int n,
+                               double* __restrict__ T) {
+    const int ld = n + 1;
+    const long long total = (long long)(m + 1) * ld;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / ld), j = (int)(idx % ld);
+        double v;
+        if (i == m) v = j < n ? -1.0 : 0.0;
+        else if (j == n) v = 1.0 + 1e-7 * (double)((i * 37) % 101) / 101.0;   // tiny perturbation against degenerate ties (the certificate is exact anyway)
+        else {
+            const int s = col_site[j];
+            v = (double)((reach[(size_t)cons[i] * 32 + (s >> 5)] >> (s & 31)) & 1u);
+        }
+        T[idx] = v;
+    }
+}
+
+struct ArgD { double v; int i; };
+__device__ __forceinline__ ArgD better_min(ArgD a, ArgD b) { return (b.v < a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
+
+// block-wide argmin with lowest-index ties (1024 threads); result valid in every thread
+__device__ ArgD block_argmin(ArgD a, ArgD* red) {
+    for (int o = 16; o > 0; o >>= 1) {
+        ArgD b{__shfl_xor_sync(FULL, a.v, o), __shfl_xor_sync(FULL, a.i, o)};
+        a = better_min(a, b);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) red[warp] = a;
+    __syncthreads();
+    ArgD r = red[lane < (int)(blockDim.x >> 5) ? lane : 0];
+    for (int o = 16; o > 0; o >>= 1) {
+        ArgD b{__shfl_xor_sync(FULL, r.v, o), __shfl_xor_sync(FULL, r.i, o)};
+        r = better_min(r, b);
+    }
+    return r;
+}
+
+// Primal simplex on the condensed tableau, all-slack start (y = 0 is feasible).  basis[i] = label of row i, nonbasis[j] =
+// label of column j; labels 0..n-1 are tiles, n.. are slacks.  info[0] = pivots, info[1] = 1 if optimal.
+__global__ void __launch_bounds__(THREADS) lp_simplex_kernel(double* __restrict__ T, int m, int n, int* __restrict__ basis, int* __restrict__ nonbasis,
+                                                            int max_pivots, int* __restrict__ info) {
+    __shared__ double prow[MAX_COLS + 1];
+    __shared__ ArgD red[32];
+    const int ld = n + 1, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n_warps = blockDim.x >> 5;
+    for (int i = tid; i < m; i += blockDim.x) basis[i] = n + i;
+    for (int j = tid; j < n; j += blockDim.x) nonbasis[j] = j;
+    __syncthreads();
+    int pivots = 0, optimal = 0;
+    for (; pivots < max_pivots; pivots++) {
+        // entering column: most negative reduced cost (Dantzig), lowest index on ties
+        ArgD e{0.0, 0x7fffffff};
+        for (int j = tid; j < n; j += blockDim.x) e = better_min(e, ArgD{T[(size_t)m * ld + j], j});
+        e = block_argmin(e, red);
+        if (e.v > -EPS) { optimal = 1; break; }
+        const int q = e.i;
+        // ratio test over the rows with a positive entry in column q
+        ArgD r{1e300, 0x7fffffff};
+        for (int i = tid; i < m; i += blockDim.x) {
+            const double a = T[(size_t)i * ld + q];
+            if (a > EPS) r = better_min(r, ArgD{T[(size_t)i * ld + n] / a, i});
+        }
+        r = block_argmin(r, red);
+        if (r.i == 0x7fffffff) break;   // unbounded: cannot happen (every tile lies in its own site's reach), never spin on it
+        const int pr = r.i;
+        const double piv = T[(size_t)pr * ld + q], inv = 1.0 / piv;
+        __syncthreads();
+        for (int j = tid; j <= n; j += blockDim.x) prow[j] = j == q ? inv : T[(size_t)pr * ld + j] * inv;   // the new pivot row
+        __syncthreads();
+        // rank-1 update: a warp per row, lanes across the columns (coalesced); the objective row is row m
+        for (int i = warp; i <= m; i += n_warps) {
+            double* row = T + (size_t)i * ld;
+            if (i == pr) {
+                for (int j = lane; j <= n; j += 32) row[j] = prow[j];
+                continue;
+            }
+            const double f = row[q];
+            __syncwarp();               // every lane has read the multiplier before lane q % 32 overwrites it
+            if (f == 0.0) continue;     // (0/1 rows: most rows do not touch the entering column)
+            for (int j = lane; j <= n; j += 32) row[j] = j == q ? -f * inv : row[j] - f * prow[j];
+        }
+        if (tid == 0) { const int t = basis[pr]; basis[pr] = nonbasis[q]; nonbasis[q] = t; }
+        __syncthreads();
+    }
+    if (tid == 0) { info[0] = pivots; info[1] = optimal; }
+}
+
+// y -> integer weights per site (floor(y * SCALE), never negative), zero for non-basic tiles
+__global__ void lp_weights_kernel(const double* __restrict__ T, int m, int n, const int* __restrict__ basis, const int* __restrict__ col_site,
+                                  int* __restrict__ weights /* [1024] zeroed */) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int label = basis[i];
+    if (label >= n) return;
+    const double y = T[(size_t)i * (n + 1) + n];
+    const long long k = y > 0.0 ? (long long)floor(y * (double)SCALE) : 0ll;
+    weights[col_site[label]] = (int)(k > (4ll << 20) ? (4ll << 20) : k);
+}
+
+// exact certificate: out[0] = sum of the weights, out[1] = max over ALL placements (not only the tableau's rows) of the load
+__global__ void __launch_bounds__(128) lp_certify_kernel(const uint32_t* __restrict__ reach, int n_placements, const int* __restrict__ weights,
+                                                         unsigned long long* __restrict__ out) {
+    const int lane = threadIdx.x & 31, p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n_placements) return;
+    long long load = 0;
+    for (uint32_t bits = reach[(size_t)p * 32 + lane]; bits; bits &= bits - 1) load += weights[lane * 32 + __ffs(bits) - 1];
+    for (int o = 16; o > 0; o >>= 1) load += __shfl_xor_sync(FULL, load, o);
+    if (lane == 0) atomicMax(&out[1], (unsigned long long)load);
+    if (p == 0) {
+        long long s = 0;
+        for (int t = lane; t < 1024; t += 32) s += weights[t];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if (lane == 0) out[0] = (unsigned long long)s;
+    }
+}
+
+}  // namespace lp
+
+// rows32_host: terrain rows; key_dims: effective (w, h) per dims key.  out_weights (host, 1024 ints, index y * 32 + x),
+// totals[0] = sum of the weights, totals[1] = largest placement load, info[0] = pivots, info[1] = optimal, info[2] = constraints.
+int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::vector<int2>& key_dims, int max_pivots, int* out_weights,
+           unsigned long long* totals, int* info) {
+    if ((int)key_dims.size() > lp::MAX_KEYS) return e->fail(TSS_E_UNSUPPORTED, "tss_lower_bound_lp: more than %d dims keys", lp::MAX_KEYS);
+    lp::Keys keys;
+    keys.n = (int)key_dims.size();
+    for (int i = 0; i < keys.n; i++) { keys.w[i] = key_dims[(size_t)i].x; keys.h[i] = key_dims[(size_t)i].y; }
+    const int n_place = keys.n * 1024;
+    std::vector<int> col_site;
+    for (int s = 0; s < 1024; s++)
+        if ((rows32_host[s >> 5] >> (s & 31)) & 1u) col_site.push_back(s);
+    const int n = (int)col_site.size();
+    totals[0] = totals[1] = 0;
+    info[0] = info[1] = info[2] = 0;
+    for (int i = 0; i < 1024; i++) out_weights[i] = 0;
+    if (n == 0) return TSS_OK;
+    // scratch slot 6: rows [32] | reach [n_place][32] | nonempty [n_place] bytes ; slot 7 is lb.cu's
+    const size_t reach_words = (size_t)n_place * 32;
+    uint32_t* buf = (uint32_t*)e->dev(6, sizeof(uint32_t) * (32 + reach_words) + (size_t)n_place);
+    if (!buf) return TSS_E_CUDA;
+    uint32_t *rows_dev = buf, *reach = buf + 32;
+    uint8_t* nonempty = (uint8_t*)(reach + reach_words);
+    TSS_CUDA(e, cudaMemcpyAsync(rows_dev, rows32_host, sizeof(uint32_t) * 32, cudaMemcpyHostToDevice, e->stream));
+    TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    lp::lp_reach_kernel<<<(n_place + 3) / 4, 128, 0, e->stream>>>(rows_dev, W, H, keys, reach, nonempty);
+    TSS_CHECK_LAUNCH(e);
+    std::vector<uint8_t> ne((size_t)n_place);
+    TSS_CUDA(e, cudaMemcpyAsync(ne.data(), nonempty, (size_t)n_place, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaStreamSynchronize(e->stream));
+    std::vector<int> cons;
+    for (int p = 0; p < n_place; p++)
+        if (ne[(size_t)p]) cons.push_back(p);
+    const int m = (int)cons.size();
+    info[2] = m;
+    const size_t cells = (size_t)(m + 1) * (n + 1);
+    if (cells > ((size_t)1 << 27)) return e->fail(TSS_E_UNSUPPORTED, "tss_lower_bound_lp: tableau of %d x %d exceeds the supported size", m, n);
+    // scratch slot 5: tableau doubles | cons [m] | col_site [n] | basis [m] | nonbasis [n] | weights [1024] | info [4] | totals [2] u64
+    const size_t ints = (size_t)m + n + m + n + 1024 + 4;
+    double* T = (double*)e->dev(5, sizeof(double) * cells + sizeof(int) * ints + 16 + 16);
+    if (!T) return TSS_E_CUDA;
+    int* cons_dev = (int*)(T + cells);
+    int *col_dev = cons_dev + m, *basis = col_dev + n, *nonbasis = basis + m, *weights = nonbasis + n, *info_dev = weights + 1024;
+    unsigned long long* totals_dev = (unsigned long long*)(((uintptr_t)(info_dev + 4) + 15) & ~(uintptr_t)15);
+    TSS_CUDA(e, cudaMemcpyAsync(cons_dev, cons.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, e->stream));
+    TSS_CUDA(e, cudaMemcpyAsync(col_dev, col_site.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    TSS_CUDA(e, cudaMemsetAsync(weights, 0, sizeof(int) * (1024 + 4), e->stream));
+    TSS_CUDA(e, cudaMemsetAsync(totals_dev, 0, sizeof(unsigned long long) * 2, e->stream));
+    const int init_blocks = (int)((cells + 255) / 256 < (size_t)e->prop.multiProcessorCount * 8 ? (cells + 255) / 256 : (size_t)e->prop.multiProcessorCount * 8);
+    lp::lp_init_kernel<<<init_blocks, 256, 0, e->stream>>>(reach, cons_dev, m, col_dev, n, T);
+    lp::lp_simplex_kernel<<<1, lp::THREADS, 0, e->stream>>>(T, m, n, basis, nonbasis, max_pivots > 0 ? max_pivots : 8 * (m + n), info_dev);
+    lp::lp_weights_kernel<<<(m + 255) / 256, 256, 0, e->stream>>>(T, m, n, basis, col_dev, weights);
+    lp::lp_certify_kernel<<<(n_place + 3) / 4, 128, 0, e->stream>>>(reach, n_place, weights, totals_dev);
+    TSS_CHECK_LAUNCH(e);
+    TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    e->stats.kernel_launches += 5;
+    TSS_CUDA(e, cudaMemcpyAsync(out_weights, weights, sizeof(int) * 1024, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaMemcpyAsync(info, info_dev, sizeof(int) * 2, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaMemcpyAsync(totals, totals_dev, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) cudaGetLastError();
+    e->stats.device_ms = ms;
+    return TSS_OK;
+}
+
+}  // namespace tss

@@ -135,6 +135,8 @@ int main(int argc, char** argv) {
     int32_t lower = -1;
     if (use_lb && only_count && w <= 32 && h <= 32) {
         if (tss_lower_bound(e, grid.data(), w, h, all_defs, n_defs, seed, 0, nullptr, 0, &lower) != TSS_OK) lower = -1;
+        int32_t lp_bound = 0;   // the fractional bound, certified in integers: never weaker than the packing up to rounding
+        if (tss_lower_bound_lp(e, grid.data(), w, h, all_defs, n_defs, 0, nullptr, nullptr, nullptr, &lp_bound, nullptr) == TSS_OK && lp_bound > lower) lower = lp_bound;
         if (!quiet && lower >= 0) std::printf("Lower bound: %d platforms\n", lower);
     }
 
