@@ -160,15 +160,23 @@ def cpu_flips(grid, epoch_steps, warm, timed, threads=None, chains_per_thread=32
     return flips / sec, [float(x) * 1e3 for x in r["epoch_seconds"][warm:]], threads, n, best, sample
 
 
+def named_grid(fx, name):
+    """test/exN.toml from the committed fixtures; "readme" = the README's 21x16 terrain = ex2 with its 2x2 hole filled"""
+    rows = fx["ex2" if name == "readme" else name]["grid"]
+    w = max(len(r) for r in rows)
+    grid = np.array([[1 if (i < len(r) and r[i] == "X") else 0 for i in range(w)] for r in rows], np.uint8)
+    if name == "readme":
+        grid[8:10, 8:10] = 1
+    return grid
+
+
 def repl_loop_cpu(name_defs):
     """crates/repl/src/main.rs:280-366 on the CPU alone (oracle encoder + CDCL stand-in, 1 thread): wall ms per instance."""
     import oracle.oracle as O
     fx = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))
     out = {}
     for name, label in name_defs:
-        rows = fx[name]["grid"]
-        w = max(len(r) for r in rows)
-        grid = np.array([[1 if (i < len(r) and r[i] == "X") else 0 for i in range(w)] for r in rows], np.uint8)
+        grid = named_grid(fx, name)
         t0 = time.perf_counter()
         r = O.solver_loop(grid, O.PLATFORMS_DEFAULT if label == "default-8" else O.PLATFORMS_1X1, conflict_budget=20_000_000)
         ms = (time.perf_counter() - t0) * 1e3
@@ -176,7 +184,7 @@ def repl_loop_cpu(name_defs):
     return out
 
 
-REPL_INSTANCES = [("ex1", "default-8"), ("ex3", "default-8"), ("ex2", "default-8"), ("ex2", "1x1")]
+REPL_INSTANCES = [("ex1", "default-8"), ("ex3", "default-8"), ("ex2", "default-8"), ("ex2", "1x1"), ("readme", "1x1")]
 
 
 def run_reference(args):
@@ -480,15 +488,14 @@ def oracle_exact(cnf):
 
 
 def repl_loop_gpu(eng, name_defs):
-    """crates/repl/src/main.rs:280-366 with the GPU engine answering the SAT iterations (and its packing lower bound ending the
-    loop when it meets the count) and the exact solver called only for what is left: wall ms per instance, host buffers."""
+    """crates/repl/src/main.rs:280-366 with the GPU engine answering the SAT iterations (and its certified lower bounds — integral
+    packing, then the fractional LP — ending the loop when they meet the count) and the exact solver called only for what is
+    left: wall ms per instance to the PROVEN optimum, host buffers."""
     import timberborn_support_solver_b200 as T
     fx = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))
     out = {}
     for name, label in name_defs:
-        rows = fx[name]["grid"]
-        w = max(len(r) for r in rows)
-        grid = T.WorldGrid(np.array([[1 if (i < len(r) and r[i] == "X") else 0 for i in range(w)] for r in rows], np.uint8))
+        grid = T.WorldGrid(named_grid(fx, name))
         defs = T.PLATFORMS_DEFAULT if label == "default-8" else T.PLATFORMS_DEFAULT[:1]
         ts, res = [], None
         for rep in range(3):
@@ -755,8 +762,9 @@ def main():
                               "input": "SLS witness completed by unit propagation x 131072, every 64th with one support removed"}
         # ---------------- the REPL flow end to end (BASELINE.json configs[0] and [2]): `load test/exN.toml; solve`
         line["repl_loop"] = {"gpu_seeded": repl_loop_gpu(eng, REPL_INSTANCES), "cpu": repl_loop_cpu(REPL_INSTANCES),
-                             "note": "crates/repl/src/main.rs:280-366 end to end, wall ms: the loop with the GPU engine answering the SAT iterations and the exact solver "
-                                     "(oracle CDCL standing in for Glucose, as on the CPU side) called only for the proof, against the same loop on the CPU alone (1 solver thread)"}
+                             "note": "crates/repl/src/main.rs:280-366 end to end = time to the PROVEN optimum, wall ms: the loop with the GPU engine answering the SAT iterations, its "
+                                     "certified lower bounds closing the gap where they can (exact_solves = 0) and the exact solver (oracle CDCL standing in for Glucose, as on the CPU side) "
+                                     "called only for what is left, against the same loop on the CPU alone (1 solver thread)"}
         # ---------------- single-solve latencies of the other named instances through the C ABI
         fx = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))
         ex1_rows = fx["ex1"]["grid"]   # test/ex1.toml

@@ -753,13 +753,16 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
     steps, best, proved = [], None, False
     give_up = 1024
     engine.clear_interrupt()
-    # packing lower bound (not in the reference): once the count meets it — or the next bound falls below it — the loop is
-    # finished and nothing is left for the exact solver to prove.  Only when the count is the sole limit (the REPL's case).
-    lower = None
+    # lower bounds (not in the reference): once the count meets one — or the next bound falls below it — the loop is finished and
+    # nothing is left for the exact solver to prove.  Only when the count is the sole limit (the REPL's case).  The integral
+    # packing (tss_lower_bound, ~0.1 ms) is computed up front; the fractional bound (tss_lower_bound_lp, a simplex solve: tens of
+    # ms on a 21x16 terrain) only when the GPU has found nothing below a count the packing does not already certify.
+    lower, lp_done = None, False
     g = encoding._grid
     only_count = not limits.weights and limits.weight_limit is None and all(d == one for d in limits.card_limits)
-    if use_lower_bound and only_count and g.width <= 32 and g.height <= 32:
-        lower = max(len(engine.lower_bound(g, encoding.defs, seed=seed)), engine.lower_bound_lp(g, encoding.defs)["bound"])
+    use_lower_bound = use_lower_bound and only_count and g.width <= 32 and g.height <= 32
+    if use_lower_bound:
+        lower = len(engine.lower_bound(g, encoding.defs, seed=seed))
     while True:
         bound_now = limits.card_limits.get(one)
         if lower is not None and best is not None and bound_now is not None and bound_now < lower:
@@ -777,6 +780,13 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
             give_up = max(1024, 32 * int(engine.stats()["last_solve_steps"]))
         source = "gpu"
         assignment = solver.full_solution() if result == SAT else None
+        if result != SAT and use_lower_bound and not lp_done and best is not None:
+            lp_done = True                                      # the GPU found nothing below the current count: can the fractional bound certify it?
+            lower = max(lower, engine.lower_bound_lp(g, encoding.defs)["bound"])
+            if limits.card_limits.get(one) is not None and limits.card_limits[one] < lower:
+                steps.append(dict(bound=limits.card_limits[one], result=UNSAT, source="lower bound"))
+                proved = True
+                break
         if result != SAT and exact_solver is not None:          # the GPU found nothing in budget: ask the prover
             result, assignment = exact_solver(cnf)
             source = "exact"

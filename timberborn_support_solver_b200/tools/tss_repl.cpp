@@ -132,16 +132,17 @@ int main(int argc, char** argv) {
 
     bool only_count = true;   // the lower bound speaks about the platform count: usable when that is the only limit
     for (size_t i = 0; i + 2 < card.size(); i += 3) only_count = only_count && card[i] == 1 && card[i + 1] == 1;
+    const double t_loop = now_ms();   // (engine creation = CUDA context start-up, ~1 s of a fresh process, is reported apart)
     int32_t lower = -1;
     if (use_lb && only_count && w <= 32 && h <= 32) {
         if (tss_lower_bound(e, grid.data(), w, h, all_defs, n_defs, seed, 0, nullptr, 0, &lower) != TSS_OK) lower = -1;
-        int32_t lp_bound = 0;   // the fractional bound, certified in integers: never weaker than the packing up to rounding
-        if (tss_lower_bound_lp(e, grid.data(), w, h, all_defs, n_defs, 0, nullptr, nullptr, nullptr, &lp_bound, nullptr) == TSS_OK && lp_bound > lower) lower = lp_bound;
+
         if (!quiet && lower >= 0) std::printf("Lower bound: %d platforms\n", lower);
     }
 
     int64_t give_up = 1024;
     int gpu_solves = 0, exact_solves = 0, best = -1;
+    bool lp_done = false;   // the fractional bound (a simplex solve) is only computed when the packing bound does not already close the gap
     std::string verdict = "open";
     for (;;) {
         // the 1x1 limit of this iteration (PlatformLimits.card_limits[1x1], main.rs:346)
@@ -184,6 +185,21 @@ int main(int argc, char** argv) {
                 give_up = 32 * st.last_solve_steps > 1024 ? 32 * st.last_solve_steps : 1024;
             }
         }
+        if (result == 0 && lower >= 0 && !lp_done && best >= 0) {   // the GPU found nothing below the current count: can the fractional bound certify it?
+            lp_done = true;
+            int32_t lp_bound = 0;
+            if (tss_lower_bound_lp(e, grid.data(), w, h, all_defs, n_defs, 0, nullptr, nullptr, nullptr, &lp_bound, nullptr) == TSS_OK && lp_bound > lower) {
+                lower = lp_bound;
+                if (!quiet) std::printf("Lower bound (fractional): %d platforms\n", lower);
+            }
+            if (bound >= 0 && bound < lower) {
+                if (inst) tss_encoding_destroy(inst);
+                tss_cnf_destroy(cnf);
+                std::printf("No solution found for the current constraints\n");
+                verdict = "optimal (lower bound)";
+                break;
+            }
+        }
         if (result == 0 && !exact_cmd.empty()) {   // the exact solver: every UNSAT answer comes from here
             result = run_exact(exact_cmd, lits, offsets, n_vars, assignment);
             source = "exact";
@@ -215,8 +231,8 @@ int main(int argc, char** argv) {
         if (bad != 0) { verdict = "invalid layout"; break; }
     }
     std::printf("Done\n");
-    std::printf("# best=%d lower_bound=%d verdict=\"%s\" gpu_solves=%d exact_solves=%d ms=%.3f\n", best, lower, verdict.c_str(), gpu_solves, exact_solves,
-                now_ms() - t_start);
+    std::printf("# best=%d lower_bound=%d verdict=\"%s\" gpu_solves=%d exact_solves=%d ms=%.3f setup_ms=%.1f\n", best, lower, verdict.c_str(), gpu_solves,
+                exact_solves, now_ms() - t_loop, t_loop - t_start);
     tss_encoding_destroy(enc);
     tss_engine_destroy(e);
     return 0;
