@@ -101,7 +101,27 @@ std::string parse_world_toml(const std::string& text, WorldGrid& out, bool* ragg
         if (i >= n || text[i] != '=') return "expected `=` after key `" + key + "`";
         i++;
         skip_ws(false);
-        if (!(in_world && key == "grid")) return "unknown field `" + key + "`";
+        if (!(in_world && key == "grid")) {
+            // not a field of Project / World: serde skips it (no deny_unknown_fields, src/lib.rs:14-17, src/world.rs:13-16).
+            // Walk over the value: quoted strings, bracketed values over several lines, or the rest of the line.
+            std::vector<char> open;
+            for (; i < n; i++) {
+                const char c = text[i];
+                if (c == '#') { while (i < n && text[i] != '\n') i++; i--; continue; }
+                if (c == '"' || c == '\'') {
+                    size_t j = i + 1;
+                    while (j < n && text[j] != c) j += (c == '"' && text[j] == '\\') ? 2 : 1;
+                    if (j >= n) return "unterminated string";
+                    i = j;
+                    continue;
+                }
+                if (c == '[' || c == '{') open.push_back(c);
+                else if (c == ']' || c == '}') { if (open.empty()) return "unbalanced bracket in the value of `" + key + "`"; open.pop_back(); }
+                else if (c == '\n' && open.empty()) break;
+            }
+            if (!open.empty()) return "unterminated value of `" + key + "`";
+            continue;
+        }
         if (i >= n || text[i] != '[') return "invalid type: expected an array of \"X\" and \" \" characters forming a grid";
         i++;
         while (true) {

@@ -293,3 +293,29 @@ def test_instance_registry_finds_the_instance_from_its_clauses(fixtures):
     import gc
     gc.collect()
     assert find(cnf)[0] == 10
+
+
+# ---- an independent third reader for the project format (oracle and product parse TOML with sibling code) --------
+def test_world_toml_agrees_with_an_independent_toml_parser():
+    """src/world.rs:21-40,49-79: `[world] grid = [rows of 'X' / ' ']`.  Python's tomllib knows nothing of either implementation:
+    what the product serialises must read back through it to the same grid, and what it reads the product and the oracle
+    must read identically (rows of unequal length are left-aligned and padded, world.rs:82-86)."""
+    import tomllib
+    rng = np.random.default_rng(5)
+    for h, w in [(1, 1), (3, 7), (16, 16), (21, 16), (32, 32), (5, 40)]:
+        g = (rng.random((h, w)) < 0.6).astype(np.uint8)
+        g[0, w - 1] = 1                                          # keep the width recoverable: the longest row defines it
+        text = T.WorldGrid(g).to_toml()
+        rows = tomllib.loads(text)["world"]["grid"]
+        assert len(rows) == h and all(set(r) <= {"X", " "} for r in rows)
+        back = np.array([[1 if (i < len(r) and r[i] == "X") else 0 for i in range(w)] for r in rows], np.uint8)
+        assert np.array_equal(back, g)
+        assert np.array_equal(T.WorldGrid.from_toml(text).data, g)
+        assert np.array_equal(O.parse_world(text)[0], g)
+        assert O.world_to_toml(g) == text
+    # hand-written document with comments, ragged rows and another table: all three readers agree
+    doc = ('# a project\n[meta]\nname = "x # not a comment"\ntags = [\n  "a", ["b"],\n]\n\n[world]\nseed = 7  # serde ignores undeclared fields\n'
+           'grid = [\n  "XX X",  # first row\n  "X",\n  "  XXXXX",\n]\nextra = { k = "v" }\n')
+    rows = tomllib.loads(doc)["world"]["grid"]
+    want = np.array([[1 if (i < len(r) and r[i] == "X") else 0 for i in range(7)] for r in rows], np.uint8)
+    assert np.array_equal(T.WorldGrid.from_toml(doc).data, want) and np.array_equal(O.parse_world(doc)[0], want)

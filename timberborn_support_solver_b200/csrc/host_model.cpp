@@ -54,7 +54,8 @@ struct Cursor {
 
 std::string parse_world_toml(const char* text, std::vector<uint8_t>& grid, int& w, int& h, bool& ragged) {
     // The project file is `[world]` + `grid = [ "..", ... ]` (crates/repl/src/main.rs:272-278 via the toml crate);
-    // this reader accepts that subset: table headers, one array-of-strings key, comments, trailing commas.
+    // this reader accepts that subset: table headers, one array-of-strings key, comments, trailing commas; other tables and
+    // keys are skipped the way serde skips undeclared fields.
     Cursor c(text);
     std::vector<std::string> rows;
     bool in_world = false, have_grid = false;
@@ -76,7 +77,27 @@ std::string parse_world_toml(const char* text, std::vector<uint8_t>& grid, int& 
         if (c.eof() || c.peek() != '=') return "expected `=` after key `" + key + "`";
         c.i++;
         c.skip(false);
-        if (!in_world || key != "grid") return "unknown field `" + key + "`";
+        if (!in_world || key != "grid") {
+            // serde ignores fields a struct does not declare (neither Project, src/lib.rs:14-17, nor World, src/world.rs:13-16, denies
+            // unknown fields): skip the value — a string, a (nested) array or inline table, or a bare scalar up to the end of the line
+            int depth = 0;
+            bool done = false;
+            while (!c.eof() && !done) {
+                const char ch = c.peek();
+                if (ch == '"' || ch == '\'') {
+                    c.i++;
+                    while (!c.eof() && c.peek() != ch) { if (ch == '"' && c.peek() == '\\') c.i++; c.i++; }
+                    if (c.eof()) return "unterminated string";
+                    c.i++;
+                } else if (ch == '[' || ch == '{') { depth++; c.i++; }
+                else if (ch == ']' || ch == '}') { if (--depth < 0) return "unbalanced bracket in the value of `" + key + "`"; c.i++; }
+                else if (ch == '#') { while (!c.eof() && c.peek() != '\n') c.i++; }
+                else if (ch == '\n' && depth == 0) done = true;
+                else c.i++;
+            }
+            if (depth != 0) return "unterminated value of `" + key + "`";
+            continue;
+        }
         if (c.eof() || c.peek() != '[') return "invalid type: expected an array of \"X\" and \" \" characters forming a grid";
         c.i++;
         for (;;) {
