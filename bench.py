@@ -465,6 +465,8 @@ def side_c4(eng, torch, dist, world, rank, phases, phase_steps):
     f1 = eng.stats()
     lay = s.best_layout()                  # re-validated by kernel (a) inside the engine
     assert lay.platform_count() == count
+    lower = len(eng.lower_bound(g, seed=1)) if rank == 0 else 0     # certified packing bound (whole-board rounds, csrc/lb.cu)
+    lower_ms = eng.stats()["device_ms"]
     t = torch.tensor([evs[0].elapsed_time(evs[1])], dtype=torch.float64, device="cuda")
     acc = torch.tensor([float(f1["sls_flips"] - f0["sls_flips"]), float(f1["candidates_scored"] - f0["candidates_scored"])], dtype=torch.float64, device="cuda")
     cmin = torch.tensor([float(count)], dtype=torch.float64, device="cuda")
@@ -479,7 +481,8 @@ def side_c4(eng, torch, dist, world, rank, phases, phase_steps):
     ms = float(t.item())
     return {"workload": "synthetic 256x256 random ceiling (p=0.7), 1x1 supports, window-decomposed SLS portfolio (BASELINE.json configs[3])",
             "scaling": "weak (own seeds and noise level per rank; per-window best of all ranks adopted after every phase)", "best_count": int(cmin.item()),
-            "ceiling_tiles": int(g.data.sum()), "trivial_lower_bound": int(-(-int(g.data.sum()) // 25)), "phases": phases + 1, "phase_steps": phase_steps,
+            "ceiling_tiles": int(g.data.sum()), "certified_lower_bound": lower, "lower_bound_ms": lower_ms,
+            "trivial_lower_bound": int(-(-int(g.data.sum()) // 25)), "phases": phases + 1, "phase_steps": phase_steps,
             "ms": ms, "flips_per_s": float(acc[0].item()) / (ms * 1e-3), "neighbour_scores_per_s": float(acc[1].item()) / (ms * 1e-3), "chains_per_gpu": n_chains}
 
 

@@ -277,7 +277,8 @@ int tss_solve_min_weight(tss_engine* e, const uint8_t* grid, int32_t w, int32_t 
  * greedy restarts on the GPU (`restarts` <= 0: 16 per SM), the winning packing is re-verified on the device before it is
  * returned.  out_xy[2*i], out_xy[2*i+1] = packed tile i (capacity `cap` tiles); *n_out = the bound.  When
  * tss_solve_upper_bound reaches this count the bound-tightening loop (crates/repl/src/main.rs:280-366) is finished without
- * the exact solver.  Grids up to 32x32; TSS_E_UNSUPPORTED beyond. */
+ * the exact solver.  Any platform set on grids up to 32x32; larger grids (up to 256x256) with 1x1 supports, by parallel rounds on
+ * the whole bitboard (`restarts` <= 0: one per SM); TSS_E_UNSUPPORTED otherwise. */
 int tss_lower_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs, uint64_t seed,
                     int32_t restarts, int32_t* out_xy, int32_t cap, int32_t* n_out);
 /* The FRACTIONAL version of that bound (csrc/lp.cu): weights y_t >= 0 on the ceiling tiles such that no in-bounds placement's

@@ -873,8 +873,10 @@ def test_lower_bound_edge_cases(eng):
     line = np.ones((1, 32), np.uint8)                                                             # a corridor: tiles 7 apart, ceil(32/7) = 5
     tiles = eng.lower_bound(T.WorldGrid(line))
     assert len(tiles) == 5 and all(b[0] - a[0] >= 7 for a, b in zip(sorted(tiles), sorted(tiles)[1:]))
+    tall = eng.lower_bound(T.WorldGrid(np.ones((33, 8), np.uint8)))                               # beyond 32 rows: the whole-board kernel
+    assert len(tall) >= 4 and all(abs(a[0] - b[0]) + abs(a[1] - b[1]) > 6 for i, a in enumerate(tall) for b in tall[:i])
     with pytest.raises(T.TssError):
-        eng.lower_bound(T.WorldGrid(np.ones((33, 8), np.uint8)))
+        eng.lower_bound(T.WorldGrid(np.ones((600, 600), np.uint8)))                               # boards beyond 256x256 do not fit shared memory
     full = np.ones((32, 32), np.uint8)
     tiles = eng.lower_bound(T.WorldGrid(full))
     assert len(tiles) >= 32 * 32 // 85 + 1 and len(tiles) <= 41                                   # radius-6 balls hold <= 85 tiles; optimum >= 1024/25
@@ -939,6 +941,43 @@ def test_solver_loop_proves_readme_and_ex2_without_the_exact_solver(eng, fixture
         assert out["steps"][-1]["source"] == "lower bound"
         plats = [tup(p) for p in out["best"].platforms().values()]
         assert O.validate(g, plats).is_valid
+
+
+def _geodesic_ball(g, x, y, radius):
+    cur = np.zeros_like(g, dtype=bool)
+    cur[y, x] = True
+    c = g.astype(bool)
+    for _ in range(radius):
+        n = cur.copy()
+        n[1:] |= cur[:-1]; n[:-1] |= cur[1:]; n[:, 1:] |= cur[:, :-1]; n[:, :-1] |= cur[:, 1:]
+        cur = n & c
+    return cur
+
+
+@pytest.mark.parametrize("w,h", [(96, 80), (33, 40), (256, 256)])
+def test_lower_bound_on_large_grids(eng, w, h):
+    """Grids beyond 32x32 (C4's shape), 1x1 supports: the whole-board packing.  Independent check in numpy: the packed tiles are
+    ceiling tiles pairwise more than 6 steps apart through the ceiling (= no site within 3 of two of them: validate()'s three
+    dilations, platform_layout.rs:127-141), and the bound is useful (well above tiles / 25, below the SLS count)."""
+    g = synth_terrain(w, h, seed=1, t=0 if (w, h) == (256, 256) else 3)
+    tiles = eng.lower_bound(T.WorldGrid(g), seed=1)
+    packed = np.zeros_like(g, dtype=bool)
+    for x, y in tiles:
+        assert g[y, x] == 1
+        packed[y, x] = True
+    assert packed.sum() == len(tiles)
+    sample = tiles if len(tiles) <= 400 else [tiles[i] for i in np.random.default_rng(0).choice(len(tiles), 400, replace=False)]
+    for x, y in sample:
+        assert (_geodesic_ball(g, x, y, 6) & packed).sum() == 1, (x, y)
+    assert len(tiles) > 1.5 * g.sum() / 25                     # far better than the trivial ceil(tiles / 25)
+    if (w, h) == (96, 80):
+        s = eng.search(T.WorldGrid(g), seed=2)
+        for _ in range(4):
+            s.run(2000, 0)
+        assert len(tiles) <= s.best_count()
+        s.close()
+    with pytest.raises(T.TssError):
+        eng.lower_bound(T.WorldGrid(g), T.PLATFORMS_DEFAULT)    # larger platform sets: grids up to 32x32 only
 
 
 def test_solver_loop_ends_on_the_lower_bound_without_the_exact_solver(eng, fixtures):

@@ -40,6 +40,7 @@ int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::
 // lb.cu — packing lower bound
 int lb_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::vector<int2>& key_dims, uint64_t seed, int restarts,
            uint32_t* out_rows32, int* out_count);
+int lb_run_big(tss_engine* e, const uint32_t* rows_host, int W, int H, uint64_t seed, int restarts, uint32_t* out_rows, int* out_count);
 // lns.cu — window decomposition for grids larger than 32x32
 struct LnsSearch;
 int lns_create(tss_engine* e, const uint8_t* grid, int w, int h, int seeds, uint64_t seed, uint32_t chain_offset, int noise, LnsSearch** out);
@@ -1426,14 +1427,29 @@ int tss_lower_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, co
     if (!e) return TSS_E_INVALID;
     if (n_out) *n_out = 0;
     if (!grid || !n_out || w <= 0 || h <= 0 || (!defs && n_defs > 0) || cap < 0 || (cap > 0 && !out_xy)) return e->fail(TSS_E_INVALID, "tss_lower_bound: bad arguments");
-    if (w > 32 || h > 32) return e->fail(TSS_E_UNSUPPORTED, "tss_lower_bound: grids larger than 32x32 are not supported");
-    bool has_1x1 = n_defs == 0;
+    bool has_1x1 = n_defs == 0, only_1x1 = true;
     for (int i = 0; i < n_defs; i++) {
         if (defs[i].w <= 0 || defs[i].h <= 0) return e->fail(TSS_E_INVALID, "tss_lower_bound: empty platform dimensions");
         has_1x1 = has_1x1 || (defs[i].w == 1 && defs[i].h == 1);
+        only_1x1 = only_1x1 && defs[i].w == 1 && defs[i].h == 1;
     }
     if (!has_1x1) return e->fail(TSS_E_INVALID, "the platform set must contain 1x1 (src/encoder.rs:564-566)");
     TSS_CUDA(e, cudaSetDevice(e->device));
+    if (w > 32 || h > 32) {   // whole-board packing in parallel rounds (lb.cu), 1x1 supports
+        if (!only_1x1) return e->fail(TSS_E_UNSUPPORTED, "tss_lower_bound: grids larger than 32x32 are supported with 1x1 supports only");
+        BitGrid bg = BitGrid::from_bytes(grid, w, h);
+        std::vector<uint32_t> pack(bg.rows.size());
+        int count = 0;
+        int rc = lb_run_big(e, bg.rows.data(), w, h, seed, restarts, pack.data(), &count);
+        if (rc) return rc;
+        *n_out = count;
+        if (count > cap) return cap == 0 ? TSS_OK : e->fail(TSS_E_CAPACITY, "tss_lower_bound: need room for %d tiles", count);
+        int n = 0;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++)
+                if ((pack[(size_t)y * bg.wpr + (x >> 5)] >> (x & 31)) & 1u) { out_xy[2 * n] = x; out_xy[2 * n + 1] = y; n++; }
+        return TSS_OK;
+    }
     std::vector<int2> key_dims;
     std::vector<tss_platform> key_proto;
     const tss_dims one{1, 1};

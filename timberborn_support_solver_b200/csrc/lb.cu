@@ -129,6 +129,160 @@ __global__ void lb_verify_kernel(const uint32_t* __restrict__ rows, int W, int H
     if (lane == 0) { result[0] = n; result[1] = bad; result[2] = off; }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Grids larger than 32x32 (e.g. the 256x256 portfolio), 1x1 supports: the same packing bound — tiles pairwise more than 6
+// steps apart through the ceiling — built by Luby-style parallel rounds on the whole bitboard.  One CTA per restart, all
+// state in shared memory.  A round: (1) every available tile counts the available tiles in its radius-6 diamond (its
+// degree); (2) a tile is selected if its key (few neighbours first, then a hash) beats every available tile in that
+// diamond — selected tiles are then more than 6 apart even in Manhattan distance, hence geodesically; (3) the geodesic
+// radius-6 balls of the selected tiles (six ceiling-masked dilations of the whole board) leave the available set.
+constexpr int BIG_THREADS = 1024;
+constexpr int BIG_MAX_WORDS = 2048;      // 256 x 256
+
+struct BigBoards {
+    uint32_t *C, *avail, *P, *A, *B;     // [nw] each
+    uint8_t* deg;                        // [nw * 32]
+};
+
+// `len` (<= 32) bits of row y of board X starting at column x0 (zeros outside the grid)
+__device__ __forceinline__ uint32_t row_bits(const uint32_t* X, int wpr, int h, int y, int x0, int len) {
+    if (y < 0 || y >= h) return 0u;
+    const int wq = x0 >> 5, sh = x0 & 31;          // arithmetic shift: floor, also for negative x0
+    const uint32_t lo = (wq >= 0 && wq < wpr) ? X[y * wpr + wq] : 0u;
+    const uint32_t hi = (wq + 1 >= 0 && wq + 1 < wpr) ? X[y * wpr + wq + 1] : 0u;
+    const uint32_t v = __funnelshift_r(lo, hi, sh);
+    return len >= 32 ? v : (v & ((1u << len) - 1u));
+}
+
+__device__ __forceinline__ void dilate_board(const uint32_t* src, uint32_t* dst, const uint32_t* C, int nw, int wpr) {
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+        const int col = i % wpr;
+        const uint32_t x = src[i];
+        uint32_t l = x << 1, r = x >> 1;
+        if (col > 0) l |= src[i - 1] >> 31;
+        if (col + 1 < wpr) r |= src[i + 1] << 31;
+        const uint32_t up = i >= wpr ? src[i - wpr] : 0u, down = i + wpr < nw ? src[i + wpr] : 0u;
+        dst[i] = (x | l | r | up | down) & C[i];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t big_key(uint32_t deg, uint32_t seed, uint32_t round, uint32_t tile) {
+    return ((255u - (deg > 255u ? 255u : deg)) << 24) | (sls::fmix32(seed ^ (round * sls::K1) ^ (tile * sls::K2)) & 0xffffffu);
+}
+
+// out_rows[restart][nw]: packing of every restart; best = max over restarts of (size << 32 | ~restart)
+__global__ void __launch_bounds__(BIG_THREADS) lb_pack_big_kernel(const uint32_t* __restrict__ rows, int W, int H, uint64_t seed, int n_restarts,
+                                                                  uint32_t* __restrict__ out_rows, unsigned long long* __restrict__ best) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int wpr = (W + 31) / 32, nw = H * wpr, tid = threadIdx.x, restart = blockIdx.x;
+    uint32_t* C = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t *avail = C + nw, *P = avail + nw, *A = P + nw, *B = A + nw;
+    uint8_t* deg = reinterpret_cast<uint8_t*>(B + nw);
+    __shared__ int any_avail, count;
+    const uint32_t base = sls::chain_base(seed, (uint32_t)restart);
+    for (int i = tid; i < nw; i += blockDim.x) { const uint32_t c = rows[i]; C[i] = c; avail[i] = c; P[i] = 0u; }
+    if (tid == 0) count = 0;
+    __syncthreads();
+    for (uint32_t round = 0; round < 64u; round++) {
+        if (tid == 0) any_avail = 0;
+        __syncthreads();
+        // (1) degrees
+        for (int i = tid; i < nw; i += blockDim.x) {
+            const int y = i / wpr, xb = (i % wpr) * 32;
+            for (uint32_t bits = avail[i]; bits; bits &= bits - 1) {
+                const int x = xb + __ffs(bits) - 1;
+                int d = 0;
+#pragma unroll
+                for (int dy = -6; dy <= 6; dy++) { const int r = 6 - (dy < 0 ? -dy : dy); d += __popc(row_bits(avail, wpr, H, y + dy, x - r, 2 * r + 1)); }
+                deg[i * 32 + (x - xb)] = (uint8_t)(d > 255 ? 255 : d);
+                any_avail = 1;
+            }
+        }
+        __syncthreads();
+        if (!any_avail) break;
+        // (2) selection: strict maximum of (key, lower tile index) over the available tiles of the diamond
+        for (int i = tid; i < nw; i += blockDim.x) {
+            const int y = i / wpr, xb = (i % wpr) * 32;
+            uint32_t sel = 0;
+            for (uint32_t bits = avail[i]; bits; bits &= bits - 1) {
+                const int b = __ffs(bits) - 1, x = xb + b, tile = y * W + x;
+                const uint32_t key = big_key(deg[i * 32 + b], base, round, (uint32_t)tile);
+                bool win = true;
+                for (int dy = -6; dy <= 6 && win; dy++) {
+                    const int r = 6 - (dy < 0 ? -dy : dy), yy = y + dy;
+                    for (uint32_t nb = row_bits(avail, wpr, H, yy, x - r, 2 * r + 1); nb && win; nb &= nb - 1) {
+                        const int xx = x - r + __ffs(nb) - 1;
+                        if (xx == x && dy == 0) continue;
+                        const int ot = yy * W + xx;
+                        const uint32_t ok = big_key(deg[(yy * wpr + (xx >> 5)) * 32 + (xx & 31)], base, round, (uint32_t)ot);
+                        win = key > ok || (key == ok && tile < ot);
+                    }
+                }
+                if (win) sel |= 1u << b;
+            }
+            A[i] = sel;
+            if (sel) atomicAdd(&count, __popc(sel));
+        }
+        __syncthreads();
+        // (3) the selected tiles join the packing; their geodesic radius-6 balls leave the available set
+        for (int i = tid; i < nw; i += blockDim.x) P[i] |= A[i];
+        __syncthreads();
+        for (int r = 0; r < 3; r++) { dilate_board(A, B, C, nw, wpr); dilate_board(B, A, C, nw, wpr); }
+        for (int i = tid; i < nw; i += blockDim.x) avail[i] &= ~A[i];
+        __syncthreads();
+    }
+    for (int i = tid; i < nw; i += blockDim.x) out_rows[(size_t)restart * nw + i] = P[i];
+    if (tid == 0) atomicMax(best, ((unsigned long long)(uint32_t)count << 32) | (uint32_t)(~(uint32_t)restart));
+}
+
+// Exact check of the winning packing: the radius-3 geodesic balls of the packed tiles are pairwise disjoint (a site in two of
+// them would support both tiles).  Labels (packed tile index + 1) spread for three synchronous rounds through the ceiling; a tile
+// that is offered two different labels is a violation.  One CTA; label / next arrays in global memory.
+// result[0] = packed tiles, result[1] = violations, result[2] = packed tiles off the ceiling.
+__global__ void __launch_bounds__(BIG_THREADS) lb_verify_big_kernel(const uint32_t* __restrict__ rows, int W, int H, const uint32_t* __restrict__ out_rows,
+                                                                    const unsigned long long* __restrict__ best, uint32_t* __restrict__ winner_rows,
+                                                                    uint32_t* __restrict__ label, uint32_t* __restrict__ next, int* __restrict__ result) {
+    const int wpr = (W + 31) / 32, nw = H * wpr, tid = threadIdx.x, tiles = W * H;
+    const uint32_t restart = ~(uint32_t)(*best & 0xffffffffu);
+    const uint32_t* P = out_rows + (size_t)restart * nw;
+    __shared__ int n_packed, n_bad, n_off;
+    if (tid == 0) { n_packed = 0; n_bad = 0; n_off = 0; }
+    __syncthreads();
+    for (int i = tid; i < nw; i += blockDim.x) {
+        winner_rows[i] = P[i];
+        if (P[i]) atomicAdd(&n_packed, __popc(P[i]));
+        if (P[i] & ~rows[i]) atomicAdd(&n_off, __popc(P[i] & ~rows[i]));
+    }
+    for (int t = tid; t < tiles; t += blockDim.x) {
+        const int x = t % W, y = t / W;
+        label[t] = ((P[y * wpr + (x >> 5)] >> (x & 31)) & 1u) ? (uint32_t)t + 1u : 0u;
+    }
+    __syncthreads();
+    for (int round = 0; round < kTerrainSupportDistance - 1; round++) {
+        for (int t = tid; t < tiles; t += blockDim.x) {
+            const int x = t % W, y = t / W;
+            uint32_t mine = label[t];
+            if ((rows[y * wpr + (x >> 5)] >> (x & 31)) & 1u) {
+                const int nx[4] = {x + 1, x, x - 1, x}, ny[4] = {y, y + 1, y, y - 1};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (nx[k] < 0 || nx[k] >= W || ny[k] < 0 || ny[k] >= H) continue;
+                    const uint32_t other = label[ny[k] * W + nx[k]];
+                    if (!other) continue;
+                    if (mine && mine != other) atomicAdd(&n_bad, 1);
+                    if (!mine) mine = other;
+                }
+            }
+            next[t] = mine;
+        }
+        __syncthreads();
+        for (int t = tid; t < tiles; t += blockDim.x) label[t] = next[t];
+        __syncthreads();
+    }
+    if (tid == 0) { result[0] = n_packed; result[1] = n_bad; result[2] = n_off; }
+}
+
 }  // namespace lb
 
 // rows32_host: terrain rows; key_dims: effective (w, h) per dims key.  out_rows32 (host, 32 words) = the packing.
@@ -165,6 +319,43 @@ int lb_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::
     if (res[1] != 0 || res[2] != 0)
         return e->fail(TSS_E_CUDA, "internal error: lower-bound packing failed verification (%d tiles share a platform, %d off the ceiling)", res[1], res[2]);
     for (int i = 0; i < 32; i++) out_rows32[i] = host[32 + i];
+    *out_count = res[0];
+    return TSS_OK;
+}
+
+// grids larger than 32x32, 1x1 supports.  rows_host: bit-packed rows [H * wpr]; out_rows (host) the same shape.
+int lb_run_big(tss_engine* e, const uint32_t* rows_host, int W, int H, uint64_t seed, int restarts, uint32_t* out_rows, int* out_count) {
+    const int wpr = (W + 31) / 32, nw = H * wpr, tiles = W * H;
+    if (nw > lb::BIG_MAX_WORDS) return e->fail(TSS_E_UNSUPPORTED, "tss_lower_bound: grid %dx%d exceeds the packing kernel's shared-memory boards", W, H);
+    if (restarts <= 0) restarts = e->prop.multiProcessorCount;
+    const size_t smem = sizeof(uint32_t) * 5 * (size_t)nw + (size_t)nw * 32;
+    TSS_CUDA(e, cudaFuncSetAttribute(lb::lb_pack_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // scratch slot 7: rows [nw] | winner [nw] | result [4] | best [2] | label [tiles] | next [tiles] | packings [restarts][nw]
+    const size_t words = (size_t)2 * nw + 8 + (size_t)2 * tiles + (size_t)restarts * nw;
+    uint32_t* buf = (uint32_t*)e->dev(7, sizeof(uint32_t) * words);
+    if (!buf) return TSS_E_CUDA;
+    uint32_t *rows_dev = buf, *winner = buf + nw;
+    int* result = (int*)(buf + 2 * nw);
+    unsigned long long* best = (unsigned long long*)(buf + 2 * nw + 4);
+    uint32_t *label = buf + 2 * nw + 8, *next = label + tiles, *packs = next + tiles;
+    TSS_CUDA(e, cudaMemcpyAsync(rows_dev, rows_host, sizeof(uint32_t) * (size_t)nw, cudaMemcpyHostToDevice, e->stream));
+    TSS_CUDA(e, cudaMemsetAsync(buf + 2 * nw, 0, sizeof(uint32_t) * 8, e->stream));
+    TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    lb::lb_pack_big_kernel<<<restarts, lb::BIG_THREADS, smem, e->stream>>>(rows_dev, W, H, seed, restarts, packs, best);
+    TSS_CHECK_LAUNCH(e);
+    lb::lb_verify_big_kernel<<<1, lb::BIG_THREADS, 0, e->stream>>>(rows_dev, W, H, packs, best, winner, label, next, result);
+    TSS_CHECK_LAUNCH(e);
+    TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    e->stats.kernel_launches += 2;
+    int res[4];
+    TSS_CUDA(e, cudaMemcpyAsync(res, result, sizeof res, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaMemcpyAsync(out_rows, winner, sizeof(uint32_t) * (size_t)nw, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) cudaGetLastError();
+    e->stats.device_ms = ms;
+    if (res[1] != 0 || res[2] != 0)
+        return e->fail(TSS_E_CUDA, "internal error: lower-bound packing failed verification (%d shared sites, %d off the ceiling)", res[1], res[2]);
     *out_count = res[0];
     return TSS_OK;
 }
