@@ -17,8 +17,16 @@
 // Kernels: lp_reach_kernel (one warp per placement: footprint, dilations -> 32 row words), lp_init_kernel (dense condensed
 // tableau [m + 1][n + 1] in doubles: constraints x ceiling tiles, right-hand side, objective row), lp_simplex_kernel (ONE CTA
 // of 1024 threads: Dantzig entering column, ratio test, rank-1 update with the pivot row staged in shared memory; the
-// instances are a few hundred columns, launch-free pivoting beats a multi-CTA update here), lp_certify_kernel (integer loads).
+// instances are a few hundred columns, launch-free pivoting beats a multi-CTA update with grid syncs), lp_simplex_cluster_kernel
+// (tableaus up to ~1.6 MB: rows resident in the shared memory of an 8-CTA thread-block cluster, exchange over distributed
+// shared memory), lp_certify_kernel (integer loads).
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "engine.hpp"
+
+namespace cg = cooperative_groups;
 
 namespace tss {
 namespace lp {
@@ -148,6 +156,85 @@ __global__ void __launch_bounds__(THREADS) lp_simplex_kernel(double* __restrict_
     if (tid == 0) { info[0] = pivots; info[1] = optimal; }
 }
 
+// ---- the same simplex for tableaus that fit the shared memory of a thread-block CLUSTER (8 CTAs: up to ~1.6 MB) --------------
+// The single-CTA kernel above is bound by what ONE SM can move to and from L2: a pivot rewrites the whole tableau (450 KB for
+// test/ex2.toml with 1x1 supports), ~20 us per pivot (ncu: long-scoreboard stalls 11 of 17, issue slots 35 %).  Here the
+// constraint rows are dealt out to the 8 CTAs of one cluster and never leave shared memory; what every CTA needs of the others
+// travels over distributed shared memory: the local winners of the ratio test are written into every CTA's slot array, the
+// pivot row is pulled from its owner's shared memory.  Objective row, basis labels and the choice of the entering column are
+// replicated (every CTA computes them from identical inputs in identical order, so they agree bit for bit).  Two cluster
+// barriers per pivot.
+constexpr int CLUSTER = 8;
+constexpr int CL_THREADS = 512;
+
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(CL_THREADS)
+lp_simplex_cluster_kernel(const double* __restrict__ T, int m, int n, const int* __restrict__ col_site, int max_pivots, int* __restrict__ info,
+                          int* __restrict__ weights /* [1024] zeroed */) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), tid = threadIdx.x, ld = n + 1;
+    const int rows_per = (m + CLUSTER - 1) / CLUSTER, row0 = rank * rows_per, my_rows = max(0, min(rows_per, m - row0));
+    extern __shared__ __align__(16) unsigned char dyn[];
+    double* Tl = reinterpret_cast<double*>(dyn);            // [rows_per][ld] my constraint rows (right-hand side at [n])
+    double* prow = Tl + (size_t)rows_per * ld;              // [ld] the new pivot row
+    double* obj = prow + ld;                                // [ld] objective row (replicated)
+    double* pcol = obj + ld;                                // [rows_per] my part of the entering column
+    ArgD* slots = reinterpret_cast<ArgD*>(pcol + rows_per); // [CLUSTER] local winners of the ratio test
+    int* basis = reinterpret_cast<int*>(slots + CLUSTER);   // [m] (replicated)
+    int* nonbasis = basis + m;                              // [n] (replicated)
+    __shared__ ArgD red[32];
+    for (int idx = tid; idx < my_rows * ld; idx += blockDim.x) Tl[idx] = T[(size_t)row0 * ld + idx];
+    for (int j = tid; j <= n; j += blockDim.x) obj[j] = T[(size_t)m * ld + j];
+    for (int i = tid; i < m; i += blockDim.x) basis[i] = n + i;
+    for (int j = tid; j < n; j += blockDim.x) nonbasis[j] = j;
+    cluster.sync();
+    int pivots = 0, optimal = 0;
+    for (; pivots < max_pivots; pivots++) {
+        ArgD e{0.0, 0x7fffffff};
+        for (int j = tid; j < n; j += blockDim.x) e = better_min(e, ArgD{obj[j], j});
+        e = block_argmin(e, red);
+        if (e.v > -EPS) { optimal = 1; break; }            // (identical in every CTA: nobody is left waiting at a barrier)
+        const int q = e.i;
+        ArgD r{1e300, 0x7fffffff};
+        for (int li = tid; li < my_rows; li += blockDim.x) {
+            const double a = Tl[(size_t)li * ld + q];
+            pcol[li] = a;
+            if (a > EPS) r = better_min(r, ArgD{Tl[(size_t)li * ld + n] / a, row0 + li});
+        }
+        r = block_argmin(r, red);
+        if (tid < CLUSTER) *cluster.map_shared_rank(&slots[rank], tid) = r;      // my winner into everybody's slot array
+        cluster.sync();
+        ArgD g = slots[0];
+#pragma unroll
+        for (int c = 1; c < CLUSTER; c++) g = better_min(g, slots[c]);
+        if (g.i == 0x7fffffff) break;                       // unbounded: cannot happen, never spin on it
+        const int pr = g.i, owner = pr / rows_per, lpr = pr - owner * rows_per;
+        const double* remote = cluster.map_shared_rank(Tl, owner) + (size_t)lpr * ld;   // the pivot row, in its owner's shared memory
+        const double inv = 1.0 / remote[q];
+        for (int j = tid; j <= n; j += blockDim.x) prow[j] = j == q ? inv : remote[j] * inv;
+        cluster.sync();                                     // everybody holds the pivot row: its owner may overwrite it now
+        for (int idx = tid; idx < my_rows * ld; idx += blockDim.x) {
+            const int li = idx / ld, j = idx - li * ld;
+            if (row0 + li == pr) { Tl[idx] = prow[j]; continue; }
+            const double f = pcol[li];
+            if (f != 0.0) Tl[idx] = j == q ? -f * inv : Tl[idx] - f * prow[j];
+        }
+        const double fo = obj[q];
+        __syncthreads();
+        for (int j = tid; j <= n; j += blockDim.x) obj[j] = j == q ? -fo * inv : obj[j] - fo * prow[j];
+        if (tid == 0) { const int t = basis[pr]; basis[pr] = nonbasis[q]; nonbasis[q] = t; }
+        __syncthreads();
+    }
+    for (int li = tid; li < my_rows; li += blockDim.x) {    // y -> integer weights: floor(y * SCALE) for my basic tiles
+        const int label = basis[row0 + li];
+        if (label >= n) continue;
+        const double y = Tl[(size_t)li * ld + n];
+        const long long k = y > 0.0 ? (long long)floor(y * (double)SCALE) : 0ll;
+        weights[col_site[label]] = (int)(k > (4ll << 20) ? (4ll << 20) : k);
+    }
+    if (rank == 0 && tid == 0) { info[0] = pivots; info[1] = optimal; }
+    cluster.sync();                                         // nobody exits while its shared memory may still be read remotely
+}
+
 // y -> integer weights per site (floor(y * SCALE), never negative), zero for non-basic tiles
 __global__ void lp_weights_kernel(const double* __restrict__ T, int m, int n, const int* __restrict__ basis, const int* __restrict__ col_site,
                                   int* __restrict__ weights /* [1024] zeroed */) {
@@ -229,8 +316,18 @@ int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::
     TSS_CUDA(e, cudaMemsetAsync(totals_dev, 0, sizeof(unsigned long long) * 2, e->stream));
     const int init_blocks = (int)((cells + 255) / 256 < (size_t)e->prop.multiProcessorCount * 8 ? (cells + 255) / 256 : (size_t)e->prop.multiProcessorCount * 8);
     lp::lp_init_kernel<<<init_blocks, 256, 0, e->stream>>>(reach, cons_dev, m, col_dev, n, T);
-    lp::lp_simplex_kernel<<<1, lp::THREADS, 0, e->stream>>>(T, m, n, basis, nonbasis, max_pivots > 0 ? max_pivots : 8 * (m + n), info_dev);
-    lp::lp_weights_kernel<<<(m + 255) / 256, 256, 0, e->stream>>>(T, m, n, basis, col_dev, weights);
+    const int pivots_cap = max_pivots > 0 ? max_pivots : 8 * (m + n);
+    const int rows_per = (m + lp::CLUSTER - 1) / lp::CLUSTER, ld = n + 1;
+    const size_t cl_smem = sizeof(double) * ((size_t)rows_per * ld + 2 * (size_t)ld + rows_per) + sizeof(lp::ArgD) * lp::CLUSTER + sizeof(int) * ((size_t)m + n);
+    const char* force = getenv("TSS_LP_SINGLE_CTA");       // (A/B switch for profiles/lb_stream.py)
+    if (cl_smem <= 200 * 1024 && !(force && force[0] == '1')) {
+        // the tableau fits the shared memory of one 8-CTA cluster: rows resident in shared memory, exchange over DSMEM
+        TSS_CUDA(e, cudaFuncSetAttribute(lp::lp_simplex_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_smem));
+        lp::lp_simplex_cluster_kernel<<<lp::CLUSTER, lp::CL_THREADS, cl_smem, e->stream>>>(T, m, n, col_dev, pivots_cap, info_dev, weights);
+    } else {
+        lp::lp_simplex_kernel<<<1, lp::THREADS, 0, e->stream>>>(T, m, n, basis, nonbasis, pivots_cap, info_dev);
+        lp::lp_weights_kernel<<<(m + 255) / 256, 256, 0, e->stream>>>(T, m, n, basis, col_dev, weights);
+    }
     lp::lp_certify_kernel<<<(n_place + 3) / 4, 128, 0, e->stream>>>(reach, n_place, weights, totals_dev);
     TSS_CHECK_LAUNCH(e);
     TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
