@@ -70,14 +70,14 @@ __global__ void __launch_bounds__(128) lp_reach_kernel(const uint32_t* __restric
 // condensed tableau, row-major with leading dimension ld = n + 1: rows 0..m-1 = constraints (column j = tile col_site[j],
 // column n = right-hand side), row m = objective (-1 per tile, value 0)
 __global__ void lp_init_kernel(const uint32_t* __restrict__ reach, const int* __restrict__ cons, int m, const int* __restrict__ col_site, int n,
-                               double* __restrict__ T) {
+                               double* __restrict__ T, double perturb) {
     const int ld = n + 1;
     const long long total = (long long)(m + 1) * ld;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(idx / ld), j = (int)(idx % ld);
         double v;
         if (i == m) v = j < n ? -1.0 : 0.0;
-        else if (j == n) v = 1.0 + 1e-7 * (double)((i * 37) % 101) / 101.0;   // tiny perturbation against degenerate ties (the certificate is exact anyway)
+        else if (j == n) v = 1.0 + perturb * (double)((i * 37) % 101) / 101.0;   // tiny perturbation against degenerate ties (the certificate is exact anyway)
         else {
             const int s = col_site[j];
             v = (double)((reach[(size_t)cons[i] * 32 + (s >> 5)] >> (s & 31)) & 1u);
@@ -315,7 +315,9 @@ int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::
     TSS_CUDA(e, cudaMemsetAsync(weights, 0, sizeof(int) * (1024 + 4), e->stream));
     TSS_CUDA(e, cudaMemsetAsync(totals_dev, 0, sizeof(unsigned long long) * 2, e->stream));
     const int init_blocks = (int)((cells + 255) / 256 < (size_t)e->prop.multiProcessorCount * 8 ? (cells + 255) / 256 : (size_t)e->prop.multiProcessorCount * 8);
-    lp::lp_init_kernel<<<init_blocks, 256, 0, e->stream>>>(reach, cons_dev, m, col_dev, n, T);
+    // (the size of the perturbation does not matter: 0 .. 1e-3 all need 1 300 - 1 800 pivots on the 21x16 terrains — the pivot count is
+    // Dantzig pricing on this LP, not degenerate stalling)
+    lp::lp_init_kernel<<<init_blocks, 256, 0, e->stream>>>(reach, cons_dev, m, col_dev, n, T, 1e-7);
     const int pivots_cap = max_pivots > 0 ? max_pivots : 8 * (m + n);
     const int rows_per = (m + lp::CLUSTER - 1) / lp::CLUSTER, ld = n + 1;
     const size_t cl_smem = sizeof(double) * ((size_t)rows_per * ld + 2 * (size_t)ld + rows_per) + sizeof(lp::ArgD) * lp::CLUSTER + sizeof(int) * ((size_t)m + n);
