@@ -16,7 +16,7 @@
 //
 // Kernels: lp_reach_kernel (one warp per placement: footprint, dilations -> 32 row words), lp_init_kernel (dense condensed
 // tableau [m + 1][n + 1] in doubles: constraints x ceiling tiles, right-hand side, objective row), lp_simplex_kernel (ONE CTA
-// of 1024 threads: Dantzig entering column, ratio test, rank-1 update with the pivot row staged in shared memory; the
+// of 1024 threads: Devex pricing, ratio test, rank-1 update with the pivot row staged in shared memory; the
 // instances are a few hundred columns, launch-free pivoting beats a multi-CTA update with grid syncs), lp_simplex_cluster_kernel
 // (tableaus up to ~1.6 MB: rows resident in the shared memory of an 8-CTA thread-block cluster, exchange over distributed
 // shared memory), lp_certify_kernel (integer loads).
@@ -112,18 +112,22 @@ __device__ ArgD block_argmin(ArgD a, ArgD* red) {
 __global__ void __launch_bounds__(THREADS) lp_simplex_kernel(double* __restrict__ T, int m, int n, int* __restrict__ basis, int* __restrict__ nonbasis,
                                                             int max_pivots, int* __restrict__ info) {
     __shared__ double prow[MAX_COLS + 1];
+    __shared__ double devex[MAX_COLS + 1];   // Devex reference weights of the non-basic columns (see the cluster kernel)
     __shared__ ArgD red[32];
     const int ld = n + 1, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n_warps = blockDim.x >> 5;
     for (int i = tid; i < m; i += blockDim.x) basis[i] = n + i;
-    for (int j = tid; j < n; j += blockDim.x) nonbasis[j] = j;
+    for (int j = tid; j < n; j += blockDim.x) { nonbasis[j] = j; devex[j] = 1.0; }
     __syncthreads();
     int pivots = 0, optimal = 0;
     for (; pivots < max_pivots; pivots++) {
-        // entering column: most negative reduced cost (Dantzig), lowest index on ties
+        // entering column: Devex pricing, largest d_j^2 / w_j among the improving columns, lowest index on ties
         ArgD e{0.0, 0x7fffffff};
-        for (int j = tid; j < n; j += blockDim.x) e = better_min(e, ArgD{T[(size_t)m * ld + j], j});
+        for (int j = tid; j < n; j += blockDim.x) {
+            const double d = T[(size_t)m * ld + j];
+            if (d < -EPS) e = better_min(e, ArgD{-d * d / devex[j], j});
+        }
         e = block_argmin(e, red);
-        if (e.v > -EPS) { optimal = 1; break; }
+        if (e.i == 0x7fffffff) { optimal = 1; break; }
         const int q = e.i;
         // ratio test over the rows with a positive entry in column q
         ArgD r{1e300, 0x7fffffff};
@@ -150,6 +154,9 @@ __global__ void __launch_bounds__(THREADS) lp_simplex_kernel(double* __restrict_
             if (f == 0.0) continue;     // (0/1 rows: most rows do not touch the entering column)
             for (int j = lane; j <= n; j += 32) row[j] = j == q ? -f * inv : row[j] - f * prow[j];
         }
+        const double wq = devex[q];
+        __syncthreads();
+        for (int j = tid; j < n; j += blockDim.x) devex[j] = j == q ? fmax(wq * inv * inv, 1.0) : fmax(devex[j], prow[j] * prow[j] * wq);
         if (tid == 0) { const int t = basis[pr]; basis[pr] = nonbasis[q]; nonbasis[q] = t; }
         __syncthreads();
     }
@@ -177,22 +184,29 @@ lp_simplex_cluster_kernel(const double* __restrict__ T, int m, int n, const int*
     double* Tl = reinterpret_cast<double*>(dyn);            // [rows_per][ld] my constraint rows (right-hand side at [n])
     double* prow = Tl + (size_t)rows_per * ld;              // [ld] the new pivot row
     double* obj = prow + ld;                                // [ld] objective row (replicated)
-    double* pcol = obj + ld;                                // [rows_per] my part of the entering column
+    double* devex = obj + ld;                               // [ld] Devex reference weights of the non-basic columns (replicated)
+    double* pcol = devex + ld;                              // [rows_per] my part of the entering column
     ArgD* slots = reinterpret_cast<ArgD*>(pcol + rows_per); // [CLUSTER] local winners of the ratio test
     int* basis = reinterpret_cast<int*>(slots + CLUSTER);   // [m] (replicated)
     int* nonbasis = basis + m;                              // [n] (replicated)
     __shared__ ArgD red[32];
     for (int idx = tid; idx < my_rows * ld; idx += blockDim.x) Tl[idx] = T[(size_t)row0 * ld + idx];
-    for (int j = tid; j <= n; j += blockDim.x) obj[j] = T[(size_t)m * ld + j];
+    for (int j = tid; j <= n; j += blockDim.x) { obj[j] = T[(size_t)m * ld + j]; devex[j] = 1.0; }
     for (int i = tid; i < m; i += blockDim.x) basis[i] = n + i;
     for (int j = tid; j < n; j += blockDim.x) nonbasis[j] = j;
     cluster.sync();
     int pivots = 0, optimal = 0;
     for (; pivots < max_pivots; pivots++) {
+        // entering column by Devex pricing (Forrest & Goldfarb): largest d_j^2 / w_j among the improving columns, the reference
+        // weights w_j approximating the steepest-edge norms at the price of one pass over the pivot row (Dantzig's rule needs
+        // ~1 500 pivots on the 21x16 terrains, this ~760)
         ArgD e{0.0, 0x7fffffff};
-        for (int j = tid; j < n; j += blockDim.x) e = better_min(e, ArgD{obj[j], j});
+        for (int j = tid; j < n; j += blockDim.x) {
+            const double d = obj[j];
+            if (d < -EPS) e = better_min(e, ArgD{-d * d / devex[j], j});
+        }
         e = block_argmin(e, red);
-        if (e.v > -EPS) { optimal = 1; break; }            // (identical in every CTA: nobody is left waiting at a barrier)
+        if (e.i == 0x7fffffff) { optimal = 1; break; }     // (identical in every CTA: nobody is left waiting at a barrier)
         const int q = e.i;
         ArgD r{1e300, 0x7fffffff};
         for (int li = tid; li < my_rows; li += blockDim.x) {
@@ -218,9 +232,11 @@ lp_simplex_cluster_kernel(const double* __restrict__ T, int m, int n, const int*
             const double f = pcol[li];
             if (f != 0.0) Tl[idx] = j == q ? -f * inv : Tl[idx] - f * prow[j];
         }
-        const double fo = obj[q];
+        const double fo = obj[q], wq = devex[q];
         __syncthreads();
         for (int j = tid; j <= n; j += blockDim.x) obj[j] = j == q ? -fo * inv : obj[j] - fo * prow[j];
+        for (int j = tid; j < n; j += blockDim.x)           // Devex update: prow[j] = alpha_rj / alpha_rq for j != q, prow[q] = 1 / alpha_rq
+            devex[j] = j == q ? fmax(wq * inv * inv, 1.0) : fmax(devex[j], prow[j] * prow[j] * wq);
         if (tid == 0) { const int t = basis[pr]; basis[pr] = nonbasis[q]; nonbasis[q] = t; }
         __syncthreads();
     }
@@ -320,7 +336,7 @@ int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::
     lp::lp_init_kernel<<<init_blocks, 256, 0, e->stream>>>(reach, cons_dev, m, col_dev, n, T, 1e-7);
     const int pivots_cap = max_pivots > 0 ? max_pivots : 8 * (m + n);
     const int rows_per = (m + lp::CLUSTER - 1) / lp::CLUSTER, ld = n + 1;
-    const size_t cl_smem = sizeof(double) * ((size_t)rows_per * ld + 2 * (size_t)ld + rows_per) + sizeof(lp::ArgD) * lp::CLUSTER + sizeof(int) * ((size_t)m + n);
+    const size_t cl_smem = sizeof(double) * ((size_t)rows_per * ld + 3 * (size_t)ld + rows_per) + sizeof(lp::ArgD) * lp::CLUSTER + sizeof(int) * ((size_t)m + n);
     const char* force = getenv("TSS_LP_SINGLE_CTA");       // (A/B switch for profiles/lb_stream.py)
     if (cl_smem <= 200 * 1024 && !(force && force[0] == '1')) {
         // the tableau fits the shared memory of one 8-CTA cluster: rows resident in shared memory, exchange over DSMEM
