@@ -78,6 +78,9 @@ typedef struct tss_stats {
 
 /* ------------------------------------------------------------------------------------------------ engine */
 int tss_version(void);
+/* Bounds-checked build only (nvcc -DTSS_CHECKED, profiles/checked_build.py): shared-memory accesses of the thread-per-chain SLS kernel
+ * that left their board since the library was loaded; -1 in the shipped build, which carries no checks. */
+int tss_debug_smem_violations(void);
 /* device < 0: current device.  Fails with TSS_E_CUDA when no CUDA device is usable (no CPU fallback). */
 int tss_engine_create(int device, tss_engine** out);
 void tss_engine_destroy(tss_engine* e);

@@ -48,6 +48,7 @@ _vp, _i32, _i64, _u64, _u32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64,
 _u8p, _i32p, _u32p, _i64p = _P(C.c_uint8), _P(C.c_int32), _P(C.c_uint32), _P(C.c_int64)
 SIGNATURES = {
     "tss_version": (C.c_int, []),
+    "tss_debug_smem_violations": (C.c_int, []),
     "tss_engine_create": (C.c_int, [C.c_int, _P(_vp)]),
     "tss_engine_destroy": (None, [_vp]),
     "tss_engine_set_stream": (C.c_int, [_vp, _vp]),

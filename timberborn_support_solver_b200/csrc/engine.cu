@@ -23,6 +23,8 @@ int sls_best_reduce(tss_engine* e, const sls::ChainState* states, int chains_per
 // sls_t16.cu — one chain per thread for grids of at most 16 rows x 26 columns (chains_per_terrain 0 or a multiple of the CTA size)
 bool sls_t16_fits(int w, int h);
 int sls_t16_cta_chains();
+int sls_t16_smem_violations();
+int sls_t16_checked_build();
 size_t sls_t16_list_words(int n_chains);
 int sls_run_t16(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, sls::ChainState* states, uint32_t* site_lists, int n_chains,
                 int chains_per_terrain, uint32_t chain_offset, uint64_t seed, long long steps, const int* bounds_dev, int target,
@@ -199,6 +201,8 @@ static double now_ms() {
 extern "C" {
 
 int tss_version(void) { return TSS_VERSION; }
+
+int tss_debug_smem_violations(void) { return sls_t16_checked_build() ? sls_t16_smem_violations() : -1; }
 
 int tss_engine_create(int device, tss_engine** out) {
     if (!out) return TSS_E_INVALID;

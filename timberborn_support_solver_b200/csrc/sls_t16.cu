@@ -56,6 +56,30 @@ struct Smem {
 };
 constexpr int BOARD = 16 * NT;             // words between the same row of consecutive boards
 
+// ---- bounds-checked build (-DTSS_CHECKED, profiles/checked_build.py): compute-sanitizer is closed on the B200 pool, and this kernel
+// aliases neighbouring boards on purpose (rows outside the grid), so the claim "every access stays inside the CTA's Smem block,
+// every STORE lands in a row of the grid of the board it means" is checked by the kernel itself: each shared-memory access of the
+// step loop goes through these two functions, violations are counted in a device global (tss_debug_smem_violations()).
+#ifdef TSS_CHECKED
+__device__ unsigned int g_smem_violations = 0;
+__device__ __forceinline__ const uint32_t* chk_ld(const Smem& sm, const uint32_t* p) {
+    const size_t off = (size_t)((const char*)p - (const char*)&sm);
+    if (off + 4 > sizeof(Smem) || (off & 3)) { atomicAdd(&g_smem_violations, 1u); return &sm.rows[0][0]; }
+    return p;
+}
+// a store into row `row` (0..15) of board `board` for thread tid, and nowhere else
+__device__ __forceinline__ uint32_t* chk_st(Smem& sm, uint32_t* p, int board, int tid) {
+    const ptrdiff_t off = p - &sm.rows[board * 16][0];
+    if (off < 0 || off >= 16 * NT || (off % NT) != tid) { atomicAdd(&g_smem_violations, 1u); return &sm.rows[board * 16][tid]; }
+    return p;
+}
+#define LD(p) (*chk_ld(sm, (p)))
+#define ST(p, board) (*chk_st(sm, (p), (board), tid))
+#else
+#define LD(p) (*(p))
+#define ST(p, board) (*(p))
+#endif
+
 __device__ __forceinline__ int pick_rotated(uint32_t bits, uint32_t o) {
     uint32_t rot = __funnelshift_r(bits, bits, o);
     return (int)((__ffs(rot) - 1 + o) & 31u);
@@ -76,8 +100,8 @@ __device__ __forceinline__ void flip(Smem& sm, int tid, int v, uint32_t& rowmask
         const uint32_t m7 = (j < 4 ? win.x >> (8 * j) : win.y >> (8 * (j - 4))) & 0xffu;
         const int off = (j - 3) * NT;
         uint32_t m = m7 << x;
-        uint32_t a0 = p[B_C0 * BOARD + off], a1 = p[B_C1 * BOARD + off], a2 = p[B_C2 * BOARD + off], t;
-        uint32_t a3 = p[B_C3 * BOARD + off], a4 = p[B_C4 * BOARD + off];
+        uint32_t a0 = LD(p + B_C0 * BOARD + off), a1 = LD(p + B_C1 * BOARD + off), a2 = LD(p + B_C2 * BOARD + off), t;
+        uint32_t a3 = LD(p + B_C3 * BOARD + off), a4 = LD(p + B_C4 * BOARD + off);
         if (ADD) {
             t = a0 & m; a0 ^= m; m = t;
             t = a1 & m; a1 ^= m; m = t;
@@ -89,14 +113,14 @@ __device__ __forceinline__ void flip(Smem& sm, int tid, int v, uint32_t& rowmask
         }
         if (m) {  // a count crossing 7 <-> 8: rare
             if (ADD) { t = a3 & m; a3 ^= m; a4 ^= t; } else { t = ~a3 & m; a3 ^= m; a4 ^= t; }
-            p[B_C3 * BOARD + off] = a3; p[B_C4 * BOARD + off] = a4;
+            ST(p + B_C3 * BOARD + off, B_C3) = a3; ST(p + B_C4 * BOARD + off, B_C4) = a4;
         }
         const uint32_t hi = a1 | a2 | a3 | a4, C = sm.C[y + j];  // C[r + 3] = row r
         const uint32_t Un = C & ~(a0 | hi);
         if (m7) {
-            p[B_C0 * BOARD + off] = a0; p[B_C1 * BOARD + off] = a1; p[B_C2 * BOARD + off] = a2;
-            p[B_U * BOARD + off] = Un;
-            p[B_O * BOARD + off] = a0 & ~hi & C;
+            ST(p + B_C0 * BOARD + off, B_C0) = a0; ST(p + B_C1 * BOARD + off, B_C1) = a1; ST(p + B_C2 * BOARD + off, B_C2) = a2;
+            ST(p + B_U * BOARD + off, B_U) = Un;
+            ST(p + B_O * BOARD + off, B_O) = a0 & ~hi & C;
         }
         nz |= Un ? 1u << j : 0u;
     }
@@ -261,7 +285,7 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
                     const uint32_t* p = Ob + (v >> 5) * NT;
                     uint32_t r7[7];
 #pragma unroll
-                    for (int j = 0; j < 7; j++) r7[j] = p[(j - 3) * NT] >> x;
+                    for (int j = 0; j < 7; j++) r7[j] = LD(p + (j - 3) * NT) >> x;
                     const uint32_t lo = pack4(r7[0], r7[1], r7[2], r7[3]);
                     const uint32_t hi = pack3(r7[4], r7[5], r7[6]);
                     const uint32_t loss = (uint32_t)(__popc(lo & win.x) + __popc(hi & win.y));
@@ -288,7 +312,7 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
                 const uint2 wt = tabt[0];
                 uint32_t R[13];  // rows y-6 .. y+6 of U; bit b of R[j] = tile column b + x - 6
 #pragma unroll
-                for (int j = 0; j < 13; j++) R[j] = (Up[(j - 6) * NT] << 3) >> x;
+                for (int j = 0; j < 13; j++) R[j] = (LD(Up + (j - 6) * NT) << 3) >> x;
                 const bool noise = ((hs >> 10) & 127u) < nq7;
                 uint32_t tw_lo = 0, tw_hi = 0;  // sites removed fewer than `ten` steps ago, as a byte-per-row window around t (rows 0-3 / 4-6)
                 for (int j = 0; j < ten; j++) {
@@ -338,6 +362,23 @@ __global__ void __launch_bounds__(NT, 3) sls_t16_kernel(const uint32_t* __restri
 
 }  // namespace slst
 
+// violations counted by a -DTSS_CHECKED build since the library was loaded (always 0 in the shipped build, which has no checks)
+int sls_t16_smem_violations() {
+#ifdef TSS_CHECKED
+    unsigned int v = 0;
+    if (cudaMemcpyFromSymbol(&v, slst::g_smem_violations, sizeof v) != cudaSuccess) return -1;
+    return (int)v;
+#else
+    return 0;
+#endif
+}
+int sls_t16_checked_build() {
+#ifdef TSS_CHECKED
+    return 1;
+#else
+    return 0;
+#endif
+}
 bool sls_t16_fits(int w, int h) { return h <= 16 && w <= slst::MAXW; }
 int sls_t16_cta_chains() { return slst::NT; }
 size_t sls_t16_list_words(int n_chains) { return (size_t)16 * slst::MAXW * (((size_t)n_chains + 31) & ~(size_t)31); }
