@@ -13,7 +13,8 @@
 // (`--exact CMD`, any DIMACS solver that prints `s SATISFIABLE|UNSATISFIABLE` and `v ...` lines, e.g. `z3 -dimacs`, glucose,
 // kissat) or from the packing lower bound meeting the count (tss_lower_bound).
 //
-//   tss_repl PROJECT.toml [--platforms default|1x1] [-l k:v[,k:v]] [--exact "CMD"] [--seed N] [--no-lower-bound] [--quiet]
+//   tss_repl PROJECT.toml [--platforms default|1x1] [-l k:v[,k:v]] [--exact "CMD"] [--seed N] [--no-lower-bound] [--quiet] [--repeat N]
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -93,6 +94,7 @@ int main(int argc, char** argv) {
     std::vector<int32_t> card;
     uint64_t seed = 0;
     bool use_lb = true, quiet = false;
+    int repeat = 1;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         if (a == "--platforms" && i + 1 < argc) platforms = argv[++i];
@@ -102,6 +104,7 @@ int main(int argc, char** argv) {
         else if (a.rfind("-l", 0) == 0 && a.size() > 2) { if (!parse_limits(a.substr(2), card)) { std::fprintf(stderr, "bad -l argument\n"); return 2; } }
         else if (a == "--no-lower-bound") use_lb = false;
         else if (a == "--quiet") quiet = true;
+        else if (a == "--repeat" && i + 1 < argc) repeat = std::atoi(argv[++i]) > 0 ? std::atoi(argv[i]) : 1;
         else if (project.empty()) project = a;
         else { std::fprintf(stderr, "usage: tss_repl PROJECT.toml [--platforms default|1x1] [-l k:v[,k:v]] [--exact CMD] [--seed N] [--no-lower-bound] [--quiet]\n"); return 2; }
     }
@@ -125,115 +128,130 @@ int main(int argc, char** argv) {
 
     tss_engine* e = nullptr;
     if (tss_engine_create(-1, &e) != TSS_OK) { std::fprintf(stderr, "no usable CUDA device (the GPU path has no CPU fallback)\n"); return 1; }
-    tss_encoding* enc = nullptr;
-    if (tss_encoding_create(grid.data(), w, h, all_defs, n_defs, &enc) != TSS_OK) { std::fprintf(stderr, "encode failed\n"); return 1; }
-    int32_t K = 0;
-    tss_encoding_sizes(enc, nullptr, nullptr, nullptr, &K);
-
-    bool only_count = true;   // the lower bound speaks about the platform count: usable when that is the only limit
-    for (size_t i = 0; i + 2 < card.size(); i += 3) only_count = only_count && card[i] == 1 && card[i + 1] == 1;
-    const double t_loop = now_ms();   // (engine creation = CUDA context start-up, ~1 s of a fresh process, is reported apart)
+    const double t_setup = now_ms();
+    // --repeat N: the whole `solve` N times in this process (fresh encoding, limits and bounds each time; the engine and its
+    // cached workspaces stay), printing only the first: the loop's warm timing without process start-up
+    const std::vector<int32_t> card0 = card;
+    std::vector<double> loop_ms;
     int32_t lower = -1;
-    if (use_lb && only_count && w <= 32 && h <= 32) {
-        if (tss_lower_bound(e, grid.data(), w, h, all_defs, n_defs, seed, 0, nullptr, 0, &lower) != TSS_OK) lower = -1;
-
-        if (!quiet && lower >= 0) std::printf("Lower bound: %d platforms\n", lower);
-    }
-
-    int64_t give_up = 1024;
     int gpu_solves = 0, exact_solves = 0, best = -1;
-    bool lp_done = false;   // the fractional bound (a simplex solve) is only computed when the packing bound does not already close the gap
     std::string verdict = "open";
-    for (;;) {
-        // the 1x1 limit of this iteration (PlatformLimits.card_limits[1x1], main.rs:346)
-        int bound = -1;
-        for (size_t i = 0; i < card.size(); i += 3)
-            if (card[i] == 1 && card[i + 1] == 1) bound = card[i + 2];
-        if (lower >= 0 && best >= 0 && bound >= 0 && bound < lower) {   // nothing below the lower bound exists
-            std::printf("No solution found for the current constraints\n");
-            verdict = "optimal (lower bound)";
-            break;
-        }
-        int32_t n_vars = 0, n_clauses = 0;
-        int64_t n_lits = 0;
-        tss_encoding_with_limits(enc, card.data(), (int32_t)card.size() / 3, nullptr, 0, 0, 0, &n_vars, &n_clauses, &n_lits, nullptr, nullptr);
-        std::vector<int32_t> lits((size_t)n_lits + 1);
-        std::vector<uint32_t> offsets((size_t)n_clauses + 1);
-        tss_encoding_with_limits(enc, card.data(), (int32_t)card.size() / 3, nullptr, 0, 0, 0, &n_vars, &n_clauses, &n_lits, lits.data(), offsets.data());
-        lits.resize((size_t)n_lits);
+    double t_loop = now_ms();
+    for (int rep = 0; rep < repeat; rep++) {
+        const bool say = rep == 0;
+#define SAY(...) do { if (say) std::printf(__VA_ARGS__); } while (0)
+        card = card0;
+        lower = -1; gpu_solves = exact_solves = 0; best = -1; verdict = "open";
+        t_loop = now_ms();   // one `solve`: encode, bounds, loop (engine creation = CUDA context start-up, ~1-4 s of a fresh process, is reported apart)
+        tss_encoding* enc = nullptr;
+        if (tss_encoding_create(grid.data(), w, h, all_defs, n_defs, &enc) != TSS_OK) { std::fprintf(stderr, "encode failed\n"); return 1; }
+        int32_t K = 0;
+        tss_encoding_sizes(enc, nullptr, nullptr, nullptr, &K);
 
-        // ---- Solve::add_cnf: all the solver is given are the clauses
-        tss_cnf* cnf = nullptr;
-        if (tss_cnf_upload(e, lits.data(), offsets.data(), n_clauses, n_vars, &cnf) != TSS_OK) { std::fprintf(stderr, "%s\n", tss_last_error(e)); return 1; }
-        tss_encoding* inst = nullptr;
-        tss_instance_info info;
-        const int found = tss_instance_find(lits.data(), offsets.data(), n_clauses, n_vars, &inst, &info, nullptr, 0);
+        bool only_count = true;   // the lower bound speaks about the platform count: usable when that is the only limit
+        for (size_t i = 0; i + 2 < card.size(); i += 3) only_count = only_count && card[i] == 1 && card[i + 1] == 1;
+        if (use_lb && only_count && w <= 32 && h <= 32) {
+            if (tss_lower_bound(e, grid.data(), w, h, all_defs, n_defs, seed, 0, nullptr, 0, &lower) != TSS_OK) lower = -1;
 
-        // ---- Solve::solve
-        std::vector<uint8_t> assignment((size_t)n_vars + 1, 2);
-        int result = 0;
-        std::string source = "gpu";
-        if (found == TSS_SAT) {
-            tss_clear_interrupt(e);
-            const int rc = tss_solve_instance(e, cnf, inst, &info, nullptr, seed++, give_up, assignment.data());
-            if (rc < 0) std::fprintf(stderr, "tss_solve_instance: %s\n", tss_last_error(e));   // logged, never fatal (crates/gui/src/app.rs:160-173)
-            result = rc == TSS_SAT ? 10 : 0;
-            gpu_solves++;
-            if (result == 10) {
-                tss_stats st;
-                tss_get_stats(e, &st);
-                give_up = 32 * st.last_solve_steps > 1024 ? 32 * st.last_solve_steps : 1024;
-            }
+            if (!quiet && lower >= 0) SAY("Lower bound: %d platforms\n", lower);
         }
-        if (result == 0 && lower >= 0 && !lp_done && best >= 0) {   // the GPU found nothing below the current count: can the fractional bound certify it?
-            lp_done = true;
-            int32_t lp_bound = 0;
-            if (tss_lower_bound_lp(e, grid.data(), w, h, all_defs, n_defs, 0, nullptr, nullptr, nullptr, &lp_bound, nullptr) == TSS_OK && lp_bound > lower) {
-                lower = lp_bound;
-                if (!quiet) std::printf("Lower bound (fractional): %d platforms\n", lower);
-            }
-            if (bound >= 0 && bound < lower) {
-                if (inst) tss_encoding_destroy(inst);
-                tss_cnf_destroy(cnf);
-                std::printf("No solution found for the current constraints\n");
+
+        int64_t give_up = 1024;
+        bool lp_done = false;   // the fractional bound (a simplex solve) is only computed when the packing bound does not already close the gap
+        for (;;) {
+            // the 1x1 limit of this iteration (PlatformLimits.card_limits[1x1], main.rs:346)
+            int bound = -1;
+            for (size_t i = 0; i < card.size(); i += 3)
+                if (card[i] == 1 && card[i + 1] == 1) bound = card[i + 2];
+            if (lower >= 0 && best >= 0 && bound >= 0 && bound < lower) {   // nothing below the lower bound exists
+                SAY("No solution found for the current constraints\n");
                 verdict = "optimal (lower bound)";
                 break;
             }
-        }
-        if (result == 0 && !exact_cmd.empty()) {   // the exact solver: every UNSAT answer comes from here
-            result = run_exact(exact_cmd, lits, offsets, n_vars, assignment);
-            source = "exact";
-            exact_solves++;
-        }
-        if (inst) tss_encoding_destroy(inst);
-        tss_cnf_destroy(cnf);
-        if (result == 20) { std::printf("No solution found for the current constraints\n"); verdict = best >= 0 ? "optimal (exact solver)" : "unsatisfiable"; break; }
-        if (result != 10) { std::printf("Solver interrupted\n"); verdict = "unknown (no exact solver answer)"; break; }
+            int32_t n_vars = 0, n_clauses = 0;
+            int64_t n_lits = 0;
+            tss_encoding_with_limits(enc, card.data(), (int32_t)card.size() / 3, nullptr, 0, 0, 0, &n_vars, &n_clauses, &n_lits, nullptr, nullptr);
+            std::vector<int32_t> lits((size_t)n_lits + 1);
+            std::vector<uint32_t> offsets((size_t)n_clauses + 1);
+            tss_encoding_with_limits(enc, card.data(), (int32_t)card.size() / 3, nullptr, 0, 0, 0, &n_vars, &n_clauses, &n_lits, lits.data(), offsets.data());
+            lits.resize((size_t)n_lits);
 
-        std::vector<tss_platform> plats((size_t)w * h + 1);
-        int32_t n = 0;
-        tss_layout_from_assignment(enc, assignment.data(), n_vars + 1, plats.data(), (int32_t)plats.size(), &n);
-        if (n == 0) { std::printf("Found a solution with no platforms - aborting\n"); verdict = "optimal (no platforms)"; best = 0; break; }
-        best = n;
-        bool has = false;
-        for (size_t i = 0; i < card.size(); i += 3)
-            if (card[i] == 1 && card[i + 1] == 1) { card[i + 2] = n - 1; has = true; }
-        if (!has) { card.push_back(1); card.push_back(1); card.push_back(n - 1); }
-        std::printf("Solution found (%d platforms total)\n", n);
-        std::map<std::pair<int, int>, int> stats;
-        for (int i = 0; i < n; i++) stats[{plats[i].def_w, plats[i].def_h}]++;
-        for (auto& [d, c] : stats) std::printf("%dx%d: %d\n", d.first, d.second, c);
-        std::vector<uint8_t> unsupported((size_t)w * h), flags((size_t)n);
-        const int uns = tss_validate(e, grid.data(), w, h, plats.data(), n, unsupported.data(), flags.data());
-        int bad = uns;
-        for (int i = 0; i < n; i++) bad += flags[i] != 0;
-        if (!quiet) std::printf(bad == 0 ? "Solution validation OK (%s)\n" : "Solution validation FAILED (%s)\n", source.c_str());
-        if (bad != 0) { verdict = "invalid layout"; break; }
+            // ---- Solve::add_cnf: all the solver is given are the clauses
+            tss_cnf* cnf = nullptr;
+            if (tss_cnf_upload(e, lits.data(), offsets.data(), n_clauses, n_vars, &cnf) != TSS_OK) { std::fprintf(stderr, "%s\n", tss_last_error(e)); return 1; }
+            tss_encoding* inst = nullptr;
+            tss_instance_info info;
+            const int found = tss_instance_find(lits.data(), offsets.data(), n_clauses, n_vars, &inst, &info, nullptr, 0);
+
+            // ---- Solve::solve
+            std::vector<uint8_t> assignment((size_t)n_vars + 1, 2);
+            int result = 0;
+            std::string source = "gpu";
+            if (found == TSS_SAT) {
+                tss_clear_interrupt(e);
+                const int rc = tss_solve_instance(e, cnf, inst, &info, nullptr, seed++, give_up, assignment.data());
+                if (rc < 0) std::fprintf(stderr, "tss_solve_instance: %s\n", tss_last_error(e));   // logged, never fatal (crates/gui/src/app.rs:160-173)
+                result = rc == TSS_SAT ? 10 : 0;
+                gpu_solves++;
+                if (result == 10) {
+                    tss_stats st;
+                    tss_get_stats(e, &st);
+                    give_up = 32 * st.last_solve_steps > 1024 ? 32 * st.last_solve_steps : 1024;
+                }
+            }
+            if (result == 0 && lower >= 0 && !lp_done && best >= 0) {   // the GPU found nothing below the current count: can the fractional bound certify it?
+                lp_done = true;
+                int32_t lp_bound = 0;
+                if (tss_lower_bound_lp(e, grid.data(), w, h, all_defs, n_defs, 0, nullptr, nullptr, nullptr, &lp_bound, nullptr) == TSS_OK && lp_bound > lower) {
+                    lower = lp_bound;
+                    if (!quiet) SAY("Lower bound (fractional): %d platforms\n", lower);
+                }
+                if (bound >= 0 && bound < lower) {
+                    if (inst) tss_encoding_destroy(inst);
+                    tss_cnf_destroy(cnf);
+                    SAY("No solution found for the current constraints\n");
+                    verdict = "optimal (lower bound)";
+                    break;
+                }
+            }
+            if (result == 0 && !exact_cmd.empty()) {   // the exact solver: every UNSAT answer comes from here
+                result = run_exact(exact_cmd, lits, offsets, n_vars, assignment);
+                source = "exact";
+                exact_solves++;
+            }
+            if (inst) tss_encoding_destroy(inst);
+            tss_cnf_destroy(cnf);
+            if (result == 20) { SAY("No solution found for the current constraints\n"); verdict = best >= 0 ? "optimal (exact solver)" : "unsatisfiable"; break; }
+            if (result != 10) { SAY("Solver interrupted\n"); verdict = "unknown (no exact solver answer)"; break; }
+
+            std::vector<tss_platform> plats((size_t)w * h + 1);
+            int32_t n = 0;
+            tss_layout_from_assignment(enc, assignment.data(), n_vars + 1, plats.data(), (int32_t)plats.size(), &n);
+            if (n == 0) { SAY("Found a solution with no platforms - aborting\n"); verdict = "optimal (no platforms)"; best = 0; break; }
+            best = n;
+            bool has = false;
+            for (size_t i = 0; i < card.size(); i += 3)
+                if (card[i] == 1 && card[i + 1] == 1) { card[i + 2] = n - 1; has = true; }
+            if (!has) { card.push_back(1); card.push_back(1); card.push_back(n - 1); }
+            SAY("Solution found (%d platforms total)\n", n);
+            std::map<std::pair<int, int>, int> stats;
+            for (int i = 0; i < n; i++) stats[{plats[i].def_w, plats[i].def_h}]++;
+            for (auto& [d, c] : stats) SAY("%dx%d: %d\n", d.first, d.second, c);
+            std::vector<uint8_t> unsupported((size_t)w * h), flags((size_t)n);
+            const int uns = tss_validate(e, grid.data(), w, h, plats.data(), n, unsupported.data(), flags.data());
+            int bad = uns;
+            for (int i = 0; i < n; i++) bad += flags[i] != 0;
+            if (!quiet) SAY(bad == 0 ? "Solution validation OK (%s)\n" : "Solution validation FAILED (%s)\n", source.c_str());
+            if (bad != 0) { verdict = "invalid layout"; break; }
+        }
+        tss_encoding_destroy(enc);
+        loop_ms.push_back(now_ms() - t_loop);
     }
     std::printf("Done\n");
-    std::printf("# best=%d lower_bound=%d verdict=\"%s\" gpu_solves=%d exact_solves=%d ms=%.3f setup_ms=%.1f\n", best, lower, verdict.c_str(), gpu_solves,
-                exact_solves, now_ms() - t_loop, t_loop - t_start);
-    tss_encoding_destroy(enc);
+    std::sort(loop_ms.begin() + (loop_ms.size() > 1 ? 1 : 0), loop_ms.end());   // the first run is cold (allocations): median of the rest
+    const double warm = loop_ms.size() > 1 ? loop_ms[1 + (loop_ms.size() - 1) / 2] : loop_ms[0];
+    std::printf("# best=%d lower_bound=%d verdict=\"%s\" gpu_solves=%d exact_solves=%d ms=%.3f setup_ms=%.1f repeats=%zu warm_ms=%.3f\n", best, lower,
+                verdict.c_str(), gpu_solves, exact_solves, loop_ms[0], t_setup - t_start, loop_ms.size(), warm);
     tss_engine_destroy(e);
     return 0;
 }
