@@ -799,6 +799,27 @@ def main():
             assert res == T.SAT and lay2.platform_count() == opt3
         line["other_configs"]["c3"] = {"workload": "README 21x16 terrain, 1x1 supports (BASELINE.json configs[2])", "count": opt3, "proven_optimum": opt3, "ms": float(np.median(t3s[2:])),
                                        "note": "tss_solve_upper_bound(card_limit=14) from host buffers, median of 5 calls after 2 warm-up calls; the README transcript stops at 15 (README.md:117-119)"}
+        # ---------------- the placement search (platform sets beyond {1x1}: what the REPL actually runs, main.rs:254) in throughput mode
+        sp = eng.search(T.WorldGrid(named_grid(fx, "ex2")), T.PLATFORMS_DEFAULT, seed=1, n_chains=info["sm_count"] * 32)
+        for _ in range(2):
+            sp.run(512, 0)
+        sp.best_count()
+        p0 = eng.stats()
+        pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pa.record()
+        for _ in range(5):
+            sp.run(2048, 0)
+        pb.record()
+        torch.cuda.synchronize()
+        pbest = sp.best_count()
+        p1 = eng.stats()
+        pms = pa.elapsed_time(pb)
+        line["other_configs"]["placement_search"] = {
+            "workload": "test/ex2.toml, the REPL's default-8 platform set, sls_multi_kernel (one chain per warp, objective = number of platforms)",
+            "flips_per_s": (p1["sls_flips"] - p0["sls_flips"]) / (pms * 1e-3), "placements_scored_per_s": (p1["candidates_scored"] - p0["candidates_scored"]) / (pms * 1e-3),
+            "sls_steps_per_s": (p1["sls_steps"] - p0["sls_steps"]) / (pms * 1e-3), "chains": sp.n_chains, "ms": pms, "best_count": pbest,
+            "proven_optimum": proven_optimum("ex2/default8")}
+        sp.close()
         # ---------------- CPU baseline (bounded sample, rank 0, N = 1): the same step rule, chains and unit on the host cores
         rate, epoch_ms, threads, n_cpu, cpu_best, sample = cpu_flips(grid.data, args.epoch_steps, 3, 12)
         given, unbounded = cdcl_time_to_optimum(grid.data, OPTIMUM_RECT16)      # 1 thread like the reference
