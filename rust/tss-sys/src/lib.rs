@@ -152,6 +152,15 @@ unsafe extern "C" {
         n_out: *mut i32,
     ) -> c_int;
 
+    pub fn tss_lower_bound_lp(
+        e: *mut tss_engine, grid: *const u8, w: i32, h: i32, defs: *const tss_dims, n_defs: i32, max_pivots: i32, out_weights: *mut i32,
+        out_total: *mut i64, out_max_load: *mut i64, out_bound: *mut i32, out_info: *mut i32,
+    ) -> c_int;
+    pub fn tss_encoding_terrain(enc: *const tss_encoding, grid: *mut u8, cap: usize, w: *mut i32, h: *mut i32) -> c_int;
+    pub fn tss_encoding_defs(enc: *const tss_encoding, defs: *mut tss_dims, cap: i32, n: *mut i32) -> c_int;
+    pub fn tss_cnf_num_vars(c: *const tss_cnf) -> c_int;
+    pub fn tss_debug_smem_violations() -> c_int;
+
     // a persistent portfolio instead of one-shot calls
     pub fn tss_search_create(
         e: *mut tss_engine, grid: *const u8, w: i32, h: i32, defs: *const tss_dims, n_defs: i32, params: *const tss_search_params,
@@ -159,6 +168,7 @@ unsafe extern "C" {
     ) -> c_int;
     pub fn tss_search_destroy(s: *mut tss_search);
     pub fn tss_search_run(s: *mut tss_search, steps: i64, target_count: i32) -> c_int;
+    pub fn tss_search_kernel(s: *const tss_search) -> c_int;
     pub fn tss_search_best_count(s: *mut tss_search, count: *mut i32) -> c_int;
     pub fn tss_search_set_bound(s: *mut tss_search, count: i32) -> c_int;
     pub fn tss_search_write_chains(s: *mut tss_search, rows: *const u32) -> c_int;
