@@ -762,7 +762,12 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
     only_count = not limits.weights and limits.weight_limit is None and all(d == one for d in limits.card_limits)
     use_lower_bound = use_lower_bound and only_count and g.width <= 32 and g.height <= 32
     if use_lower_bound:
-        lower = len(engine.lower_bound(g, encoding.defs, seed=seed))
+        try:
+            lower = len(engine.lower_bound(g, encoding.defs, seed=seed))
+        except TssError as err:             # a platform set the bound kernels do not take (more than 16 dims keys): carry on without bounds
+            if err.code != _lib.TSS_E_UNSUPPORTED:
+                raise
+            use_lower_bound = False
     while True:
         bound_now = limits.card_limits.get(one)
         if lower is not None and best is not None and bound_now is not None and bound_now < lower:
