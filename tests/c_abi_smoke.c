@@ -104,6 +104,60 @@ int main(void) {
     CHECK(tss_search_write_chains(search, rows) == TSS_E_INVALID);
     tss_search_destroy(search);
 
+    /* ---- round 2: certified lower bounds and the instance bridge, as a plain C host uses them */
+    int32_t xy[2 * 64], n_packed = -1;
+    CHECK(tss_lower_bound(e, grid, w, h, defs, 1, 1, 0, xy, 64, &n_packed) == TSS_OK && n_packed == 3);      /* ex1, 1x1 supports: 3 = the optimum */
+    CHECK(tss_lower_bound(e, grid, w, h, defs, 8, 1, 0, xy, 64, &n_packed) == TSS_OK && n_packed == 1);      /* default-8: one 5x5 covers everything */
+    CHECK(tss_lower_bound(e, grid, w, h, defs, 1, 1, 0, xy, 2, &n_packed) == TSS_E_CAPACITY && n_packed == 3);
+    CHECK(tss_lower_bound(e, grid, w, h, defs, 1, 1, 0, NULL, 0, &n_packed) == TSS_OK && n_packed == 3);      /* the bound alone */
+    CHECK(tss_lower_bound(e, grid, w, h, bad, 1, 1, 0, xy, 64, &n_packed) == TSS_E_INVALID);
+    CHECK(tss_lower_bound(e, NULL, w, h, defs, 1, 1, 0, xy, 64, &n_packed) == TSS_E_INVALID);
+    int32_t lp_w[64], lp_bound = -1, lp_info[3];
+    int64_t lp_total = 0, lp_max = 0;
+    CHECK(tss_lower_bound_lp(e, grid, w, h, defs, 1, 0, lp_w, &lp_total, &lp_max, &lp_bound, lp_info) == TSS_OK);
+    CHECK(lp_bound == 3 && lp_max > 0 && lp_bound == (int32_t)((lp_total + lp_max - 1) / lp_max) && lp_info[1] == 1 && lp_info[2] == 19);
+    int64_t sum = 0;
+    for (int i = 0; i < w * h; i++) { CHECK(lp_w[i] >= 0 && (grid[i] || lp_w[i] == 0)); sum += lp_w[i]; }
+    CHECK(sum == lp_total);
+    CHECK(tss_lower_bound_lp(e, grid, w, h, defs, 1, 0, NULL, NULL, NULL, &lp_bound, NULL) == TSS_OK && lp_bound == 3);
+    CHECK(tss_lower_bound_lp(e, grid, w, h, defs, 1, 0, NULL, NULL, NULL, NULL, NULL) == TSS_E_INVALID);
+
+    /* Solve::add_cnf + Solve::solve of the Rust shim: the solver is handed clauses only (solver_runner.rs:8-20) */
+    {
+        const int32_t card[3] = {1, 1, 3};                      /* PlatformLimits.card_limits[1x1] = 3 (main.rs:346) */
+        tss_encoding* enc1 = NULL;
+        CHECK(tss_encoding_create(grid, w, h, defs, 1, &enc1) == TSS_OK);
+        int32_t nv = 0, nc = 0;
+        int64_t nl = 0;
+        CHECK(tss_encoding_with_limits(enc1, card, 1, NULL, 0, 0, 0, &nv, &nc, &nl, NULL, NULL) == TSS_OK);   /* sizes only: records nothing */
+        int32_t* l2 = malloc(sizeof(int32_t) * (size_t)(nl + 1));
+        uint32_t* o2 = malloc(sizeof(uint32_t) * (size_t)(nc + 1));
+        uint8_t* a2 = malloc((size_t)nv + 1);
+        CHECK(l2 && o2 && a2);
+        CHECK(tss_encoding_with_limits(enc1, card, 1, NULL, 0, 0, 0, &nv, &nc, &nl, l2, o2) == TSS_OK);       /* ... this one records the instance */
+        tss_encoding_destroy(enc1);                              /* the owner may drop its handle: the registry keeps the instance */
+        tss_cnf* c2 = NULL;
+        CHECK(tss_cnf_upload(e, l2, o2, nc, nv, &c2) == TSS_OK && tss_cnf_num_vars(c2) == nv);
+        tss_encoding* inst = NULL;
+        tss_instance_info info;
+        CHECK(tss_instance_find(l2, o2, nc, nv, &inst, &info, NULL, 0) == TSS_SAT);
+        CHECK(info.exact == 1 && info.w == w && info.h == h && info.n_defs == 1 && info.card_limit_1x1 == 3 && info.n_other_card_limits == 0);
+        uint8_t g2[64];
+        int32_t w2 = 0, h2 = 0;
+        CHECK(tss_encoding_terrain(inst, g2, sizeof g2, &w2, &h2) == TSS_OK && w2 == w && h2 == h && memcmp(g2, grid, (size_t)(w * h)) == 0);
+        CHECK(tss_solve_instance(e, c2, inst, &info, NULL, 5, 2000, a2) == TSS_SAT);                          /* a verified model of exactly these clauses */
+        int32_t nf = -1;
+        CHECK(tss_cnf_check(e, c2, a2, 1, &nf, NULL) == TSS_OK && nf == 0);
+        CHECK(tss_layout_from_assignment(inst, a2, nv + 1, decoded, 64, &n_dec) == TSS_OK && n_dec == 3);
+        CHECK(tss_witness_for_cnf(e, c2, inst, decoded, 2, a2) == TSS_UNKNOWN);                               /* one support short: not a model */
+        l2[0] = -l2[0];                                          /* other clauses: not a recorded instance */
+        CHECK(tss_instance_find(l2, o2, nc, nv, &enc1, &info, NULL, 0) == TSS_UNKNOWN && enc1 == NULL);
+        tss_encoding_destroy(inst);
+        tss_cnf_destroy(c2);
+        free(l2); free(o2); free(a2);
+    }
+    CHECK(tss_debug_smem_violations() == -1);                    /* the shipped build carries no bounds checks */
+
     tss_cnf_destroy(cnf);
     tss_encoding_destroy(enc);
     free(lits); free(offsets); free(assignment);
