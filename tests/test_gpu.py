@@ -900,6 +900,61 @@ def _check_lp_certificate(g, defs, r):
     assert r["bound"] == -(-r["total"] // r["max_load"])
 
 
+def _platform_cost(kw, kh, weights):
+    """what PlatformLayout::total_weight charges one platform: the weights of every def that fits inside its def (platform_layout.rs:174-183)"""
+    cw, ch = min(kw, kh), max(kw, kh)
+    return sum(v for (dw, dh), v in weights.items() if min(dw, dh) <= cw and max(dw, dh) <= ch)
+
+
+def test_fractional_lower_bound_on_the_gui_weight_objective(eng, fixtures):
+    """crates/gui/src/app.rs:235-245 minimises total_weight.  The weighted certificate, re-derived placement by placement with the
+    oracle's validate(): bound = min over placements of ceil(total * cost / load); it never exceeds the minimum weight the oracle's
+    GUI loop proves, and the GPU-seeded GUI loop (api.weight_loop) reaches that minimum — without the exact solver where the
+    bound meets it."""
+    rng = np.random.default_rng(12)
+    cases = [("ex1", fixtures["ex1"], O.PLATFORMS_DEFAULT, GUI_WEIGHTS), ("ex3", fixtures["ex3"], O.PLATFORMS_DEFAULT, GUI_WEIGHTS)]
+    for i in range(3):
+        g = (rng.random((int(rng.integers(4, 9)), int(rng.integers(4, 9)))) < 0.8).astype(np.uint8)
+        defs = [(1, 1), (1, 3), (3, 3)] if i % 2 else [(1, 1), (1, 2), (2, 2)]
+        cases.append((f"rand{i}", g, defs, {d: int(rng.integers(1, 6)) for d in defs}))
+
+    def exact(cnf):
+        import ctypes as C
+        a = np.full(cnf.n_vars + 1, 2, np.uint8)
+        lits, offs = np.ascontiguousarray(cnf.lits, np.int32), np.ascontiguousarray(cnf.offsets, np.uint32)
+        r = O.lib().tsso_solve_csr(O._p(lits), O._p(offs, C.c_uint32), cnf.n_clauses, cnf.n_vars, O._p(a, C.c_uint8), C.c_long(-1))
+        return {10: T.SAT, 20: T.UNSAT}.get(r, T.INTERRUPTED), a
+
+    closed = 0
+    for name, g, defs, weights in cases:
+        h, w = g.shape
+        tdefs = [T.PlatformDef(*d) for d in defs]
+        wdefs = {T.PlatformDef(*d): v for d, v in weights.items()}
+        r = eng.lower_bound_lp(T.WorldGrid(g), tdefs, weights=wdefs)
+        wts = r["weights"].astype(np.int64)
+        assert (wts >= 0).all() and (wts[g == 0] == 0).all() and int(wts.sum()) == r["total"]
+        best = None
+        for kw, kh in _key_dims(tdefs):
+            cost = _platform_cost(kw, kh, weights)
+            for y in range(h - kh + 1):
+                for x in range(w - kw + 1):
+                    v = O.validate(g, [(x, y, min(kw, kh), max(kw, kh), int(kw > kh))])
+                    load = int(wts[(g & (1 - v.unsupported)).astype(bool)].sum())
+                    if load > 0:
+                        q = -(-(r["total"] * cost) // load)
+                        best = q if best is None else min(best, q)
+        assert r["bound"] == best, name
+        want = oracle_min_weight(g, defs, weights)
+        assert r["bound"] <= want, (name, r["bound"], want)
+        grid = T.WorldGrid(g)
+        out = T.weight_loop(T.Project(T.World(grid)), T.Encoding.encode(tdefs, grid), wdefs, eng, exact_solver=exact, seed=2)
+        assert out["proved_optimal"] and out["best_weight"] == want, (name, out["best_weight"], want, out["steps"])
+        plats = [tup(p) for p in out["best"].platforms().values()]
+        assert O.validate(g, plats).is_valid and O.total_weight(plats, weights) == want
+        closed += out["steps"][-1]["source"] == "lower bound"
+    print("GUI loops closed by the certified bound alone:", closed, "of", len(cases))
+
+
 @pytest.mark.parametrize("name", ["ex1", "ex3", "ex2", "readme", "rect16", "rand20x14"])
 @pytest.mark.parametrize("pset", ["1x1", "default8"])
 def test_fractional_lower_bound_certificate(eng, fixtures, readme, name, pset):

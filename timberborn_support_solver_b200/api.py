@@ -643,14 +643,17 @@ class Engine:
                                              _ptr(out, C.c_int32), len(out), C.byref(n)))
         return [(int(x), int(y)) for x, y in out[: n.value]]
 
-    def lower_bound_lp(self, grid: WorldGrid, defs=PLATFORMS_DEFAULT[:1], max_pivots=0):
-        """Fractional packing lower bound (tss_lower_bound_lp), certified in integers.
-        -> dict(bound, weights int32[h, w], total, max_load, pivots, optimal, constraints); bound = ceil(total / max_load)."""
+    def lower_bound_lp(self, grid: WorldGrid, defs=PLATFORMS_DEFAULT[:1], max_pivots=0, weights: Optional[dict] = None):
+        """Fractional packing lower bound (tss_lower_bound_lp), certified in integers: on the platform count, or with `weights`
+        ({PlatformDef: weight}, the PlatformLimits.weights map) on PlatformLayout::total_weight.
+        -> dict(bound, weights int32[h, w], total, max_load, pivots, optimal, constraints)."""
         defs = list(defs)
         wts = np.zeros((grid.height, grid.width), np.int32)
-        total, max_load, bound = C.c_int64(), C.c_int64(), C.c_int32()
+        total, max_load, bound = C.c_int64(), C.c_int64(), C.c_int64()
         info = (C.c_int32 * 3)()
-        self._check(self.lib.tss_lower_bound_lp(self._h, _ptr(grid.data, C.c_uint8), grid.width, grid.height, _defs_array(defs), len(defs), max_pivots,
+        rec = np.array([[d.width, d.height, v] for d, v in (weights or {}).items()], np.int32).reshape(-1, 3)
+        self._check(self.lib.tss_lower_bound_lp(self._h, _ptr(grid.data, C.c_uint8), grid.width, grid.height, _defs_array(defs), len(defs),
+                                                _ptr(rec, C.c_int32) if len(rec) else None, len(rec), max_pivots,
                                                 _ptr(wts, C.c_int32), C.byref(total), C.byref(max_load), C.byref(bound), info))
         return dict(bound=bound.value, weights=wts, total=total.value, max_load=max_load.value, pivots=info[0], optimal=bool(info[1]), constraints=info[2])
 
@@ -702,7 +705,8 @@ class GpuBoundSolver:
         self.engine.clear_interrupt()      # the flag is sticky by design (InterruptSolver::interrupt may fire before solve starts a kernel): one solve, one flag
         if any(d != one for d in self.limits.card_limits):
             return INTERRUPTED             # card limits the search cannot steer by: leave the instance to the exact solver
-        if self.limits.weight_limit is not None and self.limits.weights:
+        if self.limits.weights and (self.limits.weight_limit is not None or bound is None):
+            # the GUI's instances: weights always, a weight limit from the second iteration on (app.rs:235-245)
             res, layout, _ = self.engine.solve_min_weight(self.encoding._grid, self.encoding.defs, self.limits.weights, self.limits.weight_limit,
                                                           self.seed, self.budget_ms, self.max_steps)
         else:
@@ -811,3 +815,50 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
             break
         limits.card_limits[one] = count - 1                     # main.rs:346
     return dict(best=best, proved_optimal=proved, steps=steps, lower_bound=lower)
+
+
+def weight_loop(project: Project, encoding: Encoding, weights: dict, engine: Engine, exact_solver=None, seed=0, max_steps=4096, use_lower_bound=True):
+    """The GUI's loop (crates/gui/src/app.rs:212-249): solve, run_trivial_optimization, weight = total_weight(layout),
+    weight_limit = weight - 1, again — until the solver says UNSAT.  The GPU answers the SAT iterations (weighted placement
+    search, witness verified against the CNF incl. the PB constraint); the certified fractional bound on the total weight
+    (tss_lower_bound_lp with the same weights) ends the loop when the weight meets it; `exact_solver` gets what is left.
+
+    Returns dict(best=PlatformLayout|None, best_weight=int|None, proved_optimal=bool, steps=[...], lower_bound=int|None)."""
+    limits = PlatformLimits({}, dict(weights), None)
+    steps, best, best_weight, proved = [], None, None, False
+    g = encoding._grid
+    engine.clear_interrupt()
+    lower = None
+    if use_lower_bound and g.width <= 32 and g.height <= 32:
+        try:
+            lower = engine.lower_bound_lp(g, encoding.defs, weights=weights)["bound"]
+        except TssError as err:
+            if err.code != _lib.TSS_E_UNSUPPORTED:
+                raise
+    while True:
+        if lower is not None and best is not None and limits.weight_limit < lower:
+            steps.append(dict(weight_limit=limits.weight_limit, result=UNSAT, source="lower bound"))
+            proved = True
+            break
+        cnf = encoding.with_limits(limits)                      # solver_backend.rs:76-78
+        solver = GpuBoundSolver(engine, encoding, limits, seed=seed, budget_ms=0, max_steps=max_steps)
+        solver.add_cnf(cnf)
+        result = solver.solve()
+        source = "gpu"
+        assignment = solver.full_solution() if result == SAT else None
+        if result != SAT and exact_solver is not None:
+            result, assignment = exact_solver(cnf)
+            source = "exact"
+        if result != SAT:
+            steps.append(dict(weight_limit=limits.weight_limit, result=result, source=source))
+            proved = result == UNSAT and best is not None
+            break
+        layout = PlatformLayout.from_assignment(assignment, encoding)   # app.rs:156
+        layout.run_trivial_optimization(project.world)                  # app.rs:157
+        weight = layout.total_weight(weights)                            # app.rs:235
+        steps.append(dict(weight_limit=limits.weight_limit, result=SAT, weight=weight, source=source))
+        best, best_weight = layout, weight
+        if weight <= 0:
+            break
+        limits.weight_limit = weight - 1                                 # app.rs:240
+    return dict(best=best, best_weight=best_weight, proved_optimal=proved, steps=steps, lower_bound=lower)

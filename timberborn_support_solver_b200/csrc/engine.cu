@@ -37,8 +37,8 @@ int sls_run_h16(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, 
                 int noise_pct, unsigned long long* totals_dev);
 int run_peaks(tss_engine* e, double* out, int n_out);
 // lp.cu — fractional packing lower bound
-int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::vector<int2>& key_dims, int max_pivots, int* out_weights,
-           unsigned long long* totals, int* info);
+int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::vector<int2>& key_dims, const std::vector<int>& key_costs, int max_pivots,
+           int* out_weights, unsigned long long* totals, int* info);
 // lb.cu — packing lower bound
 int lb_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::vector<int2>& key_dims, uint64_t seed, int restarts,
            uint32_t* out_rows32, int* out_count);
@@ -1474,11 +1474,13 @@ int tss_lower_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, co
     return TSS_OK;
 }
 
-int tss_lower_bound_lp(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs, int32_t max_pivots,
-                       int32_t* out_weights, int64_t* out_total, int64_t* out_max_load, int32_t* out_bound, int32_t* out_info) {
+int tss_lower_bound_lp(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs, const int32_t* weights,
+                       int32_t n_weights, int32_t max_pivots, int32_t* out_weights, int64_t* out_total, int64_t* out_max_load, int64_t* out_bound,
+                       int32_t* out_info) {
     if (!e) return TSS_E_INVALID;
     if (out_bound) *out_bound = 0;
-    if (!grid || !out_bound || w <= 0 || h <= 0 || (!defs && n_defs > 0)) return e->fail(TSS_E_INVALID, "tss_lower_bound_lp: bad arguments");
+    if (!grid || !out_bound || w <= 0 || h <= 0 || (!defs && n_defs > 0) || n_weights < 0 || (n_weights > 0 && !weights))
+        return e->fail(TSS_E_INVALID, "tss_lower_bound_lp: bad arguments");
     if (w > 32 || h > 32) return e->fail(TSS_E_UNSUPPORTED, "tss_lower_bound_lp: grids larger than 32x32 are not supported");
     bool has_1x1 = n_defs == 0;
     for (int i = 0; i < n_defs; i++) {
@@ -1491,21 +1493,33 @@ int tss_lower_bound_lp(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h,
     std::vector<tss_platform> key_proto;
     const tss_dims one{1, 1};
     build_keys(n_defs ? defs : &one, n_defs ? n_defs : 1, key_dims, key_proto);
+    // what a platform of each key costs: 1 (the platform count) or, with weights, the sum of the weights of every def contained in
+    // its def — exactly what PlatformLayout::total_weight charges it (platform_layout.rs:174-183)
+    std::vector<int> key_costs(key_dims.size(), 1);
+    if (n_weights > 0)
+        for (size_t k = 0; k < key_dims.size(); k++) {
+            const Dims def{key_proto[k].def_w, key_proto[k].def_h};
+            long cost = 0;
+            for (int i = 0; i < n_weights; i++)
+                if (dims_le(Dims{weights[3 * i], weights[3 * i + 1]}, def)) cost += weights[3 * i + 2];
+            if (cost < 0 || cost > 4096) return e->fail(TSS_E_UNSUPPORTED, "tss_lower_bound_lp: platform costs must be in 0..4096 (got %ld for %dx%d)", cost, def.w, def.h);
+            key_costs[k] = (int)cost;
+        }
     uint32_t rows[32] = {0};
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++)
             if (grid[(size_t)y * w + x]) rows[y] |= 1u << x;
-    int weights[1024], info[3];
-    unsigned long long totals[2];
-    int rc = lp_run(e, rows, w, h, key_dims, max_pivots, weights, totals, info);
+    int wts[1024], info[3];
+    unsigned long long totals[3];
+    int rc = lp_run(e, rows, w, h, key_dims, key_costs, max_pivots, wts, totals, info);
     if (rc) return rc;
     if (out_weights)
         for (int y = 0; y < h; y++)
-            for (int x = 0; x < w; x++) out_weights[(size_t)y * w + x] = weights[y * 32 + x];
+            for (int x = 0; x < w; x++) out_weights[(size_t)y * w + x] = wts[y * 32 + x];
     if (out_total) *out_total = (int64_t)totals[0];
     if (out_max_load) *out_max_load = (int64_t)totals[1];
     if (out_info) { out_info[0] = info[0]; out_info[1] = info[1]; out_info[2] = info[2]; }
-    *out_bound = totals[1] > 0 ? (int32_t)((totals[0] + totals[1] - 1) / totals[1]) : 0;   // ceil(total / max load): exact
+    *out_bound = (totals[1] > 0 && totals[2] != ~0ull) ? (int64_t)totals[2] : 0;   // min over placements of ceil(total * cost / load): exact
     return TSS_OK;
 }
 

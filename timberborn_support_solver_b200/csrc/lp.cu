@@ -36,11 +36,12 @@ constexpr int MAX_KEYS = 16;
 constexpr int THREADS = 1024;
 constexpr int MAX_COLS = 1024;                 // ceiling tiles of a 32x32 grid
 constexpr double EPS = 1e-9;
-constexpr long long SCALE = 1ll << 20;         // integer weights k_t = floor(y_t * SCALE)
+// integer weights k_t = floor(y_t * scale); scale = 2^20 for costs up to 1024, smaller powers of two above (k_t fits an int)
 
 struct Keys {
     int n;
     int w[MAX_KEYS], h[MAX_KEYS];
+    int cost[MAX_KEYS];   // what a platform of this key costs: 1 for the platform count, the GUI's total_weight otherwise
 };
 
 __device__ __forceinline__ uint32_t dilate(uint32_t X, uint32_t C, int lane) {
@@ -70,14 +71,14 @@ __global__ void __launch_bounds__(128) lp_reach_kernel(const uint32_t* __restric
 // condensed tableau, row-major with leading dimension ld = n + 1: rows 0..m-1 = constraints (column j = tile col_site[j],
 // column n = right-hand side), row m = objective (-1 per tile, value 0)
 __global__ void lp_init_kernel(const uint32_t* __restrict__ reach, const int* __restrict__ cons, int m, const int* __restrict__ col_site, int n,
-                               double* __restrict__ T, double perturb) {
+                               double* __restrict__ T, double perturb, Keys keys) {
     const int ld = n + 1;
     const long long total = (long long)(m + 1) * ld;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(idx / ld), j = (int)(idx % ld);
         double v;
         if (i == m) v = j < n ? -1.0 : 0.0;
-        else if (j == n) v = 1.0 + perturb * (double)((i * 37) % 101) / 101.0;   // tiny perturbation against degenerate ties (the certificate is exact anyway)
+        else if (j == n) v = (double)keys.cost[cons[i] >> 10] * (1.0 + perturb * (double)((i * 37) % 101) / 101.0);   // cost of the placement; tiny perturbation against degenerate ties (the certificate is exact anyway)
         else {
             const int s = col_site[j];
             v = (double)((reach[(size_t)cons[i] * 32 + (s >> 5)] >> (s & 31)) & 1u);
@@ -176,7 +177,7 @@ constexpr int CL_THREADS = 512;
 
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(CL_THREADS)
 lp_simplex_cluster_kernel(const double* __restrict__ T, int m, int n, const int* __restrict__ col_site, int max_pivots, int* __restrict__ info,
-                          int* __restrict__ weights /* [1024] zeroed */) {
+                          int* __restrict__ weights /* [1024] zeroed */, double scale) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank(), tid = threadIdx.x, ld = n + 1;
     const int rows_per = (m + CLUSTER - 1) / CLUSTER, row0 = rank * rows_per, my_rows = max(0, min(rows_per, m - row0));
@@ -244,8 +245,8 @@ lp_simplex_cluster_kernel(const double* __restrict__ T, int m, int n, const int*
         const int label = basis[row0 + li];
         if (label >= n) continue;
         const double y = Tl[(size_t)li * ld + n];
-        const long long k = y > 0.0 ? (long long)floor(y * (double)SCALE) : 0ll;
-        weights[col_site[label]] = (int)(k > (4ll << 20) ? (4ll << 20) : k);
+        const long long k = y > 0.0 ? (long long)floor(y * scale) : 0ll;
+        weights[col_site[label]] = (int)(k > (1ll << 30) ? (1ll << 30) : k);
     }
     if (rank == 0 && tid == 0) { info[0] = pivots; info[1] = optimal; }
     cluster.sync();                                         // nobody exits while its shared memory may still be read remotely
@@ -253,49 +254,64 @@ lp_simplex_cluster_kernel(const double* __restrict__ T, int m, int n, const int*
 
 // y -> integer weights per site (floor(y * SCALE), never negative), zero for non-basic tiles
 __global__ void lp_weights_kernel(const double* __restrict__ T, int m, int n, const int* __restrict__ basis, const int* __restrict__ col_site,
-                                  int* __restrict__ weights /* [1024] zeroed */) {
+                                  int* __restrict__ weights /* [1024] zeroed */, double scale) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const int label = basis[i];
     if (label >= n) return;
     const double y = T[(size_t)i * (n + 1) + n];
-    const long long k = y > 0.0 ? (long long)floor(y * (double)SCALE) : 0ll;
-    weights[col_site[label]] = (int)(k > (4ll << 20) ? (4ll << 20) : k);
+    const long long k = y > 0.0 ? (long long)floor(y * scale) : 0ll;
+    weights[col_site[label]] = (int)(k > (1ll << 30) ? (1ll << 30) : k);
 }
 
-// exact certificate: out[0] = sum of the weights, out[1] = max over ALL placements (not only the tableau's rows) of the load
-__global__ void __launch_bounds__(128) lp_certify_kernel(const uint32_t* __restrict__ reach, int n_placements, const int* __restrict__ weights,
+// exact certificate, all in 64-bit integers.  out[0] = sum of the weights k_t (lp_total_kernel).  For every in-bounds placement p (ALL
+// of them, not only the tableau's rows) with load(p) = sum of the weights in its reach: a layout L costs sum_{p in L} cost(p) and
+// covers every tile, so  total <= sum_{p in L} load(p) <= (max_p load(p) / cost(p)) * cost(L):  cost(L) >= total * cost(p) / load(p)
+// for the placement with the worst ratio.  out[1] = max load, out[2] = min over placements of ceil(total * cost(p) / load(p)) — the
+// bound.  With unit costs that is ceil(total / max load).
+__global__ void lp_total_kernel(const int* __restrict__ weights, unsigned long long* __restrict__ out) {
+    long long s = 0;
+    for (int t = threadIdx.x; t < 1024; t += 32) s += weights[t];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (threadIdx.x == 0) out[0] = (unsigned long long)s;
+}
+__global__ void __launch_bounds__(128) lp_certify_kernel(const uint32_t* __restrict__ reach, int n_placements, const int* __restrict__ weights, Keys keys,
                                                          unsigned long long* __restrict__ out) {
     const int lane = threadIdx.x & 31, p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= n_placements) return;
     long long load = 0;
     for (uint32_t bits = reach[(size_t)p * 32 + lane]; bits; bits &= bits - 1) load += weights[lane * 32 + __ffs(bits) - 1];
     for (int o = 16; o > 0; o >>= 1) load += __shfl_xor_sync(FULL, load, o);
-    if (lane == 0) atomicMax(&out[1], (unsigned long long)load);
-    if (p == 0) {
-        long long s = 0;
-        for (int t = lane; t < 1024; t += 32) s += weights[t];
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-        if (lane == 0) out[0] = (unsigned long long)s;
+    if (lane == 0 && load > 0) {
+        const unsigned long long total = out[0], num = total * (unsigned long long)keys.cost[p >> 10];
+        atomicMax(&out[1], (unsigned long long)load);
+        atomicMin(&out[2], (num + (unsigned long long)load - 1ull) / (unsigned long long)load);
     }
 }
 
 }  // namespace lp
 
 // rows32_host: terrain rows; key_dims: effective (w, h) per dims key.  out_weights (host, 1024 ints, index y * 32 + x),
-// totals[0] = sum of the weights, totals[1] = largest placement load, info[0] = pivots, info[1] = optimal, info[2] = constraints.
-int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::vector<int2>& key_dims, int max_pivots, int* out_weights,
-           unsigned long long* totals, int* info) {
+// key_costs: cost of a platform per key.  totals[0] = sum of the weights, totals[1] = largest placement load, totals[2] = the bound
+// (min over placements of ceil(total * cost / load); ~0 if no placement carries load), info[0] = pivots, info[1] = optimal, info[2] = constraints.
+int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::vector<int2>& key_dims, const std::vector<int>& key_costs, int max_pivots,
+           int* out_weights, unsigned long long* totals, int* info) {
     if ((int)key_dims.size() > lp::MAX_KEYS) return e->fail(TSS_E_UNSUPPORTED, "tss_lower_bound_lp: more than %d dims keys", lp::MAX_KEYS);
     lp::Keys keys;
     keys.n = (int)key_dims.size();
-    for (int i = 0; i < keys.n; i++) { keys.w[i] = key_dims[(size_t)i].x; keys.h[i] = key_dims[(size_t)i].y; }
+    int max_cost = 1;
+    for (int i = 0; i < keys.n; i++) {
+        keys.w[i] = key_dims[(size_t)i].x; keys.h[i] = key_dims[(size_t)i].y; keys.cost[i] = key_costs[(size_t)i];
+        max_cost = key_costs[(size_t)i] > max_cost ? key_costs[(size_t)i] : max_cost;
+    }
+    double scale = (double)(1 << 20);            // y_t <= the largest cost: keep floor(y * scale) below 2^30
+    while (scale * (double)max_cost > (double)(1 << 30)) scale *= 0.5;
     const int n_place = keys.n * 1024;
     std::vector<int> col_site;
     for (int s = 0; s < 1024; s++)
         if ((rows32_host[s >> 5] >> (s & 31)) & 1u) col_site.push_back(s);
     const int n = (int)col_site.size();
-    totals[0] = totals[1] = 0;
+    totals[0] = totals[1] = totals[2] = 0;
     info[0] = info[1] = info[2] = 0;
     for (int i = 0; i < 1024; i++) out_weights[i] = 0;
     if (n == 0) return TSS_OK;
@@ -321,7 +337,7 @@ int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::
     if (cells > ((size_t)1 << 27)) return e->fail(TSS_E_UNSUPPORTED, "tss_lower_bound_lp: tableau of %d x %d exceeds the supported size", m, n);
     // scratch slot 5: tableau doubles | cons [m] | col_site [n] | basis [m] | nonbasis [n] | weights [1024] | info [4] | totals [2] u64
     const size_t ints = (size_t)m + n + m + n + 1024 + 4;
-    double* T = (double*)e->dev(5, sizeof(double) * cells + sizeof(int) * ints + 16 + 16);
+    double* T = (double*)e->dev(5, sizeof(double) * cells + sizeof(int) * ints + 16 + 24);
     if (!T) return TSS_E_CUDA;
     int* cons_dev = (int*)(T + cells);
     int *col_dev = cons_dev + m, *basis = col_dev + n, *nonbasis = basis + m, *weights = nonbasis + n, *info_dev = weights + 1024;
@@ -330,10 +346,11 @@ int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::
     TSS_CUDA(e, cudaMemcpyAsync(col_dev, col_site.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
     TSS_CUDA(e, cudaMemsetAsync(weights, 0, sizeof(int) * (1024 + 4), e->stream));
     TSS_CUDA(e, cudaMemsetAsync(totals_dev, 0, sizeof(unsigned long long) * 2, e->stream));
+    TSS_CUDA(e, cudaMemsetAsync(totals_dev + 2, 0xff, sizeof(unsigned long long), e->stream));   // running minimum
     const int init_blocks = (int)((cells + 255) / 256 < (size_t)e->prop.multiProcessorCount * 8 ? (cells + 255) / 256 : (size_t)e->prop.multiProcessorCount * 8);
     // (the size of the perturbation does not matter: 0 .. 1e-3 all need 1 300 - 1 800 pivots on the 21x16 terrains — the pivot count is
     // Dantzig pricing on this LP, not degenerate stalling)
-    lp::lp_init_kernel<<<init_blocks, 256, 0, e->stream>>>(reach, cons_dev, m, col_dev, n, T, 1e-7);
+    lp::lp_init_kernel<<<init_blocks, 256, 0, e->stream>>>(reach, cons_dev, m, col_dev, n, T, 1e-7, keys);
     const int pivots_cap = max_pivots > 0 ? max_pivots : 8 * (m + n);
     const int rows_per = (m + lp::CLUSTER - 1) / lp::CLUSTER, ld = n + 1;
     const size_t cl_smem = sizeof(double) * ((size_t)rows_per * ld + 3 * (size_t)ld + rows_per) + sizeof(lp::ArgD) * lp::CLUSTER + sizeof(int) * ((size_t)m + n);
@@ -341,18 +358,19 @@ int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::
     if (cl_smem <= 200 * 1024 && !(force && force[0] == '1')) {
         // the tableau fits the shared memory of one 8-CTA cluster: rows resident in shared memory, exchange over DSMEM
         TSS_CUDA(e, cudaFuncSetAttribute(lp::lp_simplex_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_smem));
-        lp::lp_simplex_cluster_kernel<<<lp::CLUSTER, lp::CL_THREADS, cl_smem, e->stream>>>(T, m, n, col_dev, pivots_cap, info_dev, weights);
+        lp::lp_simplex_cluster_kernel<<<lp::CLUSTER, lp::CL_THREADS, cl_smem, e->stream>>>(T, m, n, col_dev, pivots_cap, info_dev, weights, scale);
     } else {
         lp::lp_simplex_kernel<<<1, lp::THREADS, 0, e->stream>>>(T, m, n, basis, nonbasis, pivots_cap, info_dev);
-        lp::lp_weights_kernel<<<(m + 255) / 256, 256, 0, e->stream>>>(T, m, n, basis, col_dev, weights);
+        lp::lp_weights_kernel<<<(m + 255) / 256, 256, 0, e->stream>>>(T, m, n, basis, col_dev, weights, scale);
     }
-    lp::lp_certify_kernel<<<(n_place + 3) / 4, 128, 0, e->stream>>>(reach, n_place, weights, totals_dev);
+    lp::lp_total_kernel<<<1, 32, 0, e->stream>>>(weights, totals_dev);
+    lp::lp_certify_kernel<<<(n_place + 3) / 4, 128, 0, e->stream>>>(reach, n_place, weights, keys, totals_dev);
     TSS_CHECK_LAUNCH(e);
     TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
     e->stats.kernel_launches += 5;
     TSS_CUDA(e, cudaMemcpyAsync(out_weights, weights, sizeof(int) * 1024, cudaMemcpyDeviceToHost, e->stream));
     TSS_CUDA(e, cudaMemcpyAsync(info, info_dev, sizeof(int) * 2, cudaMemcpyDeviceToHost, e->stream));
-    TSS_CUDA(e, cudaMemcpyAsync(totals, totals_dev, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaMemcpyAsync(totals, totals_dev, sizeof(unsigned long long) * 3, cudaMemcpyDeviceToHost, e->stream));
     TSS_CUDA(e, cudaStreamSynchronize(e->stream));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) cudaGetLastError();

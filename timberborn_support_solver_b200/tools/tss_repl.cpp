@@ -201,9 +201,9 @@ int main(int argc, char** argv) {
             }
             if (result == 0 && lower >= 0 && !lp_done && best >= 0) {   // the GPU found nothing below the current count: can the fractional bound certify it?
                 lp_done = true;
-                int32_t lp_bound = 0;
-                if (tss_lower_bound_lp(e, grid.data(), w, h, all_defs, n_defs, 0, nullptr, nullptr, nullptr, &lp_bound, nullptr) == TSS_OK && lp_bound > lower) {
-                    lower = lp_bound;
+                int64_t lp_bound = 0;
+                if (tss_lower_bound_lp(e, grid.data(), w, h, all_defs, n_defs, nullptr, 0, 0, nullptr, nullptr, nullptr, &lp_bound, nullptr) == TSS_OK && lp_bound > lower) {
+                    lower = (int32_t)lp_bound;
                     if (!quiet) SAY("Lower bound (fractional): %d platforms\n", lower);
                 }
                 if (bound >= 0 && bound < lower) {
