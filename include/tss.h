@@ -29,13 +29,14 @@
 extern "C" {
 #endif
 
-#define TSS_VERSION 102
+#define TSS_VERSION 103
 
 /* status codes; solve results follow IPASIR / rustsat SolverResult (crates/repl/src/main.rs:326-339) */
 #define TSS_OK 0
 #define TSS_UNKNOWN 0       /* budget exhausted or interrupted: no layout within the bound was found (NOT a proof) */
 #define TSS_SAT 10          /* a validated layout within the bound was found */
-#define TSS_UNSAT 20        /* never produced by the GPU engine: only the exact solver proves UNSAT */
+#define TSS_UNSAT 20        /* never produced by a SEARCH (the exact solver proves UNSAT); tss_solve_instance returns it when the limit lies
+                               below a certified lower bound (tss_lower_bound / tss_lower_bound_lp) */
 #define TSS_E_INVALID (-1)  /* bad argument (null pointer, zero-sized grid, platform set without 1x1, ...) */
 #define TSS_E_CAPACITY (-2) /* an output buffer is too small; the required size is reported where documented */
 #define TSS_E_CUDA (-3)     /* CUDA runtime failure or no device */
@@ -336,8 +337,13 @@ int tss_cnf_num_vars(const tss_cnf* c);
 int tss_witness_for_cnf(tss_engine* e, const tss_cnf* c, const tss_encoding* enc, const tss_platform* plats, int32_t n, uint8_t* assignment);
 /* Solve::solve as the GPU answers it: ONE SAT-like search within the instance's limit (platform count, or total weight when
  * the instance carries a weight limit) that gives up after `give_up_steps` SLS steps per chain (<= 0: the engine default),
- * then tss_witness_for_cnf.  TSS_SAT with a verified model in `assignment`, or TSS_UNKNOWN — never TSS_UNSAT: the caller
- * then asks its exact solver, which stays the only prover of UNSAT. */
+ * then tss_witness_for_cnf.  TSS_SAT with a verified model in `assignment`; TSS_UNSAT when the instance's only limit (platform
+ * count, or total weight) lies below a certified lower bound (the integral packing, checked before searching; the fractional
+ * LP, computed once per instance after a search came back empty; grids up to 32x32) — the unmodified bound-tightening loops
+ * (crates/repl/src/main.rs:331-334, crates/gui/src/app.rs:212-249) then end proven optimal without their exact solver;
+ * TSS_UNKNOWN otherwise: the caller asks its exact solver, which stays the only prover of UNSAT by search.
+ * tss_engine_certified_unsat switches the bound-based UNSAT answers off (0) or on (non-zero, the default). */
+int tss_engine_certified_unsat(tss_engine* e, int enabled);
 int tss_solve_instance(tss_engine* e, const tss_cnf* c, const tss_encoding* enc, const tss_instance_info* info, const int32_t* weights,
                        uint64_t seed, int64_t give_up_steps, uint8_t* assignment);
 

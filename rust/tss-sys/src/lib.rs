@@ -1,12 +1,12 @@
-//! Raw bindings to `include/tss.h` (ABI version 102).  Every entry point cites, in the header, the reference
+//! Raw bindings to `include/tss.h` (ABI version 103).  Every entry point cites, in the header, the reference
 //! interface it stands behind; this file only mirrors types and signatures.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int};
 
-pub const TSS_VERSION: c_int = 102;
+pub const TSS_VERSION: c_int = 103;
 pub const TSS_OK: c_int = 0;
 pub const TSS_SAT: c_int = 10; // IPASIR / rustsat SolverResult::Sat
-pub const TSS_UNSAT: c_int = 20; // never returned by the GPU engine
+pub const TSS_UNSAT: c_int = 20; // only from tss_solve_instance, when the limit lies below a certified lower bound
 pub const TSS_UNKNOWN: c_int = 0; // SolverResult::Interrupted
 pub const TSS_KERNEL_AUTO: i32 = 0;
 
@@ -142,6 +142,7 @@ unsafe extern "C" {
         weights: *mut i32, weights_cap: i32,
     ) -> c_int;
     pub fn tss_witness_for_cnf(e: *mut tss_engine, c: *const tss_cnf, enc: *const tss_encoding, plats: *const tss_platform, n: i32, assignment: *mut u8) -> c_int;
+    pub fn tss_engine_certified_unsat(e: *mut tss_engine, enabled: c_int) -> c_int;
     pub fn tss_solve_instance(
         e: *mut tss_engine, c: *const tss_cnf, enc: *const tss_encoding, info: *const tss_instance_info, weights: *const i32, seed: u64,
         give_up_steps: i64, assignment: *mut u8,

@@ -1,7 +1,8 @@
 //! `GpuSeeded<S>` — the drop-in the reference's drivers use in place of `GlucoseSimp`
 //! (`crates/repl/src/main.rs:17,295`, `crates/gui/src/main.rs:2,26`): a type that is
 //! `Solve + Interrupt + SolveStats + Default + Send`, owns an exact solver `S` and a `tss_engine`, answers
-//! `solve()` from the GPU when it can and from `S` otherwise.  `S` stays the only prover of UNSAT.
+//! `solve()` from the GPU when it can and from `S` otherwise.  UNSAT comes from `S`, or from a certified lower bound of the
+//! instance (`tss_solve_instance` returning `TSS_UNSAT`), never from a search that merely found nothing.
 //!
 //! The drivers change ONE line (`use tss::GpuSeeded as GlucoseSimp;`): the solver is handed a bare `Cnf`
 //! (`crates/repl/src/solver_runner.rs:8-20`) and finds terrain, platform set, variable map and limits again through the
@@ -159,11 +160,15 @@ impl<S: Solve> Solve for GpuSeeded<S> {
                 let vals: Vec<TernaryVal> = a[1..].iter().map(|&b| if b == 1 { TernaryVal::True } else { TernaryVal::False }).collect();
                 self.witness = Some(Assignment::from(vals));
                 return Ok(SolverResult::Sat);
+            } else if rc == ffi::TSS_UNSAT {
+                // the limit lies below a CERTIFIED lower bound of the instance (packing / fractional LP, include/tss.h): the
+                // drivers' loops end here ("No solution found for the current constraints", main.rs:331-334) without the exact solver
+                return Ok(SolverResult::Unsat);
             } else if rc < 0 {
                 log::warn!("tss_solve_instance: {}", last_error(engine.0));
             }
         }
-        self.inner.solve() // the exact solver: every UNSAT answer comes from here
+        self.inner.solve() // the exact solver: every UNSAT answer by SEARCH comes from here
     }
 
     fn lit_val(&self, lit: Lit) -> Result<TernaryVal> {

@@ -155,6 +155,33 @@ int main(void) {
         CHECK(tss_cnf_check(e, c2, a2, 1, &nf, NULL) == TSS_OK && nf == 0);
         CHECK(tss_layout_from_assignment(inst, a2, nv + 1, decoded, 64, &n_dec) == TSS_OK && n_dec == 3);
         CHECK(tss_witness_for_cnf(e, c2, inst, decoded, 2, a2) == TSS_UNKNOWN);                               /* one support short: not a model */
+        {   /* the loop's next question, "at most 2 platforms" (main.rs:346): below the certified lower bound of 3 -> UNSAT, no exact solver */
+            const int32_t card2[3] = {1, 1, 2};
+            tss_encoding* enc2 = NULL;
+            CHECK(tss_encoding_create(grid, w, h, defs, 1, &enc2) == TSS_OK);
+            int32_t nv3 = 0, nc3 = 0;
+            int64_t nl3 = 0;
+            CHECK(tss_encoding_with_limits(enc2, card2, 1, NULL, 0, 0, 0, &nv3, &nc3, &nl3, NULL, NULL) == TSS_OK);
+            int32_t* l3 = malloc(sizeof(int32_t) * (size_t)(nl3 + 1));
+            uint32_t* o3 = malloc(sizeof(uint32_t) * (size_t)(nc3 + 1));
+            uint8_t* a3 = malloc((size_t)nv3 + 1);
+            CHECK(l3 && o3 && a3);
+            CHECK(tss_encoding_with_limits(enc2, card2, 1, NULL, 0, 0, 0, &nv3, &nc3, &nl3, l3, o3) == TSS_OK);
+            tss_cnf* c3 = NULL;
+            tss_encoding* inst3 = NULL;
+            tss_instance_info info3;
+            CHECK(tss_cnf_upload(e, l3, o3, nc3, nv3, &c3) == TSS_OK);
+            CHECK(tss_instance_find(l3, o3, nc3, nv3, &inst3, &info3, NULL, 0) == TSS_SAT && info3.card_limit_1x1 == 2);
+            CHECK(tss_engine_certified_unsat(e, 0) == TSS_OK);
+            CHECK(tss_solve_instance(e, c3, inst3, &info3, NULL, 5, 2000, a3) == TSS_UNKNOWN);   /* a search alone proves nothing */
+            CHECK(tss_engine_certified_unsat(e, 1) == TSS_OK);
+            CHECK(tss_solve_instance(e, c3, inst3, &info3, NULL, 5, 2000, a3) == TSS_UNSAT);
+            CHECK(tss_solve_instance(e, c3, inst3, &info3, NULL, 6, 2000, a3) == TSS_UNSAT);     /* from the cached bound */
+            tss_encoding_destroy(inst3);
+            tss_encoding_destroy(enc2);
+            tss_cnf_destroy(c3);
+            free(l3); free(o3); free(a3);
+        }
         l2[0] = -l2[0];                                          /* other clauses: not a recorded instance */
         CHECK(tss_instance_find(l2, o2, nc, nv, &enc1, &info, NULL, 0) == TSS_UNKNOWN && enc1 == NULL);
         tss_encoding_destroy(inst);

@@ -1082,14 +1082,19 @@ def test_cpp_repl_driver_reaches_the_proven_optimum(eng, fixtures, tmp_path, nam
     assert all(b < a for a, b in zip(counts, counts[1:]))
     assert "No solution found for the current constraints" in text and text.rstrip().splitlines()[-2] == "Done"
     assert f["verdict"].startswith("optimal") and "FAILED" not in text
-    if optimum == 1:                       # default-8 on ex1 / ex3: the lower bound closes the loop, the exact solver is never started
-        assert int(f["exact_solves"]) == 0 and int(f["lower_bound"]) == 1
+    # tss_solve_instance answers UNSAT below the certified lower bounds, which are tight on all five: the exact solver is never started
+    assert int(f["exact_solves"]) == 0 and int(f["lower_bound"]) == optimum and f["verdict"] == "optimal (lower bound)"
+    # ... and with the bound-based answers switched off the same loop ends on the exact solver's UNSAT
+    text, f, counts = _run_repl(tmp_path, fixtures[name], "--platforms", pset, "--seed", "3", "--no-lower-bound")
+    assert int(f["best"]) == optimum and int(f["exact_solves"]) >= 1 and f["verdict"] == "optimal (exact solver)"
 
 
 def test_cpp_repl_driver_limits_and_errors(eng, fixtures, tmp_path):
     # `solve -l 1:2` on ex1 with 1x1 supports: 3 are needed (proofs.json) -> UNSAT straight from the exact solver
     text, f, counts = _run_repl(tmp_path, fixtures["ex1"], "--platforms", "1x1", "-l", "1:2", "--no-lower-bound")
     assert counts == [] and f["verdict"] == "unsatisfiable" and int(f["exact_solves"]) == 1
+    text, f, counts = _run_repl(tmp_path, fixtures["ex1"], "--platforms", "1x1", "-l", "1:2")   # ... or from the certified bound: no exact solver
+    assert counts == [] and f["verdict"] == "unsatisfiable" and int(f["exact_solves"]) == 0 and "No solution found" in text
     # a limit on another platform type is left to the exact solver (the search cannot steer by it), and still honoured
     text, f, counts = _run_repl(tmp_path, fixtures["ex1"], "-l", "5:0,3:0")
     assert int(f["best"]) >= 2 and int(f["gpu_solves"]) >= 1 and int(f["exact_solves"]) >= 1

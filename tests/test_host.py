@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(T.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.tss_version() == 102
+    assert lib.tss_version() == 103
 
 
 def test_engine_needs_a_gpu_no_fallback():

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TSS_LIB") or os.path.join(HERE, "libtss.so")   # TSS_LIB: load another BUILD of libtss (kernel experiments)
 
-TSS_VERSION = 102   # include/tss.h
+TSS_VERSION = 103   # include/tss.h
 TSS_OK, TSS_UNKNOWN, TSS_SAT, TSS_UNSAT = 0, 0, 10, 20
 TSS_E_INVALID, TSS_E_CAPACITY, TSS_E_CUDA, TSS_E_UNSUPPORTED, TSS_E_PARSE = -1, -2, -3, -4, -5
 ERROR_NAMES = {-1: "TSS_E_INVALID", -2: "TSS_E_CAPACITY", -3: "TSS_E_CUDA", -4: "TSS_E_UNSUPPORTED", -5: "TSS_E_PARSE"}
@@ -112,6 +112,7 @@ SIGNATURES = {
     "tss_cnf_num_vars": (C.c_int, [_vp]),
     "tss_witness_for_cnf": (C.c_int, [_vp, _vp, _vp, _P(Platform), _i32, _u8p]),
     "tss_solve_instance": (C.c_int, [_vp, _vp, _vp, _P(InstanceInfo), _i32p, _u64, _i64, _u8p]),
+    "tss_engine_certified_unsat": (C.c_int, [_vp, C.c_int]),
     "tss_measure_peaks": (C.c_int, [_vp, _P(C.c_double), _i32]),
 }
 

@@ -2,6 +2,7 @@
 // a bare CNF (crates/repl/src/solver_runner.rs:8-20) find the terrain, platform set, variable map and limits it came from.
 #pragma once
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "host_model.hpp"
@@ -9,6 +10,13 @@
 struct tss_encoding_data {
     tss::Encoding enc;
     std::vector<uint8_t> grid;
+    // certified lower bounds of this terrain / platform set, computed at most once (tss_solve_instance): the bound-tightening loop
+    // asks about the same instance with a smaller limit every iteration (crates/repl/src/main.rs:346)
+    mutable std::mutex bounds_mutex;
+    mutable int packing_bound = -1;        // tss_lower_bound; -1 = not computed, -2 = not available for this instance
+    mutable long long lp_count_bound = -1; // tss_lower_bound_lp on the platform count
+    mutable std::vector<int32_t> lp_weights;   // the weight table `lp_weight_bound` was computed for
+    mutable long long lp_weight_bound = -1;    // tss_lower_bound_lp on the total weight
 };
 
 // a handle is a shared reference: the registry keeps encodings alive after the caller destroyed its own handle

@@ -45,6 +45,7 @@ struct tss_engine {
     int* interrupt_dev = nullptr;            // device flag
     cudaStream_t irq_stream = nullptr;
     std::atomic<int> interrupt_flag{0};
+    bool certified_unsat = true;             // tss_solve_instance may answer TSS_UNSAT from a certified lower bound (tss_engine_certified_unsat)
     struct tss_search* cached_search = nullptr;  // workspace reused by tss_solve_upper_bound (no cudaMalloc per call)
     struct tss_search* cached_batch = nullptr;   // workspace reused by tss_solve_batch
     struct tss_search* cached_multi = nullptr;   // workspace of the placement search (platform sets beyond {1x1}) of a one-shot solve

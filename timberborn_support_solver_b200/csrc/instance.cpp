@@ -125,6 +125,12 @@ int tss_witness_for_cnf(tss_engine* e, const tss_cnf* c, const tss_encoding* enc
     return n_falsified == 0 ? TSS_SAT : TSS_UNKNOWN;
 }
 
+int tss_engine_certified_unsat(tss_engine* e, int enabled) {
+    if (!e) return TSS_E_INVALID;
+    e->certified_unsat = enabled != 0;
+    return TSS_OK;
+}
+
 int tss_solve_instance(tss_engine* e, const tss_cnf* c, const tss_encoding* enc, const tss_instance_info* info, const int32_t* weights,
                        uint64_t seed, int64_t give_up_steps, uint8_t* assignment) {
     if (!e) return TSS_E_INVALID;
@@ -133,6 +139,27 @@ int tss_solve_instance(tss_engine* e, const tss_cnf* c, const tss_encoding* enc,
     const Encoding& E = enc->d->enc;
     std::vector<tss_dims> defs;
     for (const Dims& d : E.defs) defs.push_back(tss_dims{d.w, d.h});
+    // A limit below a CERTIFIED lower bound has no model: answer UNSAT without searching.  Only when the platform count is the
+    // sole limit (the REPL's loop); the integral packing first (~0.1 ms, computed once per instance), the fractional LP only after
+    // the search came back empty-handed.
+    const bool small = e->certified_unsat && E.w <= 32 && E.h <= 32;
+    const bool count_only = small && info->card_limit_1x1 >= 0 && !info->has_weight_limit;
+    const bool weight_only = small && info->card_limit_1x1 < 0 && info->has_weight_limit && info->n_weights > 0 && weights;
+    if (weight_only) {
+        std::lock_guard<std::mutex> lock(enc->d->bounds_mutex);
+        if (enc->d->lp_weight_bound >= 0 && enc->d->lp_weights == std::vector<int32_t>(weights, weights + 3 * (size_t)info->n_weights) &&
+            info->weight_limit < enc->d->lp_weight_bound)
+            return TSS_UNSAT;
+    }
+    if (count_only) {
+        std::lock_guard<std::mutex> lock(enc->d->bounds_mutex);
+        if (enc->d->packing_bound == -1) {
+            int32_t lb = 0;
+            enc->d->packing_bound = tss_lower_bound(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), seed, 0, nullptr, 0, &lb) == TSS_OK ? lb : -2;
+        }
+        if (enc->d->packing_bound >= 0 && info->card_limit_1x1 < enc->d->packing_bound) return TSS_UNSAT;
+        if (enc->d->lp_count_bound >= 0 && info->card_limit_1x1 < enc->d->lp_count_bound) return TSS_UNSAT;
+    }
     std::vector<tss_platform> plats((size_t)E.w * E.h + 1);
     int32_t n = 0;
     const int64_t max_steps = give_up_steps > 0 ? -give_up_steps : 0;   // a SAT-like call with a give-up point (tss.h)
@@ -145,8 +172,26 @@ int tss_solve_instance(tss_engine* e, const tss_cnf* c, const tss_encoding* enc,
         rc = tss_solve_upper_bound(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), info->card_limit_1x1, seed, 0, max_steps,
                                    plats.data(), (int32_t)plats.size(), &n);
     }
-    if (rc != TSS_SAT) return rc;
-    return tss_witness_for_cnf(e, c, enc, plats.data(), n, assignment);
+    if (rc == TSS_SAT) return tss_witness_for_cnf(e, c, enc, plats.data(), n, assignment);
+    if (rc == TSS_UNKNOWN && count_only) {   // nothing found within the limit: can the fractional bound certify that nothing exists?
+        std::lock_guard<std::mutex> lock(enc->d->bounds_mutex);
+        if (enc->d->lp_count_bound == -1) {
+            int64_t lb = 0;
+            enc->d->lp_count_bound = tss_lower_bound_lp(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), nullptr, 0, 0, nullptr, nullptr, nullptr, &lb, nullptr) == TSS_OK ? lb : -2;
+        }
+        if (enc->d->lp_count_bound >= 0 && info->card_limit_1x1 < enc->d->lp_count_bound) return TSS_UNSAT;
+    }
+    if (rc == TSS_UNKNOWN && weight_only) {   // the same question about the GUI's weight limit (crates/gui/src/app.rs:235-239)
+        std::lock_guard<std::mutex> lock(enc->d->bounds_mutex);
+        const std::vector<int32_t> wv(weights, weights + 3 * (size_t)info->n_weights);
+        if (enc->d->lp_weight_bound == -1 || enc->d->lp_weights != wv) {
+            int64_t lb = 0;
+            enc->d->lp_weights = wv;
+            enc->d->lp_weight_bound = tss_lower_bound_lp(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), weights, info->n_weights, 0, nullptr, nullptr, nullptr, &lb, nullptr) == TSS_OK ? lb : -2;
+        }
+        if (enc->d->lp_weight_bound >= 0 && info->weight_limit < enc->d->lp_weight_bound) return TSS_UNSAT;
+    }
+    return rc;
 }
 
 }  // extern "C"

@@ -9,9 +9,9 @@
 //     [exact solver on the same clauses]  only when the GPU has no answer and the lower bound has not closed the gap
 //     tss_layout_from_assignment          PlatformLayout::from_assignment             (main.rs:328-329)
 //     tss_validate                        layout.validate (warn only)                 (main.rs:353-361)
-// and prints what the REPL prints (main.rs:331-352).  The engine proves nothing: UNSAT comes from the exact solver
-// (`--exact CMD`, any DIMACS solver that prints `s SATISFIABLE|UNSATISFIABLE` and `v ...` lines, e.g. `z3 -dimacs`, glucose,
-// kissat) or from the packing lower bound meeting the count (tss_lower_bound).
+// and prints what the REPL prints (main.rs:331-352).  UNSAT comes from the exact solver (`--exact CMD`, any DIMACS solver that
+// prints `s SATISFIABLE|UNSATISFIABLE` and `v ...` lines, e.g. `z3 -dimacs`, glucose, kissat) or from tss_solve_instance when the
+// limit lies below a certified lower bound of the instance (packing / fractional LP); a search that finds nothing proves nothing.
 //
 //   tss_repl PROJECT.toml [--platforms default|1x1] [-l k:v[,k:v]] [--exact "CMD"] [--seed N] [--no-lower-bound] [--quiet] [--repeat N]
 #include <algorithm>
@@ -148,26 +148,12 @@ int main(int argc, char** argv) {
         int32_t K = 0;
         tss_encoding_sizes(enc, nullptr, nullptr, nullptr, &K);
 
-        bool only_count = true;   // the lower bound speaks about the platform count: usable when that is the only limit
-        for (size_t i = 0; i + 2 < card.size(); i += 3) only_count = only_count && card[i] == 1 && card[i + 1] == 1;
-        if (use_lb && only_count && w <= 32 && h <= 32) {
-            if (tss_lower_bound(e, grid.data(), w, h, all_defs, n_defs, seed, 0, nullptr, 0, &lower) != TSS_OK) lower = -1;
-
-            if (!quiet && lower >= 0) SAY("Lower bound: %d platforms\n", lower);
-        }
+        // the certified lower bounds live behind tss_solve_instance (it answers TSS_UNSAT below them), exactly where the Rust shim's
+        // solve() sees them: this driver, like the REPL's, knows nothing about bounds
+        tss_engine_certified_unsat(e, use_lb ? 1 : 0);
 
         int64_t give_up = 1024;
-        bool lp_done = false;   // the fractional bound (a simplex solve) is only computed when the packing bound does not already close the gap
         for (;;) {
-            // the 1x1 limit of this iteration (PlatformLimits.card_limits[1x1], main.rs:346)
-            int bound = -1;
-            for (size_t i = 0; i < card.size(); i += 3)
-                if (card[i] == 1 && card[i + 1] == 1) bound = card[i + 2];
-            if (lower >= 0 && best >= 0 && bound >= 0 && bound < lower) {   // nothing below the lower bound exists
-                SAY("No solution found for the current constraints\n");
-                verdict = "optimal (lower bound)";
-                break;
-            }
             int32_t n_vars = 0, n_clauses = 0;
             int64_t n_lits = 0;
             tss_encoding_with_limits(enc, card.data(), (int32_t)card.size() / 3, nullptr, 0, 0, 0, &n_vars, &n_clauses, &n_lits, nullptr, nullptr);
@@ -191,27 +177,12 @@ int main(int argc, char** argv) {
                 tss_clear_interrupt(e);
                 const int rc = tss_solve_instance(e, cnf, inst, &info, nullptr, seed++, give_up, assignment.data());
                 if (rc < 0) std::fprintf(stderr, "tss_solve_instance: %s\n", tss_last_error(e));   // logged, never fatal (crates/gui/src/app.rs:160-173)
-                result = rc == TSS_SAT ? 10 : 0;
+                result = rc == TSS_SAT ? 10 : rc == TSS_UNSAT ? 20 : 0;   // UNSAT: the limit lies below a certified lower bound
                 gpu_solves++;
                 if (result == 10) {
                     tss_stats st;
                     tss_get_stats(e, &st);
                     give_up = 32 * st.last_solve_steps > 1024 ? 32 * st.last_solve_steps : 1024;
-                }
-            }
-            if (result == 0 && lower >= 0 && !lp_done && best >= 0) {   // the GPU found nothing below the current count: can the fractional bound certify it?
-                lp_done = true;
-                int64_t lp_bound = 0;
-                if (tss_lower_bound_lp(e, grid.data(), w, h, all_defs, n_defs, nullptr, 0, 0, nullptr, nullptr, nullptr, &lp_bound, nullptr) == TSS_OK && lp_bound > lower) {
-                    lower = (int32_t)lp_bound;
-                    if (!quiet) SAY("Lower bound (fractional): %d platforms\n", lower);
-                }
-                if (bound >= 0 && bound < lower) {
-                    if (inst) tss_encoding_destroy(inst);
-                    tss_cnf_destroy(cnf);
-                    SAY("No solution found for the current constraints\n");
-                    verdict = "optimal (lower bound)";
-                    break;
                 }
             }
             if (result == 0 && !exact_cmd.empty()) {   // the exact solver: every UNSAT answer comes from here
@@ -221,7 +192,12 @@ int main(int argc, char** argv) {
             }
             if (inst) tss_encoding_destroy(inst);
             tss_cnf_destroy(cnf);
-            if (result == 20) { SAY("No solution found for the current constraints\n"); verdict = best >= 0 ? "optimal (exact solver)" : "unsatisfiable"; break; }
+            if (result == 20) {
+                SAY("No solution found for the current constraints\n");
+                verdict = best < 0 ? "unsatisfiable" : source == "exact" ? "optimal (exact solver)" : "optimal (lower bound)";
+                if (best >= 0 && source != "exact") lower = best;   // the certified bound that closed the loop is at least the limit it refused + 1
+                break;
+            }
             if (result != 10) { SAY("Solver interrupted\n"); verdict = "unknown (no exact solver answer)"; break; }
 
             std::vector<tss_platform> plats((size_t)w * h + 1);
