@@ -49,7 +49,7 @@ KERNEL_NAMES = {1: "sls_kernel (one chain per warp)", 2: "sls_h16_kernel (two ch
 # per-launch DRAM traffic of each variant, PASTED from its committed ncu capture (profiles/): not measured per run
 KERNEL_NCU = {
     2: {"traffic": 3067392, "traffic_note": "pasted from profiles/r1_sls_h16_kernel.md (ncu --set full, 9472 chains x 512 steps): chain states only"},
-    3: {"traffic": 11065344, "traffic_note": "pasted from profiles/r1_sls_t16_kernel.md (ncu --set full, 56832 chains x 512 steps): chain states + site lists"},
+    3: {"traffic": 11063040, "traffic_note": "pasted from profiles/r2_sls_t16_kernel.md (ncu --set full, 56832 chains x 512 steps; dram read 10 978 816 + write 84 224 bytes): chain states + site lists"},
 }
 
 

@@ -1064,7 +1064,9 @@ def _run_repl(tmp_path, grid, *args):
     out = subprocess.run([exe, str(proj), "--exact", exact, *args], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr
     summary = [ln for ln in out.stdout.splitlines() if ln.startswith("# best=")][-1]
-    fields = dict(kv.split("=", 1) for kv in summary[2:].replace('verdict="', "verdict=").replace('" gpu', " gpu").split(" ") if "=" in kv)
+    import re
+    fields = dict(kv.split("=", 1) for kv in re.sub(r'verdict="[^"]*" ', "", summary[2:]).split(" ") if "=" in kv)
+    fields["verdict"] = re.search(r'verdict="([^"]*)"', summary).group(1)
     counts = [int(ln.split("(")[1].split()[0]) for ln in out.stdout.splitlines() if ln.startswith("Solution found")]
     return out.stdout, fields, counts
 
