@@ -25,6 +25,9 @@ with tempfile.TemporaryDirectory() as tmp:
         with open(path, "w") as f:
             f.write(T.WorldGrid(grids[name]).to_toml())
         for pset in ("default", "1x1"):
-            r = subprocess.run([exe, path, "--platforms", pset, "--seed", "3", "--quiet", "--repeat", "21"], capture_output=True, text=True, timeout=600)
-            out[f"{name} {pset}"] = [ln for ln in r.stdout.splitlines() if ln.startswith("# best=")][-1] if r.returncode == 0 else r.stderr[-300:]
+            r = subprocess.run([exe, path, "--platforms", pset, "--seed", "3", "--quiet", "--repeat", "21", "--phases"], capture_output=True, text=True, timeout=600)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("# ")]
+            out[f"{name} {pset}"] = lines[0] if r.returncode == 0 else r.stderr[-300:]
+            if r.returncode == 0 and len(lines) > 1:
+                out[f"{name} {pset} phases"] = lines[1]
 print(json.dumps(out, indent=1))

@@ -265,9 +265,16 @@ def test_cnf_propagate_on_optimum_witnesses(eng, fixtures, readme):
         assert conflict[0] < 0 and wc < 0 and np.array_equal(prop[0][1:], want[1:])
         prop[prop == 2] = 0
         assert ocnf.count_falsified(prop[0]) == (0, -1)
+        # the same completion in ONE launch (tss_witness_for_cnf -> cnf_complete_kernel: in-place propagation, open variables
+        # False, every clause checked): the same model, variable for variable; not a model when a support is missing
+        dev = eng.upload_cnf(cnf)
+        fused = dev.witness(enc, lay)
+        assert fused is not None and np.array_equal(fused[1:], prop[0][1:])
+        assert dev.witness(enc, T.PlatformLayout(T.Platform(x, y, ONE, False) for x, y in sup[1:])) is None
         tight = enc.with_limits(T.PlatformLimits.new_unweighted({ONE: bound - 1}))
         otight = O.Encoding(O.PLATFORMS_1X1, g).with_limits({(1, 1): bound - 1})
         assert _check_propagation(eng, g, enc, tight, otight, [_plat_only_assignment(enc, tight, sup)], [sup], bound - 1) == 0
+        assert eng.upload_cnf(tight).witness(enc, lay) is None          # one platform more than the bound allows: a conflict in the totalizer
     assert n_clean == len(cases) >= 10
 
 

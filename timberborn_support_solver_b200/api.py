@@ -415,6 +415,16 @@ class DeviceCnf:
         e._check(e.lib.tss_cnf_propagate(e._h, self._h, _ptr(a, C.c_uint8), len(a), _ptr(conflict, C.c_int32), C.byref(rounds)))
         return a, conflict, rounds.value
 
+    def witness(self, encoding: "Encoding", layout: "PlatformLayout"):
+        """tss_witness_for_cnf: the layout completed into a model of these clauses (platform + terrain-layer variables from the
+        layout, auxiliaries by unit propagation, open variables False, every clause checked — one fused launch, csrc/cnf.cu
+        cnf_complete_kernel) -> assignment uint8[n_vars + 1], or None when it is not a model (e.g. the layout exceeds a limit)."""
+        plats = list(layout.platforms().values())
+        a = np.zeros(self.cnf.n_vars + 1, np.uint8)
+        e = self.engine
+        rc = e._check(e.lib.tss_witness_for_cnf(e._h, self._h, encoding._h, _plat_array(plats), len(plats), _ptr(a, C.c_uint8)))
+        return a if rc == 10 else None
+
 
 class Search:
     """A device-resident SLS portfolio on one terrain (kernel (b))."""
@@ -713,19 +723,12 @@ class GpuBoundSolver:
             res, layout = self.engine.solve_upper_bound(self.encoding._grid, self.encoding.defs, bound, self.seed, self.budget_ms, self.max_steps)
         if res != SAT:
             return INTERRUPTED
-        a = self.engine.layout_to_assignment(self.encoding, layout)
-        if self._cnf is not None:  # witness check against the very clauses the exact solver would get (kernel (c))
-            full = np.full(self._cnf.n_vars + 1, 2, np.uint8)
-            full[: len(a)] = a
-            # auxiliary (cardinality / PB) variables are implied: unit propagation assigns them or finds a conflict
-            prop, conflict, _ = self._dev.propagate(full[None, :])
-            if conflict[0] >= 0:
+        if self._cnf is not None:  # witness against the very clauses the exact solver would get (kernel (c)), one fused launch
+            a = self._dev.witness(self.encoding, layout)
+            if a is None:
                 return INTERRUPTED
-            prop[prop == 2] = 0
-            nf, _ = self._dev.check(prop)
-            if nf[0] != 0:
-                return INTERRUPTED
-            a = prop[0]
+        else:
+            a = self.engine.layout_to_assignment(self.encoding, layout)
         self._solution, self._layout = a, layout
         return SAT
 

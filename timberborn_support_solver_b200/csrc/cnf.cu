@@ -11,14 +11,22 @@
 //   propagation  assigning a literal is ONE atomicOr on ONE plane (monotone, so the fixpoint is order independent);
 //                rounds are synchronous — read the planes of the previous round, OR into a copy — so the number of
 //                rounds is a property of the instance and equals the oracle's (oracle/capi.cpp tsso_cnf_propagate).
+#include <algorithm>
+#include <atomic>
 #include <cstdlib>
+#include <cstring>
 
 #include "engine.hpp"
 
 struct tss_cnf {
     tss_engine* engine = nullptr;
+    void* blob = nullptr;          // ONE stream-ordered allocation from the engine's pool: lits | offsets | pad4 | short16 | long_ids | n_long | active
     int32_t* lits = nullptr;
     uint32_t* offsets = nullptr;
+    int4* pad4 = nullptr;          // [n_clauses] clauses of 1..4 literals padded with 0 (one 16-byte load per clause); x == 0: see long_ids
+    short4* short16 = nullptr;     // the same in 16-bit literals when n_vars < 32768: what cnf_complete_kernel keeps resident in shared memory
+    int* active = nullptr;         // [n_clauses] scratch of cnf_complete_kernel (the clauses its first sweep found unsatisfied)
+    int* long_ids = nullptr;       // clauses with more than 4 literals (and empty ones), in no particular order; long_ids[n_clauses] = their number
     int n_clauses = 0, n_vars = 0;
     int64_t n_lits = 0;
 };
@@ -150,6 +158,138 @@ __global__ void cnf_propagate_kernel(const int32_t* __restrict__ lits, const uin
     }
 }
 
+// ONE witness, one launch (tss_witness_for_cnf): unit propagation to the fixpoint, open variables set False, every clause
+// checked — the whole completion of a GPU layout into a model of the uploaded clauses.  The batch kernels above pay a launch
+// and two plane copies per round plus a host round trip per eight rounds (210-610 us for one assignment of test/ex1 / ex2,
+// r2 TSS_TRACE); here the assignment sits in shared memory as one byte per variable and ONE CTA sweeps the clauses until
+// nothing changes.  Propagation is IN PLACE (a clause sees what earlier clauses of the same sweep forced): unit propagation is
+// confluent — the fixpoint, and whether it holds a conflict, do not depend on the order — so the result equals the
+// synchronous rounds of cnf_propagate_kernel (tests/test_gpu.py compares both); only the number of sweeps is smaller.
+// out[0] = a clause left without a true or open literal (conflict) or -1, out[1] = clauses falsified by the completed
+// assignment, out[2] = sweeps.
+constexpr int COMPLETE_THREADS = 1024;
+constexpr size_t COMPLETE_MAX_BYTES = 200 * 1024;   // variables + 1 that fit one CTA's shared memory
+
+// padded copy of the short clauses (built once per upload, on the device): the sweep of cnf_complete_kernel then needs ONE
+// independent, coalesced 16-byte load per clause instead of the dependent chain offsets -> literals (the first version walked
+// the CSR: 33 us per sweep over the 25 K clauses of test/ex2.toml with the default-8 set, latency of one CTA's dependent L2 reads)
+__global__ void cnf_short_kernel(const int32_t* __restrict__ lits, const uint32_t* __restrict__ offsets, int n_clauses, int4* __restrict__ pad4,
+                                 short4* __restrict__ short16, int* __restrict__ long_ids) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_clauses) return;
+    const uint32_t k0 = offsets[c], len = offsets[c + 1] - k0;
+    int4 q = make_int4(0, 0, 0, 0);
+    if (len >= 1 && len <= 4) {
+        q.x = lits[k0];
+        if (len > 1) q.y = lits[k0 + 1];
+        if (len > 2) q.z = lits[k0 + 2];
+        if (len > 3) q.w = lits[k0 + 3];
+    } else {
+        long_ids[atomicAdd(&long_ids[n_clauses], 1)] = c;
+    }
+    pad4[c] = q;
+    if (short16) short16[c] = make_short4((short)q.x, (short)q.y, (short)q.z, (short)q.w);
+}
+
+// one padded clause against the assignment bytes: 0 = satisfied, 1 = unit (forces `forced`), 2 = every literal false, 3 = open
+// in two or more literals
+__device__ __forceinline__ int clause4(const uint8_t* a, int l0, int l1, int l2, int l3, int& forced) {
+    const uint8_t x0 = a[abs(l0)], x1 = a[abs(l1)], x2 = a[abs(l2)], x3 = a[abs(l3)];
+    if (x0 == (l0 > 0) || x1 == (l1 > 0) || x2 == (l2 > 0) || x3 == (l3 > 0)) return 0;
+    const int open = (x0 == 2) + (x1 == 2) + (x2 == 2) + (x3 == 2);
+    forced = x0 == 2 ? l0 : (x1 == 2 ? l1 : (x2 == 2 ? l2 : l3));
+    return open == 1 ? 1 : (open == 0 ? 2 : 3);
+}
+// the same for a clause of any length from the CSR arrays
+__device__ __forceinline__ int clause_csr(const uint8_t* a, const int32_t* __restrict__ lits, const uint32_t* __restrict__ offsets, int c, int& forced) {
+    const uint32_t k1 = offsets[c + 1];
+    int open = 0;
+    for (uint32_t k = offsets[c]; k < k1; k++) {
+        const int l = lits[k];
+        const uint8_t x = a[abs(l)];
+        if (x == (l > 0)) return 0;
+        if (x == 2) { open++; forced = l; }
+    }
+    return open == 1 ? 1 : (open == 0 ? 2 : 3);
+}
+
+// Shared memory: [assignment bytes, padded to 16][resident clauses as short4].  `resident` short clauses (the first ones) are
+// copied in once and read from shared memory; clauses beyond that come from the int4 copy.
+// The FIRST sweep visits every clause and lists the ones that are not satisfied yet (`active`, global scratch); only those can
+// ever force a literal or end up falsified — a satisfied clause stays satisfied, assignments are never withdrawn — so the later
+// sweeps and the final check walk that list alone.  For a GPU layout every base variable arrives decided and the list is the
+// cardinality network of the limit (2.8 K of the 25 K clauses of test/ex2.toml with the default-8 set): 1 us per sweep instead
+// of 10 us (the full sweep is bound by bank conflicts of the random byte reads on one SM's shared memory).
+__global__ void __launch_bounds__(COMPLETE_THREADS, 1) cnf_complete_kernel(const int32_t* __restrict__ lits, const uint32_t* __restrict__ offsets,
+                                                                            const int4* __restrict__ pad4, const short4* __restrict__ short16,
+                                                                            const int* __restrict__ long_ids, int* __restrict__ active, int n_clauses,
+                                                                            int n_vars, int resident, uint8_t* __restrict__ a_glob, int* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* a = smem;   // 0 = False, 1 = True, 2 = unassigned; a[0] = 1 makes the padding literal 0 a false, decided literal
+    short4* sc = reinterpret_cast<short4*>(smem + (((size_t)n_vars + 1 + 15) & ~(size_t)15));
+    __shared__ int conflict, falsified, n_active;
+    for (int v = threadIdx.x; v <= n_vars; v += blockDim.x) a[v] = v ? a_glob[v] : 1;
+    for (int c = threadIdx.x; c < resident; c += blockDim.x) sc[c] = short16[c];
+    if (threadIdx.x == 0) { conflict = 0x7fffffff; falsified = 0; n_active = 0; }
+    const int n_long = long_ids[n_clauses];
+    __syncthreads();
+    auto short_clause = [&](int c, int& forced) -> int {   // -1: not a short clause (x == 0: long or empty, in long_ids)
+        int l0, l1, l2, l3;
+        if (c < resident) { const short4 q = sc[c]; l0 = q.x; l1 = q.y; l2 = q.z; l3 = q.w; }
+        else { const int4 q = pad4[c]; l0 = q.x; l1 = q.y; l2 = q.z; l3 = q.w; }
+        return l0 == 0 ? -1 : clause4(a, l0, l1, l2, l3, forced);
+    };
+    auto act = [&](int c, int r, int forced, int& changed) {
+        if (r == 1) { a[abs(forced)] = forced > 0; changed = 1; }   // (two clauses forcing opposite values: one of them ends up falsified, found by the next sweep)
+        else if (r == 2) atomicMin(&conflict, c);
+    };
+    // ---- first sweep: every clause
+    int changed = 0, forced = 0, sweeps = 1;
+#pragma unroll 4
+    for (int c = threadIdx.x; c < n_clauses; c += COMPLETE_THREADS) {
+        const int r = short_clause(c, forced);
+        if (r <= 0) continue;
+        act(c, r, forced, changed);
+        active[atomicAdd(&n_active, 1)] = c;
+    }
+    for (int i = threadIdx.x; i < n_long; i += COMPLETE_THREADS) {
+        const int c = long_ids[i], r = clause_csr(a, lits, offsets, c, forced);
+        if (r == 0) continue;
+        act(c, r, forced, changed);
+        active[atomicAdd(&n_active, 1)] = c;
+    }
+    // ---- later sweeps: the clauses that were not satisfied then
+    while (__syncthreads_or(changed) && conflict == 0x7fffffff) {   // (the barrier also publishes n_active, the list and the forced values)
+        __syncthreads();   // (nobody raises `conflict` for the next sweep before everyone has read it)
+        changed = 0;
+        const int n = n_active;
+        for (int i = threadIdx.x; i < n; i += COMPLETE_THREADS) {
+            const int c = active[i];
+            int r = short_clause(c, forced);
+            if (r < 0) r = clause_csr(a, lits, offsets, c, forced);
+            act(c, r, forced, changed);
+        }
+        sweeps++;
+    }
+    if (conflict == 0x7fffffff) {   // open variables False, then the clauses that were ever unsatisfied against the completed assignment
+        for (int v = threadIdx.x + 1; v <= n_vars; v += blockDim.x)
+            if (a[v] == 2) a[v] = 0;
+        __syncthreads();
+        int bad = 0;
+        const int n = n_active;
+        for (int i = threadIdx.x; i < n; i += COMPLETE_THREADS) {
+            const int c = active[i];
+            int r = short_clause(c, forced);
+            if (r < 0) r = clause_csr(a, lits, offsets, c, forced);
+            bad += r == 2;
+        }
+        if (bad) atomicAdd(&falsified, bad);
+        __syncthreads();
+    }
+    for (int v = threadIdx.x + 1; v <= n_vars; v += blockDim.x) a_glob[v] = a[v];
+    if (threadIdx.x == 0) { out[0] = conflict == 0x7fffffff ? -1 : conflict; out[1] = falsified; out[2] = sweeps; }
+}
+
 __global__ void cnf_relax_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ neg, uint32_t* __restrict__ pos2,
                                  uint32_t* __restrict__ neg2, long long total) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -179,6 +319,42 @@ static unsigned grid_for(tss_engine* e, long long total) {
 
 }  // namespace tss
 
+// Completion of ONE assignment in one launch (cnf_complete_kernel); TSS_E_UNSUPPORTED when the variables do not fit one CTA's
+// shared memory (the caller then takes the batch kernels).  conflict: clause index or -1; n_falsified counts the clauses the
+// completed assignment (open variables False) falsifies.
+int tss::cnf_complete_single(tss_engine* e, const tss_cnf* c, uint8_t* assignment, int32_t* conflict, int32_t* n_falsified) {
+    const size_t bytes = (size_t)c->n_vars + 1;
+    if (bytes > COMPLETE_MAX_BYTES || !c->pad4) return TSS_E_UNSUPPORTED;
+    TSS_CUDA(e, cudaSetDevice(e->device));
+    uint8_t* a_dev = (uint8_t*)e->dev(0, bytes + 16);
+    uint8_t* a_pin = (uint8_t*)e->pin(1, bytes + 16);
+    if (!a_dev || !a_pin) return TSS_E_CUDA;
+    int* out_dev = (int*)(a_dev + ((bytes + 3) & ~(size_t)3));
+    int* out_pin = (int*)(a_pin + ((bytes + 3) & ~(size_t)3));
+    // shared memory: the assignment bytes, then as many 16-bit padded clauses as fit (all of them for every named instance)
+    const size_t a_bytes = (bytes + 15) & ~(size_t)15, smem_cap = (size_t)220 * 1024;
+    const int resident = c->short16 ? (int)std::min<size_t>((size_t)c->n_clauses, (smem_cap - a_bytes) / sizeof(short4)) : 0;
+    const size_t smem = a_bytes + sizeof(short4) * (size_t)resident;
+    TSS_CUDA(e, cudaFuncSetAttribute(cnf_complete_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+    std::memcpy(a_pin, assignment, bytes);
+    TSS_CUDA(e, cudaMemcpyAsync(a_dev, a_pin, bytes, cudaMemcpyHostToDevice, e->stream));
+    TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    cnf_complete_kernel<<<1, COMPLETE_THREADS, smem, e->stream>>>(c->lits, c->offsets, c->pad4, c->short16, c->long_ids, c->active, c->n_clauses, c->n_vars, resident, a_dev, out_dev);
+    TSS_CHECK_LAUNCH(e);
+    TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    e->stats.kernel_launches++;
+    TSS_CUDA(e, cudaMemcpyAsync(a_pin, a_dev, ((bytes + 3) & ~(size_t)3) + 12, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaStreamSynchronize(e->stream));
+    std::memcpy(assignment, a_pin, bytes);
+    *conflict = out_pin[0];
+    *n_falsified = out_pin[1];
+    e->stats.clauses_checked += (uint64_t)c->n_clauses * (uint64_t)(out_pin[2] + 1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->stats.device_ms = ms;
+    return TSS_OK;
+}
+
 using namespace tss;
 
 extern "C" {
@@ -193,13 +369,34 @@ int tss_cnf_upload(tss_engine* e, const int32_t* lits, const uint32_t* offsets, 
         if (v == 0 || v > n_vars) return e->fail(TSS_E_INVALID, "tss_cnf_upload: literal %d out of range (n_vars = %d)", lits[k], n_vars);
     }
     TSS_CUDA(e, cudaSetDevice(e->device));
+    // one stream-ordered allocation from the engine's pool (the bound-tightening loop uploads a CNF per iteration: cudaMalloc +
+    // cudaFree cost more than the copy), nothing synchronises: the copies and the short-clause build are ordered on the stream
+    const bool fused = (size_t)n_vars + 1 <= COMPLETE_MAX_BYTES;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_lits = 0, o_offs = o_lits + al(sizeof(int32_t) * (size_t)(n_lits > 0 ? n_lits : 1)), o_short = o_offs + al(sizeof(uint32_t) * ((size_t)n_clauses + 1)),
+                 o_s16 = o_short + (fused ? al(sizeof(int4) * (size_t)(n_clauses > 0 ? n_clauses : 1)) : 0),
+                 o_long = o_s16 + (fused && n_vars < 32768 ? al(sizeof(short4) * (size_t)(n_clauses > 0 ? n_clauses : 1)) : 0),
+                 o_act = o_long + (fused ? al(sizeof(int) * ((size_t)n_clauses + 1)) : 0), total = o_act + (fused ? al(sizeof(int) * ((size_t)n_clauses + 1)) : 0);
     tss_cnf* c = new tss_cnf();
     c->engine = e; c->n_clauses = n_clauses; c->n_vars = n_vars; c->n_lits = n_lits;
-    cudaError_t err = cudaMalloc(&c->lits, sizeof(int32_t) * (size_t)(n_lits > 0 ? n_lits : 1));
-    if (err == cudaSuccess) err = cudaMalloc(&c->offsets, sizeof(uint32_t) * (size_t)(n_clauses + 1));
+    cudaError_t err = e->pool ? cudaMallocFromPoolAsync(&c->blob, total, e->pool, e->stream) : cudaMallocAsync(&c->blob, total, e->stream);
+    if (err == cudaSuccess) {
+        c->lits = (int32_t*)((char*)c->blob + o_lits);
+        c->offsets = (uint32_t*)((char*)c->blob + o_offs);
+        if (fused) { c->pad4 = (int4*)((char*)c->blob + o_short); c->long_ids = (int*)((char*)c->blob + o_long); }
+        if (fused) c->active = (int*)((char*)c->blob + o_act);
+        if (fused && n_vars < 32768) c->short16 = (short4*)((char*)c->blob + o_s16);
+    }
     if (err == cudaSuccess && n_lits) err = cudaMemcpyAsync(c->lits, lits, sizeof(int32_t) * (size_t)n_lits, cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(c->offsets, offsets, sizeof(uint32_t) * (size_t)(n_clauses + 1), cudaMemcpyHostToDevice, e->stream);
-    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err == cudaSuccess && fused) {
+        err = cudaMemsetAsync(c->long_ids + n_clauses, 0, sizeof(int), e->stream);
+        if (err == cudaSuccess && n_clauses > 0) {
+            cnf_short_kernel<<<(n_clauses + 255) / 256, 256, 0, e->stream>>>(c->lits, c->offsets, n_clauses, c->pad4, c->short16, c->long_ids);
+            err = cudaGetLastError();
+            e->stats.kernel_launches++;
+        }
+    }
     if (err != cudaSuccess) { tss_cnf_destroy(c); return e->fail(TSS_E_CUDA, "tss_cnf_upload: %s", cudaGetErrorString(err)); }
     *out = c;
     return TSS_OK;
@@ -209,8 +406,11 @@ int tss_cnf_num_vars(const tss_cnf* c) { return c ? c->n_vars : TSS_E_INVALID; }
 
 void tss_cnf_destroy(tss_cnf* c) {
     if (!c) return;
-    cudaFree(c->lits);
-    cudaFree(c->offsets);
+    // stream-ordered free into the engine's pool (no device synchronisation); a handle that outlived its engine frees synchronously
+    if (c->blob) {
+        if (tss::engine_alive(c->engine)) cudaFreeAsync(c->blob, c->engine->stream);
+        else cudaFree(c->blob);
+    }
     delete c;
 }
 

@@ -2,6 +2,8 @@
 // (world / encoder / layout decode) live in capi_host.cpp.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 #include "engine.hpp"
 
@@ -198,6 +200,15 @@ static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+namespace tss {
+static std::mutex g_engines_mutex;
+static std::vector<const tss_engine*> g_engines;   // live engines
+bool engine_alive(const tss_engine* e) {
+    std::lock_guard<std::mutex> lock(g_engines_mutex);
+    return std::find(g_engines.begin(), g_engines.end(), e) != g_engines.end();
+}
+}  // namespace tss
+
 extern "C" {
 
 int tss_version(void) { return TSS_VERSION; }
@@ -228,8 +239,21 @@ int tss_engine_create(int device, tss_engine** out) {
         ok = cudaMalloc((void**)&e->interrupt_dev, sizeof(int)) == cudaSuccess && cudaMemset(e->interrupt_dev, 0, sizeof(int)) == cudaSuccess &&
              cudaStreamCreateWithFlags(&e->irq_stream, cudaStreamNonBlocking) == cudaSuccess;
     }
+    if (ok) {   // the engine's own pool for stream-ordered allocations; freed blocks stay cached (release threshold = everything)
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        uint64_t keep = ~0ull;
+        if (cudaMemPoolCreate(&e->pool, &props) != cudaSuccess || cudaMemPoolSetAttribute(e->pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) {
+            cudaGetLastError();
+            if (e->pool) { cudaMemPoolDestroy(e->pool); e->pool = nullptr; }   // (cudaMallocAsync from the device's default pool then)
+        }
+    }
     if (!ok) { cudaGetLastError(); tss_engine_destroy(e); return TSS_E_CUDA; }
     e->stream = e->own_stream;
+    { std::lock_guard<std::mutex> lock(tss::g_engines_mutex); tss::g_engines.push_back(e); }
     *out = e;
     return TSS_OK;
 }
@@ -238,6 +262,7 @@ static void search_free(tss_search* s);
 
 void tss_engine_destroy(tss_engine* e) {
     if (!e) return;
+    { std::lock_guard<std::mutex> lock(tss::g_engines_mutex); tss::g_engines.erase(std::remove(tss::g_engines.begin(), tss::g_engines.end(), e), tss::g_engines.end()); }
     cudaSetDevice(e->device);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     if (e->cached_search) { search_free(e->cached_search); e->cached_search = nullptr; }
@@ -254,6 +279,7 @@ void tss_engine_destroy(tss_engine* e) {
     if (e->ev3) cudaEventDestroy(e->ev3);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->pool) cudaMemPoolDestroy(e->pool);   // (blocks of CNF handles that outlive the engine stay valid until they are freed, CUDA defers the release)
     delete e;
 }
 

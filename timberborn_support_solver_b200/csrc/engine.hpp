@@ -36,6 +36,7 @@ struct tss_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the last kernel-level operation (epoch, evaluation)
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;  // bracket a whole multi-epoch pass (tss_solve_batch chunk)
     cudaDeviceProp prop{};
+    cudaMemPool_t pool = nullptr;   // stream-ordered allocations that come and go with every solver call (uploaded CNFs): cached, never returned to the OS while the engine lives
     std::string error;
     tss_stats stats{};
     // Interrupt flag polled by the search kernels.  It lives in DEVICE memory (an L2 hit per poll): polling a mapped
@@ -95,6 +96,10 @@ int launch_eval_platforms(tss_engine* e, const uint32_t* grid_rows_dev, int w, i
                           uint8_t* flags_dev, uint32_t* layers_dev);
 // packs u8 masks [n][w*h] into the compact row format on the device
 int launch_pack_bytes(tss_engine* e, const uint8_t* bytes_dev, int w, int h, int64_t n, void* compact_dev);
+// engine.cu — is this pointer an engine that has not been destroyed (handles that may outlive their engine ask before touching it)
+bool engine_alive(const tss_engine* e);
+// cnf.cu — one assignment completed (unit propagation, open variables False, every clause checked) in one launch
+int cnf_complete_single(tss_engine* e, const struct ::tss_cnf* c, uint8_t* assignment, int32_t* conflict, int32_t* n_falsified);
 // host helper: pack one u8 grid into compact rows
 void pack_compact_host(const uint8_t* grid, int w, int h, uint8_t* out);
 void rows_to_compact_host(const uint32_t* rows, int w, int h, uint8_t* out);

@@ -3,6 +3,9 @@
 // crates/gui/src/solver_backend.rs:69-97).  Host C++ only; every GPU step goes through the public C ABI, so this file is
 // also the reference for the call sequence of the Rust shim (rust/tss/src/lib.rs) and of tools/tss_repl.cpp.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -40,6 +43,20 @@ void instance_record(const std::shared_ptr<const tss_encoding_data>& d, const Pl
     if (g_records.size() > kMaxRecords) g_records.pop_back();
 }
 }  // namespace tss
+
+// TSS_TRACE=1: wall microseconds of the stages of tss_solve_instance / tss_witness_for_cnf on stderr (profiles/tss_repl_timing.py)
+namespace {
+struct Trace {
+    bool on = std::getenv("TSS_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[tss trace] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(now - t).count());
+        t = now;
+    }
+};
+}  // namespace
 
 extern "C" {
 
@@ -110,18 +127,29 @@ int tss_witness_for_cnf(tss_engine* e, const tss_cnf* c, const tss_encoding* enc
     if (nv < nb) return e->fail(TSS_E_INVALID, "tss_witness_for_cnf: the CNF has %d variables, the encoding %d", nv, nb);
     // platform variables from the layout (every dims key contained in a platform, encoder.rs:449-458), terrain layers from the
     // evaluator's support layers (kernel (a)); whatever the limits added (totalizer / PB auxiliaries) starts unassigned
+    Trace tr;
     int rc = tss_layout_to_assignment(e, enc, plats, n, assignment);
     if (rc < 0) return rc;
+    tr.lap("witness: layout_to_assignment");
     std::memset(assignment + nb + 1, 2, (size_t)(nv - nb));
-    int32_t conflict = -1;
-    rc = tss_cnf_propagate(e, c, assignment, 1, &conflict, nullptr);   // ... and is implied: unit propagation assigns it (kernel (c))
+    int32_t conflict = -1, n_falsified = 0;
+    // ... and is implied: unit propagation assigns it, open variables become False, and the model is checked against every
+    // clause the exact solver received (kernel (c)) — in ONE launch when the variables fit a CTA's shared memory
+    rc = tss::cnf_complete_single(e, c, assignment, &conflict, &n_falsified);
+    if (rc == TSS_OK) {
+        tr.lap("witness: cnf_complete");
+        return conflict < 0 && n_falsified == 0 ? TSS_SAT : TSS_UNKNOWN;   // conflict: e.g. more platforms than the bound allows
+    }
+    if (rc != TSS_E_UNSUPPORTED) return rc;
+    rc = tss_cnf_propagate(e, c, assignment, 1, &conflict, nullptr);
     if (rc < 0) return rc;
-    if (conflict >= 0) return TSS_UNKNOWN;                              // e.g. more platforms than the bound allows
+    tr.lap("witness: cnf_propagate");
+    if (conflict >= 0) return TSS_UNKNOWN;
     for (int v = 1; v <= nv; v++)
         if (assignment[v] == 2) assignment[v] = 0;
-    int32_t n_falsified = 0;
-    rc = tss_cnf_check(e, c, assignment, 1, &n_falsified, nullptr);     // the model against every clause the exact solver received
+    rc = tss_cnf_check(e, c, assignment, 1, &n_falsified, nullptr);
     if (rc < 0) return rc;
+    tr.lap("witness: cnf_check");
     return n_falsified == 0 ? TSS_SAT : TSS_UNKNOWN;
 }
 
@@ -142,6 +170,7 @@ int tss_solve_instance(tss_engine* e, const tss_cnf* c, const tss_encoding* enc,
     // A limit below a CERTIFIED lower bound has no model: answer UNSAT without searching.  Only when the platform count is the
     // sole limit (the REPL's loop); the integral packing first (~0.1 ms, computed once per instance), the fractional LP only after
     // the search came back empty-handed.
+    Trace tr;
     const bool small = e->certified_unsat && E.w <= 32 && E.h <= 32;
     const bool count_only = small && info->card_limit_1x1 >= 0 && !info->has_weight_limit;
     const bool weight_only = small && info->card_limit_1x1 < 0 && info->has_weight_limit && info->n_weights > 0 && weights;
@@ -157,6 +186,7 @@ int tss_solve_instance(tss_engine* e, const tss_cnf* c, const tss_encoding* enc,
             int32_t lb = 0;
             enc->d->packing_bound = tss_lower_bound(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), seed, 0, nullptr, 0, &lb) == TSS_OK ? lb : -2;
         }
+        tr.lap("solve: packing bound");
         if (enc->d->packing_bound >= 0 && info->card_limit_1x1 < enc->d->packing_bound) return TSS_UNSAT;
         if (enc->d->lp_count_bound >= 0 && info->card_limit_1x1 < enc->d->lp_count_bound) return TSS_UNSAT;
     }
@@ -172,6 +202,7 @@ int tss_solve_instance(tss_engine* e, const tss_cnf* c, const tss_encoding* enc,
         rc = tss_solve_upper_bound(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), info->card_limit_1x1, seed, 0, max_steps,
                                    plats.data(), (int32_t)plats.size(), &n);
     }
+    tr.lap("solve: search");
     if (rc == TSS_SAT) return tss_witness_for_cnf(e, c, enc, plats.data(), n, assignment);
     if (rc == TSS_UNKNOWN && count_only) {   // nothing found within the limit: can the fractional bound certify that nothing exists?
         std::lock_guard<std::mutex> lock(enc->d->bounds_mutex);

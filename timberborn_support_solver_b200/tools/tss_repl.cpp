@@ -13,7 +13,7 @@
 // prints `s SATISFIABLE|UNSATISFIABLE` and `v ...` lines, e.g. `z3 -dimacs`, glucose, kissat) or from tss_solve_instance when the
 // limit lies below a certified lower bound of the instance (packing / fractional LP); a search that finds nothing proves nothing.
 //
-//   tss_repl PROJECT.toml [--platforms default|1x1] [-l k:v[,k:v]] [--exact "CMD"] [--seed N] [--no-lower-bound] [--quiet] [--repeat N]
+//   tss_repl PROJECT.toml [--platforms default|1x1] [-l k:v[,k:v]] [--exact "CMD"] [--seed N] [--no-lower-bound] [--quiet] [--repeat N] [--phases]
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -93,8 +93,10 @@ int main(int argc, char** argv) {
     std::string project, exact_cmd, platforms = "default";
     std::vector<int32_t> card;
     uint64_t seed = 0;
-    bool use_lb = true, quiet = false;
+    bool use_lb = true, quiet = false, phases = false;
     int repeat = 1;
+    double ph[8] = {};   // --phases: wall ms per call site, summed over the warm repeats
+    static const char* const PH[8] = {"encoding_create", "with_limits", "cnf_upload", "instance_find", "solve_instance", "from_assignment", "validate", "destroy"};
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         if (a == "--platforms" && i + 1 < argc) platforms = argv[++i];
@@ -104,6 +106,7 @@ int main(int argc, char** argv) {
         else if (a.rfind("-l", 0) == 0 && a.size() > 2) { if (!parse_limits(a.substr(2), card)) { std::fprintf(stderr, "bad -l argument\n"); return 2; } }
         else if (a == "--no-lower-bound") use_lb = false;
         else if (a == "--quiet") quiet = true;
+        else if (a == "--phases") phases = true;
         else if (a == "--repeat" && i + 1 < argc) repeat = std::atoi(argv[++i]) > 0 ? std::atoi(argv[i]) : 1;
         else if (project.empty()) project = a;
         else { std::fprintf(stderr, "usage: tss_repl PROJECT.toml [--platforms default|1x1] [-l k:v[,k:v]] [--exact CMD] [--seed N] [--no-lower-bound] [--quiet]\n"); return 2; }
@@ -144,7 +147,10 @@ int main(int argc, char** argv) {
         lower = -1; gpu_solves = exact_solves = 0; best = -1; verdict = "open";
         t_loop = now_ms();   // one `solve`: encode, bounds, loop (engine creation = CUDA context start-up, ~1-4 s of a fresh process, is reported apart)
         tss_encoding* enc = nullptr;
+        double tp = now_ms();
+#define PHASE(i) do { const double t_ = now_ms(); if (rep > 0) ph[i] += t_ - tp; tp = t_; } while (0)
         if (tss_encoding_create(grid.data(), w, h, all_defs, n_defs, &enc) != TSS_OK) { std::fprintf(stderr, "encode failed\n"); return 1; }
+        PHASE(0);
         int32_t K = 0;
         tss_encoding_sizes(enc, nullptr, nullptr, nullptr, &K);
 
@@ -161,14 +167,17 @@ int main(int argc, char** argv) {
             std::vector<uint32_t> offsets((size_t)n_clauses + 1);
             tss_encoding_with_limits(enc, card.data(), (int32_t)card.size() / 3, nullptr, 0, 0, 0, &n_vars, &n_clauses, &n_lits, lits.data(), offsets.data());
             lits.resize((size_t)n_lits);
+            PHASE(1);
 
             // ---- Solve::add_cnf: all the solver is given are the clauses
             tss_cnf* cnf = nullptr;
             if (tss_cnf_upload(e, lits.data(), offsets.data(), n_clauses, n_vars, &cnf) != TSS_OK) { std::fprintf(stderr, "%s\n", tss_last_error(e)); return 1; }
+            PHASE(2);
             tss_encoding* inst = nullptr;
             tss_instance_info info;
             const int found = tss_instance_find(lits.data(), offsets.data(), n_clauses, n_vars, &inst, &info, nullptr, 0);
 
+            PHASE(3);
             // ---- Solve::solve
             std::vector<uint8_t> assignment((size_t)n_vars + 1, 2);
             int result = 0;
@@ -185,13 +194,16 @@ int main(int argc, char** argv) {
                     give_up = 32 * st.last_solve_steps > 1024 ? 32 * st.last_solve_steps : 1024;
                 }
             }
+            PHASE(4);
             if (result == 0 && !exact_cmd.empty()) {   // the exact solver: every UNSAT answer comes from here
                 result = run_exact(exact_cmd, lits, offsets, n_vars, assignment);
                 source = "exact";
                 exact_solves++;
             }
+            tp = now_ms();
             if (inst) tss_encoding_destroy(inst);
             tss_cnf_destroy(cnf);
+            PHASE(7);
             if (result == 20) {
                 SAY("No solution found for the current constraints\n");
                 verdict = best < 0 ? "unsatisfiable" : source == "exact" ? "optimal (exact solver)" : "optimal (lower bound)";
@@ -203,6 +215,7 @@ int main(int argc, char** argv) {
             std::vector<tss_platform> plats((size_t)w * h + 1);
             int32_t n = 0;
             tss_layout_from_assignment(enc, assignment.data(), n_vars + 1, plats.data(), (int32_t)plats.size(), &n);
+            PHASE(5);
             if (n == 0) { SAY("Found a solution with no platforms - aborting\n"); verdict = "optimal (no platforms)"; best = 0; break; }
             best = n;
             bool has = false;
@@ -215,6 +228,7 @@ int main(int argc, char** argv) {
             for (auto& [d, c] : stats) SAY("%dx%d: %d\n", d.first, d.second, c);
             std::vector<uint8_t> unsupported((size_t)w * h), flags((size_t)n);
             const int uns = tss_validate(e, grid.data(), w, h, plats.data(), n, unsupported.data(), flags.data());
+            PHASE(6);
             int bad = uns;
             for (int i = 0; i < n; i++) bad += flags[i] != 0;
             if (!quiet) SAY(bad == 0 ? "Solution validation OK (%s)\n" : "Solution validation FAILED (%s)\n", source.c_str());
@@ -228,6 +242,11 @@ int main(int argc, char** argv) {
     const double warm = loop_ms.size() > 1 ? loop_ms[1 + (loop_ms.size() - 1) / 2] : loop_ms[0];
     std::printf("# best=%d lower_bound=%d verdict=\"%s\" gpu_solves=%d exact_solves=%d ms=%.3f setup_ms=%.1f repeats=%zu warm_ms=%.3f\n", best, lower,
                 verdict.c_str(), gpu_solves, exact_solves, loop_ms[0], t_setup - t_start, loop_ms.size(), warm);
+    if (phases && repeat > 1) {
+        std::printf("# phases (ms per solve, mean of %d warm repeats):", repeat - 1);
+        for (int i = 0; i < 8; i++) std::printf(" %s=%.3f", PH[i], ph[i] / (repeat - 1));
+        std::printf("\n");
+    }
     tss_engine_destroy(e);
     return 0;
 }
