@@ -290,14 +290,16 @@ int tss_lower_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, co
  * bound on the platform count, what the REPL minimises, main.rs:346) or, with `weights` (records (def_w, def_h, weight), the
  * PlatformLimits.weights map), what PlatformLayout::total_weight charges the platform (platform_layout.rs:174-183): a bound on
  * the GUI's objective (crates/gui/src/app.rs:235-245).  The LP is solved on the GPU (dense primal simplex, at most `max_pivots`
- * pivots, <= 0: default) and the result is CERTIFIED in integer arithmetic: out_weights[w*h] (optional) = floor(y * scale) per
+ * pivots, <= 0: default; `target` > 0: stop as soon as the bound reaches `target` — every simplex iterate is feasible, so stopping
+ * early only weakens the bound — which is all the bound-tightening loop asks: "is there no layout within limit = target - 1?";
+ * <= 0: to optimality) and the result is CERTIFIED in integer arithmetic: out_weights[w*h] (optional) = floor(y * scale) per
  * tile, *out_total = their sum, *out_max_load = the largest sum over the reach of any placement, recomputed from the reach
  * bitboards, and *out_bound = min over placements of ceil(total * cost / load) (= ceil(total / max_load) with unit costs) —
  * valid whatever the floating point solve did.  It dominates tss_lower_bound up to rounding (README terrain, 1x1 supports:
  * 12 -> 14 = the optimum).  out_info[3] (optional) = pivots, 1 if the simplex reached optimality, constraints.  Grids up to 32x32. */
 int tss_lower_bound_lp(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs, const int32_t* weights,
-                       int32_t n_weights, int32_t max_pivots, int32_t* out_weights, int64_t* out_total, int64_t* out_max_load, int64_t* out_bound,
-                       int32_t* out_info);
+                       int32_t n_weights, int32_t max_pivots, int64_t target, int32_t* out_weights, int64_t* out_total, int64_t* out_max_load,
+                       int64_t* out_bound, int32_t* out_info);
 /* Terrain batch: n independent terrains [n][w*h] (grids up to 32x32), 1x1 supports; `steps` SLS steps
  * per chain, `chains_per_terrain` independent chains per terrain sharing their bound every 1024 steps (0 = one CTA
  * = 4 chains, 8 for grids of <= 16 rows; otherwise rounded up to a multiple of that).  out_counts[n] = best count per

@@ -155,7 +155,7 @@ unsafe extern "C" {
 
     pub fn tss_lower_bound_lp(
         e: *mut tss_engine, grid: *const u8, w: i32, h: i32, defs: *const tss_dims, n_defs: i32, weights: *const i32, n_weights: i32, max_pivots: i32,
-        out_weights: *mut i32, out_total: *mut i64, out_max_load: *mut i64, out_bound: *mut i64, out_info: *mut i32,
+        target: i64, out_weights: *mut i32, out_total: *mut i64, out_max_load: *mut i64, out_bound: *mut i64, out_info: *mut i32,
     ) -> c_int;
     pub fn tss_encoding_terrain(enc: *const tss_encoding, grid: *mut u8, cap: usize, w: *mut i32, h: *mut i32) -> c_int;
     pub fn tss_encoding_defs(enc: *const tss_encoding, defs: *mut tss_dims, cap: i32, n: *mut i32) -> c_int;

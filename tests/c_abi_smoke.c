@@ -114,17 +114,17 @@ int main(void) {
     CHECK(tss_lower_bound(e, NULL, w, h, defs, 1, 1, 0, xy, 64, &n_packed) == TSS_E_INVALID);
     int32_t lp_w[64], lp_info[3];
     int64_t lp_total = 0, lp_max = 0, lp_bound = -1;
-    CHECK(tss_lower_bound_lp(e, grid, w, h, defs, 1, NULL, 0, 0, lp_w, &lp_total, &lp_max, &lp_bound, lp_info) == TSS_OK);
+    CHECK(tss_lower_bound_lp(e, grid, w, h, defs, 1, NULL, 0, 0, 0, lp_w, &lp_total, &lp_max, &lp_bound, lp_info) == TSS_OK);
     CHECK(lp_bound == 3 && lp_max > 0 && lp_bound == (lp_total + lp_max - 1) / lp_max && lp_info[1] == 1 && lp_info[2] == 19);
     int64_t sum = 0;
     for (int i = 0; i < w * h; i++) { CHECK(lp_w[i] >= 0 && (grid[i] || lp_w[i] == 0)); sum += lp_w[i]; }
     CHECK(sum == lp_total);
-    CHECK(tss_lower_bound_lp(e, grid, w, h, defs, 1, NULL, 0, 0, NULL, NULL, NULL, &lp_bound, NULL) == TSS_OK && lp_bound == 3);
-    CHECK(tss_lower_bound_lp(e, grid, w, h, defs, 1, NULL, 0, 0, NULL, NULL, NULL, NULL, NULL) == TSS_E_INVALID);
+    CHECK(tss_lower_bound_lp(e, grid, w, h, defs, 1, NULL, 0, 0, 3, NULL, NULL, NULL, &lp_bound, NULL) == TSS_OK && lp_bound == 3);
+    CHECK(tss_lower_bound_lp(e, grid, w, h, defs, 1, NULL, 0, 0, 0, NULL, NULL, NULL, NULL, NULL) == TSS_E_INVALID);
     {   /* the GUI's objective (app.rs:53-62): 1x1 = 5, 1xN = 1, 3x3 = 2, 5x5 = 4; one 5x5 costs 5+1+1+1+1+2+4 = 15 and is the optimum */
         const int32_t gui_w[24] = {1, 1, 5, 1, 2, 1, 1, 3, 1, 1, 4, 1, 1, 5, 1, 1, 6, 1, 3, 3, 2, 5, 5, 4};
         int64_t wb = -1;
-        CHECK(tss_lower_bound_lp(e, grid, w, h, defs, 8, gui_w, 8, 0, NULL, NULL, NULL, &wb, NULL) == TSS_OK && wb >= 5 && wb <= 15);
+        CHECK(tss_lower_bound_lp(e, grid, w, h, defs, 8, gui_w, 8, 0, 0, NULL, NULL, NULL, &wb, NULL) == TSS_OK && wb >= 5 && wb <= 15);
     }
 
     /* Solve::add_cnf + Solve::solve of the Rust shim: the solver is handed clauses only (solver_runner.rs:8-20) */

@@ -982,6 +982,15 @@ def test_fractional_lower_bound_certificate(eng, fixtures, readme, name, pset):
     want = {"readme/1x1": 14, "ex2/1x1": 14, "rect16/1x1": 14, "ex1/1x1": 3, "ex3/1x1": 4, "ex2/default8": 4}.get(key)
     if want is not None:
         assert r["bound"] == want
+    # target: stop as soon as the bound reaches it — fewer pivots, the same answer to "does the bound reach r?", still certified;
+    # a target above the LP optimum runs to optimality
+    early = eng.lower_bound_lp(T.WorldGrid(g), defs, target=r["bound"])
+    assert early["bound"] == r["bound"] and early["pivots"] <= r["pivots"]
+    _check_lp_certificate(g, defs, early)
+    if name in ("ex2", "readme", "rect16") and pset == "1x1":
+        assert early["pivots"] < r["pivots"] and not early["optimal"]
+    beyond = eng.lower_bound_lp(T.WorldGrid(g), defs, target=r["bound"] + 1)
+    assert beyond["optimal"] and beyond["bound"] == r["bound"]
     capped = eng.lower_bound_lp(T.WorldGrid(g), defs, max_pivots=5)                # an iteration cap only weakens the bound, it stays certified
     assert not capped["optimal"] or capped["pivots"] <= 5
     _check_lp_certificate(g, defs, capped)

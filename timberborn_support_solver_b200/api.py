@@ -653,9 +653,10 @@ class Engine:
                                              _ptr(out, C.c_int32), len(out), C.byref(n)))
         return [(int(x), int(y)) for x, y in out[: n.value]]
 
-    def lower_bound_lp(self, grid: WorldGrid, defs=PLATFORMS_DEFAULT[:1], max_pivots=0, weights: Optional[dict] = None):
+    def lower_bound_lp(self, grid: WorldGrid, defs=PLATFORMS_DEFAULT[:1], max_pivots=0, weights: Optional[dict] = None, target=0):
         """Fractional packing lower bound (tss_lower_bound_lp), certified in integers: on the platform count, or with `weights`
-        ({PlatformDef: weight}, the PlatformLimits.weights map) on PlatformLayout::total_weight.
+        ({PlatformDef: weight}, the PlatformLimits.weights map) on PlatformLayout::total_weight.  target > 0: the simplex stops as
+        soon as the bound reaches it (every iterate is feasible; enough for "is there nothing within target - 1?").
         -> dict(bound, weights int32[h, w], total, max_load, pivots, optimal, constraints)."""
         defs = list(defs)
         wts = np.zeros((grid.height, grid.width), np.int32)
@@ -663,7 +664,7 @@ class Engine:
         info = (C.c_int32 * 3)()
         rec = np.array([[d.width, d.height, v] for d, v in (weights or {}).items()], np.int32).reshape(-1, 3)
         self._check(self.lib.tss_lower_bound_lp(self._h, _ptr(grid.data, C.c_uint8), grid.width, grid.height, _defs_array(defs), len(defs),
-                                                _ptr(rec, C.c_int32) if len(rec) else None, len(rec), max_pivots,
+                                                _ptr(rec, C.c_int32) if len(rec) else None, len(rec), max_pivots, int(target),
                                                 _ptr(wts, C.c_int32), C.byref(total), C.byref(max_load), C.byref(bound), info))
         return dict(bound=bound.value, weights=wts, total=total.value, max_load=max_load.value, pivots=info[0], optimal=bool(info[1]), constraints=info[2])
 
@@ -794,7 +795,8 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
         assignment = solver.full_solution() if result == SAT else None
         if result != SAT and use_lower_bound and not lp_done and best is not None:
             lp_done = True                                      # the GPU found nothing below the current count: can the fractional bound certify it?
-            lower = max(lower, engine.lower_bound_lp(g, encoding.defs)["bound"])
+            # (asked only "does the bound reach the count at hand?": the simplex stops as soon as it does)
+            lower = max(lower, engine.lower_bound_lp(g, encoding.defs, target=best.platform_count())["bound"])
             if limits.card_limits.get(one) is not None and limits.card_limits[one] < lower:
                 steps.append(dict(bound=limits.card_limits[one], result=UNSAT, source="lower bound"))
                 proved = True

@@ -15,6 +15,7 @@ struct tss_encoding_data {
     mutable std::mutex bounds_mutex;
     mutable int packing_bound = -1;        // tss_lower_bound; -1 = not computed, -2 = not available for this instance
     mutable long long lp_count_bound = -1; // tss_lower_bound_lp on the platform count
+    mutable bool lp_count_final = false, lp_weight_final = false;   // the simplex ran to optimality (not stopped at a target): asking again cannot improve the bound
     mutable std::vector<int32_t> lp_weights;   // the weight table `lp_weight_bound` was computed for
     mutable long long lp_weight_bound = -1;    // tss_lower_bound_lp on the total weight
 };

@@ -40,7 +40,7 @@ int sls_run_h16(tss_engine* e, const uint32_t* rows_dev, const uint2* tabs_dev, 
 int run_peaks(tss_engine* e, double* out, int n_out);
 // lp.cu — fractional packing lower bound
 int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::vector<int2>& key_dims, const std::vector<int>& key_costs, int max_pivots,
-           int* out_weights, unsigned long long* totals, int* info);
+           long long target, int* out_weights, unsigned long long* totals, int* info);
 // lb.cu — packing lower bound
 int lb_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::vector<int2>& key_dims, uint64_t seed, int restarts,
            uint32_t* out_rows32, int* out_count);
@@ -1501,8 +1501,8 @@ int tss_lower_bound(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, co
 }
 
 int tss_lower_bound_lp(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_dims* defs, int32_t n_defs, const int32_t* weights,
-                       int32_t n_weights, int32_t max_pivots, int32_t* out_weights, int64_t* out_total, int64_t* out_max_load, int64_t* out_bound,
-                       int32_t* out_info) {
+                       int32_t n_weights, int32_t max_pivots, int64_t target, int32_t* out_weights, int64_t* out_total, int64_t* out_max_load,
+                       int64_t* out_bound, int32_t* out_info) {
     if (!e) return TSS_E_INVALID;
     if (out_bound) *out_bound = 0;
     if (!grid || !out_bound || w <= 0 || h <= 0 || (!defs && n_defs > 0) || n_weights < 0 || (n_weights > 0 && !weights))
@@ -1537,8 +1537,13 @@ int tss_lower_bound_lp(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h,
             if (grid[(size_t)y * w + x]) rows[y] |= 1u << x;
     int wts[1024], info[3];
     unsigned long long totals[3];
-    int rc = lp_run(e, rows, w, h, key_dims, key_costs, max_pivots, wts, totals, info);
+    int rc = lp_run(e, rows, w, h, key_dims, key_costs, max_pivots, target, wts, totals, info);
     if (rc) return rc;
+    if (target > 0 && !info[1] && !(totals[1] > 0 && totals[2] != ~0ull && (int64_t)totals[2] >= target)) {
+        // stopped early on the floating-point objective, and the integer certificate falls short of the target: run to optimality
+        rc = lp_run(e, rows, w, h, key_dims, key_costs, max_pivots, 0, wts, totals, info);
+        if (rc) return rc;
+    }
     if (out_weights)
         for (int y = 0; y < h; y++)
             for (int x = 0; x < w; x++) out_weights[(size_t)y * w + x] = wts[y * 32 + x];

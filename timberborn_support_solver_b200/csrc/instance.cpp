@@ -206,19 +206,32 @@ int tss_solve_instance(tss_engine* e, const tss_cnf* c, const tss_encoding* enc,
     if (rc == TSS_SAT) return tss_witness_for_cnf(e, c, enc, plats.data(), n, assignment);
     if (rc == TSS_UNKNOWN && count_only) {   // nothing found within the limit: can the fractional bound certify that nothing exists?
         std::lock_guard<std::mutex> lock(enc->d->bounds_mutex);
-        if (enc->d->lp_count_bound == -1) {
+        // (asked only for what this call needs — "does the bound reach limit + 1?" — so the simplex may stop early; computed again,
+        // to the new target, only if a later call asks about a limit the cached bound does not settle and the solve was not final)
+        if (enc->d->lp_count_bound == -1 || (enc->d->lp_count_bound >= 0 && !enc->d->lp_count_final && info->card_limit_1x1 >= enc->d->lp_count_bound)) {
             int64_t lb = 0;
-            enc->d->lp_count_bound = tss_lower_bound_lp(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), nullptr, 0, 0, nullptr, nullptr, nullptr, &lb, nullptr) == TSS_OK ? lb : -2;
+            int32_t lp_info[3] = {0, 0, 0};
+            const int ok = tss_lower_bound_lp(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), nullptr, 0, 0, (int64_t)info->card_limit_1x1 + 1,
+                                              nullptr, nullptr, nullptr, &lb, lp_info);
+            enc->d->lp_count_bound = ok == TSS_OK ? lb : -2;
+            enc->d->lp_count_final = lp_info[1] != 0;
+            tr.lap("solve: fractional bound");
         }
         if (enc->d->lp_count_bound >= 0 && info->card_limit_1x1 < enc->d->lp_count_bound) return TSS_UNSAT;
     }
     if (rc == TSS_UNKNOWN && weight_only) {   // the same question about the GUI's weight limit (crates/gui/src/app.rs:235-239)
         std::lock_guard<std::mutex> lock(enc->d->bounds_mutex);
         const std::vector<int32_t> wv(weights, weights + 3 * (size_t)info->n_weights);
-        if (enc->d->lp_weight_bound == -1 || enc->d->lp_weights != wv) {
+        if (enc->d->lp_weight_bound == -1 || enc->d->lp_weights != wv ||
+            (enc->d->lp_weight_bound >= 0 && !enc->d->lp_weight_final && info->weight_limit >= enc->d->lp_weight_bound)) {
             int64_t lb = 0;
+            int32_t lp_info[3] = {0, 0, 0};
             enc->d->lp_weights = wv;
-            enc->d->lp_weight_bound = tss_lower_bound_lp(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), weights, info->n_weights, 0, nullptr, nullptr, nullptr, &lb, nullptr) == TSS_OK ? lb : -2;
+            const int ok = tss_lower_bound_lp(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), weights, info->n_weights, 0, info->weight_limit + 1,
+                                              nullptr, nullptr, nullptr, &lb, lp_info);
+            enc->d->lp_weight_bound = ok == TSS_OK ? lb : -2;
+            enc->d->lp_weight_final = lp_info[1] != 0;
+            tr.lap("solve: fractional bound (weights)");
         }
         if (enc->d->lp_weight_bound >= 0 && info->weight_limit < enc->d->lp_weight_bound) return TSS_UNSAT;
     }

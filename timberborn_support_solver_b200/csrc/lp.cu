@@ -111,7 +111,7 @@ __device__ ArgD block_argmin(ArgD a, ArgD* red) {
 // Primal simplex on the condensed tableau, all-slack start (y = 0 is feasible).  basis[i] = label of row i, nonbasis[j] =
 // label of column j; labels 0..n-1 are tiles, n.. are slacks.  info[0] = pivots, info[1] = 1 if optimal.
 __global__ void __launch_bounds__(THREADS) lp_simplex_kernel(double* __restrict__ T, int m, int n, int* __restrict__ basis, int* __restrict__ nonbasis,
-                                                            int max_pivots, int* __restrict__ info) {
+                                                            int max_pivots, double stop_at, int* __restrict__ info) {
     __shared__ double prow[MAX_COLS + 1];
     __shared__ double devex[MAX_COLS + 1];   // Devex reference weights of the non-basic columns (see the cluster kernel)
     __shared__ ArgD red[32];
@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(THREADS) lp_simplex_kernel(double* __restrict_
         for (int j = tid; j < n; j += blockDim.x) devex[j] = j == q ? fmax(wq * inv * inv, 1.0) : fmax(devex[j], prow[j] * prow[j] * wq);
         if (tid == 0) { const int t = basis[pr]; basis[pr] = nonbasis[q]; nonbasis[q] = t; }
         __syncthreads();
+        if (stop_at > 0.0 && T[(size_t)m * ld + n] >= stop_at) { pivots++; break; }   // the bound the caller asked about is reached
     }
     if (tid == 0) { info[0] = pivots; info[1] = optimal; }
 }
@@ -176,7 +177,7 @@ constexpr int CLUSTER = 8;
 constexpr int CL_THREADS = 512;
 
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(CL_THREADS)
-lp_simplex_cluster_kernel(const double* __restrict__ T, int m, int n, const int* __restrict__ col_site, int max_pivots, int* __restrict__ info,
+lp_simplex_cluster_kernel(const double* __restrict__ T, int m, int n, const int* __restrict__ col_site, int max_pivots, double stop_at, int* __restrict__ info,
                           int* __restrict__ weights /* [1024] zeroed */, double scale) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank(), tid = threadIdx.x, ld = n + 1;
@@ -240,6 +241,7 @@ lp_simplex_cluster_kernel(const double* __restrict__ T, int m, int n, const int*
             devex[j] = j == q ? fmax(wq * inv * inv, 1.0) : fmax(devex[j], prow[j] * prow[j] * wq);
         if (tid == 0) { const int t = basis[pr]; basis[pr] = nonbasis[q]; nonbasis[q] = t; }
         __syncthreads();
+        if (stop_at > 0.0 && obj[n] >= stop_at) { pivots++; break; }   // the bound the caller asked about is reached (obj is replicated: every CTA leaves here)
     }
     for (int li = tid; li < my_rows; li += blockDim.x) {    // y -> integer weights: floor(y * SCALE) for my basic tiles
         const int label = basis[row0 + li];
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(128) lp_certify_kernel(const uint32_t* __restr
 // key_costs: cost of a platform per key.  totals[0] = sum of the weights, totals[1] = largest placement load, totals[2] = the bound
 // (min over placements of ceil(total * cost / load); ~0 if no placement carries load), info[0] = pivots, info[1] = optimal, info[2] = constraints.
 int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::vector<int2>& key_dims, const std::vector<int>& key_costs, int max_pivots,
-           int* out_weights, unsigned long long* totals, int* info) {
+           long long target, int* out_weights, unsigned long long* totals, int* info) {
     if ((int)key_dims.size() > lp::MAX_KEYS) return e->fail(TSS_E_UNSUPPORTED, "tss_lower_bound_lp: more than %d dims keys", lp::MAX_KEYS);
     lp::Keys keys;
     keys.n = (int)key_dims.size();
@@ -352,15 +354,20 @@ int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::
     // Dantzig pricing on this LP, not degenerate stalling)
     lp::lp_init_kernel<<<init_blocks, 256, 0, e->stream>>>(reach, cons_dev, m, col_dev, n, T, 1e-7, keys);
     const int pivots_cap = max_pivots > 0 ? max_pivots : 8 * (m + n);
+    // target > 0: the caller only asks whether the bound reaches `target`.  Every iterate is feasible and the objective only grows,
+    // so the simplex may stop once it exceeds target - 1 by more than the certificate loses to rounding (floor(y * scale) per
+    // tile: < n / scale in total; right-hand sides perturbed by 1e-7): the loop's question "nothing within target - 1?" is usually
+    // settled after 60-80 % of the pivots (ex2 / README terrain with 1x1 supports: 13.0 is passed long before the optimum 13.2 / 13.13)
+    const double stop_at = target > 0 ? (double)(target - 1) + 4.0 * (double)n / scale + 2e-3 : 0.0;
     const int rows_per = (m + lp::CLUSTER - 1) / lp::CLUSTER, ld = n + 1;
     const size_t cl_smem = sizeof(double) * ((size_t)rows_per * ld + 3 * (size_t)ld + rows_per) + sizeof(lp::ArgD) * lp::CLUSTER + sizeof(int) * ((size_t)m + n);
     const char* force = getenv("TSS_LP_SINGLE_CTA");       // (A/B switch for profiles/lb_stream.py)
     if (cl_smem <= 200 * 1024 && !(force && force[0] == '1')) {
         // the tableau fits the shared memory of one 8-CTA cluster: rows resident in shared memory, exchange over DSMEM
         TSS_CUDA(e, cudaFuncSetAttribute(lp::lp_simplex_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_smem));
-        lp::lp_simplex_cluster_kernel<<<lp::CLUSTER, lp::CL_THREADS, cl_smem, e->stream>>>(T, m, n, col_dev, pivots_cap, info_dev, weights, scale);
+        lp::lp_simplex_cluster_kernel<<<lp::CLUSTER, lp::CL_THREADS, cl_smem, e->stream>>>(T, m, n, col_dev, pivots_cap, stop_at, info_dev, weights, scale);
     } else {
-        lp::lp_simplex_kernel<<<1, lp::THREADS, 0, e->stream>>>(T, m, n, basis, nonbasis, pivots_cap, info_dev);
+        lp::lp_simplex_kernel<<<1, lp::THREADS, 0, e->stream>>>(T, m, n, basis, nonbasis, pivots_cap, stop_at, info_dev);
         lp::lp_weights_kernel<<<(m + 255) / 256, 256, 0, e->stream>>>(T, m, n, basis, col_dev, weights, scale);
     }
     lp::lp_total_kernel<<<1, 32, 0, e->stream>>>(weights, totals_dev);
