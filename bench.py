@@ -486,6 +486,32 @@ def side_c4(eng, torch, dist, world, rank, phases, phase_steps):
             "ms": ms, "flips_per_s": float(acc[0].item()) / (ms * 1e-3), "neighbour_scores_per_s": float(acc[1].item()) / (ms * 1e-3), "chains_per_gpu": n_chains}
 
 
+def repl_loop_cpp_driver(name_defs):
+    """The same loop through the C++ driver over the C ABI (timberborn_support_solver_b200/tss_repl = tools/tss_repl.cpp: the Rust
+    shim's call sequence, tss_cnf_upload -> tss_instance_find -> tss_solve_instance, no exact solver attached): one whole
+    `load; solve` repeated 21 times in one process, warm median wall ms (engine creation = CUDA context start-up excluded)."""
+    import re
+    import subprocess
+    import tempfile
+    import timberborn_support_solver_b200 as T
+    exe = os.path.join(os.path.dirname(T.__file__), "tss_repl")
+    if not os.path.exists(exe):
+        return {"unavailable": "tss_repl not built (python -m timberborn_support_solver_b200.build)"}
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, label in name_defs:
+            path = os.path.join(tmp, f"{name}.toml")
+            with open(path, "w") as f:
+                f.write(T.WorldGrid(named_grid(fx, name)).to_toml())
+            r = subprocess.run([exe, path, "--platforms", "default" if label == "default-8" else "1x1", "--seed", "3", "--quiet", "--repeat", "21"],
+                               capture_output=True, text=True, timeout=300)
+            m = re.search(r'# best=(\d+) lower_bound=(-?\d+) verdict="([^"]*)" gpu_solves=(\d+) exact_solves=(\d+) ms=([\d.]+) setup_ms=([\d.]+) repeats=\d+ warm_ms=([\d.]+)', r.stdout)
+            out[f"{name} {label}"] = ({"warm_ms": float(m.group(8)), "cold_ms": float(m.group(6)), "optimum": int(m.group(1)), "verdict": m.group(3),
+                                       "gpu_solves": int(m.group(4)), "exact_solves": int(m.group(5))} if r.returncode == 0 and m else {"error": (r.stderr or r.stdout)[-200:]})
+    return out
+
+
 def oracle_exact(cnf):
     """The exact solver of the REPL loop (rustsat-glucose in the reference; here the oracle's CDCL stand-in, as on the CPU arm)."""
     import ctypes as C
@@ -771,10 +797,11 @@ def main():
                               "literals": int(len(cnf.lits)), "assignments": len(a), "propagation_rounds": rounds,
                               "input": "SLS witness completed by unit propagation x 131072, every 64th with one support removed"}
         # ---------------- the REPL flow end to end (BASELINE.json configs[0] and [2]): `load test/exN.toml; solve`
-        line["repl_loop"] = {"gpu_seeded": repl_loop_gpu(eng, REPL_INSTANCES), "cpu": repl_loop_cpu(REPL_INSTANCES),
+        line["repl_loop"] = {"gpu_seeded": repl_loop_gpu(eng, REPL_INSTANCES), "cpp_driver": repl_loop_cpp_driver(REPL_INSTANCES), "cpu": repl_loop_cpu(REPL_INSTANCES),
                              "note": "crates/repl/src/main.rs:280-366 end to end = time to the PROVEN optimum, wall ms: the loop with the GPU engine answering the SAT iterations, its "
                                      "certified lower bounds closing the gap where they can (exact_solves = 0) and the exact solver (oracle CDCL standing in for Glucose, as on the CPU side) "
-                                     "called only for what is left, against the same loop on the CPU alone (1 solver thread)"}
+                                     "called only for what is left, against the same loop on the CPU alone (1 solver thread); cpp_driver = the same loop in C++ over the C ABI (the Rust shim's call "
+                                     "sequence; the certified bounds answer UNSAT inside tss_solve_instance), warm median of 21 solves in one process"}
         # ---------------- single-solve latencies of the other named instances through the C ABI
         fx = json.load(open(os.path.join(ROOT, "tests", "golden", "fixtures.json")))
         ex1_rows = fx["ex1"]["grid"]   # test/ex1.toml

@@ -435,6 +435,60 @@ static int eval_platforms_dev(tss_engine* e, const uint8_t* grid, int w, int h, 
     return TSS_OK;
 }
 
+// ONE layout, everything a caller wants back, one synchronisation: inputs staged in pinned memory (slot 4), results copied
+// asynchronously into pinned memory (slot 5).  The generic path above costs a blocking cudaMemcpy per result array — 45-65 us per
+// call for `validate` and the witness's support layers, which the bound-tightening loop pays every iteration (TSS_TRACE).
+struct OneLayout { const int32_t* res; const uint32_t* rows; const uint32_t* layers; const uint8_t* flags; };
+static int eval_one_layout(tss_engine* e, const uint8_t* grid, int w, int h, const tss_platform* plats, int n_plats, bool want_rows, bool want_flags,
+                           bool want_layers, OneLayout& out) {
+    const int wpr = (w + 31) / 32;
+    const size_t nw = (size_t)h * wpr, np = (size_t)n_plats;
+    uint32_t* g = (uint32_t*)e->dev(0, nw * 4);
+    int4* p = (int4*)e->dev(1, sizeof(int4) * (np ? np : 1));
+    uint32_t* off = (uint32_t*)e->dev(2, sizeof(uint32_t) * 2);
+    int32_t* res = (int32_t*)e->dev(3, sizeof(int32_t) * 4);
+    uint32_t* rows = want_rows ? (uint32_t*)e->dev(4, nw * 4) : nullptr;
+    uint8_t* flags = want_flags ? (uint8_t*)e->dev(5, np ? np : 1) : nullptr;
+    uint32_t* layers = want_layers ? (uint32_t*)e->dev(6, nw * 16) : nullptr;
+    const size_t in_bytes = sizeof(int4) * np + 4 * nw + 8, out_bytes = 16 + 4 * nw + 16 * nw + np + 16;
+    char* in = (char*)e->pin(4, in_bytes);
+    char* ho = (char*)e->pin(5, out_bytes);
+    if (!g || !p || !off || !res || (want_rows && !rows) || (want_flags && !flags) || (want_layers && !layers) || !in || !ho) return TSS_E_CUDA;
+    int4* in_p = (int4*)in;
+    uint32_t* in_g = (uint32_t*)(in + sizeof(int4) * np);
+    uint32_t* in_off = in_g + nw;
+    for (size_t i = 0; i < np; i++) {
+        const Dims d = platform_dims(plats[i]);
+        in_p[i] = make_int4(plats[i].x, plats[i].y, d.w, d.h);
+    }
+    std::memset(in_g, 0, 4 * nw);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            if (grid[(size_t)y * w + x]) in_g[(size_t)y * wpr + (x >> 5)] |= 1u << (x & 31);
+    in_off[0] = 0; in_off[1] = (uint32_t)np;
+    if (np) TSS_CUDA(e, cudaMemcpyAsync(p, in_p, sizeof(int4) * np, cudaMemcpyHostToDevice, e->stream));
+    TSS_CUDA(e, cudaMemcpyAsync(g, in_g, 4 * nw, cudaMemcpyHostToDevice, e->stream));
+    TSS_CUDA(e, cudaMemcpyAsync(off, in_off, 8, cudaMemcpyHostToDevice, e->stream));
+    TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    int rc = launch_eval_platforms(e, g, w, h, p, off, 1, res, rows, flags, layers);
+    if (rc) return rc;
+    TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    int32_t* ho_res = (int32_t*)ho;
+    uint32_t* ho_rows = (uint32_t*)(ho + 16);
+    uint32_t* ho_layers = ho_rows + nw;
+    uint8_t* ho_flags = (uint8_t*)(ho_layers + 4 * nw);
+    TSS_CUDA(e, cudaMemcpyAsync(ho_res, res, 16, cudaMemcpyDeviceToHost, e->stream));
+    if (want_rows) TSS_CUDA(e, cudaMemcpyAsync(ho_rows, rows, 4 * nw, cudaMemcpyDeviceToHost, e->stream));
+    if (want_layers) TSS_CUDA(e, cudaMemcpyAsync(ho_layers, layers, 16 * nw, cudaMemcpyDeviceToHost, e->stream));
+    if (want_flags && np) TSS_CUDA(e, cudaMemcpyAsync(ho_flags, flags, np, cudaMemcpyDeviceToHost, e->stream));
+    TSS_CUDA(e, cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->stats.device_ms = ms;
+    out = OneLayout{ho_res, ho_rows, ho_layers, ho_flags};
+    return TSS_OK;
+}
+
 int tss_eval_platforms(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const tss_platform* plats,
                        const uint32_t* offsets, int64_t n, int32_t* out) {
     if (!e) return TSS_E_INVALID;
@@ -452,15 +506,13 @@ int tss_validate(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, const
     if (!e) return TSS_E_INVALID;
     if (!grid || w <= 0 || h <= 0 || n < 0 || (!plats && n > 0)) return e->fail(TSS_E_INVALID, "tss_validate: bad arguments");
     TSS_CUDA(e, cudaSetDevice(e->device));
-    uint32_t offsets[2] = {0, (uint32_t)n};
-    int rc = eval_platforms_dev(e, grid, w, h, plats, offsets, 1, true, true, false);
+    OneLayout r;
+    int rc = eval_one_layout(e, grid, w, h, plats, n, true, true, false, r);
     if (rc) return rc;
     const int wpr = (w + 31) / 32;
-    std::vector<uint32_t> rows((size_t)h * wpr);
-    int32_t res[4];
-    TSS_CUDA(e, cudaMemcpy(res, e->scratch[3].ptr, sizeof res, cudaMemcpyDeviceToHost));
-    TSS_CUDA(e, cudaMemcpy(rows.data(), e->scratch[4].ptr, rows.size() * 4, cudaMemcpyDeviceToHost));
-    if (out_flags && n > 0) TSS_CUDA(e, cudaMemcpy(out_flags, e->scratch[5].ptr, (size_t)n, cudaMemcpyDeviceToHost));
+    const uint32_t* rows = r.rows;
+    const int32_t* res = r.res;
+    if (out_flags && n > 0) std::memcpy(out_flags, r.flags, (size_t)n);
     if (out_unsupported)
         for (int y = 0; y < h; y++)
             for (int x = 0; x < w; x++) out_unsupported[(size_t)y * w + x] = (rows[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
@@ -472,11 +524,10 @@ int tss_layout_to_assignment_impl(tss_engine* e, const Encoding& enc, const uint
                                   uint8_t* assignment) {
     TSS_CUDA(e, cudaSetDevice(e->device));
     const int w = enc.w, h = enc.h, wpr = (w + 31) / 32, K = enc.K();
-    uint32_t offsets[2] = {0, (uint32_t)n_plats};
-    int rc = eval_platforms_dev(e, grid, w, h, plats, offsets, 1, false, false, true);
+    OneLayout r;
+    int rc = eval_one_layout(e, grid, w, h, plats, n_plats, false, false, true, r);
     if (rc) return rc;
-    std::vector<uint32_t> layers((size_t)4 * h * wpr);
-    TSS_CUDA(e, cudaMemcpy(layers.data(), e->scratch[6].ptr, layers.size() * 4, cudaMemcpyDeviceToHost));
+    const uint32_t* layers = r.layers;
     for (int v = 0; v <= enc.base.n_vars; v++) assignment[v] = v == 0 ? 2 : 0;
     for (int i = 0; i < n_plats; i++) {  // every dims key contained in the platform's effective dims (DAG implications)
         if (plats[i].x < 0 || plats[i].y < 0 || plats[i].x >= w || plats[i].y >= h) continue;
@@ -490,7 +541,7 @@ int tss_layout_to_assignment_impl(tss_engine* e, const Encoding& enc, const uint
             int var = enc.terr_var[(size_t)t * 4 + l];
             if (!var) continue;
             int x = t % w, y = t / w;
-            const uint32_t* plane = layers.data() + (size_t)(3 - l) * h * wpr;  // T3 = directly supported ... T0 = after 3 rounds
+            const uint32_t* plane = layers + (size_t)(3 - l) * h * wpr;  // T3 = directly supported ... T0 = after 3 rounds
             assignment[var] = (plane[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
         }
     return TSS_OK;

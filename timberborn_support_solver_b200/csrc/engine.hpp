@@ -52,7 +52,7 @@ struct tss_engine {
     struct tss_search* cached_multi = nullptr;   // workspace of the placement search (platform sets beyond {1x1}) of a one-shot solve
     struct tss::Comm* comm = nullptr;            // NCCL communicator of a multi-GPU portfolio (comm.cu), or null
     TssBuffer scratch[8];                    // device scratch slots
-    TssBuffer staging[4];                    // pinned host staging slots
+    TssBuffer staging[6];                    // pinned host staging slots
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
