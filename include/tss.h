@@ -337,6 +337,13 @@ int tss_cnf_num_vars(const tss_cnf* c);
  * limits added (totalizer / PB auxiliaries) by unit propagation, then every clause checked (kernel (c)).  assignment:
  * u8[n_vars(c) + 1].  TSS_SAT: it is a model; TSS_UNKNOWN: it is not (e.g. the layout exceeds a limit). */
 int tss_witness_for_cnf(tss_engine* e, const tss_cnf* c, const tss_encoding* enc, const tss_platform* plats, int32_t n, uint8_t* assignment);
+/* The completion step on its own, for ONE partial assignment u8[n_vars + 1] (0 / 1 / 2 = False / True / unassigned), in place:
+ * unit propagation to the fixpoint, open variables False, every clause checked.  One fused launch when the variables fit a
+ * CTA's shared memory (csrc/cnf.cu cnf_complete_kernel; in-place propagation — same fixpoint and conflict verdict as the
+ * synchronous rounds of tss_cnf_propagate), the batch kernels otherwise.  *out_conflict = a clause left without a true or open
+ * literal by the propagation, or -1 (then the assignment is complete and *out_n_falsified counts the clauses it falsifies);
+ * after a conflict the assignment holds the propagation's state and *out_n_falsified is 0. */
+int tss_cnf_complete(tss_engine* e, const tss_cnf* c, uint8_t* assignment, int32_t* out_conflict, int32_t* out_n_falsified);
 /* Solve::solve as the GPU answers it: ONE SAT-like search within the instance's limit (platform count, or total weight when
  * the instance carries a weight limit) that gives up after `give_up_steps` SLS steps per chain (<= 0: the engine default),
  * then tss_witness_for_cnf.  TSS_SAT with a verified model in `assignment`; TSS_UNSAT when the instance's only limit (platform

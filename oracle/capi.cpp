@@ -215,9 +215,7 @@ int tsso_cnf_count_falsified(void* c, const uint8_t* assignment, int* first) {
 // keeps both marks, counts as assigned, and reads as True ("True wins"), so the clause that wanted False is reported
 // as the conflict.  rounds = rounds executed including the last one that changed nothing.  conflict = lowest index of a
 // clause whose literals are all false at the fixpoint, or -1.  assignment: u8[n_vars+1] 0 F / 1 T / 2 unassigned, in/out.
-int tsso_cnf_propagate(void* c, uint8_t* assignment, int* conflict, int* rounds) {
-    auto& inst = ((CnfHandle*)c)->inst;
-    const int nv = inst.n_vars;
+static int propagate_clauses(const std::vector<Clause>& clauses, int nv, uint8_t* assignment, int* conflict, int* rounds) {
     std::vector<uint8_t> pos((size_t)nv + 1, 0), neg((size_t)nv + 1, 0);
     for (int v = 1; v <= nv; v++) { pos[v] = assignment[v] == 1; neg[v] = assignment[v] == 0; }
     int r = 0;
@@ -225,7 +223,7 @@ int tsso_cnf_propagate(void* c, uint8_t* assignment, int* conflict, int* rounds)
         changed = false;
         r++;
         std::vector<uint8_t> npos = pos, nneg = neg;
-        for (auto& cl : inst.clauses) {
+        for (auto& cl : clauses) {
             bool sat = false;
             int n_open = 0, open_lit = 0;
             for (int l : cl) {
@@ -242,14 +240,24 @@ int tsso_cnf_propagate(void* c, uint8_t* assignment, int* conflict, int* rounds)
     }
     for (int v = 1; v <= nv; v++) assignment[v] = pos[v] ? 1 : (neg[v] ? 0 : 2);
     int first = -1;
-    for (size_t i = 0; i < inst.clauses.size() && first < 0; i++) {
+    for (size_t i = 0; i < clauses.size() && first < 0; i++) {
         bool all_false = true;
-        for (int l : inst.clauses[i]) { const uint8_t a = assignment[std::abs(l)]; if (a == 2 || (l > 0 ? a == 1 : a == 0)) { all_false = false; break; } }
+        for (int l : clauses[i]) { const uint8_t a = assignment[std::abs(l)]; if (a == 2 || (l > 0 ? a == 1 : a == 0)) { all_false = false; break; } }
         if (all_false) first = (int)i;
     }
     if (conflict) *conflict = first;
     if (rounds) *rounds = r;
     return 0;
+}
+int tsso_cnf_propagate(void* c, uint8_t* assignment, int* conflict, int* rounds) {
+    auto& inst = ((CnfHandle*)c)->inst;
+    return propagate_clauses(inst.clauses, inst.n_vars, assignment, conflict, rounds);
+}
+// the same on a caller-provided CSR CNF (random clause sets in tests/test_gpu.py: kernel (c) on inputs no encoder produces)
+int tsso_propagate_csr(const int* lits, const unsigned* offsets, int n_clauses, int n_vars, uint8_t* assignment, int* conflict, int* rounds) {
+    std::vector<Clause> cls((size_t)n_clauses);
+    for (int i = 0; i < n_clauses; i++) cls[i].assign(lits + offsets[i], lits + offsets[i + 1]);
+    return propagate_clauses(cls, n_vars, assignment, conflict, rounds);
 }
 
 // ---- layout

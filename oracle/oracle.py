@@ -126,6 +126,16 @@ def dag_edges(defs):
 
 
 # --------------------------------------------------------------------------- CNF
+def propagate_csr(lits, offsets, n_vars, assignment):
+    """Unit propagation (synchronous rounds, oracle/capi.cpp) on a caller-provided CSR CNF -> (assignment, conflict clause or -1, rounds)."""
+    lits = np.ascontiguousarray(lits, np.int32)
+    offsets = np.ascontiguousarray(offsets, np.uint32)
+    a = np.ascontiguousarray(assignment, dtype=np.uint8).copy()
+    conflict, rounds = C.c_int(), C.c_int()
+    lib().tsso_propagate_csr(_p(lits if len(lits) else np.zeros(1, np.int32)), _p(offsets, C.c_uint32), len(offsets) - 1, n_vars, _p(a, C.c_uint8), C.byref(conflict), C.byref(rounds))
+    return a, conflict.value, rounds.value
+
+
 class Cnf:
     def __init__(self, handle):
         self._h = C.c_void_p(handle)

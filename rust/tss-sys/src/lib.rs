@@ -142,6 +142,7 @@ unsafe extern "C" {
         weights: *mut i32, weights_cap: i32,
     ) -> c_int;
     pub fn tss_witness_for_cnf(e: *mut tss_engine, c: *const tss_cnf, enc: *const tss_encoding, plats: *const tss_platform, n: i32, assignment: *mut u8) -> c_int;
+    pub fn tss_cnf_complete(e: *mut tss_engine, c: *const tss_cnf, assignment: *mut u8, out_conflict: *mut i32, out_n_falsified: *mut i32) -> c_int;
     pub fn tss_engine_certified_unsat(e: *mut tss_engine, enabled: c_int) -> c_int;
     pub fn tss_solve_instance(
         e: *mut tss_engine, c: *const tss_cnf, enc: *const tss_encoding, info: *const tss_instance_info, weights: *const i32, seed: u64,

@@ -278,6 +278,72 @@ def test_cnf_propagate_on_optimum_witnesses(eng, fixtures, readme):
     assert n_clean == len(cases) >= 10
 
 
+def _random_cnf(rng, n_vars, n_clauses, chain, hidden):
+    """Random clause set with unit-propagation structure: `chain` implication chains x -> y -> z ..., random clauses of 1..9
+    literals, a few long ones.  With `hidden` (a full assignment) every clause is made true under it — propagation from any part
+    of it can then never conflict; without, literals are random and an empty clause may appear."""
+    clauses = []
+    order = rng.permutation(n_vars) + 1
+    for i in range(chain):
+        a, b = int(order[i % n_vars]), int(order[(i + 1) % n_vars])
+        clauses.append((-a if rng.random() < 0.8 else a, b if rng.random() < 0.8 else -b))
+    for _ in range(n_clauses):
+        k = int(rng.choice([1, 2, 2, 3, 3, 3, 4, 5, 6, 9]))
+        vs = rng.choice(n_vars, size=min(k, n_vars), replace=False) + 1
+        clauses.append(tuple(int(v) if rng.random() < 0.5 else -int(v) for v in vs))
+    if hidden is not None:
+        fixed = []
+        for c in clauses:
+            if not any(hidden[abs(l)] == (1 if l > 0 else 0) for l in c):
+                j = int(rng.integers(len(c)))
+                c = c[:j] + (-c[j],) + c[j + 1:]
+            fixed.append(c)
+        clauses = fixed
+    elif rng.random() < 0.2:
+        clauses.append(())
+    perm = rng.permutation(len(clauses))
+    clauses = [clauses[i] for i in perm]
+    lits = np.array([l for c in clauses for l in c], np.int32)
+    offs = np.zeros(len(clauses) + 1, np.uint32)
+    offs[1:] = np.cumsum([len(c) for c in clauses])
+    return clauses, lits, offs
+
+
+@pytest.mark.parametrize("n_vars,n_clauses,cases", [(12, 20, 60), (300, 500, 40), (5000, 12000, 12), (40000, 60000, 4), (230000, 100000, 2)])
+def test_cnf_complete_random_clause_sets_match_oracle(eng, n_vars, n_clauses, cases):
+    """tss_cnf_complete (one fused launch, in-place propagation; 16-bit resident clauses below 32 768 variables, the int4 copy
+    above, the batch kernels beyond one CTA's shared memory) on clause sets no encoder produces — chains, long and empty clauses,
+    conflicts — against the oracle's synchronous unit propagation: same conflict verdict; without a conflict the same completed
+    assignment, variable for variable, and the same number of falsified clauses."""
+    rng = np.random.default_rng(n_vars)
+    n_conflict = n_clean = 0
+    for case in range(cases):
+        hidden = rng.integers(0, 2, n_vars + 1).astype(np.uint8) if case % 2 == 0 else None
+        clauses, lits, offs = _random_cnf(rng, n_vars, n_clauses, chain=n_vars // 2, hidden=hidden)
+        a = np.full(n_vars + 1, 2, np.uint8)
+        decided = rng.random(n_vars + 1) < rng.choice([0.0, 0.05, 0.3, 0.6])
+        a[decided] = hidden[decided] if hidden is not None else rng.integers(0, 2, int(decided.sum()))
+        a[0] = 2
+        want, wc, _ = O.propagate_csr(lits, offs, n_vars, a)
+        dev = eng.upload_cnf(T.Cnf(n_vars, lits, offs))
+        got, conflict, nf = dev.complete(a)
+        assert (conflict >= 0) == (wc >= 0), (case, conflict, wc)
+        if wc >= 0:
+            n_conflict += 1
+            cl = clauses[conflict]                       # the reported clause has no true and no open literal in the returned state
+            assert all(got[abs(l)] == (0 if l > 0 else 1) for l in cl), case
+            continue
+        n_clean += 1
+        want[want == 2] = 0
+        assert np.array_equal(got[1:], want[1:]), case
+        bad = sum(1 for c in clauses if not any(want[abs(l)] == (1 if l > 0 else 0) for l in c)) if n_vars <= 5000 else None
+        if bad is not None:
+            assert nf == bad, (case, nf, bad)
+        else:                                            # large sets: the batch check kernel is the yardstick (itself tested against the oracle above)
+            assert nf == dev.check(want[None, :])[0][0], case
+    assert n_clean >= cases // 2 and n_conflict > 0
+
+
 # =============================================================================== kernel (b): batched SLS
 KNOWN_OPTIMA = [("ex1", 3), ("ex3", 4), ("ex2", 14)]   # proven by the oracle's CDCL loop (tests/test_oracle.py) / SURVEY.md §6
 

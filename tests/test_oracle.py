@@ -425,3 +425,23 @@ def test_placement_model_layouts_validate_and_reach_repl_optima(fixtures):
                 plats.append((int(code) & 31, (int(code) >> 5) & 31, min(w, h), max(w, h), int(w > h)))   # canonical def + rotated flag
             v = O.validate(grid, plats)
             assert v.is_valid and len(plats) == r["best"][c] >= optimum
+
+
+def test_propagate_csr_equals_the_handle_based_propagation(fixtures):
+    """tsso_propagate_csr (caller-provided clauses, used for the random clause sets of the GPU tests) is the same code as
+    Cnf.propagate: identical result on an encoder CNF."""
+    g = fixtures["ex1"]
+    enc = O.Encoding(O.PLATFORMS_1X1, g)
+    cnf = enc.with_limits({(1, 1): 3})
+    a = np.full(cnf.n_vars + 1, 2, np.uint8)
+    pv = [v for v in range(1, enc.cnf().n_vars + 1)][:5]
+    a[pv] = 0
+    w1, c1, r1 = cnf.propagate(a)
+    w2, c2, r2 = O.propagate_csr(cnf.lits, cnf.offsets, cnf.n_vars, a)
+    assert np.array_equal(w1, w2) and c1 == c2 and r1 == r2
+    # and a hand-made chain: x1; x1 -> x2; x2 -> x3; (-x3 | -x1).  Round 1: x1.  Round 2: x2, and the last clause forces x3 False.
+    # Round 3: nothing new; x2 -> x3 has no true and no open literal left: the conflict
+    lits = np.array([1, -1, 2, -2, 3, -3, -1], np.int32)
+    offs = np.array([0, 1, 3, 5, 7], np.uint32)
+    w, c, r = O.propagate_csr(lits, offs, 3, np.full(4, 2, np.uint8))
+    assert list(w[1:]) == [1, 1, 0] and c == 2 and r == 3

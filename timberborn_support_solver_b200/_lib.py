@@ -112,6 +112,7 @@ SIGNATURES = {
     "tss_cnf_num_vars": (C.c_int, [_vp]),
     "tss_witness_for_cnf": (C.c_int, [_vp, _vp, _vp, _P(Platform), _i32, _u8p]),
     "tss_solve_instance": (C.c_int, [_vp, _vp, _vp, _P(InstanceInfo), _i32p, _u64, _i64, _u8p]),
+    "tss_cnf_complete": (C.c_int, [_vp, _vp, _u8p, _i32p, _i32p]),
     "tss_engine_certified_unsat": (C.c_int, [_vp, C.c_int]),
     "tss_measure_peaks": (C.c_int, [_vp, _P(C.c_double), _i32]),
 }

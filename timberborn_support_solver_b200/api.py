@@ -415,6 +415,15 @@ class DeviceCnf:
         e._check(e.lib.tss_cnf_propagate(e._h, self._h, _ptr(a, C.c_uint8), len(a), _ptr(conflict, C.c_int32), C.byref(rounds)))
         return a, conflict, rounds.value
 
+    def complete(self, assignment):
+        """tss_cnf_complete: ONE partial assignment -> (completed assignment uint8[n_vars + 1], conflict clause or -1, clauses falsified):
+        unit propagation, open variables False, clause check — one fused launch when the variables fit a CTA's shared memory."""
+        a = _u8(assignment).reshape(self.cnf.n_vars + 1).copy()
+        conflict, nf = C.c_int32(-1), C.c_int32(0)
+        e = self.engine
+        e._check(e.lib.tss_cnf_complete(e._h, self._h, _ptr(a, C.c_uint8), C.byref(conflict), C.byref(nf)))
+        return a, conflict.value, nf.value
+
     def witness(self, encoding: "Encoding", layout: "PlatformLayout"):
         """tss_witness_for_cnf: the layout completed into a model of these clauses (platform + terrain-layer variables from the
         layout, auxiliaries by unit propagation, open variables False, every clause checked — one fused launch, csrc/cnf.cu

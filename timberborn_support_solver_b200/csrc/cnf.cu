@@ -402,6 +402,21 @@ int tss_cnf_upload(tss_engine* e, const int32_t* lits, const uint32_t* offsets, 
     return TSS_OK;
 }
 
+int tss_cnf_complete(tss_engine* e, const tss_cnf* c, uint8_t* assignment, int32_t* out_conflict, int32_t* out_n_falsified) {
+    if (!e) return TSS_E_INVALID;
+    if (!c || !assignment || !out_conflict || !out_n_falsified) return e->fail(TSS_E_INVALID, "tss_cnf_complete: bad arguments");
+    *out_conflict = -1;
+    *out_n_falsified = 0;
+    int rc = cnf_complete_single(e, c, assignment, out_conflict, out_n_falsified);
+    if (rc != TSS_E_UNSUPPORTED) return rc;
+    // more variables than one CTA's shared memory holds: the batch kernels, round by round
+    rc = tss_cnf_propagate(e, c, assignment, 1, out_conflict, nullptr);
+    if (rc < 0 || *out_conflict >= 0) return rc;
+    for (int v = 1; v <= c->n_vars; v++)
+        if (assignment[v] == 2) assignment[v] = 0;
+    return tss_cnf_check(e, c, assignment, 1, out_n_falsified, nullptr);
+}
+
 int tss_cnf_num_vars(const tss_cnf* c) { return c ? c->n_vars : TSS_E_INVALID; }
 
 void tss_cnf_destroy(tss_cnf* c) {

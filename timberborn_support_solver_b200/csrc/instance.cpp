@@ -135,21 +135,10 @@ int tss_witness_for_cnf(tss_engine* e, const tss_cnf* c, const tss_encoding* enc
     int32_t conflict = -1, n_falsified = 0;
     // ... and is implied: unit propagation assigns it, open variables become False, and the model is checked against every
     // clause the exact solver received (kernel (c)) — in ONE launch when the variables fit a CTA's shared memory
-    rc = tss::cnf_complete_single(e, c, assignment, &conflict, &n_falsified);
-    if (rc == TSS_OK) {
-        tr.lap("witness: cnf_complete");
-        return conflict < 0 && n_falsified == 0 ? TSS_SAT : TSS_UNKNOWN;   // conflict: e.g. more platforms than the bound allows
-    }
-    if (rc != TSS_E_UNSUPPORTED) return rc;
-    rc = tss_cnf_propagate(e, c, assignment, 1, &conflict, nullptr);
+    rc = tss_cnf_complete(e, c, assignment, &conflict, &n_falsified);
     if (rc < 0) return rc;
-    tr.lap("witness: cnf_propagate");
-    if (conflict >= 0) return TSS_UNKNOWN;
-    for (int v = 1; v <= nv; v++)
-        if (assignment[v] == 2) assignment[v] = 0;
-    rc = tss_cnf_check(e, c, assignment, 1, &n_falsified, nullptr);
-    if (rc < 0) return rc;
-    tr.lap("witness: cnf_check");
+    tr.lap("witness: cnf_complete");
+    if (conflict >= 0) return TSS_UNKNOWN;   // e.g. more platforms than the bound allows
     return n_falsified == 0 ? TSS_SAT : TSS_UNKNOWN;
 }
 
