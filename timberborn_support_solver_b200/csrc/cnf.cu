@@ -20,12 +20,11 @@
 
 struct tss_cnf {
     tss_engine* engine = nullptr;
-    void* blob = nullptr;          // ONE stream-ordered allocation from the engine's pool: lits | offsets | pad4 | short16 | long_ids | n_long | active
+    void* blob = nullptr;          // ONE stream-ordered allocation from the engine's pool: lits | offsets | pad4 | long_ids | n_long | active
     int32_t* lits = nullptr;
     uint32_t* offsets = nullptr;
     int4* pad4 = nullptr;          // [n_clauses] clauses of 1..4 literals padded with 0 (one 16-byte load per clause); x == 0: see long_ids
-    short4* short16 = nullptr;     // the same in 16-bit literals when n_vars < 32768: what cnf_complete_kernel keeps resident in shared memory
-    int* active = nullptr;         // [n_clauses] scratch of cnf_complete_kernel (the clauses its first sweep found unsatisfied)
+    int* active = nullptr;         // [n_clauses] scratch of cnf_complete_kernel: active clauses beyond what its shared memory holds
     int* long_ids = nullptr;       // clauses with more than 4 literals (and empty ones), in no particular order; long_ids[n_clauses] = their number
     int n_clauses = 0, n_vars = 0;
     int64_t n_lits = 0;
@@ -174,7 +173,7 @@ constexpr size_t COMPLETE_MAX_BYTES = 200 * 1024;   // variables + 1 that fit on
 // independent, coalesced 16-byte load per clause instead of the dependent chain offsets -> literals (the first version walked
 // the CSR: 33 us per sweep over the 25 K clauses of test/ex2.toml with the default-8 set, latency of one CTA's dependent L2 reads)
 __global__ void cnf_short_kernel(const int32_t* __restrict__ lits, const uint32_t* __restrict__ offsets, int n_clauses, int4* __restrict__ pad4,
-                                 short4* __restrict__ short16, int* __restrict__ long_ids) {
+                                 int* __restrict__ long_ids) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_clauses) return;
     const uint32_t k0 = offsets[c], len = offsets[c + 1] - k0;
@@ -188,7 +187,6 @@ __global__ void cnf_short_kernel(const int32_t* __restrict__ lits, const uint32_
         long_ids[atomicAdd(&long_ids[n_clauses], 1)] = c;
     }
     pad4[c] = q;
-    if (short16) short16[c] = make_short4((short)q.x, (short)q.y, (short)q.z, (short)q.w);
 }
 
 // one padded clause against the assignment bytes: 0 = satisfied, 1 = unit (forces `forced`), 2 = every literal false, 3 = open
@@ -213,61 +211,68 @@ __device__ __forceinline__ int clause_csr(const uint8_t* a, const int32_t* __res
     return open == 1 ? 1 : (open == 0 ? 2 : 3);
 }
 
-// Shared memory: [assignment bytes, padded to 16][resident clauses as short4].  `resident` short clauses (the first ones) are
-// copied in once and read from shared memory; clauses beyond that come from the int4 copy.
-// The FIRST sweep visits every clause and lists the ones that are not satisfied yet (`active`, global scratch); only those can
-// ever force a literal or end up falsified — a satisfied clause stays satisfied, assignments are never withdrawn — so the later
-// sweeps and the final check walk that list alone.  For a GPU layout every base variable arrives decided and the list is the
-// cardinality network of the limit (2.8 K of the 25 K clauses of test/ex2.toml with the default-8 set): 1 us per sweep instead
-// of 10 us (the full sweep is bound by bank conflicts of the random byte reads on one SM's shared memory).
+// Shared memory: [assignment bytes, padded to 16][ids of the first `cap` active clauses][those clauses, padded int4].
+// The FIRST sweep visits every clause (one coalesced 16-byte load each) and keeps the ones that are not satisfied yet — `active`:
+// only those can ever force a literal or end up falsified, a satisfied clause stays satisfied because assignments are never
+// withdrawn — so the later sweeps and the final check walk that list alone, out of shared memory (entries beyond `cap` spill to a
+// global list and are re-read from pad4).  For a GPU layout every base variable arrives decided and the list is the cardinality
+// network of the limit (2.8 K of the 25 K clauses of test/ex2.toml with the default-8 set): < 1 us per sweep instead of 10 us
+// (a full sweep is bound by bank conflicts of the random byte reads on ONE SM's shared memory).
 __global__ void __launch_bounds__(COMPLETE_THREADS, 1) cnf_complete_kernel(const int32_t* __restrict__ lits, const uint32_t* __restrict__ offsets,
-                                                                            const int4* __restrict__ pad4, const short4* __restrict__ short16,
-                                                                            const int* __restrict__ long_ids, int* __restrict__ active, int n_clauses,
-                                                                            int n_vars, int resident, uint8_t* __restrict__ a_glob, int* __restrict__ out) {
+                                                                            const int4* __restrict__ pad4, const int* __restrict__ long_ids,
+                                                                            int* __restrict__ spill, int n_clauses, int n_vars, int cap,
+                                                                            uint8_t* __restrict__ a_glob, int* __restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* a = smem;   // 0 = False, 1 = True, 2 = unassigned; a[0] = 1 makes the padding literal 0 a false, decided literal
-    short4* sc = reinterpret_cast<short4*>(smem + (((size_t)n_vars + 1 + 15) & ~(size_t)15));
+    int* act_id = reinterpret_cast<int*>(smem + (((size_t)n_vars + 1 + 15) & ~(size_t)15));
+    int4* act_cl = reinterpret_cast<int4*>(act_id + cap);   // (cap is a multiple of 4)
     __shared__ int conflict, falsified, n_active;
     for (int v = threadIdx.x; v <= n_vars; v += blockDim.x) a[v] = v ? a_glob[v] : 1;
-    for (int c = threadIdx.x; c < resident; c += blockDim.x) sc[c] = short16[c];
     if (threadIdx.x == 0) { conflict = 0x7fffffff; falsified = 0; n_active = 0; }
     const int n_long = long_ids[n_clauses];
     __syncthreads();
-    auto short_clause = [&](int c, int& forced) -> int {   // -1: not a short clause (x == 0: long or empty, in long_ids)
-        int l0, l1, l2, l3;
-        if (c < resident) { const short4 q = sc[c]; l0 = q.x; l1 = q.y; l2 = q.z; l3 = q.w; }
-        else { const int4 q = pad4[c]; l0 = q.x; l1 = q.y; l2 = q.z; l3 = q.w; }
-        return l0 == 0 ? -1 : clause4(a, l0, l1, l2, l3, forced);
-    };
     auto act = [&](int c, int r, int forced, int& changed) {
         if (r == 1) { a[abs(forced)] = forced > 0; changed = 1; }   // (two clauses forcing opposite values: one of them ends up falsified, found by the next sweep)
         else if (r == 2) atomicMin(&conflict, c);
+    };
+    auto keep = [&](int c, int4 q) {
+        const int slot = atomicAdd(&n_active, 1);
+        if (slot < cap) { act_id[slot] = c; act_cl[slot] = q; }
+        else spill[slot - cap] = c;
     };
     // ---- first sweep: every clause
     int changed = 0, forced = 0, sweeps = 1;
 #pragma unroll 4
     for (int c = threadIdx.x; c < n_clauses; c += COMPLETE_THREADS) {
-        const int r = short_clause(c, forced);
-        if (r <= 0) continue;
+        const int4 q = pad4[c];
+        if (q.x == 0) continue;   // long or empty: in long_ids
+        const int r = clause4(a, q.x, q.y, q.z, q.w, forced);
+        if (r == 0) continue;
         act(c, r, forced, changed);
-        active[atomicAdd(&n_active, 1)] = c;
+        keep(c, q);
     }
     for (int i = threadIdx.x; i < n_long; i += COMPLETE_THREADS) {
         const int c = long_ids[i], r = clause_csr(a, lits, offsets, c, forced);
         if (r == 0) continue;
         act(c, r, forced, changed);
-        active[atomicAdd(&n_active, 1)] = c;
+        keep(c, make_int4(0, 0, 0, 0));
     }
+    auto revisit = [&](int i, int& forced) -> int {   // active clause i against the current assignment; returns its clause id in `forced`'s place via act()
+        int c;
+        int4 q;
+        if (i < cap) { c = act_id[i]; q = act_cl[i]; }
+        else { c = spill[i - cap]; q = pad4[c]; }
+        const int r = q.x ? clause4(a, q.x, q.y, q.z, q.w, forced) : clause_csr(a, lits, offsets, c, forced);
+        return r | (c << 2);
+    };
     // ---- later sweeps: the clauses that were not satisfied then
     while (__syncthreads_or(changed) && conflict == 0x7fffffff) {   // (the barrier also publishes n_active, the list and the forced values)
         __syncthreads();   // (nobody raises `conflict` for the next sweep before everyone has read it)
         changed = 0;
         const int n = n_active;
         for (int i = threadIdx.x; i < n; i += COMPLETE_THREADS) {
-            const int c = active[i];
-            int r = short_clause(c, forced);
-            if (r < 0) r = clause_csr(a, lits, offsets, c, forced);
-            act(c, r, forced, changed);
+            const int rc = revisit(i, forced);
+            act(rc >> 2, rc & 3, forced, changed);
         }
         sweeps++;
     }
@@ -277,12 +282,7 @@ __global__ void __launch_bounds__(COMPLETE_THREADS, 1) cnf_complete_kernel(const
         __syncthreads();
         int bad = 0;
         const int n = n_active;
-        for (int i = threadIdx.x; i < n; i += COMPLETE_THREADS) {
-            const int c = active[i];
-            int r = short_clause(c, forced);
-            if (r < 0) r = clause_csr(a, lits, offsets, c, forced);
-            bad += r == 2;
-        }
+        for (int i = threadIdx.x; i < n; i += COMPLETE_THREADS) bad += (revisit(i, forced) & 3) == 2;
         if (bad) atomicAdd(&falsified, bad);
         __syncthreads();
     }
@@ -331,15 +331,15 @@ int tss::cnf_complete_single(tss_engine* e, const tss_cnf* c, uint8_t* assignmen
     if (!a_dev || !a_pin) return TSS_E_CUDA;
     int* out_dev = (int*)(a_dev + ((bytes + 3) & ~(size_t)3));
     int* out_pin = (int*)(a_pin + ((bytes + 3) & ~(size_t)3));
-    // shared memory: the assignment bytes, then as many 16-bit padded clauses as fit (all of them for every named instance)
+    // shared memory: the assignment bytes, then room for the active clauses (20 bytes each: id + padded literals)
     const size_t a_bytes = (bytes + 15) & ~(size_t)15, smem_cap = (size_t)220 * 1024;
-    const int resident = c->short16 ? (int)std::min<size_t>((size_t)c->n_clauses, (smem_cap - a_bytes) / sizeof(short4)) : 0;
-    const size_t smem = a_bytes + sizeof(short4) * (size_t)resident;
+    const int cap = (int)std::min<size_t>(((size_t)c->n_clauses + 3) & ~(size_t)3, ((smem_cap - a_bytes) / 20) & ~(size_t)3);
+    const size_t smem = a_bytes + (size_t)20 * cap;
     TSS_CUDA(e, cudaFuncSetAttribute(cnf_complete_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
     std::memcpy(a_pin, assignment, bytes);
     TSS_CUDA(e, cudaMemcpyAsync(a_dev, a_pin, bytes, cudaMemcpyHostToDevice, e->stream));
     TSS_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    cnf_complete_kernel<<<1, COMPLETE_THREADS, smem, e->stream>>>(c->lits, c->offsets, c->pad4, c->short16, c->long_ids, c->active, c->n_clauses, c->n_vars, resident, a_dev, out_dev);
+    cnf_complete_kernel<<<1, COMPLETE_THREADS, smem, e->stream>>>(c->lits, c->offsets, c->pad4, c->long_ids, c->active, c->n_clauses, c->n_vars, cap, a_dev, out_dev);
     TSS_CHECK_LAUNCH(e);
     TSS_CUDA(e, cudaEventRecord(e->ev1, e->stream));
     e->stats.kernel_launches++;
@@ -374,8 +374,7 @@ int tss_cnf_upload(tss_engine* e, const int32_t* lits, const uint32_t* offsets, 
     const bool fused = (size_t)n_vars + 1 <= COMPLETE_MAX_BYTES;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t o_lits = 0, o_offs = o_lits + al(sizeof(int32_t) * (size_t)(n_lits > 0 ? n_lits : 1)), o_short = o_offs + al(sizeof(uint32_t) * ((size_t)n_clauses + 1)),
-                 o_s16 = o_short + (fused ? al(sizeof(int4) * (size_t)(n_clauses > 0 ? n_clauses : 1)) : 0),
-                 o_long = o_s16 + (fused && n_vars < 32768 ? al(sizeof(short4) * (size_t)(n_clauses > 0 ? n_clauses : 1)) : 0),
+                 o_long = o_short + (fused ? al(sizeof(int4) * (size_t)(n_clauses > 0 ? n_clauses : 1)) : 0),
                  o_act = o_long + (fused ? al(sizeof(int) * ((size_t)n_clauses + 1)) : 0), total = o_act + (fused ? al(sizeof(int) * ((size_t)n_clauses + 1)) : 0);
     tss_cnf* c = new tss_cnf();
     c->engine = e; c->n_clauses = n_clauses; c->n_vars = n_vars; c->n_lits = n_lits;
@@ -385,14 +384,13 @@ int tss_cnf_upload(tss_engine* e, const int32_t* lits, const uint32_t* offsets, 
         c->offsets = (uint32_t*)((char*)c->blob + o_offs);
         if (fused) { c->pad4 = (int4*)((char*)c->blob + o_short); c->long_ids = (int*)((char*)c->blob + o_long); }
         if (fused) c->active = (int*)((char*)c->blob + o_act);
-        if (fused && n_vars < 32768) c->short16 = (short4*)((char*)c->blob + o_s16);
     }
     if (err == cudaSuccess && n_lits) err = cudaMemcpyAsync(c->lits, lits, sizeof(int32_t) * (size_t)n_lits, cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(c->offsets, offsets, sizeof(uint32_t) * (size_t)(n_clauses + 1), cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess && fused) {
         err = cudaMemsetAsync(c->long_ids + n_clauses, 0, sizeof(int), e->stream);
         if (err == cudaSuccess && n_clauses > 0) {
-            cnf_short_kernel<<<(n_clauses + 255) / 256, 256, 0, e->stream>>>(c->lits, c->offsets, n_clauses, c->pad4, c->short16, c->long_ids);
+            cnf_short_kernel<<<(n_clauses + 255) / 256, 256, 0, e->stream>>>(c->lits, c->offsets, n_clauses, c->pad4, c->long_ids);
             err = cudaGetLastError();
             e->stats.kernel_launches++;
         }
