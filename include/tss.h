@@ -348,7 +348,9 @@ int tss_cnf_complete(tss_engine* e, const tss_cnf* c, uint8_t* assignment, int32
  * the instance carries a weight limit) that gives up after `give_up_steps` SLS steps per chain (<= 0: the engine default),
  * then tss_witness_for_cnf.  TSS_SAT with a verified model in `assignment`; TSS_UNSAT when the instance's only limit (platform
  * count, or total weight) lies below a certified lower bound (the integral packing, checked before searching; the fractional
- * LP, computed once per instance after a search came back empty; grids up to 32x32) — the unmodified bound-tightening loops
+ * LP, computed once per instance after a search came back empty — a first search on an eighth of the give-up budget while that
+ * bound is still to be computed, the whole budget only if the bound does not settle the question; grids up to 32x32) — the
+ * unmodified bound-tightening loops
  * (crates/repl/src/main.rs:331-334, crates/gui/src/app.rs:212-249) then end proven optimal without their exact solver;
  * TSS_UNKNOWN otherwise: the caller asks its exact solver, which stays the only prover of UNSAT by search.
  * tss_engine_certified_unsat switches the bound-based UNSAT answers off (0) or on (non-zero, the default). */

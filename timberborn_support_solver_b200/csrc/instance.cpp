@@ -181,48 +181,73 @@ int tss_solve_instance(tss_engine* e, const tss_cnf* c, const tss_encoding* enc,
     }
     std::vector<tss_platform> plats((size_t)E.w * E.h + 1);
     int32_t n = 0;
-    const int64_t max_steps = give_up_steps > 0 ? -give_up_steps : 0;   // a SAT-like call with a give-up point (tss.h)
-    int rc;
-    if (info->has_weight_limit && info->n_weights > 0 && weights) {
-        int64_t wt = 0;
-        rc = tss_solve_min_weight(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), weights, info->n_weights, info->weight_limit, seed, 0,
-                                  give_up_steps > 0 ? give_up_steps : 0, plats.data(), (int32_t)plats.size(), &n, &wt);
-    } else {
-        rc = tss_solve_upper_bound(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), info->card_limit_1x1, seed, 0, max_steps,
-                                   plats.data(), (int32_t)plats.size(), &n);
+    auto search = [&](int64_t give_up, uint64_t sd) -> int {   // a SAT-like call with a give-up point (tss.h)
+        int r;
+        if (info->has_weight_limit && info->n_weights > 0 && weights) {
+            int64_t wt = 0;
+            r = tss_solve_min_weight(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), weights, info->n_weights, info->weight_limit, sd, 0,
+                                     give_up > 0 ? give_up : 0, plats.data(), (int32_t)plats.size(), &n, &wt);
+        } else {
+            r = tss_solve_upper_bound(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), info->card_limit_1x1, sd, 0, give_up > 0 ? -give_up : 0,
+                                      plats.data(), (int32_t)plats.size(), &n);
+        }
+        tr.lap("solve: search");
+        return r;
+    };
+    // The fractional bound, asked only for what this call needs — "does the bound reach limit + 1?" — so the simplex may stop
+    // early; computed again, to the new target, only if a later call asks about a limit the cached bound does not settle and the
+    // solve was not final.  true = the limit lies below the certified bound.
+    const std::vector<int32_t> wv = weight_only ? std::vector<int32_t>(weights, weights + 3 * (size_t)info->n_weights) : std::vector<int32_t>();
+    auto count_pending = [&] { return enc->d->lp_count_bound == -1 || (enc->d->lp_count_bound >= 0 && !enc->d->lp_count_final && info->card_limit_1x1 >= enc->d->lp_count_bound); };
+    auto weight_pending = [&] {
+        return enc->d->lp_weight_bound == -1 || enc->d->lp_weights != wv || (enc->d->lp_weight_bound >= 0 && !enc->d->lp_weight_final && info->weight_limit >= enc->d->lp_weight_bound);
+    };
+    auto lp_refutes = [&]() -> bool {
+        std::lock_guard<std::mutex> lock(enc->d->bounds_mutex);
+        int64_t lb = 0;
+        int32_t lp_info[3] = {0, 0, 0};
+        if (count_only) {
+            if (count_pending()) {
+                const int ok = tss_lower_bound_lp(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), nullptr, 0, 0, (int64_t)info->card_limit_1x1 + 1,
+                                                  nullptr, nullptr, nullptr, &lb, lp_info);
+                enc->d->lp_count_bound = ok == TSS_OK ? lb : -2;
+                enc->d->lp_count_final = lp_info[1] != 0;
+                tr.lap("solve: fractional bound");
+            }
+            return enc->d->lp_count_bound >= 0 && info->card_limit_1x1 < enc->d->lp_count_bound;
+        }
+        if (weight_only) {   // the same question about the GUI's weight limit (crates/gui/src/app.rs:235-239)
+            if (weight_pending()) {
+                enc->d->lp_weights = wv;
+                const int ok = tss_lower_bound_lp(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), weights, info->n_weights, 0, info->weight_limit + 1,
+                                                  nullptr, nullptr, nullptr, &lb, lp_info);
+                enc->d->lp_weight_bound = ok == TSS_OK ? lb : -2;
+                enc->d->lp_weight_final = lp_info[1] != 0;
+                tr.lap("solve: fractional bound (weights)");
+            }
+            return enc->d->lp_weight_bound >= 0 && info->weight_limit < enc->d->lp_weight_bound;
+        }
+        return false;
+    };
+    // When the bound for this limit is still to be computed, the search first gets an eighth of its give-up budget: the limits of
+    // the loop's last iterations are the ones nothing satisfies, and there the long search was the larger half of the call
+    // (test/ex2.toml with 1x1 supports, limit 13: 1.6 ms of searching before 3.3 ms of simplex).  Found nothing and not refuted:
+    // the search runs again with the whole budget and other seeds.
+    bool pending = false;
+    if (count_only || weight_only) {
+        std::lock_guard<std::mutex> lock(enc->d->bounds_mutex);
+        pending = count_only ? count_pending() : weight_pending();
     }
-    tr.lap("solve: search");
+    const int64_t first_budget = give_up_steps / 8 > 128 ? give_up_steps / 8 : 128;
+    const bool two_phase = pending && give_up_steps > first_budget;
+    int rc = search(two_phase ? first_budget : give_up_steps, seed);
     if (rc == TSS_SAT) return tss_witness_for_cnf(e, c, enc, plats.data(), n, assignment);
-    if (rc == TSS_UNKNOWN && count_only) {   // nothing found within the limit: can the fractional bound certify that nothing exists?
-        std::lock_guard<std::mutex> lock(enc->d->bounds_mutex);
-        // (asked only for what this call needs — "does the bound reach limit + 1?" — so the simplex may stop early; computed again,
-        // to the new target, only if a later call asks about a limit the cached bound does not settle and the solve was not final)
-        if (enc->d->lp_count_bound == -1 || (enc->d->lp_count_bound >= 0 && !enc->d->lp_count_final && info->card_limit_1x1 >= enc->d->lp_count_bound)) {
-            int64_t lb = 0;
-            int32_t lp_info[3] = {0, 0, 0};
-            const int ok = tss_lower_bound_lp(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), nullptr, 0, 0, (int64_t)info->card_limit_1x1 + 1,
-                                              nullptr, nullptr, nullptr, &lb, lp_info);
-            enc->d->lp_count_bound = ok == TSS_OK ? lb : -2;
-            enc->d->lp_count_final = lp_info[1] != 0;
-            tr.lap("solve: fractional bound");
+    if (rc == TSS_UNKNOWN && (count_only || weight_only) && !e->interrupted()) {   // nothing found within the limit: can the fractional bound certify that nothing exists?
+        if (lp_refutes()) return TSS_UNSAT;
+        if (two_phase) {
+            rc = search(give_up_steps, seed ^ 0x9e3779b97f4a7c15ull);
+            if (rc == TSS_SAT) return tss_witness_for_cnf(e, c, enc, plats.data(), n, assignment);
         }
-        if (enc->d->lp_count_bound >= 0 && info->card_limit_1x1 < enc->d->lp_count_bound) return TSS_UNSAT;
-    }
-    if (rc == TSS_UNKNOWN && weight_only) {   // the same question about the GUI's weight limit (crates/gui/src/app.rs:235-239)
-        std::lock_guard<std::mutex> lock(enc->d->bounds_mutex);
-        const std::vector<int32_t> wv(weights, weights + 3 * (size_t)info->n_weights);
-        if (enc->d->lp_weight_bound == -1 || enc->d->lp_weights != wv ||
-            (enc->d->lp_weight_bound >= 0 && !enc->d->lp_weight_final && info->weight_limit >= enc->d->lp_weight_bound)) {
-            int64_t lb = 0;
-            int32_t lp_info[3] = {0, 0, 0};
-            enc->d->lp_weights = wv;
-            const int ok = tss_lower_bound_lp(e, enc->d->grid.data(), E.w, E.h, defs.data(), (int32_t)defs.size(), weights, info->n_weights, 0, info->weight_limit + 1,
-                                              nullptr, nullptr, nullptr, &lb, lp_info);
-            enc->d->lp_weight_bound = ok == TSS_OK ? lb : -2;
-            enc->d->lp_weight_final = lp_info[1] != 0;
-            tr.lap("solve: fractional bound (weights)");
-        }
-        if (enc->d->lp_weight_bound >= 0 && info->weight_limit < enc->d->lp_weight_bound) return TSS_UNSAT;
     }
     return rc;
 }
