@@ -1173,6 +1173,24 @@ def test_cpp_repl_driver_reaches_the_proven_optimum(eng, fixtures, tmp_path, nam
     assert int(f["best"]) == optimum and int(f["exact_solves"]) >= 1 and f["verdict"] == "optimal (exact solver)"
 
 
+@pytest.mark.parametrize("name", ["ex1", "ex3"])
+def test_cpp_driver_runs_the_gui_weight_loop(eng, fixtures, tmp_path, name):
+    """crates/gui/src/app.rs:212-249 through tools/tss_repl.cpp --gui: default-8 set with the GUI's default weights, weight_limit =
+    total_weight - 1 after every solution, until Unsat — over the C ABI with the shim's call sequence (the instance registry hands
+    the weights back, tss_solve_instance steers by the weight limit, the witness satisfies the PB constraint's clauses, and the
+    weighted fractional bound answers UNSAT where it meets the weight).  The final weight is the minimum the oracle's GUI loop proves."""
+    want = oracle_min_weight(fixtures[name], O.PLATFORMS_DEFAULT, GUI_WEIGHTS)
+    text, f, counts = _run_repl(tmp_path, fixtures[name], "--gui", "--seed", "3")
+    weights = [int(ln.split()[-1]) for ln in text.splitlines() if ln.startswith("Got a solution with weight")]
+    assert int(f["weight"]) == want == weights[-1] and all(b < a for a, b in zip(weights, weights[1:]))
+    assert f["verdict"].startswith("optimal") and "FAILED" not in text and int(f["gpu_solves"]) >= 2
+    if f["verdict"] == "optimal (lower bound)":
+        assert int(f["exact_solves"]) == 0 and int(f["lower_bound"]) == want
+    # ... and with the bound-based answers switched off the exact solver proves the same minimum
+    text, f, counts = _run_repl(tmp_path, fixtures[name], "--gui", "--seed", "3", "--no-lower-bound")
+    assert int(f["weight"]) == want and f["verdict"] == "optimal (exact solver)" and int(f["exact_solves"]) >= 1
+
+
 def test_cpp_repl_driver_limits_and_errors(eng, fixtures, tmp_path):
     # `solve -l 1:2` on ex1 with 1x1 supports: 3 are needed (proofs.json) -> UNSAT straight from the exact solver
     text, f, counts = _run_repl(tmp_path, fixtures["ex1"], "--platforms", "1x1", "-l", "1:2", "--no-lower-bound")

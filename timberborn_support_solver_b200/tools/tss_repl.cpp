@@ -13,7 +13,11 @@
 // prints `s SATISFIABLE|UNSATISFIABLE` and `v ...` lines, e.g. `z3 -dimacs`, glucose, kissat) or from tss_solve_instance when the
 // limit lies below a certified lower bound of the instance (packing / fractional LP); a search that finds nothing proves nothing.
 //
-//   tss_repl PROJECT.toml [--platforms default|1x1] [-l k:v[,k:v]] [--exact "CMD"] [--seed N] [--no-lower-bound] [--quiet] [--repeat N] [--phases]
+// `--gui` runs the GUI's loop instead (crates/gui/src/app.rs:212-249): the default-8 set with the GUI's default weights
+// (app.rs:53-62), no card limits; after every solution limits.weight_limit = total_weight - 1 (while that is positive), until
+// the solver says Unsat — the weight limit's pseudo-boolean constraint is part of the clauses the witness is checked against.
+//
+//   tss_repl PROJECT.toml [--platforms default|1x1] [-l k:v[,k:v]] [--gui] [--exact "CMD"] [--seed N] [--no-lower-bound] [--quiet] [--repeat N] [--phases]
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -93,7 +97,7 @@ int main(int argc, char** argv) {
     std::string project, exact_cmd, platforms = "default";
     std::vector<int32_t> card;
     uint64_t seed = 0;
-    bool use_lb = true, quiet = false, phases = false;
+    bool use_lb = true, quiet = false, phases = false, gui = false;
     int repeat = 1;
     double ph[8] = {};   // --phases: wall ms per call site, summed over the warm repeats
     static const char* const PH[8] = {"encoding_create", "with_limits", "cnf_upload", "instance_find", "solve_instance", "from_assignment", "validate", "destroy"};
@@ -107,6 +111,7 @@ int main(int argc, char** argv) {
         else if (a == "--no-lower-bound") use_lb = false;
         else if (a == "--quiet") quiet = true;
         else if (a == "--phases") phases = true;
+        else if (a == "--gui") gui = true;
         else if (a == "--repeat" && i + 1 < argc) repeat = std::atoi(argv[++i]) > 0 ? std::atoi(argv[i]) : 1;
         else if (project.empty()) project = a;
         else { std::fprintf(stderr, "usage: tss_repl PROJECT.toml [--platforms default|1x1] [-l k:v[,k:v]] [--exact CMD] [--seed N] [--no-lower-bound] [--quiet]\n"); return 2; }
@@ -126,7 +131,12 @@ int main(int argc, char** argv) {
     grid.resize((size_t)w * h);
     // PLATFORMS_DEFAULT (src/platform.rs:23-32), what the REPL solves with (main.rs:254)
     const tss_dims all_defs[8] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {3, 3}, {5, 5}};
-    const int n_defs = platforms == "1x1" ? 1 : 8;
+    const int n_defs = platforms == "1x1" && !gui ? 1 : 8;
+    // DEFAULT_PLATFORMS of the GUI (crates/gui/src/app.rs:53-62): records (def_w, def_h, weight)
+    const int32_t gui_weights[24] = {1, 1, 5, 1, 2, 1, 1, 3, 1, 1, 4, 1, 1, 5, 1, 1, 6, 1, 3, 3, 2, 5, 5, 4};
+    const int32_t* wts = gui ? gui_weights : nullptr;
+    const int32_t n_wts = gui ? 8 : 0;
+    long long best_weight = -1;
     const double t_start = now_ms();
 
     tss_engine* e = nullptr;
@@ -145,6 +155,9 @@ int main(int argc, char** argv) {
 #define SAY(...) do { if (say) std::printf(__VA_ARGS__); } while (0)
         card = card0;
         lower = -1; gpu_solves = exact_solves = 0; best = -1; verdict = "open";
+        int32_t has_wl = 0;
+        int64_t wl = 0;
+        best_weight = -1;
         t_loop = now_ms();   // one `solve`: encode, bounds, loop (engine creation = CUDA context start-up, ~1-4 s of a fresh process, is reported apart)
         tss_encoding* enc = nullptr;
         double tp = now_ms();
@@ -162,10 +175,10 @@ int main(int argc, char** argv) {
         for (;;) {
             int32_t n_vars = 0, n_clauses = 0;
             int64_t n_lits = 0;
-            tss_encoding_with_limits(enc, card.data(), (int32_t)card.size() / 3, nullptr, 0, 0, 0, &n_vars, &n_clauses, &n_lits, nullptr, nullptr);
+            tss_encoding_with_limits(enc, card.data(), (int32_t)card.size() / 3, wts, n_wts, has_wl, wl, &n_vars, &n_clauses, &n_lits, nullptr, nullptr);
             std::vector<int32_t> lits((size_t)n_lits + 1);
             std::vector<uint32_t> offsets((size_t)n_clauses + 1);
-            tss_encoding_with_limits(enc, card.data(), (int32_t)card.size() / 3, nullptr, 0, 0, 0, &n_vars, &n_clauses, &n_lits, lits.data(), offsets.data());
+            tss_encoding_with_limits(enc, card.data(), (int32_t)card.size() / 3, wts, n_wts, has_wl, wl, &n_vars, &n_clauses, &n_lits, lits.data(), offsets.data());
             lits.resize((size_t)n_lits);
             PHASE(1);
 
@@ -175,7 +188,8 @@ int main(int argc, char** argv) {
             PHASE(2);
             tss_encoding* inst = nullptr;
             tss_instance_info info;
-            const int found = tss_instance_find(lits.data(), offsets.data(), n_clauses, n_vars, &inst, &info, nullptr, 0);
+            int32_t found_weights[3 * 16];   // the PlatformLimits.weights map, handed back by the registry like the rest of the instance
+            const int found = tss_instance_find(lits.data(), offsets.data(), n_clauses, n_vars, &inst, &info, found_weights, 16);
 
             PHASE(3);
             // ---- Solve::solve
@@ -184,7 +198,7 @@ int main(int argc, char** argv) {
             std::string source = "gpu";
             if (found == TSS_SAT) {
                 tss_clear_interrupt(e);
-                const int rc = tss_solve_instance(e, cnf, inst, &info, nullptr, seed++, give_up, assignment.data());
+                const int rc = tss_solve_instance(e, cnf, inst, &info, info.n_weights > 0 ? found_weights : nullptr, seed++, give_up, assignment.data());
                 if (rc < 0) std::fprintf(stderr, "tss_solve_instance: %s\n", tss_last_error(e));   // logged, never fatal (crates/gui/src/app.rs:160-173)
                 result = rc == TSS_SAT ? 10 : rc == TSS_UNSAT ? 20 : 0;   // UNSAT: the limit lies below a certified lower bound
                 gpu_solves++;
@@ -207,7 +221,7 @@ int main(int argc, char** argv) {
             if (result == 20) {
                 SAY("No solution found for the current constraints\n");
                 verdict = best < 0 ? "unsatisfiable" : source == "exact" ? "optimal (exact solver)" : "optimal (lower bound)";
-                if (best >= 0 && source != "exact") lower = best;   // the certified bound that closed the loop is at least the limit it refused + 1
+                if (best >= 0 && source != "exact") lower = gui ? (int)best_weight : best;   // the certified bound that closed the loop is at least the limit it refused + 1
                 break;
             }
             if (result != 10) { SAY("Solver interrupted\n"); verdict = "unknown (no exact solver answer)"; break; }
@@ -218,10 +232,19 @@ int main(int argc, char** argv) {
             PHASE(5);
             if (n == 0) { SAY("Found a solution with no platforms - aborting\n"); verdict = "optimal (no platforms)"; best = 0; break; }
             best = n;
-            bool has = false;
-            for (size_t i = 0; i < card.size(); i += 3)
-                if (card[i] == 1 && card[i + 1] == 1) { card[i + 2] = n - 1; has = true; }
-            if (!has) { card.push_back(1); card.push_back(1); card.push_back(n - 1); }
+            bool last = false;
+            if (gui) {   // app.rs:235-245: weight_limit = total_weight - 1 while that is positive
+                best_weight = (long long)tss_layout_total_weight(plats.data(), n, gui_weights, 8);
+                SAY("Got a solution with weight %lld\n", best_weight);
+                has_wl = 1;
+                wl = best_weight - 1;
+                last = wl <= 0;
+            } else {
+                bool has = false;
+                for (size_t i = 0; i < card.size(); i += 3)
+                    if (card[i] == 1 && card[i + 1] == 1) { card[i + 2] = n - 1; has = true; }
+                if (!has) { card.push_back(1); card.push_back(1); card.push_back(n - 1); }
+            }
             SAY("Solution found (%d platforms total)\n", n);
             std::map<std::pair<int, int>, int> stats;
             for (int i = 0; i < n; i++) stats[{plats[i].def_w, plats[i].def_h}]++;
@@ -233,6 +256,7 @@ int main(int argc, char** argv) {
             for (int i = 0; i < n; i++) bad += flags[i] != 0;
             if (!quiet) SAY(bad == 0 ? "Solution validation OK (%s)\n" : "Solution validation FAILED (%s)\n", source.c_str());
             if (bad != 0) { verdict = "invalid layout"; break; }
+            if (last) { verdict = "optimal (weight 1)"; break; }
         }
         tss_encoding_destroy(enc);
         loop_ms.push_back(now_ms() - t_loop);
@@ -240,8 +264,8 @@ int main(int argc, char** argv) {
     std::printf("Done\n");
     std::sort(loop_ms.begin() + (loop_ms.size() > 1 ? 1 : 0), loop_ms.end());   // the first run is cold (allocations): median of the rest
     const double warm = loop_ms.size() > 1 ? loop_ms[1 + (loop_ms.size() - 1) / 2] : loop_ms[0];
-    std::printf("# best=%d lower_bound=%d verdict=\"%s\" gpu_solves=%d exact_solves=%d ms=%.3f setup_ms=%.1f repeats=%zu warm_ms=%.3f\n", best, lower,
-                verdict.c_str(), gpu_solves, exact_solves, loop_ms[0], t_setup - t_start, loop_ms.size(), warm);
+    std::printf("# best=%d lower_bound=%d verdict=\"%s\" gpu_solves=%d exact_solves=%d ms=%.3f setup_ms=%.1f repeats=%zu warm_ms=%.3f weight=%lld\n", best, lower,
+                verdict.c_str(), gpu_solves, exact_solves, loop_ms[0], t_setup - t_start, loop_ms.size(), warm, best_weight);
     if (phases && repeat > 1) {
         std::printf("# phases (ms per solve, mean of %d warm repeats):", repeat - 1);
         for (int i = 0; i < 8; i++) std::printf(" %s=%.3f", PH[i], ph[i] / (repeat - 1));
