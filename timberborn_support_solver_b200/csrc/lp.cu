@@ -176,71 +176,158 @@ __global__ void __launch_bounds__(THREADS) lp_simplex_kernel(double* __restrict_
 constexpr int CLUSTER = 8;
 constexpr int CL_THREADS = 512;
 
+// 1 / x for the pivot arithmetic: single-precision reciprocal refined by two Newton steps in double precision (error ~1 ulp).  An
+// IEEE double division is a chain of ~20 dependent FP64 operations (~800 cycles measured here, and every pivot has three of them on
+// its critical path); this is 5.  The certificate does not depend on it: it is recomputed in integers (lp_certify_kernel).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r = (double)(1.0f / (float)x);
+    r = r * (2.0 - x * r);
+    r = r * (2.0 - x * r);
+    return r;
+}
+
+// Exact warp argmin over non-negative doubles (lowest index on ties) in three 32-bit REDUX instructions instead of five shuffle
+// rounds on (double, int) pairs: non-negative doubles order like their bit patterns, so reduce the high words, then the low words
+// among the lanes that hold the minimum high word, then the indices among the lanes that hold both.  Lanes without a candidate
+// pass v = +inf, i = 0x7fffffff.  Every lane gets the result.
+__device__ __forceinline__ ArgD warp_argmin_nonneg(ArgD a) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(a.v);
+    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+    const unsigned mhi = __reduce_min_sync(FULL, hi);
+    const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
+    const bool mine = hi == mhi && lo == mlo;
+    const unsigned mi = __reduce_min_sync(FULL, mine ? (unsigned)a.i : 0xffffffffu);
+    return ArgD{__longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo)), (int)mi};
+}
+// The same for a maximum (pricing: largest Devex ratio, lowest column on ties).  Lanes without a candidate pass v = 0, i = 0x7fffffff.
+__device__ __forceinline__ ArgD warp_argmax_nonneg(ArgD a) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(a.v);
+    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+    const unsigned mhi = __reduce_max_sync(FULL, hi);
+    const unsigned mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+    const bool mine = hi == mhi && lo == mlo;
+    const unsigned mi = __reduce_min_sync(FULL, mine ? (unsigned)a.i : 0xffffffffu);
+    return ArgD{__longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo)), (int)mi};
+}
+
+__device__ __forceinline__ ArgD warp_argmin(ArgD a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ArgD b{__shfl_xor_sync(FULL, a.v, o), __shfl_xor_sync(FULL, a.i, o)};
+        a = better_min(a, b);
+    }
+    return a;
+}
+
+// One pivot = one cluster barrier.  Measured on the first version (clock64 per stage, TSS_LP_PROF=1; 11 400 cycles per pivot on
+// test/ex2.toml): the rank-1 update took 5 000 (an integer division per cell to find its row), pricing and the ratio test 1 700 +
+// 1 500 (two block-wide reductions with two barriers each for 236 columns / 30 rows), pulling the pivot row out of its owner's
+// shared memory 1 700 (dependent remote reads) and the two cluster barriers 650-850 each.  Now:
+//   * warp 0 alone prices (8 columns per lane) and runs the ratio test over this CTA's rows (one per lane): shuffles only;
+//   * every CTA then PUSHES its candidate — ratio and the whole candidate pivot row — into the shared memory of all eight CTAs
+//     (remote stores do not stall; buffers alternate with the pivot's parity, so one barrier per pivot is enough: nobody can be two
+//     barriers ahead of a CTA that still reads);
+//   * after the barrier everybody picks the winner among the eight local copies and scales its row; the update walks rows by warp
+//     (no divisions) and skips the rows that do not touch the entering column.
+// Decisions are unchanged (same keys, same tie-breaks): the same pivot sequence and certificate as before.
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(CL_THREADS)
 lp_simplex_cluster_kernel(const double* __restrict__ T, int m, int n, const int* __restrict__ col_site, int max_pivots, double stop_at, int* __restrict__ info,
-                          int* __restrict__ weights /* [1024] zeroed */, double scale) {
+                          int* __restrict__ weights /* [1024] zeroed */, double scale, long long* __restrict__ prof /* optional [8]: clock cycles per pivot stage */) {
     cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank(), tid = threadIdx.x, ld = n + 1;
+    const int rank = (int)cluster.block_rank(), tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ld = n + 1;
     const int rows_per = (m + CLUSTER - 1) / CLUSTER, row0 = rank * rows_per, my_rows = max(0, min(rows_per, m - row0));
     extern __shared__ __align__(16) unsigned char dyn[];
     double* Tl = reinterpret_cast<double*>(dyn);            // [rows_per][ld] my constraint rows (right-hand side at [n])
-    double* prow = Tl + (size_t)rows_per * ld;              // [ld] the new pivot row
-    double* obj = prow + ld;                                // [ld] objective row (replicated)
+    double* obj = Tl + (size_t)rows_per * ld;               // [ld] objective row (replicated)
     double* devex = obj + ld;                               // [ld] Devex reference weights of the non-basic columns (replicated)
     double* pcol = devex + ld;                              // [rows_per] my part of the entering column
-    ArgD* slots = reinterpret_cast<ArgD*>(pcol + rows_per); // [CLUSTER] local winners of the ratio test
-    int* basis = reinterpret_cast<int*>(slots + CLUSTER);   // [m] (replicated)
+    double* cand = pcol + rows_per;                         // [2][CLUSTER][ld] candidate pivot rows of all CTAs, by pivot parity
+    ArgD* slots = reinterpret_cast<ArgD*>(cand + (size_t)2 * CLUSTER * ld);   // [2][CLUSTER] local winners of the ratio test
+    int* basis = reinterpret_cast<int*>(slots + 2 * CLUSTER);                 // [m] (replicated)
     int* nonbasis = basis + m;                              // [n] (replicated)
-    __shared__ ArgD red[32];
+    __shared__ ArgD red[CL_THREADS / 32];                   // per-warp pricing candidates of the next pivot (Devex ratio, column)
     for (int idx = tid; idx < my_rows * ld; idx += blockDim.x) Tl[idx] = T[(size_t)row0 * ld + idx];
     for (int j = tid; j <= n; j += blockDim.x) { obj[j] = T[(size_t)m * ld + j]; devex[j] = 1.0; }
     for (int i = tid; i < m; i += blockDim.x) basis[i] = n + i;
     for (int j = tid; j < n; j += blockDim.x) nonbasis[j] = j;
-    cluster.sync();
-    int pivots = 0, optimal = 0;
-    for (; pivots < max_pivots; pivots++) {
-        // entering column by Devex pricing (Forrest & Goldfarb): largest d_j^2 / w_j among the improving columns, the reference
-        // weights w_j approximating the steepest-edge norms at the price of one pass over the pivot row (Dantzig's rule needs
-        // ~1 500 pivots on the 21x16 terrains, this ~760)
+    __syncthreads();
+    // Devex pricing (Forrest & Goldfarb): largest d_j^2 / w_j among the improving columns, the reference weights w_j approximating
+    // the steepest-edge norms at the price of one pass over the pivot row (Dantzig's rule needs ~1 500 pivots on the 21x16
+    // terrains, this ~760).  Every thread prices the columns it has just updated (one division each, all in parallel) and the
+    // warps leave their candidates in `red`; the barrier that ends the pivot publishes them.
+    auto price = [&]() {
         ArgD e{0.0, 0x7fffffff};
         for (int j = tid; j < n; j += blockDim.x) {
             const double d = obj[j];
-            if (d < -EPS) e = better_min(e, ArgD{-d * d / devex[j], j});
+            if (d < -EPS) {
+                const double key = d * d * fast_rcp(devex[j]);
+                if (key > e.v) e = ArgD{key, j};            // (columns ascend: the first of equal keys stays)
+            }
         }
-        e = block_argmin(e, red);
-        if (e.i == 0x7fffffff) { optimal = 1; break; }     // (identical in every CTA: nobody is left waiting at a barrier)
-        const int q = e.i;
-        ArgD r{1e300, 0x7fffffff};
-        for (int li = tid; li < my_rows; li += blockDim.x) {
+        e = warp_argmax_nonneg(e);
+        if (lane == 0) red[warp] = e;
+    };
+    price();
+    cluster.sync();
+    int pivots = 0, optimal = 0;
+    long long tprev = clock64(), acc[6] = {0, 0, 0, 0, 0, 0};
+#define LP_LAP(i) do { if (prof && rank == 0 && tid == 0) { const long long t_ = clock64(); acc[i] += t_ - tprev; tprev = t_; } } while (0)
+    for (; pivots < max_pivots; pivots++) {
+        const int par = pivots & 1;
+        const ArgD ent = warp_argmax_nonneg(red[lane & (CL_THREADS / 32 - 1)]);   // the entering column: every warp folds the 16 candidates itself
+        if (ent.i == 0x7fffffff) { optimal = 1; break; }    // (identical in every CTA: nobody is left waiting at a barrier)
+        const int q = ent.i;
+        const double fo = obj[q], wq = devex[q];            // (read before the barrier below; rewritten after it)
+        // ratio test over my rows, one per lane — by EVERY warp for itself (identical results, no block barrier to publish them)
+        ArgD r{__longlong_as_double(0x7ff0000000000000ll), 0x7fffffff};   // +inf: no candidate
+        for (int li = lane; li < my_rows; li += 32) {
             const double a = Tl[(size_t)li * ld + q];
-            pcol[li] = a;
-            if (a > EPS) r = better_min(r, ArgD{Tl[(size_t)li * ld + n] / a, row0 + li});
+            pcol[li] = a;                                   // (all warps store the same values)
+            if (a > EPS) r = better_min(r, ArgD{fmax(Tl[(size_t)li * ld + n] * fast_rcp(a), 0.0), row0 + li});
         }
-        r = block_argmin(r, red);
-        if (tid < CLUSTER) *cluster.map_shared_rank(&slots[rank], tid) = r;      // my winner into everybody's slot array
-        cluster.sync();
-        ArgD g = slots[0];
+        r = warp_argmin_nonneg(r);
+        __syncwarp();
+        LP_LAP(0);
+        if (r.i != 0x7fffffff) {                            // my candidate row into everybody's buffer
+            const double* mine = Tl + (size_t)(r.i - row0) * ld;
+            for (int j = tid; j <= n; j += blockDim.x) {
+                const double v = mine[j];
 #pragma unroll
-        for (int c = 1; c < CLUSTER; c++) g = better_min(g, slots[c]);
-        if (g.i == 0x7fffffff) break;                       // unbounded: cannot happen, never spin on it
-        const int pr = g.i, owner = pr / rows_per, lpr = pr - owner * rows_per;
-        const double* remote = cluster.map_shared_rank(Tl, owner) + (size_t)lpr * ld;   // the pivot row, in its owner's shared memory
-        const double inv = 1.0 / remote[q];
-        for (int j = tid; j <= n; j += blockDim.x) prow[j] = j == q ? inv : remote[j] * inv;
-        cluster.sync();                                     // everybody holds the pivot row: its owner may overwrite it now
-        for (int idx = tid; idx < my_rows * ld; idx += blockDim.x) {
-            const int li = idx / ld, j = idx - li * ld;
-            if (row0 + li == pr) { Tl[idx] = prow[j]; continue; }
-            const double f = pcol[li];
-            if (f != 0.0) Tl[idx] = j == q ? -f * inv : Tl[idx] - f * prow[j];
+                for (int c = 0; c < CLUSTER; c++) cluster.map_shared_rank(cand, c)[((size_t)par * CLUSTER + rank) * ld + j] = v;
+            }
         }
-        const double fo = obj[q], wq = devex[q];
-        __syncthreads();
-        for (int j = tid; j <= n; j += blockDim.x) obj[j] = j == q ? -fo * inv : obj[j] - fo * prow[j];
-        for (int j = tid; j < n; j += blockDim.x)           // Devex update: prow[j] = alpha_rj / alpha_rq for j != q, prow[q] = 1 / alpha_rq
-            devex[j] = j == q ? fmax(wq * inv * inv, 1.0) : fmax(devex[j], prow[j] * prow[j] * wq);
+        if (tid < CLUSTER) cluster.map_shared_rank(slots, tid)[par * CLUSTER + rank] = r;
+        LP_LAP(1);
+        cluster.sync();
+        LP_LAP(2);
+        const ArgD g = warp_argmin_nonneg(slots[par * CLUSTER + (lane & (CLUSTER - 1))]);   // the winner among the eight candidates
+        if (g.i == 0x7fffffff) break;                       // unbounded: cannot happen, never spin on it
+        const int pr = g.i, owner = pr / rows_per;
+        const double* crow = cand + ((size_t)par * CLUSTER + owner) * ld;   // the pivot row before scaling: a local copy
+        const double inv = fast_rcp(crow[q]);
+        auto prow_at = [&](int j) { return j == q ? inv : crow[j] * inv; };   // element j of the new pivot row
+        LP_LAP(3);
+        // rank-1 update: a thread owns one column (two threads share it, even / odd rows) and walks down the rows, eight at a time with
+        // all reads first; rows that do not touch the entering column (0/1 rows: most) cost one broadcast read
+        for (int j = tid & (CL_THREADS / 2 - 1); j <= n; j += CL_THREADS / 2) {
+            const double pj = prow_at(j);
+            for (int li = tid / (CL_THREADS / 2); li < my_rows; li += 2) {
+                const double f = pcol[li];                  // (uniform across the warp: no divergence)
+                double* cell = Tl + (size_t)li * ld + j;
+                if (row0 + li == pr) *cell = pj;
+                else if (f != 0.0) *cell = j == q ? -f * inv : *cell - f * pj;
+            }
+        }
+        LP_LAP(4);
+        for (int j = tid; j <= n; j += blockDim.x) {        // objective row and Devex weights: prow[j] = alpha_rj / alpha_rq for j != q, prow[q] = 1 / alpha_rq
+            const double pj = prow_at(j);
+            obj[j] = j == q ? -fo * inv : obj[j] - fo * pj;
+            if (j < n) devex[j] = j == q ? fmax(wq * inv * inv, 1.0) : fmax(devex[j], pj * pj * wq);
+        }
         if (tid == 0) { const int t = basis[pr]; basis[pr] = nonbasis[q]; nonbasis[q] = t; }
+        price();                                            // (each thread prices exactly the columns it has just written)
         __syncthreads();
+        LP_LAP(5);
         if (stop_at > 0.0 && obj[n] >= stop_at) { pivots++; break; }   // the bound the caller asked about is reached (obj is replicated: every CTA leaves here)
     }
     for (int li = tid; li < my_rows; li += blockDim.x) {    // y -> integer weights: floor(y * SCALE) for my basic tiles
@@ -251,7 +338,9 @@ lp_simplex_cluster_kernel(const double* __restrict__ T, int m, int n, const int*
         weights[col_site[label]] = (int)(k > (1ll << 30) ? (1ll << 30) : k);
     }
     if (rank == 0 && tid == 0) { info[0] = pivots; info[1] = optimal; }
-    cluster.sync();                                         // nobody exits while its shared memory may still be read remotely
+    if (prof && rank == 0 && tid == 0)
+        for (int i = 0; i < 6; i++) prof[i] = acc[i];
+    cluster.sync();                                         // nobody exits while its shared memory may still be written remotely
 }
 
 // y -> integer weights per site (floor(y * SCALE), never negative), zero for non-basic tiles
@@ -360,12 +449,17 @@ int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::
     // settled after 60-80 % of the pivots (ex2 / README terrain with 1x1 supports: 13.0 is passed long before the optimum 13.2 / 13.13)
     const double stop_at = target > 0 ? (double)(target - 1) + 4.0 * (double)n / scale + 2e-3 : 0.0;
     const int rows_per = (m + lp::CLUSTER - 1) / lp::CLUSTER, ld = n + 1;
-    const size_t cl_smem = sizeof(double) * ((size_t)rows_per * ld + 3 * (size_t)ld + rows_per) + sizeof(lp::ArgD) * lp::CLUSTER + sizeof(int) * ((size_t)m + n);
+    const size_t cl_smem = sizeof(double) * ((size_t)rows_per * ld + 2 * (size_t)ld + rows_per + 2 * (size_t)lp::CLUSTER * ld) + sizeof(lp::ArgD) * 2 * lp::CLUSTER +
+                           sizeof(int) * ((size_t)m + n);
     const char* force = getenv("TSS_LP_SINGLE_CTA");       // (A/B switch for profiles/lb_stream.py)
+    // TSS_LP_PROF=1: clock cycles of CTA 0 per pivot stage on stderr (pricing, ratio test, slot exchange + barrier, pivot row pull, barrier, update)
+    long long* prof_dev = nullptr;
+    if (getenv("TSS_LP_PROF")) prof_dev = (long long*)e->dev(7, sizeof(long long) * 8);
     if (cl_smem <= 200 * 1024 && !(force && force[0] == '1')) {
         // the tableau fits the shared memory of one 8-CTA cluster: rows resident in shared memory, exchange over DSMEM
         TSS_CUDA(e, cudaFuncSetAttribute(lp::lp_simplex_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_smem));
-        lp::lp_simplex_cluster_kernel<<<lp::CLUSTER, lp::CL_THREADS, cl_smem, e->stream>>>(T, m, n, col_dev, pivots_cap, stop_at, info_dev, weights, scale);
+        if (lp::CLUSTER > 8) TSS_CUDA(e, cudaFuncSetAttribute(lp::lp_simplex_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        lp::lp_simplex_cluster_kernel<<<lp::CLUSTER, lp::CL_THREADS, cl_smem, e->stream>>>(T, m, n, col_dev, pivots_cap, stop_at, info_dev, weights, scale, prof_dev);
     } else {
         lp::lp_simplex_kernel<<<1, lp::THREADS, 0, e->stream>>>(T, m, n, basis, nonbasis, pivots_cap, stop_at, info_dev);
         lp::lp_weights_kernel<<<(m + 255) / 256, 256, 0, e->stream>>>(T, m, n, basis, col_dev, weights, scale);
@@ -382,6 +476,12 @@ int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) cudaGetLastError();
     e->stats.device_ms = ms;
+    if (prof_dev && info[0] > 0 && cl_smem <= 200 * 1024) {
+        long long prof[6];
+        TSS_CUDA(e, cudaMemcpy(prof, prof_dev, sizeof prof, cudaMemcpyDeviceToHost));
+        static const char* const names[6] = {"fold pricing + ratio test", "push candidate rows", "cluster barrier", "pick pivot row", "row update", "objective / devex / pricing"};
+        for (int i = 0; i < 6; i++) std::fprintf(stderr, "[lp prof] %-30s %8.0f cycles per pivot\n", names[i], (double)prof[i] / info[0]);
+    }
     return TSS_OK;
 }
 
