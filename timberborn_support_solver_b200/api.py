@@ -792,17 +792,18 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
             proved = True
             break
         cnf = encoding.with_limits(limits)                      # main.rs:292-293
+        # while the fractional bound is still to be computed the search first gets an eighth of its give-up budget (the limits
+        # nothing satisfies are where a long search is wasted), the whole budget only if the bound does not refute the limit:
+        # the same schedule as tss_solve_instance (csrc/instance.cpp)
+        lp_pending = use_lower_bound and not lp_done and best is not None
+        first = max(128, give_up // 8) if (budget_ms is None and lp_pending) else give_up
         if budget_ms is None:
-            solver = GpuBoundSolver(engine, encoding, limits, seed=seed, budget_ms=0, max_steps=-give_up)
+            solver = GpuBoundSolver(engine, encoding, limits, seed=seed, budget_ms=0, max_steps=-first)
         else:
             solver = GpuBoundSolver(engine, encoding, limits, seed=seed, budget_ms=budget_ms)
         solver.add_cnf(cnf)                                     # solver_runner.rs:12
         result = solver.solve()
-        if result == SAT:
-            give_up = max(1024, 32 * int(engine.stats()["last_solve_steps"]))
-        source = "gpu"
-        assignment = solver.full_solution() if result == SAT else None
-        if result != SAT and use_lower_bound and not lp_done and best is not None:
+        if result != SAT and lp_pending:
             lp_done = True                                      # the GPU found nothing below the current count: can the fractional bound certify it?
             # (asked only "does the bound reach the count at hand?": the simplex stops as soon as it does)
             lower = max(lower, engine.lower_bound_lp(g, encoding.defs, target=best.platform_count())["bound"])
@@ -810,6 +811,14 @@ def solver_loop(project: Project, encoding: Encoding, limits: PlatformLimits, en
                 steps.append(dict(bound=limits.card_limits[one], result=UNSAT, source="lower bound"))
                 proved = True
                 break
+            if budget_ms is None and first < give_up:           # not refuted: the whole budget, other seeds
+                solver = GpuBoundSolver(engine, encoding, limits, seed=seed ^ 0x9E3779B97F4A7C15, budget_ms=0, max_steps=-give_up)
+                solver.add_cnf(cnf)
+                result = solver.solve()
+        if result == SAT:
+            give_up = max(1024, 32 * int(engine.stats()["last_solve_steps"]))
+        source = "gpu"
+        assignment = solver.full_solution() if result == SAT else None
         if result != SAT and exact_solver is not None:          # the GPU found nothing in budget: ask the prover
             result, assignment = exact_solver(cnf)
             source = "exact"
