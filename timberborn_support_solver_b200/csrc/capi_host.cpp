@@ -107,14 +107,31 @@ int tss_encoding_with_limits(const tss_encoding* enc, const int32_t* card, int32
     lim.weights = entries(weights, n_weights);
     lim.has_weight_limit = has_weight_limit != 0;
     lim.weight_limit = (long)weight_limit;
-    Cnf f = enc->d->enc.with_limits(lim);
+    auto same_entries = [](const std::vector<PlatformLimits::Entry>& a, const std::vector<PlatformLimits::Entry>& b) {
+        if (a.size() != b.size()) return false;
+        for (size_t i = 0; i < a.size(); i++)
+            if (a[i].def.w != b[i].def.w || a[i].def.h != b[i].def.h || a[i].value != b[i].value) return false;
+        return true;
+    };
+    std::shared_ptr<const Cnf> lowered;
+    {
+        std::lock_guard<std::mutex> lock(enc->d->lowered_mutex);
+        const PlatformLimits& c = enc->d->lowered_limits;
+        if (!enc->d->lowered || !same_entries(c.card_limits, lim.card_limits) || !same_entries(c.weights, lim.weights) || c.has_weight_limit != lim.has_weight_limit ||
+            (lim.has_weight_limit && c.weight_limit != lim.weight_limit)) {
+            enc->d->lowered = std::make_shared<const Cnf>(enc->d->enc.with_limits(lim));
+            enc->d->lowered_limits = lim;
+        }
+        lowered = enc->d->lowered;
+    }
+    const Cnf& f = *lowered;
     if (n_vars) *n_vars = f.n_vars;
     if (n_clauses) *n_clauses = f.n_clauses();
     if (n_lits) *n_lits = (int64_t)f.lits.size();
     if (lits && offsets) {
         std::memcpy(lits, f.lits.data(), f.lits.size() * sizeof(int32_t));
         std::memcpy(offsets, f.offsets.data(), f.offsets.size() * sizeof(uint32_t));
-        instance_record(enc->d, lim, f);   // the solver that receives these clauses can find its instance again (tss_instance_find)
+        instance_record(enc->d, lim, lowered);   // the solver that receives these clauses can find its instance again (tss_instance_find)
     }
     return TSS_OK;
 }

@@ -18,6 +18,11 @@ struct tss_encoding_data {
     mutable bool lp_count_final = false, lp_weight_final = false;   // the simplex ran to optimality (not stopped at a target): asking again cannot improve the bound
     mutable std::vector<int32_t> lp_weights;   // the weight table `lp_weight_bound` was computed for
     mutable long long lp_weight_bound = -1;    // tss_lower_bound_lp on the total weight
+    // the CNF of the last tss_encoding_with_limits call: callers ask twice, once for the sizes and once for the clauses, and the
+    // registry keeps the same object (no second lowering of the limits, no copy of the clauses)
+    mutable std::mutex lowered_mutex;
+    mutable tss::PlatformLimits lowered_limits;
+    mutable std::shared_ptr<const tss::Cnf> lowered;
 };
 
 // a handle is a shared reference: the registry keeps encodings alive after the caller destroyed its own handle
@@ -27,5 +32,5 @@ struct tss_encoding {
 
 namespace tss {
 // records (encoding, limits, the CNF with_limits produced); called by tss_encoding_with_limits
-void instance_record(const std::shared_ptr<const tss_encoding_data>& d, const PlatformLimits& limits, const Cnf& cnf);
+void instance_record(const std::shared_ptr<const tss_encoding_data>& d, const PlatformLimits& limits, const std::shared_ptr<const Cnf>& cnf);
 }  // namespace tss

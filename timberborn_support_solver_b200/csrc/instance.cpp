@@ -20,7 +20,7 @@ namespace {
 struct Record {
     std::shared_ptr<const tss_encoding_data> d;
     PlatformLimits limits;
-    Cnf cnf;   // what with_limits returned (base clauses first, then the lowered limits)
+    std::shared_ptr<const Cnf> cnf;   // what with_limits returned (base clauses first, then the lowered limits)
 };
 std::mutex g_mutex;
 std::deque<Record> g_records;   // most recent first
@@ -37,7 +37,7 @@ bool same_prefix(const Cnf& base, const int32_t* lits, const uint32_t* offsets, 
 }  // namespace
 
 namespace tss {
-void instance_record(const std::shared_ptr<const tss_encoding_data>& d, const PlatformLimits& limits, const Cnf& cnf) {
+void instance_record(const std::shared_ptr<const tss_encoding_data>& d, const PlatformLimits& limits, const std::shared_ptr<const Cnf>& cnf) {
     std::lock_guard<std::mutex> lock(g_mutex);
     g_records.push_front(Record{d, limits, cnf});
     if (g_records.size() > kMaxRecords) g_records.pop_back();
@@ -71,7 +71,7 @@ int tss_instance_find(const int32_t* lits, const uint32_t* offsets, int32_t n_cl
     const Record* hit = nullptr;
     bool exact = false;
     for (const Record& r : g_records) {   // the whole CNF as recorded (most recent first) ...
-        if (r.cnf.n_vars == n_vars && r.cnf.n_clauses() == n_clauses && same_prefix(r.cnf, lits, offsets, n_clauses)) { hit = &r; exact = true; break; }
+        if (r.cnf->n_vars == n_vars && r.cnf->n_clauses() == n_clauses && same_prefix(*r.cnf, lits, offsets, n_clauses)) { hit = &r; exact = true; break; }
     }
     if (!hit)
         for (const Record& r : g_records) {   // ... else the same base clauses (limits lowered by someone else's encoder): limits of the latest record
