@@ -187,6 +187,24 @@ def repl_loop_cpu(name_defs):
 REPL_INSTANCES = [("ex1", "default-8"), ("ex3", "default-8"), ("ex2", "default-8"), ("ex2", "1x1"), ("readme", "1x1")]
 
 
+def c5_reference(steps):
+    """configs[4] on the CPU arm: a bounded sample of the batch's first terrains, generated here (ceiling iff
+    (splitmix64(seed * 0x9E3779B97F4A7C15 + (t << 20) + y * 32 + x) >> 40) < floor(0.7 * 2^24), seed 1)."""
+    def splitmix64(z):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+    n = 32 * (os.cpu_count() or 1)
+    grids = np.zeros((n, 32, 32), np.uint8)
+    with np.errstate(over="ignore"):
+        for t in range(n):
+            idx = np.arange(1024, dtype=np.uint64) + (np.uint64(t) << np.uint64(20))
+            r = splitmix64(np.uint64(1) * np.uint64(0x9E3779B97F4A7C15) + idx) >> np.uint64(40)
+            grids[t] = (r < np.uint64(11744051)).astype(np.uint8).reshape(32, 32)
+    return c5_cpu_sample(grids, 0, steps)[1]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -210,6 +228,7 @@ def run_reference(args):
                                     "from its unbounded first solve to the first layout with 15 supports; the UNSAT proof of 14 (minutes, tests/golden/proofs.json) is not included"},
         "repl_loop": repl_loop_cpu(REPL_INSTANCES),
         "validate_layouts_per_s": vrate, "validate_sample": vsample,
+        "other_configs": {"c5": c5_reference(2000)},
     }
     print(json.dumps(line), flush=True)
 
@@ -399,6 +418,29 @@ def run_c4(args):
         dist.destroy_process_group()
 
 
+def c5_cpu_sample(grids, first_terrain, steps, n_sample=None):
+    """BASELINE.json configs[4] on the host cores: the same four chains per terrain, seeds and step rule as tss_solve_batch (chains
+    4t .. 4t+3 of seed 1, the bound shared every 1024 steps) through the oracle's flat-array port, one terrain per worker thread.
+    -> (counts of the sample, dict for the JSON line)"""
+    import oracle.oracle as O
+    from concurrent.futures import ThreadPoolExecutor
+    threads = os.cpu_count() or 1
+    n_sample = min(len(grids), n_sample or 32 * threads)
+    epochs = [(min(1024, steps - d), NO_BOUND, 0) for d in range(0, steps, 1024)]
+
+    def one(i):
+        r = O.sls_flat(grids[i], 4, epochs, seed=1, chain_offset=4 * (first_terrain + i), threads=1, want_layouts=False)
+        return int(r["best"].min())
+    one(0)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        counts = list(ex.map(one, range(n_sample)))
+    sec = time.perf_counter() - t0
+    return counts, {"terrains_per_s": n_sample / sec, "cores": threads, "kind": "port",
+                    "sample": f"terrains {first_terrain}..{first_terrain + n_sample - 1} of the batch, 4 chains x {steps} steps each (oracle/sls_flat.cpp, same chains and seeds as the GPU batch), "
+                              f"one terrain per host thread, {sec:.2f} s", "mean_count": float(np.mean(counts))}
+
+
 def side_c5(eng, torch, dist, world, rank, n_total, steps):
     """BASELINE.json configs[4] at this N (strong scaling: the batch is fixed, ranks take contiguous shards, no data-path
     collective): device time of one pass with the shard's terrains resident in HBM, and the same through tss_solve_batch from
@@ -434,7 +476,11 @@ def side_c5(eng, torch, dist, world, rank, n_total, steps):
                "max_gap": int(max(int(counts[i]) - lb for i, lb in zip(sample, lbs))),
                "note": "terrains 0-31 of the batch: SLS count against max(packing bound, fractional LP bound), both certified on the GPU (tss_lower_bound, tss_lower_bound_lp)"}
     dev_ms_max, wall_ms_max = (float(x) for x in t.tolist())
-    return {"optimality_gap_sample": gap, "workload": f"batch of {n_total} synthetic 32x32 terrains (p=0.7), 1x1 supports, {steps} SLS steps per chain (BASELINE.json configs[4])",
+    cpu = None
+    if world == 1:      # the same chains on the host cores, a bounded sample: terrains/s beside the GPU's, and the counts must be the same numbers
+        cpu_counts, cpu = c5_cpu_sample(grids, lo, steps)
+        cpu["counts_identical_to_gpu"] = bool(all(int(counts[i]) == c for i, c in enumerate(cpu_counts)))
+    return {"optimality_gap_sample": gap, "cpu_baseline": cpu, "workload": f"batch of {n_total} synthetic 32x32 terrains (p=0.7), 1x1 supports, {steps} SLS steps per chain (BASELINE.json configs[4])",
             "scaling": "strong", "terrains_per_s": n_total / (dev_ms_max * 1e-3), "ms": dev_ms_max,
             "e2e": {"terrains_per_s": n_total / (wall_ms_max * 1e-3), "ms": wall_ms_max, "h2d_bytes": int(n_total * 1024), "d2h_bytes": int(n_total * 4),
                     "note": "tss_solve_batch from host u8 grids to host counts, wall clock, slowest rank"},

@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstring>
 #include <thread>
+#include <memory>
 #include <vector>
 
 namespace {
@@ -194,7 +195,8 @@ int tsso_sls_flat(const uint8_t* grid, int w, int h, int n_chains, uint32_t chai
                   int* out_k, int* out_best, uint32_t* out_step, uint64_t* out_scored, uint64_t* out_steps, uint64_t* out_flips, double* out_seconds,
                   double* out_epoch_seconds, uint64_t* out_epoch_flips) {
     if (w > 32 || h > 32 || n_chains <= 0) return -1;
-    static Terrain T;   // (one at a time: test / bench helper)
+    std::unique_ptr<Terrain> terrain(new Terrain());   // (60 KB of tables: on the heap, one per call, so concurrent calls do not share them)
+    Terrain& T = *terrain;
     T.build(grid, w, h);
     std::vector<Chain> chains((size_t)n_chains);
     for (int i = 0; i < n_chains; i++) {

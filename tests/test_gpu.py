@@ -821,6 +821,11 @@ def test_solve_batch_terrains(eng):
         unc, cnt, _ = O.validate_sites_batch(grids[t], sites[t][None])
         assert unc[0] == 0 and cnt[0] == counts[t]
         assert counts[t] >= -(-int(grids[t].sum()) // 25)
+    # the batch is the step rule of the spec, terrain by terrain: chains 4t .. 4t+3 of the seed, the bound shared every 1024 steps —
+    # the oracle's flat-array CPU port (the bench's CPU arm for configs[4]) run that way reports the same count for every terrain
+    for t in range(0, n, 5):
+        r = O.sls_flat(grids[t], 4, [(1024, 1 << 20, 0), (1024, 1 << 20, 0), (952, 1 << 20, 0)], seed=1, chain_offset=4 * t, want_layouts=False)
+        assert int(r["best"].min()) == counts[t], t
     small = np.stack([synth_terrain(8, 8, seed=3, t=t) for t in range(12)])
     c2 = eng.solve_batch(small, seed=1, steps=2000)
     for t in range(12):
