@@ -365,6 +365,61 @@ def sls_flat(grid, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, share
                 epoch_seconds=ep_sec, epoch_flips=ep_flips)
 
 
+def lns_model(grid, seeds, phases, phase_steps, seed=0, chain_offset=0, noise_pct=20):
+    """Scalar replay of the window decomposition for grids larger than 32x32 (timberborn_support_solver_b200/csrc/lns.cu): the
+    layout starts as "a support under every ceiling tile"; phase p tiles the grid with 32x32 windows at offset OFF[p & 3], freezes
+    the supports outside the windows' 26x26 cores, and in every window `seeds` chains of the WINDOW-mode step rule look for a
+    complete window layout with fewer core supports; the best chain (lowest index on ties) rewrites the core.
+    -> list of (layout uint8[h, w], count) after every phase."""
+    C_ = _grid(grid).astype(np.uint8)
+    h, w = C_.shape
+    S = C_.copy()
+    CORE_LO, CORE_HI = 3, 29
+    OFF = [(0, 0), (-16, -16), (0, -16), (-16, 0)]
+    out = []
+    L = lib()
+    for phase in range(phases):
+        ox, oy = OFF[phase & 3]
+        corex = np.array([CORE_LO <= ((x - ox) & 31) < CORE_HI for x in range(w)])
+        corey = np.array([CORE_LO <= ((y - oy) & 31) < CORE_HI for y in range(h)])
+        core = np.outer(corey, corex)
+        F = S & ~core & C_                                   # frozen supports (under ceiling: only those support anything)
+        cov = F.copy()
+        for _ in range(3):                                   # exact geodesic cover of the frozen supports
+            nb = cov.copy()
+            nb[:, 1:] |= cov[:, :-1]; nb[:, :-1] |= cov[:, 1:]; nb[1:, :] |= cov[:-1, :]; nb[:-1, :] |= cov[1:, :]
+            cov = nb & C_
+        nwx, nwy = (w - ox + 31) // 32, (h - oy + 31) // 32
+        newS = S.copy()
+        for win in range(nwx * nwy):
+            gx0, gy0 = ox + 32 * (win % nwx), oy + 32 * (win // nwx)
+
+            def cut(X):
+                W_ = np.zeros((32, 32), np.uint8)
+                x0, x1, y0, y1 = max(gx0, 0), min(gx0 + 32, w), max(gy0, 0), min(gy0 + 32, h)
+                if x1 > x0 and y1 > y0:
+                    W_[y0 - gy0:y1 - gy0, x0 - gx0:x1 - gx0] = X[y0:y1, x0:x1]
+                return W_
+            c, s_, f = cut(C_), cut(S), cut(cov)
+            corew = np.zeros((32, 32), np.uint8)
+            corew[CORE_LO:CORE_HI, CORE_LO:CORE_HI] = 1
+            score = (s_ & corew & c).astype(np.uint8)
+            need = (c & (1 - f)).astype(np.uint8)
+            bestS = np.zeros((seeds, 32, 32), np.uint8)
+            best, k = np.zeros(seeds, np.int32), np.zeros(seeds, np.int32)
+            L.tsso_sls_window_model(_p(np.ascontiguousarray(c), C.c_uint8), _p(np.ascontiguousarray(need), C.c_uint8), CORE_LO, CORE_HI, seeds,
+                                    C.c_uint32(chain_offset + win * seeds), C.c_uint64(seed), noise_pct, C.c_longlong(phase_steps),
+                                    _p(np.ascontiguousarray(score), C.c_uint8), C.c_uint32(((phase + 1) << 20) & 0xffffffff), _p(bestS, C.c_uint8), _p(best), _p(k))
+            winner = int(np.argmin(best))                    # lowest chain on ties
+            rows = bestS[winner] & corew
+            x0, x1, y0, y1 = max(gx0 + CORE_LO, 0), min(gx0 + CORE_HI, w), max(gy0 + CORE_LO, 0), min(gy0 + CORE_HI, h)
+            if x1 > x0 and y1 > y0:
+                newS[y0:y1, x0:x1] = rows[y0 - gy0:y1 - gy0, x0 - gx0:x1 - gx0]
+        S = newS
+        out.append((S.copy(), int(S.sum())))
+    return out
+
+
 def slsm_model(grid, key_dims, costs, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, share_bound=True):
     """Replays the placement search (platform sets beyond {1x1}) on the CPU.  key_dims: [(w, h)] effective dims per key in
     the engine's key order, costs: objective cost per key, epochs: [(steps, bound, target)].

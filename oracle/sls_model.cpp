@@ -34,6 +34,12 @@ struct Model {
     int w, h;
     std::vector<uint8_t> ceil;               // [32*32], index y*32+x
     std::vector<std::vector<int>> reach;     // per site: tiles within geodesic distance <= 3 through ceiling
+    // WINDOW mode (window decomposition of grids larger than 32x32, csrc/lns.cu): the tiles that still need cover (ceiling not
+    // covered by the frozen supports outside the window's movable core) and the core [core_lo, core_hi)^2 new supports must lie in.
+    // Outside WINDOW mode: need = ceil, core = the whole window.
+    std::vector<uint8_t> need;
+    int core_lo = 0, core_hi = 32;
+    bool window = false;
 
     void build(const uint8_t* grid, int w_, int h_) {
         w = w_; h = h_;
@@ -57,6 +63,7 @@ struct Model {
             }
             for (int t = 0; t < 1024; t++) if (sup[t]) reach[s].push_back(t);
         }
+        need = ceil;
     }
 };
 
@@ -82,9 +89,9 @@ struct Runner {
     int tenure, ten = 1;  // chain tenure; effective tenure of the current step (fixed at the top of the step)
     Runner(const Model& m, Chain& ch, uint32_t b, int t) : M(m), c(ch), base(b), tenure(t) {}
 
-    bool uncovered(int t) const { return M.ceil[t] && c.cnt[t] == 0; }
-    int loss(int u) const { int n = 0; for (int t : M.reach[u]) n += c.cnt[t] == 1; return n; }
-    int gain(int v) const { int n = 0; for (int t : M.reach[v]) n += c.cnt[t] == 0; return n; }
+    bool uncovered(int t) const { return M.need[t] && c.cnt[t] == 0; }
+    int loss(int u) const { int n = 0; for (int t : M.reach[u]) n += M.need[t] && c.cnt[t] == 1; return n; }   // (tiles the frozen supports cover are no loss)
+    int gain(int v) const { int n = 0; for (int t : M.reach[v]) n += M.need[t] && c.cnt[t] == 0; return n; }
 
     int remove_min_loss(bool use_tabu, uint32_t hs) {
         uint32_t best_key = 0xffffffffu;
@@ -153,9 +160,12 @@ struct Runner {
                     int cx = x + dx, cy = y + dy, ln = lane++;
                     if (cx < 0 || cy < 0 || cx >= 32 || cy >= 32) continue;
                     int v = cy * 32 + cx;
+                    if (M.window && (cx < M.core_lo || cx >= M.core_hi || cy < M.core_lo || cy >= M.core_hi)) continue;   // only core sites may receive supports
                     if (std::find(M.reach[t].begin(), M.reach[t].end(), v) != M.reach[t].end()) cand.push_back({v, ln});
                 }
-            int nc = (int)cand.size(), v = cand[0].first;
+            int nc = (int)cand.size();
+            if (M.window && nc == 0) { c.done = 1; break; }   // cannot happen from a complete start layout; never spin on it
+            int v = cand[0].first;
             const bool noise = ((hs >> 10) & 127u) < noise_q7(noise_pct);
             uint32_t mx = 0;
             bool first = true;
@@ -212,6 +222,29 @@ int tsso_sls_model(const uint8_t* grid, int w, int h, int n_chains, uint32_t cha
         std::memcpy(out_bestS + (size_t)i * 1024, chains[i].bestS.data(), 1024);
         out_k[i] = chains[i].k; out_best[i] = chains[i].best; out_step[i] = chains[i].step;
         out_scored[i] = chains[i].scored; out_steps[i] = chains[i].steps_done;
+    }
+    return 0;
+}
+
+// WINDOW mode of the same step rule (csrc/sls.cu sls_kernel<true>, driven by csrc/lns.cu): `terrain` is the window's true ceiling
+// (reach is derived from it), `need` the tiles still to be covered, supports only inside [core_lo, core_hi)^2.  All chains start
+// from the same layout init_S with best = its support count and step = init_step (lns.cu extract_windows_kernel) and run ONE
+// epoch of `steps` steps without a bound or target.  Outputs per chain: bestS u8[1024], best, k.
+int tsso_sls_window_model(const uint8_t* terrain, const uint8_t* need, int core_lo, int core_hi, int n_chains, uint32_t chain_offset, uint64_t seed,
+                          int noise_pct, long long steps, const uint8_t* init_S, uint32_t init_step, uint8_t* out_bestS, int* out_best, int* out_k) {
+    Model M;
+    M.build(terrain, 32, 32);
+    M.need.assign(need, need + 1024);
+    M.core_lo = core_lo; M.core_hi = core_hi; M.window = true;
+    for (int i = 0; i < n_chains; i++) {
+        Chain c;
+        c.S.assign(init_S, init_S + 1024); c.bestS = c.S; c.cnt.assign(1024, 0);
+        c.k = (int)std::count(c.S.begin(), c.S.end(), (uint8_t)1);
+        c.best = c.k;
+        c.step = init_step;
+        Runner(M, c, chain_base(seed, chain_offset + (uint32_t)i), tenure_of(chain_offset + (uint32_t)i)).run(steps, NO_BOUND, 0, noise_pct);
+        std::memcpy(out_bestS + (size_t)i * 1024, c.bestS.data(), 1024);
+        out_best[i] = c.best; out_k[i] = c.k;
     }
     return 0;
 }

@@ -773,6 +773,25 @@ def test_sls_large_grids_window_decomposition(eng, w, h):
     s2.close()
 
 
+@pytest.mark.parametrize("w,h,seeds", [(48, 40, 8), (64, 64, 4), (70, 33, 8), (33, 90, 4)])
+def test_window_decomposition_bit_exact_vs_model(eng, w, h, seeds):
+    """csrc/lns.cu against its scalar replay (oracle.lns_model: frozen supports, their geodesic cover, window extraction, the
+    WINDOW mode of the step rule — need mask, core-only additions — per-window winner, core write-back): the GLOBAL layout is
+    the same set of supports after every phase, all four window offsets included."""
+    grid = synth_terrain(w, h, seed=2, t=1)
+    want = O.lns_model(grid, seeds, 5, 1200, seed=3)
+    s = eng.search(T.WorldGrid(grid), seed=3, n_chains=seeds)
+    for phase, (S, count) in enumerate(want):
+        s.run(1200, 0)
+        assert s.best_count() == count, phase
+        lay = s.best_layout()
+        got = np.zeros((h, w), np.uint8)
+        for p in lay.platforms().values():
+            got[p.y, p.x] = 1
+        assert np.array_equal(got, S), phase
+    s.close()
+
+
 def test_sls_large_grid_reaches_sum_of_component_optima(eng, fixtures):
     """Four copies of ex3 (optimum 4 each, proven) separated by empty space on a 64x40 grid: optimum 16."""
     g = np.zeros((40, 64), np.uint8)

@@ -445,3 +445,17 @@ def test_propagate_csr_equals_the_handle_based_propagation(fixtures):
     offs = np.array([0, 1, 3, 5, 7], np.uint32)
     w, c, r = O.propagate_csr(lits, offs, 3, np.full(4, 2, np.uint8))
     assert list(w[1:]) == [1, 1, 0] and c == 2 and r == 3
+
+
+def test_lns_model_keeps_the_layout_complete():
+    """oracle.lns_model (the scalar replay the GPU window decomposition is compared with): the global layout is complete after
+    every phase (validate), counts never increase, and the run is deterministic."""
+    grid = synth_terrain(48, 40, seed=2, t=1)
+    a = O.lns_model(grid, 4, 4, 600, seed=3)
+    b = O.lns_model(grid, 4, 4, 600, seed=3)
+    counts = [c for _, c in a]
+    assert counts == [c for _, c in b] and all(np.array_equal(x[0], y[0]) for x, y in zip(a, b))
+    assert all(n2 <= n1 for n1, n2 in zip(counts, counts[1:])) and counts[-1] < int(grid.sum()) // 4
+    for S, c in a:
+        unc, cnt, _ = O.validate_sites_batch(grid, S[None])
+        assert unc[0] == 0 and cnt[0] == c
