@@ -37,6 +37,7 @@ METRIC = "candidate layouts evaluated/sec"
 UNIT = "layouts/s"
 WORKLOAD = "rect 16x16 ceiling, 1x1 supports, find minimum support count (BASELINE.json configs[1])"
 NO_BOUND = 1 << 20
+C4_CHAINS_PER_WINDOW = 16   # configs[3] on both arms (the engine's default for 256x256: more chains per window only slow the steps, profiles/r2_c4_tradeoff.log)
 # algorithmic integer work of one flip = one reach-window derivation (7 words x 3 rounds x 5 ops = 105 ops)
 # + |R(s)| compare/adds on the cover counters; |R| is measured on the terrain (mean_reach)
 A_FLIP_SURVEY = 105
@@ -187,22 +188,39 @@ def repl_loop_cpu(name_defs):
 REPL_INSTANCES = [("ex1", "default-8"), ("ex3", "default-8"), ("ex2", "default-8"), ("ex2", "1x1"), ("readme", "1x1")]
 
 
-def c5_reference(steps):
-    """configs[4] on the CPU arm: a bounded sample of the batch's first terrains, generated here (ceiling iff
-    (splitmix64(seed * 0x9E3779B97F4A7C15 + (t << 20) + y * 32 + x) >> 40) < floor(0.7 * 2^24), seed 1)."""
-    def splitmix64(z):
+def synthetic_terrain(w, h, t=0, seed=1):
+    """ceiling iff (splitmix64(seed * 0x9E3779B97F4A7C15 + (t << 20) + y * w + x) >> 40) < floor(0.7 * 2^24) — the
+    generator of configs[3] / configs[4], restated here so that the CPU arm needs nothing of the product."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + np.arange(w * h, dtype=np.uint64) + (np.uint64(t) << np.uint64(20))
         z = z + np.uint64(0x9E3779B97F4A7C15)
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        return z ^ (z >> np.uint64(31))
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(40)) < np.uint64(11744051)).astype(np.uint8).reshape(h, w)
+
+
+def c5_reference(steps):
+    """configs[4] on the CPU arm: a bounded sample of the batch's first terrains."""
     n = 32 * (os.cpu_count() or 1)
-    grids = np.zeros((n, 32, 32), np.uint8)
-    with np.errstate(over="ignore"):
-        for t in range(n):
-            idx = np.arange(1024, dtype=np.uint64) + (np.uint64(t) << np.uint64(20))
-            r = splitmix64(np.uint64(1) * np.uint64(0x9E3779B97F4A7C15) + idx) >> np.uint64(40)
-            grids[t] = (r < np.uint64(11744051)).astype(np.uint8).reshape(32, 32)
+    grids = np.stack([synthetic_terrain(32, 32, t) for t in range(n)])
     return c5_cpu_sample(grids, 0, steps)[1]
+
+
+def c4_cpu_sample(grid, chains_per_window, phase_steps, phases=2):
+    """configs[3] on the host cores: the window decomposition's scalar replay with the chains through the flat-array port
+    (oracle.lns_model(flat=True): same windows, chains, seeds and step rule as csrc/lns.cu), one window per worker thread, for the
+    first `phases` phases from the all-supports start layout.  -> (counts after every phase, dict for the JSON line)"""
+    import oracle.oracle as O
+    threads = os.cpu_count() or 1
+    st = {}
+    t0 = time.perf_counter()
+    res = O.lns_model(grid, chains_per_window, phases, phase_steps, seed=1, flat=True, threads=threads, stats=st)
+    wall = time.perf_counter() - t0
+    counts = [c for _, c in res]
+    return counts, {"flips_per_s": st["flips"] / st["seconds"], "cores": threads, "kind": "port", "counts": counts, "ms_per_phase": wall * 1e3 / phases,
+                    "sample": f"the first {phases} phases x {phase_steps} steps of the 256x256 search from the all-supports layout, {chains_per_window} chains per window "
+                              f"(oracle.lns_model + oracle/sls_flat.cpp, same windows / chains / seeds as the GPU arm), one window per host thread, {wall:.1f} s"}
 
 
 def run_reference(args):
@@ -228,7 +246,7 @@ def run_reference(args):
                                     "from its unbounded first solve to the first layout with 15 supports; the UNSAT proof of 14 (minutes, tests/golden/proofs.json) is not included"},
         "repl_loop": repl_loop_cpu(REPL_INSTANCES),
         "validate_layouts_per_s": vrate, "validate_sample": vsample,
-        "other_configs": {"c5": c5_reference(2000)},
+        "other_configs": {"c5": c5_reference(2000), "c4": c4_cpu_sample(synthetic_terrain(256, 256), C4_CHAINS_PER_WINDOW, args.phase_steps)[1]},
     }
     print(json.dumps(line), flush=True)
 
@@ -494,7 +512,7 @@ def side_c4(eng, torch, dist, world, rank, phases, phase_steps):
     g = T.WorldGrid.synthetic(256, 256, 1, 0)
     # diversification by rank, not just other seeds: every rank searches with its own noise level (rank 0: the default 20 %), and
     # the per-window combination keeps, window by window, whatever worked best
-    s = eng.search(g, seed=1, chain_offset=rank * 1000000, noise_pct=C4_NOISE[rank % len(C4_NOISE)])
+    s = eng.search(g, seed=1, n_chains=C4_CHAINS_PER_WINDOW, chain_offset=rank * 1000000, noise_pct=C4_NOISE[rank % len(C4_NOISE)])
     s.run(phase_steps, 0)                  # warm-up phase (allocations, first descent from the all-supports layout)
     s.best_count()
     f0 = eng.stats()
@@ -522,12 +540,23 @@ def side_c4(eng, torch, dist, world, rank, phases, phase_steps):
         dist.all_reduce(cmin, op=dist.ReduceOp.MIN)
     n_chains = s.n_chains
     s.close()
+    cpu = None
+    if world == 1:   # the same first two phases on the host cores (bounded sample): flips/s beside the GPU's, and the counts must be the same numbers
+        per_window = n_chains // 81
+        s2 = eng.search(g, seed=1, n_chains=per_window)
+        gpu_counts = []
+        for _ in range(2):
+            s2.run(phase_steps, 0)
+            gpu_counts.append(int(s2.best_count()))
+        s2.close()
+        cpu_counts, cpu = c4_cpu_sample(g.data, per_window, phase_steps)
+        cpu["counts_identical_to_gpu"] = bool(cpu_counts == gpu_counts)
     if rank != 0:
         return None
     ms = float(t.item())
     return {"workload": "synthetic 256x256 random ceiling (p=0.7), 1x1 supports, window-decomposed SLS portfolio (BASELINE.json configs[3])",
             "scaling": "weak (own seeds and noise level per rank; per-window best of all ranks adopted after every phase)", "best_count": int(cmin.item()),
-            "ceiling_tiles": int(g.data.sum()), "certified_lower_bound": lower, "lower_bound_ms": lower_ms,
+            "ceiling_tiles": int(g.data.sum()), "certified_lower_bound": lower, "lower_bound_ms": lower_ms, "cpu_baseline": cpu,
             "trivial_lower_bound": int(-(-int(g.data.sum()) // 25)), "phases": phases + 1, "phase_steps": phase_steps,
             "ms": ms, "flips_per_s": float(acc[0].item()) / (ms * 1e-3), "neighbour_scores_per_s": float(acc[1].item()) / (ms * 1e-3), "chains_per_gpu": n_chains}
 

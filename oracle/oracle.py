@@ -365,11 +365,13 @@ def sls_flat(grid, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, share
                 epoch_seconds=ep_sec, epoch_flips=ep_flips)
 
 
-def lns_model(grid, seeds, phases, phase_steps, seed=0, chain_offset=0, noise_pct=20):
+def lns_model(grid, seeds, phases, phase_steps, seed=0, chain_offset=0, noise_pct=20, flat=False, threads=1, stats=None):
     """Scalar replay of the window decomposition for grids larger than 32x32 (timberborn_support_solver_b200/csrc/lns.cu): the
     layout starts as "a support under every ceiling tile"; phase p tiles the grid with 32x32 windows at offset OFF[p & 3], freezes
     the supports outside the windows' 26x26 cores, and in every window `seeds` chains of the WINDOW-mode step rule look for a
     complete window layout with fewer core supports; the best chain (lowest index on ties) rewrites the core.
+    flat: the windows' chains through the flat-array port (oracle/sls_flat.cpp, the fast CPU implementation: same results), one
+    window per worker thread; stats (a dict) then receives the flips and the seconds spent in the chains.
     -> list of (layout uint8[h, w], count) after every phase."""
     C_ = _grid(grid).astype(np.uint8)
     h, w = C_.shape
@@ -391,7 +393,8 @@ def lns_model(grid, seeds, phases, phase_steps, seed=0, chain_offset=0, noise_pc
             cov = nb & C_
         nwx, nwy = (w - ox + 31) // 32, (h - oy + 31) // 32
         newS = S.copy()
-        for win in range(nwx * nwy):
+
+        def one(win):
             gx0, gy0 = ox + 32 * (win % nwx), oy + 32 * (win // nwx)
 
             def cut(X):
@@ -403,15 +406,33 @@ def lns_model(grid, seeds, phases, phase_steps, seed=0, chain_offset=0, noise_pc
             c, s_, f = cut(C_), cut(S), cut(cov)
             corew = np.zeros((32, 32), np.uint8)
             corew[CORE_LO:CORE_HI, CORE_LO:CORE_HI] = 1
-            score = (s_ & corew & c).astype(np.uint8)
-            need = (c & (1 - f)).astype(np.uint8)
+            score = np.ascontiguousarray((s_ & corew & c).astype(np.uint8))
+            need = np.ascontiguousarray((c & (1 - f)).astype(np.uint8))
+            c = np.ascontiguousarray(c)
             bestS = np.zeros((seeds, 32, 32), np.uint8)
             best, k = np.zeros(seeds, np.int32), np.zeros(seeds, np.int32)
-            L.tsso_sls_window_model(_p(np.ascontiguousarray(c), C.c_uint8), _p(np.ascontiguousarray(need), C.c_uint8), CORE_LO, CORE_HI, seeds,
-                                    C.c_uint32(chain_offset + win * seeds), C.c_uint64(seed), noise_pct, C.c_longlong(phase_steps),
-                                    _p(np.ascontiguousarray(score), C.c_uint8), C.c_uint32(((phase + 1) << 20) & 0xffffffff), _p(bestS, C.c_uint8), _p(best), _p(k))
+            flips = np.zeros(seeds, np.uint64)
+            args = (_p(c, C.c_uint8), _p(need, C.c_uint8), CORE_LO, CORE_HI, seeds, C.c_uint32(chain_offset + win * seeds), C.c_uint64(seed), noise_pct,
+                    C.c_longlong(phase_steps), _p(score, C.c_uint8), C.c_uint32(((phase + 1) << 20) & 0xffffffff), _p(bestS, C.c_uint8), _p(best), _p(k))
+            if flat:
+                L.tsso_sls_window_flat(*args, _p(flips, C.c_uint64))
+            else:
+                L.tsso_sls_window_model(*args)
             winner = int(np.argmin(best))                    # lowest chain on ties
-            rows = bestS[winner] & corew
+            return gx0, gy0, bestS[winner] & corew, int(flips.sum())
+
+        import time as _time
+        t0 = _time.perf_counter()
+        if flat and threads > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(threads) as ex:
+                results = list(ex.map(one, range(nwx * nwy)))
+        else:
+            results = [one(win) for win in range(nwx * nwy)]
+        if stats is not None:
+            stats["seconds"] = stats.get("seconds", 0.0) + _time.perf_counter() - t0
+            stats["flips"] = stats.get("flips", 0) + sum(r[3] for r in results)
+        for gx0, gy0, rows, _ in results:                    # cores of different windows never overlap: the order does not matter
             x0, x1, y0, y1 = max(gx0 + CORE_LO, 0), min(gx0 + CORE_HI, w), max(gy0 + CORE_LO, 0), min(gy0 + CORE_HI, h)
             if x1 > x0 and y1 > y0:
                 newS[y0:y1, x0:x1] = rows[y0 - gy0:y1 - gy0, x0 - gx0:x1 - gx0]

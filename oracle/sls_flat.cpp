@@ -45,6 +45,10 @@ struct Terrain {
     uint16_t reach[1024][25];   // tiles within geodesic distance <= 3 through ceiling, row-major
     uint8_t n_reach[1024];
     uint64_t window[1024];      // the same set as a 7x7 mask around the site: bit (dy+3)*7 + dx+3
+    // WINDOW mode (csrc/lns.cu, see sls_model.cpp): tiles that still need cover, and the core new supports must lie in
+    uint8_t need[1024];
+    int core_lo = 0, core_hi = 32;
+    bool win_mode = false;
 
     void build(const uint8_t* grid, int w, int h) {
         std::memset(ceil, 0, sizeof ceil);
@@ -71,6 +75,7 @@ struct Terrain {
             for (int j = 0; j < 7; j++) for (int i = 0; i < 7; i++)
                 if (cur[j][i]) { reach[s][n_reach[s]++] = (uint16_t)((sy + j - 3) * 32 + sx + i - 3); window[s] |= 1ull << (j * 7 + i); }
         }
+        std::memcpy(need, ceil, sizeof need);
     }
 };
 
@@ -95,11 +100,15 @@ struct Runner {
         for (int i = 0; i < T.n_reach[s]; i++) {
             const int t = T.reach[s][i];
             c.cnt[t] = (uint8_t)(c.cnt[t] + d);
-            if (c.cnt[t] == 0) c.U[t >> 5] |= 1u << (t & 31); else c.U[t >> 5] &= ~(1u << (t & 31));
+            if (c.cnt[t] == 0 && T.need[t]) c.U[t >> 5] |= 1u << (t & 31); else c.U[t >> 5] &= ~(1u << (t & 31));
         }
         c.flips++;
     }
-    inline int count_eq(int s, uint8_t value) const { int n = 0; for (int i = 0; i < T.n_reach[s]; i++) n += c.cnt[T.reach[s][i]] == value; return n; }
+    inline int count_eq(int s, uint8_t value) const {   // (tiles the frozen supports cover are neither a gain nor a loss; need = ceil outside WINDOW mode)
+        int n = 0;
+        for (int i = 0; i < T.n_reach[s]; i++) { const int t = T.reach[s][i]; n += (c.cnt[t] == value) & T.need[t]; }
+        return n;
+    }
 
     void remove_min_loss(bool use_tabu, uint32_t hs) {
         uint32_t best_key = 0xffffffffu;
@@ -125,7 +134,7 @@ struct Runner {
         for (int t = 0; t < 1024; t++) if (c.S[t]) c.sites[c.k++] = (uint16_t)t;
         std::memset(c.cnt, 0, sizeof c.cnt);
         for (int i = 0; i < c.k; i++) for (int j = 0; j < T.n_reach[c.sites[i]]; j++) c.cnt[T.reach[c.sites[i]][j]]++;
-        for (int y = 0; y < 32; y++) { c.U[y] = 0; for (int x = 0; x < 32; x++) if (T.ceil[y * 32 + x] && !c.cnt[y * 32 + x]) c.U[y] |= 1u << x; }
+        for (int y = 0; y < 32; y++) { c.U[y] = 0; for (int x = 0; x < 32; x++) if (T.need[y * 32 + x] && !c.cnt[y * 32 + x]) c.U[y] |= 1u << x; }
         const uint16_t reset = stamp_reset(c.step);
         for (int t = 0; t < 1024; t++) c.stamp[t] = reset;
         const uint32_t nq7 = noise_q7(noise_pct);
@@ -164,6 +173,7 @@ struct Runner {
                     if (std::abs(dx) + std::abs(dy) > 3) continue;
                     const int ln = lane++;
                     if (!((wt >> ((dy + 3) * 7 + dx + 3)) & 1ull)) continue;
+                    if (T.win_mode && (x + dx < T.core_lo || x + dx >= T.core_hi || y + dy < T.core_lo || y + dy >= T.core_hi)) continue;
                     const int cv = (y + dy) * 32 + x + dx;
                     nc++;
                     const uint32_t tie = tie_add(hs, (uint32_t)ln);
@@ -172,6 +182,7 @@ struct Runner {
                     else key = (is_tabu(c.step, c.stamp[cv], ten) ? 0u : TABU_BIT) | ((uint32_t)(count_eq(cv, 0) + 1) << 16) | tie;
                     if (v < 0 || key > mx) { mx = key; v = cv; }
                 }
+            if (T.win_mode && nc == 0) { c.done = 1; break; }
             if (!noise) c.scored += (uint64_t)nc;
             cover(v, +1);
             c.S[v] = 1;
@@ -243,6 +254,33 @@ int tsso_sls_flat(const uint8_t* grid, int w, int h, int n_chains, uint32_t chai
         if (out_flips) out_flips[i] = c.flips;
     }
     if (out_seconds) *out_seconds = seconds;
+    return 0;
+}
+
+// WINDOW mode through the flat port (same contract as tsso_sls_window_model, oracle/sls_model.cpp) plus out_flips per chain:
+// the CPU arm of configs[3] (bench.py) and a second implementation the scalar model is compared with.
+int tsso_sls_window_flat(const uint8_t* terrain, const uint8_t* need, int core_lo, int core_hi, int n_chains, uint32_t chain_offset, uint64_t seed,
+                         int noise_pct, long long steps, const uint8_t* init_S, uint32_t init_step, uint8_t* out_bestS, int* out_best, int* out_k,
+                         uint64_t* out_flips) {
+    std::unique_ptr<Terrain> terrain_tables(new Terrain());
+    Terrain& T = *terrain_tables;
+    T.build(terrain, 32, 32);
+    std::memcpy(T.need, need, 1024);
+    T.core_lo = core_lo; T.core_hi = core_hi; T.win_mode = true;
+    std::unique_ptr<Chain> chain(new Chain());
+    for (int i = 0; i < n_chains; i++) {
+        Chain& c = *chain;
+        c = Chain();
+        std::memcpy(c.S, init_S, 1024);
+        std::memcpy(c.bestS, init_S, 1024);
+        c.k = (int)std::count(c.S, c.S + 1024, (uint8_t)1);
+        c.best = c.k;
+        c.step = init_step;
+        Runner(T, c, chain_base(seed, chain_offset + (uint32_t)i), tenure_of(chain_offset + (uint32_t)i)).run(steps, NO_BOUND, 0, noise_pct);
+        std::memcpy(out_bestS + (size_t)i * 1024, c.bestS, 1024);
+        out_best[i] = c.best; out_k[i] = c.k;
+        if (out_flips) out_flips[i] = c.flips;
+    }
     return 0;
 }
 

@@ -154,6 +154,14 @@ int main(void) {
         int32_t nf = -1;
         CHECK(tss_cnf_check(e, c2, a2, 1, &nf, NULL) == TSS_OK && nf == 0);
         CHECK(tss_layout_from_assignment(inst, a2, nv + 1, decoded, 64, &n_dec) == TSS_OK && n_dec == 3);
+        {   /* the completion step on its own: platform and terrain-layer variables from the layout, the totalizer left open */
+            int32_t n_base = 0, conflict = 0, n_fals = -1;
+            tss_encoding_sizes(inst, &n_base, NULL, NULL, NULL);
+            CHECK(tss_layout_to_assignment(e, inst, decoded, n_dec, a2) == TSS_OK);
+            for (int v = n_base + 1; v <= nv; v++) a2[v] = 2;
+            CHECK(tss_cnf_complete(e, c2, a2, &conflict, &n_fals) == TSS_OK && conflict == -1 && n_fals == 0);
+            for (int v = 1; v <= nv; v++) CHECK(a2[v] == 0 || a2[v] == 1);
+        }
         CHECK(tss_witness_for_cnf(e, c2, inst, decoded, 2, a2) == TSS_UNKNOWN);                               /* one support short: not a model */
         {   /* the loop's next question, "at most 2 platforms" (main.rs:346): below the certified lower bound of 3 -> UNSAT, no exact solver */
             const int32_t card2[3] = {1, 1, 2};

@@ -459,3 +459,7 @@ def test_lns_model_keeps_the_layout_complete():
     for S, c in a:
         unc, cnt, _ = O.validate_sites_batch(grid, S[None])
         assert unc[0] == 0 and cnt[0] == c
+    # the flat-array port in WINDOW mode (the bench's CPU arm for configs[3]) is a second implementation of the same rule: same layouts
+    st = {}
+    f = O.lns_model(grid, 4, 4, 600, seed=3, flat=True, threads=4, stats=st)
+    assert all(np.array_equal(x[0], y[0]) for x, y in zip(a, f)) and st["flips"] > 0

@@ -647,11 +647,13 @@ int tss_search_create(tss_engine* e, const uint8_t* grid, int32_t w, int32_t h, 
     s->noise = (params && params->noise_pct >= 0) ? params->noise_pct : sls::DEFAULT_NOISE_PCT;
     s->share = e->comm != nullptr;  // a portfolio created on an engine with a communicator shares its bound every epoch
     if (w > 32 || h > 32) {  // window decomposition: n_chains is read as chains per window (multiple of 4, default 8)
-        // default: one wave of chains — 8 CTAs of 4 warps per SM shared by the windows of a phase (a chain steps at
-        // single-warp latency, ~1.2 us per step, so chains beyond 8 per window cost no time until the device is full)
+        // default: at most 16 chains per window.  A chain steps at single-warp latency (~1.1 us per step) while the schedulers have
+        // spare issue slots; filling the device (56 per window on 256x256) halves the step rate (2.2 us per step) and buys nothing:
+        // the count is the same plateau for 4 .. 56 chains per window (profiles/r2_c4_tradeoff.log: 77 ms against 152 ms for
+        // 16 phases x 4000 steps, 4 259-4 267 against 4 258-4 268)
         const int n_win = ((w + 31) / 32 + 1) * ((h + 31) / 32 + 1);
         int fill = (e->prop.multiProcessorCount * 32 / n_win) / 4 * 4;
-        fill = fill < 8 ? 8 : (fill > 64 ? 64 : fill);
+        fill = fill < 8 ? 8 : (fill > 16 ? 16 : fill);
         int seeds = (params && params->n_chains > 0) ? ((params->n_chains + 3) / 4) * 4 : fill;
         int rc = lns_create(e, grid, w, h, seeds, s->seed, s->chain_offset, s->noise, &s->lns);
         if (rc != TSS_OK) { delete s; return rc; }
