@@ -491,7 +491,8 @@ def side_c5(eng, torch, dist, world, rank, n_total, steps):
         sample = range(0, 32)
         lbs = [max(len(eng.lower_bound(T.WorldGrid(grids[i]), seed=1)), eng.lower_bound_lp(T.WorldGrid(grids[i]))["bound"]) for i in sample]
         gap = {"terrains": len(lbs), "mean_count": float(np.mean([counts[i] for i in sample])), "mean_certified_lower_bound": float(np.mean(lbs)),
-               "max_gap": int(max(int(counts[i]) - lb for i, lb in zip(sample, lbs))),
+               "max_gap": int(max(int(counts[i]) - lb for i, lb in zip(sample, lbs))), "min_gap": int(min(int(counts[i]) - lb for i, lb in zip(sample, lbs))),
+               "proven_optimal": int(sum(1 for i, lb in zip(sample, lbs) if int(counts[i]) == lb)),
                "note": "terrains 0-31 of the batch: SLS count against max(packing bound, fractional LP bound), both certified on the GPU (tss_lower_bound, tss_lower_bound_lp)"}
     dev_ms_max, wall_ms_max = (float(x) for x in t.tolist())
     cpu = None

@@ -22,6 +22,7 @@
 // shared memory), lp_certify_kernel (integer loads).
 #include <cooperative_groups.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "engine.hpp"
@@ -343,6 +344,109 @@ lp_simplex_cluster_kernel(const double* __restrict__ T, int m, int n, const int*
     cluster.sync();                                         // nobody exits while its shared memory may still be written remotely
 }
 
+// ---- the same simplex for tableaus beyond the cluster's shared memory: the whole device, one grid barrier per pivot ------------
+// (default-8 platform sets: thousands of constraints; 1x1 supports on 24x24 .. 32x32 terrains — the GUI's default grid is 24x24,
+// crates/gui/src/app.rs: tens of MB that stay in the 126 MB L2.)  The single-CTA kernel moves all of it through ONE SM, 50-130 us
+// per pivot.  Here the constraint rows are dealt out to one CTA per SM (cooperative launch); objective row and Devex weights are
+// replicated in every CTA's shared memory exactly as in the cluster kernel, so the entering column needs no exchange; every CTA
+// publishes its ratio-test winner AND a copy of its candidate row in global memory (buffers alternate with the pivot's parity),
+// one grid barrier, then everybody picks the winner among the slots, reads that row from L2 and updates its own rows in place.
+constexpr int GRID_THREADS = 512;
+
+__global__ void __launch_bounds__(GRID_THREADS, 1)
+lp_simplex_grid_kernel(double* __restrict__ T, int m, int n, const int* __restrict__ col_site, int max_pivots, double stop_at, int* __restrict__ info,
+                       int* __restrict__ weights /* [1024] zeroed */, double scale, int* __restrict__ basis /* [m] */, int* __restrict__ nonbasis /* [n] */,
+                       double* __restrict__ cand /* [2][gridDim.x][ld] */, ArgD* __restrict__ slots /* [2][gridDim.x] */) {
+    cg::grid_group grid = cg::this_grid();
+    const int G = (int)gridDim.x, rank = (int)blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ld = n + 1;
+    const int rows_per = (m + G - 1) / G, row0 = rank * rows_per, my_rows = max(0, min(rows_per, m - row0));
+    extern __shared__ __align__(16) unsigned char dyn[];
+    double* obj = reinterpret_cast<double*>(dyn);           // [ld] objective row (replicated)
+    double* devex = obj + ld;                               // [ld] Devex reference weights (replicated)
+    double* pcol = devex + ld;                              // [rows_per] my part of the entering column
+    __shared__ ArgD red[GRID_THREADS / 32];                 // per-warp pricing candidates of the next pivot
+    __shared__ ArgD rred[GRID_THREADS / 32];                // per-warp ratio-test candidates
+    for (int j = tid; j <= n; j += blockDim.x) { obj[j] = T[(size_t)m * ld + j]; devex[j] = 1.0; }
+    if (rank == 0) {
+        for (int i = tid; i < m; i += blockDim.x) basis[i] = n + i;
+        for (int j = tid; j < n; j += blockDim.x) nonbasis[j] = j;
+    }
+    __syncthreads();
+    auto price = [&]() {
+        ArgD e{0.0, 0x7fffffff};
+        for (int j = tid; j < n; j += blockDim.x) {
+            const double d = obj[j];
+            if (d < -EPS) {
+                const double key = d * d * fast_rcp(devex[j]);
+                if (key > e.v) e = ArgD{key, j};
+            }
+        }
+        e = warp_argmax_nonneg(e);
+        if (lane == 0) red[warp] = e;
+    };
+    price();
+    __syncthreads();
+    int pivots = 0, optimal = 0;
+    for (; pivots < max_pivots; pivots++) {
+        const int par = pivots & 1;
+        const ArgD ent = warp_argmax_nonneg(red[lane & (GRID_THREADS / 32 - 1)]);
+        if (ent.i == 0x7fffffff) { optimal = 1; break; }    // (identical in every CTA: nobody is left waiting at the barrier)
+        const int q = ent.i;
+        const double fo = obj[q], wq = devex[q];
+        ArgD r{__longlong_as_double(0x7ff0000000000000ll), 0x7fffffff};
+        for (int li = tid; li < my_rows; li += blockDim.x) {   // ratio test over my rows (tableau in L2)
+            const double a = T[(size_t)(row0 + li) * ld + q];
+            pcol[li] = a;
+            if (a > EPS) r = better_min(r, ArgD{fmax(T[(size_t)(row0 + li) * ld + n] * fast_rcp(a), 0.0), row0 + li});
+        }
+        r = warp_argmin_nonneg(r);
+        if (lane == 0) rred[warp] = r;
+        __syncthreads();
+        r = warp_argmin_nonneg(rred[lane & (GRID_THREADS / 32 - 1)]);
+        if (r.i != 0x7fffffff) {                            // my candidate row, copied out before anybody may rewrite it
+            const double* mine = T + (size_t)r.i * ld;
+            double* dst = cand + ((size_t)par * G + rank) * ld;
+            for (int j = tid; j <= n; j += blockDim.x) dst[j] = mine[j];
+        }
+        if (tid == 0) slots[par * G + rank] = r;
+        grid.sync();
+        ArgD g{__longlong_as_double(0x7ff0000000000000ll), 0x7fffffff};
+        for (int c = lane; c < G; c += 32) g = better_min(g, ArgD{__ldcg(&slots[par * G + c].v), __ldcg(&slots[par * G + c].i)});   // (L2 reads: written by other SMs)
+        g = warp_argmin_nonneg(g);
+        if (g.i == 0x7fffffff) break;                       // unbounded: cannot happen, never spin on it
+        const int pr = g.i, owner = pr / rows_per;
+        const double* crow = cand + ((size_t)par * G + owner) * ld;   // the pivot row before scaling
+        const double inv = fast_rcp(__ldcg(&crow[q]));
+        for (int j = tid & (GRID_THREADS / 2 - 1); j <= n; j += GRID_THREADS / 2) {   // rank-1 update of my rows: a thread owns a column, even / odd rows
+            const double pj = j == q ? inv : __ldcg(&crow[j]) * inv;
+            for (int li = tid / (GRID_THREADS / 2); li < my_rows; li += 2) {
+                const double f = pcol[li];
+                double* cell = T + (size_t)(row0 + li) * ld + j;
+                if (row0 + li == pr) *cell = pj;
+                else if (f != 0.0) *cell = j == q ? -f * inv : *cell - f * pj;
+            }
+        }
+        for (int j = tid; j <= n; j += blockDim.x) {
+            const double pj = j == q ? inv : __ldcg(&crow[j]) * inv;
+            obj[j] = j == q ? -fo * inv : obj[j] - fo * pj;
+            if (j < n) devex[j] = j == q ? fmax(wq * inv * inv, 1.0) : fmax(devex[j], pj * pj * wq);
+        }
+        if (rank == 0 && tid == 0) { const int t = basis[pr]; basis[pr] = nonbasis[q]; nonbasis[q] = t; }
+        price();
+        __syncthreads();
+        if (stop_at > 0.0 && obj[n] >= stop_at) { pivots++; break; }
+    }
+    grid.sync();                                            // basis labels (written by CTA 0) and every row are final
+    for (int li = tid; li < my_rows; li += blockDim.x) {    // y -> integer weights: floor(y * SCALE) for my basic tiles
+        const int label = basis[row0 + li];
+        if (label >= n) continue;
+        const double y = T[(size_t)(row0 + li) * ld + n];
+        const long long k = y > 0.0 ? (long long)floor(y * scale) : 0ll;
+        weights[col_site[label]] = (int)(k > (1ll << 30) ? (1ll << 30) : k);
+    }
+    if (rank == 0 && tid == 0) { info[0] = pivots; info[1] = optimal; }
+}
+
 // y -> integer weights per site (floor(y * SCALE), never negative), zero for non-basic tiles
 __global__ void lp_weights_kernel(const double* __restrict__ T, int m, int n, const int* __restrict__ basis, const int* __restrict__ col_site,
                                   int* __restrict__ weights /* [1024] zeroed */, double scale) {
@@ -461,8 +565,25 @@ int lp_run(tss_engine* e, const uint32_t* rows32_host, int W, int H, const std::
         if (lp::CLUSTER > 8) TSS_CUDA(e, cudaFuncSetAttribute(lp::lp_simplex_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         lp::lp_simplex_cluster_kernel<<<lp::CLUSTER, lp::CL_THREADS, cl_smem, e->stream>>>(T, m, n, col_dev, pivots_cap, stop_at, info_dev, weights, scale, prof_dev);
     } else {
-        lp::lp_simplex_kernel<<<1, lp::THREADS, 0, e->stream>>>(T, m, n, basis, nonbasis, pivots_cap, stop_at, info_dev);
-        lp::lp_weights_kernel<<<(m + 255) / 256, 256, 0, e->stream>>>(T, m, n, basis, col_dev, weights, scale);
+        // beyond the cluster: one CTA per SM, cooperative launch, one grid barrier per pivot (TSS_LP_SINGLE_CTA=1: the one-CTA kernel)
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
+        const int G = std::max(1, std::min(e->prop.multiProcessorCount, (m + 3) / 4));
+        const size_t g_smem = sizeof(double) * (2 * (size_t)ld + (size_t)((m + G - 1) / G));
+        double* cand = nullptr;
+        if (coop && !(force && force[0] == '1') && g_smem <= 200 * 1024) cand = (double*)e->dev(4, sizeof(double) * 2 * (size_t)G * ld + sizeof(lp::ArgD) * 2 * (size_t)G + 64);
+        if (cand) {
+            lp::ArgD* slots = reinterpret_cast<lp::ArgD*>(cand + 2 * (size_t)G * ld);
+            int m_ = m, n_ = n, cap_ = pivots_cap;
+            double stop_ = stop_at, scale_ = scale;
+            const int* col_ = col_dev;
+            void* args[] = {&T, &m_, &n_, &col_, &cap_, &stop_, &info_dev, &weights, &scale_, &basis, &nonbasis, &cand, &slots};
+            TSS_CUDA(e, cudaFuncSetAttribute(lp::lp_simplex_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem));
+            TSS_CUDA(e, cudaLaunchCooperativeKernel((const void*)lp::lp_simplex_grid_kernel, dim3(G), dim3(lp::GRID_THREADS), args, g_smem, e->stream));
+        } else {
+            lp::lp_simplex_kernel<<<1, lp::THREADS, 0, e->stream>>>(T, m, n, basis, nonbasis, pivots_cap, stop_at, info_dev);
+            lp::lp_weights_kernel<<<(m + 255) / 256, 256, 0, e->stream>>>(T, m, n, basis, col_dev, weights, scale);
+        }
     }
     lp::lp_total_kernel<<<1, 32, 0, e->stream>>>(weights, totals_dev);
     lp::lp_certify_kernel<<<(n_place + 3) / 4, 128, 0, e->stream>>>(reach, n_place, weights, keys, totals_dev);
