@@ -1,7 +1,7 @@
 //! Raw bindings to `include/tss.h` (ABI version 103).  Every entry point cites, in the header, the reference
 //! interface it stands behind; this file only mirrors types and signatures.
 #![allow(non_camel_case_types)]
-use std::os::raw::{c_char, c_int};
+use std::os::raw::{c_char, c_int, c_void};
 
 pub const TSS_VERSION: c_int = 103;
 pub const TSS_OK: c_int = 0;
@@ -179,4 +179,38 @@ unsafe extern "C" {
     // multi-GPU portfolio: the host only ships the 128-byte NCCL id
     pub fn tss_comm_unique_id(e: *mut tss_engine, out128: *mut u8) -> c_int;
     pub fn tss_comm_init(e: *mut tss_engine, id128: *const u8, rank: i32, world: i32) -> c_int;
+
+    // ---- the rest of include/tss.h (not used by the `tss` shim; here so that the whole ABI is declared in one place)
+    pub fn tss_engine_set_stream(e: *mut tss_engine, cuda_stream: *mut c_void) -> c_int;
+    pub fn tss_device_info(e: *const tss_engine, name: *mut c_char, cap: c_int, sm_count: *mut c_int, clock_khz: *mut c_int) -> c_int;
+    pub fn tss_comm_world(e: *const tss_engine) -> c_int;
+    pub fn tss_world_parse_toml(text: *const c_char, grid: *mut u8, cap: usize, w: *mut i32, h: *mut i32, ragged: *mut i32, err: *mut c_char, err_cap: usize) -> c_int;
+    pub fn tss_world_to_toml(grid: *const u8, w: i32, h: i32, out: *mut c_char, cap: usize) -> c_int;
+    pub fn tss_world_synthetic(w: i32, h: i32, seed: u64, t: u64, density_q24: u32, grid: *mut u8) -> c_int;
+    pub fn tss_encoding_dims(enc: *const tss_encoding, out_dims: *mut tss_dims) -> c_int;
+    pub fn tss_encoding_cnf(enc: *const tss_encoding, lits: *mut i32, offsets: *mut u32) -> c_int;
+    pub fn tss_layout_trivial_optimization(grid: *const u8, w: i32, h: i32, plats: *mut tss_platform, n: i32) -> c_int;
+    pub fn tss_layout_merge_supports(grid: *const u8, w: i32, h: i32, defs: *const tss_dims, n_defs: i32, plats: *mut tss_platform, n: i32, cap: i32) -> c_int;
+    pub fn tss_layout_total_weight(plats: *const tss_platform, n: i32, weights: *const i32, n_weights: i32) -> i64;
+    pub fn tss_platform_overlaps(a: *const tss_platform, b: *const tss_platform) -> c_int;
+    pub fn tss_eval_sites(e: *mut tss_engine, grid: *const u8, w: i32, h: i32, sites: *const u8, n: i64, out_uncovered: *mut i32, out_count: *mut i32) -> c_int;
+    pub fn tss_eval_packed(e: *mut tss_engine, grid_rows: *const u32, w: i32, h: i32, layouts: *const u32, n: i64, out_uncovered: *mut i32, out_count: *mut i32) -> c_int;
+    pub fn tss_eval_compact_dev(e: *mut tss_engine, grid_dev: *const c_void, w: i32, h: i32, layouts_dev: *const c_void, n: i64, per_layout_terrain: i32, out_dev: *mut i32) -> c_int;
+    pub fn tss_compact_row_bytes(w: i32, h: i32) -> usize;
+    pub fn tss_compact_layout_bytes(w: i32, h: i32) -> usize;
+    pub fn tss_eval_platforms(e: *mut tss_engine, grid: *const u8, w: i32, h: i32, plats: *const tss_platform, offsets: *const u32, n: i64, out: *mut i32) -> c_int;
+    pub fn tss_search_global_best(s: *mut tss_search, count: *mut i32) -> c_int;
+    pub fn tss_search_n_chains(s: *const tss_search) -> c_int;
+    pub fn tss_search_read_chains(s: *mut tss_search, S: *mut u32, best_S: *mut u32, k: *mut i32, best: *mut i32, step: *mut u32, scored: *mut u64) -> c_int;
+    pub fn tss_search_read_placements(
+        s: *mut tss_search, items: *mut u16, k: *mut i32, best_items: *mut u16, best_k: *mut i32, best: *mut i32, step: *mut u32, key_dims: *mut tss_dims,
+        n_keys: *mut i32,
+    ) -> c_int;
+    pub fn tss_search_set_weights(s: *mut tss_search, weights: *const i32, n_weights: i32) -> c_int;
+    pub fn tss_sls_spec_probe(out: *mut u32);
+    pub fn tss_solve_batch(
+        e: *mut tss_engine, grids: *const u8, w: i32, h: i32, n: i64, seed: u64, steps: i64, chains_per_terrain: i32, out_counts: *mut i32,
+        out_layouts: *mut u32,
+    ) -> c_int;
+    pub fn tss_measure_peaks(e: *mut tss_engine, out: *mut f64, n_out: i32) -> c_int;
 }
