@@ -365,13 +365,15 @@ def sls_flat(grid, n_chains, epochs, seed=0, chain_offset=0, noise_pct=20, share
                 epoch_seconds=ep_sec, epoch_flips=ep_flips)
 
 
-def lns_model(grid, seeds, phases, phase_steps, seed=0, chain_offset=0, noise_pct=20, flat=False, threads=1, stats=None):
+def lns_model(grid, seeds, phases, phase_steps, seed=0, chain_offset=0, noise_pct=20, flat=False, threads=1, stats=None, ranks=None):
     """Scalar replay of the window decomposition for grids larger than 32x32 (timberborn_support_solver_b200/csrc/lns.cu): the
     layout starts as "a support under every ceiling tile"; phase p tiles the grid with 32x32 windows at offset OFF[p & 3], freezes
     the supports outside the windows' 26x26 cores, and in every window `seeds` chains of the WINDOW-mode step rule look for a
     complete window layout with fewer core supports; the best chain (lowest index on ties) rewrites the core.
     flat: the windows' chains through the flat-array port (oracle/sls_flat.cpp, the fast CPU implementation: same results), one
     window per worker thread; stats (a dict) then receives the flips and the seconds spent in the chains.
+    ranks: [(chain_offset, noise_pct), ...] — the multi-GPU portfolio (csrc/lns.cu window_keys_kernel / contribute_windows_kernel): every
+    rank searches every window with its own chains; per window the rank with the fewest core supports wins (lowest rank on ties).
     -> list of (layout uint8[h, w], count) after every phase."""
     C_ = _grid(grid).astype(np.uint8)
     h, w = C_.shape
@@ -409,17 +411,23 @@ def lns_model(grid, seeds, phases, phase_steps, seed=0, chain_offset=0, noise_pc
             score = np.ascontiguousarray((s_ & corew & c).astype(np.uint8))
             need = np.ascontiguousarray((c & (1 - f)).astype(np.uint8))
             c = np.ascontiguousarray(c)
-            bestS = np.zeros((seeds, 32, 32), np.uint8)
-            best, k = np.zeros(seeds, np.int32), np.zeros(seeds, np.int32)
-            flips = np.zeros(seeds, np.uint64)
-            args = (_p(c, C.c_uint8), _p(need, C.c_uint8), CORE_LO, CORE_HI, seeds, C.c_uint32(chain_offset + win * seeds), C.c_uint64(seed), noise_pct,
-                    C.c_longlong(phase_steps), _p(score, C.c_uint8), C.c_uint32(((phase + 1) << 20) & 0xffffffff), _p(bestS, C.c_uint8), _p(best), _p(k))
-            if flat:
-                L.tsso_sls_window_flat(*args, _p(flips, C.c_uint64))
-            else:
-                L.tsso_sls_window_model(*args)
-            winner = int(np.argmin(best))                    # lowest chain on ties
-            return gx0, gy0, bestS[winner] & corew, int(flips.sum())
+            win_key, win_rows, n_flips = None, None, 0
+            for r, (r_offset, r_noise) in enumerate(ranks or [(chain_offset, noise_pct)]):
+                bestS = np.zeros((seeds, 32, 32), np.uint8)
+                best, k = np.zeros(seeds, np.int32), np.zeros(seeds, np.int32)
+                flips = np.zeros(seeds, np.uint64)
+                args = (_p(c, C.c_uint8), _p(need, C.c_uint8), CORE_LO, CORE_HI, seeds, C.c_uint32(r_offset + win * seeds), C.c_uint64(seed), r_noise,
+                        C.c_longlong(phase_steps), _p(score, C.c_uint8), C.c_uint32(((phase + 1) << 20) & 0xffffffff), _p(bestS, C.c_uint8), _p(best), _p(k))
+                if flat:
+                    L.tsso_sls_window_flat(*args, _p(flips, C.c_uint64))
+                else:
+                    L.tsso_sls_window_model(*args)
+                winner = int(np.argmin(best))                # lowest chain on ties
+                key = int(best[winner]) * 64 + r             # fewest core supports, lowest rank on ties
+                n_flips += int(flips.sum())
+                if win_key is None or key < win_key:
+                    win_key, win_rows = key, bestS[winner] & corew
+            return gx0, gy0, win_rows, n_flips
 
         import time as _time
         t0 = _time.perf_counter()

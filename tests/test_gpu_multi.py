@@ -69,6 +69,13 @@ def test_native_nccl_portfolio_two_gpus(tmp_path):
     assert c0 == c1 and all(b <= a for a, b in zip(c0, c0[1:])) and len(lay0) == c0[-1]   # same counts on every rank, never increasing
     assert lay0 == lay1                                              # ... and the very same layout (assembled window by window from the winners)
     assert c0[-1] <= single, (c0, single)                            # two GPUs combine per window: at equal phases never worse than one
+    # ... and it is exactly what the scalar replay of the two-rank portfolio assembles (oracle.lns_model: per window the rank with the
+    # fewest core supports, lowest rank on ties), phase by phase
+    import oracle.oracle as O
+    import timberborn_support_solver_b200 as T
+    want = O.lns_model(T.WorldGrid.synthetic(96, 80, 1, 3).data, 8, 5, 1200, seed=9, flat=True, threads=4, ranks=[(0, 20), (100000, 20)])
+    assert [c for _, c in want] == c0
+    assert lay0 == sorted((int(x), int(y)) for y, x in zip(*np.nonzero(want[-1][0])))
     print("C4-shaped portfolio, 5 phases: two GPUs", c0, "one GPU", single)
     for (l0, g0), (l1, g1) in zip(h0, h1):
         assert g0 == g1                                             # every rank sees the same global bound after each epoch
