@@ -106,6 +106,17 @@ impl<S: Solve> Solve for GpuSeeded<S> {
 
     fn add_cnf(&mut self, cnf: Cnf) -> Result<()> {
         if let Some(engine) = &self.engine {
+            unsafe {
+                // (a second add_cnf on the same solver replaces the uploaded clauses; the drivers create one solver per iteration)
+                if !self.cnf.is_null() {
+                    ffi::tss_cnf_destroy(self.cnf);
+                    self.cnf = ptr::null_mut();
+                }
+                if !self.enc.is_null() {
+                    ffi::tss_encoding_destroy(self.enc);
+                    self.enc = ptr::null_mut();
+                }
+            }
             // CSR with DIMACS-signed literals: Lit(idx, negated) -> +/-(idx + 1)
             let (mut lits, mut offsets, mut n_vars) = (Vec::<i32>::new(), vec![0u32], 0i32);
             for clause in cnf.iter() {
