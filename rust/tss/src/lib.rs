@@ -150,7 +150,10 @@ impl<S: Solve> Solve for GpuSeeded<S> {
     where
         C: AsRef<rustsat::types::Cl> + ?Sized,
     {
-        self.enc = ptr::null_mut(); // clauses beyond the recorded instance: the GPU's view would be stale
+        if !self.enc.is_null() {
+            unsafe { ffi::tss_encoding_destroy(self.enc) }; // clauses beyond the recorded instance: the GPU's view would be stale
+            self.enc = ptr::null_mut();
+        }
         self.inner.add_clause_ref(clause)
     }
 
