@@ -237,7 +237,7 @@ class Encoding:
         return Encoding(h, terrain, defs)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "load", None) is not None:   # (module globals are gone at interpreter shutdown)
             _lib.load().tss_encoding_destroy(self._h)
             self._h = None
 
